@@ -1,0 +1,210 @@
+// C-ABI entry points for the fused pool, plus library bookkeeping.  See include/aecf_b200.h.
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "pool_dispatch.cuh"
+
+namespace aecf {
+
+static std::atomic<unsigned long long> g_launches{0};
+static thread_local char g_cuda_error[256] = "";
+
+void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int set_cuda_error(cudaError_t err, const char* what) {
+    std::snprintf(g_cuda_error, sizeof(g_cuda_error), "%s: %s (%s)", what, cudaGetErrorName(err),
+                  cudaGetErrorString(err));
+    return AECF_ERR_CUDA;
+}
+
+int use_device(int device) {
+    AECF_CUDA_OK(cudaSetDevice(device));
+    return AECF_OK;
+}
+
+int sm_count(int device) {
+    static std::atomic<int> cached[64];
+    if (device < 0 || device >= 64) return 148;
+    int n = cached[device].load(std::memory_order_relaxed);
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || n <= 0) n = 148;
+        cached[device].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
+
+constexpr int POOL_BWD_MAX_BLOCKS = 2048;
+
+// Sum the per-block partials in block order: d_q[D] (scaled) and d_bias_kv[2D] = [dbk | dbv].
+__global__ void pool_bwd_finalize_kernel(const float* __restrict__ partials, int blocks, int D, float scale,
+                                         int q_shared, float* __restrict__ d_q, float* __restrict__ d_bias_kv) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3 * D) return;
+    float s = 0.f;
+    for (int b = 0; b < blocks; ++b) s += partials[static_cast<size_t>(b) * 3 * D + i];
+    const int which = i / D, d = i - which * D;
+    if (which == 0) { if (q_shared && d_q) d_q[d] = s * scale; }
+    else if (d_bias_kv) d_bias_kv[(which == 1 ? D : 0) + d] = s;
+}
+
+
+
+struct PoolPlan {
+    PoolParams p;
+    int M, J;
+    bool drop, bf16;
+};
+
+// Validate a descriptor and derive the lane/head geometry (pool_core.cuh).
+static int make_plan(const aecf_pool_desc* d, PoolPlan* plan) {
+    if (d == nullptr) return AECF_ERR_INVALID;
+    if (d->batch < 0 || d->embed_dim <= 0 || d->num_heads <= 0 || d->num_tokens <= 0) return AECF_ERR_INVALID;
+    if (d->embed_dim % d->num_heads != 0) return AECF_ERR_INVALID;
+    if (d->dtype != AECF_F32 && d->dtype != AECF_BF16) return AECF_ERR_INVALID;
+    if (d->offset >> 32) return AECF_ERR_INVALID;
+    if (!(d->dropout_p >= 0.f && d->dropout_p <= 1.f)) return AECF_ERR_INVALID;
+    if (d->masking < 0 || d->masking > 2) return AECF_ERR_INVALID;
+    if (d->num_tokens > AECF_MAX_TOKENS) return AECF_ERR_UNSUPPORTED;
+    const int V = d->dtype == AECF_BF16 ? 8 : 4;
+    const int D = d->embed_dim, H = d->num_heads, hd = D / H;
+    if (hd % V != 0) return AECF_ERR_UNSUPPORTED;
+    const int G = hd / V;
+    if (!is_pow2(G)) return AECF_ERR_UNSUPPORTED;
+    const int NC = D / V;
+    // J chunk columns per lane: enough to hold a whole head in one warp (R <= J), and two columns
+    // (512 contiguous bytes x 2 per token) whenever the row is long enough.
+    const int R = G < 32 ? 1 : G / 32;
+    int J = NC > 32 ? 2 : 1;
+    if (J < R) J = R;
+    if (J > 4) return AECF_ERR_UNSUPPORTED;          // head_dim > 128 * V elements
+    const int WPS = (NC + 32 * J - 1) / (32 * J);
+    if (WPS > POOL_WARPS || !is_pow2(WPS)) return AECF_ERR_UNSUPPORTED;
+
+    PoolParams& p = plan->p;
+    std::memset(&p, 0, sizeof(p));
+    p.B = d->batch; p.D = D; p.H = H; p.NC = NC; p.G = G; p.logG = ilog2(G);
+    p.LG = G < 32 ? G : 32; p.R = R; p.WPS = WPS; p.SPC = POOL_WARPS / WPS;
+    p.scale = static_cast<float>(std::sqrt(1.0 / static_cast<double>(hd)));   // math.sqrt(1.0 / float(E)), functional.py:6632
+    p.p_drop = d->dropout_p;
+    p.one_minus_p = static_cast<float>(1.0 - static_cast<double>(d->dropout_p));
+    p.base_mask_prob = d->base_mask_prob;
+    p.log_m = static_cast<float>(std::log(static_cast<double>(d->num_tokens)));   // math.log(seq_len), AECFLayer.py:127,191
+    p.training = d->training; p.masking = d->masking; p.min_active = d->min_active;
+    p.q_shared = d->q_is_shared;
+    p.rng.k0 = static_cast<uint32_t>(d->seed); p.rng.k1 = static_cast<uint32_t>(d->seed >> 32);
+    p.rng.offset = static_cast<uint32_t>(d->offset); p.rng.row0 = d->row0;
+    p.bias_sb = d->bias_stride_b; p.bias_sh = d->bias_stride_h;
+    if (d->kv_stride_b == 0 && d->kv_stride_m == 0) {
+        p.kv_sm = 2LL * D; p.kv_sb = p.kv_sm * d->num_tokens;
+    } else {
+        if (d->kv_stride_b < 2LL * D || d->kv_stride_m < 2LL * D) return AECF_ERR_INVALID;
+        if ((d->kv_stride_b * (16 / V)) % 16 != 0 || (d->kv_stride_m * (16 / V)) % 16 != 0) return AECF_ERR_ALIGNMENT;
+        p.kv_sb = d->kv_stride_b; p.kv_sm = d->kv_stride_m;
+    }
+    plan->M = d->num_tokens; plan->J = J;
+    plan->drop = d->training && d->dropout_p > 0.f;
+    plan->bf16 = d->dtype == AECF_BF16;
+    return AECF_OK;
+}
+
+}  // namespace aecf
+
+using namespace aecf;
+
+extern "C" {
+
+int aecf_abi_version(void) { return AECF_ABI_VERSION; }
+
+const char* aecf_strerror(int status) {
+    switch (status) {
+        case AECF_OK: return "ok";
+        case AECF_ERR_INVALID: return "invalid argument";
+        case AECF_ERR_UNSUPPORTED: return "shape or dtype outside what the sm_100a kernels cover (no fallback by design)";
+        case AECF_ERR_ALIGNMENT: return "pointer or leading dimension not 16-byte aligned";
+        case AECF_ERR_WORKSPACE: return "workspace too small";
+        case AECF_ERR_CUDA: return "CUDA error (see aecf_last_cuda_error)";
+        default: return "unknown status";
+    }
+}
+
+const char* aecf_last_cuda_error(void) { return g_cuda_error; }
+uint64_t aecf_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+const char* aecf_build_info(void) {
+    return "aecf_b200 abi 1, sm_100a, nvcc " AECF_STR(__CUDACC_VER_MAJOR__) "." AECF_STR(__CUDACC_VER_MINOR__);
+}
+
+int aecf_pool_fwd(const aecf_pool_desc* desc, const void* q, const void* kv, const float* score_bias,
+                  void* ctx, float* pooled, float* entropy, float* mask_rate, float* masked,
+                  uint8_t* mask_bits, void* stream) {
+    PoolPlan plan;
+    int rc = make_plan(desc, &plan);
+    if (rc != AECF_OK) return rc;
+    if (desc->batch == 0) return AECF_OK;
+    if (!q || !kv || !ctx || !pooled) return AECF_ERR_INVALID;
+    if (!aligned16(q) || !aligned16(kv) || !aligned16(ctx)) return AECF_ERR_ALIGNMENT;
+    if ((rc = use_device(desc->device)) != AECF_OK) return rc;
+    PoolParams& p = plan.p;
+    p.q = q; p.kv = kv; p.bias = score_bias;
+    p.ctx = ctx; p.pooled = pooled; p.entropy = entropy; p.mask_rate = mask_rate; p.masked = masked;
+    p.mask_bits = mask_bits;
+    const int grid = static_cast<int>((p.B + p.SPC - 1) / p.SPC);
+    if (plan.bf16)
+        return plan.drop ? launch_pool_fwd<__nv_bfloat16, true>(plan.M, plan.J, p, grid, stream)
+                         : launch_pool_fwd<__nv_bfloat16, false>(plan.M, plan.J, p, grid, stream);
+    return plan.drop ? launch_pool_fwd<float, true>(plan.M, plan.J, p, grid, stream)
+                     : launch_pool_fwd<float, false>(plan.M, plan.J, p, grid, stream);
+}
+
+size_t aecf_pool_bwd_workspace_bytes(const aecf_pool_desc* desc) {
+    if (desc == nullptr || desc->embed_dim <= 0) return 0;
+    return static_cast<size_t>(POOL_BWD_MAX_BLOCKS) * 3 * desc->embed_dim * sizeof(float);
+}
+
+int aecf_pool_bwd(const aecf_pool_desc* desc, const void* q, const void* kv, const float* score_bias,
+                  const void* d_ctx, const float* d_pooled, const float* d_entropy,
+                  void* d_kv, void* d_q, float* d_bias_kv,
+                  void* workspace, size_t workspace_bytes, void* stream) {
+    PoolPlan plan;
+    int rc = make_plan(desc, &plan);
+    if (rc != AECF_OK) return rc;
+    if (!q || !kv || !d_ctx || !d_kv || !d_q || !workspace) return AECF_ERR_INVALID;
+    if (!aligned16(q) || !aligned16(kv) || !aligned16(d_ctx) || !aligned16(d_kv) || !aligned16(d_q) ||
+        !aligned16(workspace))
+        return AECF_ERR_ALIGNMENT;
+    if (workspace_bytes < aecf_pool_bwd_workspace_bytes(desc)) return AECF_ERR_WORKSPACE;
+    if ((rc = use_device(desc->device)) != AECF_OK) return rc;
+    PoolParams& p = plan.p;
+    p.q = q; p.kv = kv; p.bias = score_bias;
+    p.d_ctx = d_ctx; p.d_pooled = d_pooled; p.d_entropy = d_entropy; p.d_kv = d_kv; p.d_q = d_q;
+    p.partials = static_cast<float*>(workspace);
+
+    int per_sm;
+    if (plan.bf16) per_sm = plan.drop ? pool_bwd_blocks_per_sm<__nv_bfloat16, true>(plan.M, plan.J)
+                                      : pool_bwd_blocks_per_sm<__nv_bfloat16, false>(plan.M, plan.J);
+    else per_sm = plan.drop ? pool_bwd_blocks_per_sm<float, true>(plan.M, plan.J)
+                            : pool_bwd_blocks_per_sm<float, false>(plan.M, plan.J);
+    if (per_sm <= 0) per_sm = 1;
+    long long want = (p.B + p.SPC - 1) / p.SPC;
+    long long cap = static_cast<long long>(sm_count(desc->device)) * per_sm;   // persistent: one resident wave
+    if (cap > POOL_BWD_MAX_BLOCKS) cap = POOL_BWD_MAX_BLOCKS;
+    int grid = static_cast<int>(want < cap ? want : cap);
+    if (grid < 1) grid = 1;
+
+    if (plan.bf16)
+        rc = plan.drop ? launch_pool_bwd<__nv_bfloat16, true>(plan.M, plan.J, p, grid, stream)
+                       : launch_pool_bwd<__nv_bfloat16, false>(plan.M, plan.J, p, grid, stream);
+    else
+        rc = plan.drop ? launch_pool_bwd<float, true>(plan.M, plan.J, p, grid, stream)
+                       : launch_pool_bwd<float, false>(plan.M, plan.J, p, grid, stream);
+    if (rc != AECF_OK) return rc;
+    const int n = 3 * p.D;
+    pool_bwd_finalize_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        p.partials, grid, p.D, p.scale, p.q_shared, p.q_shared ? static_cast<float*>(d_q) : nullptr, d_bias_kv);
+    count_launch();
+    AECF_CUDA_OK(cudaGetLastError());
+    return AECF_OK;
+}
+
+}  // extern "C"

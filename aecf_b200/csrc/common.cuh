@@ -1,0 +1,133 @@
+// Shared device/host helpers for the aecf_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/aecf_b200.h"
+
+namespace aecf {
+
+constexpr unsigned FULL_MASK = 0xffffffffu;
+
+#define AECF_STR_(x) #x
+#define AECF_STR(x) AECF_STR_(x)
+
+// ---- host-side bookkeeping (api.cu) --------------------------------------------------
+void count_launch(unsigned n = 1);
+int set_cuda_error(cudaError_t err, const char* what);   // records and returns AECF_ERR_CUDA
+int use_device(int device);                               // cudaSetDevice; 0 or AECF_ERR_CUDA
+int sm_count(int device);
+
+#define AECF_CUDA_OK(call)                                              \
+    do {                                                                \
+        cudaError_t err__ = (call);                                     \
+        if (err__ != cudaSuccess) return ::aecf::set_cuda_error(err__, #call); \
+    } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- 16-byte vectors of the storage type ---------------------------------------------
+template <typename T> struct Vec;
+
+template <> struct Vec<float> {
+    static constexpr int N = 4;
+    static __device__ __forceinline__ void unpack(const uint4& r, float (&f)[4]) {
+        f[0] = __uint_as_float(r.x); f[1] = __uint_as_float(r.y);
+        f[2] = __uint_as_float(r.z); f[3] = __uint_as_float(r.w);
+    }
+    static __device__ __forceinline__ uint4 pack(const float (&f)[4]) {
+        return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]),
+                          __float_as_uint(f[2]), __float_as_uint(f[3]));
+    }
+};
+
+template <> struct Vec<__nv_bfloat16> {
+    static constexpr int N = 8;
+    static __device__ __forceinline__ void unpack(const uint4& r, float (&f)[8]) {
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            f[2 * i] = __uint_as_float(w[i] << 16);
+            f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+    static __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+        uint32_t r;   // cvt.rn.bf16x2.f32 d, a, b  puts a in the upper half
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+        return r;
+    }
+    static __device__ __forceinline__ uint4 pack(const float (&f)[8]) {
+        return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+    }
+};
+
+// Streaming 128-bit load of read-once data: read-only path, do not allocate in L1.
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {
+    uint4 r;
+    asm("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+        : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint4 ldg_cached(const void* p) {
+    return __ldg(reinterpret_cast<const uint4*>(p));
+}
+__device__ __forceinline__ void stg_vec(void* p, const uint4& v) {
+    *reinterpret_cast<uint4*>(p) = v;
+}
+// Streaming store: written once, consumed by a later kernel from HBM/L2.
+__device__ __forceinline__ void stg_stream(void* p, const uint4& v) {
+    asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <typename T> __device__ __forceinline__ float to_float(T v);
+template <> __device__ __forceinline__ float to_float<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_float<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_float(float v);
+template <> __device__ __forceinline__ float from_float<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// ---- Philox4x32-10 (contract in include/aecf_b200.h, mirrored by oracle/philox.py) -----
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        if (r != 9) { k.x += 0x9E3779B9u; k.y += 0xBB67AE85u; }
+    }
+    return c;
+}
+__device__ __forceinline__ float uniform01(uint32_t x) {      // curand_uniform: (0, 1]
+    return fmaf(__uint2float_rn(x), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+}
+constexpr uint32_t STREAM_MASK = 0u, STREAM_DROPOUT = 1u;
+
+struct RngKey { uint32_t k0, k1, offset; unsigned long long row0; };
+
+// The 4 uniforms of (row, stream, head, block) -- tokens 4*block .. 4*block+3.
+__device__ __forceinline__ void draw4(const RngKey& key, unsigned long long local_row, uint32_t stream,
+                                      uint32_t head, uint32_t block, float (&u)[4]) {
+    const unsigned long long row = key.row0 + local_row;
+    const uint4 c = make_uint4(static_cast<uint32_t>(row), static_cast<uint32_t>(row >> 32), key.offset,
+                               (stream << 28) | (head << 4) | block);
+    const uint4 r = philox4x32_10(c, make_uint2(key.k0, key.k1));
+    u[0] = uniform01(r.x); u[1] = uniform01(r.y); u[2] = uniform01(r.z); u[3] = uniform01(r.w);
+}
+
+// Static-index select out of a small register array (keeps the array in registers).
+template <int M>
+__device__ __forceinline__ float select(const float (&a)[M], int i) {
+    float v = a[0];
+#pragma unroll
+    for (int m = 1; m < M; ++m) v = (i == m) ? a[m] : v;
+    return v;
+}
+
+inline int ilog2(int x) { int l = 0; while ((1 << l) < x) ++l; return l; }
+inline bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+
+}  // namespace aecf

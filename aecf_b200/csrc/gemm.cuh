@@ -1,0 +1,54 @@
+// Shared pieces of the GEMM entry point: the epilogue functor and the tcgen05 hooks.
+#pragma once
+
+#include "common.cuh"
+
+namespace aecf {
+
+struct GemmEpilogue {
+    void* C;
+    long long ldc;
+    const void* bias;
+    int dtype_c, dtype_bias, accumulate;
+    float* partial;                    // split-K: raw fp32 partial sums [split][M][N], epilogue applied by the reduce
+
+    __device__ __forceinline__ float bias_at(long long j) const {
+        if (bias == nullptr) return 0.f;
+        return dtype_bias == AECF_BF16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(bias)[j])
+                                       : static_cast<const float*>(bias)[j];
+    }
+    __device__ __forceinline__ void store(long long i, long long j, float v, int split, long long M, long long N) const {
+        if (partial != nullptr) {
+            partial[(static_cast<long long>(split) * M + i) * N + j] = v;
+            return;
+        }
+        v += bias_at(j);
+        if (dtype_c == AECF_BF16) {
+            __nv_bfloat16* c = static_cast<__nv_bfloat16*>(C) + i * ldc + j;
+            if (accumulate) v += __bfloat162float(*c);
+            *c = __float2bfloat16_rn(v);
+        } else {
+            float* c = static_cast<float*>(C) + i * ldc + j;
+            if (accumulate) v += *c;
+            *c = v;
+        }
+    }
+};
+
+inline GemmEpilogue make_epilogue(const aecf_gemm_desc* d, const void* bias, void* C) {
+    GemmEpilogue ep;
+    ep.C = C; ep.ldc = d->ldc; ep.bias = bias;
+    ep.dtype_c = d->dtype_c; ep.dtype_bias = d->dtype_bias; ep.accumulate = d->accumulate;
+    ep.partial = nullptr;
+    return ep;
+}
+
+int launch_splitk_reduce(const float* partial, long long M, long long N, int splits, const GemmEpilogue& ep,
+                         cudaStream_t s);
+
+// gemm_tcgen05.cu: returns AECF_ERR_UNSUPPORTED when the shape/dtype is outside what it covers.
+int gemm_tcgen05(const aecf_gemm_desc* d, const void* A, const void* B, const void* bias, void* C,
+                 void* workspace, size_t workspace_bytes, cudaStream_t s);
+size_t gemm_tcgen05_workspace_bytes(const aecf_gemm_desc* d);
+
+}  // namespace aecf

@@ -1,0 +1,250 @@
+// Fused pool backward (recompute), persistent over rows.
+//
+// Re-derives the softmax/dropout weights from q and kv (nothing is saved by the forward: this is
+// the recompute the reference's use_checkpoint= flag asks torch.utils.checkpoint for, reference
+// aecf/AECFLayer.py:501-512), then emits dK and dV straight into the packed d_kv buffer and
+// accumulates the three batch reductions that share its data:
+//     d_q (shared query)  = scale * sum_b sum_m ds[b,h,m] k[b,m,h,:]
+//     d_bias_v            = sum_b,m dV      d_bias_k = sum_b,m dK   (analytically ~0)
+// Closed form: SURVEY.md Appendix B; the autograd graph it replaces is that of
+// torch/nn/functional.py:6632-6647, 6657-6659.
+// HBM-bound: algorithmic bytes per sample = s*(2*M*D + D + 2*M*D)  (SURVEY.md section 8d).
+//
+// The batch sums live in shared memory (one private strip per warp, lane-contiguous float4 so
+// the read-modify-write is conflict free), not in registers: that keeps the kernel at two CTAs
+// per SM.  They are folded in a fixed order at the end, so results are run-to-run identical.
+#pragma once
+
+#include "pool_core.cuh"
+
+namespace aecf {
+
+template <int J, int V>
+struct BwdSmem {
+    static constexpr int ACC = J * V * 32;               // floats per accumulator strip
+    static constexpr int PER_WARP = 2 * ACC + J * 32;    // acc_q | acc_bv | acc_sds
+    static constexpr int bytes(int M) { return (POOL_WARPS * M + POOL_WARPS * PER_WARP) * 4; }
+};
+
+template <typename T, int M, int J, bool DROP>
+__global__ void __launch_bounds__(POOL_WARPS * 32, 2)
+pool_bwd_kernel(const PoolParams p) {
+    using Core = PoolCore<T, M, J, DROP>;
+    using Smem = BwdSmem<J, Core::V>;
+    constexpr int V = Core::V;
+    constexpr int Q4 = V / 4;
+    // Keep the raw K chunks in registers between the score pass and the dq pass when they are few;
+    // otherwise the second read goes through L1 (the first one allocates there).
+    constexpr bool KEEP_K = (M * J <= 6);
+
+    extern __shared__ __align__(16) float smem[];
+    float* xchg = smem;                                               // [POOL_WARPS][M]
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    float* strip = smem + POOL_WARPS * M + warp * Smem::PER_WARP;     // this warp's accumulators
+    float4* acc_q = reinterpret_cast<float4*>(strip);                 // [J][Q4][32]
+    float4* acc_bv = reinterpret_cast<float4*>(strip + Smem::ACC);    // [J][Q4][32]
+    float* acc_sds = strip + 2 * Smem::ACC;                           // [J][32]
+    for (int i = lane; i < Smem::PER_WARP; i += 32) strip[i] = 0.f;
+    __syncwarp();
+
+    const int slice = warp % p.WPS;
+    const int c0 = slice * Core::CPW + lane;
+    const char* kv = static_cast<const char*>(p.kv);
+    char* dkv = static_cast<char*>(p.d_kv);
+
+    float qs[J][V];
+    if (p.q_shared) Core::load_query(p, 0, c0, qs);
+
+    const long long stride = static_cast<long long>(gridDim.x) * p.SPC;
+    for (long long base = static_cast<long long>(blockIdx.x) * p.SPC; base < p.B; base += stride) {
+        const long long row_raw = base + warp / p.WPS;
+        const bool row_ok = row_raw < p.B;
+        const long long row = row_ok ? row_raw : p.B - 1;
+        if (!p.q_shared) Core::load_query(p, row, c0, qs);
+
+        // upstream gradient of the context, issued early
+        uint4 dcraw[J];
+        {
+            const char* dc = static_cast<const char*>(p.d_ctx) + static_cast<size_t>(row) * p.D * sizeof(T);
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const int c = c0 + 32 * j;
+                dcraw[j] = (c < p.NC) ? ldg_stream(dc + static_cast<size_t>(c) * 16) : make_uint4(0, 0, 0, 0);
+            }
+        }
+
+        uint4 kraw[KEEP_K ? M : 1][KEEP_K ? J : 1];
+        float w[M][J], wd[M][J];
+        unsigned keep;
+        Core::attention_weights(
+            p, row, c0, qs,
+            [&](int m, int j) {
+                const int c = c0 + 32 * j;
+                const void* src = kv + Core::kv_offset(p, row, m, 0, c);
+                uint4 r = make_uint4(0, 0, 0, 0);
+                if (c < p.NC) r = KEEP_K ? ldg_stream(src) : ldg_cached(src);
+                if (KEEP_K) kraw[KEEP_K ? m : 0][KEEP_K ? j : 0] = r;
+                return r;
+            },
+            w, wd, keep);
+
+        // ---- value pass: d wd = dctx . v ; dV = wd * dctx ; d_bias_v += (sum_m wd) * dctx --------
+        float dwd[M][J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const int c = c0 + 32 * j;
+            float dc[V];
+            Vec<T>::unpack(dcraw[j], dc);
+            uint4 raw[M];
+#pragma unroll
+            for (int m = 0; m < M; ++m)
+                raw[m] = (c < p.NC) ? ldg_stream(kv + Core::kv_offset(p, row, m, 1, c)) : make_uint4(0, 0, 0, 0);
+            float sum_wd = 0.f;
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                float f[V], dv[V];
+                Vec<T>::unpack(raw[m], f);
+                float a = 0.f;
+#pragma unroll
+                for (int v = 0; v < V; ++v) { a = fmaf(dc[v], f[v], a); dv[v] = wd[m][j] * dc[v]; }
+                dwd[m][j] = a;
+                sum_wd += wd[m][j];
+                if (row_ok && c < p.NC) stg_vec(dkv + Core::kv_offset(p, row, m, 1, c), Vec<T>::pack(dv));
+            }
+            if (row_ok) {
+#pragma unroll
+                for (int q4 = 0; q4 < Q4; ++q4) {
+                    float4 a = acc_bv[(j * Q4 + q4) * 32 + lane];
+                    a.x = fmaf(sum_wd, dc[4 * q4], a.x); a.y = fmaf(sum_wd, dc[4 * q4 + 1], a.y);
+                    a.z = fmaf(sum_wd, dc[4 * q4 + 2], a.z); a.w = fmaf(sum_wd, dc[4 * q4 + 3], a.w);
+                    acc_bv[(j * Q4 + q4) * 32 + lane] = a;
+                }
+            }
+        }
+        Core::head_reduce(p, dwd);
+
+        // gradient arriving through the head-averaged weights (info['attention_weights'], and in
+        // eval mode info['entropy'], reference aecf/AECFLayer.py:151-156, 538)
+        if (p.d_pooled != nullptr || p.d_entropy != nullptr) {
+            float dpw[M];
+#pragma unroll
+            for (int m = 0; m < M; ++m)
+                dpw[m] = p.d_pooled ? __ldg(p.d_pooled + static_cast<size_t>(row) * M + m) : 0.f;
+            if (p.d_entropy != nullptr) {
+                float pw[M];
+                Core::head_mean(p, c0, warp, lane, wd, xchg, pw);
+                float raw;
+                clamped_entropy<M>(pw, p.log_m, &raw);
+                const bool inside = (raw >= 0.f) && (raw <= p.log_m);
+                const float de = __ldg(p.d_entropy + row);
+#pragma unroll
+                for (int m = 0; m < M; ++m) dpw[m] += inside ? -(logf(pw[m]) + 1.0f) * de : 0.f;
+            }
+            const float h = static_cast<float>(p.H);
+#pragma unroll
+            for (int m = 0; m < M; ++m)
+#pragma unroll
+                for (int j = 0; j < J; ++j) dwd[m][j] += dpw[m] / h;
+        }
+
+        // ---- dropout and softmax backward ------------------------------------------------
+        float ds[M][J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            float dot = 0.f;
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                float dw = dwd[m][j];
+                if (DROP) dw = ((keep >> (m * J + j)) & 1u) ? dw / p.one_minus_p : 0.f;
+                ds[m][j] = dw;
+                dot = fmaf(w[m][j], dw, dot);
+            }
+            float sum_ds = 0.f;
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                ds[m][j] = w[m][j] * (ds[m][j] - dot);
+                sum_ds += ds[m][j];
+            }
+            if (row_ok && (c0 + 32 * j) < p.NC) acc_sds[j * 32 + lane] += sum_ds;
+        }
+
+        // ---- key pass: dK = ds * (scale * q) ; dq += ds * k --------------------------------
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const int c = c0 + 32 * j;
+            uint4 raw[M];
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                if (KEEP_K) raw[m] = kraw[KEEP_K ? m : 0][KEEP_K ? j : 0];
+                else raw[m] = (c < p.NC) ? ldg_cached(kv + Core::kv_offset(p, row, m, 0, c)) : make_uint4(0, 0, 0, 0);
+            }
+            float dq[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) dq[v] = 0.f;
+            float sum_ds = 0.f;
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                float f[V], dk[V];
+                Vec<T>::unpack(raw[m], f);
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    dk[v] = ds[m][j] * qs[j][v];
+                    dq[v] = fmaf(ds[m][j], f[v], dq[v]);
+                }
+                sum_ds += ds[m][j];
+                if (row_ok && c < p.NC) stg_vec(dkv + Core::kv_offset(p, row, m, 0, c), Vec<T>::pack(dk));
+            }
+            if (row_ok) {
+                if (p.q_shared) {
+#pragma unroll
+                    for (int q4 = 0; q4 < Q4; ++q4) {
+                        float4 a = acc_q[(j * Q4 + q4) * 32 + lane];
+                        a.x += dq[4 * q4]; a.y += dq[4 * q4 + 1]; a.z += dq[4 * q4 + 2]; a.w += dq[4 * q4 + 3];
+                        acc_q[(j * Q4 + q4) * 32 + lane] = a;
+                    }
+                } else {
+                    // per-row query: d_q[row] = scale * dq; the strip accumulates d_bias_k = sum dK instead
+                    float o[V];
+#pragma unroll
+                    for (int v = 0; v < V; ++v) o[v] = dq[v] * p.scale;
+                    if (c < p.NC)
+                        stg_vec(static_cast<char*>(p.d_q) + static_cast<size_t>(row) * p.D * sizeof(T)
+                                    + static_cast<size_t>(c) * 16, Vec<T>::pack(o));
+#pragma unroll
+                    for (int q4 = 0; q4 < Q4; ++q4) {
+                        float4 a = acc_q[(j * Q4 + q4) * 32 + lane];
+                        a.x = fmaf(sum_ds, qs[j][4 * q4], a.x); a.y = fmaf(sum_ds, qs[j][4 * q4 + 1], a.y);
+                        a.z = fmaf(sum_ds, qs[j][4 * q4 + 2], a.z); a.w = fmaf(sum_ds, qs[j][4 * q4 + 3], a.w);
+                        acc_q[(j * Q4 + q4) * 32 + lane] = a;
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- fold the warps' strips in a fixed order into this CTA's partial [3][D] -----------------
+    // partial[0] = d_q (shared query, unscaled)   partial[1] = d_bias_v   partial[2] = d_bias_k
+    __syncthreads();
+    const int D = p.D;
+    float* out = p.partials + static_cast<size_t>(blockIdx.x) * 3 * D;
+    const float* strips = smem + POOL_WARPS * M;
+    for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) {
+        const int which = i / D, d = i - which * D;
+        const int c = d / V, v = d - c * V;
+        const int sl = c / Core::CPW, cl = c - sl * Core::CPW;
+        const int j = cl >> 5, ln = cl & 31;
+        const int idx = ((j * Q4 + (v >> 2)) * 32 + ln) * 4 + (v & 3);
+        float s = 0.f;
+        for (int smp = 0; smp < p.SPC; ++smp) {
+            const float* st = strips + (smp * p.WPS + sl) * Smem::PER_WARP;
+            if (which == 1) s += st[Smem::ACC + idx];
+            else if (which == 0) s += p.q_shared ? st[idx] : 0.f;
+            else s += p.q_shared ? st[2 * Smem::ACC + j * 32 + ln] : st[idx];
+        }
+        if (which == 2 && p.q_shared) s *= __ldg(static_cast<const float*>(p.q) + d) * p.scale;
+        out[i] = s;
+    }
+}
+
+}  // namespace aecf

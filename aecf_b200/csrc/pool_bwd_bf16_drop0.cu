@@ -1,0 +1,3 @@
+#define AECF_POOL_T __nv_bfloat16
+#define AECF_POOL_DROP false
+#include "pool_bwd_inst.inc"

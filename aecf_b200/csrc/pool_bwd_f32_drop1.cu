@@ -1,0 +1,3 @@
+#define AECF_POOL_T float
+#define AECF_POOL_DROP true
+#include "pool_bwd_inst.inc"

@@ -1,0 +1,244 @@
+// Shared core of the fused pool kernels.
+//
+// Work split (DESIGN.md "pool kernels").  A row of D elements is cut into NC = D / V chunks of
+// V = 16 bytes / sizeof(T) elements.  A warp owns a SLICE of 32*J consecutive chunks of one
+// sample (J = 1, 2 or 4 chunk columns; lane l holds chunks l, l+32, ... of the slice), so every
+// warp-wide load instruction covers 512 contiguous bytes.  WPS = ceil(NC / (32 J)) warps share a
+// sample; at the headline shape (D = 512, bf16) one warp owns the whole sample.
+// A head spans G = head_dim / V consecutive chunks: for G <= 32 it is an aligned group of G lanes
+// inside one chunk column, for G > 32 it is all 32 lanes of R = G / 32 consecutive columns
+// (R <= J, so a head never straddles warps).  Per-head dot products are segmented xor-shuffle
+// reductions; afterwards every lane of a head holds the head's value.
+// Heads are independent everywhere except the head-mean of the forward (and of the eval-mode
+// entropy gradient), which crosses warps through shared memory when WPS > 1.
+#pragma once
+
+#include "common.cuh"
+
+namespace aecf {
+
+constexpr int POOL_WARPS = 8;               // warps per CTA for both directions
+
+struct PoolParams {
+    long long B;
+    int D, H, NC, G, logG, LG, R;           // LG = min(G, 32) lanes per head group, R = max(1, G / 32)
+    int WPS, SPC;                           // warps per sample, samples per CTA (WPS * SPC = POOL_WARPS)
+    float scale, p_drop, one_minus_p, base_mask_prob, log_m;   // one_minus_p = float(1.0 - double(p_drop))
+    int training, masking, min_active, q_shared;   // masking: 0 off, 1 training-mode stage, 2 eval-mode stage
+    RngKey rng;
+    const void* q;
+    const void* kv;
+    const float* bias;
+    long long bias_sb, bias_sh;
+    long long kv_sb, kv_sm;                 // kv / d_kv element strides between rows / tokens
+    // forward outputs
+    void* ctx;
+    float* pooled;
+    float* entropy;
+    float* mask_rate;
+    float* masked;
+    uint8_t* mask_bits;
+    // backward
+    const void* d_ctx;
+    const float* d_pooled;
+    const float* d_entropy;
+    void* d_kv;
+    void* d_q;
+    float* partials;                        // [grid][3][D] fp32: dq | dbv | dbk
+};
+
+template <typename T, int M, int J, bool DROP>
+struct PoolCore {
+    static constexpr int V = Vec<T>::N;
+    static constexpr int CPW = 32 * J;               // chunks per warp slice
+
+    // byte offset of chunk c of the K half (half = 0) or V half (half = 1) of token m of `row`
+    static __device__ __forceinline__ size_t kv_offset(const PoolParams& p, long long row, int m, int half, int c) {
+        return (static_cast<size_t>(row) * p.kv_sb + static_cast<size_t>(m) * p.kv_sm
+                + static_cast<size_t>(half) * p.D) * sizeof(T) + static_cast<size_t>(c) * 16;
+    }
+
+    // projected query chunks, pre-multiplied by scale (torch/nn/functional.py:6632)
+    static __device__ __forceinline__ void load_query(const PoolParams& p, long long row, int c0, float (&qs)[J][V]) {
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const int c = c0 + 32 * j;
+#pragma unroll
+            for (int v = 0; v < V; ++v) qs[j][v] = 0.f;
+            if (c < p.NC) {
+                if (p.q_shared) {
+                    const float* q = static_cast<const float*>(p.q) + static_cast<size_t>(c) * V;
+#pragma unroll
+                    for (int v4 = 0; v4 < V; v4 += 4) {
+                        const float4 t = __ldg(reinterpret_cast<const float4*>(q + v4));
+                        qs[j][v4] = t.x * p.scale; qs[j][v4 + 1] = t.y * p.scale;
+                        qs[j][v4 + 2] = t.z * p.scale; qs[j][v4 + 3] = t.w * p.scale;
+                    }
+                } else {
+                    const char* q = static_cast<const char*>(p.q) + (static_cast<size_t>(row) * p.D) * sizeof(T)
+                                    + static_cast<size_t>(c) * 16;
+                    float f[V];
+                    Vec<T>::unpack(ldg_stream(q), f);
+#pragma unroll
+                    for (int v = 0; v < V; ++v) qs[j][v] = f[v] * p.scale;
+                }
+            }
+        }
+    }
+
+    // Sum x[m][j] over the lanes (and chunk columns) that make up each head.
+    static __device__ __forceinline__ void head_reduce(const PoolParams& p, float (&x)[M][J]) {
+        for (int off = p.LG >> 1; off > 0; off >>= 1) {
+#pragma unroll
+            for (int m = 0; m < M; ++m)
+#pragma unroll
+                for (int j = 0; j < J; ++j) x[m][j] += __shfl_xor_sync(FULL_MASK, x[m][j], off);
+        }
+#pragma unroll
+        for (int r = 1; r < J; r <<= 1) {
+            if (r < p.R) {
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    float t[J];
+#pragma unroll
+                    for (int j = 0; j < J; ++j) t[j] = x[m][j] + x[m][j ^ r];
+#pragma unroll
+                    for (int j = 0; j < J; ++j) x[m][j] = t[j];
+                }
+            }
+        }
+    }
+
+    // This warp's share of the sum over heads of x (each head of the slice counted R times).
+    static __device__ __forceinline__ void head_sum_partial(const PoolParams& p, int c0, const float (&x)[M][J],
+                                                            float (&part)[M]) {
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            float t = 0.f;
+#pragma unroll
+            for (int j = 0; j < J; ++j) t += (c0 + 32 * j < p.NC) ? x[m][j] : 0.f;
+            for (int off = p.LG; off < 32; off <<= 1) t += __shfl_xor_sync(FULL_MASK, t, off);
+            part[m] = t;
+        }
+    }
+
+    // Head mean of x for the whole sample (torch/nn/functional.py:6657-6659).  `xchg` is a
+    // [POOL_WARPS][M] shared array; contains a __syncthreads() when the sample spans several warps,
+    // so every warp of the CTA must call it.
+    static __device__ __forceinline__ void head_mean(const PoolParams& p, int c0, int warp, int lane,
+                                                     const float (&x)[M][J], float* xchg, float (&mean)[M]) {
+        float part[M];
+        head_sum_partial(p, c0, x, part);
+        if (p.WPS > 1) {
+            if (lane == 0) {
+#pragma unroll
+                for (int m = 0; m < M; ++m) xchg[warp * M + m] = part[m];
+            }
+            __syncthreads();
+            const int first = (warp / p.WPS) * p.WPS;
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                float t = 0.f;
+                for (int s = 0; s < p.WPS; ++s) t += xchg[(first + s) * M + m];   // fixed order
+                part[m] = t;
+            }
+            __syncthreads();                                   // xchg may be reused by the next row
+        }
+        const float denom = static_cast<float>(p.H * p.R);     // R copies of each head when G > 32 (R = 2^k: exact)
+#pragma unroll
+        for (int m = 0; m < M; ++m) mean[m] = part[m] / denom;
+    }
+
+    // Scores -> softmax -> dropout for the heads of this warp's slice.
+    //   w    : softmax weights          (torch/nn/functional.py:6642-6643)
+    //   wd   : post-dropout weights     (:6645)
+    //   keep : dropout keep flags, bit (m * J + j); d wd / d w = keep / (1 - p)
+    template <typename LoadK>
+    static __device__ __forceinline__ void attention_weights(
+        const PoolParams& p, long long row, int c0, const float (&qs)[J][V], LoadK load_k,
+        float (&w)[M][J], float (&wd)[M][J], unsigned& keep) {
+        float s[M][J];
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            uint4 raw[J];
+#pragma unroll
+            for (int j = 0; j < J; ++j) raw[j] = load_k(m, j);
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                float f[V];
+                Vec<T>::unpack(raw[j], f);
+                float acc = 0.f;
+#pragma unroll
+                for (int v = 0; v < V; ++v) acc = fmaf(qs[j][v], f[v], acc);
+                s[m][j] = acc;
+            }
+        }
+        head_reduce(p, s);
+
+        int head[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) head[j] = min((c0 + 32 * j) >> p.logG, p.H - 1);
+
+        if (p.bias != nullptr) {                                       // :6638 baddbmm(attn_mask, q, k^T)
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const float* b = p.bias + static_cast<size_t>(row) * p.bias_sb + static_cast<size_t>(head[j]) * p.bias_sh;
+#pragma unroll
+                for (int m = 0; m < M; ++m) s[m][j] += __ldg(b + m);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < J; ++j) {                                   // softmax over the M tokens
+            float mx = s[0][j];
+#pragma unroll
+            for (int m = 1; m < M; ++m) mx = fmaxf(mx, s[m][j]);
+            float sum = 0.f;
+#pragma unroll
+            for (int m = 0; m < M; ++m) { w[m][j] = expf(s[m][j] - mx); sum += w[m][j]; }
+#pragma unroll
+            for (int m = 0; m < M; ++m) w[m][j] = w[m][j] / sum;
+        }
+        keep = 0xffffffffu;
+        if (DROP) {
+            keep = 0u;
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+#pragma unroll
+                for (int blk = 0; blk < (M + 3) / 4; ++blk) {
+                    float u[4];
+                    draw4(p.rng, static_cast<unsigned long long>(row), STREAM_DROPOUT,
+                          static_cast<uint32_t>(head[j]), blk, u);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int m = 4 * blk + i;
+                        if (m < M) {
+                            const bool k = (u[i] >= p.p_drop) && (p.p_drop < 1.0f);
+                            keep |= k ? (1u << (m * J + j)) : 0u;
+                            // w * keep / (1 - p): a true division, like the injected reference draw
+                            wd[m][j] = k ? w[m][j] / p.one_minus_p : 0.f;
+                        }
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int m = 0; m < M; ++m)
+#pragma unroll
+                for (int j = 0; j < J; ++j) wd[m][j] = w[m][j];
+        }
+    }
+};
+
+// Shannon entropy with the reference's clamp: clamp(-sum xlogy(w, w), 0, log M), NaN passes through.
+template <int M>
+__device__ __forceinline__ float clamped_entropy(const float (&w)[M], float log_m, float* raw_out = nullptr) {
+    float acc = 0.f;
+#pragma unroll
+    for (int m = 0; m < M; ++m)      // explicit _rn ops: never contracted to FMA, so the rounding
+        acc = __fadd_rn(acc, (w[m] == 0.f) ? 0.f : __fmul_rn(w[m], logf(w[m])));   // sequence is xlogy then sum
+    const float raw = -acc;
+    if (raw_out) *raw_out = raw;
+    return (raw != raw) ? raw : fminf(fmaxf(raw, 0.f), log_m);
+}
+
+}  // namespace aecf

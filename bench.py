@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""Benchmark of the AECF fusion hot path (BASELINE.json metric):
+
+    fused-pool fwd+bwd samples/sec at B=64K, M=3, D=512, H=8; HBM GB/s as % of peak
+
+    python bench.py [--gpus N --steps K --warmup W]          this repo's sm_100a path
+    python bench.py --impl reference [...]                    the reference's CPU path (oracle port)
+
+One step = MultimodalAttentionPool forward(return_info=True) + CurriculumMasking.entropy_loss +
+backward from an upstream gradient d_out, through the public module API.
+`value`  : whole-job samples/s with the batch already resident in HBM.
+`e2e`    : the same, with the batch starting in pinned host memory every step (H2D inside the timed
+           region, double-buffered on a copy stream) and the entropy-loss scalar read back each step.
+`roofline`: the fused pool backward kernel (the largest HBM-bound kernel), algorithmic bytes per launch
+           divided by its CUDA-event duration inside the timed steps, against MEASURED_PEAKS.json.
+`kernels`: per-launch-site CUDA-event averages from the same timed steps (pool forward roofline and
+           tensor-pipe utilisation of the projection GEMMs are derived from these).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "fused-pool fwd+bwd samples/sec at B=64K,M=3,D=512,H=8; HBM GB/s as % of peak"
+UNIT = "samples/s"
+FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md
+FALLBACK_BF16_TFLOPS = 1590.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--batch", type=int, default=65536, help="rows per GPU (weak scaling)")
+    ap.add_argument("--tokens", type=int, default=3)
+    ap.add_argument("--dim", type=int, default=512)
+    ap.add_argument("--heads", type=int, default=8)
+    ap.add_argument("--dtype", choices=["bf16", "fp32"], default="bf16")
+    ap.add_argument("--dropout", type=float, default=0.0)
+    ap.add_argument("--cpu-sample", type=int, default=4096, help="rows of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    except Exception:
+        return {"hbm_gbs": FALLBACK_HBM_GBS, "bf16_tflops": FALLBACK_BF16_TFLOPS, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.stop_flag, self.thread = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [s.strip() for s in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def __enter__(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self.stop_flag.set()
+        self.thread.join(timeout=10)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]),
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port of the reference path, all host threads, bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_step_fn(args, rows):
+    import torch
+    from oracle import aecf_oracle as oracle
+    from oracle import philox
+
+    torch.manual_seed(0)
+    M, D, H = args.tokens, args.dim, args.heads
+    mha = torch.nn.MultiheadAttention(D, H, batch_first=True)          # default init of the reference's module
+    params = {"in_proj_weight": mha.in_proj_weight.detach(), "in_proj_bias": mha.in_proj_bias.detach(),
+              "out_proj.weight": mha.out_proj.weight.detach(), "out_proj.bias": mha.out_proj.bias.detach()}
+    q0 = torch.randn(1, 1, D) * (2.0 / D) ** 0.5
+    x = torch.randn(rows, M, D)
+    u_mask = torch.from_numpy(philox.mask_uniforms(0x5EED, 0, 0, rows, M))
+    d_out = torch.randn(rows, 1, D)
+    masking = dict(base_mask_prob=0.15, entropy_target=0.7, min_active=1)
+
+    def step():
+        with torch.no_grad():
+            q = q0.expand(rows, 1, D)
+            fwd = oracle.pool_forward(q, x, None, params["in_proj_weight"], params["in_proj_bias"],
+                                      params["out_proj.weight"], params["out_proj.bias"], H, training=True,
+                                      u_mask=u_mask, masking=masking)
+            loss = oracle.entropy_loss(fwd.info["entropy"], M)
+            grads = oracle.pool_backward(q, x, None, params["in_proj_weight"], params["out_proj.weight"], H,
+                                         fwd.saved, d_out)
+            return loss, grads
+    return step
+
+
+def time_cpu(args, rows, steps, warmup):
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = cpu_step_fn(args, rows)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return rows / dt, dt * 1e3, cores
+
+
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def workload_config(args, n_gpus):
+    return {"workload": f"MultimodalAttentionPool D={args.dim} H={args.heads} M={args.tokens} with CurriculumMasking, "
+                        f"B={args.batch} per GPU, {args.dtype} (BASELINE.json configs[1])",
+            "global_batch": args.batch * n_gpus, "tokens": args.tokens, "embed_dim": args.dim, "heads": args.heads,
+            "dropout": args.dropout, "parallelism": f"dp{n_gpus}",
+            "l2": "inputs larger than L2 (kv 403 MB, x 201 MB per step vs 126 MB L2); no flush needed",
+            "step": "forward(return_info) + entropy_loss + backward(d_out), public module API"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port; the reference itself is pure Python over
+    torch and /root/reference is not on the GPU box), all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rows = args.cpu_sample
+    value, ms, cores = time_cpu(args, rows, max(1, min(args.steps, 5)), max(1, min(args.warmup, 2)))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": max(1, min(args.steps, 5)), "warmup": max(1, min(args.warmup, 2)), "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{rows} rows of the same workload per step, fp32, torch CPU ops "
+                                       f"({cpu_model()})"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# the sm_100a path
+# ------------------------------------------------------------------------------------------------
+class KernelTimer:
+    """ops.profile_hook: CUDA events around every C-ABI call site, on the launching stream."""
+
+    def __init__(self, torch):
+        self.torch, self.records, self.enabled = torch, [], False
+
+    def __call__(self, name):
+        timer = self
+
+        class Ctx:
+            def __enter__(self_inner):
+                if timer.enabled:
+                    self_inner.a = timer.torch.cuda.Event(enable_timing=True)
+                    self_inner.b = timer.torch.cuda.Event(enable_timing=True)
+                    self_inner.a.record()
+                return self_inner
+
+            def __exit__(self_inner, *exc):
+                if timer.enabled:
+                    self_inner.b.record()
+                    timer.records.append((name, self_inner.a, self_inner.b))
+                return False
+        return Ctx()
+
+    def averages(self, steps):
+        tot, cnt = {}, {}
+        for name, a, b in self.records:
+            tot[name] = tot.get(name, 0.0) + a.elapsed_time(b)
+            cnt[name] = cnt.get(name, 0) + 1
+        return {k: {"ms": tot[k] / cnt[k], "calls_per_step": cnt[k] / steps} for k in tot}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import aecf_b200
+    from aecf_b200 import _lib, ops
+    from aecf_b200.dp import GradientSync
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: aecf_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    es = 2 if dtype == torch.bfloat16 else 4
+    B, M, D, H = args.batch, args.tokens, args.dim, args.heads
+
+    torch.manual_seed(0)
+    query, pool = aecf_b200.create_fusion_pool(D, M, 0.15, num_heads=H, dropout=args.dropout, device=dev, dtype=dtype)
+    cm = pool.curriculum_masking
+    sync = GradientSync(pool, query).attach()
+    sync.set_shard(B * world)                                     # Philox keyed on the global row
+    torch.manual_seed(1234 + rank)
+    x = torch.randn(B, M, D, device=dev, dtype=dtype).requires_grad_(True)
+    d_out = torch.randn(B, 1, D, device=dev, dtype=dtype)
+
+    def step(xin):
+        out, info = pool(query.expand(B, -1, -1), xin, return_info=True)
+        loss = cm.entropy_loss(info["entropy"])
+        out.backward(d_out)
+        sync.finish()
+        return loss
+
+    def clear():
+        x.grad = None
+        query.grad = None
+        pool.zero_grad(set_to_none=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    timer = KernelTimer(torch)
+    ops.profile_hook = timer
+
+    # ---- device-resident timing -----------------------------------------------------------
+    for _ in range(args.warmup):
+        step(x); clear()
+    barrier()
+    launches0 = _lib.launch_count()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    timer.enabled = True
+    with ClockSampler(local) as clocks:
+        start.record()
+        for _ in range(args.steps):
+            step(x); clear()
+        end.record()
+        barrier()
+    timer.enabled = False
+    ms = start.elapsed_time(end) / args.steps
+    launches = (_lib.launch_count() - launches0)
+    kernels = timer.averages(args.steps)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = B * world / (ms * 1e-3)
+
+    # ---- end to end: batch starts in pinned host memory every step -----------------------------
+    e2e = None
+    if not args.no_e2e:
+        host = torch.randn(B, M, D, dtype=dtype).pin_memory()
+        host_loss = torch.zeros(1, dtype=torch.float32).pin_memory()
+        bufs = [torch.empty(B, M, D, device=dev, dtype=dtype).requires_grad_(True) for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=dev)
+        copied = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+
+        def upload(i):
+            slot = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[slot])
+                bufs[slot].detach().copy_(host, non_blocking=True)
+                copied[slot].record(copy_stream)
+
+        def e2e_loop(n):
+            for c in consumed:
+                c.record()
+            upload(0)
+            for i in range(n):
+                slot = i % 2
+                if i + 1 < n:
+                    upload(i + 1)
+                torch.cuda.current_stream().wait_event(copied[slot])
+                loss = step(bufs[slot])
+                host_loss.copy_(loss.reshape(1), non_blocking=True)
+                consumed[slot].record()
+                bufs[slot].grad = None
+                query.grad = None
+                pool.zero_grad(set_to_none=True)
+            torch.cuda.synchronize()
+
+        e2e_loop(max(2, args.warmup))
+        barrier()
+        t0 = time.perf_counter()
+        e2e_loop(args.steps)
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        if world > 1:
+            t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t.item())
+        e2e = {"value": B * world / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": B * M * D * es * world, "d2h_bytes_per_step": 4 * world,
+               "note": "host batch -> double-buffered H2D on a copy stream -> step -> loss scalar D2H"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the fused pool kernels and tensor-pipe use of the GEMMs ----------------------
+    peaks = measured_peaks()
+    fwd_bytes = B * (es * (2 * M * D + D) + 4 * (2 * M + 2))
+    bwd_bytes = B * (es * (2 * M * D + D + 2 * M * D))
+
+    def hbm(name, nbytes):
+        if name not in kernels:
+            return None
+        gbs = nbytes / (kernels[name]["ms"] * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": gbs / peaks["hbm_gbs"], "frac_of_nominal_8TBs": gbs / 8000.0, "traffic": None,
+                "ms": kernels[name]["ms"], "algorithmic_bytes": nbytes, "peak_source": peaks["source"]}
+
+    gemm_flops = {"kv_proj": 2 * B * M * D * 2 * D, "out_proj": 2 * B * D * D, "d_ctx": 2 * B * D * D,
+                  "d_out_weight": 2 * B * D * D, "d_x": 2 * B * M * 2 * D * D, "d_kv_weight": 2 * B * M * 2 * D * D}
+    gemms = {}
+    for name, fl in gemm_flops.items():
+        if name in kernels:
+            tf = fl / (kernels[name]["ms"] * 1e-3) / 1e12
+            gemms[name] = {"ms": kernels[name]["ms"], "tflops": tf, "frac_of_peak": tf / peaks["bf16_tflops"]}
+    roof = hbm("pool_bwd", bwd_bytes)
+    pool_ms = sum(kernels[k]["ms"] for k in ("pool_fwd", "pool_bwd") if k in kernels)
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if dtype == torch.bfloat16 else "f32", "data": "synthetic",
+            "config": workload_config(args, world), "impl": "b200",
+            "roofline": roof, "roofline_pool_fwd": hbm("pool_fwd", fwd_bytes),
+            "pool_kernels_only": {"value": B / (pool_ms * 1e-3) if pool_ms else None, "unit": UNIT, "ms": pool_ms,
+                                  "note": "fused pool fwd+bwd kernels alone, per GPU (the 273 M samples/s target)"},
+            "gemm_tensor_pipe": gemms, "kernels": kernels,
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(), "library": _lib.build_info()}
+
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_value, cpu_ms, cores = time_cpu(args, args.cpu_sample, 3, 1)
+        line["cpu_baseline"] = {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{args.cpu_sample} rows of the same workload per step, 3 steps, fp32, "
+                                          f"torch CPU ops ({cpu_model()})", "ms_per_step": cpu_ms}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

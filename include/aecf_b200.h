@@ -1,0 +1,190 @@
+/*
+ * aecf_b200 -- C ABI of the B200-native AECF fusion hot path.
+ *
+ * This is the drop-in boundary.  The reference has no FFI of its
+ * own: its hot path is Python calling torch (reference aecf/AECFLayer.py:515-521 ->
+ * torch.nn.MultiheadAttention, and :130-283 CurriculumMasking).  Each entry point below
+ * replaces the stretch of that call chain cited next to it and is what a maintainer
+ * would bind with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless marked host
+ *  - the caller (torch) owns every buffer, including workspaces; nothing is allocated,
+ *    freed or retained here; pointers are borrowed for the duration of the enqueue
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never
+ *    synchronises the host, and is re-entrant (autograd's worker thread calls the
+ *    backward entry points)
+ *  - return value: 0 or a negative aecf_status; nothing throws, exits or aborts
+ *  - there is no CPU path: without a CUDA device every compute call returns
+ *    AECF_ERR_CUDA
+ *
+ * Random stream contract (mirrored by oracle/philox.py, the CPU checker):
+ *    Philox4x32-10, key = (seed & 0xffffffff, seed >> 32)
+ *    counter = (row & 0xffffffff, row >> 32, offset & 0xffffffff,
+ *               (stream << 28) | (head << 4) | block)
+ *    row    = row0 + local row index (GLOBAL sample index: an N-rank batch-sharded run
+ *             reproduces the 1-rank masks bit for bit)
+ *    stream = 0 curriculum mask (head = 0), 1 attention dropout
+ *    block  = m / 4 (< 16); lane m % 4 of the 4x32-bit output is the draw of token m
+ *    u      = float(x) * 2^-32 + 2^-33   in (0, 1]
+ *    mask keeps token m iff u <= keep_prob;  dropout keeps (head, m) iff u >= dropout_p
+ */
+#ifndef AECF_B200_H
+#define AECF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(AECF_BUILDING_LIB)
+#define AECF_API __attribute__((visibility("default")))
+#else
+#define AECF_API
+#endif
+
+#define AECF_ABI_VERSION 1
+#define AECF_MAX_TOKENS 8
+
+typedef enum aecf_status {
+    AECF_OK = 0,
+    AECF_ERR_INVALID = -1,      /* bad argument (null pointer, non-positive size, H does not divide D ...) */
+    AECF_ERR_UNSUPPORTED = -2,  /* valid for the reference but outside what the kernels cover; no fallback */
+    AECF_ERR_ALIGNMENT = -3,    /* a pointer or leading dimension is not 16-byte aligned */
+    AECF_ERR_WORKSPACE = -4,    /* workspace too small */
+    AECF_ERR_CUDA = -5          /* a CUDA runtime/driver call failed (see aecf_last_cuda_error) */
+} aecf_status;
+
+typedef enum aecf_dtype { AECF_F32 = 0, AECF_BF16 = 1 } aecf_dtype;
+
+/* Operand layouts for aecf_gemm.  "K-major": the reduction index is contiguous. */
+typedef enum aecf_layout { AECF_K_MAJOR = 0, AECF_MN_MAJOR = 1 } aecf_layout;
+
+typedef enum aecf_gemm_impl { AECF_GEMM_AUTO = 0, AECF_GEMM_SIMT = 1, AECF_GEMM_TCGEN05 = 2 } aecf_gemm_impl;
+
+/* ---- fused attention pool ------------------------------------------------------------
+ * One descriptor for forward and backward.  All pool arithmetic is fp32; `dtype` is the
+ * storage type of kv / ctx / d_ctx / d_kv (and of q, d_q when the query is per-row). */
+typedef struct aecf_pool_desc {
+    int32_t  device;          /* CUDA device ordinal the pointers live on */
+    int32_t  dtype;           /* aecf_dtype */
+    int64_t  batch;           /* B: rows in this call (>= 0; 0 is a no-op) */
+    int32_t  num_tokens;      /* M: modality tokens per row, 1..AECF_MAX_TOKENS */
+    int32_t  embed_dim;       /* D */
+    int32_t  num_heads;       /* H, divides D; D/H must be (16 bytes / element size) * 2^k */
+    int32_t  training;        /* attention module in training mode (enables dropout) */
+    int32_t  masking;         /* 0: no CurriculumMasking stage; 1: module in training mode; 2: in eval mode */
+    int32_t  min_active;      /* CurriculumMasking.min_active */
+    int32_t  q_is_shared;     /* 1: one fp32 projected query [D] for all rows; 0: per-row [B, D] in dtype */
+    float    base_mask_prob;  /* CurriculumMasking.base_mask_prob */
+    float    entropy_target;  /* CurriculumMasking.entropy_target */
+    float    dropout_p;       /* attention dropout (used only when training) */
+    uint64_t seed;            /* Philox key */
+    uint64_t offset;          /* Philox call offset, < 2^32 */
+    uint64_t row0;            /* global index of local row 0 */
+    int64_t  bias_stride_b;   /* score_bias strides in elements (0 broadcasts); token index is contiguous */
+    int64_t  bias_stride_h;
+    int64_t  kv_stride_b;     /* kv / d_kv strides in elements between rows and between tokens; 0, 0 means the */
+    int64_t  kv_stride_m;     /* packed [B, M, 2D] layout (M*2D, 2D); a sequence-first [M, B, 2D] buffer is (2D, B*2D) */
+} aecf_pool_desc;
+
+/* Forward: scale, per-head scores, softmax, dropout, weighted value sum, head mean, and the whole
+ * CurriculumMasking stage.  Replaces torch/nn/functional.py:6632-6647, 6657-6659 and reference
+ * aecf/AECFLayer.py:130-283 (~45 ATen launches, >= 5 host syncs) with one launch.
+ *   q          [D] fp32 (q_is_shared) or [B, D] dtype : projected query, NOT yet scaled
+ *   kv         [B, M, 2D] dtype : projected keys (cols 0..D) and values (cols D..2D); other row/token
+ *              strides via kv_stride_b / kv_stride_m (d_kv of the backward uses the same strides)
+ *   score_bias nullable fp32, additive (key_padding_mask / attn_mask as torch merges them,
+ *              functional.py:6608-6620); element (b, h, m) at b*bias_stride_b + h*bias_stride_h + m
+ *   ctx        [B, D] dtype          out: per-head weighted value sum, heads concatenated
+ *   pooled     [B, M] fp32           out: info['attention_weights'] (head mean, post-dropout)
+ *   entropy    [B] fp32, nullable    out: info['entropy']
+ *   mask_rate  [B] fp32, nullable    out: info['mask_rate']
+ *   masked     [B, M] fp32, nullable out: info['masked_attention_weights']
+ *   mask_bits  [B] u8, nullable      out: bit m set iff token m is active after min_active repair */
+AECF_API int aecf_pool_fwd(const aecf_pool_desc* desc, const void* q, const void* kv, const float* score_bias,
+                  void* ctx, float* pooled, float* entropy, float* mask_rate, float* masked,
+                  uint8_t* mask_bits, void* stream);
+
+/* Backward: recomputes the attention weights from q/kv (nothing from forward is stored; this is what
+ * use_checkpoint= asked for, reference aecf/AECFLayer.py:501-512) and produces every activation
+ * gradient of the pool in one launch plus a tiny deterministic finalize.
+ *   d_ctx      [B, D] dtype
+ *   d_pooled   [B, M] fp32, nullable : gradient w.r.t. info['attention_weights']
+ *   d_entropy  [B] fp32, nullable    : gradient w.r.t. info['entropy'] (eval mode only, :151-156)
+ *   d_kv       [B, M, 2D] dtype      out
+ *   d_q        q_is_shared ? [D] fp32 (summed over rows) : [B, D] dtype   out
+ *   d_bias_kv  [2D] fp32, nullable   out: column sums of d_kv (gradient of in_proj_bias[D:])
+ *   workspace  >= aecf_pool_bwd_workspace_bytes(desc) bytes */
+AECF_API int aecf_pool_bwd(const aecf_pool_desc* desc, const void* q, const void* kv, const float* score_bias,
+                  const void* d_ctx, const float* d_pooled, const float* d_entropy,
+                  void* d_kv, void* d_q, float* d_bias_kv,
+                  void* workspace, size_t workspace_bytes, void* stream);
+AECF_API size_t aecf_pool_bwd_workspace_bytes(const aecf_pool_desc* desc);
+
+/* ---- projections ------------------------------------------------------------------------
+ * C[m, n] = sum_k A[m, k] * B[n, k] (+ bias[n]) (+ C if accumulate), fp32 accumulation.
+ * Replaces torch.nn.functional.linear at torch/nn/functional.py:5854-5855, 6653 and the four
+ * matmuls autograd derives from them.
+ *   a_layout K_MAJOR : A(i, k) at A[i*lda + k]     MN_MAJOR : A(i, k) at A[k*lda + i]
+ *   b_layout K_MAJOR : B(j, k) at B[j*ldb + k]     MN_MAJOR : B(j, k) at B[k*ldb + j]
+ *   C(i, j) at C[i*ldc + j]; bias has dtype_bias and n elements
+ * impl TCGEN05 needs bf16 A and B; AUTO picks it whenever it applies. */
+typedef struct aecf_gemm_desc {
+    int32_t device;
+    int32_t dtype_a, dtype_b, dtype_c, dtype_bias;   /* aecf_dtype */
+    int32_t a_layout, b_layout;                      /* aecf_layout */
+    int32_t accumulate;                              /* 1: C += ... */
+    int32_t impl;                                    /* aecf_gemm_impl */
+    int64_t m, n, k;
+    int64_t lda, ldb, ldc;
+} aecf_gemm_desc;
+
+AECF_API int aecf_gemm(const aecf_gemm_desc* desc, const void* A, const void* B, const void* bias, void* C,
+              void* workspace, size_t workspace_bytes, void* stream);
+AECF_API size_t aecf_gemm_workspace_bytes(const aecf_gemm_desc* desc);
+
+/* ---- small reductions ------------------------------------------------------------------
+ * out[c] = sum_r x[r*ld + c] for a [rows, cols] matrix, fp32 accumulation, deterministic.
+ * (gradient of out_proj.bias; torch/nn/functional.py:6653 backward).  workspace >= the _bytes query. */
+AECF_API int aecf_colsum(int32_t device, int32_t dtype_x, int32_t dtype_out, const void* x, int64_t rows,
+                int64_t cols, int64_t ld, void* out, void* workspace, size_t workspace_bytes, void* stream);
+AECF_API size_t aecf_colsum_workspace_bytes(int64_t rows, int64_t cols);
+
+/* CurriculumMasking.entropy_loss (reference aecf/AECFLayer.py:285-314):
+ * loss[0] = max(0, mean((nan_to_num(e) - target)^2)), deterministic single-block reduction. */
+AECF_API int aecf_entropy_loss_fwd(int32_t device, const float* entropy, int64_t n, float target, float* loss,
+                          void* stream);
+/* d_entropy[i] = d_loss[0] * 2 * (e[i] - target) / n   (zero where e[i] is not finite) */
+AECF_API int aecf_entropy_loss_bwd(int32_t device, const float* entropy, int64_t n, float target,
+                          const float* d_loss, float* d_entropy, void* stream);
+
+/* Standalone CurriculumMasking.forward / compute_entropy on caller-supplied weights [rows, len] fp32,
+ * len <= 64 (reference aecf/AECFLayer.py:101-283; the pool kernel carries the same stage fused).
+ *   mode 1: training (mask, repair, renormalise)   2: eval (weights unchanged, entropy of the input)
+ *        3: entropy only (compute_entropy).  masked / entropy / mask_rate are nullable. */
+AECF_API int aecf_curriculum_mask(int32_t device, const float* weights, int64_t rows, int32_t len, int32_t mode,
+                                  float base_mask_prob, int32_t min_active, uint64_t seed, uint64_t offset,
+                                  uint64_t row0, float* masked, float* entropy, float* mask_rate, void* stream);
+/* d_weights = d_entropy * d clamp(-sum xlogy(w, w), 0, log len) / d w */
+AECF_API int aecf_entropy_bwd(int32_t device, const float* weights, int64_t rows, int32_t len,
+                              const float* d_entropy, float* d_weights, void* stream);
+
+/* Projection-free single-head attention of the functional fast path
+ * (reference aecf/AECFLayer.py:556-581): out[b, s, :] = softmax_t(q[b,s]·k[b,t] / sqrt(D)) · v[b,t]. */
+AECF_API int aecf_sdpa_fwd(int32_t device, int32_t dtype, const void* q, const void* k, const void* v, void* out,
+                  int64_t batch, int32_t tgt_len, int32_t src_len, int32_t embed_dim, void* stream);
+
+/* ---- diagnostics ----------------------------------------------------------------------- */
+AECF_API int         aecf_abi_version(void);
+AECF_API const char* aecf_strerror(int status);
+AECF_API const char* aecf_last_cuda_error(void);      /* host string, thread-local */
+AECF_API uint64_t    aecf_launch_count(void);         /* kernels launched by this library since load */
+AECF_API const char* aecf_build_info(void);           /* "sm_100a nvcc 12.9 ..." */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AECF_B200_H */

@@ -12,8 +12,8 @@ Stream contract (identical text in ``include/aecf_b200.h``):
     counter = (row & 0xffffffff, row >> 32, offset & 0xffffffff,
                (stream << 28) | (head << 4) | block)
     stream  = 0 for the curriculum mask (head = 0), 1 for attention dropout
-    block   = m // 4, and lane m % 4 of the 4x32-bit output is the draw for
-              modality token m  (so M <= 8 needs blocks 0 and 1)
+    block   = m // 4 (< 16), and lane m % 4 of the 4x32-bit output is the draw for
+              token m  (the pool's M <= 8 needs blocks 0 and 1)
     uniform = float32(x) * 2**-32 + 2**-33      (curand_uniform: in (0, 1])
     mask keeps token m      iff  u <= keep_prob          (aecf/AECFLayer.py:204,
                                   torch CUDA bernoulli convention,
@@ -72,8 +72,8 @@ def uniform_from_bits(x):
 
 def _draw(seed, offset, rows, stream, head, num_tokens):
     """uint32 draws of shape rows.shape + (num_tokens,) for one (stream, head)."""
-    if num_tokens > 8:
-        raise ValueError("the stream contract covers at most 8 modality tokens")
+    if num_tokens > 64:
+        raise ValueError("the stream contract covers at most 64 tokens (4-bit block index)")
     if not 0 <= int(offset) < 2 ** 32:
         raise ValueError("offset must fit in 32 bits")
     seed = int(seed) & 0xFFFFFFFFFFFFFFFF
@@ -83,7 +83,7 @@ def _draw(seed, offset, rows, stream, head, num_tokens):
     c0 = (rows & _LO).astype(np.uint32)
     c1 = (rows >> _S32).astype(np.uint32)
     c2 = np.uint32(int(offset))
-    out = np.empty(rows.shape + (8,), dtype=np.uint32)
+    out = np.empty(rows.shape + (4 * ((num_tokens + 3) // 4),), dtype=np.uint32)
     for block in range((num_tokens + 3) // 4):
         c3 = np.uint32((int(stream) << 28) | (int(head) << 4) | block)
         r = philox4x32_10(c0, c1, c2, c3, k0, k1)

@@ -1,0 +1,441 @@
+"""Parity of the CUDA path (through the public module API -> C ABI) with the oracle and with the
+reference's own outputs (tests/golden).  Run on the B200 box:  pytest tests -m gpu
+
+Tolerances (BASELINE.json north_star): fp32 1e-5 relative, bf16 2e-2 relative, masks and the
+active-token set bit-exact.
+"""
+import json
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import aecf_b200
+from aecf_b200 import _lib, ops
+from oracle import aecf_oracle as oracle
+from oracle import philox
+from tests.golden.cases import CASES, CASES_BY_NAME, PHILOX_SEED, Case, build_inputs, masking_kwargs
+from tests.helpers import assert_close, load_golden, run_oracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+FP32_TOL = 1e-5
+BF16_TOL = 2e-2
+
+
+def make_pool(case: Case, inp: dict, dtype: torch.dtype):
+    cm = aecf_b200.CurriculumMasking(**masking_kwargs(case))
+    pool = aecf_b200.MultimodalAttentionPool(case.D, num_heads=case.H, dropout=case.dropout,
+                                             curriculum_masking=cm, device=DEV, dtype=dtype)
+    with torch.no_grad():
+        pool.attention.in_proj_weight.copy_(inp["in_proj_weight"])
+        pool.attention.in_proj_bias.copy_(inp["in_proj_bias"])
+        pool.attention.out_proj.weight.copy_(inp["out_proj.weight"])
+        pool.attention.out_proj.bias.copy_(inp["out_proj.bias"])
+    pool.train(case.training)
+    pool.row_offset = case.row0
+    pool._want_mask_bits = True
+    return pool, cm
+
+
+def run_cuda(case: Case, inp: dict, dtype: torch.dtype):
+    """Forward + backward through the public API with the case's Philox (seed, offset, row0)."""
+    pool, cm = make_pool(case, inp, dtype)
+    query0 = torch.nn.Parameter(inp["query0"].to(DEV, dtype))
+    x = inp["x"].to(DEV, dtype).requires_grad_(True)
+    value = inp["value"].to(DEV, dtype).requires_grad_(True) if case.separate_value else None
+    kpm = inp["key_padding_mask"].to(DEV) if case.kpm else None
+    aecf_b200.set_rng_state(PHILOX_SEED, case.offset)
+    try:
+        out, info = pool(query0.expand(case.B, -1, -1), x, value, key_padding_mask=kpm, return_info=True)
+        ent_loss = cm.entropy_loss(info["entropy"])
+    finally:
+        aecf_b200.set_rng_state(None)
+    loss = (out.float() * inp["grad_out"].to(DEV)).sum()
+    if case.pooled_grad:
+        loss = loss + (info["attention_weights"] * inp["grad_pooled"].to(DEV)).sum()
+    if not case.training:
+        loss = loss + 0.5 * info["entropy"].sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    grads = {
+        "key": x.grad, "query0": query0.grad,
+        "in_proj_weight": pool.attention.in_proj_weight.grad, "in_proj_bias": pool.attention.in_proj_bias.grad,
+        "out_proj.weight": pool.attention.out_proj.weight.grad, "out_proj.bias": pool.attention.out_proj.bias.grad,
+    }
+    if value is not None:
+        grads["value"] = value.grad
+    return out, info, ent_loss, grads, cm
+
+
+def expected_bits(mask: torch.Tensor) -> np.ndarray:
+    m = (mask.reshape(mask.shape[0], -1) > 0).numpy().astype(np.int64)
+    return (m * (1 << np.arange(m.shape[1]))).sum(1).astype(np.uint8)
+
+
+def check_forward(case, out, info, ent_loss, ref, ref_loss, tol, exact_masks=True):
+    assert_close("out", out.cpu(), ref.out, tol)
+    assert_close("attention_weights", info["attention_weights"].cpu(), ref.info["attention_weights"], tol, atol=tol)
+    assert_close("entropy", info["entropy"].cpu(), ref.info["entropy"], tol, atol=tol * max(math.log(max(case.M, 2)), 1))
+    if exact_masks:
+        assert np.array_equal(info["mask_bits"].cpu().numpy(), expected_bits(ref.info["mask"])), "mask bits differ"
+        assert torch.equal(info["mask_rate"].cpu(), ref.info["mask_rate"].float()), "mask_rate differs"
+    assert_close("masked_attention_weights", info["masked_attention_weights"].cpu(),
+                 ref.info["masked_attention_weights"], tol, atol=tol)
+    assert_close("entropy_loss", ent_loss.cpu(), ref_loss, tol, atol=tol)
+    if case.training:
+        assert "target_entropy" in info
+        assert_close("target_entropy", info["target_entropy"].cpu(), ref.info["target_entropy"], 1e-6, atol=1e-6)
+        assert not info["entropy"].requires_grad                       # detached in training (reference :278)
+    else:
+        assert "target_entropy" not in info and info["entropy"].requires_grad
+    assert info["attention_weights"].requires_grad                      # keeps its graph (reference :538)
+    assert not info["masked_attention_weights"].requires_grad
+
+
+def check_grads(case, grads, ref_grads, tol):
+    assert_close("grad key", grads["key"].cpu(), ref_grads["key"], tol)
+    if case.separate_value:
+        assert_close("grad value", grads["value"].cpu(), ref_grads["value"], tol)
+    assert_close("grad query0", grads["query0"].cpu(), ref_grads["query0"], tol)
+    assert_close("grad out_proj.bias", grads["out_proj.bias"].cpu(), ref_grads["out_proj.bias"], tol)
+    assert_close("grad out_proj.weight", grads["out_proj.weight"].cpu(), ref_grads["out_proj.weight"], tol)
+    assert_close("grad in_proj_weight", grads["in_proj_weight"].cpu(), ref_grads["in_proj_weight"], tol)
+    scale = float(ref_grads["in_proj_bias"].abs().max())    # the K-bias third is analytically zero
+    assert_close("grad in_proj_bias", grads["in_proj_bias"].cpu(), ref_grads["in_proj_bias"], tol, atol=tol * scale)
+
+
+FP32_CASES = [c for c in CASES if c.dtype == "float32"]
+
+
+@pytest.mark.parametrize("case", FP32_CASES, ids=lambda c: c.name)
+def test_fp32_matches_oracle(case):
+    inp = build_inputs(case)
+    ref, ref_grads = run_oracle(case, inp)
+    last = case.M if (case.training and case.M > 1) else 2
+    ref_loss = oracle.entropy_loss(ref.info["entropy"], last, case.entropy_target)
+    out, info, ent_loss, grads, cm = run_cuda(case, inp, torch.float32)
+    assert cm._last_seq_len == last
+    check_forward(case, out, info, ent_loss, ref, ref_loss, FP32_TOL)
+    check_grads(case, grads, ref_grads, FP32_TOL)
+
+
+@pytest.mark.parametrize("case", FP32_CASES, ids=lambda c: c.name)
+def test_fp32_matches_reference_golden(case):
+    """Directly against what the unmodified reference produced on the same inputs and draws."""
+    g = load_golden(case)
+    inp = build_inputs(case)
+    out, info, ent_loss, grads, _ = run_cuda(case, inp, torch.float32)
+    tol = 2e-5       # the reference's own fp32 rounding (MKL summation order) is part of this distance
+    assert_close("out", out.cpu(), g["out"], tol)
+    assert_close("attention_weights", info["attention_weights"].cpu(), g["attention_weights"], tol, atol=tol)
+    assert_close("entropy", info["entropy"].cpu(), g["entropy"], tol, atol=tol)
+    assert np.array_equal(info["mask_rate"].cpu().numpy(), g["mask_rate"]), "mask_rate differs from the reference"
+    live = g["attention_weights"] > 0
+    bits = info["mask_bits"].cpu().numpy()[:, None] >> np.arange(case.M)[None, :] & 1
+    if case.training and case.M > 1:
+        assert np.array_equal((bits.reshape(g["attention_weights"].shape) > 0) & live,
+                              g["masked_attention_weights"] > 0), "active-token set differs from the reference"
+    assert_close("masked", info["masked_attention_weights"].cpu(), g["masked_attention_weights"], tol, atol=tol)
+    assert_close("entropy_loss", ent_loss.cpu(), g["entropy_loss"], tol, atol=tol)
+    assert sorted(k for k in info if k != "mask_bits") == sorted(json.loads(str(g["info_keys"])))
+    assert_close("grad_x", grads["key"].cpu(), g["grad_x"], tol)
+    assert_close("grad_query0", grads["query0"].cpu(), g["grad_query0"], tol)
+    assert_close("grad_out_proj_bias", grads["out_proj.bias"].cpu(), g["grad_out_proj_bias"], tol)
+    if case.full_grads:
+        assert_close("grad_in_proj_weight", grads["in_proj_weight"].cpu(), g["grad_in_proj_weight"], tol)
+        assert_close("grad_out_proj_weight", grads["out_proj.weight"].cpu(), g["grad_out_proj_weight"], tol)
+    else:
+        assert_close("grad_in_proj_weight_rowsum", grads["in_proj_weight"].cpu().sum(1), g["grad_in_proj_weight_rowsum"], tol)
+        assert_close("grad_out_proj_weight_strided", grads["out_proj.weight"].cpu().flatten()[::97],
+                     g["grad_out_proj_weight_strided"], tol)
+
+
+BF16_CASES = [c for c in FP32_CASES if c.name in (
+    "config1_d512_h1_m3", "d64_h8_m3", "d64_h8_m3_dropout", "xray_d256_h4_m2", "d128_h4_m8_minactive2",
+    "d64_h4_m4_kpm", "d64_h2_m3_separate_value", "d256_h16_m6")]
+
+
+def _bf16_inputs(case):
+    inp = build_inputs(case)
+    for k in ("in_proj_weight", "in_proj_bias", "out_proj.weight", "out_proj.bias", "query0", "x", "value", "grad_out"):
+        if k in inp:
+            inp[k] = inp[k].bfloat16().float()
+    return inp
+
+
+@pytest.mark.parametrize("case", BF16_CASES, ids=lambda c: c.name)
+def test_bf16_matches_fp32_math_oracle(case):
+    """north_star: bf16 within 2e-2 of fp32 math on the bf16-rounded inputs."""
+    inp = _bf16_inputs(case)
+    ref, ref_grads = run_oracle(case, inp)
+    last = case.M if (case.training and case.M > 1) else 2
+    ref_loss = oracle.entropy_loss(ref.info["entropy"], last, case.entropy_target)
+    out, info, ent_loss, grads, _ = run_cuda(case, inp, torch.bfloat16)
+    check_forward(case, out.float(), info, ent_loss, ref, ref_loss, BF16_TOL, exact_masks=False)
+    check_grads(case, {k: v.float() for k, v in grads.items()}, ref_grads, BF16_TOL)
+    flips = int((torch.from_numpy(np.unpackbits(info["mask_bits"].cpu().numpy()[:, None], axis=1, bitorder="little")
+                                  [:, :case.M]) != (ref.info["mask"].reshape(case.B, case.M) > 0)).sum())
+    assert flips <= max(1, case.B * case.M // 50), f"{flips} mask flips against fp32 math"
+
+
+@pytest.mark.parametrize("case", BF16_CASES, ids=lambda c: c.name)
+def test_bf16_masks_exact_against_stage_rounded_oracle(case):
+    """With the oracle rounding K/V, ctx and out to bf16 where the CUDA path stores them, the masks
+    and the active-token sets are bit-exact and everything else is far inside the bf16 budget."""
+    inp = _bf16_inputs(case)
+    ref, ref_grads = run_oracle(case, inp, storage=torch.bfloat16)
+    out, info, _, grads, _ = run_cuda(case, inp, torch.bfloat16)
+    assert np.array_equal(info["mask_bits"].cpu().numpy(), expected_bits(ref.info["mask"])), "mask bits differ"
+    assert torch.equal(info["mask_rate"].cpu(), ref.info["mask_rate"].float())
+    assert_close("attention_weights", info["attention_weights"].cpu(), ref.info["attention_weights"], 1e-4, atol=1e-5)
+    assert_close("entropy", info["entropy"].cpu(), ref.info["entropy"], 1e-4, atol=1e-5)
+    assert_close("out", out.float().cpu(), ref.out, 1e-2)
+    assert_close("grad key", grads["key"].float().cpu(), ref_grads["key"], BF16_TOL)
+
+
+# ---------------------------------------------------------------------------------------------
+# full-size, size-independent properties (BASELINE.json configs[1]: B=65536, M=3, D=512, H=8 bf16)
+# ---------------------------------------------------------------------------------------------
+def _headline(B=65536, M=3, D=512, H=8, dtype=torch.bfloat16, dropout=0.0, seed=0):
+    torch.manual_seed(seed)
+    q, pool = aecf_b200.create_fusion_pool(D, M, 0.15, num_heads=H, dropout=dropout, device=DEV, dtype=dtype)
+    x = torch.randn(B, M, D, device=DEV, dtype=dtype)
+    return q, pool, x
+
+
+def test_headline_shape_properties_and_determinism():
+    q, pool, x = _headline(dropout=0.1)
+    pool._want_mask_bits = True
+    B, M = x.shape[0], x.shape[1]
+    runs = []
+    for _ in range(2):
+        aecf_b200.set_rng_state(123, 7)
+        xg = x.clone().requires_grad_(True)
+        out, info = pool(q.expand(B, -1, -1), xg, return_info=True)
+        (out.float().pow(2).mean() + 0.01 * pool.curriculum_masking.entropy_loss(info["entropy"])).backward()
+        runs.append((out.detach(), info, xg.grad, pool.attention.in_proj_weight.grad.clone(), q.grad.clone()))
+        pool.zero_grad(); q.grad = None
+    aecf_b200.set_rng_state(None)
+    (o1, i1, gx1, gw1, gq1), (o2, i2, gx2, gw2, gq2) = runs
+    # bit-reproducible run to run (no atomics anywhere on the path)
+    assert torch.equal(o1, o2) and torch.equal(gx1, gx2) and torch.equal(gw1, gw2) and torch.equal(gq1, gq2)
+    assert torch.equal(i1["mask_bits"], i2["mask_bits"])
+    masked = i1["masked_attention_weights"]
+    assert torch.allclose(masked.sum(-1), torch.ones_like(masked.sum(-1)), atol=1e-5)
+    bits = i1["mask_bits"].long()
+    active = sum((bits >> m) & 1 for m in range(M))
+    assert int(active.min()) >= 1
+    assert torch.equal(i1["mask_rate"].reshape(-1), 1.0 - active.float() / M)
+    ent = i1["entropy"]
+    assert float(ent.min()) >= 0.0 and float(ent.max()) <= math.log(M) + 1e-6
+    assert ((masked > 0).reshape(B, M) <= (((bits[:, None] >> torch.arange(M, device=DEV)) & 1) > 0)).all()
+    for t in (o1, gx1, gw1, gq1):
+        assert torch.isfinite(t.float()).all()
+    # mask statistics: with flat attention keep_prob ~ 0.85 per token
+    assert abs(float(i1["mask_rate"].mean()) - 0.15) < 0.01
+
+
+def test_batch_sharding_reproduces_masks_and_sums_gradients():
+    """Rows are independent and Philox is keyed on the GLOBAL row: two half-batches with
+    row_offset = 0 / B/2 give the full-batch outputs and masks bit for bit, and parameter gradients
+    that add up to the full-batch ones (the data-parallel contract)."""
+    q, pool, x = _headline(B=8192, dropout=0.1)
+    pool._want_mask_bits = True
+    B = x.shape[0]
+
+    def step(xs, row0):
+        pool.row_offset = row0
+        aecf_b200.set_rng_state(99, 3)
+        xs = xs.clone().requires_grad_(True)
+        out, info = pool(q.expand(xs.shape[0], -1, -1), xs, return_info=True)
+        out.float().pow(2).sum().backward()
+        res = (out.detach(), info["mask_bits"].clone(), xs.grad, pool.attention.in_proj_weight.grad.float().clone(),
+               q.grad.float().clone())
+        pool.zero_grad(); q.grad = None
+        return res
+
+    full = step(x, 0)
+    lo, hi = step(x[: B // 2], 0), step(x[B // 2:], B // 2)
+    aecf_b200.set_rng_state(None); pool.row_offset = 0
+    assert torch.equal(torch.cat([lo[0], hi[0]]), full[0])
+    assert torch.equal(torch.cat([lo[1], hi[1]]), full[1])
+    assert torch.equal(torch.cat([lo[2], hi[2]]), full[2])
+    assert_close("in_proj_weight grad", (lo[3] + hi[3]).cpu(), full[3].cpu(), 2e-2)
+    assert_close("query grad", (lo[4] + hi[4]).cpu(), full[4].cpu(), 2e-2)
+
+
+# ---------------------------------------------------------------------------------------------
+# API surface on the device
+# ---------------------------------------------------------------------------------------------
+def test_sequence_first_layout_matches_batch_first():
+    case = CASES_BY_NAME["d64_h8_m3"]
+    inp = build_inputs(case)
+    pool_b, _ = make_pool(case, inp, torch.float32)
+    pool_s, _ = make_pool(case, inp, torch.float32)
+    pool_s.batch_first = False
+    q = inp["query0"].to(DEV)
+    x = inp["x"].to(DEV)
+    outs = []
+    for pool, qq, xx in ((pool_b, q.expand(case.B, -1, -1), x),
+                         (pool_s, q.expand(-1, case.B, -1), x.transpose(0, 1).contiguous())):
+        aecf_b200.set_rng_state(PHILOX_SEED, 0)
+        xx = xx.clone().requires_grad_(True)
+        out, info = pool(qq, xx, return_info=True)
+        out.pow(2).sum().backward()
+        outs.append((out, info, xx.grad))
+    aecf_b200.set_rng_state(None)
+    assert outs[1][0].shape == (1, case.B, case.D)
+    assert torch.equal(outs[0][0].reshape(case.B, case.D), outs[1][0].reshape(case.B, case.D))
+    assert torch.equal(outs[0][1]["mask_bits"], outs[1][1]["mask_bits"])
+    assert torch.equal(outs[0][2], outs[1][2].transpose(0, 1))
+
+
+def test_per_row_queries_match_oracle():
+    case = CASES_BY_NAME["d64_h8_m3_dropout"]
+    inp = build_inputs(case)
+    queries = torch.from_numpy(philox.normal(4242, (case.B, 1, case.D))).float() * 0.3
+    fwd = oracle.pool_forward(queries, inp["x"], None, inp["in_proj_weight"], inp["in_proj_bias"],
+                              inp["out_proj.weight"], inp["out_proj.bias"], case.H, dropout_p=case.dropout,
+                              training=True, u_drop=inp["u_drop"], u_mask=inp["u_mask"], masking=masking_kwargs(case))
+    grads = oracle.pool_backward(queries, inp["x"], None, inp["in_proj_weight"], inp["out_proj.weight"], case.H,
+                                 fwd.saved, inp["grad_out"], dropout_p=case.dropout, training=True)
+    pool, _ = make_pool(case, inp, torch.float32)
+    qd = queries.to(DEV).requires_grad_(True)
+    xd = inp["x"].to(DEV).requires_grad_(True)
+    aecf_b200.set_rng_state(PHILOX_SEED, case.offset)
+    out, info = pool(qd, xd, return_info=True)
+    aecf_b200.set_rng_state(None)
+    (out * inp["grad_out"].to(DEV)).sum().backward()
+    assert_close("out", out.cpu(), fwd.out, FP32_TOL)
+    assert np.array_equal(info["mask_bits"].cpu().numpy(), expected_bits(fwd.info["mask"]))
+    assert_close("grad query", qd.grad.cpu(), grads["query"], FP32_TOL)
+    assert_close("grad key", xd.grad.cpu(), grads["key"], FP32_TOL)
+    assert_close("grad in_proj_weight", pool.attention.in_proj_weight.grad.cpu(), grads["in_proj_weight"], FP32_TOL)
+    scale = float(grads["in_proj_bias"].abs().max())
+    assert_close("grad in_proj_bias", pool.attention.in_proj_bias.grad.cpu(), grads["in_proj_bias"], FP32_TOL,
+                 atol=FP32_TOL * scale)
+
+
+def test_no_masking_module_and_plain_output():
+    case = CASES_BY_NAME["d64_h8_m3"]
+    inp = build_inputs(case)
+    pool, _ = make_pool(case, inp, torch.float32)
+    pool.curriculum_masking = None                                  # runtime toggle (xrays/train_xrays_example.py:179-187)
+    q, x = inp["query0"].to(DEV).expand(case.B, -1, -1), inp["x"].to(DEV)
+    out = pool(q, x)
+    assert isinstance(out, torch.Tensor) and out.shape == (case.B, 1, case.D)
+    out2, info = pool(q, x, return_info=True, use_checkpoint=True)
+    assert set(info) == {"attention_weights"} and torch.equal(out, out2)
+    ref, _ = run_oracle(case, inp)
+    assert_close("out", out.cpu(), ref.out, FP32_TOL)
+
+
+def test_unsupported_shapes_fail_loudly():
+    pool = aecf_b200.MultimodalAttentionPool(64, num_heads=4, device=DEV)
+    x = torch.randn(4, 3, 64, device=DEV)
+    with pytest.raises(_lib.UnsupportedShapeError):
+        pool(torch.randn(4, 2, 64, device=DEV), x)                  # two queries per sample
+    with pytest.raises(_lib.UnsupportedShapeError):
+        pool(torch.randn(4, 1, 64, device=DEV), torch.randn(4, 9, 64, device=DEV))   # 9 tokens > 8
+    odd = aecf_b200.MultimodalAttentionPool(60, num_heads=4, device=DEV)             # head_dim 15
+    with pytest.raises(_lib.UnsupportedShapeError):
+        odd(torch.randn(4, 1, 60, device=DEV), torch.randn(4, 3, 60, device=DEV))
+    with pytest.raises(RuntimeError, match="CUDA tensors"):
+        pool(torch.randn(4, 1, 64), torch.randn(4, 3, 64))          # CPU tensors: no fallback
+
+
+def test_functional_fast_path_and_module_path():
+    q = torch.from_numpy(philox.normal(1, (6, 2, 64))).float()
+    k = torch.from_numpy(philox.normal(2, (6, 5, 64))).float()
+    out = aecf_b200.multimodal_attention_pool(q.to(DEV), k.to(DEV))
+    assert_close("sdpa", out.cpu(), oracle.sdpa_single_head(q, k, k), FP32_TOL)
+    out_bf = aecf_b200.multimodal_attention_pool(q.to(DEV).bfloat16(), k.to(DEV).bfloat16())
+    assert_close("sdpa bf16", out_bf.float().cpu(), oracle.sdpa_single_head(q.bfloat16().float(), k.bfloat16().float(),
+                                                                           k.bfloat16().float()), BF16_TOL)
+    cm = aecf_b200.CurriculumMasking(0.15)
+    y = aecf_b200.multimodal_attention_pool(torch.randn(8, 1, 64, device=DEV), torch.randn(8, 3, 64, device=DEV),
+                                            num_heads=4, curriculum_masking=cm, training=True)
+    assert y.shape == (8, 1, 64) and y.is_cuda and torch.isfinite(y).all()
+
+
+def test_standalone_masking_and_entropy():
+    cm = aecf_b200.CurriculumMasking(base_mask_prob=0.9, min_active=2).to(DEV)
+    w = torch.softmax(2 * torch.from_numpy(philox.normal(5, (257, 10))).float(), -1)
+    aecf_b200.set_rng_state(77, 5)
+    masked, info = cm(w.to(DEV))
+    aecf_b200.set_rng_state(None)
+    u = torch.from_numpy(philox.mask_uniforms(77, 5, 0, 257, 10))
+    ref = oracle.curriculum_mask(w, u, base_mask_prob=0.9, min_active=2)
+    assert set(info) == {"entropy", "mask_rate", "target_entropy"}
+    assert torch.equal(info["mask_rate"].cpu(), ref["mask_rate"])
+    assert torch.equal(masked.cpu() > 0, ref["masked"] > 0)
+    assert_close("masked", masked.cpu(), ref["masked"], FP32_TOL, atol=1e-6)
+    assert_close("entropy", info["entropy"].cpu(), ref["entropy"], FP32_TOL, atol=1e-6)
+    assert cm._last_seq_len == 10
+    # eval mode: weights pass through, entropy stays differentiable (reference :150-156)
+    cm.eval()
+    wd = w.to(DEV).requires_grad_(True)
+    same, einfo = cm(wd)
+    assert same is wd and set(einfo) == {"entropy", "mask_rate"}
+    einfo["entropy"].sum().backward()
+    wc = w.clone().requires_grad_(True)
+    oracle.shannon_entropy(wc).sum().backward()
+    assert_close("d entropy", wd.grad.cpu(), wc.grad, FP32_TOL)
+    assert_close("compute_entropy", cm.compute_entropy(w.to(DEV)).cpu(), oracle.shannon_entropy(w), FP32_TOL, atol=1e-6)
+    edge = torch.tensor([[1.0, 0.0, 0.0], [0.33, 0.33, 0.34]], device=DEV)          # README.md:311-316
+    cm.train()
+    out, _ = cm(edge)
+    assert torch.isfinite(out).all()
+
+
+def test_entropy_loss_gradient_in_eval_mode():
+    cm = aecf_b200.CurriculumMasking().to(DEV)
+    e = (torch.rand(1000, 1, device=DEV) * 1.1).requires_grad_(True)
+    loss = cm.entropy_loss(e)
+    loss.backward()
+    ec = e.detach().cpu().requires_grad_(True)
+    ref = oracle.entropy_loss(ec, 2, 0.7)
+    ref.backward()
+    assert_close("loss", loss.cpu(), ref, FP32_TOL)
+    assert_close("d loss", e.grad.cpu(), ec.grad, FP32_TOL)
+    bad = torch.tensor([float("nan"), float("inf"), float("-inf"), 0.3], device=DEV)
+    assert_close("scrubbed", cm.entropy_loss(bad).cpu(), oracle.entropy_loss(bad.cpu(), 2, 0.7), FP32_TOL)
+
+
+# ---------------------------------------------------------------------------------------------
+# the projection GEMM on its own, every operand layout the path uses
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("impl", [_lib.GEMM_SIMT, _lib.GEMM_AUTO], ids=["simt", "auto"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("shape", [(384, 256, 128), (200, 136, 72), (1024, 512, 2048), (1, 512, 512), (512, 512, 1)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_gemm_layouts(impl, dtype, shape):
+    m, n, k = shape
+    torch.manual_seed(m + n + k)
+    a = torch.randn(m, k, device=DEV).to(dtype)
+    b = torch.randn(n, k, device=DEV).to(dtype)
+    bias = torch.randn(n, device=DEV).to(dtype)
+    want = a.double() @ b.double().t()
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    for a_lay, a_mem in ((_lib.K_MAJOR, a), (_lib.MN_MAJOR, a.t().contiguous())):
+        for b_lay, b_mem in ((_lib.K_MAJOR, b), (_lib.MN_MAJOR, b.t().contiguous())):
+            for use_bias in (False, True):
+                out = ops.gemm(a_mem, b_mem, m=m, n=n, k=k, a_layout=a_lay, b_layout=b_lay,
+                               lda=a_mem.stride(0), ldb=b_mem.stride(0), bias=bias if use_bias else None,
+                               out_dtype=torch.float32, impl=impl)
+                ref = want + (bias.double() if use_bias else 0.0)
+                assert_close(f"gemm a_layout={a_lay} b_layout={b_lay} bias={use_bias}", out.cpu(), ref.cpu(), tol)
+    # strided output (the separate-value path writes K and V into the halves of one buffer)
+    buf = torch.zeros(m, 2 * n, device=DEV, dtype=dtype)
+    ops.gemm(a, b, m=m, n=n, k=k, a_layout=_lib.K_MAJOR, b_layout=_lib.K_MAJOR, lda=k, ldb=k, out=buf[:, n:], ldc=2 * n,
+             impl=impl)
+    assert_close("strided C", buf[:, n:].float().cpu(), want.cpu(), 2e-2 if dtype == torch.bfloat16 else tol)
+    assert float(buf[:, :n].abs().max()) == 0.0
+
+
+def test_colsum():
+    for dtype in (torch.float32, torch.bfloat16):
+        x = torch.randn(5000, 512, device=DEV).to(dtype)
+        assert_close("colsum", ops.colsum(x, out_dtype=torch.float32).cpu(), x.double().sum(0).cpu(), 1e-5)
