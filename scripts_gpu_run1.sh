@@ -1,0 +1,15 @@
+#!/bin/bash
+# GPU run 1: parity tests, a first bench line, launch list + full ncu capture of the pool kernels
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
+timeout 1500 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider --timeout 300 > gpurun_out/tests.log 2>&1
+echo "pytest exit $?" >> gpurun_out/tests.log
+timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
+echo "bench exit $?" >> gpurun_out/bench.err
+timeout 300 python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/plain.log 2>&1 && \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
+timeout 300 python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/plain2.log 2>&1 && \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:pool_ -s 4 -c 4 -o gpurun_out/prof_pool_r1 \
+    python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+tail -5 gpurun_out/tests.log; tail -c 600 gpurun_out/bench.json; tail -3 gpurun_out/bench.err
