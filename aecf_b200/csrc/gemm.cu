@@ -72,20 +72,20 @@ gemm_simt_kernel(const TA* __restrict__ A, const TB* __restrict__ B, long long M
 
 // Fold split-K partials [splits][M][N] (fp32) in order, then apply the epilogue.
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, long long M, long long N, int splits,
-                                     GemmEpilogue ep) {
+                                     long long split_stride, GemmEpilogue ep) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= M * N) return;
     float s = 0.f;
-    for (int z = 0; z < splits; ++z) s += partial[static_cast<long long>(z) * M * N + i];
+    for (int z = 0; z < splits; ++z) s += partial[static_cast<long long>(z) * split_stride + i];
     GemmEpilogue direct = ep;
     direct.partial = nullptr;
     direct.store(i / N, i % N, s, 0, M, N);
 }
 
-int launch_splitk_reduce(const float* partial, long long M, long long N, int splits, const GemmEpilogue& ep,
-                         cudaStream_t s) {
+int launch_splitk_reduce(const float* partial, long long M, long long N, int splits, long long split_stride,
+                         const GemmEpilogue& ep, cudaStream_t s) {
     const long long total = M * N;
-    splitk_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(partial, M, N, splits, ep);
+    splitk_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(partial, M, N, splits, split_stride, ep);
     count_launch();
     AECF_CUDA_OK(cudaGetLastError());
     return AECF_OK;
@@ -137,7 +137,7 @@ static int gemm_simt(const aecf_gemm_desc* d, const void* A, const void* B, cons
     else if (b16) rc = launch_simt<float, __nv_bfloat16>(d, A, B, ep, splits, s);
     else rc = launch_simt<float, float>(d, A, B, ep, splits, s);
     if (rc != AECF_OK || splits == 1) return rc;
-    return launch_splitk_reduce(ep.partial, d->m, d->n, splits, ep, s);
+    return launch_splitk_reduce(ep.partial, d->m, d->n, splits, d->m * d->n, ep, s);
 }
 
 static bool valid_dtype(int t) { return t == AECF_F32 || t == AECF_BF16; }

@@ -43,8 +43,8 @@ inline GemmEpilogue make_epilogue(const aecf_gemm_desc* d, const void* bias, voi
     return ep;
 }
 
-int launch_splitk_reduce(const float* partial, long long M, long long N, int splits, const GemmEpilogue& ep,
-                         cudaStream_t s);
+int launch_splitk_reduce(const float* partial, long long M, long long N, int splits, long long split_stride,
+                         const GemmEpilogue& ep, cudaStream_t s);
 
 // gemm_tcgen05.cu: returns AECF_ERR_UNSUPPORTED when the shape/dtype is outside what it covers.
 int gemm_tcgen05(const aecf_gemm_desc* d, const void* A, const void* B, const void* bias, void* C,

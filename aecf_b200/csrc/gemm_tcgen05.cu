@@ -1,7 +1,475 @@
+// bf16 GEMM on the 5th-generation tensor cores: C[m,n] = sum_k A[m,k] B[n,k] (+ bias[n]).
+//
+//   operands  : TMA (cp.async.bulk.tensor, 128-byte swizzle) into a 4-stage shared-memory ring;
+//               K-major or MN-major in global memory -- the UMMA smem descriptor carries the major
+//   math      : tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16 per instruction, issued by one
+//               elected thread; fp32 accumulators live in TMEM (2 x BN columns, double buffered)
+//   epilogue  : tcgen05.ld TMEM -> registers, + bias, -> bf16/fp32 -> swizzled smem -> TMA store,
+//               overlapped with the next tile's main loop (persistent CTAs, one per SM)
+//   split-K   : for the weight-gradient products (K = B*M rows, tiny output) each work item writes an
+//               fp32 partial tile; splitk_reduce (gemm.cu) folds them in a fixed order
+//
+// Replaces the cuBLAS calls behind torch.nn.functional.linear at torch/nn/functional.py:5855, 6653
+// and the matmuls autograd derives from them.  Descriptor bit layouts follow the PTX ISA tables as
+// restated in cute/arch/mma_sm100_desc.hpp (SmemDescriptor, InstrDescriptor).
+#include <cuda.h>
+
+#include <mutex>
+
 #include "gemm.cuh"
+
 namespace aecf {
-int gemm_tcgen05(const aecf_gemm_desc*, const void*, const void*, const void*, void*, void*, size_t, cudaStream_t) {
-    return AECF_ERR_UNSUPPORTED;
+
+namespace tc {
+
+constexpr int BM = 128;            // UMMA M (cta_group::1)
+constexpr int BK = 64;             // one 128-byte swizzle atom of bf16 along K
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int NUM_THREADS = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int EPI_THREADS = 128;
+constexpr long long SPIN_LIMIT = 4000000000LL;   // ~2 s of SM clocks: trap instead of hanging the GPU
+
+template <int BN> struct Cfg {
+    static constexpr int A_BYTES = BM * BK * 2;                 // 16 KB
+    static constexpr int B_BYTES = BN * BK * 2;                 // 16 / 32 KB
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int EPI_BYTES = 2 * BM * 128;              // staging: two [128 rows x 128 B] swizzled boxes
+    static constexpr int TMEM_COLS = 2 * BN;                    // double-buffered accumulator
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct Params {
+    int m, n, k;
+    int tiles_m, tiles_n, splits, kb_per_split, kb_total;
+    int a_mn_major, b_mn_major;
+    int c_is_f32;              // element type of the TMA-stored C / partial
+    int has_bias, bias_is_bf16;
+    const void* bias;
+    int partial_rows;          // rows of one split's partial (= m) when splits > 1
+};
+
+// ---- raw PTX wrappers -----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
 }
-size_t gemm_tcgen05_workspace_bytes(const aecf_gemm_desc*) { return 0; }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    const long long t0 = clock64();
+    while (true) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+        if (clock64() - t0 > SPIN_LIMIT) __trap();          // a pipeline bug must fail, not hang the box
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 :: "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {     // arrives on `bar` when all prior MMAs retire
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                 :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, leading/stride byte
+// offsets in 16-byte units, version 1 (Blackwell), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= 1ull << 46;
+    d |= 2ull << 61;
+    return d;
+}
+// Descriptor of the 16-deep K slice `ks` of an operand tile of `rows` MN-rows in the stage buffer.
+//   K-major : rows of 128 B (64 bf16 of K), 8-row groups 1024 B apart; a K slice is 32 B further in.
+//   MN-major: 64-wide MN atoms, each [64 K-rows x 128 B], 8-K-row groups 1024 B apart (SBO), atoms
+//             BK*128 B apart (LBO); a K slice is 16 K-rows = 2048 B further in.
+__device__ __forceinline__ uint64_t operand_desc(uint32_t base, int mn_major, int ks) {
+    if (!mn_major) return make_smem_desc(base + ks * (UMMA_K * 2), 0, 8 * 128);
+    return make_smem_desc(base + ks * (UMMA_K * 128), BK * 128, 8 * 128);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 [4,6)=1, a=bf16 [7,10)=1, b=bf16 [10,13)=1,
+// a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29).
+__device__ __forceinline__ uint32_t make_idesc(int bn, int a_mn, int b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn) << 15) |
+           (static_cast<uint32_t>(b_mn) << 16) | (static_cast<uint32_t>(bn >> 3) << 17) |
+           (static_cast<uint32_t>(BM >> 4) << 24);
+}
+
+struct WorkItem { int m_blk, n_blk, split, kb_begin, kb_count; };
+
+__device__ __forceinline__ WorkItem decode(const Params& p, int item) {
+    WorkItem w;
+    const int tiles = p.tiles_m * p.tiles_n;
+    w.split = item / tiles;
+    const int t = item - w.split * tiles;
+    w.m_blk = t / p.tiles_n;                 // n fastest: neighbouring CTAs share the A row block in L2
+    w.n_blk = t - w.m_blk * p.tiles_n;
+    w.kb_begin = w.split * p.kb_per_split;
+    w.kb_count = min(p.kb_per_split, p.kb_total - w.kb_begin);
+    return w;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_c, const Params p) {
+    using C = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stage_base = smem;
+    uint8_t* epi_base = smem + STAGES * C::STAGE_BYTES;                       // 1024-aligned (stage sizes are)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_base + C::EPI_BYTES);
+    uint64_t* full = bars;                        // [STAGES] TMA -> MMA
+    uint64_t* empty = bars + STAGES;              // [STAGES] MMA -> TMA
+    uint64_t* tmem_full = bars + 2 * STAGES;      // [2] MMA -> epilogue
+    uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2] epilogue -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    __shared__ float bias_tile[BN];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int items = p.tiles_m * p.tiles_n * p.splits;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_a); prefetch_tmap(&map_b); prefetch_tmap(&map_c);
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EPI_THREADS); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {                                  // one warp allocates TMEM and owns the dealloc
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(tmem_slot)), "r"(static_cast<uint32_t>(C::TMEM_COLS)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int it = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x) {
+                const WorkItem w = decode(p, item);
+                for (int kb = 0; kb < w.kb_count; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+                    uint8_t* a_dst = stage_base + s * C::STAGE_BYTES;
+                    uint8_t* b_dst = a_dst + C::A_BYTES;
+                    mbar_expect_tx(&full[s], C::STAGE_BYTES);
+                    const int k0 = (w.kb_begin + kb) * BK;
+                    if (!p.a_mn_major) {
+                        tma_load_2d(&map_a, &full[s], a_dst, k0, w.m_blk * BM);
+                    } else {
+#pragma unroll
+                        for (int a = 0; a < BM / 64; ++a)
+                            tma_load_2d(&map_a, &full[s], a_dst + a * (BK * 128), w.m_blk * BM + a * 64, k0);
+                    }
+                    if (!p.b_mn_major) {
+                        tma_load_2d(&map_b, &full[s], b_dst, k0, w.n_blk * BN);
+                    } else {
+#pragma unroll
+                        for (int a = 0; a < BN / 64; ++a)
+                            tma_load_2d(&map_b, &full[s], b_dst + a * (BK * 128), w.n_blk * BN + a * 64, k0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(BN, p.a_mn_major, p.b_mn_major);
+            int it = 0, tile_it = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x, ++tile_it) {
+                const WorkItem w = decode(p, item);
+                const int as = tile_it & 1;
+                mbar_wait(&tmem_empty[as], ((tile_it >> 1) & 1) ^ 1);          // epilogue drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * BN;
+                for (int kb = 0; kb < w.kb_count; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&full[s], (it / STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(stage_base + s * C::STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + C::A_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < BK / UMMA_K; ++ks)
+                        umma_bf16(tmem_d, operand_desc(a_addr, p.a_mn_major, ks), operand_desc(b_addr, p.b_mn_major, ks),
+                                  idesc, (kb | ks) != 0 ? 1u : 0u);
+                    umma_commit(&empty[s]);                                    // smem slot free once these MMAs retire
+                }
+                umma_commit(&tmem_full[as]);                                   // accumulator complete
+            }
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> (+bias, convert) -> swizzled smem -> TMA store =====
+        const int quad = warp & 3;                   // TMEM lane quadrant this warp may read
+        const int row = quad * 32 + lane;            // row of the tile held by this thread
+        const int et = threadIdx.x - 64;             // 0..127
+        int tile_it = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x, ++tile_it) {
+            const WorkItem w = decode(p, item);
+            const int as = tile_it & 1;
+            const int n0 = w.n_blk * BN, m0 = w.m_blk * BM;
+            const bool direct = (p.splits == 1);
+            // bias slice of this tile (fp32 in smem); previous tile's readers are past the barrier below
+            if (direct && p.has_bias) {
+                for (int i = et; i < BN; i += EPI_THREADS) {
+                    const int col = n0 + i;
+                    float b = 0.f;
+                    if (col < p.n)
+                        b = p.bias_is_bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(p.bias)[col])
+                                           : static_cast<const float*>(p.bias)[col];
+                    bias_tile[i] = b;
+                }
+            }
+            mbar_wait(&tmem_full[as], (tile_it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + as * BN + (static_cast<uint32_t>(quad * 32) << 16);
+            const int out_row0 = (direct ? 0 : w.split * p.partial_rows) + m0;
+            // The staging buffer is two [128 rows x 128 B] boxes: 128 bf16 columns or 64 fp32 columns per round.
+            const int cols_per_round = p.c_is_f32 ? 64 : 128;
+            const int rounds = BN / cols_per_round;
+#pragma unroll 1
+            for (int rd = 0; rd < rounds; ++rd) {
+                if (et == 0) tma_store_wait_read();                            // staging free again?
+                asm volatile("bar.sync 1, %0;" :: "n"(EPI_THREADS) : "memory");
+                const int col_in_tile = rd * cols_per_round;
+#pragma unroll 1
+                for (int g = 0; g < cols_per_round / 32; ++g) {                // 32 columns per TMEM load
+                    uint32_t r[32];
+                    tmem_ld_32x32(t_row + col_in_tile + g * 32, r);
+                    tmem_ld_wait();
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        v[i] = __uint_as_float(r[i]);
+                        if (direct && p.has_bias) v[i] += bias_tile[col_in_tile + g * 32 + i];
+                    }
+                    if (p.c_is_f32) {
+                        // box g: [128 rows x 32 fp32 = 128 B]; 16-byte chunk c of row `row` sits at chunk c ^ (row & 7)
+                        uint8_t* box = epi_base + g * (BM * 128) + row * 128;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            *reinterpret_cast<uint4*>(box + ((c ^ (row & 7)) << 4)) =
+                                make_uint4(__float_as_uint(v[4 * c]), __float_as_uint(v[4 * c + 1]),
+                                           __float_as_uint(v[4 * c + 2]), __float_as_uint(v[4 * c + 3]));
+                    } else {
+                        // box g / 2: [128 rows x 64 bf16 = 128 B]; this load fills chunks (g % 2) * 4 .. + 3
+                        uint8_t* box = epi_base + (g >> 1) * (BM * 128) + row * 128;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const int chunk = (g & 1) * 4 + c;
+                            *reinterpret_cast<uint4*>(box + ((chunk ^ (row & 7)) << 4)) =
+                                make_uint4(Vec<__nv_bfloat16>::pack2(v[8 * c], v[8 * c + 1]),
+                                           Vec<__nv_bfloat16>::pack2(v[8 * c + 2], v[8 * c + 3]),
+                                           Vec<__nv_bfloat16>::pack2(v[8 * c + 4], v[8 * c + 5]),
+                                           Vec<__nv_bfloat16>::pack2(v[8 * c + 6], v[8 * c + 7]));
+                        }
+                    }
+                }
+                if (rd == rounds - 1) {                                        // all TMEM reads of this tile done
+                    tc_fence_before();
+                    mbar_arrive(&tmem_empty[as]);
+                }
+                fence_proxy_async();                                           // smem writes -> visible to TMA
+                asm volatile("bar.sync 1, %0;" :: "n"(EPI_THREADS) : "memory");
+                if (et == 0) {
+                    const int col0 = n0 + col_in_tile;
+                    const int box_cols = p.c_is_f32 ? 32 : 64;
+#pragma unroll
+                    for (int g = 0; g < 2; ++g)
+                        if (col0 + g * box_cols < p.n)
+                            tma_store_2d(&map_c, epi_base + g * (BM * 128), col0 + g * box_cols, out_row0);
+                    tma_store_commit();
+                }
+            }
+        }
+        if (et == 0) tma_store_wait_all();
+    }
+
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
+                     :: "r"(tmem_base), "r"(static_cast<uint32_t>(C::TMEM_COLS)) : "memory");
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeFn encode_fn() {
+    static EncodeFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeFn>(sym);
+    });
+    return fn;
+}
+
+// 2-D row-major tensor [rows, cols] with leading dimension ld (elements); box = [box_rows, box_cols],
+// box_cols * elem_bytes == 128 (one swizzle atom).
+static bool make_map(CUtensorMap* map, const void* ptr, CUtensorMapDataType dt, int es, long long rows, long long cols,
+                     long long ld, int box_rows, int box_cols) {
+    EncodeFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * es};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) ==
+           CUDA_SUCCESS;
+}
+
+struct Plan { bool ok; int bn, tiles_m, tiles_n, splits, kb_per_split, kb_total; };
+
+static Plan make_plan(const aecf_gemm_desc* d) {
+    Plan pl{};
+    pl.ok = false;
+    if (d->dtype_a != AECF_BF16 || d->dtype_b != AECF_BF16 || d->accumulate) return pl;
+    if (d->m < 128 || d->n < 128 || d->k < 64) return pl;                 // GEMV-shaped / tiny: SIMT kernel
+    if (d->m > 0x7fffffffLL || d->n > 0x7fffffffLL || d->k > 0x7fffffffLL) return pl;
+    if ((d->lda * 2) % 16 != 0 || (d->ldb * 2) % 16 != 0) return pl;
+    const int ces = d->dtype_c == AECF_BF16 ? 2 : 4;
+    if ((d->ldc * ces) % 16 != 0) return pl;
+    pl.bn = d->n >= 256 ? 256 : 128;
+    pl.tiles_m = static_cast<int>((d->m + tc::BM - 1) / tc::BM);
+    pl.tiles_n = static_cast<int>((d->n + pl.bn - 1) / pl.bn);
+    pl.kb_total = static_cast<int>((d->k + tc::BK - 1) / tc::BK);
+    const int sms = sm_count(d->device);
+    const long long tiles = static_cast<long long>(pl.tiles_m) * pl.tiles_n;
+    int splits = 1;
+    if (tiles * 2 <= sms && pl.kb_total >= 16) {       // weight-gradient shape: few tiles, long reduction
+        splits = static_cast<int>(sms / tiles);
+        const int by_k = pl.kb_total / 8;
+        if (splits > by_k) splits = by_k;
+        if (splits < 1) splits = 1;
+    }
+    pl.kb_per_split = (pl.kb_total + splits - 1) / splits;
+    pl.splits = (pl.kb_total + pl.kb_per_split - 1) / pl.kb_per_split;
+    pl.ok = true;
+    return pl;
+}
+
+}  // namespace tc
+
+size_t gemm_tcgen05_workspace_bytes(const aecf_gemm_desc* d) {
+    const tc::Plan pl = tc::make_plan(d);
+    if (!pl.ok || pl.splits == 1) return 0;
+    return static_cast<size_t>(pl.splits) * pl.tiles_m * tc::BM * d->n * sizeof(float);
+}
+
+int gemm_tcgen05(const aecf_gemm_desc* d, const void* A, const void* B, const void* bias, void* C, void* workspace,
+                 size_t workspace_bytes, cudaStream_t s) {
+    using namespace tc;
+    const Plan pl = make_plan(d);
+    if (!pl.ok) return AECF_ERR_UNSUPPORTED;
+    if (!aligned16(A) || !aligned16(B) || !aligned16(C)) return AECF_ERR_UNSUPPORTED;
+    if (pl.splits > 1) {
+        if (!workspace || workspace_bytes < gemm_tcgen05_workspace_bytes(d)) return AECF_ERR_WORKSPACE;
+        if (!aligned16(workspace) || (d->n * 4) % 16 != 0) return AECF_ERR_UNSUPPORTED;
+    }
+    CUtensorMap map_a, map_b, map_c;
+    bool ok = true;
+    // A: K-major [m, k] -> box [BM rows, 64 k];  MN-major stored [k, m] -> box [64 k rows, 64 m]
+    if (d->a_layout == AECF_K_MAJOR) ok &= make_map(&map_a, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->m, d->k, d->lda, BM, BK);
+    else ok &= make_map(&map_a, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->k, d->m, d->lda, BK, 64);
+    if (d->b_layout == AECF_K_MAJOR) ok &= make_map(&map_b, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->n, d->k, d->ldb, pl.bn, BK);
+    else ok &= make_map(&map_b, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->k, d->n, d->ldb, BK, 64);
+    const bool partial = pl.splits > 1;
+    const bool c_f32 = partial || d->dtype_c == AECF_F32;
+    if (partial) ok &= make_map(&map_c, workspace, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, static_cast<long long>(pl.splits) * pl.tiles_m * BM, d->n, d->n, BM, 32);
+    else if (c_f32) ok &= make_map(&map_c, C, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d->m, d->n, d->ldc, BM, 32);
+    else ok &= make_map(&map_c, C, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->m, d->n, d->ldc, BM, 64);
+    if (!ok) return AECF_ERR_UNSUPPORTED;
+
+    Params p{};
+    p.m = static_cast<int>(d->m); p.n = static_cast<int>(d->n); p.k = static_cast<int>(d->k);
+    p.tiles_m = pl.tiles_m; p.tiles_n = pl.tiles_n; p.splits = pl.splits;
+    p.kb_per_split = pl.kb_per_split; p.kb_total = pl.kb_total;
+    p.a_mn_major = d->a_layout == AECF_MN_MAJOR; p.b_mn_major = d->b_layout == AECF_MN_MAJOR;
+    p.c_is_f32 = c_f32;
+    p.has_bias = bias != nullptr; p.bias_is_bf16 = d->dtype_bias == AECF_BF16; p.bias = bias;
+    p.partial_rows = pl.tiles_m * BM;              // padded: a ragged last row block must not spill into the next split
+
+    const long long items = static_cast<long long>(pl.tiles_m) * pl.tiles_n * pl.splits;
+    const int sms = sm_count(d->device);
+    const int grid = static_cast<int>(items < sms ? items : sms);
+    if (pl.bn == 256) {
+        AECF_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM_BYTES));
+        gemm_tcgen05_kernel<256><<<grid, NUM_THREADS, Cfg<256>::SMEM_BYTES, s>>>(map_a, map_b, map_c, p);
+    } else {
+        AECF_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM_BYTES));
+        gemm_tcgen05_kernel<128><<<grid, NUM_THREADS, Cfg<128>::SMEM_BYTES, s>>>(map_a, map_b, map_c, p);
+    }
+    count_launch();
+    AECF_CUDA_OK(cudaGetLastError());
+    if (!partial) return AECF_OK;
+    GemmEpilogue ep = make_epilogue(d, bias, C);
+    return launch_splitk_reduce(static_cast<const float*>(workspace), d->m, d->n, pl.splits,
+                                static_cast<long long>(pl.tiles_m) * BM * d->n, ep, s);
+}
+
 }  // namespace aecf

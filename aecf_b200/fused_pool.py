@@ -95,9 +95,10 @@ class FusedPoolFunction(torch.autograd.Function):
         ctx.save_for_backward(q_src, key, value, in_w, out_w, qp, kv, attn, score_bias)
         if bits is None:
             bits = torch.empty(0, dtype=torch.uint8, device=dev)
-        ctx.mark_non_differentiable(mask_rate, masked, bits)
-        if cfg.masking != 2:
-            ctx.mark_non_differentiable(entropy)        # detached in training mode (reference :278)
+        if cfg.masking != 2:                            # entropy is detached in training mode (reference :278)
+            ctx.mark_non_differentiable(mask_rate, masked, bits, entropy)
+        else:
+            ctx.mark_non_differentiable(mask_rate, masked, bits)
         return out, pooled, entropy, mask_rate, masked, bits
 
     @staticmethod

@@ -234,6 +234,7 @@ def test_headline_shape_properties_and_determinism():
     for t in (o1, gx1, gw1, gq1):
         assert torch.isfinite(t.float()).all()
     # mask statistics: with flat attention keep_prob ~ 0.85 per token
+    assert not i1["mask_rate"].requires_grad and not i1["entropy"].requires_grad
     assert abs(float(i1["mask_rate"].mean()) - 0.15) < 0.01
 
 
@@ -423,7 +424,7 @@ def test_gemm_layouts(impl, dtype, shape):
         for b_lay, b_mem in ((_lib.K_MAJOR, b), (_lib.MN_MAJOR, b.t().contiguous())):
             for use_bias in (False, True):
                 out = ops.gemm(a_mem, b_mem, m=m, n=n, k=k, a_layout=a_lay, b_layout=b_lay,
-                               lda=a_mem.stride(0), ldb=b_mem.stride(0), bias=bias if use_bias else None,
+                               lda=a_mem.shape[1], ldb=b_mem.shape[1], bias=bias if use_bias else None,
                                out_dtype=torch.float32, impl=impl)
                 ref = want + (bias.double() if use_bias else 0.0)
                 assert_close(f"gemm a_layout={a_lay} b_layout={b_lay} bias={use_bias}", out.cpu(), ref.cpu(), tol)
