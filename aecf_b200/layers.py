@@ -34,17 +34,31 @@ __all__ = ["CurriculumMasking", "MultimodalAttentionPool", "multimodal_attention
 # takes the next offset, so a run is reproducible after seeding, like the reference's torch RNG use.
 # ---------------------------------------------------------------------------------------------
 class _PhiloxState:
+    """Hands out one (seed, call offset) pair per forward that draws random numbers.
+
+    On a CUDA device the pair comes from torch's own Philox generator for that device -- the seed
+    set by ``torch.manual_seed`` and the generator's running offset, which is advanced like any torch
+    random op would -- so re-seeding restarts the stream exactly as it does for the reference's
+    ``torch.bernoulli`` / dropout draws.  ``set_rng_state`` pins an explicit pair instead (parity tests).
+    """
+
     def __init__(self):
         self.lock = threading.Lock()
         self.explicit_seed: Optional[int] = None
         self.seen_seed: Optional[int] = None
         self.offset = 0
 
-    def next(self) -> Tuple[int, int]:
+    def next(self, device: Optional[torch.device] = None) -> Tuple[int, int]:
         with self.lock:
+            if self.explicit_seed is None and device is not None and device.type == "cuda":
+                gen = torch.cuda.default_generators[device.index if device.index is not None
+                                                    else torch.cuda.current_device()]
+                off = gen.get_offset()
+                gen.set_offset(off + 4)                          # one Philox block, like a torch random op
+                return gen.initial_seed() & 0xFFFFFFFFFFFFFFFF, (off // 4) & 0xFFFFFFFF
             seed = self.explicit_seed if self.explicit_seed is not None else torch.initial_seed()
             if self.explicit_seed is None and seed != self.seen_seed:
-                self.seen_seed, self.offset = seed, 0            # torch.manual_seed() was called again
+                self.seen_seed, self.offset = seed, 0
             off = self.offset
             self.offset = (self.offset + 1) & 0xFFFFFFFF
             return seed & 0xFFFFFFFFFFFFFFFF, off
@@ -112,7 +126,7 @@ class CurriculumMasking(nn.Module):
             zeros = torch.zeros(lead, device=weights.device, dtype=weights.dtype)
             return weights, {"entropy": zeros, "mask_rate": zeros.clone(), "target_entropy": zeros.clone()}
         self._last_seq_len = length                                       # :187
-        seed, offset = _rng.next()
+        seed, offset = _rng.next(weights.device)
         w2 = weights.detach().reshape(-1, length).to(torch.float32).contiguous()
         masked, entropy, mask_rate = ops.curriculum_mask(
             w2, 1, base_mask_prob=self.base_mask_prob, min_active=self.min_active, seed=seed, offset=offset)
@@ -306,7 +320,7 @@ class MultimodalAttentionPool(nn.Module):
             if cm.training and tokens > 1:
                 cm._last_seq_len = tokens                               # reference :187
         draws = (att.training and att.dropout > 0.0) or masking == 1
-        seed, offset = _rng.next() if draws else (0, 0)
+        seed, offset = _rng.next(key.device) if draws else (0, 0)
         cfg = PoolConfig(
             num_heads=self.num_heads, dropout_p=att.dropout, training=att.training, masking=masking,
             base_mask_prob=cm.base_mask_prob if fused_cm else 0.15,

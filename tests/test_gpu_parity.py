@@ -238,6 +238,22 @@ def test_headline_shape_properties_and_determinism():
     assert abs(float(i1["mask_rate"].mean()) - 0.15) < 0.01
 
 
+def test_torch_manual_seed_reproduces_masks():
+    """Without set_rng_state the Philox (seed, offset) follow torch's CUDA generator: re-seeding replays
+    the same masks, the next call draws new ones."""
+    q, pool, x = _headline(B=4096)
+    pool._want_mask_bits = True
+
+    def masks():
+        return pool(q.expand(x.shape[0], -1, -1), x, return_info=True)[1]["mask_bits"].clone()
+
+    torch.manual_seed(11)
+    a1, a2 = masks(), masks()
+    torch.manual_seed(11)
+    b1 = masks()
+    assert torch.equal(a1, b1) and not torch.equal(a1, a2)
+
+
 def test_batch_sharding_reproduces_masks_and_sums_gradients():
     """Rows are independent and Philox is keyed on the GLOBAL row: two half-batches with
     row_offset = 0 / B/2 give the full-batch outputs and masks bit for bit, and parameter gradients
