@@ -37,19 +37,29 @@ int sm_count(int device) {
 
 constexpr int POOL_BWD_MAX_BLOCKS = 2048;
 
-// Sum the per-block partials in block order: d_q[D] (scaled) and d_bias_kv[2D] = [dbk | dbv].
-__global__ void pool_bwd_finalize_kernel(const float* __restrict__ partials, int blocks, int D, float scale,
-                                         int q_shared, float* __restrict__ d_q, float* __restrict__ d_bias_kv) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 3 * D) return;
+// Sum the per-block partials: d_q[D] (scaled) and d_bias_kv[2D] = [dbk | dbv].  Block (32 columns x 8
+// lanes): lane y sums partials y, y+8, ... in order, the 8 lane sums are folded in order -> deterministic.
+__global__ void __launch_bounds__(256)
+pool_bwd_finalize_kernel(const float* __restrict__ partials, int blocks, int D, float scale, int q_shared,
+                         float* __restrict__ d_q, float* __restrict__ d_bias_kv) {
+    __shared__ float red[8][33];
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + x;
     float s = 0.f;
-    for (int b = 0; b < blocks; ++b) s += partials[static_cast<size_t>(b) * 3 * D + i];
+    if (i < 3 * D) {
+#pragma unroll 4
+        for (int b = y; b < blocks; b += 8) s += partials[static_cast<size_t>(b) * 3 * D + i];
+    }
+    red[y][x] = s;
+    __syncthreads();
+    if (y != 0 || i >= 3 * D) return;
+    s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][x];
     const int which = i / D, d = i - which * D;
     if (which == 0) { if (q_shared && d_q) d_q[d] = s * scale; }
     else if (d_bias_kv) d_bias_kv[(which == 1 ? D : 0) + d] = s;
 }
-
-
 
 struct PoolPlan {
     PoolParams p;
@@ -200,7 +210,7 @@ int aecf_pool_bwd(const aecf_pool_desc* desc, const void* q, const void* kv, con
                        : launch_pool_bwd<float, false>(plan.M, plan.J, p, grid, stream);
     if (rc != AECF_OK) return rc;
     const int n = 3 * p.D;
-    pool_bwd_finalize_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    pool_bwd_finalize_kernel<<<(n + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         p.partials, grid, p.D, p.scale, p.q_shared, p.q_shared ? static_cast<float*>(d_q) : nullptr, d_bias_kv);
     count_launch();
     AECF_CUDA_OK(cudaGetLastError());

@@ -93,7 +93,7 @@ int launch_splitk_reduce(const float* partial, long long M, long long N, int spl
 
 static int simt_splits(const aecf_gemm_desc* d) {
     const long long tiles = ((d->m + SBM - 1) / SBM) * ((d->n + SBN - 1) / SBN);
-    if (tiles >= 148 || d->k < 2048) return 1;
+    if (d->m == 1 || tiles >= 148 || d->k < 2048) return 1;
     long long s = (2 * 148 + tiles - 1) / tiles;
     const long long by_k = d->k / 512;
     if (s > by_k) s = by_k;
@@ -121,9 +121,68 @@ static int launch_simt(const aecf_gemm_desc* d, const void* A, const void* B, Ge
     return AECF_OK;
 }
 
+// ---- single-row products (the shared fusion query and its gradient): out[n] = sum_k a[k] B(n, k) -----
+// B K-major: one warp per output, lanes stride k.  B MN-major: 32 outputs x 8 k-lanes per block.
+template <typename TA, typename TB>
+__global__ void __launch_bounds__(256)
+gemv_kmajor_kernel(const TA* __restrict__ a, long long a_stride, const TB* __restrict__ B, long long N, long long K,
+                   long long ldb, GemmEpilogue ep) {
+    const long long n = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    if (n >= N) return;
+    const int lane = threadIdx.x & 31;
+    float acc = 0.f;
+    for (long long k = lane; k < K; k += 32) acc = fmaf(load_elem(a + k * a_stride), load_elem(B + n * ldb + k), acc);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(FULL_MASK, acc, off);
+    if (lane == 0) ep.store(0, n, acc, 0, 1, N);
+}
+
+template <typename TA, typename TB>
+__global__ void __launch_bounds__(256)
+gemv_mnmajor_kernel(const TA* __restrict__ a, long long a_stride, const TB* __restrict__ B, long long N, long long K,
+                    long long ldb, GemmEpilogue ep) {
+    __shared__ float red[8][33];
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const long long n = static_cast<long long>(blockIdx.x) * 32 + x;
+    float acc = 0.f;
+    if (n < N) {
+#pragma unroll 4
+        for (long long k = y; k < K; k += 8) acc = fmaf(load_elem(a + k * a_stride), load_elem(B + k * ldb + n), acc);
+    }
+    red[y][x] = acc;
+    __syncthreads();
+    if (y == 0 && n < N) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += red[i][x];
+        ep.store(0, n, s, 0, 1, N);
+    }
+}
+
+template <typename TA, typename TB>
+static int launch_gemv(const aecf_gemm_desc* d, const void* A, const void* B, const GemmEpilogue& ep, cudaStream_t s) {
+    const TA* a = static_cast<const TA*>(A);
+    const TB* b = static_cast<const TB*>(B);
+    const long long a_stride = d->a_layout == AECF_K_MAJOR ? 1 : d->lda;
+    if (d->b_layout == AECF_K_MAJOR)
+        gemv_kmajor_kernel<TA, TB><<<static_cast<unsigned>((d->n + 7) / 8), 256, 0, s>>>(a, a_stride, b, d->n, d->k, d->ldb, ep);
+    else
+        gemv_mnmajor_kernel<TA, TB><<<static_cast<unsigned>((d->n + 31) / 32), 256, 0, s>>>(a, a_stride, b, d->n, d->k, d->ldb, ep);
+    count_launch();
+    AECF_CUDA_OK(cudaGetLastError());
+    return AECF_OK;
+}
+
 static int gemm_simt(const aecf_gemm_desc* d, const void* A, const void* B, const void* bias, void* C,
                      void* workspace, size_t workspace_bytes, cudaStream_t s) {
     GemmEpilogue ep = make_epilogue(d, bias, C);
+    const bool a16 = d->dtype_a == AECF_BF16, b16 = d->dtype_b == AECF_BF16;
+    if (d->m == 1) {
+        if (a16 && b16) return launch_gemv<__nv_bfloat16, __nv_bfloat16>(d, A, B, ep, s);
+        if (a16) return launch_gemv<__nv_bfloat16, float>(d, A, B, ep, s);
+        if (b16) return launch_gemv<float, __nv_bfloat16>(d, A, B, ep, s);
+        return launch_gemv<float, float>(d, A, B, ep, s);
+    }
     const int splits = simt_splits(d);
     if (splits > 1) {
         if (workspace == nullptr || workspace_bytes < static_cast<size_t>(splits) * d->m * d->n * sizeof(float))
@@ -131,7 +190,6 @@ static int gemm_simt(const aecf_gemm_desc* d, const void* A, const void* B, cons
         ep.partial = static_cast<float*>(workspace);
     }
     int rc;
-    const bool a16 = d->dtype_a == AECF_BF16, b16 = d->dtype_b == AECF_BF16;
     if (a16 && b16) rc = launch_simt<__nv_bfloat16, __nv_bfloat16>(d, A, B, ep, splits, s);
     else if (a16) rc = launch_simt<__nv_bfloat16, float>(d, A, B, ep, splits, s);
     else if (b16) rc = launch_simt<float, __nv_bfloat16>(d, A, B, ep, splits, s);

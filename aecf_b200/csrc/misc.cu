@@ -26,7 +26,21 @@ colsum_stage1(const T* __restrict__ x, long long rows, long long cols, long long
 #pragma unroll
     for (int v = 0; v < V; ++v) acc[v] = 0.f;
     if (col0 < cols) {
-        for (long long r = r0 + threadIdx.y; r < r1; r += COLSUM_ROW_LANES) {
+        constexpr int U = 8;                               // independent 16-byte loads in flight per thread
+        long long r = r0 + threadIdx.y;
+        for (; r + (U - 1) * COLSUM_ROW_LANES < r1; r += U * COLSUM_ROW_LANES) {
+            uint4 raw[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) raw[u] = ldg_stream(x + (r + u * COLSUM_ROW_LANES) * ld + col0);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                float f[V];
+                Vec<T>::unpack(raw[u], f);
+#pragma unroll
+                for (int v = 0; v < V; ++v) acc[v] += f[v];
+            }
+        }
+        for (; r < r1; r += COLSUM_ROW_LANES) {
             float f[V];
             Vec<T>::unpack(ldg_stream(x + r * ld + col0), f);
 #pragma unroll
@@ -74,10 +88,20 @@ __global__ void __launch_bounds__(1024) entropy_loss_fwd_kernel(const float* __r
                                                                 float* __restrict__ loss) {
     __shared__ float warp_sum[32];
     float acc = 0.f;
-    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-        bool fin;
-        const float d = scrub_entropy(e[i], &fin) - target;
-        acc = fmaf(d, d, acc);
+    constexpr int U = 8;                                   // independent loads in flight per thread
+    for (long long i0 = threadIdx.x; i0 < n; i0 += static_cast<long long>(blockDim.x) * U) {
+        float v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + static_cast<long long>(u) * blockDim.x;
+            v[u] = (i < n) ? e[i] : target;                // out of range: contributes (target - target)^2 = 0
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            bool fin;
+            const float d = scrub_entropy(v[u], &fin) - target;
+            acc = fmaf(d, d, acc);
+        }
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(FULL_MASK, acc, off);

@@ -33,9 +33,10 @@ pool_bwd_kernel(const PoolParams p) {
     using Smem = BwdSmem<J, Core::V>;
     constexpr int V = Core::V;
     constexpr int Q4 = V / 4;
-    // Keep the raw K chunks in registers between the score pass and the dq pass when they are few;
-    // otherwise the second read goes through L1 (the first one allocates there).
-    constexpr bool KEEP_K = (M * J <= 6);
+    // Every load of a row -- d_ctx, K and (when it fits in registers) V -- is issued before any
+    // arithmetic, so a warp makes one trip to HBM per row.  K is needed again for d_q after the softmax
+    // backward; it is re-read through L1 (the first read allocates there) rather than held in registers.
+    constexpr bool PRELOAD_V = (M * J <= 8);
 
     extern __shared__ __align__(16) float smem[];
     float* xchg = smem;                                               // [POOL_WARPS][M]
@@ -50,8 +51,6 @@ pool_bwd_kernel(const PoolParams p) {
 
     const int slice = warp % p.WPS;
     const int c0 = slice * Core::CPW + lane;
-    const char* kv = static_cast<const char*>(p.kv);
-    char* dkv = static_cast<char*>(p.d_kv);
 
     float qs[J][V];
     if (p.q_shared) Core::load_query(p, 0, c0, qs);
@@ -63,43 +62,48 @@ pool_bwd_kernel(const PoolParams p) {
         const long long row = row_ok ? row_raw : p.B - 1;
         if (!p.q_shared) Core::load_query(p, row, c0, qs);
 
-        // upstream gradient of the context, issued early
+        const size_t row_off = Core::row_offset(p, row, c0);
+        const char* kv_row = static_cast<const char*>(p.kv) + row_off;
+        char* dkv_row = static_cast<char*>(p.d_kv) + row_off;
+        auto valid = [&](int j) { return c0 + 32 * j < p.NC; };
+
+        // upstream gradient of the context and the values, issued first
         uint4 dcraw[J];
         {
-            const char* dc = static_cast<const char*>(p.d_ctx) + static_cast<size_t>(row) * p.D * sizeof(T);
+            const char* dc = static_cast<const char*>(p.d_ctx) + static_cast<size_t>(row) * p.D * sizeof(T)
+                             + static_cast<size_t>(c0) * 16;
 #pragma unroll
-            for (int j = 0; j < J; ++j) {
-                const int c = c0 + 32 * j;
-                dcraw[j] = (c < p.NC) ? ldg_stream(dc + static_cast<size_t>(c) * 16) : make_uint4(0, 0, 0, 0);
-            }
+            for (int j = 0; j < J; ++j) dcraw[j] = valid(j) ? ldg_stream(dc + j * 512) : make_uint4(0, 0, 0, 0);
+        }
+        uint4 vraw[PRELOAD_V ? M : 1][PRELOAD_V ? J : 1];
+        if (PRELOAD_V) {
+#pragma unroll
+            for (int m = 0; m < M; ++m)
+#pragma unroll
+                for (int j = 0; j < J; ++j)
+                    vraw[PRELOAD_V ? m : 0][PRELOAD_V ? j : 0] =
+                        valid(j) ? ldg_stream(kv_row + Core::kv_rel(p, m, 1, j)) : make_uint4(0, 0, 0, 0);
         }
 
-        uint4 kraw[KEEP_K ? M : 1][KEEP_K ? J : 1];
         float w[M][J], wd[M][J];
         unsigned keep;
         Core::attention_weights(
             p, row, c0, qs,
-            [&](int m, int j) {
-                const int c = c0 + 32 * j;
-                const void* src = kv + Core::kv_offset(p, row, m, 0, c);
-                uint4 r = make_uint4(0, 0, 0, 0);
-                if (c < p.NC) r = KEEP_K ? ldg_stream(src) : ldg_cached(src);
-                if (KEEP_K) kraw[KEEP_K ? m : 0][KEEP_K ? j : 0] = r;
-                return r;
-            },
+            [&](int m, int j) { return valid(j) ? ldg_cached(kv_row + Core::kv_rel(p, m, 0, j)) : make_uint4(0, 0, 0, 0); },
             w, wd, keep);
 
         // ---- value pass: d wd = dctx . v ; dV = wd * dctx ; d_bias_v += (sum_m wd) * dctx --------
         float dwd[M][J];
 #pragma unroll
         for (int j = 0; j < J; ++j) {
-            const int c = c0 + 32 * j;
             float dc[V];
             Vec<T>::unpack(dcraw[j], dc);
             uint4 raw[M];
 #pragma unroll
-            for (int m = 0; m < M; ++m)
-                raw[m] = (c < p.NC) ? ldg_stream(kv + Core::kv_offset(p, row, m, 1, c)) : make_uint4(0, 0, 0, 0);
+            for (int m = 0; m < M; ++m) {
+                if (PRELOAD_V) raw[m] = vraw[PRELOAD_V ? m : 0][PRELOAD_V ? j : 0];
+                else raw[m] = valid(j) ? ldg_stream(kv_row + Core::kv_rel(p, m, 1, j)) : make_uint4(0, 0, 0, 0);
+            }
             float sum_wd = 0.f;
 #pragma unroll
             for (int m = 0; m < M; ++m) {
@@ -110,7 +114,7 @@ pool_bwd_kernel(const PoolParams p) {
                 for (int v = 0; v < V; ++v) { a = fmaf(dc[v], f[v], a); dv[v] = wd[m][j] * dc[v]; }
                 dwd[m][j] = a;
                 sum_wd += wd[m][j];
-                if (row_ok && c < p.NC) stg_vec(dkv + Core::kv_offset(p, row, m, 1, c), Vec<T>::pack(dv));
+                if (row_ok && valid(j)) stg_vec(dkv_row + Core::kv_rel(p, m, 1, j), Vec<T>::pack(dv));
             }
             if (row_ok) {
 #pragma unroll
@@ -133,7 +137,10 @@ pool_bwd_kernel(const PoolParams p) {
                 dpw[m] = p.d_pooled ? __ldg(p.d_pooled + static_cast<size_t>(row) * M + m) : 0.f;
             if (p.d_entropy != nullptr) {
                 float pw[M];
-                Core::head_mean(p, c0, warp, lane, wd, xchg, pw);
+                Core::head_sum(p, c0, warp, lane, wd, xchg, pw);
+                const float denom = static_cast<float>(p.H * p.R);
+#pragma unroll
+                for (int m = 0; m < M; ++m) pw[m] = pw[m] / denom;
                 float raw;
                 clamped_entropy<M>(pw, p.log_m, &raw);
                 const bool inside = (raw >= 0.f) && (raw <= p.log_m);
@@ -166,19 +173,16 @@ pool_bwd_kernel(const PoolParams p) {
                 ds[m][j] = w[m][j] * (ds[m][j] - dot);
                 sum_ds += ds[m][j];
             }
-            if (row_ok && (c0 + 32 * j) < p.NC) acc_sds[j * 32 + lane] += sum_ds;
+            if (row_ok && valid(j)) acc_sds[j * 32 + lane] += sum_ds;
         }
 
-        // ---- key pass: dK = ds * (scale * q) ; dq += ds * k --------------------------------
+        // ---- key pass: dK = ds * (scale * q) ; dq += ds * k (K re-read: L1 hit) ------------------
 #pragma unroll
         for (int j = 0; j < J; ++j) {
-            const int c = c0 + 32 * j;
             uint4 raw[M];
 #pragma unroll
-            for (int m = 0; m < M; ++m) {
-                if (KEEP_K) raw[m] = kraw[KEEP_K ? m : 0][KEEP_K ? j : 0];
-                else raw[m] = (c < p.NC) ? ldg_cached(kv + Core::kv_offset(p, row, m, 0, c)) : make_uint4(0, 0, 0, 0);
-            }
+            for (int m = 0; m < M; ++m)
+                raw[m] = valid(j) ? ldg_cached(kv_row + Core::kv_rel(p, m, 0, j)) : make_uint4(0, 0, 0, 0);
             float dq[V];
 #pragma unroll
             for (int v = 0; v < V; ++v) dq[v] = 0.f;
@@ -193,7 +197,7 @@ pool_bwd_kernel(const PoolParams p) {
                     dq[v] = fmaf(ds[m][j], f[v], dq[v]);
                 }
                 sum_ds += ds[m][j];
-                if (row_ok && c < p.NC) stg_vec(dkv + Core::kv_offset(p, row, m, 0, c), Vec<T>::pack(dk));
+                if (row_ok && valid(j)) stg_vec(dkv_row + Core::kv_rel(p, m, 0, j), Vec<T>::pack(dk));
             }
             if (row_ok) {
                 if (p.q_shared) {
@@ -208,9 +212,9 @@ pool_bwd_kernel(const PoolParams p) {
                     float o[V];
 #pragma unroll
                     for (int v = 0; v < V; ++v) o[v] = dq[v] * p.scale;
-                    if (c < p.NC)
+                    if (valid(j))
                         stg_vec(static_cast<char*>(p.d_q) + static_cast<size_t>(row) * p.D * sizeof(T)
-                                    + static_cast<size_t>(c) * 16, Vec<T>::pack(o));
+                                    + static_cast<size_t>(c0) * 16 + j * 512, Vec<T>::pack(o));
 #pragma unroll
                     for (int q4 = 0; q4 < Q4; ++q4) {
                         float4 a = acc_q[(j * Q4 + q4) * 32 + lane];

@@ -52,10 +52,13 @@ struct PoolCore {
     static constexpr int V = Vec<T>::N;
     static constexpr int CPW = 32 * J;               // chunks per warp slice
 
-    // byte offset of chunk c of the K half (half = 0) or V half (half = 1) of token m of `row`
-    static __device__ __forceinline__ size_t kv_offset(const PoolParams& p, long long row, int m, int half, int c) {
-        return (static_cast<size_t>(row) * p.kv_sb + static_cast<size_t>(m) * p.kv_sm
-                + static_cast<size_t>(half) * p.D) * sizeof(T) + static_cast<size_t>(c) * 16;
+    // byte offset of this lane's first chunk (c0) of `row` inside kv / d_kv ...
+    static __device__ __forceinline__ size_t row_offset(const PoolParams& p, long long row, int c0) {
+        return static_cast<size_t>(row) * p.kv_sb * sizeof(T) + static_cast<size_t>(c0) * 16;
+    }
+    // ... and, relative to it, of chunk column j of the K half (half = 0) or V half (half = 1) of token m
+    static __device__ __forceinline__ int kv_rel(const PoolParams& p, int m, int half, int j) {
+        return (m * static_cast<int>(p.kv_sm) + half * p.D) * static_cast<int>(sizeof(T)) + j * 512;
     }
 
     // projected query chunks, pre-multiplied by scale (torch/nn/functional.py:6632)
@@ -122,17 +125,16 @@ struct PoolCore {
         }
     }
 
-    // Head mean of x for the whole sample (torch/nn/functional.py:6657-6659).  `xchg` is a
-    // [POOL_WARPS][M] shared array; contains a __syncthreads() when the sample spans several warps,
-    // so every warp of the CTA must call it.
-    static __device__ __forceinline__ void head_mean(const PoolParams& p, int c0, int warp, int lane,
-                                                     const float (&x)[M][J], float* xchg, float (&mean)[M]) {
-        float part[M];
-        head_sum_partial(p, c0, x, part);
+    // Sum over ALL heads of the sample of x (each head counted R times; divide by H * R for the head
+    // mean of torch/nn/functional.py:6657-6659).  `xchg` is a [POOL_WARPS][M] shared array; contains
+    // __syncthreads() when the sample spans several warps, so every warp of the CTA must call it.
+    static __device__ __forceinline__ void head_sum(const PoolParams& p, int c0, int warp, int lane,
+                                                    const float (&x)[M][J], float* xchg, float (&total)[M]) {
+        head_sum_partial(p, c0, x, total);
         if (p.WPS > 1) {
             if (lane == 0) {
 #pragma unroll
-                for (int m = 0; m < M; ++m) xchg[warp * M + m] = part[m];
+                for (int m = 0; m < M; ++m) xchg[warp * M + m] = total[m];
             }
             __syncthreads();
             const int first = (warp / p.WPS) * p.WPS;
@@ -140,13 +142,10 @@ struct PoolCore {
             for (int m = 0; m < M; ++m) {
                 float t = 0.f;
                 for (int s = 0; s < p.WPS; ++s) t += xchg[(first + s) * M + m];   // fixed order
-                part[m] = t;
+                total[m] = t;
             }
             __syncthreads();                                   // xchg may be reused by the next row
         }
-        const float denom = static_cast<float>(p.H * p.R);     // R copies of each head when G > 32 (R = 2^k: exact)
-#pragma unroll
-        for (int m = 0; m < M; ++m) mean[m] = part[m] / denom;
     }
 
     // Scores -> softmax -> dropout for the heads of this warp's slice.
@@ -192,11 +191,14 @@ struct PoolCore {
             float mx = s[0][j];
 #pragma unroll
             for (int m = 1; m < M; ++m) mx = fmaxf(mx, s[m][j]);
+            // ex2.approx / rcp: ~2^-22 relative, far inside the 1e-5 budget; the masking stage that
+            // decides the mask bits keeps exact IEEE arithmetic (pool_fwd.cuh)
             float sum = 0.f;
 #pragma unroll
-            for (int m = 0; m < M; ++m) { w[m][j] = expf(s[m][j] - mx); sum += w[m][j]; }
+            for (int m = 0; m < M; ++m) { w[m][j] = __expf(s[m][j] - mx); sum += w[m][j]; }
+            const float inv = __frcp_rn(sum);
 #pragma unroll
-            for (int m = 0; m < M; ++m) w[m][j] = w[m][j] / sum;
+            for (int m = 0; m < M; ++m) w[m][j] = w[m][j] * inv;
         }
         keep = 0xffffffffu;
         if (DROP) {

@@ -4,11 +4,88 @@
 //      renormalise, mask_rate).
 // Replaces torch/nn/functional.py:6632-6647, 6657-6659 and reference aecf/AECFLayer.py:130-283.
 // HBM-bound: algorithmic bytes per sample = s*(2*M*D + D) + 4*(2*M + 2)  (SURVEY.md section 8d).
+//
+// Structure.  The data phase is warp-per-sample-slice (pool_core.cuh) and issues every load of
+// the slice before any arithmetic.  The masking stage is a few dozen scalar operations per SAMPLE:
+// run by the warp that owns the sample it would cost a full warp instruction per scalar op, so the
+// warps hand their head sums to shared memory and warp 0 finishes all of the CTA's samples at once,
+// one sample per lane (r1 profile: 1 160 -> ~400 warp instructions per sample).
 #pragma once
 
 #include "pool_core.cuh"
 
 namespace aecf {
+
+// CurriculumMasking.forward for one sample, exact IEEE arithmetic (reference aecf/AECFLayer.py:130-283).
+template <int M>
+__device__ __forceinline__ void masking_stage(const PoolParams& p, long long row, const float (&pw)[M],
+                                              float (&mw)[M], float& entropy, float& mask_rate, unsigned& bits) {
+    entropy = 0.f;
+    mask_rate = 0.f;
+    bits = (1u << M) - 1u;
+#pragma unroll
+    for (int m = 0; m < M; ++m) mw[m] = pw[m];
+    if (!p.masking) return;
+    if (p.masking == 2) {                                             // eval mode, :150-156
+        entropy = clamped_entropy<M>(pw, p.log_m);
+        return;
+    }
+    if (M <= 1) return;                                               // :159-167: zeros, weights unchanged
+    float wn[M];
+    float total = 0.f;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {                                     // :170-176 NaN/Inf scrub
+        wn[m] = (fabsf(pw[m]) <= 3.402823466e38f) ? pw[m] : 0.f;
+        total = __fadd_rn(total, wn[m]);
+    }
+    const bool degenerate = total < 1e-8f;                            // :178 (the _eps buffer)
+#pragma unroll
+    for (int m = 0; m < M; ++m) wn[m] = degenerate ? (1.0f / M) : wn[m] / total;   // :181-184
+    entropy = clamped_entropy<M>(wn, p.log_m);                        // :190
+    const float norm_entropy = fminf(fmaxf(entropy / p.log_m, 0.f), 1.f);          // :192
+    // mul then sub, each rounded (no FMA contraction): the mask threshold must match bit for bit
+    const float keep_prob =
+        fminf(fmaxf(__fsub_rn(1.0f, __fmul_rn(p.base_mask_prob, norm_entropy)), 0.f), 1.f);   // :197-201
+
+    float u[(M + 3) / 4 * 4];
+#pragma unroll
+    for (int blk = 0; blk < (M + 3) / 4; ++blk) {
+        float u4[4];
+        draw4(p.rng, static_cast<unsigned long long>(row), STREAM_MASK, 0u, blk, u4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) u[4 * blk + i] = u4[i];
+    }
+    bits = 0u;
+    int active = 0;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {                                     // :204 bernoulli(keep_prob)
+        const bool k = u[m] <= keep_prob;
+        bits |= k ? (1u << m) : 0u;
+        active += k ? 1 : 0;
+    }
+    const int need = min(p.min_active, M);                            // :207
+    if (active < need) {                                              // :209-260: REPLACE by the top-`need` set
+        bits = 0u;
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+            int rank = 0;                                             // entries that beat i (ties: lower index wins)
+#pragma unroll
+            for (int j = 0; j < M; ++j) rank += (wn[j] > wn[i] || (wn[j] == wn[i] && j < i)) ? 1 : 0;
+            bits |= (rank < need) ? (1u << i) : 0u;
+        }
+        active = need;
+    }
+    float kept_sum = 0.f;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {                                     // :263-264
+        mw[m] = ((bits >> m) & 1u) ? wn[m] : 0.f;
+        kept_sum = __fadd_rn(kept_sum, mw[m]);
+    }
+    const bool valid = kept_sum > 1e-8f;                              // :267
+#pragma unroll
+    for (int m = 0; m < M; ++m) mw[m] = valid ? mw[m] / kept_sum : wn[m];          // :268-272
+    mask_rate = __fsub_rn(1.0f, static_cast<float>(active) / static_cast<float>(M));   // :275
+}
 
 template <typename T, int M, int J, bool DROP>
 __global__ void __launch_bounds__(POOL_WARPS * 32)
@@ -16,18 +93,19 @@ pool_fwd_kernel(const PoolParams p) {
     using Core = PoolCore<T, M, J, DROP>;
     constexpr int V = Core::V;
     __shared__ float xchg[POOL_WARPS * M];
+    __shared__ float head_sums[POOL_WARPS * M];       // [sample slot][m], written by the slice-0 warps
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int slice = warp % p.WPS;
-    const long long row_raw = static_cast<long long>(blockIdx.x) * p.SPC + warp / p.WPS;
-    const bool row_ok = row_raw < p.B;
-    const long long row = row_ok ? row_raw : p.B - 1;   // tail warps recompute the last row, store nothing
+    const int slot = warp / p.WPS;
+    const long long row0 = static_cast<long long>(blockIdx.x) * p.SPC;
+    const bool row_ok = row0 + slot < p.B;
+    const long long row = row_ok ? row0 + slot : p.B - 1;   // tail warps recompute the last row, store nothing
     const int c0 = slice * Core::CPW + lane;
 
-    const char* kv = static_cast<const char*>(p.kv);
+    const char* kv_row = static_cast<const char*>(p.kv) + Core::row_offset(p, row, c0);
     auto load_kv = [&](int m, int half, int j) -> uint4 {
-        const int c = c0 + 32 * j;
-        return (c < p.NC) ? ldg_stream(kv + Core::kv_offset(p, row, m, half, c)) : make_uint4(0, 0, 0, 0);
+        return (c0 + 32 * j < p.NC) ? ldg_stream(kv_row + Core::kv_rel(p, m, half, j)) : make_uint4(0, 0, 0, 0);
     };
 
     // Issue the value loads first when they fit in registers: the whole slice is then in flight
@@ -69,99 +147,43 @@ pool_fwd_kernel(const PoolParams p) {
         }
     }
     if (row_ok) {
-        char* ctx = static_cast<char*>(p.ctx) + static_cast<size_t>(row) * p.D * sizeof(T);
+        char* ctx = static_cast<char*>(p.ctx) + static_cast<size_t>(row) * p.D * sizeof(T) + static_cast<size_t>(c0) * 16;
 #pragma unroll
-        for (int j = 0; j < J; ++j) {
-            const int c = c0 + 32 * j;
-            if (c < p.NC) stg_vec(ctx + static_cast<size_t>(c) * 16, Vec<T>::pack(acc[j]));
-        }
+        for (int j = 0; j < J; ++j)
+            if (c0 + 32 * j < p.NC) stg_vec(ctx + j * 512, Vec<T>::pack(acc[j]));
     }
 
-    // ---- head mean (torch/nn/functional.py:6657-6659) -------------------------------------
-    float pw[M];
-    Core::head_mean(p, c0, warp, lane, wd, xchg, pw);
-    if (!row_ok || slice != 0) return;            // one warp per sample finishes; no barrier follows
-
-    // ---- CurriculumMasking.forward (reference aecf/AECFLayer.py:130-283); every lane computes
-    //      the same few scalars, lanes 0..M-1 write them -------------------------------------
-    float mw[M];
-    float entropy = 0.f, mask_rate = 0.f;
-    unsigned bits = (1u << M) - 1u;
+    // ---- head sums of the post-dropout weights -> shared memory ----------------------------------
+    float total[M];
+    Core::head_sum(p, c0, warp, lane, wd, xchg, total);
+    if (slice == 0 && lane == 0) {
 #pragma unroll
-    for (int m = 0; m < M; ++m) mw[m] = pw[m];
-
-    if (p.masking) {
-        if (p.masking == 2) {                                         // eval mode, :150-156
-            entropy = clamped_entropy<M>(pw, p.log_m);
-        } else if (M > 1) {
-            float wn[M];
-            float total = 0.f;
-#pragma unroll
-            for (int m = 0; m < M; ++m) {                             // :170-176 NaN/Inf scrub
-                wn[m] = (fabsf(pw[m]) <= 3.402823466e38f) ? pw[m] : 0.f;
-                total = __fadd_rn(total, wn[m]);
-            }
-            const bool degenerate = total < 1e-8f;                    // :178 (the _eps buffer)
-#pragma unroll
-            for (int m = 0; m < M; ++m) wn[m] = degenerate ? (1.0f / M) : wn[m] / total;   // :181-184
-            entropy = clamped_entropy<M>(wn, p.log_m);                // :190
-            const float norm_entropy = fminf(fmaxf(entropy / p.log_m, 0.f), 1.f);          // :192
-            // mul then sub, each rounded (no FMA contraction): the mask threshold must match bit for bit
-            const float keep_prob =
-                fminf(fmaxf(__fsub_rn(1.0f, __fmul_rn(p.base_mask_prob, norm_entropy)), 0.f), 1.f);   // :197-201
-
-            float u[(M + 3) / 4 * 4];
-#pragma unroll
-            for (int blk = 0; blk < (M + 3) / 4; ++blk) {
-                float u4[4];
-                draw4(p.rng, static_cast<unsigned long long>(row), STREAM_MASK, 0u, blk, u4);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) u[4 * blk + i] = u4[i];
-            }
-            bits = 0u;
-            int active = 0;
-#pragma unroll
-            for (int m = 0; m < M; ++m) {                             // :204 bernoulli(keep_prob)
-                const bool k = u[m] <= keep_prob;
-                bits |= k ? (1u << m) : 0u;
-                active += k ? 1 : 0;
-            }
-            const int need = min(p.min_active, M);                    // :207
-            if (active < need) {                                      // :209-260: REPLACE by the top-`need` set
-                bits = 0u;
-#pragma unroll
-                for (int i = 0; i < M; ++i) {
-                    int rank = 0;                                     // entries that beat i (ties: lower index wins)
-#pragma unroll
-                    for (int j = 0; j < M; ++j)
-                        rank += (wn[j] > wn[i] || (wn[j] == wn[i] && j < i)) ? 1 : 0;
-                    bits |= (rank < need) ? (1u << i) : 0u;
-                }
-                active = need;
-            }
-            float kept_sum = 0.f;
-#pragma unroll
-            for (int m = 0; m < M; ++m) {                             // :263-264
-                mw[m] = ((bits >> m) & 1u) ? wn[m] : 0.f;
-                kept_sum = __fadd_rn(kept_sum, mw[m]);
-            }
-            const bool valid = kept_sum > 1e-8f;                      // :267
-#pragma unroll
-            for (int m = 0; m < M; ++m) mw[m] = valid ? mw[m] / kept_sum : wn[m];   // :268-272
-            mask_rate = __fsub_rn(1.0f, static_cast<float>(active) / static_cast<float>(M));  // :275
-        }
-        // M <= 1 in training mode: entropy = mask_rate = 0, weights unchanged (:159-167)
+        for (int m = 0; m < M; ++m) head_sums[slot * M + m] = total[m];
     }
+    if (warp != 0) {                                   // hand over and retire; warp 0 finishes the CTA's samples
+        asm volatile("bar.arrive 1, %0;" :: "n"(POOL_WARPS * 32) : "memory");
+        return;
+    }
+    asm volatile("bar.sync 1, %0;" :: "n"(POOL_WARPS * 32) : "memory");
 
-    if (lane < M) {
-        p.pooled[static_cast<size_t>(row) * M + lane] = select<M>(pw, lane);
-        if (p.masked) p.masked[static_cast<size_t>(row) * M + lane] = select<M>(mw, lane);
+    // ---- head mean (torch/nn/functional.py:6657-6659) and CurriculumMasking, one sample per lane -------
+    const long long my_row = row0 + lane;
+    if (lane >= p.SPC || my_row >= p.B) return;
+    const float denom = static_cast<float>(p.H * p.R);     // R copies of each head when G > 32 (R = 2^k: exact)
+    float pw[M], mw[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) pw[m] = head_sums[lane * M + m] / denom;
+    float entropy, mask_rate;
+    unsigned bits;
+    masking_stage<M>(p, my_row, pw, mw, entropy, mask_rate, bits);
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        p.pooled[static_cast<size_t>(my_row) * M + m] = pw[m];
+        if (p.masked) p.masked[static_cast<size_t>(my_row) * M + m] = mw[m];
     }
-    if (lane == 0) {
-        if (p.entropy) p.entropy[row] = entropy;
-        if (p.mask_rate) p.mask_rate[row] = mask_rate;
-        if (p.mask_bits) p.mask_bits[row] = static_cast<uint8_t>(bits);
-    }
+    if (p.entropy) p.entropy[my_row] = entropy;
+    if (p.mask_rate) p.mask_rate[my_row] = mask_rate;
+    if (p.mask_bits) p.mask_bits[my_row] = static_cast<uint8_t>(bits);
 }
 
 }  // namespace aecf

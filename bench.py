@@ -286,9 +286,11 @@ def run_b200(args):
     timer.enabled = True
     with ClockSampler(local) as clocks:
         start.record()
+        t_issue = time.perf_counter()
         for _ in range(args.steps):
             step(x); clear()
         end.record()
+        issue_ms = (time.perf_counter() - t_issue) * 1e3 / args.steps   # host time to enqueue one step
         barrier()
     timer.enabled = False
     ms = start.elapsed_time(end) / args.steps
@@ -383,7 +385,8 @@ def run_b200(args):
             "roofline": roof, "roofline_pool_fwd": hbm("pool_fwd", fwd_bytes),
             "pool_kernels_only": {"value": B / (pool_ms * 1e-3) if pool_ms else None, "unit": UNIT, "ms": pool_ms,
                                   "note": "fused pool fwd+bwd kernels alone, per GPU (the 273 M samples/s target)"},
-            "gemm_tensor_pipe": gemms, "kernels": kernels,
+            "gemm_tensor_pipe": gemms, "kernels": kernels, "host_issue_ms_per_step": issue_ms,
+            "kernel_ms_sum": sum(k["ms"] * k["calls_per_step"] for k in kernels.values()),
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(), "library": _lib.build_info()}
 
     if world == 1 and not args.no_cpu_baseline:
