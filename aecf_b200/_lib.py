@@ -25,6 +25,8 @@ EXPORTS = (
     "aecf_gemm", "aecf_gemm_workspace_bytes",
     "aecf_colsum", "aecf_colsum_workspace_bytes",
     "aecf_entropy_loss_fwd", "aecf_entropy_loss_bwd", "aecf_curriculum_mask", "aecf_entropy_bwd", "aecf_sdpa_fwd",
+    "aecf_fusion_fwd", "aecf_fusion_bwd", "aecf_fusion_workspace_bytes",
+    "aecf_timing_enable", "aecf_timing_collect", "aecf_timing_site_name",
     "aecf_abi_version", "aecf_strerror", "aecf_last_cuda_error", "aecf_launch_count", "aecf_build_info",
 )
 
@@ -51,6 +53,22 @@ class GemmDesc(C.Structure):
         ("m", C.c_int64), ("n", C.c_int64), ("k", C.c_int64),
         ("lda", C.c_int64), ("ldb", C.c_int64), ("ldc", C.c_int64),
     ]
+
+
+class FusionTensors(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "query", "key", "value", "in_proj_weight", "in_proj_bias", "out_proj_weight", "out_proj_bias", "score_bias",
+        "q_proj", "kv", "ctx", "out", "pooled", "entropy", "mask_rate", "masked", "mask_bits")]
+
+
+class FusionGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "d_out", "d_pooled", "d_entropy", "d_ctx", "d_kv", "d_q_rows",
+        "d_key", "d_value", "d_query", "d_in_proj_weight", "d_in_proj_bias", "d_out_proj_weight", "d_out_proj_bias")]
+
+
+BWD_ALL, BWD_OUT_PROJ, BWD_REST = 0, 1, 2
+SITE_COUNT = 16
 
 
 class AecfError(RuntimeError):
@@ -97,6 +115,19 @@ def _declare(lib):
     lib.aecf_entropy_bwd.argtypes = [C.c_int32, f32p, C.c_int64, C.c_int32, f32p, f32p, vp]
     lib.aecf_sdpa_fwd.restype = C.c_int
     lib.aecf_sdpa_fwd.argtypes = [C.c_int32, C.c_int32, vp, vp, vp, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, vp]
+    lib.aecf_fusion_fwd.restype = C.c_int
+    lib.aecf_fusion_fwd.argtypes = [C.POINTER(PoolDesc), C.POINTER(FusionTensors), vp, C.c_size_t, vp]
+    lib.aecf_fusion_bwd.restype = C.c_int
+    lib.aecf_fusion_bwd.argtypes = [C.POINTER(PoolDesc), C.POINTER(FusionTensors), C.POINTER(FusionGrads), C.c_int32,
+                                    vp, C.c_size_t, vp]
+    lib.aecf_fusion_workspace_bytes.restype = C.c_size_t
+    lib.aecf_fusion_workspace_bytes.argtypes = [C.POINTER(PoolDesc)]
+    lib.aecf_timing_enable.restype = C.c_int
+    lib.aecf_timing_enable.argtypes = [C.c_int32]
+    lib.aecf_timing_collect.restype = C.c_int
+    lib.aecf_timing_collect.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int32)]
+    lib.aecf_timing_site_name.restype = C.c_char_p
+    lib.aecf_timing_site_name.argtypes = [C.c_int32]
     lib.aecf_abi_version.restype = C.c_int
     lib.aecf_abi_version.argtypes = []
     lib.aecf_strerror.restype = C.c_char_p
@@ -150,6 +181,19 @@ def launch_count() -> int:
 
 def build_info() -> str:
     return load().aecf_build_info().decode()
+
+
+def timing_enable(on: bool) -> None:
+    check(load().aecf_timing_enable(1 if on else 0), "aecf_timing_enable")
+
+
+def timing_collect() -> dict:
+    """{site name: (total ms, launches)} of the kernels enqueued since timing was enabled; synchronises."""
+    lib = load()
+    ms = (C.c_float * SITE_COUNT)()
+    n = (C.c_int32 * SITE_COUNT)()
+    check(lib.aecf_timing_collect(ms, n), "aecf_timing_collect")
+    return {lib.aecf_timing_site_name(i).decode(): (float(ms[i]), int(n[i])) for i in range(SITE_COUNT) if n[i]}
 
 
 def ptr(t) -> Optional[int]:

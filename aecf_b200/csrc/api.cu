@@ -160,6 +160,7 @@ int aecf_pool_fwd(const aecf_pool_desc* desc, const void* q, const void* kv, con
     p.ctx = ctx; p.pooled = pooled; p.entropy = entropy; p.mask_rate = mask_rate; p.masked = masked;
     p.mask_bits = mask_bits;
     const int grid = static_cast<int>((p.B + p.SPC - 1) / p.SPC);
+    TimedLaunch timed(static_cast<cudaStream_t>(stream));
     if (plan.bf16)
         return plan.drop ? launch_pool_fwd<__nv_bfloat16, true>(plan.M, plan.J, p, grid, stream)
                          : launch_pool_fwd<__nv_bfloat16, false>(plan.M, plan.J, p, grid, stream);
@@ -202,14 +203,18 @@ int aecf_pool_bwd(const aecf_pool_desc* desc, const void* q, const void* kv, con
     int grid = static_cast<int>(want < cap ? want : cap);
     if (grid < 1) grid = 1;
 
-    if (plan.bf16)
-        rc = plan.drop ? launch_pool_bwd<__nv_bfloat16, true>(plan.M, plan.J, p, grid, stream)
-                       : launch_pool_bwd<__nv_bfloat16, false>(plan.M, plan.J, p, grid, stream);
-    else
-        rc = plan.drop ? launch_pool_bwd<float, true>(plan.M, plan.J, p, grid, stream)
-                       : launch_pool_bwd<float, false>(plan.M, plan.J, p, grid, stream);
+    {
+        TimedLaunch timed(static_cast<cudaStream_t>(stream));
+        if (plan.bf16)
+            rc = plan.drop ? launch_pool_bwd<__nv_bfloat16, true>(plan.M, plan.J, p, grid, stream)
+                           : launch_pool_bwd<__nv_bfloat16, false>(plan.M, plan.J, p, grid, stream);
+        else
+            rc = plan.drop ? launch_pool_bwd<float, true>(plan.M, plan.J, p, grid, stream)
+                           : launch_pool_bwd<float, false>(plan.M, plan.J, p, grid, stream);
+    }
     if (rc != AECF_OK) return rc;
     const int n = 3 * p.D;
+    TimedLaunch timed_finalize(static_cast<cudaStream_t>(stream), AECF_SITE_POOL_BWD_FINALIZE);
     pool_bwd_finalize_kernel<<<(n + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         p.partials, grid, p.D, p.scale, p.q_shared, p.q_shared ? static_cast<float*>(d_q) : nullptr, d_bias_kv);
     count_launch();

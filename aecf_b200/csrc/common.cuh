@@ -21,6 +21,21 @@ int set_cuda_error(cudaError_t err, const char* what);   // records and returns 
 int use_device(int device);                               // cudaSetDevice; 0 or AECF_ERR_CUDA
 int sm_count(int device);
 
+// per-kernel timing (timing.cu): the current site is thread-local, set by the whole-step entry points
+int  timing_begin(cudaStream_t s, int site_override = -1);   // returns a record index or -1 when disabled
+void timing_end(int record, cudaStream_t s);
+struct ScopedSite {
+    int previous;
+    explicit ScopedSite(int site);
+    ~ScopedSite();
+};
+struct TimedLaunch {                                          // brackets the launches of one C-ABI call
+    int record;
+    cudaStream_t stream;
+    explicit TimedLaunch(cudaStream_t s, int site_override = -1) : record(timing_begin(s, site_override)), stream(s) {}
+    ~TimedLaunch() { if (record >= 0) timing_end(record, stream); }
+};
+
 #define AECF_CUDA_OK(call)                                              \
     do {                                                                \
         cudaError_t err__ = (call);                                     \

@@ -1,0 +1,271 @@
+// Whole-step entry points: the complete MultimodalAttentionPool forward / backward as one C-ABI call
+// each (include/aecf_b200.h).  They compose the per-kernel entry points in the order the reference's
+// call chain implies (reference aecf/AECFLayer.py:515-541 over torch/nn/functional.py:5847-5865,
+// 6630-6659; backward per SURVEY.md Appendix B), so the host pays one FFI crossing per direction.
+#include "common.cuh"
+
+namespace aecf {
+
+// [d_qp fp32 D | d_bias_kv fp32 2D] -> in_proj_bias gradient [3D] in the parameter dtype
+template <typename T>
+__global__ void pack_in_bias_kernel(const float* __restrict__ d_q, const float* __restrict__ d_bias_kv, int D,
+                                    T* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3 * D) return;
+    out[i] = from_float<T>(i < D ? d_q[i] : d_bias_kv[i - D]);
+}
+
+struct Geometry {
+    long long B, rows;
+    int M, D, es, dt;
+    bool shared;
+};
+
+static int geometry(const aecf_pool_desc* d, Geometry* g) {
+    if (!d || d->batch < 0 || d->embed_dim <= 0 || d->num_tokens <= 0) return AECF_ERR_INVALID;
+    if (d->dtype != AECF_F32 && d->dtype != AECF_BF16) return AECF_ERR_INVALID;
+    g->B = d->batch; g->M = d->num_tokens; g->D = d->embed_dim; g->rows = g->B * g->M;
+    g->dt = d->dtype; g->es = d->dtype == AECF_BF16 ? 2 : 4; g->shared = d->q_is_shared != 0;
+    return AECF_OK;
+}
+
+static const void* at(const void* p, long long elems, int es) {
+    return p ? static_cast<const char*>(p) + elems * es : nullptr;
+}
+static void* at(void* p, long long elems, int es) { return p ? static_cast<char*>(p) + elems * es : nullptr; }
+
+struct Workspace {
+    char* gemm; size_t gemm_bytes;
+    char* pool; size_t pool_bytes;
+    char* colsum; size_t colsum_bytes;
+    float* d_qp;       // [D]
+    float* d_bias_kv;  // [2D]
+    float* d_bq;       // [D] (per-row query)
+    size_t total;
+};
+
+static size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+
+static aecf_gemm_desc gemm_desc(int device, int dta, int dtb, int dtc, int dtbias, int al, int bl, long long m,
+                                long long n, long long k, long long lda, long long ldb, long long ldc) {
+    aecf_gemm_desc g{};
+    g.device = device; g.dtype_a = dta; g.dtype_b = dtb; g.dtype_c = dtc; g.dtype_bias = dtbias;
+    g.a_layout = al; g.b_layout = bl; g.accumulate = 0; g.impl = AECF_GEMM_AUTO;
+    g.m = m; g.n = n; g.k = k; g.lda = lda; g.ldb = ldb; g.ldc = ldc;
+    return g;
+}
+
+// Largest GEMM workspace any product of the step can ask for (split-K partials of the weight gradients).
+static size_t max_gemm_workspace(const aecf_pool_desc* d, const Geometry& g) {
+    const int dt = g.dt, D = g.D;
+    size_t need = 16;
+    const aecf_gemm_desc probes[] = {
+        gemm_desc(d->device, dt, dt, dt, dt, AECF_MN_MAJOR, AECF_MN_MAJOR, 2 * D, D, g.rows, 2 * D, D, D),   // dW_kv
+        gemm_desc(d->device, dt, dt, dt, dt, AECF_MN_MAJOR, AECF_MN_MAJOR, D, D, g.rows, 2 * D, D, D),       // dW_k / dW_v
+        gemm_desc(d->device, dt, dt, dt, dt, AECF_MN_MAJOR, AECF_MN_MAJOR, D, D, g.B, D, D, D),              // dW_o, dW_q
+        gemm_desc(d->device, dt, dt, dt, dt, AECF_K_MAJOR, AECF_K_MAJOR, g.rows, 2 * D, D, D, D, 2 * D),     // kv
+        gemm_desc(d->device, dt, dt, dt, dt, AECF_K_MAJOR, AECF_MN_MAJOR, g.rows, D, 2 * D, 2 * D, D, D),    // dX
+    };
+    for (const aecf_gemm_desc& p : probes) {
+        const size_t w = aecf_gemm_workspace_bytes(&p);
+        if (w > need) need = w;
+    }
+    return need;
+}
+
+static int carve(const aecf_pool_desc* d, const Geometry& g, void* base, Workspace* w) {
+    w->gemm_bytes = align256(max_gemm_workspace(d, g));
+    w->pool_bytes = align256(aecf_pool_bwd_workspace_bytes(d));
+    w->colsum_bytes = align256(aecf_colsum_workspace_bytes(g.B, g.D));
+    size_t off = 0;
+    char* b = static_cast<char*>(base);
+    w->gemm = b + off; off += w->gemm_bytes;
+    w->pool = b + off; off += w->pool_bytes;
+    w->colsum = b + off; off += w->colsum_bytes;
+    w->d_qp = reinterpret_cast<float*>(b + off); off += align256(sizeof(float) * g.D);
+    w->d_bias_kv = reinterpret_cast<float*>(b + off); off += align256(sizeof(float) * 2 * g.D);
+    w->d_bq = reinterpret_cast<float*>(b + off); off += align256(sizeof(float) * g.D);
+    w->total = off;
+    return AECF_OK;
+}
+
+#define AECF_TRY(expr)                   \
+    do {                                 \
+        const int rc__ = (expr);         \
+        if (rc__ != AECF_OK) return rc__; \
+    } while (0)
+
+}  // namespace aecf
+
+using namespace aecf;
+
+extern "C" {
+
+size_t aecf_fusion_workspace_bytes(const aecf_pool_desc* desc) {
+    Geometry g;
+    if (geometry(desc, &g) != AECF_OK) return 0;
+    Workspace w;
+    carve(desc, g, nullptr, &w);
+    return w.total;
+}
+
+int aecf_fusion_fwd(const aecf_pool_desc* desc, const aecf_fusion_tensors* t, void* workspace, size_t workspace_bytes,
+                    void* stream) {
+    Geometry g;
+    AECF_TRY(geometry(desc, &g));
+    if (!t || !t->query || !t->key || !t->in_proj_weight || !t->out_proj_weight || !t->q_proj || !t->kv || !t->ctx ||
+        !t->out || !t->pooled || !workspace)
+        return AECF_ERR_INVALID;
+    if (g.B == 0) return AECF_OK;
+    Workspace w;
+    carve(desc, g, workspace, &w);
+    if (workspace_bytes < w.total) return AECF_ERR_WORKSPACE;
+    const int dt = g.dt, es = g.es, D = g.D, dev = desc->device;
+    const bool bias = t->in_proj_bias != nullptr;
+    const long long DD = static_cast<long long>(D) * D;
+
+    {   // query projection (torch/nn/functional.py:5854); a shared query is projected once, in fp32
+        ScopedSite site(AECF_SITE_Q_PROJ);
+        const aecf_gemm_desc q = g.shared
+            ? gemm_desc(dev, dt, dt, AECF_F32, dt, AECF_K_MAJOR, AECF_K_MAJOR, 1, D, D, D, D, D)
+            : gemm_desc(dev, dt, dt, dt, dt, AECF_K_MAJOR, AECF_K_MAJOR, g.B, D, D, D, D, D);
+        AECF_TRY(aecf_gemm(&q, t->query, t->in_proj_weight, t->in_proj_bias, t->q_proj, w.gemm, w.gemm_bytes, stream));
+    }
+    {   // packed key/value projection (:5855); written straight into [rows, 2D] (no split copy, :5857-5863)
+        ScopedSite site(AECF_SITE_KV_PROJ);
+        if (!t->value) {
+            const aecf_gemm_desc kv = gemm_desc(dev, dt, dt, dt, dt, AECF_K_MAJOR, AECF_K_MAJOR, g.rows, 2 * D, D, D, D, 2 * D);
+            AECF_TRY(aecf_gemm(&kv, t->key, at(t->in_proj_weight, DD, es), bias ? at(t->in_proj_bias, D, es) : nullptr,
+                               t->kv, w.gemm, w.gemm_bytes, stream));
+        } else {
+            const aecf_gemm_desc half = gemm_desc(dev, dt, dt, dt, dt, AECF_K_MAJOR, AECF_K_MAJOR, g.rows, D, D, D, D, 2 * D);
+            AECF_TRY(aecf_gemm(&half, t->key, at(t->in_proj_weight, DD, es), bias ? at(t->in_proj_bias, D, es) : nullptr,
+                               t->kv, w.gemm, w.gemm_bytes, stream));
+            AECF_TRY(aecf_gemm(&half, t->value, at(t->in_proj_weight, 2 * DD, es),
+                               bias ? at(t->in_proj_bias, 2 * D, es) : nullptr, at(t->kv, D, es), w.gemm, w.gemm_bytes, stream));
+        }
+    }
+    {
+        ScopedSite site(AECF_SITE_POOL_FWD);
+        AECF_TRY(aecf_pool_fwd(desc, t->q_proj, t->kv, t->score_bias, t->ctx, t->pooled, t->entropy, t->mask_rate,
+                               t->masked, t->mask_bits, stream));
+    }
+    {   // out projection (:6653)
+        ScopedSite site(AECF_SITE_OUT_PROJ);
+        const aecf_gemm_desc o = gemm_desc(dev, dt, dt, dt, dt, AECF_K_MAJOR, AECF_K_MAJOR, g.B, D, D, D, D, D);
+        AECF_TRY(aecf_gemm(&o, t->ctx, t->out_proj_weight, t->out_proj_bias, t->out, w.gemm, w.gemm_bytes, stream));
+    }
+    return AECF_OK;
+}
+
+int aecf_fusion_bwd(const aecf_pool_desc* desc, const aecf_fusion_tensors* t, const aecf_fusion_grads* gr, int32_t phase,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+    Geometry g;
+    AECF_TRY(geometry(desc, &g));
+    if (!t || !gr || !workspace || phase < AECF_BWD_ALL || phase > AECF_BWD_REST) return AECF_ERR_INVALID;
+    if (!t->query || !t->key || !t->in_proj_weight || !t->out_proj_weight || !t->q_proj || !t->kv || !t->ctx ||
+        !gr->d_out || !gr->d_ctx || !gr->d_kv)
+        return AECF_ERR_INVALID;
+    if (!g.shared && !gr->d_q_rows) return AECF_ERR_INVALID;
+    if (g.B == 0) return AECF_OK;
+    Workspace w;
+    carve(desc, g, workspace, &w);
+    if (workspace_bytes < w.total) return AECF_ERR_WORKSPACE;
+    const int dt = g.dt, es = g.es, D = g.D, dev = desc->device;
+    const long long DD = static_cast<long long>(D) * D;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+
+    if (phase != AECF_BWD_REST) {
+        // ---- out-projection backward: its two parameter gradients are final first -------------------
+        if (gr->d_out_proj_bias) {
+            ScopedSite site(AECF_SITE_D_OUT_BIAS);
+            AECF_TRY(aecf_colsum(dev, dt, dt, gr->d_out, g.B, D, D, gr->d_out_proj_bias, w.colsum, w.colsum_bytes, stream));
+        }
+        if (gr->d_out_proj_weight) {                         // dWo = g^T ctx
+            ScopedSite site(AECF_SITE_D_OUT_WEIGHT);
+            const aecf_gemm_desc d = gemm_desc(dev, dt, dt, dt, dt, AECF_MN_MAJOR, AECF_MN_MAJOR, D, D, g.B, D, D, D);
+            AECF_TRY(aecf_gemm(&d, gr->d_out, t->ctx, nullptr, gr->d_out_proj_weight, w.gemm, w.gemm_bytes, stream));
+        }
+        {                                                    // d_ctx = g Wo
+            ScopedSite site(AECF_SITE_D_CTX);
+            const aecf_gemm_desc d = gemm_desc(dev, dt, dt, dt, dt, AECF_K_MAJOR, AECF_MN_MAJOR, g.B, D, D, D, D, D);
+            AECF_TRY(aecf_gemm(&d, gr->d_out, t->out_proj_weight, nullptr, gr->d_ctx, w.gemm, w.gemm_bytes, stream));
+        }
+        if (phase == AECF_BWD_OUT_PROJ) return AECF_OK;
+    }
+
+    {   // ---- fused recompute backward of the pool ---------------------------------------------------
+        ScopedSite site(AECF_SITE_POOL_BWD);
+        void* dq = g.shared ? static_cast<void*>(w.d_qp) : gr->d_q_rows;
+        AECF_TRY(aecf_pool_bwd(desc, t->q_proj, t->kv, t->score_bias, gr->d_ctx, gr->d_pooled, gr->d_entropy, gr->d_kv, dq,
+                               w.d_bias_kv, w.pool, w.pool_bytes, stream));
+    }
+    {   // ---- input gradients -----------------------------------------------------------------------------
+        ScopedSite site(AECF_SITE_D_X);
+        if (!t->value) {
+            if (gr->d_key) {
+                const aecf_gemm_desc d = gemm_desc(dev, dt, dt, dt, dt, AECF_K_MAJOR, AECF_MN_MAJOR, g.rows, D, 2 * D, 2 * D, D, D);
+                AECF_TRY(aecf_gemm(&d, gr->d_kv, at(t->in_proj_weight, DD, es), nullptr, gr->d_key, w.gemm, w.gemm_bytes, stream));
+            }
+        } else {
+            const aecf_gemm_desc d = gemm_desc(dev, dt, dt, dt, dt, AECF_K_MAJOR, AECF_MN_MAJOR, g.rows, D, D, 2 * D, D, D);
+            if (gr->d_key)
+                AECF_TRY(aecf_gemm(&d, gr->d_kv, at(t->in_proj_weight, DD, es), nullptr, gr->d_key, w.gemm, w.gemm_bytes, stream));
+            if (gr->d_value)
+                AECF_TRY(aecf_gemm(&d, at(gr->d_kv, D, es), at(t->in_proj_weight, 2 * DD, es), nullptr, gr->d_value, w.gemm,
+                                   w.gemm_bytes, stream));
+        }
+    }
+    if (gr->d_in_proj_weight) {   // ---- in-projection weight gradient ---------------------------------------
+        {
+            ScopedSite site(AECF_SITE_D_KV_WEIGHT);
+            if (!t->value) {          // dW_kv = dKV^T X
+                const aecf_gemm_desc d = gemm_desc(dev, dt, dt, dt, dt, AECF_MN_MAJOR, AECF_MN_MAJOR, 2 * D, D, g.rows, 2 * D, D, D);
+                AECF_TRY(aecf_gemm(&d, gr->d_kv, t->key, nullptr, at(gr->d_in_proj_weight, DD, es), w.gemm, w.gemm_bytes, stream));
+            } else {
+                const aecf_gemm_desc d = gemm_desc(dev, dt, dt, dt, dt, AECF_MN_MAJOR, AECF_MN_MAJOR, D, D, g.rows, 2 * D, D, D);
+                AECF_TRY(aecf_gemm(&d, gr->d_kv, t->key, nullptr, at(gr->d_in_proj_weight, DD, es), w.gemm, w.gemm_bytes, stream));
+                AECF_TRY(aecf_gemm(&d, at(gr->d_kv, D, es), t->value, nullptr, at(gr->d_in_proj_weight, 2 * DD, es), w.gemm,
+                                   w.gemm_bytes, stream));
+            }
+        }
+        ScopedSite site(AECF_SITE_D_Q_WEIGHT);
+        if (g.shared) {               // dW_q = d_qp (outer) q0
+            const aecf_gemm_desc d = gemm_desc(dev, AECF_F32, dt, dt, dt, AECF_MN_MAJOR, AECF_MN_MAJOR, D, D, 1, D, D, D);
+            AECF_TRY(aecf_gemm(&d, w.d_qp, t->query, nullptr, gr->d_in_proj_weight, w.gemm, w.gemm_bytes, stream));
+        } else {                      // dW_q = d_q^T Q
+            const aecf_gemm_desc d = gemm_desc(dev, dt, dt, dt, dt, AECF_MN_MAJOR, AECF_MN_MAJOR, D, D, g.B, D, D, D);
+            AECF_TRY(aecf_gemm(&d, gr->d_q_rows, t->query, nullptr, gr->d_in_proj_weight, w.gemm, w.gemm_bytes, stream));
+        }
+    }
+    if (gr->d_query) {                // ---- gradient of the (unprojected) query --------------------------------
+        ScopedSite site(AECF_SITE_D_QUERY);
+        if (g.shared) {
+            const aecf_gemm_desc d = gemm_desc(dev, AECF_F32, dt, dt, dt, AECF_K_MAJOR, AECF_MN_MAJOR, 1, D, D, D, D, D);
+            AECF_TRY(aecf_gemm(&d, w.d_qp, t->in_proj_weight, nullptr, gr->d_query, w.gemm, w.gemm_bytes, stream));
+        } else {
+            const aecf_gemm_desc d = gemm_desc(dev, dt, dt, dt, dt, AECF_K_MAJOR, AECF_MN_MAJOR, g.B, D, D, D, D, D);
+            AECF_TRY(aecf_gemm(&d, gr->d_q_rows, t->in_proj_weight, nullptr, gr->d_query, w.gemm, w.gemm_bytes, stream));
+        }
+    }
+    if (gr->d_in_proj_bias) {         // ---- [d_bq | d_bk | d_bv] in the parameter dtype ------------------------
+        ScopedSite site(AECF_SITE_D_IN_BIAS);
+        const float* dbq = w.d_qp;
+        if (!g.shared) {
+            AECF_TRY(aecf_colsum(dev, dt, AECF_F32, gr->d_q_rows, g.B, D, D, w.d_bq, w.colsum, w.colsum_bytes, stream));
+            dbq = w.d_bq;
+        }
+        TimedLaunch timed(s);
+        const int n = 3 * D;
+        if (dt == AECF_BF16)
+            pack_in_bias_kernel<__nv_bfloat16><<<(n + 255) / 256, 256, 0, s>>>(dbq, w.d_bias_kv, D,
+                                                                              static_cast<__nv_bfloat16*>(gr->d_in_proj_bias));
+        else
+            pack_in_bias_kernel<float><<<(n + 255) / 256, 256, 0, s>>>(dbq, w.d_bias_kv, D, static_cast<float*>(gr->d_in_proj_bias));
+        count_launch();
+        AECF_CUDA_OK(cudaGetLastError());
+    }
+    return AECF_OK;
+}
+
+}  // extern "C"

@@ -237,6 +237,7 @@ int aecf_gemm(const aecf_gemm_desc* d, const void* A, const void* B, const void*
     if (!A || !B || !C) return AECF_ERR_INVALID;
     if ((rc = use_device(d->device)) != AECF_OK) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    TimedLaunch timed(s);
     if (d->impl != AECF_GEMM_SIMT) {
         rc = gemm_tcgen05(d, A, B, bias, C, workspace, workspace_bytes, s);
         if (rc != AECF_ERR_UNSUPPORTED || d->impl == AECF_GEMM_TCGEN05) return rc;

@@ -62,11 +62,22 @@ colsum_stage1(const T* __restrict__ x, long long rows, long long cols, long long
 }
 
 template <typename TO>
-__global__ void colsum_stage2(const float* __restrict__ partial, long long cols, int splits, TO* __restrict__ out) {
-    const long long c = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (c >= cols) return;
+__global__ void __launch_bounds__(256)
+colsum_stage2(const float* __restrict__ partial, long long cols, int splits, TO* __restrict__ out) {
+    __shared__ float red[8][33];                       // 32 columns x 8 lanes; fixed-order folds -> deterministic
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const long long c = static_cast<long long>(blockIdx.x) * 32 + x;
     float s = 0.f;
-    for (int i = 0; i < splits; ++i) s += partial[static_cast<long long>(i) * cols + c];
+    if (c < cols) {
+#pragma unroll 4
+        for (int i = y; i < splits; i += 8) s += partial[static_cast<long long>(i) * cols + c];
+    }
+    red[y][x] = s;
+    __syncthreads();
+    if (y != 0 || c >= cols) return;
+    s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][x];
     out[c] = from_float<TO>(s);
 }
 
@@ -315,6 +326,7 @@ int aecf_colsum(int32_t device, int32_t dtype_x, int32_t dtype_out, const void* 
     int rc = use_device(device);
     if (rc != AECF_OK) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    TimedLaunch timed(s);
     const int splits = colsum_splits(rows);
     const dim3 block(32, COLSUM_ROW_LANES), grid(static_cast<unsigned>((cols / V + 31) / 32), splits);
     float* partial = static_cast<float*>(workspace);
@@ -322,7 +334,7 @@ int aecf_colsum(int32_t device, int32_t dtype_x, int32_t dtype_out, const void* 
         colsum_stage1<__nv_bfloat16><<<grid, block, 0, s>>>(static_cast<const __nv_bfloat16*>(x), rows, cols, ld, splits, partial);
     else
         colsum_stage1<float><<<grid, block, 0, s>>>(static_cast<const float*>(x), rows, cols, ld, splits, partial);
-    const unsigned g2 = static_cast<unsigned>((cols + 255) / 256);
+    const unsigned g2 = static_cast<unsigned>((cols + 31) / 32);
     if (dtype_out == AECF_BF16)
         colsum_stage2<__nv_bfloat16><<<g2, 256, 0, s>>>(partial, cols, splits, static_cast<__nv_bfloat16*>(out));
     else
@@ -336,6 +348,7 @@ int aecf_entropy_loss_fwd(int32_t device, const float* entropy, int64_t n, float
     if (!entropy || !loss || n <= 0) return AECF_ERR_INVALID;
     int rc = use_device(device);
     if (rc != AECF_OK) return rc;
+    TimedLaunch timed(static_cast<cudaStream_t>(stream), AECF_SITE_ENTROPY_LOSS);
     entropy_loss_fwd_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(entropy, n, target, loss);
     count_launch();
     AECF_CUDA_OK(cudaGetLastError());

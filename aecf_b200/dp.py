@@ -80,13 +80,11 @@ class GradientSync:
 
     # -- called from the backward (autograd worker thread) -----------------------------------
     def on_ready(self, name: str, grad: torch.Tensor) -> None:
-        if name not in self.slices or name in self.reported:
-            return
+        if name not in self.slices or name in self.reported or self.world_size == 1:
+            return                                                     # single process: autograd's .grad is final
         self.reported.add(name)
         view = self.bucket[self.slices[name]]
         view.copy_(grad.reshape(-1))                                   # cast to fp32 into the flat bucket
-        if self.world_size == 1:
-            return
         if self.cuda:
             ready = torch.cuda.Event()
             ready.record(torch.cuda.current_stream(self.bucket.device))

@@ -2,10 +2,10 @@
 
 Forward  (reference aecf/AECFLayer.py:515-541 over torch/nn/functional.py:5847-5865, 6630-6659):
     q-proj GEMM -> packed KV GEMM -> fused pool kernel (scores, softmax, dropout, value sum,
-    head mean, curriculum mask) -> out-proj GEMM
+    head mean, curriculum mask) -> out-proj GEMM            [aecf_fusion_fwd, csrc/fusion.cu]
 Backward (autograd of the same lines in the reference):
     colsum + dWo GEMM + dctx GEMM -> fused recompute pool backward -> dX GEMM + dWkv GEMM
-    -> the small query-side products
+    -> the small query-side products                        [aecf_fusion_bwd]
 Nothing the forward computed is kept except the projected K/V and the context.
 """
 from __future__ import annotations
@@ -45,7 +45,11 @@ def _rows(x3d: torch.Tensor) -> torch.Tensor:
 
 
 class FusedPoolFunction(torch.autograd.Function):
-    """out, pooled, entropy, mask_rate, masked, mask_bits = f(query, key, value, params...)."""
+    """out, pooled, entropy, mask_rate, masked, mask_bits = f(query, key, value, params...).
+
+    One C-ABI call for the forward (``aecf_fusion_fwd``), one or two for the backward
+    (``aecf_fusion_bwd``; two phases when a data-parallel hook wants the out-projection gradients early).
+    """
 
     @staticmethod
     def forward(ctx, q_src, key, value, in_w, in_b, out_w, out_b, score_bias, cfg: PoolConfig):
@@ -58,43 +62,36 @@ class FusedPoolFunction(torch.autograd.Function):
         else:
             B, M = key.shape[0], key.shape[1]
             kv_strides = (0, 0)
-        rows = B * M
-        b_q = b_kv = b_k = b_v = None
-        if in_b is not None:
-            b_q, b_kv, b_k, b_v = in_b[:D], in_b[D:], in_b[D:2 * D], in_b[2 * D:]
-
-        # ---- in-projection (torch/nn/functional.py:5847-5865) --------------------------------
-        if cfg.q_shared:
-            # one query for the whole batch: project it once, in fp32
-            qp = ops.linear(q_src.reshape(1, D), in_w[:D], b_q, out_dtype=torch.float32, name="q_proj").reshape(D)
-        else:
-            qp = ops.linear(q_src.reshape(B, D), in_w[:D], b_q, name="q_proj")
-        kv = torch.empty((rows, 2 * D), dtype=dt, device=dev)
-        if value is None:
-            ops.linear(_rows(key), in_w[D:], b_kv, out=kv, name="kv_proj")
-        else:                                   # separate value tensor: two GEMMs into the halves
-            ops.linear(_rows(key), in_w[D:2 * D], b_k, out=kv[:, :D], ldc=2 * D, name="k_proj")
-            ops.linear(_rows(value), in_w[2 * D:], b_v, out=kv[:, D:], ldc=2 * D, name="v_proj")
-
-        # ---- fused pool ------------------------------------------------------------------------
         desc = ops.make_pool_desc(
             dev, dt, batch=B, num_tokens=M, embed_dim=D, num_heads=cfg.num_heads, training=cfg.training,
             masking=cfg.masking, min_active=cfg.min_active, q_is_shared=cfg.q_shared,
             base_mask_prob=cfg.base_mask_prob, entropy_target=cfg.entropy_target, dropout_p=cfg.dropout_p,
             seed=cfg.seed, offset=cfg.offset, row0=cfg.row0, bias_strides=cfg.bias_strides, kv_strides=kv_strides)
-        attn, pooled, entropy, mask_rate, masked, bits = ops.pool_fwd(desc, qp, kv, score_bias, cfg.want_mask_bits)
 
-        # ---- out-projection (:6653) -------------------------------------------------------------
-        out = ops.linear(attn, out_w, out_b, name="out_proj")
+        q_in = q_src.reshape(D) if cfg.q_shared else q_src.reshape(B, D)
+        if not q_in.is_contiguous():
+            q_in = q_in.contiguous()
+        qp = torch.empty((D,), dtype=torch.float32, device=dev) if cfg.q_shared else torch.empty((B, D), dtype=dt, device=dev)
+        kv = torch.empty((B * M, 2 * D), dtype=dt, device=dev)
+        attn = torch.empty((B, D), dtype=dt, device=dev)
+        out = torch.empty((B, D), dtype=dt, device=dev)
+        pooled = torch.empty((B, M), dtype=torch.float32, device=dev)
+        entropy = torch.empty((B,), dtype=torch.float32, device=dev)
+        mask_rate = torch.empty((B,), dtype=torch.float32, device=dev)
+        masked = torch.empty((B, M), dtype=torch.float32, device=dev)
+        bits = torch.empty((B if cfg.want_mask_bits else 0,), dtype=torch.uint8, device=dev)
+        p = _lib.ptr
+        tensors = _lib.FusionTensors(
+            query=p(q_in), key=p(key), value=p(value), in_proj_weight=p(in_w), in_proj_bias=p(in_b),
+            out_proj_weight=p(out_w), out_proj_bias=p(out_b), score_bias=p(score_bias),
+            q_proj=p(qp), kv=p(kv), ctx=p(attn), out=p(out), pooled=p(pooled), entropy=p(entropy),
+            mask_rate=p(mask_rate), masked=p(masked), mask_bits=p(bits) if cfg.want_mask_bits else None)
+        ops.fusion_fwd(desc, tensors, dev)
 
         ctx.cfg, ctx.desc = cfg, desc
-        ctx.has_value = value is not None
-        ctx.has_in_bias, ctx.has_out_bias = in_b is not None, out_b is not None
         ctx.shape = (B, M, D)
         ctx.q_shape = q_src.shape
-        ctx.save_for_backward(q_src, key, value, in_w, out_w, qp, kv, attn, score_bias)
-        if bits is None:
-            bits = torch.empty(0, dtype=torch.uint8, device=dev)
+        ctx.save_for_backward(q_in, key, value, in_w, in_b, out_w, out_b, qp, kv, attn, score_bias)
         if cfg.masking != 2:                            # entropy is detached in training mode (reference :278)
             ctx.mark_non_differentiable(mask_rate, masked, bits, entropy)
         else:
@@ -104,7 +101,7 @@ class FusedPoolFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_out, g_pooled, g_entropy, _g_rate, _g_masked, _g_bits):
         cfg: PoolConfig = ctx.cfg
-        q_src, key, value, in_w, out_w, qp, kv, attn, score_bias = ctx.saved_tensors
+        q_in, key, value, in_w, in_b, out_w, out_b, qp, kv, attn, score_bias = ctx.saved_tensors
         B, M, D = ctx.shape
         dev, dt = key.device, key.dtype
         need_q, need_key, need_value, need_in_w, need_in_b, need_out_w, need_out_b = ctx.needs_input_grad[:7]
@@ -116,72 +113,51 @@ class FusedPoolFunction(torch.autograd.Function):
             g = g_out.reshape(B, D)
             if g.dtype != dt or not g.is_contiguous():
                 g = g.to(dt).contiguous()
-
-        # ---- out-projection backward: its two parameter gradients are ready first ------------
-        d_out_w = d_out_b = None
-        if need_out_b and ctx.has_out_bias:
-            d_out_b = ops.colsum(g, name="d_out_bias")
-            if notify:
-                notify("out_proj.bias", d_out_b)
-        if need_out_w:
-            d_out_w = ops.matmul_tn(g, attn, name="d_out_weight")
-            if notify:
-                notify("out_proj.weight", d_out_w)
-        d_attn = ops.matmul_nn(g, out_w, name="d_ctx")
-
-        # ---- fused recompute backward of the pool -----------------------------------------------
         d_pooled = None
         if g_pooled is not None:
             d_pooled = g_pooled.reshape(B, M).to(torch.float32).contiguous()
         d_entropy = None
         if g_entropy is not None and cfg.masking == 2:
             d_entropy = g_entropy.reshape(B).to(torch.float32).contiguous()
-        d_kv, d_qp, d_bias_kv = ops.pool_bwd(ctx.desc, qp, kv, score_bias, d_attn, d_pooled, d_entropy)
-        d_kv2 = d_kv.reshape(B * M, 2 * D)
 
-        # ---- in-projection backward ----------------------------------------------------------------
-        d_key = d_value = None
-        key2, value2 = _rows(key), (_rows(value) if ctx.has_value else None)
-        if not ctx.has_value:
-            if need_key:
-                d_key = ops.matmul_nn(d_kv2, in_w[D:], name="d_x").reshape(key.shape)
-        else:
-            if need_key:
-                d_key = ops.matmul_nn(d_kv2[:, :D], in_w[D:2 * D], name="d_key").reshape(key.shape)
-            if need_value:
-                d_value = ops.matmul_nn(d_kv2[:, D:], in_w[2 * D:], name="d_value").reshape(value.shape)
+        new = lambda shape, dtype=dt: torch.empty(shape, dtype=dtype, device=dev)
+        d_ctx, d_kv = new((B, D)), new((B * M, 2 * D))
+        d_q_rows = None if cfg.q_shared else new((B, D))
+        d_key = new(key.shape) if need_key else None
+        d_value = new(value.shape) if (value is not None and need_value) else None
+        d_q = new(q_in.shape, q_in.dtype) if need_q else None
+        d_in_w = torch.empty_like(in_w) if need_in_w else None
+        d_in_b = torch.empty_like(in_b) if (need_in_b and in_b is not None) else None
+        d_out_w = torch.empty_like(out_w) if need_out_w else None
+        d_out_b = torch.empty_like(out_b) if (need_out_b and out_b is not None) else None
 
-        d_in_w = d_in_b = d_q = None
-        if need_in_w:
-            d_in_w = torch.empty_like(in_w)
-            if not ctx.has_value:
-                ops.matmul_tn(d_kv2, key2, out=d_in_w[D:], name="d_kv_weight")
-            else:
-                ops.matmul_tn(d_kv2[:, :D], key2, out=d_in_w[D:2 * D], name="d_k_weight")
-                ops.matmul_tn(d_kv2[:, D:], value2, out=d_in_w[2 * D:], name="d_v_weight")
-        if cfg.q_shared:
-            d_qp_row = d_qp.reshape(1, D)                     # fp32, already summed over the batch
-            if need_in_w:     # dWq = d_qp (outer) q0
-                ops.gemm(d_qp_row, q_src.reshape(1, D), m=D, n=D, k=1, a_layout=_lib.MN_MAJOR,
-                         b_layout=_lib.MN_MAJOR, lda=D, ldb=D, out=d_in_w[:D], name="d_q_weight")
-            if need_q:
-                d_q = ops.matmul_nn(d_qp_row, in_w[:D], out_dtype=q_src.dtype, name="d_query").reshape(ctx.q_shape)
-            d_bq = d_qp
+        p = _lib.ptr
+        tensors = _lib.FusionTensors(
+            query=p(q_in), key=p(key), value=p(value), in_proj_weight=p(in_w), in_proj_bias=p(in_b),
+            out_proj_weight=p(out_w), out_proj_bias=p(out_b), score_bias=p(score_bias),
+            q_proj=p(qp), kv=p(kv), ctx=p(attn))
+        grads = _lib.FusionGrads(
+            d_out=p(g), d_pooled=p(d_pooled), d_entropy=p(d_entropy), d_ctx=p(d_ctx), d_kv=p(d_kv), d_q_rows=p(d_q_rows),
+            d_key=p(d_key), d_value=p(d_value), d_query=p(d_q), d_in_proj_weight=p(d_in_w), d_in_proj_bias=p(d_in_b),
+            d_out_proj_weight=p(d_out_w), d_out_proj_bias=p(d_out_b))
+        ws = ops.fusion_workspace(ctx.desc, dev)
+        if notify is None:
+            ops.fusion_bwd(ctx.desc, tensors, grads, _lib.BWD_ALL, ws, dev)
         else:
-            q2 = q_src.reshape(B, D)
-            if need_in_w:
-                ops.matmul_tn(d_qp, q2, out=d_in_w[:D], name="d_q_weight")
-            if need_q:
-                d_q = ops.matmul_nn(d_qp, in_w[:D], name="d_query").reshape(ctx.q_shape)
-            d_bq = ops.colsum(d_qp, out_dtype=torch.float32, name="d_q_bias") if (need_in_b and ctx.has_in_bias) else None
-        if need_in_w and notify:
-            notify("in_proj_weight", d_in_w)
-        if need_in_b and ctx.has_in_bias:
-            d_in_b = torch.empty(3 * D, dtype=in_w.dtype, device=dev)
-            d_in_b[:D].copy_(d_bq)
-            d_in_b[D:].copy_(d_bias_kv)
-            if notify:
+            # the out-projection gradients are final first: hand them to the all-reduce while the pool
+            # backward and the in-projection GEMMs run
+            ops.fusion_bwd(ctx.desc, tensors, grads, _lib.BWD_OUT_PROJ, ws, dev)
+            if d_out_b is not None:
+                notify("out_proj.bias", d_out_b)
+            if d_out_w is not None:
+                notify("out_proj.weight", d_out_w)
+            ops.fusion_bwd(ctx.desc, tensors, grads, _lib.BWD_REST, ws, dev)
+            if d_in_w is not None:
+                notify("in_proj_weight", d_in_w)
+            if d_in_b is not None:
                 notify("in_proj_bias", d_in_b)
+        if d_q is not None:
+            d_q = d_q.reshape(ctx.q_shape)
         return d_q, d_key, d_value, d_in_w, d_in_b, d_out_w, d_out_b, None, None
 
 

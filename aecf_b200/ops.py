@@ -242,3 +242,21 @@ def entropy_bwd(weights2d: torch.Tensor, d_entropy: torch.Tensor) -> torch.Tenso
                                           d_w.data_ptr(), _stream(dev))
     _lib.check(rc, "aecf_entropy_bwd")
     return d_w
+
+
+def fusion_workspace(desc: _lib.PoolDesc, dev: torch.device) -> torch.Tensor:
+    return _workspace(_lib.load().aecf_fusion_workspace_bytes(C.byref(desc)), dev)
+
+
+def fusion_fwd(desc: _lib.PoolDesc, tensors: _lib.FusionTensors, dev: torch.device) -> None:
+    """Whole forward (q/kv projections, fused pool, out projection) in one C-ABI call."""
+    ws = fusion_workspace(desc, dev)
+    rc = _lib.load().aecf_fusion_fwd(C.byref(desc), C.byref(tensors), ws.data_ptr(), ws.numel(), _stream(dev))
+    _lib.check(rc, f"aecf_fusion_fwd B={desc.batch} M={desc.num_tokens} D={desc.embed_dim} H={desc.num_heads}")
+
+
+def fusion_bwd(desc: _lib.PoolDesc, tensors: _lib.FusionTensors, grads: _lib.FusionGrads, phase: int,
+               ws: torch.Tensor, dev: torch.device) -> None:
+    rc = _lib.load().aecf_fusion_bwd(C.byref(desc), C.byref(tensors), C.byref(grads), phase, ws.data_ptr(), ws.numel(),
+                                     _stream(dev))
+    _lib.check(rc, f"aecf_fusion_bwd phase={phase} B={desc.batch} M={desc.num_tokens} D={desc.embed_dim}")

@@ -195,36 +195,9 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # the sm_100a path
 # ------------------------------------------------------------------------------------------------
-class KernelTimer:
-    """ops.profile_hook: CUDA events around every C-ABI call site, on the launching stream."""
-
-    def __init__(self, torch):
-        self.torch, self.records, self.enabled = torch, [], False
-
-    def __call__(self, name):
-        timer = self
-
-        class Ctx:
-            def __enter__(self_inner):
-                if timer.enabled:
-                    self_inner.a = timer.torch.cuda.Event(enable_timing=True)
-                    self_inner.b = timer.torch.cuda.Event(enable_timing=True)
-                    self_inner.a.record()
-                return self_inner
-
-            def __exit__(self_inner, *exc):
-                if timer.enabled:
-                    self_inner.b.record()
-                    timer.records.append((name, self_inner.a, self_inner.b))
-                return False
-        return Ctx()
-
-    def averages(self, steps):
-        tot, cnt = {}, {}
-        for name, a, b in self.records:
-            tot[name] = tot.get(name, 0.0) + a.elapsed_time(b)
-            cnt[name] = cnt.get(name, 0) + 1
-        return {k: {"ms": tot[k] / cnt[k], "calls_per_step": cnt[k] / steps} for k in tot}
+def kernel_averages(sites, steps):
+    """aecf_timing_collect() totals -> {launch site: {ms per launch, launches per step}}."""
+    return {name: {"ms": total / count, "calls_per_step": count / steps} for name, (total, count) in sites.items()}
 
 
 def run_b200(args):
@@ -232,7 +205,7 @@ def run_b200(args):
     import torch.distributed as dist
 
     import aecf_b200
-    from aecf_b200 import _lib, ops
+    from aecf_b200 import _lib
     from aecf_b200.dp import GradientSync
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -274,16 +247,13 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    timer = KernelTimer(torch)
-    ops.profile_hook = timer
-
     # ---- device-resident timing -----------------------------------------------------------
     for _ in range(args.warmup):
         step(x); clear()
     barrier()
     launches0 = _lib.launch_count()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    timer.enabled = True
+    _lib.timing_enable(True)         # CUDA events next to every launch of the library, on the launching stream
     with ClockSampler(local) as clocks:
         start.record()
         t_issue = time.perf_counter()
@@ -292,10 +262,10 @@ def run_b200(args):
         end.record()
         issue_ms = (time.perf_counter() - t_issue) * 1e3 / args.steps   # host time to enqueue one step
         barrier()
-    timer.enabled = False
     ms = start.elapsed_time(end) / args.steps
     launches = (_lib.launch_count() - launches0)
-    kernels = timer.averages(args.steps)
+    kernels = kernel_averages(_lib.timing_collect(), args.steps)
+    _lib.timing_enable(False)
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -177,6 +177,74 @@ AECF_API int aecf_entropy_bwd(int32_t device, const float* weights, int64_t rows
 AECF_API int aecf_sdpa_fwd(int32_t device, int32_t dtype, const void* q, const void* k, const void* v, void* out,
                   int64_t batch, int32_t tgt_len, int32_t src_len, int32_t embed_dim, void* stream);
 
+/* ---- whole-step entry points -------------------------------------------------------------
+ * The complete forward and backward of MultimodalAttentionPool (reference aecf/AECFLayer.py:515-541 and
+ * the autograd graph behind it) as one call each, so the host pays one FFI crossing per direction instead
+ * of one per kernel.  They run exactly the calls above, in order, on `stream`.
+ * All pointers are device pointers; nullable ones are marked.  `dtype` of the descriptor is the type of
+ * every tensor not marked fp32. */
+typedef struct aecf_fusion_tensors {
+    /* inputs */
+    const void*  query;            /* q_is_shared ? [D] : [B, D] */
+    const void*  key;              /* [B*M, D]; rows ordered like kv (b-major, or m-major when kv_stride_* say so) */
+    const void*  value;            /* nullable: separate value tensor, same layout as key */
+    const void*  in_proj_weight;   /* [3D, D] */
+    const void*  in_proj_bias;     /* [3D], nullable */
+    const void*  out_proj_weight;  /* [D, D] */
+    const void*  out_proj_bias;    /* [D], nullable */
+    const float* score_bias;       /* nullable, see aecf_pool_fwd */
+    /* forward results that the backward reads again (the caller keeps them alive) */
+    void*  q_proj;                 /* q_is_shared ? [D] fp32 : [B, D] */
+    void*  kv;                     /* [B*M, 2D] */
+    void*  ctx;                    /* [B, D] */
+    /* forward outputs */
+    void*    out;                  /* [B, D] */
+    float*   pooled;               /* [B, M] fp32 */
+    float*   entropy;              /* [B] fp32, nullable */
+    float*   mask_rate;            /* [B] fp32, nullable */
+    float*   masked;               /* [B, M] fp32, nullable */
+    uint8_t* mask_bits;            /* [B], nullable */
+} aecf_fusion_tensors;
+
+typedef struct aecf_fusion_grads {
+    const void*  d_out;            /* [B, D] */
+    const float* d_pooled;         /* [B, M] fp32, nullable */
+    const float* d_entropy;        /* [B] fp32, nullable (eval mode) */
+    /* scratch the caller provides */
+    void* d_ctx;                   /* [B, D] */
+    void* d_kv;                    /* [B*M, 2D] */
+    void* d_q_rows;                /* [B, D]; only when !q_is_shared */
+    /* results; a null pointer skips that gradient */
+    void* d_key;                   /* [B*M, D] */
+    void* d_value;                 /* [B*M, D], only with a separate value */
+    void* d_query;                 /* q_is_shared ? [D] : [B, D] */
+    void* d_in_proj_weight;        /* [3D, D] */
+    void* d_in_proj_bias;          /* [3D] */
+    void* d_out_proj_weight;       /* [D, D] */
+    void* d_out_proj_bias;         /* [D] */
+} aecf_fusion_grads;
+
+enum { AECF_BWD_ALL = 0, AECF_BWD_OUT_PROJ = 1, AECF_BWD_REST = 2 };
+
+AECF_API int aecf_fusion_fwd(const aecf_pool_desc* desc, const aecf_fusion_tensors* t, void* workspace,
+                             size_t workspace_bytes, void* stream);
+/* phase AECF_BWD_OUT_PROJ computes d_out_proj_{bias,weight} and d_ctx; AECF_BWD_REST everything else
+ * (a data-parallel caller starts the all-reduce of the out-projection gradients in between). */
+AECF_API int aecf_fusion_bwd(const aecf_pool_desc* desc, const aecf_fusion_tensors* t, const aecf_fusion_grads* g,
+                             int32_t phase, void* workspace, size_t workspace_bytes, void* stream);
+AECF_API size_t aecf_fusion_workspace_bytes(const aecf_pool_desc* desc);
+
+/* ---- per-kernel timing (CUDA events recorded next to each launch, on the launching stream) ------------- */
+typedef enum aecf_site {
+    AECF_SITE_OTHER = 0, AECF_SITE_Q_PROJ, AECF_SITE_KV_PROJ, AECF_SITE_POOL_FWD, AECF_SITE_OUT_PROJ,
+    AECF_SITE_D_OUT_BIAS, AECF_SITE_D_OUT_WEIGHT, AECF_SITE_D_CTX, AECF_SITE_POOL_BWD, AECF_SITE_POOL_BWD_FINALIZE,
+    AECF_SITE_D_X, AECF_SITE_D_KV_WEIGHT, AECF_SITE_D_Q_WEIGHT, AECF_SITE_D_QUERY, AECF_SITE_D_IN_BIAS,
+    AECF_SITE_ENTROPY_LOSS, AECF_SITE_COUNT
+} aecf_site;
+AECF_API int         aecf_timing_enable(int32_t enable);                    /* clears earlier records */
+AECF_API int         aecf_timing_collect(float* total_ms, int32_t* launches); /* arrays of AECF_SITE_COUNT; syncs */
+AECF_API const char* aecf_timing_site_name(int32_t site);
+
 /* ---- diagnostics ----------------------------------------------------------------------- */
 AECF_API int         aecf_abi_version(void);
 AECF_API const char* aecf_strerror(int status);

@@ -122,12 +122,13 @@ def test_shard_rows_cover_the_batch_exactly():
             assert max(n for _, n in pieces) - min(n for _, n in pieces) <= 1
 
 
-def test_single_process_sync_is_identity():
+def test_single_process_sync_leaves_gradients_alone():
     t = _inputs()
     pool = _Params(t)
     query = torch.nn.Parameter(t["q0"].clone())
     sync = GradientSync(pool, query).attach()
     g = torch.randn_like(pool.attention.out_proj.weight)
-    pool._grad_ready("out_proj.weight", g)
+    pool.attention.out_proj.weight.grad = g.clone()
+    pool._grad_ready("out_proj.weight", g * 3)          # ignored: there is nobody to reduce with
     sync.finish()
-    assert torch.equal(pool.attention.out_proj.weight.grad, g)
+    assert torch.equal(pool.attention.out_proj.weight.grad, g) and not sync.pending
