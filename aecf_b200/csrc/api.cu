@@ -160,12 +160,13 @@ int aecf_pool_fwd(const aecf_pool_desc* desc, const void* q, const void* kv, con
     p.ctx = ctx; p.pooled = pooled; p.entropy = entropy; p.mask_rate = mask_rate; p.masked = masked;
     p.mask_bits = mask_bits;
     const int grid = static_cast<int>((p.B + p.SPC - 1) / p.SPC);
+    const int sms = sm_count(desc->device);
     TimedLaunch timed(static_cast<cudaStream_t>(stream));
     if (plan.bf16)
-        return plan.drop ? launch_pool_fwd<__nv_bfloat16, true>(plan.M, plan.J, p, grid, stream)
-                         : launch_pool_fwd<__nv_bfloat16, false>(plan.M, plan.J, p, grid, stream);
-    return plan.drop ? launch_pool_fwd<float, true>(plan.M, plan.J, p, grid, stream)
-                     : launch_pool_fwd<float, false>(plan.M, plan.J, p, grid, stream);
+        return plan.drop ? launch_pool_fwd<__nv_bfloat16, true>(plan.M, plan.J, p, grid, sms, stream)
+                         : launch_pool_fwd<__nv_bfloat16, false>(plan.M, plan.J, p, grid, sms, stream);
+    return plan.drop ? launch_pool_fwd<float, true>(plan.M, plan.J, p, grid, sms, stream)
+                     : launch_pool_fwd<float, false>(plan.M, plan.J, p, grid, sms, stream);
 }
 
 size_t aecf_pool_bwd_workspace_bytes(const aecf_pool_desc* desc) {

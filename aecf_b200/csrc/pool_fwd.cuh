@@ -186,4 +186,111 @@ pool_fwd_kernel(const PoolParams p) {
     if (p.mask_bits) p.mask_bits[my_row] = static_cast<uint8_t>(bits);
 }
 
+// ---- streaming variant (one warp owns a whole sample, WPS == 1): the headline path ----------------------
+// Persistent warps, each on a contiguous block of rows.  The next row's K/V chunks are copied
+// global -> shared with cp.async (16 B per lane, no register staging) while the current row is being
+// reduced, so every warp keeps one full sample (6 KB at M=3, D=512 bf16) in flight at all times and the
+// arithmetic never waits on HBM.  Head sums of up to 32 consecutive rows stay in lane registers (lane i
+// keeps row i); the masking stage then runs once per 32 rows with one row per lane.
+template <typename T, int M, int J, bool DROP>
+__global__ void __launch_bounds__(512, 1)
+pool_fwd_stream_kernel(const PoolParams p, const long long rows_per_warp) {
+    using Core = PoolCore<T, M, J, DROP>;
+    constexpr int V = Core::V;
+    constexpr int CH = M * 2 * J;                       // 16-byte chunks per lane per sample
+    extern __shared__ uint4 ring[];                     // [warps][2 stages][CH][32 lanes]
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long long gw = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp;
+    const long long row_begin = gw * rows_per_warp;
+    const long long row_end = min(p.B, row_begin + rows_per_warp);
+    if (row_begin >= row_end) return;                   // warp-uniform; no block-level barrier in this kernel
+    uint4* my = ring + static_cast<size_t>(warp) * 2 * CH * 32;
+    const int c0 = lane;
+    const char* kv = static_cast<const char*>(p.kv);
+
+    auto prefetch = [&](long long row, int stage) {
+        const char* src = kv + Core::row_offset(p, row, c0);
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+#pragma unroll
+            for (int half = 0; half < 2; ++half)
+#pragma unroll
+                for (int j = 0; j < J; ++j)
+                    if (c0 + 32 * j < p.NC)
+                        cp_async16(&my[(stage * CH + (m * 2 + half) * J + j) * 32 + lane], src + Core::kv_rel(p, m, half, j));
+        cp_async_commit();
+    };
+    prefetch(row_begin, 0);
+
+    float qs[J][V];
+    if (p.q_shared) Core::load_query(p, 0, c0, qs);
+    const float denom = static_cast<float>(p.H * p.R);
+    float mine[M];                                      // head sums of the row this lane will finish
+#pragma unroll
+    for (int m = 0; m < M; ++m) mine[m] = 0.f;
+
+    int it = 0;
+    for (long long row = row_begin; row < row_end; ++row, ++it) {
+        const int stage = it & 1;
+        if (row + 1 < row_end) prefetch(row + 1, stage ^ 1);
+        else cp_async_commit();                         // empty group keeps the wait count uniform
+        if (!p.q_shared) Core::load_query(p, row, c0, qs);
+        cp_async_wait<1>();                             // this row's chunks have landed (own copies only)
+        auto staged = [&](int m, int half, int j) -> uint4 {
+            return (c0 + 32 * j < p.NC) ? my[(stage * CH + (m * 2 + half) * J + j) * 32 + lane] : make_uint4(0, 0, 0, 0);
+        };
+
+        float w[M][J], wd[M][J];
+        unsigned keep;
+        Core::attention_weights(p, row, c0, qs, [&](int m, int j) { return staged(m, 0, j); }, w, wd, keep);
+
+        float acc[J][V];
+#pragma unroll
+        for (int j = 0; j < J; ++j)
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc[j][v] = 0.f;
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                float f[V];
+                Vec<T>::unpack(staged(m, 1, j), f);
+#pragma unroll
+                for (int v = 0; v < V; ++v) acc[j][v] = fmaf(wd[m][j], f[v], acc[j][v]);
+            }
+        char* ctx = static_cast<char*>(p.ctx) + static_cast<size_t>(row) * p.D * sizeof(T) + static_cast<size_t>(c0) * 16;
+#pragma unroll
+        for (int j = 0; j < J; ++j)
+            if (c0 + 32 * j < p.NC) stg_vec(ctx + j * 512, Vec<T>::pack(acc[j]));
+
+        float total[M];
+        Core::head_sum_partial(p, c0, wd, total);       // WPS == 1: the warp holds every head
+#pragma unroll
+        for (int m = 0; m < M; ++m) mine[m] = (lane == (it & 31)) ? total[m] : mine[m];
+
+        if ((it & 31) == 31 || row + 1 == row_end) {    // finish up to 32 rows, one per lane
+            const long long first = row - (it & 31);
+            const long long my_row = first + lane;
+            if (my_row <= row) {
+                float pw[M], mw[M];
+#pragma unroll
+                for (int m = 0; m < M; ++m) pw[m] = mine[m] / denom;
+                float entropy, mask_rate;
+                unsigned bits;
+                masking_stage<M>(p, my_row, pw, mw, entropy, mask_rate, bits);
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    p.pooled[static_cast<size_t>(my_row) * M + m] = pw[m];
+                    if (p.masked) p.masked[static_cast<size_t>(my_row) * M + m] = mw[m];
+                }
+                if (p.entropy) p.entropy[my_row] = entropy;
+                if (p.mask_rate) p.mask_rate[my_row] = mask_rate;
+                if (p.mask_bits) p.mask_bits[my_row] = static_cast<uint8_t>(bits);
+            }
+            __syncwarp();
+        }
+    }
+}
+
 }  // namespace aecf

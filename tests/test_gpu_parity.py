@@ -196,6 +196,38 @@ def test_bf16_masks_exact_against_stage_rounded_oracle(case):
 
 
 # ---------------------------------------------------------------------------------------------
+# rows wider than one warp's slice: several warps share a sample (pool_core.cuh, WPS > 1)
+# ---------------------------------------------------------------------------------------------
+WIDE_CASES = [
+    Case("wide_d1024_h8_m3", B=24, M=3, D=1024, H=8, dropout=0.1, pooled_grad=True, data_seed=31, offset=2),
+    Case("wide_d2048_h16_m2", B=12, M=2, D=2048, H=16, data_seed=32, base_mask_prob=0.5),
+    Case("wide_d1024_h4_m4_eval", B=10, M=4, D=1024, H=4, training=False, pooled_grad=True, data_seed=33),
+    Case("wide_d512_h8_m5_kpm", B=20, M=5, D=512, H=8, kpm=True, min_active=2, base_mask_prob=0.8, data_seed=34),
+]
+
+
+@pytest.mark.parametrize("case", WIDE_CASES, ids=lambda c: c.name)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_wide_rows_span_several_warps(case, dtype):
+    if dtype == torch.float32:
+        inp = build_inputs(case)
+        ref, ref_grads = run_oracle(case, inp)
+        tol = FP32_TOL
+    else:
+        inp = _bf16_inputs(case)
+        ref, ref_grads = run_oracle(case, inp, storage=torch.bfloat16)
+        tol = BF16_TOL
+    out, info, _, grads, _ = run_cuda(case, inp, dtype)
+    assert np.array_equal(info["mask_bits"].cpu().numpy(), expected_bits(ref.info["mask"])), "mask bits differ"
+    assert torch.equal(info["mask_rate"].cpu(), ref.info["mask_rate"].float())
+    assert_close("out", out.float().cpu(), ref.out, tol)
+    assert_close("attention_weights", info["attention_weights"].cpu(), ref.info["attention_weights"],
+                 tol if dtype == torch.float32 else 1e-4, atol=1e-5)
+    assert_close("entropy", info["entropy"].cpu(), ref.info["entropy"], tol if dtype == torch.float32 else 1e-4, atol=1e-5)
+    check_grads(case, {k: v.float() for k, v in grads.items()}, ref_grads, tol)
+
+
+# ---------------------------------------------------------------------------------------------
 # full-size, size-independent properties (BASELINE.json configs[1]: B=65536, M=3, D=512, H=8 bf16)
 # ---------------------------------------------------------------------------------------------
 def _headline(B=65536, M=3, D=512, H=8, dtype=torch.bfloat16, dropout=0.0, seed=0):
