@@ -6,21 +6,24 @@ sum-all-reduce of the fusion parameter gradients per step (1 051 136 elements at
 
   * rank r owns global rows [r*B/N, (r+1)*B/N); ``pool.row_offset`` keys the Philox counters on the
     GLOBAL row, so any N reproduces the 1-GPU masks and dropout bit for bit
-  * gradients are reduced in readiness order -- out_proj first, in_proj and the query last -- each
-    group on a side stream as soon as the backward has produced it, overlapping the rest of the
-    backward (the fused pool backward and the two large in-projection GEMMs)
-  * reduction happens in an fp32 flat bucket regardless of the parameter dtype
+  * the backward writes its parameter gradients straight into one flat bucket (no copies); the
+    bucket is reduced in two groups in readiness order -- the out-projection gradients as soon as
+    ``aecf_fusion_bwd(AECF_BWD_OUT_PROJ)`` has produced them, on a side stream, while the fused pool
+    backward and the in-projection GEMMs still run; the in-projection and query gradients at the end
+  * ``overlap=False`` reduces the whole bucket once, after the backward, on the compute stream
 
 Works with any ``torch.distributed`` backend: NCCL on the GPUs, gloo in the CPU tests of the host logic.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
 
 PARAM_ORDER = ("out_proj.bias", "out_proj.weight", "in_proj_weight", "in_proj_bias", "query")
+EARLY = ("out_proj.bias", "out_proj.weight")            # final after the first backward phase
 
 
 def shard_rows(global_batch: int, rank: int, world_size: int) -> Tuple[int, int]:
@@ -31,41 +34,59 @@ def shard_rows(global_batch: int, rank: int, world_size: int) -> Tuple[int, int]
 
 
 class GradientSync:
-    """Overlapped all-reduce (mean) of the fusion parameter gradients of one pool + its query.
+    """All-reduce (mean by default) of the fusion parameter gradients of one pool + its query.
 
-    ``attach()`` hooks the pool so that its backward reports each parameter gradient the moment it is
-    final; ``finish()`` waits for the collectives and writes the averaged gradients into ``.grad``.
+    ``attach()`` hooks the pool: its backward then writes gradients into ``self.bucket`` and reports
+    each one the moment it is final.  ``finish()`` -- call it after ``loss.backward()`` -- waits for the
+    collectives and points every ``param.grad`` at its reduced slice of the bucket.
     """
 
     def __init__(self, pool, query: Optional[torch.nn.Parameter] = None, process_group=None,
-                 average: bool = True):
+                 average: bool = True, overlap: Optional[bool] = None):
         self.pool, self.query, self.group, self.average = pool, query, process_group, average
+        if overlap is None:
+            overlap = os.environ.get("AECF_DP_OVERLAP", "1") != "0"
+        self.overlap = overlap
         att = pool.attention
         self.params: Dict[str, torch.nn.Parameter] = {}
         for name, p in (("out_proj.bias", att.out_proj.bias), ("out_proj.weight", att.out_proj.weight),
                         ("in_proj_weight", att.in_proj_weight), ("in_proj_bias", att.in_proj_bias), ("query", query)):
             if p is not None:
                 self.params[name] = p
-        device = att.in_proj_weight.device
+        device, dtype = att.in_proj_weight.device, att.in_proj_weight.dtype
+        if any(p.dtype != dtype for p in self.params.values()):
+            raise ValueError("GradientSync needs the fusion query and the pool parameters in one dtype")
         self.slices: Dict[str, slice] = {}
         n = 0
         for name in PARAM_ORDER:
             if name in self.params:
                 k = self.params[name].numel()
                 self.slices[name] = slice(n, n + k)
-                n += (k + 3) // 4 * 4                       # keep every slice 16-byte aligned
-        self.bucket = torch.zeros(n, dtype=torch.float32, device=device)
+                n += (k + 7) // 8 * 8                       # keep every slice 16-byte aligned
+            if name == EARLY[-1]:
+                self.early_end = n
+        self.bucket = torch.zeros(n, dtype=dtype, device=device)
+        self.views = {name: self.bucket[sl].view(self.params[name].shape) for name, sl in self.slices.items()}
         self.cuda = device.type == "cuda"
         self.comm_stream = torch.cuda.Stream(device=device) if self.cuda else None
-        self.pending: List[Tuple[str, object]] = []
+        self.pending: List[object] = []
         self.reported: set = set()
+        self.reduced_upto = 0
 
     # -- wiring -----------------------------------------------------------------------------
     def attach(self) -> "GradientSync":
         self.pool._grad_ready = self.on_ready
+        self.pool._grad_buffers = self.views            # the fused backward writes its gradients here
         if self.query is not None:
-            self.query.register_hook(lambda g: self.on_ready("query", g) or g)
+            self.query.register_hook(self._query_hook)
         return self
+
+    def _query_hook(self, grad: torch.Tensor) -> torch.Tensor:
+        view = self.views["query"]
+        if grad.data_ptr() != view.data_ptr():          # the shared-query bypass did not apply: copy in
+            view.copy_(grad.reshape(view.shape))
+        self.on_ready("query", view)
+        return grad
 
     @property
     def world_size(self) -> int:
@@ -78,39 +99,50 @@ class GradientSync:
         self.pool.row_offset = row0
         return row0, rows
 
-    # -- called from the backward (autograd worker thread) -----------------------------------
-    def on_ready(self, name: str, grad: torch.Tensor) -> None:
-        if name not in self.slices or name in self.reported or self.world_size == 1:
-            return                                                     # single process: autograd's .grad is final
-        self.reported.add(name)
-        view = self.bucket[self.slices[name]]
-        view.copy_(grad.reshape(-1))                                   # cast to fp32 into the flat bucket
-        if self.cuda:
+    def _reduce(self, lo: int, hi: int, side_stream: bool) -> None:
+        if hi <= lo:
+            return
+        view = self.bucket[lo:hi]
+        avg = self.average and dist.get_backend(self.group) == "nccl"
+        op = dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM
+        if self.cuda and side_stream:
             ready = torch.cuda.Event()
             ready.record(torch.cuda.current_stream(self.bucket.device))
             with torch.cuda.stream(self.comm_stream):
                 self.comm_stream.wait_event(ready)
-                work = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                self.pending.append(dist.all_reduce(view, op=op, group=self.group, async_op=True))
         else:
-            work = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-        self.pending.append((name, work))
+            self.pending.append(dist.all_reduce(view, op=op, group=self.group, async_op=True))
+        if self.average and not avg:
+            self._scale_later = True
+
+    # -- called from the backward (autograd worker thread) -----------------------------------
+    def on_ready(self, name: str, grad: torch.Tensor) -> None:
+        if name not in self.slices or name in self.reported or self.world_size == 1:
+            return                                                     # single process: autograd's .grad is final
+        view = self.views[name]
+        if grad.data_ptr() != view.data_ptr():                         # produced elsewhere: copy into the bucket
+            view.copy_(grad.reshape(view.shape))
+        self.reported.add(name)
+        if self.overlap and self.reduced_upto == 0 and all(n in self.reported for n in EARLY if n in self.slices):
+            self._reduce(0, self.early_end, side_stream=True)
+            self.reduced_upto = self.early_end
 
     # -- called by the training loop after loss.backward() -----------------------------------
     def finish(self) -> None:
-        """Wait for the collectives and store the reduced gradients in ``param.grad``."""
-        for _, work in self.pending:
+        """Reduce what is left, wait for the collectives and store the results in ``param.grad``."""
+        if not self.reported:
+            return
+        self._reduce(self.reduced_upto, self.bucket.numel(), side_stream=False)
+        for work in self.pending:
             work.wait()
-        if self.cuda and self.pending:
+        if self.cuda and self.overlap:
             torch.cuda.current_stream(self.bucket.device).wait_stream(self.comm_stream)
-        scale = 1.0 / self.world_size if self.average else 1.0
+        if getattr(self, "_scale_later", False):
+            self.bucket.mul_(1.0 / self.world_size)
+            self._scale_later = False
         for name in self.reported:
-            p = self.params[name]
-            reduced = self.bucket[self.slices[name]].reshape(p.shape)
-            if p.grad is None:
-                p.grad = torch.empty_like(p)
-            if scale != 1.0:
-                p.grad.copy_(reduced * scale)
-            else:
-                p.grad.copy_(reduced)
+            self.params[name].grad = self.views[name]
         self.pending.clear()
         self.reported.clear()
+        self.reduced_upto = 0

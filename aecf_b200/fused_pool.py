@@ -37,6 +37,9 @@ class PoolConfig:
     # data-parallel hook: called in backward with (name, grad tensor) as soon as a parameter
     # gradient is final, so that its all-reduce overlaps the rest of the backward
     grad_ready: Optional[Callable[[str, torch.Tensor], None]] = None
+    # data-parallel: {parameter name: tensor} the backward writes that parameter's gradient into
+    # (slices of the all-reduce bucket), instead of allocating it
+    grad_buffers: Optional[dict] = None
 
 
 def _rows(x3d: torch.Tensor) -> torch.Tensor:
@@ -125,11 +128,19 @@ class FusedPoolFunction(torch.autograd.Function):
         d_q_rows = None if cfg.q_shared else new((B, D))
         d_key = new(key.shape) if need_key else None
         d_value = new(value.shape) if (value is not None and need_value) else None
-        d_q = new(q_in.shape, q_in.dtype) if need_q else None
-        d_in_w = torch.empty_like(in_w) if need_in_w else None
-        d_in_b = torch.empty_like(in_b) if (need_in_b and in_b is not None) else None
-        d_out_w = torch.empty_like(out_w) if need_out_w else None
-        d_out_b = torch.empty_like(out_b) if (need_out_b and out_b is not None) else None
+        bufs = cfg.grad_buffers or {}
+
+        def grad_like(name, like):
+            b = bufs.get(name)
+            if b is not None and b.numel() == like.numel() and b.dtype == like.dtype and b.is_contiguous():
+                return b.view(like.shape)
+            return torch.empty_like(like)
+
+        d_q = (grad_like("query", q_in) if cfg.q_shared else new(q_in.shape, q_in.dtype)) if need_q else None
+        d_in_w = grad_like("in_proj_weight", in_w) if need_in_w else None
+        d_in_b = grad_like("in_proj_bias", in_b) if (need_in_b and in_b is not None) else None
+        d_out_w = grad_like("out_proj.weight", out_w) if need_out_w else None
+        d_out_b = grad_like("out_proj.bias", out_b) if (need_out_b and out_b is not None) else None
 
         p = _lib.ptr
         tensors = _lib.FusionTensors(

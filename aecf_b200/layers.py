@@ -207,6 +207,7 @@ class MultimodalAttentionPool(nn.Module):
         # data-parallel state (aecf_b200.dp): global index of local row 0, gradient-ready callback
         self.row_offset = 0
         self._grad_ready = None
+        self._grad_buffers = None
         self._want_mask_bits = False
 
     # -- validation: same exception types and messages as the reference (:450-498) -----------
@@ -328,7 +329,7 @@ class MultimodalAttentionPool(nn.Module):
             min_active=cm.min_active if fused_cm else 1,
             seed=seed, offset=offset, row0=int(self.row_offset), q_shared=q_shared,
             seq_first=not self.batch_first, want_mask_bits=self._want_mask_bits, bias_strides=bias_strides,
-            grad_ready=self._grad_ready)
+            grad_ready=self._grad_ready, grad_buffers=self._grad_buffers)
         out, pooled, entropy, mask_rate, masked, bits = FusedPoolFunction.apply(
             q_src, key_c, value_c, att.in_proj_weight, att.in_proj_bias, att.out_proj.weight, att.out_proj.bias,
             bias, cfg)

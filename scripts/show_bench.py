@@ -1,6 +1,6 @@
 """Pretty-print a bench.py JSON line: python scripts/show_bench.py gpurun_out/bench.json"""
 import json, sys
-d = json.load(open(sys.argv[1]))
+d = json.loads([l for l in open(sys.argv[1]) if l.lstrip().startswith('{')][-1])
 print(f"value {d['value']/1e6:.2f} M samples/s   {d['ms_per_step']:.4f} ms/step   launches {d['gpu_launches']}   clocks {d['clocks']}")
 print(f"host issue {d.get('host_issue_ms_per_step')} ms/step   kernel sum {d.get('kernel_ms_sum')} ms")
 for name in ("roofline", "roofline_pool_fwd"):

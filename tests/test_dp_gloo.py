@@ -62,6 +62,7 @@ class _Params(torch.nn.Module):
         self.attention.out_proj.bias = torch.nn.Parameter(t["bo"].clone())
         self.row_offset = 0
         self._grad_ready = None
+        self._grad_buffers = None
 
 
 def _worker(rank, port, out_dir):
@@ -73,19 +74,22 @@ def _worker(rank, port, out_dir):
         query = torch.nn.Parameter(t["q0"].clone())
         sync = GradientSync(pool, query, average=False).attach()
         row0, rows = sync.set_shard(B)
-        assert pool.row_offset == row0 and pool._grad_ready is not None
+        assert pool.row_offset == row0 and pool._grad_ready is not None and set(pool._grad_buffers) == set(PARAM_ORDER)
         fwd, grads = _step(t, row0, rows)
         # report in the order the fused backward produces them: out_proj first, in_proj and query last
-        for name in PARAM_ORDER:
-            key = {"query": "query"}.get(name, name)
+        for i, name in enumerate(PARAM_ORDER):
             if name == "query":
-                query.grad = None
-                sync.on_ready("query", grads[key])
-            else:
-                pool._grad_ready(name, grads[key])
-        assert len(sync.pending) == len(PARAM_ORDER)
+                sync._query_hook(grads[name])
+            elif name == "in_proj_weight":                # what the fused backward does: write in place
+                pool._grad_buffers[name].copy_(grads[name])
+                pool._grad_ready(name, pool._grad_buffers[name])
+            else:                                         # a gradient produced elsewhere is copied in
+                pool._grad_ready(name, grads[name])
+            # the out-projection group is reduced as soon as both of its members are in
+            assert len(sync.pending) == (1 if i >= 1 else 0)
         sync.finish()
         assert not sync.pending and not sync.reported
+        assert pool.attention.in_proj_weight.grad.data_ptr() == pool._grad_buffers["in_proj_weight"].data_ptr()
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), row0=row0, rows=rows,
                  mask=fwd.info["mask"].numpy(), out=fwd.out.numpy(),
                  **{f"g_{n}": p.grad.numpy() for n, p in sync.params.items()})
