@@ -39,7 +39,7 @@ FALLBACK_BF16_TFLOPS = 1590.0
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--batch", type=int, default=65536, help="rows per GPU (weak scaling)")
@@ -52,6 +52,18 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
+
+
+def ncu_traffic(kernel: str, args):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture of this exact workload
+    (profiles/ncu_traffic.json), or None when the workload differs from the captured one."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)
+        key = f"B={args.batch},M={args.tokens},D={args.dim},H={args.heads},{args.dtype},dropout={args.dropout}"
+        return t.get(key, {}).get(kernel)
+    except Exception:
+        return None
 
 
 def measured_peaks():
@@ -69,41 +81,56 @@ def measured_peaks():
 # clocks during the timed region
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML every ~2 ms DURING the timed region
+    (nvidia-smi takes longer per query than a whole timed region lasts)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
         self.index, self.samples, self.stop_flag, self.thread = index, [], threading.Event(), None
+        self.max_mhz, self.handle, self.nvml = None, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
     def _run(self):
+        nv = self.nvml
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [s.strip() for s in out.strip().split(",")]
-                if len(parts) >= 6:
-                    self.samples.append(parts)
+                mhz = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                self.samples.append((float(mhz), int(reasons)))
             except Exception:
                 pass
-            self.stop_flag.wait(0.1)
+            self.stop_flag.wait(0.002)
 
     def __enter__(self):
-        self.thread = threading.Thread(target=self._run, daemon=True)
-        self.thread.start()
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
         return self
 
     def __exit__(self, *exc):
         self.stop_flag.set()
-        self.thread.join(timeout=10)
+        if self.thread is not None:
+            self.thread.join(timeout=10)
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]),
-                "reasons": reasons, "samples": len(self.samples)}
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        sm = sorted(s[0] for s in self.samples)
+        bits = 0
+        for _, r in self.samples:
+            bits |= r
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.max_mhz,
+                "reasons": [name for bit, name in self.REASONS.items() if bits & bit], "samples": len(self.samples),
+                "source": "NVML, sampled every 2 ms inside the timed region"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -337,7 +364,7 @@ def run_b200(args):
             return None
         gbs = nbytes / (kernels[name]["ms"] * 1e-3) / 1e9
         return {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": gbs / peaks["hbm_gbs"], "frac_of_nominal_8TBs": gbs / 8000.0, "traffic": None,
+                "frac": gbs / peaks["hbm_gbs"], "frac_of_nominal_8TBs": gbs / 8000.0, "traffic": ncu_traffic(name, args),
                 "ms": kernels[name]["ms"], "algorithmic_bytes": nbytes, "peak_source": peaks["source"]}
 
     gemm_flops = {"kv_proj": 2 * B * M * D * 2 * D, "out_proj": 2 * B * D * D, "d_ctx": 2 * B * D * D,

@@ -9,6 +9,6 @@ timeout 300 python bench.py --steps 3 --warmup 2 --no-e2e --no-cpu-baseline > gp
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 3 --warmup 2 --no-e2e --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
 timeout 300 python bench.py --steps 3 --warmup 2 --no-e2e --no-cpu-baseline > gpurun_out/plain2.log 2>&1 && \
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"pool_(fwd|bwd)_kernel" -s 4 -c 2 -o gpurun_out/prof_pool \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"pool_(fwd|bwd)" -s 3 -c 3 -o gpurun_out/prof_pool \
     python bench.py --steps 3 --warmup 2 --no-e2e --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 tail -6 gpurun_out/tests.log; tail -c 300 gpurun_out/bench.json; tail -3 gpurun_out/bench.err

@@ -367,6 +367,45 @@ def test_per_row_queries_match_oracle():
                  atol=FP32_TOL * scale)
 
 
+def test_attn_mask_forms_match_oracle():
+    """attn_mask as torch accepts it for one target token: (1, M) bool, (1, M) float, (B*H, 1, M) float,
+    alone or merged with a key_padding_mask (torch/nn/functional.py:6608-6620)."""
+    case = CASES_BY_NAME["d64_h4_m4_kpm"]
+    inp = build_inputs(case)
+    B, M, H, D = case.B, case.M, case.H, case.D
+    kpm = inp["key_padding_mask"]
+    per_head = torch.from_numpy(philox.normal(77, (B * H, 1, M))).float()
+    per_head[::5, 0, 1] = float("-inf")
+    masks = {
+        "bool_2d": (torch.tensor([[False, False, True, False]]), None),
+        "float_2d": (torch.tensor([[0.0, -1.5, 0.5, float("-inf")]]), None),
+        "float_3d": (per_head, None),
+        "float_3d_plus_kpm": (per_head, kpm),
+    }
+    q = inp["query0"].expand(B, 1, D)
+    for name, (am, pad) in masks.items():
+        bias = am.float() if am.dtype != torch.bool else torch.zeros(am.shape).masked_fill(am, float("-inf"))
+        bias = bias.reshape(1, 1, 1, M) if bias.dim() == 2 else bias.reshape(B, H, 1, M)
+        if pad is not None:
+            bias = bias + torch.zeros(B, 1, 1, M).masked_fill(pad.view(B, 1, 1, M), float("-inf"))
+        ref = oracle.pool_forward(q, inp["x"], None, inp["in_proj_weight"], inp["in_proj_bias"], inp["out_proj.weight"],
+                                  inp["out_proj.bias"], H, training=True, u_mask=inp["u_mask"], u_drop=inp["u_drop"],
+                                  score_bias=bias, masking=masking_kwargs(case))
+        grads = oracle.pool_backward(q, inp["x"], None, inp["in_proj_weight"], inp["out_proj.weight"], H, ref.saved,
+                                     inp["grad_out"])
+        pool, _ = make_pool(case, inp, torch.float32)
+        x = inp["x"].to(DEV).requires_grad_(True)
+        aecf_b200.set_rng_state(PHILOX_SEED, case.offset)
+        out, info = pool(q.to(DEV), x, attn_mask=am.to(DEV), key_padding_mask=None if pad is None else pad.to(DEV),
+                         return_info=True)
+        aecf_b200.set_rng_state(None)
+        (out * inp["grad_out"].to(DEV)).sum().backward()
+        assert_close(f"{name}: out", out.cpu(), ref.out, FP32_TOL)
+        assert_close(f"{name}: weights", info["attention_weights"].cpu(), ref.info["attention_weights"], FP32_TOL, atol=1e-6)
+        assert np.array_equal(info["mask_bits"].cpu().numpy(), expected_bits(ref.info["mask"])), name
+        assert_close(f"{name}: grad x", x.grad.cpu(), grads["key"], FP32_TOL)
+
+
 def test_no_masking_module_and_plain_output():
     case = CASES_BY_NAME["d64_h8_m3"]
     inp = build_inputs(case)
