@@ -37,25 +37,26 @@ int sm_count(int device) {
 
 constexpr int POOL_BWD_MAX_BLOCKS = 2048;
 
-// Sum the per-block partials: d_q[D] (scaled) and d_bias_kv[2D] = [dbk | dbv].  Block (32 columns x 8
-// lanes): lane y sums partials y, y+8, ... in order, the 8 lane sums are folded in order -> deterministic.
-__global__ void __launch_bounds__(256)
+// Sum the per-block partials: d_q[D] (scaled) and d_bias_kv[2D] = [dbk | dbv].  Block (32 columns x 32
+// lanes): lane y sums partials y, y+32, ... in order (all loads issued together), the 32 lane sums are
+// folded in order -> deterministic.
+__global__ void __launch_bounds__(1024)
 pool_bwd_finalize_kernel(const float* __restrict__ partials, int blocks, int D, float scale, int q_shared,
                          float* __restrict__ d_q, float* __restrict__ d_bias_kv) {
-    __shared__ float red[8][33];
+    __shared__ float red[32][33];
     const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
     const int i = blockIdx.x * 32 + x;
     float s = 0.f;
     if (i < 3 * D) {
-#pragma unroll 4
-        for (int b = y; b < blocks; b += 8) s += partials[static_cast<size_t>(b) * 3 * D + i];
+#pragma unroll 16
+        for (int b = y; b < blocks; b += 32) s += partials[static_cast<size_t>(b) * 3 * D + i];
     }
     red[y][x] = s;
     __syncthreads();
     if (y != 0 || i >= 3 * D) return;
     s = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) s += red[k][x];
+    for (int k = 0; k < 32; ++k) s += red[k][x];
     const int which = i / D, d = i - which * D;
     if (which == 0) { if (q_shared && d_q) d_q[d] = s * scale; }
     else if (d_bias_kv) d_bias_kv[(which == 1 ? D : 0) + d] = s;
@@ -216,7 +217,7 @@ int aecf_pool_bwd(const aecf_pool_desc* desc, const void* q, const void* kv, con
     if (rc != AECF_OK) return rc;
     const int n = 3 * p.D;
     TimedLaunch timed_finalize(static_cast<cudaStream_t>(stream), AECF_SITE_POOL_BWD_FINALIZE);
-    pool_bwd_finalize_kernel<<<(n + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    pool_bwd_finalize_kernel<<<(n + 31) / 32, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
         p.partials, grid, p.D, p.scale, p.q_shared, p.q_shared ? static_cast<float*>(d_q) : nullptr, d_bias_kv);
     count_launch();
     AECF_CUDA_OK(cudaGetLastError());

@@ -14,6 +14,7 @@
 // restated in cute/arch/mma_sm100_desc.hpp (SmemDescriptor, InstrDescriptor).
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "gemm.cuh"
@@ -41,7 +42,7 @@ template <int BN> struct Cfg {
 
 struct Params {
     int m, n, k;
-    int tiles_m, tiles_n, splits, kb_per_split, kb_total;
+    int tiles_m, tiles_n, groups_m, splits, kb_per_split, kb_total;   // groups_m = ceil(tiles_m / cluster size)
     int a_mn_major, b_mn_major;
     int c_is_f32;              // element type of the TMA-stored C / partial
     int has_bias, bias_is_bf16;
@@ -85,6 +86,22 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// Same, multicast: the box lands at the same shared-memory offset in every CTA of `mask` and completes
+// bytes on the mbarrier at the same offset in each of them.
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%4, %5}], [%2], %3;"
+        :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  :: "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
@@ -99,6 +116,10 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {     // arrives on `bar` when all prior MMAs retire
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                  :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {   // ... on `bar` in every CTA of `mask`
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
     asm volatile(
@@ -149,19 +170,23 @@ __device__ __forceinline__ uint32_t make_idesc(int bn, int a_mn, int b_mn) {
 
 struct WorkItem { int m_blk, n_blk, split, kb_begin, kb_count; };
 
-__device__ __forceinline__ WorkItem decode(const Params& p, int item) {
+// Work items are (split, row-block group, column block); the CL CTAs of a cluster take the CL row blocks of
+// a group (same column block, same k range), which is what lets them share the B tile by TMA multicast.
+template <int CL>
+__device__ __forceinline__ WorkItem decode(const Params& p, int item, int cta_rank) {
     WorkItem w;
-    const int tiles = p.tiles_m * p.tiles_n;
+    const int tiles = p.groups_m * p.tiles_n;
     w.split = item / tiles;
     const int t = item - w.split * tiles;
-    w.m_blk = t / p.tiles_n;                 // n fastest: neighbouring CTAs share the A row block in L2
-    w.n_blk = t - w.m_blk * p.tiles_n;
+    const int group = t / p.tiles_n;         // n fastest: neighbouring clusters share the A row blocks in L2
+    w.m_blk = group * CL + cta_rank;         // may be == tiles_m for the odd last group: loads zero-fill, stores clip
+    w.n_blk = t - group * p.tiles_n;
     w.kb_begin = w.split * p.kb_per_split;
     w.kb_count = min(p.kb_per_split, p.kb_total - w.kb_begin);
     return w;
 }
 
-template <int BN>
+template <int BN, int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_c, const Params p) {
@@ -179,11 +204,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     __shared__ float bias_tile[BN];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int items = p.tiles_m * p.tiles_n * p.splits;
+    const int items = p.groups_m * p.tiles_n * p.splits;
+    const int cta_rank = CL > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+    const int first_item = blockIdx.x / CL, item_stride = gridDim.x / CL;
+    constexpr uint16_t kAllCtas = (1u << CL) - 1;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_a); prefetch_tmap(&map_b); prefetch_tmap(&map_c);
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CL); }   // every CTA's MMA frees a slot
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EPI_THREADS); }
         fence_barrier_init();
     }
@@ -194,6 +222,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                  // peers' barriers exist before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -201,11 +230,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         // ===== TMA producer =====
         if (lane == 0) {
             int it = 0;
-            for (int item = blockIdx.x; item < items; item += gridDim.x) {
-                const WorkItem w = decode(p, item);
+            for (int item = first_item; item < items; item += item_stride) {
+                const WorkItem w = decode<CL>(p, item, cta_rank);
                 for (int kb = 0; kb < w.kb_count; ++kb, ++it) {
                     const int s = it % STAGES;
-                    mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+                    mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);     // freed by the MMAs of ALL CTAs of the cluster
                     uint8_t* a_dst = stage_base + s * C::STAGE_BYTES;
                     uint8_t* b_dst = a_dst + C::A_BYTES;
                     mbar_expect_tx(&full[s], C::STAGE_BYTES);
@@ -217,12 +246,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         for (int a = 0; a < BM / 64; ++a)
                             tma_load_2d(&map_a, &full[s], a_dst + a * (BK * 128), w.m_blk * BM + a * 64, k0);
                     }
-                    if (!p.b_mn_major) {
-                        tma_load_2d(&map_b, &full[s], b_dst, k0, w.n_blk * BN);
-                    } else {
+                    if (CL == 1) {
+                        if (!p.b_mn_major) {
+                            tma_load_2d(&map_b, &full[s], b_dst, k0, w.n_blk * BN);
+                        } else {
 #pragma unroll
-                        for (int a = 0; a < BN / 64; ++a)
-                            tma_load_2d(&map_b, &full[s], b_dst + a * (BK * 128), w.n_blk * BN + a * 64, k0);
+                            for (int a = 0; a < BN / 64; ++a)
+                                tma_load_2d(&map_b, &full[s], b_dst + a * (BK * 128), w.n_blk * BN + a * 64, k0);
+                        }
+                    } else {
+                        // this CTA fetches 1/CL of the B tile and multicasts it to the whole cluster: every
+                        // CTA's stage receives the full tile, each from L2 only once
+                        constexpr int PART = BN / CL;
+                        if (!p.b_mn_major) {
+                            tma_load_2d_mc(&map_b, &full[s], b_dst + cta_rank * (PART * 128), k0,
+                                           w.n_blk * BN + cta_rank * PART, kAllCtas);
+                        } else {
+#pragma unroll
+                            for (int a = 0; a < PART / 64; ++a) {
+                                const int atom = cta_rank * (PART / 64) + a;
+                                tma_load_2d_mc(&map_b, &full[s], b_dst + atom * (BK * 128), w.n_blk * BN + atom * 64, k0, kAllCtas);
+                            }
+                        }
                     }
                 }
             }
@@ -232,8 +277,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (lane == 0) {
             const uint32_t idesc = make_idesc(BN, p.a_mn_major, p.b_mn_major);
             int it = 0, tile_it = 0;
-            for (int item = blockIdx.x; item < items; item += gridDim.x, ++tile_it) {
-                const WorkItem w = decode(p, item);
+            for (int item = first_item; item < items; item += item_stride, ++tile_it) {
+                const WorkItem w = decode<CL>(p, item, cta_rank);
                 const int as = tile_it & 1;
                 mbar_wait(&tmem_empty[as], ((tile_it >> 1) & 1) ^ 1);          // epilogue drained this accumulator
                 tc_fence_after();
@@ -248,7 +293,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     for (int ks = 0; ks < BK / UMMA_K; ++ks)
                         umma_bf16(tmem_d, operand_desc(a_addr, p.a_mn_major, ks), operand_desc(b_addr, p.b_mn_major, ks),
                                   idesc, (kb | ks) != 0 ? 1u : 0u);
-                    umma_commit(&empty[s]);                                    // smem slot free once these MMAs retire
+                    if (CL == 1) umma_commit(&empty[s]);                       // smem slot free once these MMAs retire
+                    else umma_commit_mc(&empty[s], kAllCtas);                  // ... in every CTA that multicasts into it
                 }
                 umma_commit(&tmem_full[as]);                                   // accumulator complete
             }
@@ -259,10 +305,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int row = quad * 32 + lane;            // row of the tile held by this thread
         const int et = threadIdx.x - 64;             // 0..127
         int tile_it = 0;
-        for (int item = blockIdx.x; item < items; item += gridDim.x, ++tile_it) {
-            const WorkItem w = decode(p, item);
+        for (int item = first_item; item < items; item += item_stride, ++tile_it) {
+            const WorkItem w = decode<CL>(p, item, cta_rank);
             const int as = tile_it & 1;
             const int n0 = w.n_blk * BN, m0 = w.m_blk * BM;
+            const bool tile_valid = w.m_blk < p.tiles_m;       // false only for the filler tile of an odd last group
             const bool direct = (p.splits == 1);
             // bias slice of this tile (fp32 in smem); previous tile's readers are past the barrier below
             if (direct && p.has_bias) {
@@ -326,7 +373,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 }
                 fence_proxy_async();                                           // smem writes -> visible to TMA
                 asm volatile("bar.sync 1, %0;" :: "n"(EPI_THREADS) : "memory");
-                if (et == 0) {
+                if (et == 0 && tile_valid) {
                     const int col0 = n0 + col_in_tile;
                     const int box_cols = p.c_is_f32 ? 32 : 64;
 #pragma unroll
@@ -343,6 +390,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     __syncwarp();
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                  // nobody leaves while a peer may still multicast into it
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
@@ -383,7 +431,7 @@ static bool make_map(CUtensorMap* map, const void* ptr, CUtensorMapDataType dt, 
            CUDA_SUCCESS;
 }
 
-struct Plan { bool ok; int bn, tiles_m, tiles_n, splits, kb_per_split, kb_total; };
+struct Plan { bool ok; int bn, cluster, tiles_m, tiles_n, groups_m, splits, kb_per_split, kb_total; };
 
 static Plan make_plan(const aecf_gemm_desc* d) {
     Plan pl{};
@@ -398,8 +446,13 @@ static Plan make_plan(const aecf_gemm_desc* d) {
     pl.tiles_m = static_cast<int>((d->m + tc::BM - 1) / tc::BM);
     pl.tiles_n = static_cast<int>((d->n + pl.bn - 1) / pl.bn);
     pl.kb_total = static_cast<int>((d->k + tc::BK - 1) / tc::BK);
+    // Pairs of CTAs (a cluster of 2) on vertically adjacent row blocks share the B tile by TMA multicast:
+    // a third less L2 -> SM traffic per FLOP, which is what bounds these K = 512..1024 products.
+    static const bool no_cluster = [] { const char* e = getenv("AECF_GEMM_CLUSTER"); return e && e[0] == '1'; }();
+    pl.cluster = (pl.tiles_m >= 2 && !no_cluster) ? 2 : 1;
+    pl.groups_m = (pl.tiles_m + pl.cluster - 1) / pl.cluster;
     const int sms = sm_count(d->device);
-    const long long tiles = static_cast<long long>(pl.tiles_m) * pl.tiles_n;
+    const long long tiles = static_cast<long long>(pl.groups_m) * pl.cluster * pl.tiles_n;
     int splits = 1;
     if (tiles * 2 <= sms && pl.kb_total >= 16) {       // weight-gradient shape: few tiles, long reduction
         splits = static_cast<int>(sms / tiles);
@@ -436,7 +489,7 @@ int gemm_tcgen05(const aecf_gemm_desc* d, const void* A, const void* B, const vo
     // A: K-major [m, k] -> box [BM rows, 64 k];  MN-major stored [k, m] -> box [64 k rows, 64 m]
     if (d->a_layout == AECF_K_MAJOR) ok &= make_map(&map_a, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->m, d->k, d->lda, BM, BK);
     else ok &= make_map(&map_a, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->k, d->m, d->lda, BK, 64);
-    if (d->b_layout == AECF_K_MAJOR) ok &= make_map(&map_b, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->n, d->k, d->ldb, pl.bn, BK);
+    if (d->b_layout == AECF_K_MAJOR) ok &= make_map(&map_b, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->n, d->k, d->ldb, pl.bn / pl.cluster, BK);
     else ok &= make_map(&map_b, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->k, d->n, d->ldb, BK, 64);
     const bool partial = pl.splits > 1;
     const bool c_f32 = partial || d->dtype_c == AECF_F32;
@@ -447,23 +500,36 @@ int gemm_tcgen05(const aecf_gemm_desc* d, const void* A, const void* B, const vo
 
     Params p{};
     p.m = static_cast<int>(d->m); p.n = static_cast<int>(d->n); p.k = static_cast<int>(d->k);
-    p.tiles_m = pl.tiles_m; p.tiles_n = pl.tiles_n; p.splits = pl.splits;
+    p.tiles_m = pl.tiles_m; p.tiles_n = pl.tiles_n; p.groups_m = pl.groups_m; p.splits = pl.splits;
     p.kb_per_split = pl.kb_per_split; p.kb_total = pl.kb_total;
     p.a_mn_major = d->a_layout == AECF_MN_MAJOR; p.b_mn_major = d->b_layout == AECF_MN_MAJOR;
     p.c_is_f32 = c_f32;
     p.has_bias = bias != nullptr; p.bias_is_bf16 = d->dtype_bias == AECF_BF16; p.bias = bias;
     p.partial_rows = pl.tiles_m * BM;              // padded: a ragged last row block must not spill into the next split
 
-    const long long items = static_cast<long long>(pl.tiles_m) * pl.tiles_n * pl.splits;
+    const long long items = static_cast<long long>(pl.groups_m) * pl.tiles_n * pl.splits;     // one per cluster
     const int sms = sm_count(d->device);
-    const int grid = static_cast<int>(items < sms ? items : sms);
-    if (pl.bn == 256) {
-        AECF_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<256>::SMEM_BYTES));
-        gemm_tcgen05_kernel<256><<<grid, NUM_THREADS, Cfg<256>::SMEM_BYTES, s>>>(map_a, map_b, map_c, p);
-    } else {
-        AECF_CUDA_OK(cudaFuncSetAttribute(gemm_tcgen05_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM_BYTES));
-        gemm_tcgen05_kernel<128><<<grid, NUM_THREADS, Cfg<128>::SMEM_BYTES, s>>>(map_a, map_b, map_c, p);
-    }
+    long long ctas = items * pl.cluster;
+    const long long cap = sms / pl.cluster * pl.cluster;
+    if (ctas > cap) ctas = cap;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(ctas));
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = pl.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+#define AECF_TC_LAUNCH(BN_, CL_)                                                                                  \
+    do {                                                                                                          \
+        auto kernel = gemm_tcgen05_kernel<BN_, CL_>;                                                              \
+        cfg.dynamicSmemBytes = Cfg<BN_>::SMEM_BYTES;                                                              \
+        AECF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN_>::SMEM_BYTES)); \
+        AECF_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, map_a, map_b, map_c, p));                                   \
+    } while (0)
+    if (pl.bn == 256) { if (pl.cluster == 2) AECF_TC_LAUNCH(256, 2); else AECF_TC_LAUNCH(256, 1); }
+    else { if (pl.cluster == 2) AECF_TC_LAUNCH(128, 2); else AECF_TC_LAUNCH(128, 1); }
+#undef AECF_TC_LAUNCH
     count_launch();
     AECF_CUDA_OK(cudaGetLastError());
     if (!partial) return AECF_OK;
