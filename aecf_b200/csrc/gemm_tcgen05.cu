@@ -29,6 +29,7 @@ constexpr int UMMA_K = 16;
 constexpr int STAGES = 4;
 constexpr int NUM_THREADS = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 constexpr int EPI_THREADS = 128;
+constexpr int PREFETCH_DIST = 12;  // k-blocks of L2 prefetch lookahead (1.5 tiles at K = 512)
 constexpr long long SPIN_LIMIT = 4000000000LL;   // ~2 s of SM clocks: trap instead of hanging the GPU
 
 template <int BN> struct Cfg {
@@ -93,6 +94,12 @@ __device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t*
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
         " [%0], [%1, {%4, %5}], [%2], %3;"
         :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1) : "memory");
+}
+// Pull a box into L2 only (no shared-memory destination): issued PREFETCH_DIST k-blocks ahead of the real
+// load so that the load hits L2 instead of paying the HBM latency inside the 4-stage ring.
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
+                 :: "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -229,46 +236,57 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
+            constexpr int PART = BN / CL;                 // this CTA's share of the B tile
+            // coordinates of one k-block's boxes; `go(map, dst_offset_in_stage_operand, c0, c1)` per box
+            auto for_each_a_box = [&](const WorkItem& w, int kb, auto&& go) {
+                const int k0 = (w.kb_begin + kb) * BK;
+                if (!p.a_mn_major) go(0, k0, w.m_blk * BM);
+                else
+                    for (int a = 0; a < BM / 64; ++a) go(a * (BK * 128), w.m_blk * BM + a * 64, k0);
+            };
+            auto for_each_b_box = [&](const WorkItem& w, int kb, auto&& go) {
+                const int k0 = (w.kb_begin + kb) * BK;
+                if (!p.b_mn_major) go(cta_rank * (PART * 128), k0, w.n_blk * BN + cta_rank * PART);
+                else
+                    for (int a = 0; a < PART / 64; ++a) {
+                        const int atom = cta_rank * (PART / 64) + a;
+                        go(atom * (BK * 128), w.n_blk * BN + atom * 64, k0);
+                    }
+            };
+            // lookahead cursor for the L2 prefetch stream
+            int pf_item = first_item, pf_kb = 0;
+            WorkItem pf_w = pf_item < items ? decode<CL>(p, pf_item, cta_rank) : WorkItem{};
+            auto pf_advance = [&]() {
+                if (pf_item >= items) return;
+                if (++pf_kb == pf_w.kb_count) {
+                    pf_item += item_stride;
+                    pf_kb = 0;
+                    if (pf_item < items) pf_w = decode<CL>(p, pf_item, cta_rank);
+                }
+            };
+            for (int i = 0; i < PREFETCH_DIST; ++i) pf_advance();
+
             int it = 0;
             for (int item = first_item; item < items; item += item_stride) {
                 const WorkItem w = decode<CL>(p, item, cta_rank);
                 for (int kb = 0; kb < w.kb_count; ++kb, ++it) {
+                    if (pf_item < items) {
+                        for_each_a_box(pf_w, pf_kb, [&](int, int c0, int c1) { tma_prefetch_2d(&map_a, c0, c1); });
+                        for_each_b_box(pf_w, pf_kb, [&](int, int c0, int c1) { tma_prefetch_2d(&map_b, c0, c1); });
+                        pf_advance();
+                    }
                     const int s = it % STAGES;
                     mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);     // freed by the MMAs of ALL CTAs of the cluster
                     uint8_t* a_dst = stage_base + s * C::STAGE_BYTES;
                     uint8_t* b_dst = a_dst + C::A_BYTES;
                     mbar_expect_tx(&full[s], C::STAGE_BYTES);
-                    const int k0 = (w.kb_begin + kb) * BK;
-                    if (!p.a_mn_major) {
-                        tma_load_2d(&map_a, &full[s], a_dst, k0, w.m_blk * BM);
-                    } else {
-#pragma unroll
-                        for (int a = 0; a < BM / 64; ++a)
-                            tma_load_2d(&map_a, &full[s], a_dst + a * (BK * 128), w.m_blk * BM + a * 64, k0);
-                    }
-                    if (CL == 1) {
-                        if (!p.b_mn_major) {
-                            tma_load_2d(&map_b, &full[s], b_dst, k0, w.n_blk * BN);
-                        } else {
-#pragma unroll
-                            for (int a = 0; a < BN / 64; ++a)
-                                tma_load_2d(&map_b, &full[s], b_dst + a * (BK * 128), w.n_blk * BN + a * 64, k0);
-                        }
-                    } else {
-                        // this CTA fetches 1/CL of the B tile and multicasts it to the whole cluster: every
-                        // CTA's stage receives the full tile, each from L2 only once
-                        constexpr int PART = BN / CL;
-                        if (!p.b_mn_major) {
-                            tma_load_2d_mc(&map_b, &full[s], b_dst + cta_rank * (PART * 128), k0,
-                                           w.n_blk * BN + cta_rank * PART, kAllCtas);
-                        } else {
-#pragma unroll
-                            for (int a = 0; a < PART / 64; ++a) {
-                                const int atom = cta_rank * (PART / 64) + a;
-                                tma_load_2d_mc(&map_b, &full[s], b_dst + atom * (BK * 128), w.n_blk * BN + atom * 64, k0, kAllCtas);
-                            }
-                        }
-                    }
+                    for_each_a_box(w, kb, [&](int off, int c0, int c1) { tma_load_2d(&map_a, &full[s], a_dst + off, c0, c1); });
+                    // with a cluster, this CTA fetches 1/CL of the B tile and multicasts it: every CTA's stage
+                    // receives the full tile, each part read from L2 only once
+                    for_each_b_box(w, kb, [&](int off, int c0, int c1) {
+                        if (CL == 1) tma_load_2d(&map_b, &full[s], b_dst + off, c0, c1);
+                        else tma_load_2d_mc(&map_b, &full[s], b_dst + off, c0, c1, kAllCtas);
+                    });
                 }
             }
         }
