@@ -29,7 +29,10 @@ constexpr int UMMA_K = 16;
 constexpr int STAGES = 4;
 constexpr int NUM_THREADS = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 constexpr int EPI_THREADS = 128;
-constexpr int PREFETCH_DIST = 12;  // k-blocks of L2 prefetch lookahead (1.5 tiles at K = 512)
+// k-blocks of L2 prefetch lookahead for the producer.  Measured on B200 (profiles/r1_gemm_experiments.md):
+// 12 k-blocks ahead made every projection 15-35 % SLOWER (the prefetch stream competes with the real
+// loads for TMA issue and L2 bandwidth), so it is off.
+constexpr int PREFETCH_DIST = 0;
 constexpr long long SPIN_LIMIT = 4000000000LL;   // ~2 s of SM clocks: trap instead of hanging the GPU
 
 template <int BN> struct Cfg {
@@ -270,7 +273,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             for (int item = first_item; item < items; item += item_stride) {
                 const WorkItem w = decode<CL>(p, item, cta_rank);
                 for (int kb = 0; kb < w.kb_count; ++kb, ++it) {
-                    if (pf_item < items) {
+                    if (PREFETCH_DIST > 0 && pf_item < items) {
                         for_each_a_box(pf_w, pf_kb, [&](int, int c0, int c1) { tma_prefetch_2d(&map_a, c0, c1); });
                         for_each_b_box(pf_w, pf_kb, [&](int, int c0, int c1) { tma_prefetch_2d(&map_b, c0, c1); });
                         pf_advance();
