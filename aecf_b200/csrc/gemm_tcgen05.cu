@@ -178,6 +178,48 @@ __device__ __forceinline__ uint32_t make_idesc(int bn, int a_mn, int b_mn) {
            (static_cast<uint32_t>(BM >> 4) << 24);
 }
 
+// ---- cta_group::2 helpers: a pair of CTAs (one cluster) works on one 256-row tile -------------------------
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;     // clears the CTA-rank bit of a shared::cluster address -> leader CTA
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    // lands in THIS CTA's shared memory, completes bytes on the LEADER CTA's barrier at the same offset
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_on_cta(uint64_t* bar, uint32_t target_cta) {   // arrive on `bar` of another CTA
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        :: "r"(smem_u32(bar)), "r"(target_cta) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {       // acquire at cluster scope
+    const uint32_t addr = smem_u32(bar);
+    const long long t0 = clock64();
+    while (true) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+        if (clock64() - t0 > SPIN_LIMIT) __trap();
+    }
+}
+
 struct WorkItem { int m_blk, n_blk, split, kb_begin, kb_count; };
 
 // Work items are (split, row-block group, column block); the CL CTAs of a cluster take the CL row blocks of
@@ -419,6 +461,220 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
 }
 
+// ================================================================================================
+// cta_group::2 variant: the two CTAs of a cluster compute ONE 256 x 256 tile.  Each CTA stages its own
+// 128 rows of A and HALF of the B tile (128 of the 256 columns), so a stage is 32 KB instead of 48 KB
+// and the ring is 6 deep instead of 4 -- 5 k-blocks of load latency covered instead of 3, which is what
+// the single-CTA kernel lacks (ncu: tensor pipe 59-78 % active, waiting on the ring).  The leader CTA
+// issues tcgen05.mma.cta_group::2 (M = 256); each CTA's TMEM receives its own 128 accumulator rows and
+// each CTA runs its own epilogue.
+// ================================================================================================
+constexpr int STAGES_2SM = 6;
+template <int BN> struct Cfg2 {
+    static constexpr int A_BYTES = BM * BK * 2;                 // 16 KB: this CTA's 128 rows
+    static constexpr int B_BYTES = (BN / 2) * BK * 2;           // 16 KB: this CTA's half of the columns
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int EPI_BYTES = 2 * BM * 128;
+    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int SMEM_BYTES = STAGES_2SM * STAGE_BYTES + EPI_BYTES + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                        const __grid_constant__ CUtensorMap map_c, const Params p) {
+    using C = Cfg2<BN>;
+    constexpr int S = STAGES_2SM;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stage_base = smem;
+    uint8_t* epi_base = smem + S * C::STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_base + C::EPI_BYTES);
+    uint64_t* full = bars;                    // [S]  leader's copy is the live one: bytes of BOTH CTAs' loads
+    uint64_t* empty = bars + S;               // [S]  per CTA, freed by the leader's MMA commit (multicast)
+    uint64_t* tmem_full = bars + 2 * S;       // [2]  per CTA, leader's MMA commit (multicast)
+    uint64_t* tmem_empty = bars + 2 * S + 2;  // [2]  leader's copy: both CTAs' epilogue threads arrive
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+    __shared__ float bias_tile[BN];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int items = p.groups_m * p.tiles_n * p.splits;
+    const int cta_rank = static_cast<int>(cluster_ctarank());
+    const bool leader = cta_rank == 0;
+    const int first_item = blockIdx.x / 2, item_stride = gridDim.x / 2;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_a); prefetch_tmap(&map_b); prefetch_tmap(&map_c);
+        for (int i = 0; i < S; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * EPI_THREADS); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(tmem_slot)), "r"(static_cast<uint32_t>(C::TMEM_COLS)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs; the leader also arms the barrier for both CTAs' bytes) =====
+        if (lane == 0) {
+            int it = 0;
+            for (int item = first_item; item < items; item += item_stride) {
+                const WorkItem w = decode<2>(p, item, cta_rank);
+                for (int kb = 0; kb < w.kb_count; ++kb, ++it) {
+                    const int s = it % S;
+                    mbar_wait_cluster(&empty[s], ((it / S) & 1) ^ 1);
+                    uint8_t* a_dst = stage_base + s * C::STAGE_BYTES;
+                    uint8_t* b_dst = a_dst + C::A_BYTES;
+                    if (leader) mbar_expect_tx(&full[s], 2 * C::STAGE_BYTES);
+                    const int k0 = (w.kb_begin + kb) * BK;
+                    if (!p.a_mn_major) {
+                        tma_load_2d_2sm(&map_a, &full[s], a_dst, k0, w.m_blk * BM);
+                    } else {
+#pragma unroll
+                        for (int a = 0; a < BM / 64; ++a)
+                            tma_load_2d_2sm(&map_a, &full[s], a_dst + a * (BK * 128), w.m_blk * BM + a * 64, k0);
+                    }
+                    const int n_half = w.n_blk * BN + cta_rank * (BN / 2);
+                    if (!p.b_mn_major) {
+                        tma_load_2d_2sm(&map_b, &full[s], b_dst, k0, n_half);
+                    } else {
+#pragma unroll
+                        for (int a = 0; a < BN / 128; ++a)
+                            tma_load_2d_2sm(&map_b, &full[s], b_dst + a * (BK * 128), n_half + a * 64, k0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: leader CTA only, one instruction drives both SMs' tensor cores =====
+        if (leader && lane == 0) {
+            // M = 256: m_dim field = 256 >> 4
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(p.a_mn_major) << 15) |
+                                   (static_cast<uint32_t>(p.b_mn_major) << 16) | (static_cast<uint32_t>(BN >> 3) << 17) |
+                                   (static_cast<uint32_t>(256 >> 4) << 24);
+            int it = 0, tile_it = 0;
+            for (int item = first_item; item < items; item += item_stride, ++tile_it) {
+                const WorkItem w = decode<2>(p, item, cta_rank);
+                const int as = tile_it & 1;
+                mbar_wait_cluster(&tmem_empty[as], ((tile_it >> 1) & 1) ^ 1);   // both CTAs drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * BN;
+                for (int kb = 0; kb < w.kb_count; ++kb, ++it) {
+                    const int s = it % S;
+                    mbar_wait_cluster(&full[s], (it / S) & 1);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(stage_base + s * C::STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + C::A_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < BK / UMMA_K; ++ks)
+                        umma_bf16_2sm(tmem_d, operand_desc(a_addr, p.a_mn_major, ks), operand_desc(b_addr, p.b_mn_major, ks),
+                                      idesc, (kb | ks) != 0 ? 1u : 0u);
+                    umma_commit_2sm(&empty[s], 0b11);                          // frees the slot in both CTAs
+                }
+                umma_commit_2sm(&tmem_full[as], 0b11);                         // accumulator complete in both CTAs
+            }
+        }
+    } else {
+        // ===== epilogue: each CTA drains its own 128 rows =====
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        const int et = threadIdx.x - 64;
+        int tile_it = 0;
+        for (int item = first_item; item < items; item += item_stride, ++tile_it) {
+            const WorkItem w = decode<2>(p, item, cta_rank);
+            const int as = tile_it & 1;
+            const int n0 = w.n_blk * BN, m0 = w.m_blk * BM;
+            const bool tile_valid = w.m_blk < p.tiles_m;
+            const bool direct = (p.splits == 1);
+            if (direct && p.has_bias) {
+                for (int i = et; i < BN; i += EPI_THREADS) {
+                    const int col = n0 + i;
+                    float b = 0.f;
+                    if (col < p.n)
+                        b = p.bias_is_bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(p.bias)[col])
+                                           : static_cast<const float*>(p.bias)[col];
+                    bias_tile[i] = b;
+                }
+            }
+            mbar_wait_cluster(&tmem_full[as], (tile_it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + as * BN + (static_cast<uint32_t>(quad * 32) << 16);
+            const int out_row0 = (direct ? 0 : w.split * p.partial_rows) + m0;
+            const int cols_per_round = p.c_is_f32 ? 64 : 128;
+            const int rounds = BN / cols_per_round;
+#pragma unroll 1
+            for (int rd = 0; rd < rounds; ++rd) {
+                if (et == 0) tma_store_wait_read();
+                asm volatile("bar.sync 1, %0;" :: "n"(EPI_THREADS) : "memory");
+                const int col_in_tile = rd * cols_per_round;
+#pragma unroll 1
+                for (int g = 0; g < cols_per_round / 32; ++g) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(t_row + col_in_tile + g * 32, r);
+                    tmem_ld_wait();
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        v[i] = __uint_as_float(r[i]);
+                        if (direct && p.has_bias) v[i] += bias_tile[col_in_tile + g * 32 + i];
+                    }
+                    if (p.c_is_f32) {
+                        uint8_t* box = epi_base + g * (BM * 128) + row * 128;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            *reinterpret_cast<uint4*>(box + ((c ^ (row & 7)) << 4)) =
+                                make_uint4(__float_as_uint(v[4 * c]), __float_as_uint(v[4 * c + 1]),
+                                           __float_as_uint(v[4 * c + 2]), __float_as_uint(v[4 * c + 3]));
+                    } else {
+                        uint8_t* box = epi_base + (g >> 1) * (BM * 128) + row * 128;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const int chunk = (g & 1) * 4 + c;
+                            *reinterpret_cast<uint4*>(box + ((chunk ^ (row & 7)) << 4)) =
+                                make_uint4(Vec<__nv_bfloat16>::pack2(v[8 * c], v[8 * c + 1]),
+                                           Vec<__nv_bfloat16>::pack2(v[8 * c + 2], v[8 * c + 3]),
+                                           Vec<__nv_bfloat16>::pack2(v[8 * c + 4], v[8 * c + 5]),
+                                           Vec<__nv_bfloat16>::pack2(v[8 * c + 6], v[8 * c + 7]));
+                        }
+                    }
+                }
+                if (rd == rounds - 1) {                      // this thread's TMEM reads are done: tell the LEADER's MMA
+                    tc_fence_before();
+                    mbar_arrive_on_cta(&tmem_empty[as], 0);
+                }
+                fence_proxy_async();
+                asm volatile("bar.sync 1, %0;" :: "n"(EPI_THREADS) : "memory");
+                if (et == 0 && tile_valid) {
+                    const int col0 = n0 + col_in_tile;
+                    const int box_cols = p.c_is_f32 ? 32 : 64;
+#pragma unroll
+                    for (int g = 0; g < 2; ++g)
+                        if (col0 + g * box_cols < p.n)
+                            tma_store_2d(&map_c, epi_base + g * (BM * 128), col0 + g * box_cols, out_row0);
+                    tma_store_commit();
+                }
+            }
+        }
+        if (et == 0) tma_store_wait_all();
+    }
+
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;"
+                     :: "r"(tmem_base), "r"(static_cast<uint32_t>(C::TMEM_COLS)) : "memory");
+    }
+}
+
 // ---- host side -------------------------------------------------------------------------------
 using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -452,7 +708,7 @@ static bool make_map(CUtensorMap* map, const void* ptr, CUtensorMapDataType dt, 
            CUDA_SUCCESS;
 }
 
-struct Plan { bool ok; int bn, cluster, tiles_m, tiles_n, groups_m, splits, kb_per_split, kb_total; };
+struct Plan { bool ok, two_sm; int bn, cluster, tiles_m, tiles_n, groups_m, splits, kb_per_split, kb_total; };
 
 static Plan make_plan(const aecf_gemm_desc* d) {
     Plan pl{};
@@ -471,6 +727,9 @@ static Plan make_plan(const aecf_gemm_desc* d) {
     // a third less L2 -> SM traffic per FLOP, which is what bounds these K = 512..1024 products.
     static const bool no_cluster = [] { const char* e = getenv("AECF_GEMM_CLUSTER"); return e && e[0] == '1'; }();
     pl.cluster = (pl.tiles_m >= 2 && !no_cluster) ? 2 : 1;
+    // cta_group::2 (one 256 x 256 tile per CTA pair, 6-stage ring): opt-in until it has been measured
+    static const bool want_2sm = [] { const char* e = getenv("AECF_GEMM_2SM"); return e && e[0] == '1'; }();
+    pl.two_sm = want_2sm && pl.cluster == 2 && pl.bn == 256;
     pl.groups_m = (pl.tiles_m + pl.cluster - 1) / pl.cluster;
     const int sms = sm_count(d->device);
     const long long tiles = static_cast<long long>(pl.groups_m) * pl.cluster * pl.tiles_n;
@@ -548,7 +807,12 @@ int gemm_tcgen05(const aecf_gemm_desc* d, const void* A, const void* B, const vo
         AECF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN_>::SMEM_BYTES)); \
         AECF_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, map_a, map_b, map_c, p));                                   \
     } while (0)
-    if (pl.bn == 256) { if (pl.cluster == 2) AECF_TC_LAUNCH(256, 2); else AECF_TC_LAUNCH(256, 1); }
+    if (pl.two_sm) {
+        auto kernel = gemm_tcgen05_2sm_kernel<256>;
+        cfg.dynamicSmemBytes = Cfg2<256>::SMEM_BYTES;
+        AECF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<256>::SMEM_BYTES));
+        AECF_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, map_a, map_b, map_c, p));
+    } else if (pl.bn == 256) { if (pl.cluster == 2) AECF_TC_LAUNCH(256, 2); else AECF_TC_LAUNCH(256, 1); }
     else { if (pl.cluster == 2) AECF_TC_LAUNCH(128, 2); else AECF_TC_LAUNCH(128, 1); }
 #undef AECF_TC_LAUNCH
     count_launch();
