@@ -469,12 +469,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 // issues tcgen05.mma.cta_group::2 (M = 256); each CTA's TMEM receives its own 128 accumulator rows and
 // each CTA runs its own epilogue.
 // ================================================================================================
-constexpr int STAGES_2SM = 6;
+constexpr int STAGES_2SM = 5;
 template <int BN> struct Cfg2 {
     static constexpr int A_BYTES = BM * BK * 2;                 // 16 KB: this CTA's 128 rows
     static constexpr int B_BYTES = (BN / 2) * BK * 2;           // 16 KB: this CTA's half of the columns
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int EPI_BYTES = 2 * BM * 128;
+    static constexpr int EPI_BUF = 2 * BM * 128;                // one staging buffer: two [128 rows x 128 B] boxes
+    static constexpr int EPI_BYTES = 2 * EPI_BUF;               // double buffered: convert round r+1 while round r is stored
     static constexpr int TMEM_COLS = 2 * BN;
     static constexpr int SMEM_BYTES = STAGES_2SM * STAGE_BYTES + EPI_BYTES + 1024 + 256;
 };
@@ -585,7 +586,7 @@ gemm_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
         const int et = threadIdx.x - 64;
-        int tile_it = 0;
+        int tile_it = 0, round_it = 0;
         for (int item = first_item; item < items; item += item_stride, ++tile_it) {
             const WorkItem w = decode<2>(p, item, cta_rank);
             const int as = tile_it & 1;
@@ -609,8 +610,9 @@ gemm_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
             const int cols_per_round = p.c_is_f32 ? 64 : 128;
             const int rounds = BN / cols_per_round;
 #pragma unroll 1
-            for (int rd = 0; rd < rounds; ++rd) {
-                if (et == 0) tma_store_wait_read();
+            for (int rd = 0; rd < rounds; ++rd, ++round_it) {
+                uint8_t* stage_buf = epi_base + (round_it & 1) * C::EPI_BUF;
+                if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store 2 rounds ago has left this buffer
                 asm volatile("bar.sync 1, %0;" :: "n"(EPI_THREADS) : "memory");
                 const int col_in_tile = rd * cols_per_round;
 #pragma unroll 1
@@ -625,14 +627,14 @@ gemm_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
                         if (direct && p.has_bias) v[i] += bias_tile[col_in_tile + g * 32 + i];
                     }
                     if (p.c_is_f32) {
-                        uint8_t* box = epi_base + g * (BM * 128) + row * 128;
+                        uint8_t* box = stage_buf + g * (BM * 128) + row * 128;
 #pragma unroll
                         for (int c = 0; c < 8; ++c)
                             *reinterpret_cast<uint4*>(box + ((c ^ (row & 7)) << 4)) =
                                 make_uint4(__float_as_uint(v[4 * c]), __float_as_uint(v[4 * c + 1]),
                                            __float_as_uint(v[4 * c + 2]), __float_as_uint(v[4 * c + 3]));
                     } else {
-                        uint8_t* box = epi_base + (g >> 1) * (BM * 128) + row * 128;
+                        uint8_t* box = stage_buf + (g >> 1) * (BM * 128) + row * 128;
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
                             const int chunk = (g & 1) * 4 + c;
@@ -656,7 +658,7 @@ gemm_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
 #pragma unroll
                     for (int g = 0; g < 2; ++g)
                         if (col0 + g * box_cols < p.n)
-                            tma_store_2d(&map_c, epi_base + g * (BM * 128), col0 + g * box_cols, out_row0);
+                            tma_store_2d(&map_c, stage_buf + g * (BM * 128), col0 + g * box_cols, out_row0);
                     tma_store_commit();
                 }
             }
