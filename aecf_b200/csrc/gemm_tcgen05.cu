@@ -729,9 +729,7 @@ static Plan make_plan(const aecf_gemm_desc* d) {
     // a third less L2 -> SM traffic per FLOP, which is what bounds these K = 512..1024 products.
     static const bool no_cluster = [] { const char* e = getenv("AECF_GEMM_CLUSTER"); return e && e[0] == '1'; }();
     pl.cluster = (pl.tiles_m >= 2 && !no_cluster) ? 2 : 1;
-    // cta_group::2 (one 256 x 256 tile per CTA pair, 6-stage ring): opt-in until it has been measured
-    static const bool want_2sm = [] { const char* e = getenv("AECF_GEMM_2SM"); return e && e[0] == '1'; }();
-    pl.two_sm = want_2sm && pl.cluster == 2 && pl.bn == 256;
+    pl.two_sm = false;        // decided below, once the k range of a work item is known
     pl.groups_m = (pl.tiles_m + pl.cluster - 1) / pl.cluster;
     const int sms = sm_count(d->device);
     const long long tiles = static_cast<long long>(pl.groups_m) * pl.cluster * pl.tiles_n;
@@ -744,6 +742,12 @@ static Plan make_plan(const aecf_gemm_desc* d) {
     }
     pl.kb_per_split = (pl.kb_total + splits - 1) / splits;
     pl.splits = (pl.kb_total + pl.kb_per_split - 1) / pl.kb_per_split;
+    // cta_group::2 (one 256 x 256 tile per CTA pair, deeper ring) wins when the main loop of a work item is
+    // long (measured: dX K=1024 173 -> 154-160 us, dW_kv 164 -> 158-161 us) and loses on the K = 512 products
+    // whose tiles are epilogue-heavy (kv_proj 180 -> 203 us); AECF_GEMM_2SM=0/1 forces it off/on.
+    static const int force_2sm = [] { const char* e = getenv("AECF_GEMM_2SM"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
+    const bool long_k = pl.kb_per_split >= 16;
+    pl.two_sm = pl.cluster == 2 && pl.bn == 256 && (force_2sm < 0 ? long_k : force_2sm == 1);
     pl.ok = true;
     return pl;
 }
