@@ -41,7 +41,8 @@ template <int BN> struct Cfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int EPI_BYTES = 2 * BM * 128;              // staging: two [128 rows x 128 B] swizzled boxes
     static constexpr int TMEM_COLS = 2 * BN;                    // double-buffered accumulator
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int BIAS_BYTES = 2 * BN * 4;               // fp32 bias slice, double buffered by tile parity
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BIAS_BYTES + 128 /*barriers*/;
 };
 
 struct Params {
@@ -243,17 +244,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_c, const Params p) {
     using C = Cfg<BN>;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem[];                          // swizzle-128B tiles need 1024-byte alignment
+    if (smem_u32(smem) & 1023u) __trap();
     uint8_t* stage_base = smem;
     uint8_t* epi_base = smem + STAGES * C::STAGE_BYTES;                       // 1024-aligned (stage sizes are)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_base + C::EPI_BYTES);
+    float* bias_tile = reinterpret_cast<float*>(epi_base + C::EPI_BYTES);      // [2][BN]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_base + C::EPI_BYTES + C::BIAS_BYTES);
     uint64_t* full = bars;                        // [STAGES] TMA -> MMA
     uint64_t* empty = bars + STAGES;              // [STAGES] MMA -> TMA
     uint64_t* tmem_full = bars + 2 * STAGES;      // [2] MMA -> epilogue
     uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2] epilogue -> MMA
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-    __shared__ float bias_tile[BN];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int items = p.groups_m * p.tiles_n * p.splits;
@@ -364,9 +365,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
     } else {
         // ===== epilogue: TMEM -> registers -> (+bias, convert) -> swizzled smem -> TMA store =====
+        // Every epilogue warp is self-contained: it owns 32 accumulator rows (its TMEM lane quadrant), a
+        // private 8 KB staging area (two [32 rows x 128 B] swizzled boxes) and issues its own TMA stores, so
+        // the four warps never wait for one another -- only __syncwarp(), no block-level barrier.
         const int quad = warp & 3;                   // TMEM lane quadrant this warp may read
-        const int row = quad * 32 + lane;            // row of the tile held by this thread
-        const int et = threadIdx.x - 64;             // 0..127
+        const int ew = warp - 2;                     // 0..3: staging slot
+        uint8_t* wbuf = epi_base + ew * (2 * 32 * 128);
         int tile_it = 0;
         for (int item = first_item; item < items; item += item_stride, ++tile_it) {
             const WorkItem w = decode<CL>(p, item, cta_rank);
@@ -374,28 +378,33 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const int n0 = w.n_blk * BN, m0 = w.m_blk * BM;
             const bool tile_valid = w.m_blk < p.tiles_m;       // false only for the filler tile of an odd last group
             const bool direct = (p.splits == 1);
-            // bias slice of this tile (fp32 in smem); previous tile's readers are past the barrier below
+            mbar_wait(&tmem_full[as], (tile_it >> 1) & 1);
+            tc_fence_after();
+            // fp32 bias slice of this tile, in the buffer of this tile's parity.  All four warps write the same
+            // values; a warp two tiles ahead would reuse this buffer, but it cannot pass the tmem_full wait
+            // above before every thread has finished the tile that last used it (tmem_empty arrives after the
+            // last bias read), so no reader ever sees a foreign tile's values.
+            float* wbias = bias_tile + as * BN;
             if (direct && p.has_bias) {
-                for (int i = et; i < BN; i += EPI_THREADS) {
+                for (int i = lane; i < BN; i += 32) {
                     const int col = n0 + i;
                     float b = 0.f;
                     if (col < p.n)
                         b = p.bias_is_bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(p.bias)[col])
                                            : static_cast<const float*>(p.bias)[col];
-                    bias_tile[i] = b;
+                    wbias[i] = b;
                 }
+                __syncwarp();
             }
-            mbar_wait(&tmem_full[as], (tile_it >> 1) & 1);
-            tc_fence_after();
             const uint32_t t_row = tmem_base + as * BN + (static_cast<uint32_t>(quad * 32) << 16);
-            const int out_row0 = (direct ? 0 : w.split * p.partial_rows) + m0;
-            // The staging buffer is two [128 rows x 128 B] boxes: 128 bf16 columns or 64 fp32 columns per round.
+            const int out_row0 = (direct ? 0 : w.split * p.partial_rows) + m0 + quad * 32;
+            // the staging area holds 128 bf16 columns or 64 fp32 columns per round
             const int cols_per_round = p.c_is_f32 ? 64 : 128;
             const int rounds = BN / cols_per_round;
 #pragma unroll 1
             for (int rd = 0; rd < rounds; ++rd) {
-                if (et == 0) tma_store_wait_read();                            // staging free again?
-                asm volatile("bar.sync 1, %0;" :: "n"(EPI_THREADS) : "memory");
+                if (lane == 0) tma_store_wait_read();                          // my previous store has left the staging area
+                __syncwarp();
                 const int col_in_tile = rd * cols_per_round;
 #pragma unroll 1
                 for (int g = 0; g < cols_per_round / 32; ++g) {                // 32 columns per TMEM load
@@ -406,23 +415,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         v[i] = __uint_as_float(r[i]);
-                        if (direct && p.has_bias) v[i] += bias_tile[col_in_tile + g * 32 + i];
+                        if (direct && p.has_bias) v[i] += wbias[col_in_tile + g * 32 + i];
                     }
                     if (p.c_is_f32) {
-                        // box g: [128 rows x 32 fp32 = 128 B]; 16-byte chunk c of row `row` sits at chunk c ^ (row & 7)
-                        uint8_t* box = epi_base + g * (BM * 128) + row * 128;
+                        // box g: [32 rows x 32 fp32 = 128 B]; 16-byte chunk c of row `lane` sits at chunk c ^ (lane & 7)
+                        uint8_t* box = wbuf + g * (32 * 128) + lane * 128;
 #pragma unroll
                         for (int c = 0; c < 8; ++c)
-                            *reinterpret_cast<uint4*>(box + ((c ^ (row & 7)) << 4)) =
+                            *reinterpret_cast<uint4*>(box + ((c ^ (lane & 7)) << 4)) =
                                 make_uint4(__float_as_uint(v[4 * c]), __float_as_uint(v[4 * c + 1]),
                                            __float_as_uint(v[4 * c + 2]), __float_as_uint(v[4 * c + 3]));
                     } else {
-                        // box g / 2: [128 rows x 64 bf16 = 128 B]; this load fills chunks (g % 2) * 4 .. + 3
-                        uint8_t* box = epi_base + (g >> 1) * (BM * 128) + row * 128;
+                        // box g / 2: [32 rows x 64 bf16 = 128 B]; this load fills chunks (g % 2) * 4 .. + 3
+                        uint8_t* box = wbuf + (g >> 1) * (32 * 128) + lane * 128;
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
                             const int chunk = (g & 1) * 4 + c;
-                            *reinterpret_cast<uint4*>(box + ((chunk ^ (row & 7)) << 4)) =
+                            *reinterpret_cast<uint4*>(box + ((chunk ^ (lane & 7)) << 4)) =
                                 make_uint4(Vec<__nv_bfloat16>::pack2(v[8 * c], v[8 * c + 1]),
                                            Vec<__nv_bfloat16>::pack2(v[8 * c + 2], v[8 * c + 3]),
                                            Vec<__nv_bfloat16>::pack2(v[8 * c + 4], v[8 * c + 5]),
@@ -435,19 +444,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     mbar_arrive(&tmem_empty[as]);
                 }
                 fence_proxy_async();                                           // smem writes -> visible to TMA
-                asm volatile("bar.sync 1, %0;" :: "n"(EPI_THREADS) : "memory");
-                if (et == 0 && tile_valid) {
+                __syncwarp();
+                if (lane == 0 && tile_valid) {
                     const int col0 = n0 + col_in_tile;
                     const int box_cols = p.c_is_f32 ? 32 : 64;
 #pragma unroll
                     for (int g = 0; g < 2; ++g)
                         if (col0 + g * box_cols < p.n)
-                            tma_store_2d(&map_c, epi_base + g * (BM * 128), col0 + g * box_cols, out_row0);
+                            tma_store_2d(&map_c, wbuf + g * (32 * 128), col0 + g * box_cols, out_row0);
                     tma_store_commit();
                 }
             }
         }
-        if (et == 0) tma_store_wait_all();
+        if (lane == 0) tma_store_wait_all();
     }
 
     __syncwarp();
@@ -779,9 +788,11 @@ int gemm_tcgen05(const aecf_gemm_desc* d, const void* A, const void* B, const vo
     else ok &= make_map(&map_b, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->k, d->n, d->ldb, BK, 64);
     const bool partial = pl.splits > 1;
     const bool c_f32 = partial || d->dtype_c == AECF_F32;
-    if (partial) ok &= make_map(&map_c, workspace, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, static_cast<long long>(pl.splits) * pl.tiles_m * BM, d->n, d->n, BM, 32);
-    else if (c_f32) ok &= make_map(&map_c, C, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d->m, d->n, d->ldc, BM, 32);
-    else ok &= make_map(&map_c, C, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->m, d->n, d->ldc, BM, 64);
+    // store boxes: the 1SM kernel's epilogue warps each store their own 32 rows; the 2SM kernel stores 128 rows at once
+    const int c_rows = pl.two_sm ? BM : 32;
+    if (partial) ok &= make_map(&map_c, workspace, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, static_cast<long long>(pl.splits) * pl.tiles_m * BM, d->n, d->n, c_rows, 32);
+    else if (c_f32) ok &= make_map(&map_c, C, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d->m, d->n, d->ldc, c_rows, 32);
+    else ok &= make_map(&map_c, C, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->m, d->n, d->ldc, c_rows, 64);
     if (!ok) return AECF_ERR_UNSUPPORTED;
 
     Params p{};
