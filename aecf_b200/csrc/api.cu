@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "pool_dispatch.cuh"
@@ -22,6 +23,11 @@ int set_cuda_error(cudaError_t err, const char* what) {
 int use_device(int device) {
     AECF_CUDA_OK(cudaSetDevice(device));
     return AECF_OK;
+}
+
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("AECF_PDL"); return !(e && e[0] == '0'); }();
+    return on;
 }
 
 int sm_count(int device) {
@@ -47,6 +53,7 @@ pool_bwd_finalize_kernel(const float* __restrict__ partials, int blocks, int D, 
     const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
     const int i = blockIdx.x * 32 + x;
     float s = 0.f;
+    pdl_wait();
     if (i < 3 * D) {
 #pragma unroll 16
         for (int b = y; b < blocks; b += 32) s += partials[static_cast<size_t>(b) * 3 * D + i];
@@ -217,10 +224,10 @@ int aecf_pool_bwd(const aecf_pool_desc* desc, const void* q, const void* kv, con
     if (rc != AECF_OK) return rc;
     const int n = 3 * p.D;
     TimedLaunch timed_finalize(static_cast<cudaStream_t>(stream), AECF_SITE_POOL_BWD_FINALIZE);
-    pool_bwd_finalize_kernel<<<(n + 31) / 32, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
-        p.partials, grid, p.D, p.scale, p.q_shared, p.q_shared ? static_cast<float*>(d_q) : nullptr, d_bias_kv);
+    AECF_CUDA_OK(launch_pdl(pool_bwd_finalize_kernel, dim3((n + 31) / 32), dim3(1024), 0, static_cast<cudaStream_t>(stream),
+                            p.partials, grid, p.D, p.scale, p.q_shared, p.q_shared ? static_cast<float*>(d_q) : nullptr,
+                            d_bias_kv));
     count_launch();
-    AECF_CUDA_OK(cudaGetLastError());
     return AECF_OK;
 }
 

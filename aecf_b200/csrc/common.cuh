@@ -42,6 +42,28 @@ struct TimedLaunch {                                          // brackets the la
         if (err__ != cudaSuccess) return ::aecf::set_cuda_error(err__, #call); \
     } while (0)
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------
+// Every kernel of the library is launched with programmatic stream serialization and starts with
+// pdl_wait(): its CTAs may be scheduled while the previous kernel of the stream is still draining
+// (launch latency and per-CTA prologues -- barrier init, TMEM allocation, tensor-map prefetch --
+// overlap that tail), but nothing touches global memory before the previous kernel has completed and
+// flushed.  AECF_PDL=0 in the environment falls back to ordinary launches.
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---- 16-byte vectors of the storage type ---------------------------------------------

@@ -11,6 +11,7 @@ template <typename T>
 __global__ void pack_in_bias_kernel(const float* __restrict__ d_q, const float* __restrict__ d_bias_kv, int D,
                                     T* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_wait();
     if (i >= 3 * D) return;
     out[i] = from_float<T>(i < D ? d_q[i] : d_bias_kv[i - D]);
 }
@@ -258,12 +259,12 @@ int aecf_fusion_bwd(const aecf_pool_desc* desc, const aecf_fusion_tensors* t, co
         TimedLaunch timed(s);
         const int n = 3 * D;
         if (dt == AECF_BF16)
-            pack_in_bias_kernel<__nv_bfloat16><<<(n + 255) / 256, 256, 0, s>>>(dbq, w.d_bias_kv, D,
-                                                                              static_cast<__nv_bfloat16*>(gr->d_in_proj_bias));
+            AECF_CUDA_OK(launch_pdl(pack_in_bias_kernel<__nv_bfloat16>, dim3((n + 255) / 256), dim3(256), 0, s, dbq, w.d_bias_kv,
+                                    D, static_cast<__nv_bfloat16*>(gr->d_in_proj_bias)));
         else
-            pack_in_bias_kernel<float><<<(n + 255) / 256, 256, 0, s>>>(dbq, w.d_bias_kv, D, static_cast<float*>(gr->d_in_proj_bias));
+            AECF_CUDA_OK(launch_pdl(pack_in_bias_kernel<float>, dim3((n + 255) / 256), dim3(256), 0, s, dbq, w.d_bias_kv, D,
+                                    static_cast<float*>(gr->d_in_proj_bias)));
         count_launch();
-        AECF_CUDA_OK(cudaGetLastError());
     }
     return AECF_OK;
 }

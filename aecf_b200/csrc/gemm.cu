@@ -25,6 +25,7 @@ gemm_simt_kernel(const TA* __restrict__ A, const TB* __restrict__ B, long long M
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    pdl_wait();
 
     for (long long k0 = k_begin; k0 < k_end; k0 += SBK) {
 #pragma unroll
@@ -74,6 +75,7 @@ gemm_simt_kernel(const TA* __restrict__ A, const TB* __restrict__ B, long long M
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, long long M, long long N, int splits,
                                      long long split_stride, GemmEpilogue ep) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    pdl_wait();
     if (i >= M * N) return;
     float s = 0.f;
     for (int z = 0; z < splits; ++z) s += partial[static_cast<long long>(z) * split_stride + i];
@@ -85,9 +87,9 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, long lon
 int launch_splitk_reduce(const float* partial, long long M, long long N, int splits, long long split_stride,
                          const GemmEpilogue& ep, cudaStream_t s) {
     const long long total = M * N;
-    splitk_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(partial, M, N, splits, split_stride, ep);
+    AECF_CUDA_OK(launch_pdl(splitk_reduce_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, s, partial,
+                            M, N, splits, split_stride, ep));
     count_launch();
-    AECF_CUDA_OK(cudaGetLastError());
     return AECF_OK;
 }
 
@@ -110,14 +112,14 @@ static int launch_simt(const aecf_gemm_desc* d, const void* A, const void* B, Ge
     const TA* a = static_cast<const TA*>(A);
     const TB* b = static_cast<const TB*>(B);
     const bool ak = d->a_layout == AECF_K_MAJOR, bk = d->b_layout == AECF_K_MAJOR;
-#define AECF_SIMT(AK, BK) gemm_simt_kernel<TA, TB, AK, BK><<<grid, 256, 0, s>>>(a, b, d->m, d->n, d->k, d->lda, d->ldb, kps, ep)
+#define AECF_SIMT(AK, BK) \
+    AECF_CUDA_OK(launch_pdl(gemm_simt_kernel<TA, TB, AK, BK>, grid, dim3(256), 0, s, a, b, d->m, d->n, d->k, d->lda, d->ldb, kps, ep))
     if (ak && bk) AECF_SIMT(true, true);
     else if (ak && !bk) AECF_SIMT(true, false);
     else if (!ak && bk) AECF_SIMT(false, true);
     else AECF_SIMT(false, false);
 #undef AECF_SIMT
     count_launch();
-    AECF_CUDA_OK(cudaGetLastError());
     return AECF_OK;
 }
 
@@ -128,6 +130,7 @@ __global__ void __launch_bounds__(256)
 gemv_kmajor_kernel(const TA* __restrict__ a, long long a_stride, const TB* __restrict__ B, long long N, long long K,
                    long long ldb, GemmEpilogue ep) {
     const long long n = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    pdl_wait();
     if (n >= N) return;
     const int lane = threadIdx.x & 31;
     float acc = 0.f;
@@ -145,6 +148,7 @@ gemv_mnmajor_kernel(const TA* __restrict__ a, long long a_stride, const TB* __re
     const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
     const long long n = static_cast<long long>(blockIdx.x) * 32 + x;
     float acc = 0.f;
+    pdl_wait();
     if (n < N) {
 #pragma unroll 4
         for (long long k = y; k < K; k += 8) acc = fmaf(load_elem(a + k * a_stride), load_elem(B + k * ldb + n), acc);
@@ -165,11 +169,12 @@ static int launch_gemv(const aecf_gemm_desc* d, const void* A, const void* B, co
     const TB* b = static_cast<const TB*>(B);
     const long long a_stride = d->a_layout == AECF_K_MAJOR ? 1 : d->lda;
     if (d->b_layout == AECF_K_MAJOR)
-        gemv_kmajor_kernel<TA, TB><<<static_cast<unsigned>((d->n + 7) / 8), 256, 0, s>>>(a, a_stride, b, d->n, d->k, d->ldb, ep);
+        AECF_CUDA_OK(launch_pdl(gemv_kmajor_kernel<TA, TB>, dim3(static_cast<unsigned>((d->n + 7) / 8)), dim3(256), 0, s, a,
+                                a_stride, b, d->n, d->k, d->ldb, ep));
     else
-        gemv_mnmajor_kernel<TA, TB><<<static_cast<unsigned>((d->n + 31) / 32), 256, 0, s>>>(a, a_stride, b, d->n, d->k, d->ldb, ep);
+        AECF_CUDA_OK(launch_pdl(gemv_mnmajor_kernel<TA, TB>, dim3(static_cast<unsigned>((d->n + 31) / 32)), dim3(256), 0, s, a,
+                                a_stride, b, d->n, d->k, d->ldb, ep));
     count_launch();
-    AECF_CUDA_OK(cudaGetLastError());
     return AECF_OK;
 }
 

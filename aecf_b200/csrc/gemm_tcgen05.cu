@@ -278,6 +278,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (CL > 1) cluster_sync_all();                  // peers' barriers exist before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                                      // everything above overlapped the previous kernel's tail
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -529,6 +530,7 @@ gemm_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
 
     if (warp == 0) {
         // ===== TMA producer (both CTAs; the leader also arms the barrier for both CTAs' bytes) =====
@@ -813,10 +815,12 @@ int gemm_tcgen05(const aecf_gemm_desc* d, const void* A, const void* B, const vo
     cfg.gridDim = dim3(static_cast<unsigned>(ctas));
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = pl.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
 #define AECF_TC_LAUNCH(BN_, CL_)                                                                                  \
     do {                                                                                                          \
         auto kernel = gemm_tcgen05_kernel<BN_, CL_>;                                                              \

@@ -25,6 +25,7 @@ colsum_stage1(const T* __restrict__ x, long long rows, long long cols, long long
     float acc[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) acc[v] = 0.f;
+    pdl_wait();
     if (col0 < cols) {
         constexpr int U = 8;                               // independent 16-byte loads in flight per thread
         long long r = r0 + threadIdx.y;
@@ -68,6 +69,7 @@ colsum_stage2(const float* __restrict__ partial, long long cols, int splits, TO*
     const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
     const long long c = static_cast<long long>(blockIdx.x) * 32 + x;
     float s = 0.f;
+    pdl_wait();
     if (c < cols) {
 #pragma unroll 4
         for (int i = y; i < splits; i += 8) s += partial[static_cast<long long>(i) * cols + c];
@@ -82,7 +84,7 @@ colsum_stage2(const float* __restrict__ partial, long long cols, int splits, TO*
 }
 
 static int colsum_splits(long long rows) {
-    long long s = (rows + 511) / 512;
+    long long s = (rows + 255) / 256;
     if (s < 1) s = 1;
     if (s > COLSUM_MAX_SPLITS) s = COLSUM_MAX_SPLITS;
     return static_cast<int>(s);
@@ -99,7 +101,8 @@ __global__ void __launch_bounds__(1024) entropy_loss_fwd_kernel(const float* __r
                                                                 float* __restrict__ loss) {
     __shared__ float warp_sum[32];
     float acc = 0.f;
-    constexpr int U = 8;                                   // independent loads in flight per thread
+    pdl_wait();
+    constexpr int U = 32;                                  // independent loads in flight per thread
     for (long long i0 = threadIdx.x; i0 < n; i0 += static_cast<long long>(blockDim.x) * U) {
         float v[U];
 #pragma unroll
@@ -331,16 +334,18 @@ int aecf_colsum(int32_t device, int32_t dtype_x, int32_t dtype_out, const void* 
     const dim3 block(32, COLSUM_ROW_LANES), grid(static_cast<unsigned>((cols / V + 31) / 32), splits);
     float* partial = static_cast<float*>(workspace);
     if (dtype_x == AECF_BF16)
-        colsum_stage1<__nv_bfloat16><<<grid, block, 0, s>>>(static_cast<const __nv_bfloat16*>(x), rows, cols, ld, splits, partial);
+        AECF_CUDA_OK(launch_pdl(colsum_stage1<__nv_bfloat16>, grid, block, 0, s, static_cast<const __nv_bfloat16*>(x), rows, cols,
+                                ld, splits, partial));
     else
-        colsum_stage1<float><<<grid, block, 0, s>>>(static_cast<const float*>(x), rows, cols, ld, splits, partial);
-    const unsigned g2 = static_cast<unsigned>((cols + 31) / 32);
+        AECF_CUDA_OK(launch_pdl(colsum_stage1<float>, grid, block, 0, s, static_cast<const float*>(x), rows, cols, ld, splits,
+                                partial));
+    const dim3 g2(static_cast<unsigned>((cols + 31) / 32));
     if (dtype_out == AECF_BF16)
-        colsum_stage2<__nv_bfloat16><<<g2, 256, 0, s>>>(partial, cols, splits, static_cast<__nv_bfloat16*>(out));
+        AECF_CUDA_OK(launch_pdl(colsum_stage2<__nv_bfloat16>, g2, dim3(256), 0, s, partial, cols, splits,
+                                static_cast<__nv_bfloat16*>(out)));
     else
-        colsum_stage2<float><<<g2, 256, 0, s>>>(partial, cols, splits, static_cast<float*>(out));
+        AECF_CUDA_OK(launch_pdl(colsum_stage2<float>, g2, dim3(256), 0, s, partial, cols, splits, static_cast<float*>(out)));
     count_launch(2);
-    AECF_CUDA_OK(cudaGetLastError());
     return AECF_OK;
 }
 
@@ -349,9 +354,9 @@ int aecf_entropy_loss_fwd(int32_t device, const float* entropy, int64_t n, float
     int rc = use_device(device);
     if (rc != AECF_OK) return rc;
     TimedLaunch timed(static_cast<cudaStream_t>(stream), AECF_SITE_ENTROPY_LOSS);
-    entropy_loss_fwd_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(entropy, n, target, loss);
+    AECF_CUDA_OK(launch_pdl(entropy_loss_fwd_kernel, dim3(1), dim3(1024), 0, static_cast<cudaStream_t>(stream), entropy,
+                            static_cast<long long>(n), target, loss));
     count_launch();
-    AECF_CUDA_OK(cudaGetLastError());
     return AECF_OK;
 }
 

@@ -48,6 +48,7 @@ pool_bwd_kernel(const PoolParams p) {
     float* acc_sds = strip + 2 * Smem::ACC;                           // [J][32]
     for (int i = lane; i < Smem::PER_WARP; i += 32) strip[i] = 0.f;
     __syncwarp();
+    pdl_wait();
 
     const int slice = warp % p.WPS;
     const int c0 = slice * Core::CPW + lane;

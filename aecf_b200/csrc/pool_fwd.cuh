@@ -102,6 +102,7 @@ pool_fwd_kernel(const PoolParams p) {
     const bool row_ok = row0 + slot < p.B;
     const long long row = row_ok ? row0 + slot : p.B - 1;   // tail warps recompute the last row, store nothing
     const int c0 = slice * Core::CPW + lane;
+    pdl_wait();
 
     const char* kv_row = static_cast<const char*>(p.kv) + Core::row_offset(p, row, c0);
     auto load_kv = [&](int m, int half, int j) -> uint4 {
@@ -208,6 +209,7 @@ pool_fwd_stream_kernel(const PoolParams p, const long long rows_per_warp) {
     uint4* my = ring + static_cast<size_t>(warp) * 2 * CH * 32;
     const int c0 = lane;
     const char* kv = static_cast<const char*>(p.kv);
+    pdl_wait();
 
     auto prefetch = [&](long long row, int stage) {
         const char* src = kv + Core::row_offset(p, row, c0);
