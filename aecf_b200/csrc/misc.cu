@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(1024) entropy_loss_fwd_kernel(const float* __r
     __shared__ float warp_sum[32];
     float acc = 0.f;
     pdl_wait();
-    constexpr int U = 32;                                  // independent loads in flight per thread
+    constexpr int U = 8;                                   // independent loads in flight per thread
     for (long long i0 = threadIdx.x; i0 < n; i0 += static_cast<long long>(blockDim.x) * U) {
         float v[U];
 #pragma unroll
