@@ -12,7 +12,7 @@ from typing import Optional
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libaecf_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # enums of include/aecf_b200.h
 F32, BF16 = 0, 1
@@ -22,7 +22,8 @@ OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_ALIGNMENT, ERR_WORKSPACE, ERR_CUDA = 0, -1
 
 EXPORTS = (
     "aecf_pool_fwd", "aecf_pool_bwd", "aecf_pool_bwd_workspace_bytes",
-    "aecf_gemm", "aecf_gemm_workspace_bytes",
+    "aecf_fold_score_cols", "aecf_pool_fwd_folded", "aecf_pool_bwd_folded", "aecf_fold_prepare", "aecf_fold_finish",
+    "aecf_gemm", "aecf_gemm_aux", "aecf_gemm_workspace_bytes",
     "aecf_colsum", "aecf_colsum_workspace_bytes",
     "aecf_entropy_loss_fwd", "aecf_entropy_loss_bwd", "aecf_curriculum_mask", "aecf_entropy_bwd", "aecf_sdpa_fwd",
     "aecf_fusion_fwd", "aecf_fusion_bwd", "aecf_fusion_workspace_bytes",
@@ -41,6 +42,7 @@ class PoolDesc(C.Structure):
         ("seed", C.c_uint64), ("offset", C.c_uint64), ("row0", C.c_uint64),
         ("bias_stride_b", C.c_int64), ("bias_stride_h", C.c_int64),
         ("kv_stride_b", C.c_int64), ("kv_stride_m", C.c_int64),
+        ("fold_key", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -58,7 +60,7 @@ class GemmDesc(C.Structure):
 class FusionTensors(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "query", "key", "value", "in_proj_weight", "in_proj_bias", "out_proj_weight", "out_proj_bias", "score_bias",
-        "q_proj", "kv", "ctx", "out", "pooled", "entropy", "mask_rate", "masked", "mask_bits")]
+        "q_proj", "kv", "ctx", "out", "pooled", "entropy", "mask_rate", "masked", "mask_bits", "scores", "folded_w")]
 
 
 class FusionGrads(C.Structure):
@@ -68,7 +70,7 @@ class FusionGrads(C.Structure):
 
 
 BWD_ALL, BWD_OUT_PROJ, BWD_REST = 0, 1, 2
-SITE_COUNT = 16
+SITE_COUNT = 18
 
 
 class AecfError(RuntimeError):
@@ -95,6 +97,18 @@ def _declare(lib):
     lib.aecf_pool_bwd.argtypes = [C.POINTER(PoolDesc), vp, vp, f32p, vp, f32p, f32p, vp, vp, f32p, vp, C.c_size_t, vp]
     lib.aecf_pool_bwd_workspace_bytes.restype = C.c_size_t
     lib.aecf_pool_bwd_workspace_bytes.argtypes = [C.POINTER(PoolDesc)]
+    lib.aecf_fold_score_cols.restype = C.c_int
+    lib.aecf_fold_score_cols.argtypes = [C.c_int32, C.c_int32]
+    lib.aecf_pool_fwd_folded.restype = C.c_int
+    lib.aecf_pool_fwd_folded.argtypes = [C.POINTER(PoolDesc), f32p, vp, f32p, vp, f32p, f32p, f32p, f32p, u8p, vp]
+    lib.aecf_pool_bwd_folded.restype = C.c_int
+    lib.aecf_pool_bwd_folded.argtypes = [C.POINTER(PoolDesc), vp, f32p, vp, f32p, vp, f32p, f32p, vp, f32p, vp, C.c_size_t, vp]
+    lib.aecf_fold_prepare.restype = C.c_int
+    lib.aecf_fold_prepare.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, f32p, vp, vp, vp]
+    lib.aecf_fold_finish.restype = C.c_int
+    lib.aecf_fold_finish.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, f32p, f32p, vp, vp, f32p, vp]
+    lib.aecf_gemm_aux.restype = C.c_int
+    lib.aecf_gemm_aux.argtypes = [C.POINTER(GemmDesc), vp, vp, vp, vp, f32p, C.c_int32, C.c_int64, vp, C.c_size_t, vp]
     lib.aecf_gemm.restype = C.c_int
     lib.aecf_gemm.argtypes = [C.POINTER(GemmDesc), vp, vp, vp, vp, vp, C.c_size_t, vp]
     lib.aecf_gemm_workspace_bytes.restype = C.c_size_t

@@ -72,11 +72,12 @@ pool_bwd_finalize_kernel(const float* __restrict__ partials, int blocks, int D, 
 struct PoolPlan {
     PoolParams p;
     int M, J;
-    bool drop, bf16;
+    bool drop, bf16, fold;
 };
 
-// Validate a descriptor and derive the lane/head geometry (pool_core.cuh).
-static int make_plan(const aecf_pool_desc* d, PoolPlan* plan) {
+// Validate a descriptor and derive the lane/head geometry (pool_core.cuh).  `fold`: the folded-key-projection
+// entry points, whose kv / scores / d_kv are matrices of B*M rows addressed by ROW strides.
+static int make_plan(const aecf_pool_desc* d, PoolPlan* plan, bool fold = false) {
     if (d == nullptr) return AECF_ERR_INVALID;
     if (d->batch < 0 || d->embed_dim <= 0 || d->num_heads <= 0 || d->num_tokens <= 0) return AECF_ERR_INVALID;
     if (d->embed_dim % d->num_heads != 0) return AECF_ERR_INVALID;
@@ -114,13 +115,27 @@ static int make_plan(const aecf_pool_desc* d, PoolPlan* plan) {
     p.rng.k0 = static_cast<uint32_t>(d->seed); p.rng.k1 = static_cast<uint32_t>(d->seed >> 32);
     p.rng.offset = static_cast<uint32_t>(d->offset); p.rng.row0 = d->row0;
     p.bias_sb = d->bias_stride_b; p.bias_sh = d->bias_stride_h;
-    if (d->kv_stride_b == 0 && d->kv_stride_m == 0) {
+    if (fold) {
+        if (!d->q_is_shared) return AECF_ERR_UNSUPPORTED;       // the fold needs one query for all rows
+        long long rs_b = d->kv_stride_b, rs_m = d->kv_stride_m;   // in rows of the [B*M, .] matrices
+        if (rs_b == 0 && rs_m == 0) { rs_b = d->num_tokens; rs_m = 1; }
+        if (rs_b < 1 || rs_m < 1) return AECF_ERR_INVALID;
+        const int hsp = aecf_fold_score_cols(d->dtype, H);
+        p.HSP = hsp;
+        p.kv_sb = rs_b * D; p.kv_sm = rs_m * D;
+        p.dkv_sb = rs_b * (D + hsp); p.dkv_sm = rs_m * (D + hsp);
+        const int hs = (H + 3) & ~3;
+        p.s_sb = rs_b * hs; p.s_sm = rs_m * hs;
+    } else if (d->kv_stride_b == 0 && d->kv_stride_m == 0) {
         p.kv_sm = 2LL * D; p.kv_sb = p.kv_sm * d->num_tokens;
+        p.dkv_sb = p.kv_sb; p.dkv_sm = p.kv_sm;
     } else {
         if (d->kv_stride_b < 2LL * D || d->kv_stride_m < 2LL * D) return AECF_ERR_INVALID;
         if ((d->kv_stride_b * (16 / V)) % 16 != 0 || (d->kv_stride_m * (16 / V)) % 16 != 0) return AECF_ERR_ALIGNMENT;
         p.kv_sb = d->kv_stride_b; p.kv_sm = d->kv_stride_m;
+        p.dkv_sb = p.kv_sb; p.dkv_sm = p.kv_sm;
     }
+    plan->fold = fold;
     plan->M = d->num_tokens; plan->J = J;
     plan->drop = d->training && d->dropout_p > 0.f;
     plan->bf16 = d->dtype == AECF_BF16;
@@ -150,61 +165,82 @@ const char* aecf_strerror(int status) {
 const char* aecf_last_cuda_error(void) { return g_cuda_error; }
 uint64_t aecf_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 const char* aecf_build_info(void) {
-    return "aecf_b200 abi 1, sm_100a, nvcc " AECF_STR(__CUDACC_VER_MAJOR__) "." AECF_STR(__CUDACC_VER_MINOR__);
+    return "aecf_b200 abi " AECF_STR(AECF_ABI_VERSION) ", sm_100a, nvcc " AECF_STR(__CUDACC_VER_MAJOR__) "." AECF_STR(__CUDACC_VER_MINOR__);
 }
 
-int aecf_pool_fwd(const aecf_pool_desc* desc, const void* q, const void* kv, const float* score_bias,
-                  void* ctx, float* pooled, float* entropy, float* mask_rate, float* masked,
-                  uint8_t* mask_bits, void* stream) {
+static int pool_fwd_impl(const aecf_pool_desc* desc, bool fold, const void* q, const float* scores, const void* kv,
+                         const float* score_bias, void* ctx, float* pooled, float* entropy, float* mask_rate,
+                         float* masked, uint8_t* mask_bits, void* stream) {
     PoolPlan plan;
-    int rc = make_plan(desc, &plan);
+    int rc = make_plan(desc, &plan, fold);
     if (rc != AECF_OK) return rc;
     if (desc->batch == 0) return AECF_OK;
-    if (!q || !kv || !ctx || !pooled) return AECF_ERR_INVALID;
-    if (!aligned16(q) || !aligned16(kv) || !aligned16(ctx)) return AECF_ERR_ALIGNMENT;
+    if ((!fold && !q) || (fold && !scores) || !kv || !ctx || !pooled) return AECF_ERR_INVALID;
+    if ((q && !aligned16(q)) || !aligned16(kv) || !aligned16(ctx)) return AECF_ERR_ALIGNMENT;
     if ((rc = use_device(desc->device)) != AECF_OK) return rc;
     PoolParams& p = plan.p;
-    p.q = q; p.kv = kv; p.bias = score_bias;
+    p.q = q; p.kv = kv; p.bias = score_bias; p.scores = scores;
     p.ctx = ctx; p.pooled = pooled; p.entropy = entropy; p.mask_rate = mask_rate; p.masked = masked;
     p.mask_bits = mask_bits;
     const int grid = static_cast<int>((p.B + p.SPC - 1) / p.SPC);
     const int sms = sm_count(desc->device);
     TimedLaunch timed(static_cast<cudaStream_t>(stream));
     if (plan.bf16)
-        return plan.drop ? launch_pool_fwd<__nv_bfloat16, true>(plan.M, plan.J, p, grid, sms, stream)
-                         : launch_pool_fwd<__nv_bfloat16, false>(plan.M, plan.J, p, grid, sms, stream);
-    return plan.drop ? launch_pool_fwd<float, true>(plan.M, plan.J, p, grid, sms, stream)
-                     : launch_pool_fwd<float, false>(plan.M, plan.J, p, grid, sms, stream);
+        return plan.drop ? launch_pool_fwd<__nv_bfloat16, true>(plan.M, plan.J, p, grid, sms, fold, stream)
+                         : launch_pool_fwd<__nv_bfloat16, false>(plan.M, plan.J, p, grid, sms, fold, stream);
+    return plan.drop ? launch_pool_fwd<float, true>(plan.M, plan.J, p, grid, sms, fold, stream)
+                     : launch_pool_fwd<float, false>(plan.M, plan.J, p, grid, sms, fold, stream);
 }
+
+extern "C" {
+
+int aecf_fold_score_cols(int32_t dtype, int32_t num_heads) {
+    const int per16 = dtype == AECF_BF16 ? 8 : 4;
+    return (num_heads + per16 - 1) / per16 * per16;
+}
+
+int aecf_pool_fwd(const aecf_pool_desc* desc, const void* q, const void* kv, const float* score_bias,
+                  void* ctx, float* pooled, float* entropy, float* mask_rate, float* masked,
+                  uint8_t* mask_bits, void* stream) {
+    return pool_fwd_impl(desc, false, q, nullptr, kv, score_bias, ctx, pooled, entropy, mask_rate, masked, mask_bits, stream);
+}
+
+int aecf_pool_fwd_folded(const aecf_pool_desc* desc, const float* scores, const void* v, const float* score_bias,
+                         void* ctx, float* pooled, float* entropy, float* mask_rate, float* masked,
+                         uint8_t* mask_bits, void* stream) {
+    return pool_fwd_impl(desc, true, nullptr, scores, v, score_bias, ctx, pooled, entropy, mask_rate, masked, mask_bits, stream);
+}
+
+}  // extern "C"
 
 size_t aecf_pool_bwd_workspace_bytes(const aecf_pool_desc* desc) {
     if (desc == nullptr || desc->embed_dim <= 0) return 0;
     return static_cast<size_t>(POOL_BWD_MAX_BLOCKS) * 3 * desc->embed_dim * sizeof(float);
 }
 
-int aecf_pool_bwd(const aecf_pool_desc* desc, const void* q, const void* kv, const float* score_bias,
-                  const void* d_ctx, const float* d_pooled, const float* d_entropy,
-                  void* d_kv, void* d_q, float* d_bias_kv,
-                  void* workspace, size_t workspace_bytes, void* stream) {
+static int pool_bwd_impl(const aecf_pool_desc* desc, bool fold, const void* q, const float* scores, const void* kv,
+                         const float* score_bias, const void* d_ctx, const float* d_pooled, const float* d_entropy,
+                         void* d_kv, void* d_q, float* d_bias_kv, void* workspace, size_t workspace_bytes, void* stream) {
     PoolPlan plan;
-    int rc = make_plan(desc, &plan);
+    int rc = make_plan(desc, &plan, fold);
     if (rc != AECF_OK) return rc;
-    if (!q || !kv || !d_ctx || !d_kv || !d_q || !workspace) return AECF_ERR_INVALID;
-    if (!aligned16(q) || !aligned16(kv) || !aligned16(d_ctx) || !aligned16(d_kv) || !aligned16(d_q) ||
+    if (!q || !kv || !d_ctx || !d_kv || (!fold && !d_q) || (fold && !scores) || !workspace) return AECF_ERR_INVALID;
+    if (!aligned16(q) || !aligned16(kv) || !aligned16(d_ctx) || !aligned16(d_kv) || (d_q && !aligned16(d_q)) ||
         !aligned16(workspace))
         return AECF_ERR_ALIGNMENT;
     if (workspace_bytes < aecf_pool_bwd_workspace_bytes(desc)) return AECF_ERR_WORKSPACE;
+    if (desc->batch == 0) return AECF_OK;
     if ((rc = use_device(desc->device)) != AECF_OK) return rc;
     PoolParams& p = plan.p;
-    p.q = q; p.kv = kv; p.bias = score_bias;
+    p.q = q; p.kv = kv; p.bias = score_bias; p.scores = scores;
     p.d_ctx = d_ctx; p.d_pooled = d_pooled; p.d_entropy = d_entropy; p.d_kv = d_kv; p.d_q = d_q;
     p.partials = static_cast<float*>(workspace);
 
     int per_sm;
-    if (plan.bf16) per_sm = plan.drop ? pool_bwd_blocks_per_sm<__nv_bfloat16, true>(plan.M, plan.J)
-                                      : pool_bwd_blocks_per_sm<__nv_bfloat16, false>(plan.M, plan.J);
-    else per_sm = plan.drop ? pool_bwd_blocks_per_sm<float, true>(plan.M, plan.J)
-                            : pool_bwd_blocks_per_sm<float, false>(plan.M, plan.J);
+    if (plan.bf16) per_sm = plan.drop ? pool_bwd_blocks_per_sm<__nv_bfloat16, true>(plan.M, plan.J, fold)
+                                      : pool_bwd_blocks_per_sm<__nv_bfloat16, false>(plan.M, plan.J, fold);
+    else per_sm = plan.drop ? pool_bwd_blocks_per_sm<float, true>(plan.M, plan.J, fold)
+                            : pool_bwd_blocks_per_sm<float, false>(plan.M, plan.J, fold);
     if (per_sm <= 0) per_sm = 1;
     long long want = (p.B + p.SPC - 1) / p.SPC;
     long long cap = static_cast<long long>(sm_count(desc->device)) * per_sm;   // persistent: one resident wave
@@ -215,11 +251,11 @@ int aecf_pool_bwd(const aecf_pool_desc* desc, const void* q, const void* kv, con
     {
         TimedLaunch timed(static_cast<cudaStream_t>(stream));
         if (plan.bf16)
-            rc = plan.drop ? launch_pool_bwd<__nv_bfloat16, true>(plan.M, plan.J, p, grid, stream)
-                           : launch_pool_bwd<__nv_bfloat16, false>(plan.M, plan.J, p, grid, stream);
+            rc = plan.drop ? launch_pool_bwd<__nv_bfloat16, true>(plan.M, plan.J, p, grid, fold, stream)
+                           : launch_pool_bwd<__nv_bfloat16, false>(plan.M, plan.J, p, grid, fold, stream);
         else
-            rc = plan.drop ? launch_pool_bwd<float, true>(plan.M, plan.J, p, grid, stream)
-                           : launch_pool_bwd<float, false>(plan.M, plan.J, p, grid, stream);
+            rc = plan.drop ? launch_pool_bwd<float, true>(plan.M, plan.J, p, grid, fold, stream)
+                           : launch_pool_bwd<float, false>(plan.M, plan.J, p, grid, fold, stream);
     }
     if (rc != AECF_OK) return rc;
     const int n = 3 * p.D;
@@ -231,4 +267,23 @@ int aecf_pool_bwd(const aecf_pool_desc* desc, const void* q, const void* kv, con
     return AECF_OK;
 }
 
+extern "C" {
+
+int aecf_pool_bwd(const aecf_pool_desc* desc, const void* q, const void* kv, const float* score_bias,
+                  const void* d_ctx, const float* d_pooled, const float* d_entropy,
+                  void* d_kv, void* d_q, float* d_bias_kv,
+                  void* workspace, size_t workspace_bytes, void* stream) {
+    return pool_bwd_impl(desc, false, q, nullptr, kv, score_bias, d_ctx, d_pooled, d_entropy, d_kv, d_q, d_bias_kv,
+                         workspace, workspace_bytes, stream);
+}
+
+int aecf_pool_bwd_folded(const aecf_pool_desc* desc, const void* q_proj, const float* scores, const void* v,
+                         const float* score_bias, const void* d_ctx, const float* d_pooled, const float* d_entropy,
+                         void* d_vs, float* d_bias_kv, void* workspace, size_t workspace_bytes, void* stream) {
+    return pool_bwd_impl(desc, true, q_proj, scores, v, score_bias, d_ctx, d_pooled, d_entropy, d_vs, nullptr, d_bias_kv,
+                         workspace, workspace_bytes, stream);
+}
+
 }  // extern "C"
+
+}  // extern "C" (opened above aecf_abi_version)

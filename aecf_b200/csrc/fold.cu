@@ -1,0 +1,133 @@
+// Folded key projection: the two small kernels either side of the GEMMs (include/aecf_b200.h, "folded key
+// projection").  With one fusion query for all rows (reference aecf/AECFLayer.py:694 expands a [1,1,D]
+// parameter) the key projection of torch/nn/functional.py:5855 collapses to one D-vector per head:
+//     score[b,h,m] = scale * q_h . (Wk_h x[b,m] + bk_h) = x[b,m] . Qk[h] + const(h)
+// so K is never materialised, forward or backward.
+#include "common.cuh"
+
+namespace aecf {
+
+// folded_w = [ Wv (D rows) ; Qk (H rows) ; zeros (HSP - H rows) ], each row D wide.
+//   blocks [0, fold_blocks): one thread per (r, d), r < HSP:  Qk[r, d] = scale * sum_j q[r*hd + j] * Wk[r*hd + j, d]
+//   the remaining blocks copy Wv, 16 bytes per thread, grid-stride.
+template <typename T>
+__global__ void __launch_bounds__(256)
+fold_prepare_kernel(const float* __restrict__ q_proj, const T* __restrict__ in_proj_weight, int D, int H, int HSP,
+                    float scale, int fold_blocks, T* __restrict__ folded_w) {
+    pdl_wait();
+    const int hd = D / H;
+    if (static_cast<int>(blockIdx.x) < fold_blocks) {
+        const int i = blockIdx.x * 256 + threadIdx.x;
+        if (i >= HSP * D) return;
+        const int r = i / D, d = i - r * D;
+        float acc = 0.f;
+        if (r < H) {
+            const T* wk = in_proj_weight + (static_cast<size_t>(D) + static_cast<size_t>(r) * hd) * D + d;
+            const float* q = q_proj + r * hd;
+#pragma unroll 8
+            for (int j = 0; j < hd; ++j) acc = fmaf(__ldg(q + j), to_float<T>(wk[static_cast<size_t>(j) * D]), acc);
+            acc *= scale;
+        }
+        folded_w[(static_cast<size_t>(D) + r) * D + d] = from_float<T>(acc);
+        return;
+    }
+    const uint4* src = reinterpret_cast<const uint4*>(in_proj_weight + 2 * static_cast<size_t>(D) * D);
+    uint4* dst = reinterpret_cast<uint4*>(folded_w);
+    const size_t n16 = static_cast<size_t>(D) * D * sizeof(T) / 16;
+    const size_t stride = static_cast<size_t>(gridDim.x - fold_blocks) * 256;
+    for (size_t i = static_cast<size_t>(blockIdx.x - fold_blocks) * 256 + threadIdx.x; i < n16; i += stride) dst[i] = src[i];
+}
+
+// g = [dWv (D rows) ; R (H rows) ; ...] fp32, each row D wide; one warp per in-projection row i (head h = i / hd):
+//   dWv[i, :] = g[i, :]              dWk[i, :] = scale * q[i] * R[h, :]        d_q[i] = scale * Wk[i, :] . R[h, :]
+template <typename T>
+__global__ void __launch_bounds__(256)
+fold_finish_kernel(const float* __restrict__ g, const float* __restrict__ q_proj, const T* __restrict__ in_proj_weight,
+                   int D, int H, float scale, T* __restrict__ d_in_proj_weight, float* __restrict__ d_q_proj) {
+    pdl_wait();
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (i >= D) return;
+    const int h = i / (D / H);
+    const float* r = g + (static_cast<size_t>(D) + h) * D;
+    const float* gv = g + static_cast<size_t>(i) * D;
+    const T* wk = in_proj_weight + (static_cast<size_t>(D) + i) * D;
+    const float sq = scale * __ldg(q_proj + i);
+    T* dwk = d_in_proj_weight ? d_in_proj_weight + (static_cast<size_t>(D) + i) * D : nullptr;
+    T* dwv = d_in_proj_weight ? d_in_proj_weight + (2 * static_cast<size_t>(D) + i) * D : nullptr;
+    float dot = 0.f;
+    for (int d = lane; d < D; d += 32) {
+        const float rv = __ldg(r + d);
+        dot = fmaf(to_float<T>(wk[d]), rv, dot);
+        if (dwk) {
+            dwk[d] = from_float<T>(sq * rv);
+            dwv[d] = from_float<T>(__ldg(gv + d));
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) dot += __shfl_xor_sync(FULL_MASK, dot, off);
+    if (lane == 0 && d_q_proj) d_q_proj[i] = scale * dot;
+}
+
+static int fold_check(int dtype, int D, int H) {
+    if (dtype != AECF_F32 && dtype != AECF_BF16) return AECF_ERR_INVALID;
+    if (D <= 0 || H <= 0 || D % H != 0) return AECF_ERR_INVALID;
+    if ((static_cast<long long>(D) * D * (dtype == AECF_BF16 ? 2 : 4)) % 16 != 0) return AECF_ERR_UNSUPPORTED;
+    return AECF_OK;
+}
+
+}  // namespace aecf
+
+using namespace aecf;
+
+extern "C" {
+
+int aecf_fold_prepare(int32_t device, int32_t dtype, int32_t embed_dim, int32_t num_heads, const float* q_proj,
+                      const void* in_proj_weight, void* folded_w, void* stream) {
+    int rc = fold_check(dtype, embed_dim, num_heads);
+    if (rc != AECF_OK) return rc;
+    if (!q_proj || !in_proj_weight || !folded_w) return AECF_ERR_INVALID;
+    if (!aligned16(in_proj_weight) || !aligned16(folded_w)) return AECF_ERR_ALIGNMENT;
+    if ((rc = use_device(device)) != AECF_OK) return rc;
+    const int D = embed_dim, H = num_heads, hsp = aecf_fold_score_cols(dtype, H);
+    const float scale = static_cast<float>(sqrt(1.0 / static_cast<double>(D / H)));
+    const int fold_blocks = (hsp * D + 255) / 256;
+    const int copy_blocks = 128;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    TimedLaunch timed(s);
+    if (dtype == AECF_BF16)
+        AECF_CUDA_OK(launch_pdl(fold_prepare_kernel<__nv_bfloat16>, dim3(fold_blocks + copy_blocks), dim3(256), 0, s, q_proj,
+                                static_cast<const __nv_bfloat16*>(in_proj_weight), D, H, hsp, scale, fold_blocks,
+                                static_cast<__nv_bfloat16*>(folded_w)));
+    else
+        AECF_CUDA_OK(launch_pdl(fold_prepare_kernel<float>, dim3(fold_blocks + copy_blocks), dim3(256), 0, s, q_proj,
+                                static_cast<const float*>(in_proj_weight), D, H, hsp, scale, fold_blocks,
+                                static_cast<float*>(folded_w)));
+    count_launch();
+    return AECF_OK;
+}
+
+int aecf_fold_finish(int32_t device, int32_t dtype, int32_t embed_dim, int32_t num_heads, const float* g,
+                     const float* q_proj, const void* in_proj_weight, void* d_in_proj_weight, float* d_q_proj,
+                     void* stream) {
+    int rc = fold_check(dtype, embed_dim, num_heads);
+    if (rc != AECF_OK) return rc;
+    if (!g || !q_proj || !in_proj_weight) return AECF_ERR_INVALID;
+    if ((rc = use_device(device)) != AECF_OK) return rc;
+    const int D = embed_dim, H = num_heads;
+    const float scale = static_cast<float>(sqrt(1.0 / static_cast<double>(D / H)));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    TimedLaunch timed(s);
+    if (dtype == AECF_BF16)
+        AECF_CUDA_OK(launch_pdl(fold_finish_kernel<__nv_bfloat16>, dim3((D + 7) / 8), dim3(256), 0, s, g, q_proj,
+                                static_cast<const __nv_bfloat16*>(in_proj_weight), D, H, scale,
+                                static_cast<__nv_bfloat16*>(d_in_proj_weight), d_q_proj));
+    else
+        AECF_CUDA_OK(launch_pdl(fold_finish_kernel<float>, dim3((D + 7) / 8), dim3(256), 0, s, g, q_proj,
+                                static_cast<const float*>(in_proj_weight), D, H, scale, static_cast<float*>(d_in_proj_weight),
+                                d_q_proj));
+    count_launch();
+    return AECF_OK;
+}
+
+}  // extern "C"

@@ -18,8 +18,9 @@ __global__ void pack_in_bias_kernel(const float* __restrict__ d_q, const float* 
 
 struct Geometry {
     long long B, rows;
-    int M, D, es, dt;
-    bool shared;
+    int M, D, H, es, dt;
+    bool shared, fold;
+    int HS, HSP;       // folded key projection: score columns (fp32, H rounded up to 4) / score-gradient columns (dt, 16-byte multiple)
 };
 
 static int geometry(const aecf_pool_desc* d, Geometry* g) {
@@ -27,6 +28,9 @@ static int geometry(const aecf_pool_desc* d, Geometry* g) {
     if (d->dtype != AECF_F32 && d->dtype != AECF_BF16) return AECF_ERR_INVALID;
     g->B = d->batch; g->M = d->num_tokens; g->D = d->embed_dim; g->rows = g->B * g->M;
     g->dt = d->dtype; g->es = d->dtype == AECF_BF16 ? 2 : 4; g->shared = d->q_is_shared != 0;
+    g->H = d->num_heads; g->fold = d->fold_key != 0;
+    g->HS = (g->H + 3) & ~3; g->HSP = aecf_fold_score_cols(d->dtype, g->H);
+    if (g->fold && (!g->shared || g->H <= 0 || g->H > 32)) return AECF_ERR_UNSUPPORTED;
     return AECF_OK;
 }
 
@@ -42,6 +46,7 @@ struct Workspace {
     float* d_qp;       // [D]
     float* d_bias_kv;  // [2D]
     float* d_bq;       // [D] (per-row query)
+    float* fold_g;     // [D + HSP, D] fp32: [dWv ; R] of the folded backward
     size_t total;
 };
 
@@ -66,6 +71,9 @@ static size_t max_gemm_workspace(const aecf_pool_desc* d, const Geometry& g) {
         gemm_desc(d->device, dt, dt, dt, dt, AECF_MN_MAJOR, AECF_MN_MAJOR, D, D, g.B, D, D, D),              // dW_o, dW_q
         gemm_desc(d->device, dt, dt, dt, dt, AECF_K_MAJOR, AECF_K_MAJOR, g.rows, 2 * D, D, D, D, 2 * D),     // kv
         gemm_desc(d->device, dt, dt, dt, dt, AECF_K_MAJOR, AECF_MN_MAJOR, g.rows, D, 2 * D, 2 * D, D, D),    // dX
+        gemm_desc(d->device, dt, dt, AECF_F32, dt, AECF_MN_MAJOR, AECF_MN_MAJOR, D + g.HSP, D, g.rows, D + g.HSP, D, D),   // folded [dWv ; R]
+        gemm_desc(d->device, dt, dt, dt, dt, AECF_K_MAJOR, AECF_MN_MAJOR, g.rows, D, D + g.HSP, D + g.HSP, D, D),          // folded dX
+        gemm_desc(d->device, dt, dt, dt, dt, AECF_K_MAJOR, AECF_K_MAJOR, g.rows, D, D, D, D, D),                           // folded V
     };
     for (const aecf_gemm_desc& p : probes) {
         const size_t w = aecf_gemm_workspace_bytes(&p);
@@ -86,6 +94,8 @@ static int carve(const aecf_pool_desc* d, const Geometry& g, void* base, Workspa
     w->d_qp = reinterpret_cast<float*>(b + off); off += align256(sizeof(float) * g.D);
     w->d_bias_kv = reinterpret_cast<float*>(b + off); off += align256(sizeof(float) * 2 * g.D);
     w->d_bq = reinterpret_cast<float*>(b + off); off += align256(sizeof(float) * g.D);
+    w->fold_g = reinterpret_cast<float*>(b + off);
+    if (g.fold) off += align256(sizeof(float) * (g.D + g.HSP) * g.D);
     w->total = off;
     return AECF_OK;
 }
@@ -132,6 +142,25 @@ int aecf_fusion_fwd(const aecf_pool_desc* desc, const aecf_fusion_tensors* t, vo
             : gemm_desc(dev, dt, dt, dt, dt, AECF_K_MAJOR, AECF_K_MAJOR, g.B, D, D, D, D, D);
         AECF_TRY(aecf_gemm(&q, t->query, t->in_proj_weight, t->in_proj_bias, t->q_proj, w.gemm, w.gemm_bytes, stream));
     }
+    if (g.fold) {
+        // folded key projection: no K.  [Wv ; Qk] -> values + per-head scores in one pass over x -> pool -> out
+        if (t->value || !t->scores || !t->folded_w) return AECF_ERR_INVALID;
+        {
+            ScopedSite site(AECF_SITE_FOLD_PREPARE);
+            AECF_TRY(aecf_fold_prepare(dev, dt, D, g.H, static_cast<const float*>(t->q_proj), t->in_proj_weight, t->folded_w, stream));
+        }
+        {
+            ScopedSite site(AECF_SITE_KV_PROJ);
+            const aecf_gemm_desc v = gemm_desc(dev, dt, dt, dt, dt, AECF_K_MAJOR, AECF_K_MAJOR, g.rows, D, D, D, D, D);
+            AECF_TRY(aecf_gemm_aux(&v, t->key, t->folded_w, bias ? at(t->in_proj_bias, 2 * D, es) : nullptr, t->kv, t->scores,
+                                   g.H, g.HS, w.gemm, w.gemm_bytes, stream));
+        }
+        {
+            ScopedSite site(AECF_SITE_POOL_FWD);
+            AECF_TRY(aecf_pool_fwd_folded(desc, t->scores, t->kv, t->score_bias, t->ctx, t->pooled, t->entropy, t->mask_rate,
+                                          t->masked, t->mask_bits, stream));
+        }
+    } else {
     {   // packed key/value projection (:5855); written straight into [rows, 2D] (no split copy, :5857-5863)
         ScopedSite site(AECF_SITE_KV_PROJ);
         if (!t->value) {
@@ -150,6 +179,7 @@ int aecf_fusion_fwd(const aecf_pool_desc* desc, const aecf_fusion_tensors* t, vo
         ScopedSite site(AECF_SITE_POOL_FWD);
         AECF_TRY(aecf_pool_fwd(desc, t->q_proj, t->kv, t->score_bias, t->ctx, t->pooled, t->entropy, t->mask_rate,
                                t->masked, t->mask_bits, stream));
+    }
     }
     {   // out projection (:6653)
         ScopedSite site(AECF_SITE_OUT_PROJ);
@@ -195,6 +225,30 @@ int aecf_fusion_bwd(const aecf_pool_desc* desc, const aecf_fusion_tensors* t, co
         if (phase == AECF_BWD_OUT_PROJ) return AECF_OK;
     }
 
+    if (g.fold) {
+        if (t->value || !t->scores || !t->folded_w) return AECF_ERR_INVALID;
+        const int KF = D + g.HSP;                            // contraction / row width of d_vs = [dV | ds]
+        {
+            ScopedSite site(AECF_SITE_POOL_BWD);
+            AECF_TRY(aecf_pool_bwd_folded(desc, t->q_proj, t->scores, t->kv, t->score_bias, gr->d_ctx, gr->d_pooled,
+                                          gr->d_entropy, gr->d_kv, w.d_bias_kv, w.pool, w.pool_bytes, stream));
+        }
+        if (gr->d_key) {                                     // dX = [dV | ds] . [Wv ; Qk]
+            ScopedSite site(AECF_SITE_D_X);
+            const aecf_gemm_desc d = gemm_desc(dev, dt, dt, dt, dt, AECF_K_MAJOR, AECF_MN_MAJOR, g.rows, D, KF, KF, D, D);
+            AECF_TRY(aecf_gemm(&d, gr->d_kv, t->folded_w, nullptr, gr->d_key, w.gemm, w.gemm_bytes, stream));
+        }
+        if (gr->d_in_proj_weight || gr->d_query || gr->d_in_proj_bias) {
+            {                                                // [dWv ; R] = [dV | ds]^T . X   (fp32)
+                ScopedSite site(AECF_SITE_D_KV_WEIGHT);
+                const aecf_gemm_desc d = gemm_desc(dev, dt, dt, AECF_F32, dt, AECF_MN_MAJOR, AECF_MN_MAJOR, KF, D, g.rows, KF, D, D);
+                AECF_TRY(aecf_gemm(&d, gr->d_kv, t->key, nullptr, w.fold_g, w.gemm, w.gemm_bytes, stream));
+            }
+            ScopedSite site(AECF_SITE_FOLD_FINISH);          // dWv, dWk = scale q (x) R, d_qp = scale Wk . R
+            AECF_TRY(aecf_fold_finish(dev, dt, D, g.H, w.fold_g, static_cast<const float*>(t->q_proj), t->in_proj_weight,
+                                      gr->d_in_proj_weight, w.d_qp, stream));
+        }
+    } else {
     {   // ---- fused recompute backward of the pool ---------------------------------------------------
         ScopedSite site(AECF_SITE_POOL_BWD);
         void* dq = g.shared ? static_cast<void*>(w.d_qp) : gr->d_q_rows;
@@ -217,7 +271,7 @@ int aecf_fusion_bwd(const aecf_pool_desc* desc, const aecf_fusion_tensors* t, co
                                    w.gemm_bytes, stream));
         }
     }
-    if (gr->d_in_proj_weight) {   // ---- in-projection weight gradient ---------------------------------------
+    if (gr->d_in_proj_weight) {   // ---- in-projection weight gradient (key / value rows) ----------------------
         {
             ScopedSite site(AECF_SITE_D_KV_WEIGHT);
             if (!t->value) {          // dW_kv = dKV^T X
@@ -230,6 +284,9 @@ int aecf_fusion_bwd(const aecf_pool_desc* desc, const aecf_fusion_tensors* t, co
                                    w.gemm_bytes, stream));
             }
         }
+    }
+    }
+    if (gr->d_in_proj_weight) {   // ---- query rows of the in-projection weight gradient -------------------------
         ScopedSite site(AECF_SITE_D_Q_WEIGHT);
         if (g.shared) {               // dW_q = d_qp (outer) q0
             const aecf_gemm_desc d = gemm_desc(dev, AECF_F32, dt, dt, dt, AECF_MN_MAJOR, AECF_MN_MAJOR, D, D, 1, D, D, D);

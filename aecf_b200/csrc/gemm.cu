@@ -179,7 +179,7 @@ static int launch_gemv(const aecf_gemm_desc* d, const void* A, const void* B, co
 }
 
 static int gemm_simt(const aecf_gemm_desc* d, const void* A, const void* B, const void* bias, void* C,
-                     void* workspace, size_t workspace_bytes, cudaStream_t s) {
+                     void* workspace, size_t workspace_bytes, cudaStream_t s, bool allow_split = true) {
     GemmEpilogue ep = make_epilogue(d, bias, C);
     const bool a16 = d->dtype_a == AECF_BF16, b16 = d->dtype_b == AECF_BF16;
     if (d->m == 1) {
@@ -188,7 +188,7 @@ static int gemm_simt(const aecf_gemm_desc* d, const void* A, const void* B, cons
         if (b16) return launch_gemv<float, __nv_bfloat16>(d, A, B, ep, s);
         return launch_gemv<float, float>(d, A, B, ep, s);
     }
-    const int splits = simt_splits(d);
+    const int splits = allow_split ? simt_splits(d) : 1;
     if (splits > 1) {
         if (workspace == nullptr || workspace_bytes < static_cast<size_t>(splits) * d->m * d->n * sizeof(float))
             return AECF_ERR_WORKSPACE;
@@ -248,6 +248,33 @@ int aecf_gemm(const aecf_gemm_desc* d, const void* A, const void* B, const void*
         if (rc != AECF_ERR_UNSUPPORTED || d->impl == AECF_GEMM_TCGEN05) return rc;
     }
     return gemm_simt(d, A, B, bias, C, workspace, workspace_bytes, s);
+}
+
+int aecf_gemm_aux(const aecf_gemm_desc* d, const void* A, const void* B, const void* bias, void* C, float* aux,
+                  int32_t aux_cols, int64_t aux_ld, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_desc(d);
+    if (rc != AECF_OK) return rc;
+    if (aux_cols <= 0 || aux_cols > 32 || aux_ld < ((aux_cols + 3) & ~3) || d->accumulate) return AECF_ERR_INVALID;
+    if (d->m == 0 || d->n == 0) return AECF_OK;
+    if (!A || !B || !C || !aux) return AECF_ERR_INVALID;
+    if ((rc = use_device(d->device)) != AECF_OK) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    TimedLaunch timed(s);
+    if (d->impl != AECF_GEMM_SIMT) {
+        rc = gemm_tcgen05(d, A, B, bias, C, workspace, workspace_bytes, s, aux, aux_cols, aux_ld);
+        if (rc != AECF_ERR_UNSUPPORTED || d->impl == AECF_GEMM_TCGEN05) return rc;
+    }
+    // fp32 / small shapes: the same two products as two SIMT launches
+    if ((rc = gemm_simt(d, A, B, bias, C, workspace, workspace_bytes, s)) != AECF_OK) return rc;
+    aecf_gemm_desc side = *d;
+    side.n = (aux_cols + 3) & ~3;                       // the padding columns come out too (zero rows of B)
+    side.dtype_c = AECF_F32; side.ldc = aux_ld;
+    const int es_b = d->dtype_b == AECF_BF16 ? 2 : 4;
+    const int aux_rows = (aux_cols + 16 / es_b - 1) / (16 / es_b) * (16 / es_b);
+    if (side.n > aux_rows) side.n = aux_rows;
+    const long long skip = d->b_layout == AECF_K_MAJOR ? d->n * d->ldb : d->n;
+    return gemm_simt(&side, A, static_cast<const char*>(B) + skip * es_b, nullptr, aux, workspace, workspace_bytes, s,
+                     /*allow_split=*/false);
 }
 
 }  // extern "C"

@@ -47,8 +47,10 @@ int launch_splitk_reduce(const float* partial, long long M, long long N, int spl
                          const GemmEpilogue& ep, cudaStream_t s);
 
 // gemm_tcgen05.cu: returns AECF_ERR_UNSUPPORTED when the shape/dtype is outside what it covers.
+// aux != nullptr: the side output of aecf_gemm_aux (B then has d->n + roundup8(aux_cols) rows).
 int gemm_tcgen05(const aecf_gemm_desc* d, const void* A, const void* B, const void* bias, void* C,
-                 void* workspace, size_t workspace_bytes, cudaStream_t s);
+                 void* workspace, size_t workspace_bytes, cudaStream_t s, float* aux = nullptr, int aux_cols = 0,
+                 long long aux_ld = 0);
 size_t gemm_tcgen05_workspace_bytes(const aecf_gemm_desc* d);
 
 }  // namespace aecf

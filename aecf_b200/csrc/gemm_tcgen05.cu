@@ -40,7 +40,8 @@ template <int BN> struct Cfg {
     static constexpr int B_BYTES = BN * BK * 2;                 // 16 / 32 KB
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int EPI_BYTES = 2 * BM * 128;              // staging: two [128 rows x 128 B] swizzled boxes
-    static constexpr int TMEM_COLS = 2 * BN;                    // double-buffered accumulator
+    static constexpr int ACC_STRIDE = BN > 128 ? 256 : 128;     // TMEM column stride between the two accumulators
+    static constexpr int TMEM_COLS = 2 * ACC_STRIDE;            // double-buffered accumulator (a power of two)
     static constexpr int BIAS_BYTES = 2 * BN * 4;               // fp32 bias slice, double buffered by tile parity
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BIAS_BYTES + 128 /*barriers*/;
 };
@@ -53,6 +54,11 @@ struct Params {
     int has_bias, bias_is_bf16;
     const void* bias;
     int partial_rows;          // rows of one split's partial (= m) when splits > 1
+    // side output (aecf_gemm_aux): columns [c_cols, n) of the product leave as fp32 into aux[row * aux_ld + j];
+    // columns [0, c_cols) are the ordinary C (bias, TMA store).  Without a side output c_cols == n.
+    int c_cols, aux_cols;
+    long long aux_ld;
+    float* aux;
 };
 
 // ---- raw PTX wrappers -----------------------------------------------------------------------
@@ -347,7 +353,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 const int as = tile_it & 1;
                 mbar_wait(&tmem_empty[as], ((tile_it >> 1) & 1) ^ 1);          // epilogue drained this accumulator
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + as * BN;
+                const uint32_t tmem_d = tmem_base + as * C::ACC_STRIDE;
                 for (int kb = 0; kb < w.kb_count; ++kb, ++it) {
                     const int s = it % STAGES;
                     mbar_wait(&full[s], (it / STAGES) & 1);
@@ -390,25 +396,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 for (int i = lane; i < BN; i += 32) {
                     const int col = n0 + i;
                     float b = 0.f;
-                    if (col < p.n)
+                    if (col < p.c_cols)
                         b = p.bias_is_bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(p.bias)[col])
                                            : static_cast<const float*>(p.bias)[col];
                     wbias[i] = b;
                 }
                 __syncwarp();
             }
-            const uint32_t t_row = tmem_base + as * BN + (static_cast<uint32_t>(quad * 32) << 16);
+            const uint32_t t_row = tmem_base + as * C::ACC_STRIDE + (static_cast<uint32_t>(quad * 32) << 16);
             const int out_row0 = (direct ? 0 : w.split * p.partial_rows) + m0 + quad * 32;
             // the staging area holds 128 bf16 columns or 64 fp32 columns per round
             const int cols_per_round = p.c_is_f32 ? 64 : 128;
-            const int rounds = BN / cols_per_round;
+            const int rounds = (BN + cols_per_round - 1) / cols_per_round;
 #pragma unroll 1
             for (int rd = 0; rd < rounds; ++rd) {
                 if (lane == 0) tma_store_wait_read();                          // my previous store has left the staging area
                 __syncwarp();
                 const int col_in_tile = rd * cols_per_round;
+                const int groups = min(cols_per_round, BN - col_in_tile) / 32;  // BN = 192: the last round is half full
 #pragma unroll 1
-                for (int g = 0; g < cols_per_round / 32; ++g) {                // 32 columns per TMEM load
+                for (int g = 0; g < groups; ++g) {                             // 32 columns per TMEM load
                     uint32_t r[32];
                     tmem_ld_32x32(t_row + col_in_tile + g * 32, r);
                     tmem_ld_wait();
@@ -417,6 +424,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     for (int i = 0; i < 32; ++i) {
                         v[i] = __uint_as_float(r[i]);
                         if (direct && p.has_bias) v[i] += wbias[col_in_tile + g * 32 + i];
+                    }
+                    if (p.aux != nullptr && n0 + col_in_tile + g * 32 == p.c_cols) {
+                        // the side columns: fp32 straight from the accumulator, one row per thread (32-byte runs)
+                        const int row = m0 + quad * 32 + lane;
+                        if (tile_valid && row < p.m) {
+                            float4* dst = reinterpret_cast<float4*>(p.aux + static_cast<long long>(row) * p.aux_ld);
+#pragma unroll
+                            for (int c = 0; c < 8; ++c)
+                                if (4 * c < p.aux_cols) dst[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                        }
                     }
                     if (p.c_is_f32) {
                         // box g: [32 rows x 32 fp32 = 128 B]; 16-byte chunk c of row `lane` sits at chunk c ^ (lane & 7)
@@ -451,7 +468,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     const int box_cols = p.c_is_f32 ? 32 : 64;
 #pragma unroll
                     for (int g = 0; g < 2; ++g)
-                        if (col0 + g * box_cols < p.n)
+                        if (col0 + g * box_cols < p.c_cols && col_in_tile + g * box_cols < BN)
                             tma_store_2d(&map_c, wbuf + g * (32 * 128), col0 + g * box_cols, out_row0);
                     tma_store_commit();
                 }
@@ -608,7 +625,7 @@ gemm_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
                 for (int i = et; i < BN; i += EPI_THREADS) {
                     const int col = n0 + i;
                     float b = 0.f;
-                    if (col < p.n)
+                    if (col < p.c_cols)
                         b = p.bias_is_bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(p.bias)[col])
                                            : static_cast<const float*>(p.bias)[col];
                     bias_tile[i] = b;
@@ -668,7 +685,7 @@ gemm_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
                     const int box_cols = p.c_is_f32 ? 32 : 64;
 #pragma unroll
                     for (int g = 0; g < 2; ++g)
-                        if (col0 + g * box_cols < p.n)
+                        if (col0 + g * box_cols < p.c_cols)
                             tma_store_2d(&map_c, stage_buf + g * (BM * 128), col0 + g * box_cols, out_row0);
                     tma_store_commit();
                 }
@@ -723,7 +740,10 @@ static bool make_map(CUtensorMap* map, const void* ptr, CUtensorMapDataType dt, 
 
 struct Plan { bool ok, two_sm; int bn, cluster, tiles_m, tiles_n, groups_m, splits, kb_per_split, kb_total; };
 
-static Plan make_plan(const aecf_gemm_desc* d) {
+// rows of B that carry the side output: aux_cols rounded up to 16 bytes of bf16
+static int aux_rows_of(int aux_cols) { return (aux_cols + 7) & ~7; }
+
+static Plan make_plan(const aecf_gemm_desc* d, int aux_cols = 0) {
     Plan pl{};
     pl.ok = false;
     if (d->dtype_a != AECF_BF16 || d->dtype_b != AECF_BF16 || d->accumulate) return pl;
@@ -732,9 +752,17 @@ static Plan make_plan(const aecf_gemm_desc* d) {
     if ((d->lda * 2) % 16 != 0 || (d->ldb * 2) % 16 != 0) return pl;
     const int ces = d->dtype_c == AECF_BF16 ? 2 : 4;
     if ((d->ldc * ces) % 16 != 0) return pl;
+    const long long n_total = d->n + aux_rows_of(aux_cols);
     pl.bn = d->n >= 256 ? 256 : 128;
+    if (aux_cols > 0) {
+        // side output: 192-wide tiles cover n + 8 with the least padding for every embed_dim of the sweep
+        // (520 -> 3 tiles, 1032 -> 6, 2056 -> 11); the side columns must start a 32-column TMEM group, and the
+        // 96-row halves of the B tile that the cluster multicasts exist only for a K-major B
+        if (aux_cols > 32 || d->n % 32 != 0 || d->b_layout != AECF_K_MAJOR) return pl;
+        pl.bn = 192;
+    }
     pl.tiles_m = static_cast<int>((d->m + tc::BM - 1) / tc::BM);
-    pl.tiles_n = static_cast<int>((d->n + pl.bn - 1) / pl.bn);
+    pl.tiles_n = static_cast<int>((n_total + pl.bn - 1) / pl.bn);
     pl.kb_total = static_cast<int>((d->k + tc::BK - 1) / tc::BK);
     // Pairs of CTAs (a cluster of 2) on vertically adjacent row blocks share the B tile by TMA multicast:
     // a third less L2 -> SM traffic per FLOP, which is what bounds these K = 512..1024 products.
@@ -759,6 +787,7 @@ static Plan make_plan(const aecf_gemm_desc* d) {
     static const int force_2sm = [] { const char* e = getenv("AECF_GEMM_2SM"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
     const bool long_k = pl.kb_per_split >= 16;
     pl.two_sm = pl.cluster == 2 && pl.bn == 256 && (force_2sm < 0 ? long_k : force_2sm == 1);
+    if (aux_cols > 0 && pl.splits != 1) return pl;       // the side output is written by the direct epilogue only
     pl.ok = true;
     return pl;
 }
@@ -772,9 +801,12 @@ size_t gemm_tcgen05_workspace_bytes(const aecf_gemm_desc* d) {
 }
 
 int gemm_tcgen05(const aecf_gemm_desc* d, const void* A, const void* B, const void* bias, void* C, void* workspace,
-                 size_t workspace_bytes, cudaStream_t s) {
+                 size_t workspace_bytes, cudaStream_t s, float* aux, int aux_cols, long long aux_ld) {
     using namespace tc;
-    const Plan pl = make_plan(d);
+    if (aux == nullptr) aux_cols = 0;
+    const Plan pl = make_plan(d, aux_cols);
+    if (aux_cols > 0 && (!aligned16(aux) || aux_ld % 4 != 0 || aux_ld < ((aux_cols + 3) & ~3))) return AECF_ERR_UNSUPPORTED;
+    const long long n_total = d->n + aux_rows_of(aux_cols);
     if (!pl.ok) return AECF_ERR_UNSUPPORTED;
     if (!aligned16(A) || !aligned16(B) || !aligned16(C)) return AECF_ERR_UNSUPPORTED;
     if (pl.splits > 1) {
@@ -786,7 +818,7 @@ int gemm_tcgen05(const aecf_gemm_desc* d, const void* A, const void* B, const vo
     // A: K-major [m, k] -> box [BM rows, 64 k];  MN-major stored [k, m] -> box [64 k rows, 64 m]
     if (d->a_layout == AECF_K_MAJOR) ok &= make_map(&map_a, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->m, d->k, d->lda, BM, BK);
     else ok &= make_map(&map_a, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->k, d->m, d->lda, BK, 64);
-    if (d->b_layout == AECF_K_MAJOR) ok &= make_map(&map_b, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->n, d->k, d->ldb, pl.bn / pl.cluster, BK);
+    if (d->b_layout == AECF_K_MAJOR) ok &= make_map(&map_b, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, n_total, d->k, d->ldb, pl.bn / pl.cluster, BK);
     else ok &= make_map(&map_b, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->k, d->n, d->ldb, BK, 64);
     const bool partial = pl.splits > 1;
     const bool c_f32 = partial || d->dtype_c == AECF_F32;
@@ -798,7 +830,8 @@ int gemm_tcgen05(const aecf_gemm_desc* d, const void* A, const void* B, const vo
     if (!ok) return AECF_ERR_UNSUPPORTED;
 
     Params p{};
-    p.m = static_cast<int>(d->m); p.n = static_cast<int>(d->n); p.k = static_cast<int>(d->k);
+    p.m = static_cast<int>(d->m); p.n = static_cast<int>(n_total); p.k = static_cast<int>(d->k);
+    p.c_cols = static_cast<int>(d->n); p.aux = aux_cols > 0 ? aux : nullptr; p.aux_cols = aux_cols; p.aux_ld = aux_ld;
     p.tiles_m = pl.tiles_m; p.tiles_n = pl.tiles_n; p.groups_m = pl.groups_m; p.splits = pl.splits;
     p.kb_per_split = pl.kb_per_split; p.kb_total = pl.kb_total;
     p.a_mn_major = d->a_layout == AECF_MN_MAJOR; p.b_mn_major = d->b_layout == AECF_MN_MAJOR;
@@ -834,6 +867,7 @@ int gemm_tcgen05(const aecf_gemm_desc* d, const void* A, const void* B, const vo
         AECF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<256>::SMEM_BYTES));
         AECF_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, map_a, map_b, map_c, p));
     } else if (pl.bn == 256) { if (pl.cluster == 2) AECF_TC_LAUNCH(256, 2); else AECF_TC_LAUNCH(256, 1); }
+    else if (pl.bn == 192) { if (pl.cluster == 2) AECF_TC_LAUNCH(192, 2); else AECF_TC_LAUNCH(192, 1); }
     else { if (pl.cluster == 2) AECF_TC_LAUNCH(128, 2); else AECF_TC_LAUNCH(128, 1); }
 #undef AECF_TC_LAUNCH
     count_launch();

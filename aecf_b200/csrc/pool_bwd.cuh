@@ -26,13 +26,17 @@ struct BwdSmem {
     static constexpr int bytes(int M) { return (POOL_WARPS * M + POOL_WARPS * PER_WARP) * 4; }
 };
 
-template <typename T, int M, int J, bool DROP>
+// FOLD (folded key projection): kv holds the values only, the scores come precomputed, there is no
+// key pass -- the score gradient ds[b, m, h] itself is stored next to dV (d_kv rows are [dV (D) | ds (HSP)]) and
+// the dX / dW GEMMs that follow contract over D + HSP, which applies and accumulates the rank-H key-side terms.
+template <typename T, int M, int J, bool DROP, bool FOLD>
 __global__ void __launch_bounds__(POOL_WARPS * 32, 2)
 pool_bwd_kernel(const PoolParams p) {
     using Core = PoolCore<T, M, J, DROP>;
     using Smem = BwdSmem<J, Core::V>;
     constexpr int V = Core::V;
     constexpr int Q4 = V / 4;
+    constexpr int VHALF = FOLD ? 0 : 1;
     // Every load of a row -- d_ctx, K and (when it fits in registers) V -- is issued before any
     // arithmetic, so a warp makes one trip to HBM per row.  K is needed again for d_q after the softmax
     // backward; it is re-read through L1 (the first read allocates there) rather than held in registers.
@@ -54,18 +58,17 @@ pool_bwd_kernel(const PoolParams p) {
     const int c0 = slice * Core::CPW + lane;
 
     float qs[J][V];
-    if (p.q_shared) Core::load_query(p, 0, c0, qs);
+    if (!FOLD && p.q_shared) Core::load_query(p, 0, c0, qs);
 
     const long long stride = static_cast<long long>(gridDim.x) * p.SPC;
     for (long long base = static_cast<long long>(blockIdx.x) * p.SPC; base < p.B; base += stride) {
         const long long row_raw = base + warp / p.WPS;
         const bool row_ok = row_raw < p.B;
         const long long row = row_ok ? row_raw : p.B - 1;
-        if (!p.q_shared) Core::load_query(p, row, c0, qs);
+        if (!FOLD && !p.q_shared) Core::load_query(p, row, c0, qs);
 
-        const size_t row_off = Core::row_offset(p, row, c0);
-        const char* kv_row = static_cast<const char*>(p.kv) + row_off;
-        char* dkv_row = static_cast<char*>(p.d_kv) + row_off;
+        const char* kv_row = static_cast<const char*>(p.kv) + Core::row_offset(p, row, c0);
+        char* dkv_row = static_cast<char*>(p.d_kv) + Core::drow_offset(p, row, c0);
         auto valid = [&](int j) { return c0 + 32 * j < p.NC; };
 
         // upstream gradient of the context and the values, issued first
@@ -83,15 +86,21 @@ pool_bwd_kernel(const PoolParams p) {
 #pragma unroll
                 for (int j = 0; j < J; ++j)
                     vraw[PRELOAD_V ? m : 0][PRELOAD_V ? j : 0] =
-                        valid(j) ? ldg_stream(kv_row + Core::kv_rel(p, m, 1, j)) : make_uint4(0, 0, 0, 0);
+                        valid(j) ? ldg_stream(kv_row + Core::kv_rel(p, m, VHALF, j)) : make_uint4(0, 0, 0, 0);
         }
 
         float w[M][J], wd[M][J];
         unsigned keep;
-        Core::attention_weights(
-            p, row, c0, qs,
-            [&](int m, int j) { return valid(j) ? ldg_cached(kv_row + Core::kv_rel(p, m, 0, j)) : make_uint4(0, 0, 0, 0); },
-            w, wd, keep);
+        if constexpr (FOLD) {
+            float s[M][J];
+            Core::load_scores(p, row, c0, s);
+            Core::softmax_dropout(p, row, c0, s, w, wd, keep);
+        } else {
+            Core::attention_weights(
+                p, row, c0, qs,
+                [&](int m, int j) { return valid(j) ? ldg_cached(kv_row + Core::kv_rel(p, m, 0, j)) : make_uint4(0, 0, 0, 0); },
+                w, wd, keep);
+        }
 
         // ---- value pass: d wd = dctx . v ; dV = wd * dctx ; d_bias_v += (sum_m wd) * dctx --------
         float dwd[M][J];
@@ -103,7 +112,7 @@ pool_bwd_kernel(const PoolParams p) {
 #pragma unroll
             for (int m = 0; m < M; ++m) {
                 if (PRELOAD_V) raw[m] = vraw[PRELOAD_V ? m : 0][PRELOAD_V ? j : 0];
-                else raw[m] = valid(j) ? ldg_stream(kv_row + Core::kv_rel(p, m, 1, j)) : make_uint4(0, 0, 0, 0);
+                else raw[m] = valid(j) ? ldg_stream(kv_row + Core::kv_rel(p, m, VHALF, j)) : make_uint4(0, 0, 0, 0);
             }
             float sum_wd = 0.f;
 #pragma unroll
@@ -115,7 +124,7 @@ pool_bwd_kernel(const PoolParams p) {
                 for (int v = 0; v < V; ++v) { a = fmaf(dc[v], f[v], a); dv[v] = wd[m][j] * dc[v]; }
                 dwd[m][j] = a;
                 sum_wd += wd[m][j];
-                if (row_ok && valid(j)) stg_vec(dkv_row + Core::kv_rel(p, m, 1, j), Vec<T>::pack(dv));
+                if (row_ok && valid(j)) stg_vec(dkv_row + Core::dkv_rel(p, m, VHALF, j), Vec<T>::pack(dv));
             }
             if (row_ok) {
 #pragma unroll
@@ -177,6 +186,26 @@ pool_bwd_kernel(const PoolParams p) {
             if (row_ok && valid(j)) acc_sds[j * 32 + lane] += sum_ds;
         }
 
+        if constexpr (FOLD) {
+            // ---- score gradients next to dV: column D + head of the (row, m) line of d_kv; the first lane of
+            // each head writes it, lanes 0 .. HSP-H-1 of the sample's first warp zero the padding columns
+            if (row_ok) {
+                T* line = reinterpret_cast<T*>(static_cast<char*>(p.d_kv) + static_cast<size_t>(row) * p.dkv_sb * sizeof(T)) + p.D;
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const int c = c0 + 32 * j;
+                    if (c < p.NC && (c & (p.G - 1)) == 0) {
+                        const int head = c >> p.logG;
+#pragma unroll
+                        for (int m = 0; m < M; ++m) line[m * p.dkv_sm + head] = from_float<T>(ds[m][j]);
+                    }
+                }
+                if (slice == 0 && lane < p.HSP - p.H) {
+#pragma unroll
+                    for (int m = 0; m < M; ++m) line[m * p.dkv_sm + p.H + lane] = from_float<T>(0.f);
+                }
+            }
+        } else {
         // ---- key pass: dK = ds * (scale * q) ; dq += ds * k (K re-read: L1 hit) ------------------
 #pragma unroll
         for (int j = 0; j < J; ++j) {
@@ -198,7 +227,7 @@ pool_bwd_kernel(const PoolParams p) {
                     dq[v] = fmaf(ds[m][j], f[v], dq[v]);
                 }
                 sum_ds += ds[m][j];
-                if (row_ok && valid(j)) stg_vec(dkv_row + Core::kv_rel(p, m, 0, j), Vec<T>::pack(dk));
+                if (row_ok && valid(j)) stg_vec(dkv_row + Core::dkv_rel(p, m, 0, j), Vec<T>::pack(dk));
             }
             if (row_ok) {
                 if (p.q_shared) {
@@ -226,6 +255,7 @@ pool_bwd_kernel(const PoolParams p) {
                 }
             }
         }
+        }   // !FOLD
     }
 
     // ---- fold the warps' strips in a fixed order into this CTA's partial [3][D] -----------------

@@ -30,7 +30,13 @@ struct PoolParams {
     const void* kv;
     const float* bias;
     long long bias_sb, bias_sh;
-    long long kv_sb, kv_sm;                 // kv / d_kv element strides between rows / tokens
+    long long kv_sb, kv_sm;                 // kv element strides between rows / tokens
+    long long dkv_sb, dkv_sm;               // d_kv element strides (the same, except in the folded layout)
+    // folded key projection (FOLD kernels): kv holds the projected VALUES only ([*, D] rows, the V
+    // "half" sits at offset 0), the scaled per-head scores come precomputed, and d_kv rows are [dV (D) | ds (HSP)]
+    const float* scores;                    // [*, HS] fp32, element (b, m, h) at b*s_sb + m*s_sm + h
+    long long s_sb, s_sm;
+    int HSP;                                // score-gradient columns per d_kv row (H rounded up to 16 bytes)
     // forward outputs
     void* ctx;
     float* pooled;
@@ -59,6 +65,14 @@ struct PoolCore {
     // ... and, relative to it, of chunk column j of the K half (half = 0) or V half (half = 1) of token m
     static __device__ __forceinline__ int kv_rel(const PoolParams& p, int m, int half, int j) {
         return (m * static_cast<int>(p.kv_sm) + half * p.D) * static_cast<int>(sizeof(T)) + j * 512;
+    }
+
+    // the same two offsets inside d_kv (its rows are wider than kv's in the folded layout)
+    static __device__ __forceinline__ size_t drow_offset(const PoolParams& p, long long row, int c0) {
+        return static_cast<size_t>(row) * p.dkv_sb * sizeof(T) + static_cast<size_t>(c0) * 16;
+    }
+    static __device__ __forceinline__ long long dkv_rel(const PoolParams& p, int m, int half, int j) {
+        return (m * p.dkv_sm + half * p.D) * static_cast<long long>(sizeof(T)) + j * 512;
     }
 
     // projected query chunks, pre-multiplied by scale (torch/nn/functional.py:6632)
@@ -157,6 +171,33 @@ struct PoolCore {
         const PoolParams& p, long long row, int c0, const float (&qs)[J][V], LoadK load_k,
         float (&w)[M][J], float (&wd)[M][J], unsigned& keep) {
         float s[M][J];
+        key_scores(p, qs, load_k, s);
+        softmax_dropout(p, row, c0, s, w, wd, keep);
+    }
+
+    // head index of each of this lane's chunk columns
+    static __device__ __forceinline__ void heads_of(const PoolParams& p, int c0, int (&head)[J]) {
+#pragma unroll
+        for (int j = 0; j < J; ++j) head[j] = min((c0 + 32 * j) >> p.logG, p.H - 1);
+    }
+
+    // Folded key projection: the scaled scores of (row, m, head) were produced by the value GEMM's side
+    // output (scores = x . (scale * Wk_h^T q_h); the key bias shifts every token of a head alike and drops
+    // out of the softmax).  Plain loads: 32 lanes read at most 32 / LG distinct floats of one 32-byte sector.
+    static __device__ __forceinline__ void load_scores(const PoolParams& p, long long row, int c0, float (&s)[M][J]) {
+        int head[J];
+        heads_of(p, c0, head);
+        const float* base = p.scores + static_cast<size_t>(row) * p.s_sb;
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+#pragma unroll
+            for (int j = 0; j < J; ++j) s[m][j] = __ldg(base + static_cast<size_t>(m) * p.s_sm + head[j]);
+    }
+
+    // s[m][j] = (scale * q_head) . k[m, head], every lane of a head holding the head's value
+    template <typename LoadK>
+    static __device__ __forceinline__ void key_scores(const PoolParams& p, const float (&qs)[J][V], LoadK load_k,
+                                                      float (&s)[M][J]) {
 #pragma unroll
         for (int m = 0; m < M; ++m) {
             uint4 raw[J];
@@ -173,10 +214,14 @@ struct PoolCore {
             }
         }
         head_reduce(p, s);
+    }
 
+    // (+ additive mask) -> softmax over the M tokens -> dropout
+    static __device__ __forceinline__ void softmax_dropout(
+        const PoolParams& p, long long row, int c0, float (&s)[M][J],
+        float (&w)[M][J], float (&wd)[M][J], unsigned& keep) {
         int head[J];
-#pragma unroll
-        for (int j = 0; j < J; ++j) head[j] = min((c0 + 32 * j) >> p.logG, p.H - 1);
+        heads_of(p, c0, head);
 
         if (p.bias != nullptr) {                                       // :6638 baddbmm(attn_mask, q, k^T)
 #pragma unroll

@@ -29,8 +29,9 @@ namespace aecf {
 
 // J = chunk columns per lane (1, 2, 4); DROP = attention dropout active.
 // grid: CTAs of the slice kernel; sms: SM count (the streaming kernel sizes its persistent grid from it)
-template <typename T, bool DROP> int launch_pool_fwd(int M, int J, const PoolParams& p, int grid, int sms, void* stream);
-template <typename T, bool DROP> int launch_pool_bwd(int M, int J, const PoolParams& p, int grid, void* stream);
-template <typename T, bool DROP> int pool_bwd_blocks_per_sm(int M, int J);
+// fold: the folded-key-projection variants (values only in kv, precomputed scores)
+template <typename T, bool DROP> int launch_pool_fwd(int M, int J, const PoolParams& p, int grid, int sms, bool fold, void* stream);
+template <typename T, bool DROP> int launch_pool_bwd(int M, int J, const PoolParams& p, int grid, bool fold, void* stream);
+template <typename T, bool DROP> int pool_bwd_blocks_per_sm(int M, int J, bool fold);
 
 }  // namespace aecf

@@ -87,11 +87,13 @@ __device__ __forceinline__ void masking_stage(const PoolParams& p, long long row
     mask_rate = __fsub_rn(1.0f, static_cast<float>(active) / static_cast<float>(M));   // :275
 }
 
-template <typename T, int M, int J, bool DROP>
+// FOLD: folded key projection -- kv holds the values only and the scores come precomputed (pool_core.cuh).
+template <typename T, int M, int J, bool DROP, bool FOLD>
 __global__ void __launch_bounds__(POOL_WARPS * 32)
 pool_fwd_kernel(const PoolParams p) {
     using Core = PoolCore<T, M, J, DROP>;
     constexpr int V = Core::V;
+    constexpr int VHALF = FOLD ? 0 : 1;                 // which D-wide half of a kv row holds the values
     __shared__ float xchg[POOL_WARPS * M];
     __shared__ float head_sums[POOL_WARPS * M];       // [sample slot][m], written by the slice-0 warps
     const int lane = threadIdx.x & 31;
@@ -117,15 +119,20 @@ pool_fwd_kernel(const PoolParams p) {
 #pragma unroll
         for (int m = 0; m < M; ++m)
 #pragma unroll
-            for (int j = 0; j < J; ++j) vraw[PRELOAD_V ? m : 0][PRELOAD_V ? j : 0] = load_kv(m, 1, j);
+            for (int j = 0; j < J; ++j) vraw[PRELOAD_V ? m : 0][PRELOAD_V ? j : 0] = load_kv(m, VHALF, j);
     }
-
-    float qs[J][V];
-    Core::load_query(p, row, c0, qs);
 
     float w[M][J], wd[M][J];
     unsigned keep;
-    Core::attention_weights(p, row, c0, qs, [&](int m, int j) { return load_kv(m, 0, j); }, w, wd, keep);
+    if constexpr (FOLD) {
+        float s[M][J];
+        Core::load_scores(p, row, c0, s);
+        Core::softmax_dropout(p, row, c0, s, w, wd, keep);
+    } else {
+        float qs[J][V];
+        Core::load_query(p, row, c0, qs);
+        Core::attention_weights(p, row, c0, qs, [&](int m, int j) { return load_kv(m, 0, j); }, w, wd, keep);
+    }
 
     // ---- weighted value sum (torch/nn/functional.py:6647) ---------------------------------
     float acc[J][V];
@@ -138,7 +145,7 @@ pool_fwd_kernel(const PoolParams p) {
         uint4 raw[J];
 #pragma unroll
         for (int j = 0; j < J; ++j)
-            raw[j] = PRELOAD_V ? vraw[PRELOAD_V ? m : 0][PRELOAD_V ? j : 0] : load_kv(m, 1, j);
+            raw[j] = PRELOAD_V ? vraw[PRELOAD_V ? m : 0][PRELOAD_V ? j : 0] : load_kv(m, VHALF, j);
 #pragma unroll
         for (int j = 0; j < J; ++j) {
             float f[V];
@@ -193,12 +200,14 @@ pool_fwd_kernel(const PoolParams p) {
 // reduced, so every warp keeps one full sample (6 KB at M=3, D=512 bf16) in flight at all times and the
 // arithmetic never waits on HBM.  Head sums of up to 32 consecutive rows stay in lane registers (lane i
 // keeps row i); the masking stage then runs once per 32 rows with one row per lane.
-template <typename T, int M, int J, bool DROP>
+template <typename T, int M, int J, bool DROP, bool FOLD>
 __global__ void __launch_bounds__(512, 1)
 pool_fwd_stream_kernel(const PoolParams p, const long long rows_per_warp) {
     using Core = PoolCore<T, M, J, DROP>;
     constexpr int V = Core::V;
-    constexpr int CH = M * 2 * J;                       // 16-byte chunks per lane per sample
+    constexpr int HALVES = FOLD ? 1 : 2;                // folded: only the values are staged
+    constexpr int VHALF = FOLD ? 0 : 1;
+    constexpr int CH = M * HALVES * J;                  // 16-byte chunks per lane per sample
     extern __shared__ uint4 ring[];                     // [warps][2 stages][CH][32 lanes]
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -216,17 +225,19 @@ pool_fwd_stream_kernel(const PoolParams p, const long long rows_per_warp) {
 #pragma unroll
         for (int m = 0; m < M; ++m)
 #pragma unroll
-            for (int half = 0; half < 2; ++half)
+            for (int half = 0; half < HALVES; ++half)
 #pragma unroll
                 for (int j = 0; j < J; ++j)
                     if (c0 + 32 * j < p.NC)
-                        cp_async16(&my[(stage * CH + (m * 2 + half) * J + j) * 32 + lane], src + Core::kv_rel(p, m, half, j));
+                        cp_async16(&my[(stage * CH + (m * HALVES + half) * J + j) * 32 + lane], src + Core::kv_rel(p, m, half, j));
         cp_async_commit();
     };
     prefetch(row_begin, 0);
 
     float qs[J][V];
-    if (p.q_shared) Core::load_query(p, 0, c0, qs);
+    if (!FOLD && p.q_shared) Core::load_query(p, 0, c0, qs);
+    float s_next[M][J];                                 // folded: the next row's scores, loaded one row ahead
+    if constexpr (FOLD) Core::load_scores(p, row_begin, c0, s_next);
     const float denom = static_cast<float>(p.H * p.R);
     float mine[M];                                      // head sums of the row this lane will finish
 #pragma unroll
@@ -237,15 +248,24 @@ pool_fwd_stream_kernel(const PoolParams p, const long long rows_per_warp) {
         const int stage = it & 1;
         if (row + 1 < row_end) prefetch(row + 1, stage ^ 1);
         else cp_async_commit();                         // empty group keeps the wait count uniform
-        if (!p.q_shared) Core::load_query(p, row, c0, qs);
+        if (!FOLD && !p.q_shared) Core::load_query(p, row, c0, qs);
+        float s[M][J];
+        if constexpr (FOLD) {
+#pragma unroll
+            for (int m = 0; m < M; ++m)
+#pragma unroll
+                for (int j = 0; j < J; ++j) s[m][j] = s_next[m][j];
+            if (row + 1 < row_end) Core::load_scores(p, row + 1, c0, s_next);
+        }
         cp_async_wait<1>();                             // this row's chunks have landed (own copies only)
         auto staged = [&](int m, int half, int j) -> uint4 {
-            return (c0 + 32 * j < p.NC) ? my[(stage * CH + (m * 2 + half) * J + j) * 32 + lane] : make_uint4(0, 0, 0, 0);
+            return (c0 + 32 * j < p.NC) ? my[(stage * CH + (m * HALVES + half) * J + j) * 32 + lane] : make_uint4(0, 0, 0, 0);
         };
 
         float w[M][J], wd[M][J];
         unsigned keep;
-        Core::attention_weights(p, row, c0, qs, [&](int m, int j) { return staged(m, 0, j); }, w, wd, keep);
+        if constexpr (FOLD) Core::softmax_dropout(p, row, c0, s, w, wd, keep);
+        else Core::attention_weights(p, row, c0, qs, [&](int m, int j) { return staged(m, 0, j); }, w, wd, keep);
 
         float acc[J][V];
 #pragma unroll
@@ -257,7 +277,7 @@ pool_fwd_stream_kernel(const PoolParams p, const long long rows_per_warp) {
 #pragma unroll
             for (int j = 0; j < J; ++j) {
                 float f[V];
-                Vec<T>::unpack(staged(m, 1, j), f);
+                Vec<T>::unpack(staged(m, VHALF, j), f);
 #pragma unroll
                 for (int v = 0; v < V; ++v) acc[j][v] = fmaf(wd[m][j], f[v], acc[j][v]);
             }

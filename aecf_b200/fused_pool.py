@@ -3,6 +3,8 @@
 Forward  (reference aecf/AECFLayer.py:515-541 over torch/nn/functional.py:5847-5865, 6630-6659):
     q-proj GEMM -> packed KV GEMM -> fused pool kernel (scores, softmax, dropout, value sum,
     head mean, curriculum mask) -> out-proj GEMM            [aecf_fusion_fwd, csrc/fusion.cu]
+    With the folded key projection (one shared query, the bf16 default): q-proj -> fold -> ONE GEMM that
+    yields the values and, as an fp32 side output, the per-head scores -> pool -> out-proj; K never exists.
 Backward (autograd of the same lines in the reference):
     colsum + dWo GEMM + dctx GEMM -> fused recompute pool backward -> dX GEMM + dWkv GEMM
     -> the small query-side products                        [aecf_fusion_bwd]
@@ -32,6 +34,7 @@ class PoolConfig:
     row0: int = 0
     q_shared: bool = True
     seq_first: bool = False     # key/value are [M, B, D] (batch_first=False), used in place
+    fold: bool = False          # folded key projection (include/aecf_b200.h): shared query, key is value
     want_mask_bits: bool = False
     bias_strides: tuple = (0, 0)
     # data-parallel hook: called in backward with (name, grad tensor) as soon as a parameter
@@ -59,23 +62,29 @@ class FusedPoolFunction(torch.autograd.Function):
         dev = ops.require_cuda(q_src, key, value, in_w, in_b, out_w, out_b, score_bias)
         dt = key.dtype
         D = key.shape[-1]
+        fold = bool(cfg.fold)
         if cfg.seq_first:
             M, B = key.shape[0], key.shape[1]
-            kv_strides = (2 * D, B * 2 * D)
+            kv_strides = (1, B) if fold else (2 * D, B * 2 * D)     # folded: strides in rows of [B*M, .] matrices
         else:
             B, M = key.shape[0], key.shape[1]
             kv_strides = (0, 0)
+        H = cfg.num_heads
+        hs, hsp = ops.fold_score_cols(dt, H)
         desc = ops.make_pool_desc(
             dev, dt, batch=B, num_tokens=M, embed_dim=D, num_heads=cfg.num_heads, training=cfg.training,
             masking=cfg.masking, min_active=cfg.min_active, q_is_shared=cfg.q_shared,
             base_mask_prob=cfg.base_mask_prob, entropy_target=cfg.entropy_target, dropout_p=cfg.dropout_p,
-            seed=cfg.seed, offset=cfg.offset, row0=cfg.row0, bias_strides=cfg.bias_strides, kv_strides=kv_strides)
+            seed=cfg.seed, offset=cfg.offset, row0=cfg.row0, bias_strides=cfg.bias_strides, kv_strides=kv_strides,
+            fold_key=fold)
 
         q_in = q_src.reshape(D) if cfg.q_shared else q_src.reshape(B, D)
         if not q_in.is_contiguous():
             q_in = q_in.contiguous()
         qp = torch.empty((D,), dtype=torch.float32, device=dev) if cfg.q_shared else torch.empty((B, D), dtype=dt, device=dev)
-        kv = torch.empty((B * M, 2 * D), dtype=dt, device=dev)
+        kv = torch.empty((B * M, D if fold else 2 * D), dtype=dt, device=dev)     # folded: the values only
+        scores = torch.empty((B * M, hs), dtype=torch.float32, device=dev) if fold else None
+        folded_w = torch.empty((D + hsp, D), dtype=dt, device=dev) if fold else None
         attn = torch.empty((B, D), dtype=dt, device=dev)
         out = torch.empty((B, D), dtype=dt, device=dev)
         pooled = torch.empty((B, M), dtype=torch.float32, device=dev)
@@ -88,13 +97,14 @@ class FusedPoolFunction(torch.autograd.Function):
             query=p(q_in), key=p(key), value=p(value), in_proj_weight=p(in_w), in_proj_bias=p(in_b),
             out_proj_weight=p(out_w), out_proj_bias=p(out_b), score_bias=p(score_bias),
             q_proj=p(qp), kv=p(kv), ctx=p(attn), out=p(out), pooled=p(pooled), entropy=p(entropy),
-            mask_rate=p(mask_rate), masked=p(masked), mask_bits=p(bits) if cfg.want_mask_bits else None)
+            mask_rate=p(mask_rate), masked=p(masked), mask_bits=p(bits) if cfg.want_mask_bits else None,
+            scores=p(scores), folded_w=p(folded_w))
         ops.fusion_fwd(desc, tensors, dev)
 
         ctx.cfg, ctx.desc = cfg, desc
         ctx.shape = (B, M, D)
         ctx.q_shape = q_src.shape
-        ctx.save_for_backward(q_in, key, value, in_w, in_b, out_w, out_b, qp, kv, attn, score_bias)
+        ctx.save_for_backward(q_in, key, value, in_w, in_b, out_w, out_b, qp, kv, attn, score_bias, scores, folded_w)
         if cfg.masking != 2:                            # entropy is detached in training mode (reference :278)
             ctx.mark_non_differentiable(mask_rate, masked, bits, entropy)
         else:
@@ -104,7 +114,7 @@ class FusedPoolFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_out, g_pooled, g_entropy, _g_rate, _g_masked, _g_bits):
         cfg: PoolConfig = ctx.cfg
-        q_in, key, value, in_w, in_b, out_w, out_b, qp, kv, attn, score_bias = ctx.saved_tensors
+        q_in, key, value, in_w, in_b, out_w, out_b, qp, kv, attn, score_bias, scores, folded_w = ctx.saved_tensors
         B, M, D = ctx.shape
         dev, dt = key.device, key.dtype
         need_q, need_key, need_value, need_in_w, need_in_b, need_out_w, need_out_b = ctx.needs_input_grad[:7]
@@ -124,7 +134,9 @@ class FusedPoolFunction(torch.autograd.Function):
             d_entropy = g_entropy.reshape(B).to(torch.float32).contiguous()
 
         new = lambda shape, dtype=dt: torch.empty(shape, dtype=dtype, device=dev)
-        d_ctx, d_kv = new((B, D)), new((B * M, 2 * D))
+        # folded: rows of d_kv are [dV (D) | ds (HSP)]
+        d_kv_cols = D + ops.fold_score_cols(dt, cfg.num_heads)[1] if cfg.fold else 2 * D
+        d_ctx, d_kv = new((B, D)), new((B * M, d_kv_cols))
         d_q_rows = None if cfg.q_shared else new((B, D))
         d_key = new(key.shape) if need_key else None
         d_value = new(value.shape) if (value is not None and need_value) else None
@@ -146,7 +158,7 @@ class FusedPoolFunction(torch.autograd.Function):
         tensors = _lib.FusionTensors(
             query=p(q_in), key=p(key), value=p(value), in_proj_weight=p(in_w), in_proj_bias=p(in_b),
             out_proj_weight=p(out_w), out_proj_bias=p(out_b), score_bias=p(score_bias),
-            q_proj=p(qp), kv=p(kv), ctx=p(attn))
+            q_proj=p(qp), kv=p(kv), ctx=p(attn), scores=p(scores), folded_w=p(folded_w))
         grads = _lib.FusionGrads(
             d_out=p(g), d_pooled=p(d_pooled), d_entropy=p(d_entropy), d_ctx=p(d_ctx), d_kv=p(d_kv), d_q_rows=p(d_q_rows),
             d_key=p(d_key), d_value=p(d_value), d_query=p(d_q), d_in_proj_weight=p(d_in_w), d_in_proj_bias=p(d_in_b),

@@ -16,6 +16,7 @@ Deliberate differences (DESIGN.md "reference quirks"):
 from __future__ import annotations
 
 import math
+import os
 import threading
 from typing import Any, Dict, Optional, Tuple, Union
 
@@ -209,6 +210,10 @@ class MultimodalAttentionPool(nn.Module):
         self._grad_ready = None
         self._grad_buffers = None
         self._want_mask_bits = False
+        # Folded key projection (include/aecf_b200.h): None = automatic -- on for bf16 whenever one fusion query
+        # is shared by all rows and key is value (AECF_FOLD=0 in the environment turns the automatic choice off);
+        # True forces it wherever it applies (also fp32), False keeps the K projection.
+        self.fold_key_projection: Optional[bool] = None
 
     # -- validation: same exception types and messages as the reference (:450-498) -----------
     def _validate(self, query, key, value):
@@ -320,6 +325,11 @@ class MultimodalAttentionPool(nn.Module):
             masking = 1 if cm.training else 2
             if cm.training and tokens > 1:
                 cm._last_seq_len = tokens                               # reference :187
+        can_fold = q_shared and value_c is None and self.num_heads <= 32
+        if self.fold_key_projection is None:
+            fold = can_fold and dt == torch.bfloat16 and os.environ.get("AECF_FOLD", "1") != "0"
+        else:
+            fold = can_fold and bool(self.fold_key_projection)
         draws = (att.training and att.dropout > 0.0) or masking == 1
         seed, offset = _rng.next(key.device) if draws else (0, 0)
         cfg = PoolConfig(
@@ -328,7 +338,7 @@ class MultimodalAttentionPool(nn.Module):
             entropy_target=cm.entropy_target if fused_cm else 0.7,
             min_active=cm.min_active if fused_cm else 1,
             seed=seed, offset=offset, row0=int(self.row_offset), q_shared=q_shared,
-            seq_first=not self.batch_first, want_mask_bits=self._want_mask_bits, bias_strides=bias_strides,
+            seq_first=not self.batch_first, fold=fold, want_mask_bits=self._want_mask_bits, bias_strides=bias_strides,
             grad_ready=self._grad_ready, grad_buffers=self._grad_buffers)
         out, pooled, entropy, mask_rate, masked, bits = FusedPoolFunction.apply(
             q_src, key_c, value_c, att.in_proj_weight, att.in_proj_bias, att.out_proj.weight, att.out_proj.bias,

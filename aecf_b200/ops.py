@@ -133,14 +133,42 @@ def make_pool_desc(dev: torch.device, dtype: torch.dtype, *, batch: int, num_tok
                    num_heads: int, training: bool, masking: int, min_active: int, q_is_shared: bool,
                    base_mask_prob: float, entropy_target: float, dropout_p: float, seed: int, offset: int,
                    row0: int, bias_strides: Tuple[int, int] = (0, 0),
-                   kv_strides: Tuple[int, int] = (0, 0)) -> _lib.PoolDesc:
+                   kv_strides: Tuple[int, int] = (0, 0), fold_key: bool = False) -> _lib.PoolDesc:
     return _lib.PoolDesc(device=dev.index or 0, dtype=dtype_code(dtype), batch=batch, num_tokens=num_tokens,
                          embed_dim=embed_dim, num_heads=num_heads, training=int(training), masking=int(masking),
                          min_active=int(min_active), q_is_shared=int(q_is_shared),
                          base_mask_prob=float(base_mask_prob), entropy_target=float(entropy_target),
                          dropout_p=float(dropout_p), seed=seed & 0xFFFFFFFFFFFFFFFF, offset=offset & 0xFFFFFFFF,
                          row0=row0, bias_stride_b=bias_strides[0], bias_stride_h=bias_strides[1],
-                         kv_stride_b=kv_strides[0], kv_stride_m=kv_strides[1])
+                         kv_stride_b=kv_strides[0], kv_stride_m=kv_strides[1], fold_key=int(fold_key), reserved=0)
+
+
+def fold_score_cols(dtype: torch.dtype, num_heads: int) -> Tuple[int, int]:
+    """(HS, HSP) of the folded key projection: columns of the fp32 score matrix (heads rounded up to 4) and
+    score-gradient columns appended to each d_kv row (heads rounded up to 16 bytes of ``dtype``)."""
+    per16 = 8 if dtype == torch.bfloat16 else 4
+    return (num_heads + 3) // 4 * 4, (num_heads + per16 - 1) // per16 * per16
+
+
+def gemm_aux(a: torch.Tensor, b: torch.Tensor, *, m: int, n: int, k: int, aux_cols: int,
+             bias: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None,
+             impl: int = _lib.GEMM_AUTO) -> Tuple[torch.Tensor, torch.Tensor]:
+    """C[m, n] = A B[:n]^T (+ bias) and the fp32 side output aux[m, aux_cols] = A B[n:n+aux_cols]^T, K-major
+    operands (``aecf_gemm_aux``).  ``b`` has n + roundup(aux_cols, 16 bytes) rows."""
+    dev = require_cuda(a, b, bias)
+    lib = _lib.load()
+    out = torch.empty((m, n), dtype=out_dtype or a.dtype, device=dev)
+    aux_ld = (aux_cols + 3) // 4 * 4
+    aux = torch.empty((m, aux_ld), dtype=torch.float32, device=dev)
+    d = _lib.GemmDesc(device=dev.index or 0, dtype_a=dtype_code(a.dtype), dtype_b=dtype_code(b.dtype),
+                      dtype_c=dtype_code(out.dtype), dtype_bias=dtype_code(bias.dtype) if bias is not None else 0,
+                      a_layout=_lib.K_MAJOR, b_layout=_lib.K_MAJOR, accumulate=0, impl=impl,
+                      m=m, n=n, k=k, lda=a.stride(0), ldb=b.stride(0), ldc=n)
+    ws = _workspace(lib.aecf_gemm_workspace_bytes(C.byref(d)), dev)
+    rc = lib.aecf_gemm_aux(C.byref(d), a.data_ptr(), b.data_ptr(), _lib.ptr(bias), out.data_ptr(), aux.data_ptr(),
+                           aux_cols, aux_ld, ws.data_ptr(), ws.numel(), _stream(dev))
+    _lib.check(rc, f"aecf_gemm_aux m={m} n={n} k={k} aux={aux_cols}")
+    return out, aux
 
 
 def pool_fwd(desc: _lib.PoolDesc, q: torch.Tensor, kv: torch.Tensor, score_bias: Optional[torch.Tensor],

@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=4096, help="rows of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--fold", choices=["auto", "on", "off"], default="auto",
+                    help="folded key projection (auto: the module's choice, on for bf16)")
     return ap.parse_args()
 
 
@@ -61,6 +63,8 @@ def ncu_traffic(kernel: str, args):
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             t = json.load(f)
         key = f"B={args.batch},M={args.tokens},D={args.dim},H={args.heads},{args.dtype},dropout={args.dropout}"
+        if getattr(args, "folded", False):
+            key += ",fold"
         return t.get(key, {}).get(kernel)
     except Exception:
         return None
@@ -195,7 +199,8 @@ def workload_config(args, n_gpus):
                         f"B={args.batch} per GPU, {args.dtype} (BASELINE.json configs[1])",
             "global_batch": args.batch * n_gpus, "tokens": args.tokens, "embed_dim": args.dim, "heads": args.heads,
             "dropout": args.dropout, "parallelism": f"dp{n_gpus}",
-            "l2": "inputs larger than L2 (kv 403 MB, x 201 MB per step vs 126 MB L2); no flush needed",
+            "fold_key_projection": bool(getattr(args, "folded", False)),
+            "l2": "inputs larger than L2 (x 201 MB, values 201 MB per step vs 126 MB L2); no flush needed",
             "step": "forward(return_info) + entropy_loss + backward(d_out), public module API"}
 
 
@@ -253,6 +258,8 @@ def run_b200(args):
     torch.manual_seed(0)
     query, pool = aecf_b200.create_fusion_pool(D, M, 0.15, num_heads=H, dropout=args.dropout, device=dev, dtype=dtype)
     cm = pool.curriculum_masking
+    pool.fold_key_projection = {"auto": None, "on": True, "off": False}[args.fold]
+    args.folded = (dtype == torch.bfloat16 and os.environ.get("AECF_FOLD", "1") != "0") if args.fold == "auto" else args.fold == "on"
     sync = GradientSync(pool, query).attach()
     sync.set_shard(B * world)                                     # Philox keyed on the global row
     torch.manual_seed(1234 + rank)
@@ -366,8 +373,16 @@ def run_b200(args):
 
     # ---- roofline of the fused pool kernels and tensor-pipe use of the GEMMs ----------------------
     peaks = measured_peaks()
-    fwd_bytes = B * (es * (2 * M * D + D) + 4 * (2 * M + 2))
-    bwd_bytes = B * (es * (2 * M * D + D + 2 * M * D))
+    # algorithmic bytes per launch of the kernels AS LAUNCHED.  Unfolded: fwd reads K and V,
+    # bwd re-reads them and writes dK and dV.  Folded key projection: K does not exist -- fwd reads V and the fp32
+    # scores, bwd reads V, scores, d_ctx and writes [dV | ds].
+    hs, hsp = (H + 3) // 4 * 4, (H + (16 // es) - 1) // (16 // es) * (16 // es)
+    if args.folded:
+        fwd_bytes = B * (es * (M * D + D) + 4 * M * hs + 4 * (2 * M + 2))
+        bwd_bytes = B * (es * (M * D + D + M * (D + hsp)) + 4 * M * hs)
+    else:
+        fwd_bytes = B * (es * (2 * M * D + D) + 4 * (2 * M + 2))
+        bwd_bytes = B * (es * (2 * M * D + D + 2 * M * D))
 
     def hbm(name, nbytes):
         if name not in kernels:
@@ -377,8 +392,9 @@ def run_b200(args):
                 "frac": gbs / peaks["hbm_gbs"], "frac_of_nominal_8TBs": gbs / 8000.0, "traffic": ncu_traffic(name, args),
                 "ms": kernels[name]["ms"], "algorithmic_bytes": nbytes, "peak_source": peaks["source"]}
 
-    gemm_flops = {"kv_proj": 2 * B * M * D * 2 * D, "out_proj": 2 * B * D * D, "d_ctx": 2 * B * D * D,
-                  "d_out_weight": 2 * B * D * D, "d_x": 2 * B * M * 2 * D * D, "d_kv_weight": 2 * B * M * 2 * D * D}
+    kvw = (D + hsp) if args.folded else 2 * D       # projected columns per token: [V | scores] or [K | V]
+    gemm_flops = {"kv_proj": 2 * B * M * D * kvw, "out_proj": 2 * B * D * D, "d_ctx": 2 * B * D * D,
+                  "d_out_weight": 2 * B * D * D, "d_x": 2 * B * M * kvw * D, "d_kv_weight": 2 * B * M * kvw * D}
     gemms = {}
     for name, fl in gemm_flops.items():
         if name in kernels:
@@ -393,6 +409,7 @@ def run_b200(args):
             "config": workload_config(args, world), "impl": "b200",
             "roofline": roof, "roofline_pool_fwd": hbm("pool_fwd", fwd_bytes),
             "pool_kernels_only": {"value": B / (pool_ms * 1e-3) if pool_ms else None, "unit": UNIT, "ms": pool_ms,
+                                  "bytes_per_sample": (fwd_bytes + bwd_bytes) // B,
                                   "note": "fused pool fwd+bwd kernels alone, per GPU (the 273 M samples/s target)"},
             "gemm_tensor_pipe": gemms, "kernels": kernels, "host_issue_ms_per_step": issue_ms,
             "ms_per_step_with_kernel_events": ms_with_events,

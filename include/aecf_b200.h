@@ -45,7 +45,7 @@ extern "C" {
 #define AECF_API
 #endif
 
-#define AECF_ABI_VERSION 1
+#define AECF_ABI_VERSION 2
 #define AECF_MAX_TOKENS 8
 
 typedef enum aecf_status {
@@ -88,6 +88,8 @@ typedef struct aecf_pool_desc {
     int64_t  bias_stride_h;
     int64_t  kv_stride_b;     /* kv / d_kv strides in elements between rows and between tokens; 0, 0 means the */
     int64_t  kv_stride_m;     /* packed [B, M, 2D] layout (M*2D, 2D); a sequence-first [M, B, 2D] buffer is (2D, B*2D) */
+    int32_t  fold_key;        /* whole-step entry points only: 1 = folded key projection (see "folded key projection") */
+    int32_t  reserved;        /* 0 */
 } aecf_pool_desc;
 
 /* Forward: scale, per-head scores, softmax, dropout, weighted value sum, head mean, and the whole
@@ -124,6 +126,43 @@ AECF_API int aecf_pool_bwd(const aecf_pool_desc* desc, const void* q, const void
                   void* workspace, size_t workspace_bytes, void* stream);
 AECF_API size_t aecf_pool_bwd_workspace_bytes(const aecf_pool_desc* desc);
 
+/* ---- folded key projection (one query shared by all rows) ------------------------------------
+ * With a single fusion query the keys never need to exist:
+ *     score[b, h, m] = scale * q_h . (Wk_h x[b, m] + bk_h) = x[b, m] . Qk[h] + const(h),
+ *     Qk[h] = scale * Wk_h^T q_h  (one D-vector per head),
+ * and const(h) shifts all tokens of a head alike, so it drops out of the softmax.  The value projection GEMM
+ * produces the scores as a side output in the same pass over x (aecf_gemm_aux, B = [Wv ; Qk]); the pool kernels
+ * then read the values and the scores only.  Backward: dK = ds (x) (scale q) has rank H per row, so instead of
+ * dK the kernel stores ds itself next to dV, d_vs[row] = [dV (D) | ds (HSP)], and the two GEMMs that follow
+ * contract over D + HSP:  dX = d_vs . [Wv ; Qk]   and   [dWv ; R] = d_vs^T . X,  R[h] = sum_{b,m} ds[b,h,m] x[b,m],
+ * from which dWk[h*hd + j] = scale * q[h*hd + j] * R[h] and d q[h*hd + j] = scale * Wk[h*hd + j] . R[h].
+ * Half the projection FLOPs and 45 % of the pool kernels' HBM bytes disappear; the arithmetic is re-associated,
+ * so results differ from the unfolded path by rounding only (fp32: ~1e-6 relative).
+ * These entry points take matrices of B*M rows; kv_stride_b / kv_stride_m of the descriptor are in ROWS here
+ * ((0, 0) = (M, 1): row b*M + m; a sequence-first batch is (1, B)).
+ *   scores [B*M, HS]  fp32, HS = num_heads rounded up to 4
+ *   v      [B*M, D]   dtype
+ *   d_vs   [B*M, D + HSP] dtype, HSP = aecf_fold_score_cols(dtype, num_heads) (16-byte multiple)
+ *   q_proj [D] fp32   (only its product with sum ds enters d_bias_kv[0 .. D), analytically zero)
+ * d_bias_kv as in aecf_pool_bwd. */
+AECF_API int aecf_fold_score_cols(int32_t dtype, int32_t num_heads);
+AECF_API int aecf_pool_fwd_folded(const aecf_pool_desc* desc, const float* scores, const void* v, const float* score_bias,
+                         void* ctx, float* pooled, float* entropy, float* mask_rate, float* masked,
+                         uint8_t* mask_bits, void* stream);
+AECF_API int aecf_pool_bwd_folded(const aecf_pool_desc* desc, const void* q_proj, const float* scores, const void* v,
+                         const float* score_bias, const void* d_ctx, const float* d_pooled, const float* d_entropy,
+                         void* d_vs, float* d_bias_kv, void* workspace, size_t workspace_bytes, void* stream);
+/* Forward preparation: folded_w [D + HSP, D] dtype = [ Wv ; Qk (H rows) ; zero rows ] from the projected query
+ * q_proj [D] fp32 and in_proj_weight [3D, D]. */
+AECF_API int aecf_fold_prepare(int32_t device, int32_t dtype, int32_t embed_dim, int32_t num_heads, const float* q_proj,
+                      const void* in_proj_weight, void* folded_w, void* stream);
+/* Backward completion: from g = [dWv ; R] ([D + HSP, D] fp32, the output of the d_vs^T . X product) write
+ * d_in_proj_weight rows [D, 2D) (dWk) and [2D, 3D) (dWv) in dtype (either may be skipped with a null
+ * d_in_proj_weight) and d_q_proj [D] fp32 (+= nothing: overwritten). */
+AECF_API int aecf_fold_finish(int32_t device, int32_t dtype, int32_t embed_dim, int32_t num_heads, const float* g,
+                     const float* q_proj, const void* in_proj_weight, void* d_in_proj_weight, float* d_q_proj,
+                     void* stream);
+
 /* ---- projections ------------------------------------------------------------------------
  * C[m, n] = sum_k A[m, k] * B[n, k] (+ bias[n]) (+ C if accumulate), fp32 accumulation.
  * Replaces torch.nn.functional.linear at torch/nn/functional.py:5854-5855, 6653 and the four
@@ -145,6 +184,18 @@ typedef struct aecf_gemm_desc {
 AECF_API int aecf_gemm(const aecf_gemm_desc* desc, const void* A, const void* B, const void* bias, void* C,
               void* workspace, size_t workspace_bytes, void* stream);
 AECF_API size_t aecf_gemm_workspace_bytes(const aecf_gemm_desc* desc);
+
+/* Same product with a narrow fp32 side output taken from extra rows of B (the folded key projection
+ * computes the attention scores this way, in the same pass over A as the value projection):
+ *   C[i, j]   = sum_k A[i, k] * B[j, k] + bias[j]           j < n            (dtype_c, ldc)
+ *   aux[i, j] = sum_k A[i, k] * B[n + j, k]                 j < aux_cols     (fp32, aux_ld)
+ * B has n + aux_rows rows, aux_rows = aux_cols rounded up to 16 bytes of dtype_b; aux_ld >= aux_cols rounded
+ * up to 4 and the columns aux_cols .. of each aux row up to that multiple are written too (with the products
+ * of the padding rows of B).  aux_cols <= 32.  On the tcgen05 path (bf16, n % 32 == 0, B K-major) it is ONE
+ * launch: 128 x 192 tiles, the side columns leave the epilogue as fp32 straight from the accumulator. */
+AECF_API int aecf_gemm_aux(const aecf_gemm_desc* desc, const void* A, const void* B, const void* bias, void* C,
+                           float* aux, int32_t aux_cols, int64_t aux_ld, void* workspace, size_t workspace_bytes,
+                           void* stream);
 
 /* ---- small reductions ------------------------------------------------------------------
  * out[c] = sum_r x[r*ld + c] for a [rows, cols] matrix, fp32 accumulation, deterministic.
@@ -204,6 +255,10 @@ typedef struct aecf_fusion_tensors {
     float*   mask_rate;            /* [B] fp32, nullable */
     float*   masked;               /* [B, M] fp32, nullable */
     uint8_t* mask_bits;            /* [B], nullable */
+    /* folded key projection (desc->fold_key): forward results the backward reads again; kv is then [B*M, D]
+     * (values only) and d_kv of aecf_fusion_grads [B*M, D + HSP] */
+    float*   scores;               /* [B*M, HS] fp32 */
+    void*    folded_w;             /* [D + HSP, D] */
 } aecf_fusion_tensors;
 
 typedef struct aecf_fusion_grads {
@@ -239,7 +294,7 @@ typedef enum aecf_site {
     AECF_SITE_OTHER = 0, AECF_SITE_Q_PROJ, AECF_SITE_KV_PROJ, AECF_SITE_POOL_FWD, AECF_SITE_OUT_PROJ,
     AECF_SITE_D_OUT_BIAS, AECF_SITE_D_OUT_WEIGHT, AECF_SITE_D_CTX, AECF_SITE_POOL_BWD, AECF_SITE_POOL_BWD_FINALIZE,
     AECF_SITE_D_X, AECF_SITE_D_KV_WEIGHT, AECF_SITE_D_Q_WEIGHT, AECF_SITE_D_QUERY, AECF_SITE_D_IN_BIAS,
-    AECF_SITE_ENTROPY_LOSS, AECF_SITE_COUNT
+    AECF_SITE_ENTROPY_LOSS, AECF_SITE_FOLD_PREPARE, AECF_SITE_FOLD_FINISH, AECF_SITE_COUNT
 } aecf_site;
 AECF_API int         aecf_timing_enable(int32_t enable);                    /* clears earlier records */
 AECF_API int         aecf_timing_collect(float* total_ms, int32_t* launches); /* arrays of AECF_SITE_COUNT; syncs */

@@ -142,7 +142,7 @@ def pool_forward(query: Tensor, key: Tensor, value: Optional[Tensor],
                  u_drop: Optional[Tensor] = None, u_mask: Optional[Tensor] = None,
                  score_bias: Optional[Tensor] = None,
                  masking: Optional[dict] = None,
-                 storage: Optional[torch.dtype] = None) -> PoolResult:
+                 storage: Optional[torch.dtype] = None, fold_key: bool = False) -> PoolResult:
     """MultimodalAttentionPool.forward, batch_first -- reference aecf/AECFLayer.py:409-547
     over torch/nn/functional.py:5847-5865 and :6630-6659.
 
@@ -153,6 +153,10 @@ def pool_forward(query: Tensor, key: Tensor, value: Optional[Tensor],
     ``storage``: if set (e.g. torch.bfloat16) the intermediates the CUDA path
     writes to HBM (projected K/V, context, output) are rounded to that dtype while
     all arithmetic stays in ``query.dtype`` -- the stage-exact model of the bf16 path.
+    ``fold_key`` (stage model of the CUDA path's folded key projection, single shared query only): the
+    scores are associated as x . (scale * Wk_h^T q_h) with that per-head vector rounded to ``storage``
+    and the key bias dropped (it shifts every token of a head alike, so the softmax does not see it);
+    mathematically identical to the reference's (x Wk^T + bk) . (scale q_h), the rounding differs.
     """
     if value is None:
         value = key
@@ -176,6 +180,12 @@ def pool_forward(query: Tensor, key: Tensor, value: Optional[Tensor],
     vh = v.view(B, M, H, hd).transpose(1, 2)
     q_scaled = qh * math.sqrt(1.0 / float(hd))                   # :6632
     scores = q_scaled @ kh.transpose(-2, -1)                     # :6642   [B,H,S,M]
+    if fold_key:
+        assert S == 1, "the folded association needs one query per sample"
+        scale = math.sqrt(1.0 / float(hd))
+        qk = torch.einsum("he,hed->hd", qp[0, 0].view(H, hd), Wk.view(H, hd, D)) * scale   # [H, D]
+        qk = _round(qk, storage)
+        scores = torch.einsum("bmd,hd->bhm", key, qk).unsqueeze(2)                       # [B,H,1,M]
     if score_bias is not None:
         scores = scores + score_bias                             # :6638 baddbmm
     w = torch.softmax(scores, dim=-1)                            # :6643

@@ -30,7 +30,7 @@ def score_bias_from_kpm(kpm: Optional[torch.Tensor], dtype) -> Optional[torch.Te
 
 
 def run_oracle(case: Case, inp: Optional[dict] = None, dtype: Optional[torch.dtype] = None,
-               storage: Optional[torch.dtype] = None):
+               storage: Optional[torch.dtype] = None, fold_key: bool = False):
     """Oracle forward + closed-form backward on a golden case; returns (forward result, grads)."""
     inp = inp if inp is not None else build_inputs(case, dtype)
     B, D = case.B, case.D
@@ -41,7 +41,7 @@ def run_oracle(case: Case, inp: Optional[dict] = None, dtype: Optional[torch.dty
         inp["out_proj.weight"], inp["out_proj.bias"], case.H,
         dropout_p=case.dropout, training=case.training, u_drop=inp["u_drop"], u_mask=inp["u_mask"],
         score_bias=score_bias_from_kpm(inp.get("key_padding_mask"), inp["x"].dtype),
-        masking=masking_kwargs(case), storage=storage)
+        masking=masking_kwargs(case), storage=storage, fold_key=fold_key)
     grads = oracle.pool_backward(
         q, inp["x"], value, inp["in_proj_weight"], inp["out_proj.weight"], case.H, fwd.saved,
         inp["grad_out"], grad_pooled=inp["grad_pooled"] if case.pooled_grad else None,

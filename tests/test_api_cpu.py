@@ -21,11 +21,11 @@ def test_library_loads_and_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.aecf_abi_version() == 1
+    assert lib.aecf_abi_version() == _lib.ABI_VERSION == 2
     assert b"sm_100a" in lib.aecf_build_info()
     assert lib.aecf_strerror(-2).decode().startswith("shape or dtype outside")
     # structs mirror the header: sizes are what the C compiler lays out (natural alignment)
-    assert ctypes.sizeof(_lib.PoolDesc) == 112 and ctypes.sizeof(_lib.GemmDesc) == 88
+    assert ctypes.sizeof(_lib.PoolDesc) == 120 and ctypes.sizeof(_lib.GemmDesc) == 88
 
 
 def test_descriptor_validation_needs_no_gpu():

@@ -24,7 +24,9 @@ FP32_TOL = 1e-5
 BF16_TOL = 2e-2
 
 
-def make_pool(case: Case, inp: dict, dtype: torch.dtype):
+def make_pool(case: Case, inp: dict, dtype: torch.dtype, fold=None):
+    """fold: None = the module's automatic choice (folded key projection for bf16 with a shared query), True/False
+    force it on (wherever it applies) / off."""
     cm = aecf_b200.CurriculumMasking(**masking_kwargs(case))
     pool = aecf_b200.MultimodalAttentionPool(case.D, num_heads=case.H, dropout=case.dropout,
                                              curriculum_masking=cm, device=DEV, dtype=dtype)
@@ -36,12 +38,13 @@ def make_pool(case: Case, inp: dict, dtype: torch.dtype):
     pool.train(case.training)
     pool.row_offset = case.row0
     pool._want_mask_bits = True
+    pool.fold_key_projection = fold
     return pool, cm
 
 
-def run_cuda(case: Case, inp: dict, dtype: torch.dtype):
+def run_cuda(case: Case, inp: dict, dtype: torch.dtype, fold=None):
     """Forward + backward through the public API with the case's Philox (seed, offset, row0)."""
-    pool, cm = make_pool(case, inp, dtype)
+    pool, cm = make_pool(case, inp, dtype, fold)
     query0 = torch.nn.Parameter(inp["query0"].to(DEV, dtype))
     x = inp["x"].to(DEV, dtype).requires_grad_(True)
     value = inp["value"].to(DEV, dtype).requires_grad_(True) if case.separate_value else None
@@ -152,6 +155,23 @@ def test_fp32_matches_reference_golden(case):
                      g["grad_out_proj_weight_strided"], tol)
 
 
+FOLDABLE_FP32_CASES = [c for c in FP32_CASES if not c.separate_value]
+
+
+@pytest.mark.parametrize("case", FOLDABLE_FP32_CASES, ids=lambda c: c.name)
+def test_fp32_folded_key_projection_matches_oracle(case):
+    """The folded key projection (scores = x . (scale Wk_h^T q_h) out of the value GEMM's side output, ds stored
+    next to dV, rank-H key-side gradients through the GEMMs' extra columns) in fp32 against the UNFOLDED oracle:
+    same tolerance as the unfolded path, masks and active sets bit-exact."""
+    inp = build_inputs(case)
+    ref, ref_grads = run_oracle(case, inp)
+    last = case.M if (case.training and case.M > 1) else 2
+    ref_loss = oracle.entropy_loss(ref.info["entropy"], last, case.entropy_target)
+    out, info, ent_loss, grads, _ = run_cuda(case, inp, torch.float32, fold=True)
+    check_forward(case, out, info, ent_loss, ref, ref_loss, FP32_TOL)
+    check_grads(case, grads, ref_grads, FP32_TOL)
+
+
 BF16_CASES = [c for c in FP32_CASES if c.name in (
     "config1_d512_h1_m3", "d64_h8_m3", "d64_h8_m3_dropout", "xray_d256_h4_m2", "d128_h4_m8_minactive2",
     "d64_h4_m4_kpm", "d64_h2_m3_separate_value", "d256_h16_m6")]
@@ -165,14 +185,16 @@ def _bf16_inputs(case):
     return inp
 
 
+@pytest.mark.parametrize("fold", [True, False], ids=["folded", "unfolded"])
 @pytest.mark.parametrize("case", BF16_CASES, ids=lambda c: c.name)
-def test_bf16_matches_fp32_math_oracle(case):
-    """north_star: bf16 within 2e-2 of fp32 math on the bf16-rounded inputs."""
+def test_bf16_matches_fp32_math_oracle(case, fold):
+    """north_star: bf16 within 2e-2 of fp32 math on the bf16-rounded inputs,
+    with the folded key projection (the bf16 default) and without it."""
     inp = _bf16_inputs(case)
     ref, ref_grads = run_oracle(case, inp)
     last = case.M if (case.training and case.M > 1) else 2
     ref_loss = oracle.entropy_loss(ref.info["entropy"], last, case.entropy_target)
-    out, info, ent_loss, grads, _ = run_cuda(case, inp, torch.bfloat16)
+    out, info, ent_loss, grads, _ = run_cuda(case, inp, torch.bfloat16, fold=fold)
     check_forward(case, out.float(), info, ent_loss, ref, ref_loss, BF16_TOL, exact_masks=False)
     check_grads(case, {k: v.float() for k, v in grads.items()}, ref_grads, BF16_TOL)
     flips = int((torch.from_numpy(np.unpackbits(info["mask_bits"].cpu().numpy()[:, None], axis=1, bitorder="little")
@@ -180,13 +202,16 @@ def test_bf16_matches_fp32_math_oracle(case):
     assert flips <= max(1, case.B * case.M // 50), f"{flips} mask flips against fp32 math"
 
 
+@pytest.mark.parametrize("fold", [True, False], ids=["folded", "unfolded"])
 @pytest.mark.parametrize("case", BF16_CASES, ids=lambda c: c.name)
-def test_bf16_masks_exact_against_stage_rounded_oracle(case):
-    """With the oracle rounding K/V, ctx and out to bf16 where the CUDA path stores them, the masks
-    and the active-token sets are bit-exact and everything else is far inside the bf16 budget."""
+def test_bf16_masks_exact_against_stage_rounded_oracle(case, fold):
+    """With the oracle rounding K/V, ctx and out to bf16 where the CUDA path stores them (folded: the per-head
+    score vector Qk instead of K), the masks and the active-token sets are bit-exact and everything else is far
+    inside the bf16 budget."""
     inp = _bf16_inputs(case)
-    ref, ref_grads = run_oracle(case, inp, storage=torch.bfloat16)
-    out, info, _, grads, _ = run_cuda(case, inp, torch.bfloat16)
+    folded = fold and not case.separate_value            # with a separate value tensor the module keeps K
+    ref, ref_grads = run_oracle(case, inp, storage=torch.bfloat16, fold_key=folded)
+    out, info, _, grads, _ = run_cuda(case, inp, torch.bfloat16, fold=fold)
     assert np.array_equal(info["mask_bits"].cpu().numpy(), expected_bits(ref.info["mask"])), "mask bits differ"
     assert torch.equal(info["mask_rate"].cpu(), ref.info["mask_rate"].float())
     assert_close("attention_weights", info["attention_weights"].cpu(), ref.info["attention_weights"], 1e-4, atol=1e-5)
@@ -215,7 +240,7 @@ def test_wide_rows_span_several_warps(case, dtype):
         tol = FP32_TOL
     else:
         inp = _bf16_inputs(case)
-        ref, ref_grads = run_oracle(case, inp, storage=torch.bfloat16)
+        ref, ref_grads = run_oracle(case, inp, storage=torch.bfloat16, fold_key=True)   # bf16 folds by default
         tol = BF16_TOL
     out, info, _, grads, _ = run_cuda(case, inp, dtype)
     assert np.array_equal(info["mask_bits"].cpu().numpy(), expected_bits(ref.info["mask"])), "mask bits differ"
@@ -225,6 +250,80 @@ def test_wide_rows_span_several_warps(case, dtype):
                  tol if dtype == torch.float32 else 1e-4, atol=1e-5)
     assert_close("entropy", info["entropy"].cpu(), ref.info["entropy"], tol if dtype == torch.float32 else 1e-4, atol=1e-5)
     check_grads(case, {k: v.float() for k, v in grads.items()}, ref_grads, tol)
+
+
+@pytest.mark.parametrize("case", WIDE_CASES, ids=lambda c: c.name)
+def test_wide_rows_folded_fp32(case):
+    inp = build_inputs(case)
+    ref, ref_grads = run_oracle(case, inp)
+    out, info, _, grads, _ = run_cuda(case, inp, torch.float32, fold=True)
+    assert np.array_equal(info["mask_bits"].cpu().numpy(), expected_bits(ref.info["mask"])), "mask bits differ"
+    assert_close("out", out.cpu(), ref.out, FP32_TOL)
+    assert_close("attention_weights", info["attention_weights"].cpu(), ref.info["attention_weights"], FP32_TOL, atol=1e-5)
+    check_grads(case, grads, ref_grads, FP32_TOL)
+
+
+def test_folded_sequence_first_and_large_batch_against_unfolded():
+    """bf16, B large enough for the tcgen05 GEMMs (192-wide tiles with the fp32 score side output, K = D + 8
+    contractions in the backward): folded and unfolded paths agree within the bf16 budget, in both layouts,
+    and the folded path is bit-identical between the batch-first and the sequence-first layout."""
+    torch.manual_seed(5)
+    B, M, D, H = 1000, 3, 512, 8
+    q, pool = aecf_b200.create_fusion_pool(D, M, 0.3, num_heads=H, dropout=0.1, device=DEV, dtype=torch.bfloat16)
+    with torch.no_grad():
+        pool.attention.in_proj_bias.normal_(0, 0.1)
+        q.mul_(8.0)
+    pool._want_mask_bits = True
+    x = (torch.randn(B, M, D, device=DEV) * 2).bfloat16()
+    g = torch.randn(B, 1, D, device=DEV).bfloat16()
+    res = {}
+    for name, fold, seq_first in (("folded", True, False), ("unfolded", False, False), ("folded_seq", True, True)):
+        pool.fold_key_projection = fold
+        pool.batch_first = not seq_first
+        xs = (x.transpose(0, 1).contiguous() if seq_first else x.clone()).requires_grad_(True)
+        qq = q.expand(-1, B, -1) if seq_first else q.expand(B, -1, -1)
+        aecf_b200.set_rng_state(31, 2)
+        out, info = pool(qq, xs, return_info=True)
+        (out.reshape(B, D).float() * g.reshape(B, D).float()).sum().backward()
+        res[name] = dict(out=out.detach().reshape(B, D).float(), pooled=info["attention_weights"].detach().reshape(B, M),
+                         bits=info["mask_bits"].clone(), gx=(xs.grad.transpose(0, 1) if seq_first else xs.grad).float(),
+                         gw=pool.attention.in_proj_weight.grad.float().clone(), gb=pool.attention.in_proj_bias.grad.float().clone(),
+                         gq=q.grad.float().clone())
+        pool.zero_grad(); q.grad = None
+    aecf_b200.set_rng_state(None)
+    pool.batch_first = True
+    a, b, c = res["folded"], res["unfolded"], res["folded_seq"]
+    for k in ("out", "gx", "gw", "gq"):
+        assert_close(f"folded vs unfolded {k}", a[k].cpu(), b[k].cpu(), BF16_TOL)
+    assert_close("pooled", a["pooled"].cpu(), b["pooled"].cpu(), 1e-2, atol=2e-3)
+    assert_close("bias grad (value third)", a["gb"][2 * D:].cpu(), b["gb"][2 * D:].cpu(), BF16_TOL)
+    flips = int((a["bits"] != b["bits"]).sum())
+    assert flips <= B // 50, f"{flips} rows with different masks between the folded and the unfolded path"
+    for k in ("out", "pooled", "bits", "gx"):
+        assert torch.equal(a[k], c[k]), f"sequence-first folded path differs in {k}"
+    assert_close("seq-first gw", a["gw"].cpu(), c["gw"].cpu(), 1e-2)
+
+
+@pytest.mark.parametrize("shape", [(640, 512, 512, 8), (300, 256, 128, 4), (1024, 1024, 256, 16), (96, 64, 64, 1)],
+                         ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "fp32"])
+def test_gemm_with_side_output(shape, dtype):
+    """aecf_gemm_aux: C = A B[:n]^T + bias and the fp32 side output A B[n:n+aux]^T in one call (one tcgen05 launch
+    with 192-wide tiles when bf16 and m, n >= 128; two SIMT launches otherwise)."""
+    m, n, k, aux = shape
+    torch.manual_seed(m + n)
+    per16 = 8 if dtype == torch.bfloat16 else 4
+    rows = n + (aux + per16 - 1) // per16 * per16
+    a = torch.randn(m, k, device=DEV).to(dtype)
+    b = torch.randn(rows, k, device=DEV).to(dtype)
+    b[n + aux:] = 0
+    bias = torch.randn(n, device=DEV).to(dtype)
+    c, side = ops.gemm_aux(a, b, m=m, n=n, k=k, aux_cols=aux, bias=bias, out_dtype=torch.float32)
+    want = a.double() @ b.double().t()
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert_close("C", c.cpu(), (want[:, :n] + bias.double()).cpu(), tol)
+    assert_close("side", side[:, :aux].cpu(), want[:, n:n + aux].cpu(), 1e-5 if dtype == torch.float32 else 1e-5)
+    assert float(side[:, aux:].abs().max()) == 0.0 if side.shape[1] > aux else True
 
 
 # ---------------------------------------------------------------------------------------------
