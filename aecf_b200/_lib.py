@@ -43,6 +43,7 @@ class PoolDesc(C.Structure):
         ("bias_stride_b", C.c_int64), ("bias_stride_h", C.c_int64),
         ("kv_stride_b", C.c_int64), ("kv_stride_m", C.c_int64),
         ("fold_key", C.c_int32), ("reserved", C.c_int32),
+        ("rng_state", C.c_void_p),
     ]
 
 

@@ -114,6 +114,7 @@ static int make_plan(const aecf_pool_desc* d, PoolPlan* plan, bool fold = false)
     p.q_shared = d->q_is_shared;
     p.rng.k0 = static_cast<uint32_t>(d->seed); p.rng.k1 = static_cast<uint32_t>(d->seed >> 32);
     p.rng.offset = static_cast<uint32_t>(d->offset); p.rng.row0 = d->row0;
+    p.rng_state = reinterpret_cast<const unsigned long long*>(d->rng_state);
     p.bias_sb = d->bias_stride_b; p.bias_sh = d->bias_stride_h;
     if (fold) {
         if (!d->q_is_shared) return AECF_ERR_UNSUPPORTED;       // the fold needs one query for all rows

@@ -153,6 +153,18 @@ constexpr uint32_t STREAM_MASK = 0u, STREAM_DROPOUT = 1u;
 
 struct RngKey { uint32_t k0, k1, offset; unsigned long long row0; };
 
+// The key a kernel draws with: the by-value one, or -- under CUDA-graph capture -- the (seed, offset) pair read
+// from device memory at run time (aecf_pool_desc::rng_state), so that replays draw fresh numbers.
+__device__ __forceinline__ RngKey effective_rng(const RngKey& by_value, const unsigned long long* state) {
+    RngKey k = by_value;
+    if (state != nullptr) {
+        const unsigned long long seed = __ldg(state), off = __ldg(state + 1);
+        k.k0 = static_cast<uint32_t>(seed); k.k1 = static_cast<uint32_t>(seed >> 32);
+        k.offset = static_cast<uint32_t>(off + by_value.offset);
+    }
+    return k;
+}
+
 // The 4 uniforms of (row, stream, head, block) -- tokens 4*block .. 4*block+3.
 __device__ __forceinline__ void draw4(const RngKey& key, unsigned long long local_row, uint32_t stream,
                                       uint32_t head, uint32_t block, float (&u)[4]) {

@@ -53,6 +53,7 @@ pool_bwd_kernel(const PoolParams p) {
     for (int i = lane; i < Smem::PER_WARP; i += 32) strip[i] = 0.f;
     __syncwarp();
     pdl_wait();
+    const RngKey rng = effective_rng(p.rng, p.rng_state);
 
     const int slice = warp % p.WPS;
     const int c0 = slice * Core::CPW + lane;
@@ -94,10 +95,10 @@ pool_bwd_kernel(const PoolParams p) {
         if constexpr (FOLD) {
             float s[M][J];
             Core::load_scores(p, row, c0, s);
-            Core::softmax_dropout(p, row, c0, s, w, wd, keep);
+            Core::softmax_dropout(p, rng, row, c0, s, w, wd, keep);
         } else {
             Core::attention_weights(
-                p, row, c0, qs,
+                p, rng, row, c0, qs,
                 [&](int m, int j) { return valid(j) ? ldg_cached(kv_row + Core::kv_rel(p, m, 0, j)) : make_uint4(0, 0, 0, 0); },
                 w, wd, keep);
         }

@@ -26,6 +26,7 @@ struct PoolParams {
     float scale, p_drop, one_minus_p, base_mask_prob, log_m;   // one_minus_p = float(1.0 - double(p_drop))
     int training, masking, min_active, q_shared;   // masking: 0 off, 1 training-mode stage, 2 eval-mode stage
     RngKey rng;
+    const unsigned long long* rng_state;    // device {seed, offset} overriding rng.k0/k1/offset (graph capture), or null
     const void* q;
     const void* kv;
     const float* bias;
@@ -168,11 +169,11 @@ struct PoolCore {
     //   keep : dropout keep flags, bit (m * J + j); d wd / d w = keep / (1 - p)
     template <typename LoadK>
     static __device__ __forceinline__ void attention_weights(
-        const PoolParams& p, long long row, int c0, const float (&qs)[J][V], LoadK load_k,
+        const PoolParams& p, const RngKey& rng, long long row, int c0, const float (&qs)[J][V], LoadK load_k,
         float (&w)[M][J], float (&wd)[M][J], unsigned& keep) {
         float s[M][J];
         key_scores(p, qs, load_k, s);
-        softmax_dropout(p, row, c0, s, w, wd, keep);
+        softmax_dropout(p, rng, row, c0, s, w, wd, keep);
     }
 
     // head index of each of this lane's chunk columns
@@ -218,7 +219,7 @@ struct PoolCore {
 
     // (+ additive mask) -> softmax over the M tokens -> dropout
     static __device__ __forceinline__ void softmax_dropout(
-        const PoolParams& p, long long row, int c0, float (&s)[M][J],
+        const PoolParams& p, const RngKey& rng, long long row, int c0, float (&s)[M][J],
         float (&w)[M][J], float (&wd)[M][J], unsigned& keep) {
         int head[J];
         heads_of(p, c0, head);
@@ -253,7 +254,7 @@ struct PoolCore {
 #pragma unroll
                 for (int blk = 0; blk < (M + 3) / 4; ++blk) {
                     float u[4];
-                    draw4(p.rng, static_cast<unsigned long long>(row), STREAM_DROPOUT,
+                    draw4(rng, static_cast<unsigned long long>(row), STREAM_DROPOUT,
                           static_cast<uint32_t>(head[j]), blk, u);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {

@@ -18,7 +18,7 @@ namespace aecf {
 
 // CurriculumMasking.forward for one sample, exact IEEE arithmetic (reference aecf/AECFLayer.py:130-283).
 template <int M>
-__device__ __forceinline__ void masking_stage(const PoolParams& p, long long row, const float (&pw)[M],
+__device__ __forceinline__ void masking_stage(const PoolParams& p, const RngKey& rng, long long row, const float (&pw)[M],
                                               float (&mw)[M], float& entropy, float& mask_rate, unsigned& bits) {
     entropy = 0.f;
     mask_rate = 0.f;
@@ -51,7 +51,7 @@ __device__ __forceinline__ void masking_stage(const PoolParams& p, long long row
 #pragma unroll
     for (int blk = 0; blk < (M + 3) / 4; ++blk) {
         float u4[4];
-        draw4(p.rng, static_cast<unsigned long long>(row), STREAM_MASK, 0u, blk, u4);
+        draw4(rng, static_cast<unsigned long long>(row), STREAM_MASK, 0u, blk, u4);
 #pragma unroll
         for (int i = 0; i < 4; ++i) u[4 * blk + i] = u4[i];
     }
@@ -105,6 +105,7 @@ pool_fwd_kernel(const PoolParams p) {
     const long long row = row_ok ? row0 + slot : p.B - 1;   // tail warps recompute the last row, store nothing
     const int c0 = slice * Core::CPW + lane;
     pdl_wait();
+    const RngKey rng = effective_rng(p.rng, p.rng_state);
 
     const char* kv_row = static_cast<const char*>(p.kv) + Core::row_offset(p, row, c0);
     auto load_kv = [&](int m, int half, int j) -> uint4 {
@@ -127,11 +128,11 @@ pool_fwd_kernel(const PoolParams p) {
     if constexpr (FOLD) {
         float s[M][J];
         Core::load_scores(p, row, c0, s);
-        Core::softmax_dropout(p, row, c0, s, w, wd, keep);
+        Core::softmax_dropout(p, rng, row, c0, s, w, wd, keep);
     } else {
         float qs[J][V];
         Core::load_query(p, row, c0, qs);
-        Core::attention_weights(p, row, c0, qs, [&](int m, int j) { return load_kv(m, 0, j); }, w, wd, keep);
+        Core::attention_weights(p, rng, row, c0, qs, [&](int m, int j) { return load_kv(m, 0, j); }, w, wd, keep);
     }
 
     // ---- weighted value sum (torch/nn/functional.py:6647) ---------------------------------
@@ -183,7 +184,7 @@ pool_fwd_kernel(const PoolParams p) {
     for (int m = 0; m < M; ++m) pw[m] = head_sums[lane * M + m] / denom;
     float entropy, mask_rate;
     unsigned bits;
-    masking_stage<M>(p, my_row, pw, mw, entropy, mask_rate, bits);
+    masking_stage<M>(p, rng, my_row, pw, mw, entropy, mask_rate, bits);
 #pragma unroll
     for (int m = 0; m < M; ++m) {
         p.pooled[static_cast<size_t>(my_row) * M + m] = pw[m];
@@ -219,6 +220,7 @@ pool_fwd_stream_kernel(const PoolParams p, const long long rows_per_warp) {
     const int c0 = lane;
     const char* kv = static_cast<const char*>(p.kv);
     pdl_wait();
+    const RngKey rng = effective_rng(p.rng, p.rng_state);
 
     auto prefetch = [&](long long row, int stage) {
         const char* src = kv + Core::row_offset(p, row, c0);
@@ -264,8 +266,8 @@ pool_fwd_stream_kernel(const PoolParams p, const long long rows_per_warp) {
 
         float w[M][J], wd[M][J];
         unsigned keep;
-        if constexpr (FOLD) Core::softmax_dropout(p, row, c0, s, w, wd, keep);
-        else Core::attention_weights(p, row, c0, qs, [&](int m, int j) { return staged(m, 0, j); }, w, wd, keep);
+        if constexpr (FOLD) Core::softmax_dropout(p, rng, row, c0, s, w, wd, keep);
+        else Core::attention_weights(p, rng, row, c0, qs, [&](int m, int j) { return staged(m, 0, j); }, w, wd, keep);
 
         float acc[J][V];
 #pragma unroll
@@ -300,7 +302,7 @@ pool_fwd_stream_kernel(const PoolParams p, const long long rows_per_warp) {
                 for (int m = 0; m < M; ++m) pw[m] = mine[m] / denom;
                 float entropy, mask_rate;
                 unsigned bits;
-                masking_stage<M>(p, my_row, pw, mw, entropy, mask_rate, bits);
+                masking_stage<M>(p, rng, my_row, pw, mw, entropy, mask_rate, bits);
 #pragma unroll
                 for (int m = 0; m < M; ++m) {
                     p.pooled[static_cast<size_t>(my_row) * M + m] = pw[m];

@@ -31,6 +31,7 @@ class PoolConfig:
     min_active: int = 1
     seed: int = 0
     offset: int = 0
+    rng_state: Optional[torch.Tensor] = None    # device int64 {seed, offset} read at run time (CUDA-graph capture)
     row0: int = 0
     q_shared: bool = True
     seq_first: bool = False     # key/value are [M, B, D] (batch_first=False), used in place
@@ -76,7 +77,7 @@ class FusedPoolFunction(torch.autograd.Function):
             masking=cfg.masking, min_active=cfg.min_active, q_is_shared=cfg.q_shared,
             base_mask_prob=cfg.base_mask_prob, entropy_target=cfg.entropy_target, dropout_p=cfg.dropout_p,
             seed=cfg.seed, offset=cfg.offset, row0=cfg.row0, bias_strides=cfg.bias_strides, kv_strides=kv_strides,
-            fold_key=fold)
+            fold_key=fold, rng_state=cfg.rng_state)
 
         q_in = q_src.reshape(D) if cfg.q_shared else q_src.reshape(B, D)
         if not q_in.is_contiguous():

@@ -48,6 +48,37 @@ class _PhiloxState:
         self.explicit_seed: Optional[int] = None
         self.seen_seed: Optional[int] = None
         self.offset = 0
+        # CUDA-graph capture: per-device int64 tensor {seed, next offset} that captured forwards read and
+        # advance ON THE DEVICE (a by-value pair would be frozen into the graph); see aecf_b200.graphs
+        self.device_states: Dict[int, torch.Tensor] = {}
+
+    def prepare_device_state(self, device: torch.device) -> torch.Tensor:
+        """Create (or refresh) the device-side {seed, next offset} pair from the host-side state.  Must run
+        outside capture: captured forwards then draw from it and advance it with captured kernels."""
+        seed, offset = self.next(device)
+        index = device.index if device.index is not None else torch.cuda.current_device()
+        host = torch.tensor([seed - (1 << 64) if seed >= (1 << 63) else seed, offset], dtype=torch.int64)
+        with self.lock:
+            state = self.device_states.get(index)
+            if state is None:
+                state = self.device_states[index] = host.to(device)
+            else:
+                state.copy_(host)
+        return state
+
+    def captured(self, device: torch.device) -> torch.Tensor:
+        """Inside capture: a snapshot of the device-side pair for this call (the backward's recompute reads
+        the same snapshot), after which the device-side offset moves on -- both as captured kernels."""
+        index = device.index if device.index is not None else torch.cuda.current_device()
+        state = self.device_states.get(index)
+        if state is None:
+            raise RuntimeError(
+                "aecf_b200: a forward that draws random numbers is being captured into a CUDA graph, but the "
+                "device-side Philox state does not exist yet. Call aecf_b200.graphs.prepare(device) before the "
+                "capture (aecf_b200.graphs.capture_step does it for you).")
+        used = state.clone()
+        state[1:2].add_(1)
+        return used
 
     def next(self, device: Optional[torch.device] = None) -> Tuple[int, int]:
         with self.lock:
@@ -74,6 +105,12 @@ def set_rng_state(seed: Optional[int], offset: int = 0) -> None:
         _rng.explicit_seed = seed
         _rng.seen_seed = None
         _rng.offset = int(offset) & 0xFFFFFFFF
+        stale = list(_rng.device_states)
+    if seed is not None and stale and not torch.cuda.is_current_stream_capturing():
+        for index in stale:                                  # graphs captured earlier follow the new pair too
+            s64 = seed & 0xFFFFFFFFFFFFFFFF
+            host = torch.tensor([s64 - (1 << 64) if s64 >= (1 << 63) else s64, _rng.offset], dtype=torch.int64)
+            _rng.device_states[index].copy_(host)
 
 
 def get_rng_state() -> Tuple[int, int]:
@@ -331,13 +368,17 @@ class MultimodalAttentionPool(nn.Module):
         else:
             fold = can_fold and bool(self.fold_key_projection)
         draws = (att.training and att.dropout > 0.0) or masking == 1
-        seed, offset = _rng.next(key.device) if draws else (0, 0)
+        rng_state = None
+        if draws and torch.cuda.is_current_stream_capturing():
+            seed, offset, rng_state = 0, 0, _rng.captured(key.device)
+        else:
+            seed, offset = _rng.next(key.device) if draws else (0, 0)
         cfg = PoolConfig(
             num_heads=self.num_heads, dropout_p=att.dropout, training=att.training, masking=masking,
             base_mask_prob=cm.base_mask_prob if fused_cm else 0.15,
             entropy_target=cm.entropy_target if fused_cm else 0.7,
             min_active=cm.min_active if fused_cm else 1,
-            seed=seed, offset=offset, row0=int(self.row_offset), q_shared=q_shared,
+            seed=seed, offset=offset, rng_state=rng_state, row0=int(self.row_offset), q_shared=q_shared,
             seq_first=not self.batch_first, fold=fold, want_mask_bits=self._want_mask_bits, bias_strides=bias_strides,
             grad_ready=self._grad_ready, grad_buffers=self._grad_buffers)
         out, pooled, entropy, mask_rate, masked, bits = FusedPoolFunction.apply(

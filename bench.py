@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=4096, help="rows of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--graph", choices=["on", "off"], default="on",
+                    help="replay the step as one CUDA graph (aecf_b200.graphs) instead of enqueueing ~25 kernels from Python")
     ap.add_argument("--fold", choices=["auto", "on", "off"], default="auto",
                     help="folded key projection (auto: the module's choice, on for bf16)")
     return ap.parse_args()
@@ -201,7 +203,9 @@ def workload_config(args, n_gpus):
             "dropout": args.dropout, "parallelism": f"dp{n_gpus}",
             "fold_key_projection": bool(getattr(args, "folded", False)),
             "l2": "inputs larger than L2 (x 201 MB, values 201 MB per step vs 126 MB L2); no flush needed",
-            "step": "forward(return_info) + entropy_loss + backward(d_out), public module API"}
+            "step": "forward(return_info) + entropy_loss + backward(d_out), public module API"
+                    + (", captured once with aecf_b200.graphs.GraphedStep and replayed" if getattr(args, "graph", "off") == "on"
+                       and getattr(args, "impl", "b200") == "b200" else "")}
 
 
 def run_reference(args):
@@ -285,10 +289,24 @@ def run_b200(args):
 
     # ---- device-resident timing -----------------------------------------------------------
     # Region A (the reported value): K steps, no per-kernel events -- kernels chain by programmatic dependent
-    # launch.  Region B: K more steps with a CUDA event pair around every launch of the library (on the
-    # launching stream) for the per-kernel durations behind `roofline`, `kernels` and `gemm_tensor_pipe`.
+    # launch; with --graph on (default) the step was captured once (warm-up steps run eagerly first) and each
+    # timed step is one graph replay.  Region B: K more EAGER steps with a CUDA event pair around every launch
+    # of the library (on the launching stream) for the per-kernel durations behind `roofline`, `kernels` and
+    # `gemm_tensor_pipe`.
+    use_graph = args.graph == "on"
     for _ in range(args.warmup):
         step(x); clear()
+    barrier()
+    launches0 = _lib.launch_count()
+    if use_graph:
+        graphed = aecf_b200.graphs.GraphedStep(lambda: step(x), reset=clear, warmup=0, device=dev)
+        launches_per_step = _lib.launch_count() - launches0              # counted while capturing one step
+        for _ in range(args.warmup):
+            graphed()
+        run_step = graphed
+    else:
+        def run_step():
+            step(x); clear()
     barrier()
     launches0 = _lib.launch_count()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -296,12 +314,13 @@ def run_b200(args):
         start.record()
         t_issue = time.perf_counter()
         for _ in range(args.steps):
-            step(x); clear()
+            run_step()
         end.record()
         issue_ms = (time.perf_counter() - t_issue) * 1e3 / args.steps   # host time to enqueue one step
         barrier()
         ms = start.elapsed_time(end) / args.steps
-        launches = (_lib.launch_count() - launches0)
+        launches = launches_per_step * args.steps if use_graph else (_lib.launch_count() - launches0)
+        clear()
         _lib.timing_enable(True)
         start_b, end_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start_b.record()
@@ -335,6 +354,24 @@ def run_b200(args):
                 bufs[slot].detach().copy_(host, non_blocking=True)
                 copied[slot].record(copy_stream)
 
+        def clear_all():
+            for b in bufs:
+                b.grad = None
+            query.grad = None
+            pool.zero_grad(set_to_none=True)
+
+        if use_graph:                                   # one graph per input slot (each replays on its own buffer)
+            clear_all()
+            slot_steps = [aecf_b200.graphs.GraphedStep(lambda b=b: step(b), reset=clear_all, warmup=1, device=dev)
+                          for b in bufs]
+        else:
+            def eager_slot(b):
+                def run():
+                    loss = step(b)
+                    return loss
+                return run
+            slot_steps = [eager_slot(b) for b in bufs]
+
         def e2e_loop(n):
             for c in consumed:
                 c.record()
@@ -344,12 +381,11 @@ def run_b200(args):
                 if i + 1 < n:
                     upload(i + 1)
                 torch.cuda.current_stream().wait_event(copied[slot])
-                loss = step(bufs[slot])
+                loss = slot_steps[slot]()
                 host_loss.copy_(loss.reshape(1), non_blocking=True)
                 consumed[slot].record()
-                bufs[slot].grad = None
-                query.grad = None
-                pool.zero_grad(set_to_none=True)
+                if not use_graph:
+                    clear_all()
             torch.cuda.synchronize()
 
         e2e_loop(max(2, args.warmup))
@@ -414,7 +450,8 @@ def run_b200(args):
             "gemm_tensor_pipe": gemms, "kernels": kernels, "host_issue_ms_per_step": issue_ms,
             "ms_per_step_with_kernel_events": ms_with_events,
             "kernel_ms_sum": sum(k["ms"] * k["calls_per_step"] for k in kernels.values()),
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(), "library": _lib.build_info()}
+            "e2e": e2e, "gpu_launches": launches, "cuda_graph": use_graph, "clocks": clocks.summary(),
+            "library": _lib.build_info()}
 
     if world == 1 and not args.no_cpu_baseline:
         cpu_value, cpu_ms, cores = time_cpu(args, args.cpu_sample, 3, 1)

@@ -90,6 +90,10 @@ typedef struct aecf_pool_desc {
     int64_t  kv_stride_m;     /* packed [B, M, 2D] layout (M*2D, 2D); a sequence-first [M, B, 2D] buffer is (2D, B*2D) */
     int32_t  fold_key;        /* whole-step entry points only: 1 = folded key projection (see "folded key projection") */
     int32_t  reserved;        /* 0 */
+    /* CUDA-graph capture: a by-value (seed, offset) would be frozen into the graph.  When non-null, this DEVICE
+     * pointer to {seed, offset} (two uint64) is read by the kernels at run time instead: key = seed, call offset =
+     * low 32 bits of (offset + desc.offset); the caller advances the device-side offset between replays. */
+    const uint64_t* rng_state;
 } aecf_pool_desc;
 
 /* Forward: scale, per-head scores, softmax, dropout, weighted value sum, head mean, and the whole

@@ -25,7 +25,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert b"sm_100a" in lib.aecf_build_info()
     assert lib.aecf_strerror(-2).decode().startswith("shape or dtype outside")
     # structs mirror the header: sizes are what the C compiler lays out (natural alignment)
-    assert ctypes.sizeof(_lib.PoolDesc) == 120 and ctypes.sizeof(_lib.GemmDesc) == 88
+    assert ctypes.sizeof(_lib.PoolDesc) == 128 and ctypes.sizeof(_lib.GemmDesc) == 88
 
 
 def test_descriptor_validation_needs_no_gpu():
