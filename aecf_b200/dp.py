@@ -6,11 +6,14 @@ sum-all-reduce of the fusion parameter gradients per step (1 051 136 elements at
 
   * rank r owns global rows [r*B/N, (r+1)*B/N); ``pool.row_offset`` keys the Philox counters on the
     GLOBAL row, so any N reproduces the 1-GPU masks and dropout bit for bit
-  * the backward writes its parameter gradients straight into one flat bucket (no copies); the
-    bucket is reduced in two groups in readiness order -- the out-projection gradients as soon as
-    ``aecf_fusion_bwd(AECF_BWD_OUT_PROJ)`` has produced them, on a side stream, while the fused pool
-    backward and the in-projection GEMMs still run; the in-projection and query gradients at the end
-  * ``overlap=False`` reduces the whole bucket once, after the backward, on the compute stream
+  * the backward writes its parameter gradients straight into one flat bucket (no copies), which is reduced
+    with ONE all-reduce after the backward, on the compute stream (the default): measured at 8 B200s with the
+    step replayed as a CUDA graph, 46 us on top of a 686 us step (profiles/r1_run17_dp8_study.json)
+  * ``overlap=True`` (or AECF_DP_OVERLAP=1) reduces in two groups in readiness order instead -- the
+    out-projection gradients on a side stream as soon as ``aecf_fusion_bwd(AECF_BWD_OUT_PROJ)`` has produced
+    them, the rest at the end.  It measured SLOWER (814 vs 732 us per step at N = 8): the persistent GEMM and
+    pool kernels size their grids to own every SM, and NCCL's CTAs landing on some SMs first delay the CTAs
+    that should have run there, which stretches the whole kernel
 
 Works with any ``torch.distributed`` backend: NCCL on the GPUs, gloo in the CPU tests of the host logic.
 """
@@ -45,7 +48,7 @@ class GradientSync:
                  average: bool = True, overlap: Optional[bool] = None):
         self.pool, self.query, self.group, self.average = pool, query, process_group, average
         if overlap is None:
-            overlap = os.environ.get("AECF_DP_OVERLAP", "1") != "0"
+            overlap = os.environ.get("AECF_DP_OVERLAP", "0") == "1"
         self.overlap = overlap
         att = pool.attention
         self.params: Dict[str, torch.nn.Parameter] = {}
@@ -72,6 +75,7 @@ class GradientSync:
         self.pending: List[object] = []
         self.reported: set = set()
         self.reduced_upto = 0
+        self.enabled = True                              # False: gradients stay local (measurements, gradient accumulation)
 
     # -- wiring -----------------------------------------------------------------------------
     def attach(self) -> "GradientSync":
@@ -118,7 +122,7 @@ class GradientSync:
 
     # -- called from the backward (autograd worker thread) -----------------------------------
     def on_ready(self, name: str, grad: torch.Tensor) -> None:
-        if name not in self.slices or name in self.reported or self.world_size == 1:
+        if not self.enabled or name not in self.slices or name in self.reported or self.world_size == 1:
             return                                                     # single process: autograd's .grad is final
         view = self.views[name]
         if grad.data_ptr() != view.data_ptr():                         # produced elsewhere: copy into the bucket

@@ -51,6 +51,9 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=4096, help="rows of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--dp-study", action="store_true",
+                    help="N > 1: also time the step with the other all-reduce mode and with no all-reduce at all "
+                         "(separates collective cost from rank-to-rank variance); per-rank times are reported either way")
     ap.add_argument("--graph", choices=["on", "off"], default="on",
                     help="replay the step as one CUDA graph (aecf_b200.graphs) instead of enqueueing ~25 kernels from Python")
     ap.add_argument("--fold", choices=["auto", "on", "off"], default="auto",
@@ -236,6 +239,16 @@ def kernel_averages(sites, steps):
     return {name: {"ms": total / count, "calls_per_step": count / steps} for name, (total, count) in sites.items()}
 
 
+def finish_process(world):
+    """Leave without tearing NCCL down.  With the step captured into CUDA graphs that hold NCCL kernels,
+    destroy_process_group() blocked for minutes on the 8-GPU box (r1 run 16); every rank has passed the last
+    barrier and rank 0 has printed its line, so exit directly."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1:
+        os._exit(0)
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -255,6 +268,11 @@ def run_b200(args):
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"            # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
+        # a multi-rank run that wedges (a lost peer, a collective that never completes) must not sit on N GPUs
+        # until somebody's outer timeout: hard stop after 10 minutes
+        guard = threading.Timer(600.0, lambda: os._exit(3))
+        guard.daemon = True
+        guard.start()
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     es = 2 if dtype == torch.bfloat16 else 4
     B, M, D, H = args.batch, args.tokens, args.dim, args.heads
@@ -331,10 +349,53 @@ def run_b200(args):
     ms_with_events = start_b.elapsed_time(end_b) / args.steps
     kernels = kernel_averages(_lib.timing_collect(), args.steps)
     _lib.timing_enable(False)
+
+    def time_region(run):
+        """W warm-up + K timed calls of `run`, CUDA events, this rank's ms per step."""
+        for _ in range(args.warmup):
+            run()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.steps):
+            run()
+        b.record()
+        barrier()
+        return a.elapsed_time(b) / args.steps
+
+    def gather_ms(local_ms):
+        t = torch.zeros(world, device=dev, dtype=torch.float64)
+        t[rank] = local_ms
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(v) for v in t.tolist()]
+
+    dp_info = None
     if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        per_rank = gather_ms(ms)
+        ms = max(per_rank)
+        dp_info = {"all_reduce": "overlapped on a side stream (two groups)" if sync.overlap else "one call after the backward",
+                   "per_rank_ms": per_rank, "in_graph": use_graph}
+        if args.dp_study:
+            def variant(configure, restore):
+                configure(); clear()
+                if use_graph:
+                    g = aecf_b200.graphs.GraphedStep(lambda: step(x), reset=clear, warmup=1, device=dev)
+                    t_ms = time_region(g)
+                    del g
+                else:
+                    t_ms = time_region(lambda: (step(x), clear()))
+                restore(); clear()
+                return gather_ms(t_ms)
+
+            was = sync.overlap
+            other = variant(lambda: setattr(sync, "overlap", not was), lambda: setattr(sync, "overlap", was))
+            dp_info["other_mode"] = {"all_reduce": "one call after the backward" if was else "overlapped on a side stream",
+                                     "per_rank_ms": other, "ms_per_step": max(other),
+                                     "value": B * world / (max(other) * 1e-3)}
+            # no collective at all: what rank-to-rank variance alone costs
+            alone = variant(lambda: setattr(sync, "enabled", False), lambda: setattr(sync, "enabled", True))
+            dp_info["no_all_reduce"] = {"per_rank_ms": alone, "ms_per_step": max(alone),
+                                        "value": B * world / (max(alone) * 1e-3)}
     value = B * world / (ms * 1e-3)
 
     # ---- end to end: batch starts in pinned host memory every step -----------------------------
@@ -403,8 +464,8 @@ def run_b200(args):
                "note": "host batch -> double-buffered H2D on a copy stream -> step -> loss scalar D2H"}
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        barrier()                                        # rank 0 is past its last collective too
+        finish_process(world)
         return
 
     # ---- roofline of the fused pool kernels and tensor-pipe use of the GEMMs ----------------------
@@ -452,6 +513,8 @@ def run_b200(args):
             "kernel_ms_sum": sum(k["ms"] * k["calls_per_step"] for k in kernels.values()),
             "e2e": e2e, "gpu_launches": launches, "cuda_graph": use_graph, "clocks": clocks.summary(),
             "library": _lib.build_info()}
+    if dp_info is not None:
+        line["data_parallel"] = dp_info
 
     if world == 1 and not args.no_cpu_baseline:
         cpu_value, cpu_ms, cores = time_cpu(args, args.cpu_sample, 3, 1)
@@ -459,8 +522,8 @@ def run_b200(args):
                                 "sample": f"{args.cpu_sample} rows of the same workload per step, 3 steps, fp32, "
                                           f"torch CPU ops ({cpu_model()})", "ms_per_step": cpu_ms}
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    barrier()
+    finish_process(world)
 
 
 def main():

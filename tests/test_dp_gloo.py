@@ -65,14 +65,14 @@ class _Params(torch.nn.Module):
         self._grad_buffers = None
 
 
-def _worker(rank, port, out_dir):
+def _worker(rank, port, out_dir, overlap):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=WORLD)
     try:
         t = _inputs()
         pool = _Params(t)
         query = torch.nn.Parameter(t["q0"].clone())
-        sync = GradientSync(pool, query, average=False).attach()
+        sync = GradientSync(pool, query, average=False, overlap=overlap).attach()
         row0, rows = sync.set_shard(B)
         assert pool.row_offset == row0 and pool._grad_ready is not None and set(pool._grad_buffers) == set(PARAM_ORDER)
         fwd, grads = _step(t, row0, rows)
@@ -85,8 +85,9 @@ def _worker(rank, port, out_dir):
                 pool._grad_ready(name, pool._grad_buffers[name])
             else:                                         # a gradient produced elsewhere is copied in
                 pool._grad_ready(name, grads[name])
-            # the out-projection group is reduced as soon as both of its members are in
-            assert len(sync.pending) == (1 if i >= 1 else 0)
+            # overlap=True: the out-projection group is reduced as soon as both of its members are in;
+            # the default (overlap=False) reduces the whole bucket once, in finish()
+            assert len(sync.pending) == ((1 if i >= 1 else 0) if overlap else 0)
         sync.finish()
         assert not sync.pending and not sync.reported
         assert pool.attention.in_proj_weight.grad.data_ptr() == pool._grad_buffers["in_proj_weight"].data_ptr()
@@ -97,9 +98,10 @@ def _worker(rank, port, out_dir):
         dist.destroy_process_group()
 
 
-def test_two_ranks_reproduce_one_rank(tmp_path):
+@pytest.mark.parametrize("overlap", [False, True], ids=["one_all_reduce", "overlapped_groups"])
+def test_two_ranks_reproduce_one_rank(tmp_path, overlap):
     port = _free_port()
-    mp.spawn(_worker, args=(port, str(tmp_path)), nprocs=WORLD, join=True)
+    mp.spawn(_worker, args=(port, str(tmp_path), overlap), nprocs=WORLD, join=True)
     t = _inputs()
     full_fwd, full_grads = _step(t, 0, B)
     shards = [np.load(tmp_path / f"rank{r}.npz") for r in range(WORLD)]
