@@ -42,6 +42,10 @@ struct TimedLaunch {                                          // brackets the la
         if (err__ != cudaSuccess) return ::aecf::set_cuda_error(err__, #call); \
     } while (0)
 
+// fold.cu: dWq, d_query and the packed in-projection bias gradient of a shared query, one launch
+int launch_query_tail(int dtype, int D, const float* d_qp, const void* q0, const void* in_proj_weight,
+                      const float* d_bias_kv, void* d_in_proj_weight, void* d_query, void* d_in_proj_bias, cudaStream_t s);
+
 // ---- programmatic dependent launch (PDL) -----------------------------------------------------
 // Every kernel of the library is launched with programmatic stream serialization and starts with
 // pdl_wait(): its CTAs may be scheduled while the previous kernel of the stream is still draining

@@ -8,27 +8,36 @@
 namespace aecf {
 
 // folded_w = [ Wv (D rows) ; Qk (H rows) ; zeros (HSP - H rows) ], each row D wide.
-//   blocks [0, fold_blocks): one thread per (r, d), r < HSP:  Qk[r, d] = scale * sum_j q[r*hd + j] * Wk[r*hd + j, d]
+//   blocks [0, fold_blocks): block (strip of 32 columns d, row r < HSP), 32 x 8 threads: the 8 thread rows split the
+//       head_dim terms of  Qk[r, d] = scale * sum_j q[r*hd + j] * Wk[r*hd + j, d]  (every load independent) and are
+//       folded through shared memory in a fixed order
 //   the remaining blocks copy Wv, 16 bytes per thread, grid-stride.
 template <typename T>
 __global__ void __launch_bounds__(256)
 fold_prepare_kernel(const float* __restrict__ q_proj, const T* __restrict__ in_proj_weight, int D, int H, int HSP,
                     float scale, int fold_blocks, T* __restrict__ folded_w) {
+    __shared__ float red[8][33];
     pdl_wait();
     const int hd = D / H;
     if (static_cast<int>(blockIdx.x) < fold_blocks) {
-        const int i = blockIdx.x * 256 + threadIdx.x;
-        if (i >= HSP * D) return;
-        const int r = i / D, d = i - r * D;
+        const int strips = (D + 31) / 32;
+        const int r = blockIdx.x / strips;
+        const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+        const int d = (blockIdx.x - r * strips) * 32 + x;
         float acc = 0.f;
-        if (r < H) {
+        if (r < H && d < D) {
             const T* wk = in_proj_weight + (static_cast<size_t>(D) + static_cast<size_t>(r) * hd) * D + d;
             const float* q = q_proj + r * hd;
-#pragma unroll 8
-            for (int j = 0; j < hd; ++j) acc = fmaf(__ldg(q + j), to_float<T>(wk[static_cast<size_t>(j) * D]), acc);
-            acc *= scale;
+#pragma unroll 4
+            for (int j = y; j < hd; j += 8) acc = fmaf(__ldg(q + j), to_float<T>(wk[static_cast<size_t>(j) * D]), acc);
         }
-        folded_w[(static_cast<size_t>(D) + r) * D + d] = from_float<T>(acc);
+        red[y][x] = acc;
+        __syncthreads();
+        if (y != 0 || d >= D) return;
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += red[k][x];
+        folded_w[(static_cast<size_t>(D) + r) * D + d] = from_float<T>(s * scale);
         return;
     }
     const uint4* src = reinterpret_cast<const uint4*>(in_proj_weight + 2 * static_cast<size_t>(D) * D);
@@ -69,6 +78,64 @@ fold_finish_kernel(const float* __restrict__ g, const float* __restrict__ q_proj
     if (lane == 0 && d_q_proj) d_q_proj[i] = scale * dot;
 }
 
+// The query-side tail of the backward for a shared query, one launch instead of three (outer product, GEMV, pack):
+//   dWq[i, :]  = d_qp[i] * q0[:]                 rows [0, D) of d_in_proj_weight        (torch/nn/functional.py:5854)
+//   d_query[i] = sum_k d_qp[k] * Wq[k, i]
+//   d_in_proj_bias = [ d_qp | d_bias_kv ]        in the parameter dtype
+// Block b owns the 8 indices i = 8b .. 8b+7.
+template <typename T>
+__global__ void __launch_bounds__(256)
+query_tail_kernel(const float* __restrict__ d_qp, const T* __restrict__ q0, const T* __restrict__ in_proj_weight,
+                  const float* __restrict__ d_bias_kv, int D, T* __restrict__ d_in_proj_weight, T* __restrict__ d_query,
+                  T* __restrict__ d_in_proj_bias) {
+    __shared__ float red[32][9];
+    pdl_wait();
+    const int i0 = blockIdx.x * 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (d_in_proj_weight != nullptr && i0 + warp < D) {
+        const int i = i0 + warp;
+        const float g = __ldg(d_qp + i);
+        T* row = d_in_proj_weight + static_cast<size_t>(i) * D;
+        for (int d = lane; d < D; d += 32) row[d] = from_float<T>(g * to_float<T>(q0[d]));
+    }
+    if (d_query != nullptr) {
+        const int ii = threadIdx.x & 7, kl = threadIdx.x >> 3;           // 8 columns x 32 row lanes
+        float acc = 0.f;
+        if (i0 + ii < D)
+            for (int k = kl; k < D; k += 32) acc = fmaf(__ldg(d_qp + k), to_float<T>(in_proj_weight[static_cast<size_t>(k) * D + i0 + ii]), acc);
+        red[kl][ii] = acc;
+        __syncthreads();
+        if (threadIdx.x < 8 && i0 + threadIdx.x < D) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) s += red[k][threadIdx.x];
+            d_query[i0 + threadIdx.x] = from_float<T>(s);
+        }
+    }
+    if (d_in_proj_bias != nullptr && threadIdx.x < 8 && i0 + threadIdx.x < D) {
+        const int i = i0 + threadIdx.x;
+        d_in_proj_bias[i] = from_float<T>(d_qp[i]);
+        d_in_proj_bias[D + i] = from_float<T>(d_bias_kv[i]);
+        d_in_proj_bias[2 * D + i] = from_float<T>(d_bias_kv[D + i]);
+    }
+}
+
+int launch_query_tail(int dtype, int D, const float* d_qp, const void* q0, const void* in_proj_weight,
+                      const float* d_bias_kv, void* d_in_proj_weight, void* d_query, void* d_in_proj_bias, cudaStream_t s) {
+    const dim3 grid((D + 7) / 8), block(256);
+    if (dtype == AECF_BF16)
+        AECF_CUDA_OK(launch_pdl(query_tail_kernel<__nv_bfloat16>, grid, block, 0, s, d_qp, static_cast<const __nv_bfloat16*>(q0),
+                                static_cast<const __nv_bfloat16*>(in_proj_weight), d_bias_kv, D,
+                                static_cast<__nv_bfloat16*>(d_in_proj_weight), static_cast<__nv_bfloat16*>(d_query),
+                                static_cast<__nv_bfloat16*>(d_in_proj_bias)));
+    else
+        AECF_CUDA_OK(launch_pdl(query_tail_kernel<float>, grid, block, 0, s, d_qp, static_cast<const float*>(q0),
+                                static_cast<const float*>(in_proj_weight), d_bias_kv, D, static_cast<float*>(d_in_proj_weight),
+                                static_cast<float*>(d_query), static_cast<float*>(d_in_proj_bias)));
+    count_launch();
+    return AECF_OK;
+}
+
 static int fold_check(int dtype, int D, int H) {
     if (dtype != AECF_F32 && dtype != AECF_BF16) return AECF_ERR_INVALID;
     if (D <= 0 || H <= 0 || D % H != 0) return AECF_ERR_INVALID;
@@ -91,7 +158,7 @@ int aecf_fold_prepare(int32_t device, int32_t dtype, int32_t embed_dim, int32_t 
     if ((rc = use_device(device)) != AECF_OK) return rc;
     const int D = embed_dim, H = num_heads, hsp = aecf_fold_score_cols(dtype, H);
     const float scale = static_cast<float>(sqrt(1.0 / static_cast<double>(D / H)));
-    const int fold_blocks = (hsp * D + 255) / 256;
+    const int fold_blocks = hsp * ((D + 31) / 32);
     const int copy_blocks = 128;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     TimedLaunch timed(s);

@@ -286,40 +286,36 @@ int aecf_fusion_bwd(const aecf_pool_desc* desc, const aecf_fusion_tensors* t, co
         }
     }
     }
-    if (gr->d_in_proj_weight) {   // ---- query rows of the in-projection weight gradient -------------------------
-        ScopedSite site(AECF_SITE_D_Q_WEIGHT);
-        if (g.shared) {               // dW_q = d_qp (outer) q0
-            const aecf_gemm_desc d = gemm_desc(dev, AECF_F32, dt, dt, dt, AECF_MN_MAJOR, AECF_MN_MAJOR, D, D, 1, D, D, D);
-            AECF_TRY(aecf_gemm(&d, w.d_qp, t->query, nullptr, gr->d_in_proj_weight, w.gemm, w.gemm_bytes, stream));
-        } else {                      // dW_q = d_q^T Q
-            const aecf_gemm_desc d = gemm_desc(dev, dt, dt, dt, dt, AECF_MN_MAJOR, AECF_MN_MAJOR, D, D, g.B, D, D, D);
-            AECF_TRY(aecf_gemm(&d, gr->d_q_rows, t->query, nullptr, gr->d_in_proj_weight, w.gemm, w.gemm_bytes, stream));
+    if (g.shared) {
+        // ---- query side, shared query: dWq = d_qp (x) q0, d_query = d_qp . Wq, [d_bq | d_bk | d_bv] -- one launch
+        if (gr->d_in_proj_weight || gr->d_query || gr->d_in_proj_bias) {
+            ScopedSite site(AECF_SITE_D_QUERY);
+            TimedLaunch timed(s);
+            AECF_TRY(launch_query_tail(dt, D, w.d_qp, t->query, t->in_proj_weight, w.d_bias_kv, gr->d_in_proj_weight,
+                                       gr->d_query, gr->d_in_proj_bias, s));
         }
+        return AECF_OK;
     }
-    if (gr->d_query) {                // ---- gradient of the (unprojected) query --------------------------------
+    if (gr->d_in_proj_weight) {   // ---- query rows of the in-projection weight gradient: dW_q = d_q^T Q -------------
+        ScopedSite site(AECF_SITE_D_Q_WEIGHT);
+        const aecf_gemm_desc d = gemm_desc(dev, dt, dt, dt, dt, AECF_MN_MAJOR, AECF_MN_MAJOR, D, D, g.B, D, D, D);
+        AECF_TRY(aecf_gemm(&d, gr->d_q_rows, t->query, nullptr, gr->d_in_proj_weight, w.gemm, w.gemm_bytes, stream));
+    }
+    if (gr->d_query) {                // ---- gradient of the (unprojected) per-row queries ------------------------
         ScopedSite site(AECF_SITE_D_QUERY);
-        if (g.shared) {
-            const aecf_gemm_desc d = gemm_desc(dev, AECF_F32, dt, dt, dt, AECF_K_MAJOR, AECF_MN_MAJOR, 1, D, D, D, D, D);
-            AECF_TRY(aecf_gemm(&d, w.d_qp, t->in_proj_weight, nullptr, gr->d_query, w.gemm, w.gemm_bytes, stream));
-        } else {
-            const aecf_gemm_desc d = gemm_desc(dev, dt, dt, dt, dt, AECF_K_MAJOR, AECF_MN_MAJOR, g.B, D, D, D, D, D);
-            AECF_TRY(aecf_gemm(&d, gr->d_q_rows, t->in_proj_weight, nullptr, gr->d_query, w.gemm, w.gemm_bytes, stream));
-        }
+        const aecf_gemm_desc d = gemm_desc(dev, dt, dt, dt, dt, AECF_K_MAJOR, AECF_MN_MAJOR, g.B, D, D, D, D, D);
+        AECF_TRY(aecf_gemm(&d, gr->d_q_rows, t->in_proj_weight, nullptr, gr->d_query, w.gemm, w.gemm_bytes, stream));
     }
     if (gr->d_in_proj_bias) {         // ---- [d_bq | d_bk | d_bv] in the parameter dtype ------------------------
         ScopedSite site(AECF_SITE_D_IN_BIAS);
-        const float* dbq = w.d_qp;
-        if (!g.shared) {
-            AECF_TRY(aecf_colsum(dev, dt, AECF_F32, gr->d_q_rows, g.B, D, D, w.d_bq, w.colsum, w.colsum_bytes, stream));
-            dbq = w.d_bq;
-        }
+        AECF_TRY(aecf_colsum(dev, dt, AECF_F32, gr->d_q_rows, g.B, D, D, w.d_bq, w.colsum, w.colsum_bytes, stream));
         TimedLaunch timed(s);
         const int n = 3 * D;
         if (dt == AECF_BF16)
-            AECF_CUDA_OK(launch_pdl(pack_in_bias_kernel<__nv_bfloat16>, dim3((n + 255) / 256), dim3(256), 0, s, dbq, w.d_bias_kv,
+            AECF_CUDA_OK(launch_pdl(pack_in_bias_kernel<__nv_bfloat16>, dim3((n + 255) / 256), dim3(256), 0, s, w.d_bq, w.d_bias_kv,
                                     D, static_cast<__nv_bfloat16*>(gr->d_in_proj_bias)));
         else
-            AECF_CUDA_OK(launch_pdl(pack_in_bias_kernel<float>, dim3((n + 255) / 256), dim3(256), 0, s, dbq, w.d_bias_kv, D,
+            AECF_CUDA_OK(launch_pdl(pack_in_bias_kernel<float>, dim3((n + 255) / 256), dim3(256), 0, s, w.d_bq, w.d_bias_kv, D,
                                     static_cast<float*>(gr->d_in_proj_bias)));
         count_launch();
     }

@@ -30,7 +30,10 @@ struct BwdSmem {
 // key pass -- the score gradient ds[b, m, h] itself is stored next to dV (d_kv rows are [dV (D) | ds (HSP)]) and
 // the dX / dW GEMMs that follow contract over D + HSP, which applies and accumulates the rank-H key-side terms.
 template <typename T, int M, int J, bool DROP, bool FOLD>
-__global__ void __launch_bounds__(POOL_WARPS * 32, 2)
+// The folded variant has no key pass and fits 80 registers without spilling for M * J <= 10 (ptxas -v): three CTAs
+// per SM instead of two, i.e. half as many loads again in flight for a kernel that waits on HBM latency
+// (ncu r1 run 18: long-scoreboard stalls dominate, 25 % of the warp slots occupied).
+__global__ void __launch_bounds__(POOL_WARPS * 32, (FOLD && M * J <= 10 && J <= 2) ? 3 : 2)
 pool_bwd_kernel(const PoolParams p) {
     using Core = PoolCore<T, M, J, DROP>;
     using Smem = BwdSmem<J, Core::V>;
