@@ -202,7 +202,7 @@ pool_fwd_kernel(const PoolParams p) {
 // arithmetic never waits on HBM.  Head sums of up to 32 consecutive rows stay in lane registers (lane i
 // keeps row i); the masking stage then runs once per 32 rows with one row per lane.
 template <typename T, int M, int J, bool DROP, bool FOLD>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__((FOLD && J <= 2) ? 768 : 512, 1)
 pool_fwd_stream_kernel(const PoolParams p, const long long rows_per_warp) {
     using Core = PoolCore<T, M, J, DROP>;
     constexpr int V = Core::V;
