@@ -29,10 +29,8 @@ constexpr int UMMA_K = 16;
 constexpr int STAGES = 4;
 constexpr int NUM_THREADS = 192;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 constexpr int EPI_THREADS = 128;
-// k-blocks of L2 prefetch lookahead for the producer.  Measured on B200 (profiles/r1_gemm_experiments.md):
-// 12 k-blocks ahead made every projection 15-35 % SLOWER (the prefetch stream competes with the real
-// loads for TMA issue and L2 bandwidth), so it is off.
-constexpr int PREFETCH_DIST = 0;
+// (An L2 prefetch stream 12 k-blocks ahead of the ring made every projection 15-35 % SLOWER on B200 --
+// profiles/r1_gemm_experiments.md -- and was removed.)
 constexpr long long SPIN_LIMIT = 4000000000LL;   // ~2 s of SM clocks: trap instead of hanging the GPU
 
 template <int BN> struct Cfg {
@@ -104,12 +102,6 @@ __device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* map, uint64_t*
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
         " [%0], [%1, {%4, %5}], [%2], %3;"
         :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1) : "memory");
-}
-// Pull a box into L2 only (no shared-memory destination): issued PREFETCH_DIST k-blocks ahead of the real
-// load so that the load hits L2 instead of paying the HBM latency inside the 4-stage ring.
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
-                 :: "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -227,6 +219,24 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
     }
 }
 
+// One lane of a fully active warp (the lowest).  The producer and the MMA issuer walk their loops with the WHOLE warp
+// and elect inside: under `if (lane == 0)` the compiler has to emulate every uniform-datapath instruction (UTMALDG,
+// UTCHMMA, UTCBAR) of the divergent region with an election loop plus vector->uniform register moves -- 38
+// instructions per tcgen05.mma in r1 run 18's SASS, more issue latency than the MMA takes to execute.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+// Advancing a shared-memory descriptor by `bytes` is an add on its 14-bit start-address field (16-byte units); every
+// address stays inside the 227 KB of shared memory, so the field never carries into its neighbours.
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (bytes >> 4); }
+__device__ __forceinline__ uint32_t k_slice_bytes(int mn_major) { return mn_major ? UMMA_K * 128 : UMMA_K * 2; }
+
 struct WorkItem { int m_blk, n_blk, split, kb_begin, kb_count; };
 
 // Work items are (split, row-block group, column block); the CL CTAs of a cluster take the CL row blocks of
@@ -287,88 +297,74 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     pdl_wait();                                      // everything above overlapped the previous kernel's tail
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            constexpr int PART = BN / CL;                 // this CTA's share of the B tile
-            // coordinates of one k-block's boxes; `go(map, dst_offset_in_stage_operand, c0, c1)` per box
-            auto for_each_a_box = [&](const WorkItem& w, int kb, auto&& go) {
-                const int k0 = (w.kb_begin + kb) * BK;
-                if (!p.a_mn_major) go(0, k0, w.m_blk * BM);
-                else
-                    for (int a = 0; a < BM / 64; ++a) go(a * (BK * 128), w.m_blk * BM + a * 64, k0);
-            };
-            auto for_each_b_box = [&](const WorkItem& w, int kb, auto&& go) {
-                const int k0 = (w.kb_begin + kb) * BK;
-                if (!p.b_mn_major) go(cta_rank * (PART * 128), k0, w.n_blk * BN + cta_rank * PART);
-                else
-                    for (int a = 0; a < PART / 64; ++a) {
-                        const int atom = cta_rank * (PART / 64) + a;
-                        go(atom * (BK * 128), w.n_blk * BN + atom * 64, k0);
-                    }
-            };
-            // lookahead cursor for the L2 prefetch stream
-            int pf_item = first_item, pf_kb = 0;
-            WorkItem pf_w = pf_item < items ? decode<CL>(p, pf_item, cta_rank) : WorkItem{};
-            auto pf_advance = [&]() {
-                if (pf_item >= items) return;
-                if (++pf_kb == pf_w.kb_count) {
-                    pf_item += item_stride;
-                    pf_kb = 0;
-                    if (pf_item < items) pf_w = decode<CL>(p, pf_item, cta_rank);
-                }
-            };
-            for (int i = 0; i < PREFETCH_DIST; ++i) pf_advance();
-
-            int it = 0;
-            for (int item = first_item; item < items; item += item_stride) {
-                const WorkItem w = decode<CL>(p, item, cta_rank);
-                for (int kb = 0; kb < w.kb_count; ++kb, ++it) {
-                    if (PREFETCH_DIST > 0 && pf_item < items) {
-                        for_each_a_box(pf_w, pf_kb, [&](int, int c0, int c1) { tma_prefetch_2d(&map_a, c0, c1); });
-                        for_each_b_box(pf_w, pf_kb, [&](int, int c0, int c1) { tma_prefetch_2d(&map_b, c0, c1); });
-                        pf_advance();
-                    }
-                    const int s = it % STAGES;
-                    mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);     // freed by the MMAs of ALL CTAs of the cluster
+        // ===== TMA producer: the whole warp walks the loop, one elected lane issues (see elect_one) =====
+        constexpr int PART = BN / CL;                 // this CTA's share of the B tile
+        int it = 0;
+        for (int item = first_item; item < items; item += item_stride) {
+            const WorkItem w = decode<CL>(p, item, cta_rank);
+            for (int kb = 0; kb < w.kb_count; ++kb, ++it) {
+                const int s = it % STAGES;
+                mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);     // freed by the MMAs of ALL CTAs of the cluster
+                if (elect_one()) {
                     uint8_t* a_dst = stage_base + s * C::STAGE_BYTES;
                     uint8_t* b_dst = a_dst + C::A_BYTES;
+                    const int k0 = (w.kb_begin + kb) * BK;
                     mbar_expect_tx(&full[s], C::STAGE_BYTES);
-                    for_each_a_box(w, kb, [&](int off, int c0, int c1) { tma_load_2d(&map_a, &full[s], a_dst + off, c0, c1); });
+                    if (!p.a_mn_major) {
+                        tma_load_2d(&map_a, &full[s], a_dst, k0, w.m_blk * BM);
+                    } else {
+#pragma unroll
+                        for (int a = 0; a < BM / 64; ++a)
+                            tma_load_2d(&map_a, &full[s], a_dst + a * (BK * 128), w.m_blk * BM + a * 64, k0);
+                    }
                     // with a cluster, this CTA fetches 1/CL of the B tile and multicasts it: every CTA's stage
                     // receives the full tile, each part read from L2 only once
-                    for_each_b_box(w, kb, [&](int off, int c0, int c1) {
-                        if (CL == 1) tma_load_2d(&map_b, &full[s], b_dst + off, c0, c1);
-                        else tma_load_2d_mc(&map_b, &full[s], b_dst + off, c0, c1, kAllCtas);
-                    });
+                    if (!p.b_mn_major) {
+                        if (CL == 1) tma_load_2d(&map_b, &full[s], b_dst + cta_rank * (PART * 128), k0, w.n_blk * BN + cta_rank * PART);
+                        else tma_load_2d_mc(&map_b, &full[s], b_dst + cta_rank * (PART * 128), k0, w.n_blk * BN + cta_rank * PART, kAllCtas);
+                    } else {
+#pragma unroll
+                        for (int a = 0; a < PART / 64; ++a) {
+                            const int atom = cta_rank * (PART / 64) + a;
+                            if (CL == 1) tma_load_2d(&map_b, &full[s], b_dst + atom * (BK * 128), w.n_blk * BN + atom * 64, k0);
+                            else tma_load_2d_mc(&map_b, &full[s], b_dst + atom * (BK * 128), w.n_blk * BN + atom * 64, k0, kAllCtas);
+                        }
+                    }
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc(BN, p.a_mn_major, p.b_mn_major);
-            int it = 0, tile_it = 0;
-            for (int item = first_item; item < items; item += item_stride, ++tile_it) {
-                const WorkItem w = decode<CL>(p, item, cta_rank);
-                const int as = tile_it & 1;
-                mbar_wait(&tmem_empty[as], ((tile_it >> 1) & 1) ^ 1);          // epilogue drained this accumulator
+        // ===== MMA issuer: the whole warp walks the loop, one elected lane issues (see elect_one) =====
+        const uint32_t idesc = make_idesc(BN, p.a_mn_major, p.b_mn_major);
+        const uint32_t stage0 = smem_u32(stage_base);
+        const uint64_t a_desc0 = operand_desc(stage0, p.a_mn_major, 0);                 // stage 0, K slice 0
+        const uint64_t b_desc0 = operand_desc(stage0 + C::A_BYTES, p.b_mn_major, 0);
+        const uint32_t a_ks = k_slice_bytes(p.a_mn_major), b_ks = k_slice_bytes(p.b_mn_major);
+        int it = 0, tile_it = 0;
+        for (int item = first_item; item < items; item += item_stride, ++tile_it) {
+            const WorkItem w = decode<CL>(p, item, cta_rank);
+            const int as = tile_it & 1;
+            mbar_wait(&tmem_empty[as], ((tile_it >> 1) & 1) ^ 1);          // epilogue drained this accumulator
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + as * C::ACC_STRIDE;
+            for (int kb = 0; kb < w.kb_count; ++kb, ++it) {
+                const int s = it % STAGES;
+                mbar_wait(&full[s], (it / STAGES) & 1);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + as * C::ACC_STRIDE;
-                for (int kb = 0; kb < w.kb_count; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    mbar_wait(&full[s], (it / STAGES) & 1);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(stage_base + s * C::STAGE_BYTES);
-                    const uint32_t b_addr = a_addr + C::A_BYTES;
+                if (elect_one()) {
+                    const uint64_t a_d = desc_advance(a_desc0, s * C::STAGE_BYTES);
+                    const uint64_t b_d = desc_advance(b_desc0, s * C::STAGE_BYTES);
 #pragma unroll
                     for (int ks = 0; ks < BK / UMMA_K; ++ks)
-                        umma_bf16(tmem_d, operand_desc(a_addr, p.a_mn_major, ks), operand_desc(b_addr, p.b_mn_major, ks),
-                                  idesc, (kb | ks) != 0 ? 1u : 0u);
+                        umma_bf16(tmem_d, desc_advance(a_d, ks * a_ks), desc_advance(b_d, ks * b_ks), idesc, (kb | ks) != 0 ? 1u : 0u);
                     if (CL == 1) umma_commit(&empty[s]);                       // smem slot free once these MMAs retire
                     else umma_commit_mc(&empty[s], kAllCtas);                  // ... in every CTA that multicasts into it
                 }
-                umma_commit(&tmem_full[as]);                                   // accumulator complete
+                __syncwarp();
             }
+            if (elect_one()) umma_commit(&tmem_full[as]);                      // accumulator complete
+            __syncwarp();
         }
     } else {
         // ===== epilogue: TMEM -> registers -> (+bias, convert) -> swizzled smem -> TMA store =====
@@ -550,14 +546,14 @@ gemm_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     pdl_wait();
 
     if (warp == 0) {
-        // ===== TMA producer (both CTAs; the leader also arms the barrier for both CTAs' bytes) =====
-        if (lane == 0) {
-            int it = 0;
-            for (int item = first_item; item < items; item += item_stride) {
-                const WorkItem w = decode<2>(p, item, cta_rank);
-                for (int kb = 0; kb < w.kb_count; ++kb, ++it) {
-                    const int s = it % S;
-                    mbar_wait_cluster(&empty[s], ((it / S) & 1) ^ 1);
+        // ===== TMA producer (both CTAs; the leader also arms the barrier for both CTAs' bytes); whole warp, one elected lane =====
+        int it = 0;
+        for (int item = first_item; item < items; item += item_stride) {
+            const WorkItem w = decode<2>(p, item, cta_rank);
+            for (int kb = 0; kb < w.kb_count; ++kb, ++it) {
+                const int s = it % S;
+                mbar_wait_cluster(&empty[s], ((it / S) & 1) ^ 1);
+                if (elect_one()) {
                     uint8_t* a_dst = stage_base + s * C::STAGE_BYTES;
                     uint8_t* b_dst = a_dst + C::A_BYTES;
                     if (leader) mbar_expect_tx(&full[s], 2 * C::STAGE_BYTES);
@@ -578,15 +574,20 @@ gemm_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
                             tma_load_2d_2sm(&map_b, &full[s], b_dst + a * (BK * 128), n_half + a * 64, k0);
                     }
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: leader CTA only, one instruction drives both SMs' tensor cores =====
-        if (leader && lane == 0) {
+        // ===== MMA issuer: leader CTA only, one instruction drives both SMs' tensor cores; whole warp, one elected lane =====
+        if (leader) {
             // M = 256: m_dim field = 256 >> 4
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(p.a_mn_major) << 15) |
                                    (static_cast<uint32_t>(p.b_mn_major) << 16) | (static_cast<uint32_t>(BN >> 3) << 17) |
                                    (static_cast<uint32_t>(256 >> 4) << 24);
+            const uint32_t stage0 = smem_u32(stage_base);
+            const uint64_t a_desc0 = operand_desc(stage0, p.a_mn_major, 0);
+            const uint64_t b_desc0 = operand_desc(stage0 + C::A_BYTES, p.b_mn_major, 0);
+            const uint32_t a_ks = k_slice_bytes(p.a_mn_major), b_ks = k_slice_bytes(p.b_mn_major);
             int it = 0, tile_it = 0;
             for (int item = first_item; item < items; item += item_stride, ++tile_it) {
                 const WorkItem w = decode<2>(p, item, cta_rank);
@@ -598,15 +599,19 @@ gemm_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
                     const int s = it % S;
                     mbar_wait_cluster(&full[s], (it / S) & 1);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(stage_base + s * C::STAGE_BYTES);
-                    const uint32_t b_addr = a_addr + C::A_BYTES;
+                    if (elect_one()) {
+                        const uint64_t a_d = desc_advance(a_desc0, s * C::STAGE_BYTES);
+                        const uint64_t b_d = desc_advance(b_desc0, s * C::STAGE_BYTES);
 #pragma unroll
-                    for (int ks = 0; ks < BK / UMMA_K; ++ks)
-                        umma_bf16_2sm(tmem_d, operand_desc(a_addr, p.a_mn_major, ks), operand_desc(b_addr, p.b_mn_major, ks),
-                                      idesc, (kb | ks) != 0 ? 1u : 0u);
-                    umma_commit_2sm(&empty[s], 0b11);                          // frees the slot in both CTAs
+                        for (int ks = 0; ks < BK / UMMA_K; ++ks)
+                            umma_bf16_2sm(tmem_d, desc_advance(a_d, ks * a_ks), desc_advance(b_d, ks * b_ks), idesc,
+                                          (kb | ks) != 0 ? 1u : 0u);
+                        umma_commit_2sm(&empty[s], 0b11);                          // frees the slot in both CTAs
+                    }
+                    __syncwarp();
                 }
-                umma_commit_2sm(&tmem_full[as], 0b11);                         // accumulator complete in both CTAs
+                if (elect_one()) umma_commit_2sm(&tmem_full[as], 0b11);            // accumulator complete in both CTAs
+                __syncwarp();
             }
         }
     } else {

@@ -103,6 +103,9 @@ class FusedPoolFunction(torch.autograd.Function):
         ops.fusion_fwd(desc, tensors, dev)
 
         ctx.cfg, ctx.desc = cfg, desc
+        # gradients of outputs the loss does not use arrive as None instead of freshly zero-filled tensors:
+        # no fill kernels, and the backward kernel skips the d_pooled / d_entropy terms altogether
+        ctx.set_materialize_grads(False)
         ctx.shape = (B, M, D)
         ctx.q_shape = q_src.shape
         ctx.save_for_backward(q_in, key, value, in_w, in_b, out_w, out_b, qp, kv, attn, score_bias, scores, folded_w)
