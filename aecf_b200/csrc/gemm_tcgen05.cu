@@ -786,16 +786,14 @@ static Plan make_plan(const aecf_gemm_desc* d, int aux_cols = 0) {
     }
     pl.kb_per_split = (pl.kb_total + splits - 1) / splits;
     pl.splits = (pl.kb_total + pl.kb_per_split - 1) / pl.kb_per_split;
-    // cta_group::2 (one 256 x 256 tile per CTA pair, deeper ring) wins when the main loop of a work item is
-    // long (measured: dX K=1024 173 -> 154-160 us, dW_kv 164 -> 158-161 us) and loses on the K = 512 products
-    // whose tiles are epilogue-heavy (kv_proj 180 -> 203 us); AECF_GEMM_2SM=0/1 forces it off/on.
+    // cta_group::2 (one 256 x 256 tile per CTA pair: each CTA stages its 128 rows of A and HALF of the B tile, a third
+    // fewer operand bytes delivered per FLOP, and a deeper ring).  A/B on one box with the warp-uniform issue loops
+    // (profiles/r1_gemm_experiments.md, run 24): it wins from 9 k-blocks per work item on -- dX (K = 520) 109 -> 103 us,
+    // [dWv ; R] 121 -> 112 us even though its 520 rows fill only 2.03 of 3 CTA pairs -- and loses on the 8-k-block
+    // products (out_proj 38 -> 42 us), whose per-tile pair handshake is not amortised.  AECF_GEMM_2SM=0/1 forces it.
     static const int force_2sm = [] { const char* e = getenv("AECF_GEMM_2SM"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
-    // A CTA pair owns 256 rows: an odd number of row blocks leaves half a pair computing padding, which on a short
-    // M costs more than the deeper ring gains (the folded [dWv ; R] product has M = D + 8 = 520: 5 row blocks are
-    // 768 rows for pairs but 640 for single CTAs).
-    const bool long_k = pl.kb_per_split >= 16;
-    const bool pairs_fit = pl.tiles_m % 2 == 0 || pl.tiles_m >= 16;
-    pl.two_sm = pl.cluster == 2 && pl.bn == 256 && (force_2sm < 0 ? (long_k && pairs_fit) : force_2sm == 1);
+    const bool long_k = pl.kb_per_split >= 9;
+    pl.two_sm = pl.cluster == 2 && pl.bn == 256 && (force_2sm < 0 ? long_k : force_2sm == 1);
     if (aux_cols > 0 && pl.splits != 1) return pl;       // the side output is written by the direct epilogue only
     pl.ok = true;
     return pl;
