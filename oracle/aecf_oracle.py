@@ -225,13 +225,19 @@ def pool_backward(query: Tensor, key: Tensor, value: Optional[Tensor],
                   saved: Dict[str, Tensor], grad_out: Tensor, *,
                   grad_pooled: Optional[Tensor] = None, grad_entropy: Optional[Tensor] = None,
                   dropout_p: float = 0.0, training: bool = True, has_bias: bool = True,
-                  storage: Optional[torch.dtype] = None) -> Dict[str, Tensor]:
+                  storage: Optional[torch.dtype] = None, fold_key: bool = False) -> Dict[str, Tensor]:
     """Closed-form backward of pool_forward.
 
     The reference has no backward source: it is autograd over
     torch/nn/functional.py:5847-5865, 6630-6659.  tests/test_oracle_golden.py
     checks this against autograd of the reference itself.
     Single-query form (S == 1), which is the hot path.
+    ``fold_key``: the association the CUDA path's folded key projection uses (one shared query): dK is never
+    formed; with ds the score gradient, Qk[h] = scale * Wk_h^T q_h and R[h] = sum_{b,m} ds[b,h,m] x[b,m],
+        dX   = dV Wv + ds Qk            dWk[h*hd + j] = scale * q[h*hd + j] * R[h]
+        d q[h*hd + j] = scale * Wk[h*hd + j] . R[h]        (the bk * sum ds term is analytically zero and dropped)
+    Same mathematics as autograd of the reference, re-associated; tests/test_oracle_golden.py checks it against
+    the reference's own gradients.
     """
     if value is None:
         value = key
@@ -271,6 +277,8 @@ def pool_backward(query: Tensor, key: Tensor, value: Optional[Tensor],
     else:
         d_w = d_wd
     d_s = w * (d_w - (w * d_w).sum(-1, keepdim=True))
+    if fold_key:
+        return _folded_input_grads(query, key, in_proj_weight, saved, d_s, d_v, d_wo, d_bo, scale, H, has_bias, storage)
     d_qh = scale * torch.einsum("bhm,bmhe->bhe", d_s, kh)
     d_k = scale * torch.einsum("bhm,bhe->bmhe", d_s, qp)
     d_k = _round(d_k.reshape(B, M, D), storage)
@@ -291,6 +299,35 @@ def pool_backward(query: Tensor, key: Tensor, value: Optional[Tensor],
     grads["in_proj_weight"] = torch.cat([d_wq, d_wk, d_wv], 0)
     if has_bias:
         grads["in_proj_bias"] = torch.cat([d_qp.sum(0), d_k.sum((0, 1)), d_v.sum((0, 1))], 0)
+    return grads
+
+
+def _folded_input_grads(query, key, in_proj_weight, saved, d_s, d_v, d_wo, d_bo, scale, H, has_bias, storage):
+    """Input / in-projection gradients of pool_backward in the folded association (see its docstring)."""
+    B, _, D = query.shape
+    M = key.shape[1]
+    hd = D // H
+    Wq, Wk, Wv = in_proj_weight[:D], in_proj_weight[D:2 * D], in_proj_weight[2 * D:]
+    q0 = saved["qp"][0, 0]                                         # the one projected query, [D]
+    qk = _round(torch.einsum("he,hed->hd", q0.view(H, hd), Wk.view(H, hd, D)) * scale, storage)     # [H, D]
+    d_s = _round(d_s, storage)                                     # stored next to dV in the storage dtype
+    d_v = _round(d_v.reshape(B, M, D), storage)
+    x = key.reshape(B * M, D)
+    r = torch.einsum("bhm,bmd->hd", d_s, key)                      # R[h] = sum ds x
+    d_wk = (scale * q0).view(H, hd, 1) * r.view(H, 1, D)           # [H, hd, D]
+    d_q0 = scale * torch.einsum("hed,hd->he", Wk.view(H, hd, D), r).reshape(D)
+    d_wq = torch.outer(d_q0, query[0, 0])
+    d_wv = d_v.reshape(B * M, D).t() @ x
+    grads = {
+        "out_proj.weight": d_wo, "out_proj.bias": d_bo,
+        "key": d_v @ Wv + torch.einsum("bhm,hd->bmd", d_s, qk),
+        # the caller sums the per-row query gradient over the batch: put the whole (already reduced) gradient in row 0
+        "query": torch.cat([(d_q0 @ Wq).view(1, 1, D), torch.zeros(B - 1, 1, D, dtype=query.dtype)], 0),
+        "in_proj_weight": torch.cat([d_wq, d_wk.reshape(D, D), d_wv], 0),
+    }
+    if has_bias:
+        d_bk = (scale * q0).view(H, hd) * d_s.sum((0, 2)).view(H, 1)
+        grads["in_proj_bias"] = torch.cat([d_q0, d_bk.reshape(D), d_v.sum((0, 1))], 0)
     return grads
 
 

@@ -46,7 +46,7 @@ def run_oracle(case: Case, inp: Optional[dict] = None, dtype: Optional[torch.dty
         q, inp["x"], value, inp["in_proj_weight"], inp["out_proj.weight"], case.H, fwd.saved,
         inp["grad_out"], grad_pooled=inp["grad_pooled"] if case.pooled_grad else None,
         grad_entropy=None if case.training else torch.full((B, 1), 0.5, dtype=inp["x"].dtype),
-        dropout_p=case.dropout, training=case.training, storage=storage)
+        dropout_p=case.dropout, training=case.training, storage=storage, fold_key=fold_key)
     grads["query0"] = grads.pop("query").sum(0, keepdim=True)
     return fwd, grads
 

@@ -8,7 +8,7 @@ import torch
 
 import aecf
 import aecf_b200
-from aecf_b200 import _lib
+from aecf_b200 import _lib, ops
 from aecf_b200.layers import _PhiloxState
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -151,3 +151,47 @@ def test_philox_call_counter():
         assert aecf_b200.get_rng_state() == (99, 7)
     finally:
         aecf_b200.set_rng_state(None)
+
+
+def test_folded_entry_points_validate_without_a_gpu():
+    """Descriptor / argument checks of the folded-key-projection entry points run before any CUDA call."""
+    lib = _lib.load()
+    assert lib.aecf_fold_score_cols(_lib.BF16, 8) == 8 and lib.aecf_fold_score_cols(_lib.BF16, 12) == 16
+    assert lib.aecf_fold_score_cols(_lib.F32, 1) == 4 and lib.aecf_fold_score_cols(_lib.F32, 8) == 8
+    assert ops.fold_score_cols(torch.bfloat16, 8) == (8, 8) and ops.fold_score_cols(torch.float32, 6) == (8, 8)
+    d = _lib.PoolDesc(device=0, dtype=_lib.BF16, batch=4, num_tokens=3, embed_dim=64, num_heads=8, q_is_shared=0)
+    # the fold needs ONE query for all rows
+    assert lib.aecf_pool_fwd_folded(ctypes.byref(d), 16, 16, None, 16, 16, None, None, None, None, None) == _lib.ERR_UNSUPPORTED
+    d.q_is_shared = 1
+    assert lib.aecf_pool_fwd_folded(ctypes.byref(d), None, 16, None, 16, 16, None, None, None, None, None) == _lib.ERR_INVALID
+    assert lib.aecf_pool_fwd_folded(ctypes.byref(d), 16, 8, None, 16, 16, None, None, None, None, None) == _lib.ERR_ALIGNMENT
+    d.kv_stride_b, d.kv_stride_m = 1, -2                                 # row strides must be positive
+    assert lib.aecf_pool_fwd_folded(ctypes.byref(d), 16, 16, None, 16, 16, None, None, None, None, None) == _lib.ERR_INVALID
+    d.kv_stride_b, d.kv_stride_m = 0, 0
+    assert lib.aecf_pool_bwd_folded(ctypes.byref(d), 16, 16, 16, None, 16, None, None, 16, None, 16, 0, None) == _lib.ERR_WORKSPACE
+    g = _lib.GemmDesc(device=0, dtype_a=_lib.BF16, dtype_b=_lib.BF16, dtype_c=_lib.BF16, m=256, n=128, k=64,
+                      lda=64, ldb=64, ldc=128)
+    for cols, ld in ((0, 8), (33, 36), (8, 4)):                          # no side columns / too many / aux_ld too small
+        assert lib.aecf_gemm_aux(ctypes.byref(g), 16, 16, None, 16, 16, cols, ld, None, 0, None) == _lib.ERR_INVALID
+    assert lib.aecf_fold_prepare(0, 7, 64, 8, 16, 16, 16, None) == _lib.ERR_INVALID       # unknown dtype
+    assert lib.aecf_fold_prepare(0, _lib.BF16, 64, 7, 16, 16, 16, None) == _lib.ERR_INVALID   # 7 does not divide 64
+    assert lib.aecf_fold_finish(0, _lib.F32, 64, 8, None, 16, 16, None, None, None) == _lib.ERR_INVALID
+    # whole-step entry point: a folded descriptor with per-row queries is refused before anything is enqueued
+    d.fold_key, d.q_is_shared = 1, 0
+    t = _lib.FusionTensors()
+    assert lib.aecf_fusion_fwd(ctypes.byref(d), ctypes.byref(t), 16, 1 << 30, None) == _lib.ERR_UNSUPPORTED
+
+
+def test_graph_helper_needs_a_gpu_and_says_so():
+    from aecf_b200 import graphs
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        graphs.GraphedStep(lambda: None)
+
+
+def test_pool_exposes_the_fold_switch():
+    pool = aecf.MultimodalAttentionPool(16, num_heads=2)
+    assert pool.fold_key_projection is None                              # automatic: on for bf16 with a shared query
+    pool.fold_key_projection = False
+    assert "fold" not in repr(pool)                                      # extra_repr stays the reference's

@@ -43,6 +43,35 @@ def test_forward_matches_reference(case):
                  g["entropy_loss"], tol, atol=tol)
 
 
+FOLDABLE = [c for c in CASES if not c.separate_value]
+
+
+@pytest.mark.parametrize("case", FOLDABLE, ids=lambda c: c.name)
+def test_folded_key_projection_matches_reference(case):
+    """The association the CUDA path's folded key projection uses (scores = x . (scale Wk_h^T q_h), rank-H key-side
+    gradients through R = sum ds x) against the reference's own outputs and autograd gradients: identical masks,
+    everything else to rounding."""
+    g = load_golden(case)
+    fwd, grads = run_oracle(case, fold_key=True)
+    f64 = case.dtype == "float64"
+    tol, gtol = (1e-11, 1e-10) if f64 else (1e-5, 3e-5)
+    assert_close("out", fwd.out, g["out"], tol)
+    assert_close("attention_weights", fwd.info["attention_weights"], g["attention_weights"], tol, atol=tol)
+    assert_close("entropy", fwd.info["entropy"], g["entropy"], tol, atol=tol)
+    assert np.array_equal(fwd.info["mask_rate"].numpy(), g["mask_rate"])
+    if case.training and case.M > 1:
+        live = g["attention_weights"] > 0
+        assert np.array_equal((fwd.info["mask"].numpy() > 0) & live, g["masked_attention_weights"] > 0)
+    assert_close("grad_x", grads["key"], g["grad_x"], gtol)
+    assert_close("grad_query0", grads["query0"], g["grad_query0"], gtol)
+    scale = float(np.abs(g["grad_in_proj_bias"]).max())
+    assert_close("grad_in_proj_bias", grads["in_proj_bias"], g["grad_in_proj_bias"], gtol, atol=gtol * scale)
+    if case.full_grads:
+        assert_close("grad_in_proj_weight", grads["in_proj_weight"], g["grad_in_proj_weight"], gtol)
+    else:
+        assert_close("grad_in_proj_weight_rowsum", grads["in_proj_weight"].sum(1), g["grad_in_proj_weight_rowsum"], gtol)
+
+
 @pytest.mark.parametrize("case", CASES, ids=lambda c: c.name)
 def test_backward_matches_reference_autograd(case):
     g = load_golden(case)
