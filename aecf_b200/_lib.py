@@ -27,6 +27,7 @@ EXPORTS = (
     "aecf_colsum", "aecf_colsum_workspace_bytes",
     "aecf_entropy_loss_fwd", "aecf_entropy_loss_bwd", "aecf_curriculum_mask", "aecf_entropy_bwd", "aecf_sdpa_fwd",
     "aecf_fusion_fwd", "aecf_fusion_bwd", "aecf_fusion_workspace_bytes",
+    "aecf_peer_flag_bytes", "aecf_peer_enable_access", "aecf_peer_allreduce",
     "aecf_timing_enable", "aecf_timing_collect", "aecf_timing_site_name",
     "aecf_abi_version", "aecf_strerror", "aecf_last_cuda_error", "aecf_launch_count", "aecf_build_info",
 )
@@ -56,6 +57,11 @@ class GemmDesc(C.Structure):
         ("m", C.c_int64), ("n", C.c_int64), ("k", C.c_int64),
         ("lda", C.c_int64), ("ldb", C.c_int64), ("ldc", C.c_int64),
     ]
+
+
+class PeerDesc(C.Structure):
+    _fields_ = [("device", C.c_int32), ("dtype", C.c_int32), ("world", C.c_int32), ("rank", C.c_int32),
+                ("count", C.c_int64), ("average", C.c_int32), ("grid_limit", C.c_int32)]
 
 
 class FusionTensors(C.Structure):
@@ -137,6 +143,12 @@ def _declare(lib):
                                     vp, C.c_size_t, vp]
     lib.aecf_fusion_workspace_bytes.restype = C.c_size_t
     lib.aecf_fusion_workspace_bytes.argtypes = [C.POINTER(PoolDesc)]
+    lib.aecf_peer_flag_bytes.restype = C.c_size_t
+    lib.aecf_peer_flag_bytes.argtypes = []
+    lib.aecf_peer_enable_access.restype = C.c_int
+    lib.aecf_peer_enable_access.argtypes = [C.c_int32, C.c_int32]
+    lib.aecf_peer_allreduce.restype = C.c_int
+    lib.aecf_peer_allreduce.argtypes = [C.POINTER(PeerDesc), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), vp]
     lib.aecf_timing_enable.restype = C.c_int
     lib.aecf_timing_enable.argtypes = [C.c_int32]
     lib.aecf_timing_collect.restype = C.c_int

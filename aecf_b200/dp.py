@@ -36,6 +36,58 @@ def shard_rows(global_batch: int, rank: int, world_size: int) -> Tuple[int, int]
     return start, base + (1 if rank < extra else 0)
 
 
+class PeerAllReduce:
+    """In-place all-reduce of one CUDA tensor across the ranks of ONE node over NVLink peer memory, without NCCL:
+    ``csrc/peer_allreduce.cu`` (barrier, every rank reduces its slice from all buckets in rank order and stores it
+    into all buckets, barrier; bit-identical results on every rank, graph-capturable).
+
+    Construction is collective: every rank exports its bucket and a small flag block through CUDA IPC (torch's
+    tensor sharing), the handles travel through ``all_gather_object`` of ``group`` (any backend), and every rank
+    maps the other ranks' buffers and enables peer access to their devices.  The bucket must stay alive, and must
+    not be reallocated, for the lifetime of this object.  Opt-in (``GradientSync(collective="peer")`` or
+    ``AECF_DP_PEER=1``): single-device emulation is tested (``tests/test_gpu_peer_allreduce.py``), the
+    multi-process path is scheduled for its first hardware run in round 2.
+    """
+
+    def __init__(self, bucket: torch.Tensor, group=None, average: bool = True):
+        from torch.multiprocessing.reductions import reduce_tensor
+
+        from . import _lib, ops
+        if not bucket.is_cuda or not bucket.is_contiguous():
+            raise ValueError("PeerAllReduce needs a contiguous CUDA tensor")
+        self.bucket, self.group, self.average = bucket, group, average
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if self.world > 8:
+            raise ValueError("PeerAllReduce covers the (at most 8) GPUs of one NVLink node")
+        dev = bucket.device
+        self.flags = ops.peer_flag_block(dev)
+        self.buckets, self.flag_blocks = [bucket], [self.flags]
+        if self.world > 1:
+            torch.cuda.synchronize(dev)
+            payload = (reduce_tensor(bucket), reduce_tensor(self.flags), dev.index or 0)
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, payload, group=group)
+            self.buckets, self.flag_blocks = [], []
+            for r, (b, f, peer_dev) in enumerate(gathered):
+                if r == self.rank:
+                    self.buckets.append(bucket)
+                    self.flag_blocks.append(self.flags)
+                    continue
+                _lib.check(_lib.load().aecf_peer_enable_access(dev.index or 0, peer_dev), f"peer access {dev.index} -> {peer_dev}")
+                self.buckets.append(b[0](*b[1]))             # rebuild_cuda_tensor: rank r's memory mapped into this process
+                self.flag_blocks.append(f[0](*f[1]))
+            dist.barrier(group=group)                        # everybody has mapped everything before anybody signals
+        self._ops = ops
+
+    def __call__(self) -> None:
+        """Enqueue the all-reduce on the current stream of the bucket's device."""
+        if self.world == 1:
+            return
+        with torch.cuda.device(self.bucket.device):
+            self._ops.peer_allreduce(self.buckets, self.flag_blocks, self.rank, average=self.average)
+
+
 class GradientSync:
     """All-reduce (mean by default) of the fusion parameter gradients of one pool + its query.
 
@@ -45,8 +97,13 @@ class GradientSync:
     """
 
     def __init__(self, pool, query: Optional[torch.nn.Parameter] = None, process_group=None,
-                 average: bool = True, overlap: Optional[bool] = None):
+                 average: bool = True, overlap: Optional[bool] = None, collective: Optional[str] = None):
         self.pool, self.query, self.group, self.average = pool, query, process_group, average
+        if collective is None:
+            collective = "peer" if os.environ.get("AECF_DP_PEER", "0") == "1" else "nccl"
+        if collective not in ("nccl", "peer"):
+            raise ValueError(f"collective must be 'nccl' or 'peer', got {collective!r}")
+        self.collective = collective                     # 'nccl': torch.distributed all_reduce; 'peer': PeerAllReduce
         if overlap is None:
             overlap = os.environ.get("AECF_DP_OVERLAP", "0") == "1"
         self.overlap = overlap
@@ -76,6 +133,10 @@ class GradientSync:
         self.reported: set = set()
         self.reduced_upto = 0
         self.enabled = True                              # False: gradients stay local (measurements, gradient accumulation)
+        self.peer = None
+        if collective == "peer" and self.cuda and dist.is_initialized() and dist.get_world_size(process_group) > 1:
+            self.peer = PeerAllReduce(self.bucket, process_group, average)     # one kernel for the whole bucket
+            self.overlap = False
 
     # -- wiring -----------------------------------------------------------------------------
     def attach(self) -> "GradientSync":
@@ -136,6 +197,12 @@ class GradientSync:
     def finish(self) -> None:
         """Reduce what is left, wait for the collectives and store the results in ``param.grad``."""
         if not self.reported:
+            return
+        if self.peer is not None:
+            self.peer()                                  # in place, on the compute stream, complete when it returns on-stream
+            for name in self.reported:
+                self.params[name].grad = self.views[name]
+            self.reported.clear()
             return
         self._reduce(self.reduced_upto, self.bucket.numel(), side_stream=False)
         for work in self.pending:

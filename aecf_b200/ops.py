@@ -274,6 +274,27 @@ def entropy_bwd(weights2d: torch.Tensor, d_entropy: torch.Tensor) -> torch.Tenso
     return d_w
 
 
+def peer_flag_block(dev: torch.device) -> torch.Tensor:
+    """A zeroed flag block for ``peer_allreduce`` (one per rank, lives as long as the buckets are mapped)."""
+    return torch.zeros(_lib.load().aecf_peer_flag_bytes() // 4, dtype=torch.int32, device=dev)
+
+
+def peer_allreduce(buckets, flags, rank: int, *, average: bool = False, stream: Optional[int] = None,
+                   grid_limit: int = 0) -> None:
+    """In-place sum (mean) of ``buckets[rank]`` with every other entry of ``buckets`` -- this process's mappings of
+    all ranks' buckets -- over peer memory (``aecf_peer_allreduce``).  Every rank makes the same call with its own
+    ``rank``; the call returns at once and completes on the stream when the whole bucket is reduced."""
+    mine = buckets[rank]
+    dev = require_cuda(mine, flags[rank])
+    world = len(buckets)
+    d = _lib.PeerDesc(device=dev.index or 0, dtype=dtype_code(mine.dtype), world=world, rank=rank,
+                      count=mine.numel(), average=int(average), grid_limit=int(grid_limit))
+    data = (C.c_void_p * world)(*[b.data_ptr() for b in buckets])
+    flag_ptrs = (C.c_void_p * world)(*[f.data_ptr() for f in flags])
+    rc = _lib.load().aecf_peer_allreduce(C.byref(d), data, flag_ptrs, _stream(dev) if stream is None else stream)
+    _lib.check(rc, f"aecf_peer_allreduce world={world} rank={rank} count={mine.numel()}")
+
+
 def fusion_workspace(desc: _lib.PoolDesc, dev: torch.device) -> torch.Tensor:
     return _workspace(_lib.load().aecf_fusion_workspace_bytes(C.byref(desc)), dev)
 

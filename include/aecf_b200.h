@@ -293,6 +293,27 @@ AECF_API int aecf_fusion_bwd(const aecf_pool_desc* desc, const aecf_fusion_tenso
                              int32_t phase, void* workspace, size_t workspace_bytes, void* stream);
 AECF_API size_t aecf_fusion_workspace_bytes(const aecf_pool_desc* desc);
 
+/* ---- data-parallel all-reduce over NVLink peer memory ------------------------------------------------
+ * In-place sum (or mean) of one gradient bucket across the W <= 8 ranks of a node, one kernel per rank over peer
+ * mappings of every rank's bucket (csrc/peer_allreduce.cu: barrier, each rank reduces its slice from all buckets in
+ * rank order and stores it into all buckets, barrier).  Results are bit-identical on every rank.  The reference has no
+ * distributed code; this replaces the NCCL all-reduce a data-parallel training loop would issue after the backward.
+ *   peer_data[r]  : HOST array of W DEVICE pointers -- rank r's bucket as mapped in this process (CUDA IPC); all
+ *                   buckets hold `count` elements padded to a multiple of 16 bytes
+ *   peer_flags[r] : HOST array of W DEVICE pointers -- rank r's flag block, aecf_peer_flag_bytes() bytes, zeroed once
+ * The caller maps the buffers (aecf_b200.dp.PeerAllReduce does it with torch's CUDA IPC) and must have enabled peer
+ * access (aecf_peer_enable_access).  Every rank must make the same sequence of calls.  Graph-capturable: the call
+ * epoch lives in the flag block and is advanced by the kernel. */
+typedef struct aecf_peer_desc {
+    int32_t device, dtype, world, rank;
+    int64_t count;
+    int32_t average;          /* 1: divide the sum by world */
+    int32_t grid_limit;       /* 0 = default (32 CTAs) */
+} aecf_peer_desc;
+AECF_API size_t aecf_peer_flag_bytes(void);
+AECF_API int    aecf_peer_enable_access(int32_t device, int32_t peer_device);
+AECF_API int    aecf_peer_allreduce(const aecf_peer_desc* desc, void* const* peer_data, void* const* peer_flags, void* stream);
+
 /* ---- per-kernel timing (CUDA events recorded next to each launch, on the launching stream) ------------- */
 typedef enum aecf_site {
     AECF_SITE_OTHER = 0, AECF_SITE_Q_PROJ, AECF_SITE_KV_PROJ, AECF_SITE_POOL_FWD, AECF_SITE_OUT_PROJ,
