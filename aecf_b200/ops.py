@@ -14,22 +14,6 @@ from . import _lib
 
 _DTYPE = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
 
-# Optional per-call timing hook used by bench.py: ``profile_hook(name) -> context manager``.
-profile_hook = None
-
-
-class _NullCtx:
-    def __enter__(self):
-        return self
-
-    def __exit__(self, *exc):
-        return False
-
-
-def _prof(name: str):
-    return profile_hook(name) if profile_hook is not None else _NullCtx()
-
-
 def dtype_code(dtype: torch.dtype) -> int:
     try:
         return _DTYPE[dtype]
@@ -84,9 +68,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, m: int, n: int, k: int, a_layout: 
                       m=m, n=n, k=k, lda=lda, ldb=ldb, ldc=ldc)
     ws_bytes = lib.aecf_gemm_workspace_bytes(C.byref(d))
     ws = _workspace(ws_bytes, dev)
-    with _prof(name):
-        rc = lib.aecf_gemm(C.byref(d), a.data_ptr(), b.data_ptr(), _lib.ptr(bias), out.data_ptr(),
-                           ws.data_ptr(), ws.numel(), _stream(dev))
+    rc = lib.aecf_gemm(C.byref(d), a.data_ptr(), b.data_ptr(), _lib.ptr(bias), out.data_ptr(),
+                       ws.data_ptr(), ws.numel(), _stream(dev))
     _lib.check(rc, f"aecf_gemm[{name}] m={m} n={n} k={k}")
     return out
 
@@ -122,9 +105,8 @@ def colsum(x2d: torch.Tensor, out_dtype: Optional[torch.dtype] = None, name="col
     rows, cols = x2d.shape
     out = torch.empty(cols, dtype=out_dtype or x2d.dtype, device=dev)
     ws = _workspace(lib.aecf_colsum_workspace_bytes(rows, cols), dev)
-    with _prof(name):
-        rc = lib.aecf_colsum(dev.index or 0, dtype_code(x2d.dtype), dtype_code(out.dtype), x2d.data_ptr(), rows, cols,
-                             x2d.stride(0), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev))
+    rc = lib.aecf_colsum(dev.index or 0, dtype_code(x2d.dtype), dtype_code(out.dtype), x2d.data_ptr(), rows, cols,
+                         x2d.stride(0), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev))
     _lib.check(rc, "aecf_colsum")
     return out
 
@@ -185,10 +167,9 @@ def pool_fwd(desc: _lib.PoolDesc, q: torch.Tensor, kv: torch.Tensor, score_bias:
     mask_rate = torch.empty((B,), dtype=torch.float32, device=dev)
     masked = torch.empty((B, M), dtype=torch.float32, device=dev)
     bits = torch.empty((B,), dtype=torch.uint8, device=dev) if want_mask_bits else None
-    with _prof("pool_fwd"):
-        rc = lib.aecf_pool_fwd(C.byref(desc), q.data_ptr(), kv.data_ptr(), _lib.ptr(score_bias), ctx.data_ptr(),
-                               pooled.data_ptr(), entropy.data_ptr(), mask_rate.data_ptr(), masked.data_ptr(),
-                               _lib.ptr(bits), _stream(dev))
+    rc = lib.aecf_pool_fwd(C.byref(desc), q.data_ptr(), kv.data_ptr(), _lib.ptr(score_bias), ctx.data_ptr(),
+                           pooled.data_ptr(), entropy.data_ptr(), mask_rate.data_ptr(), masked.data_ptr(),
+                           _lib.ptr(bits), _stream(dev))
     _lib.check(rc, f"aecf_pool_fwd B={B} M={M} D={D} H={desc.num_heads}")
     return ctx, pooled, entropy, mask_rate, masked, bits
 
@@ -206,10 +187,9 @@ def pool_bwd(desc: _lib.PoolDesc, q: torch.Tensor, kv: torch.Tensor, score_bias:
         d_q = torch.empty((B, D), dtype=kv.dtype, device=dev)
     d_bias_kv = torch.empty((2 * D,), dtype=torch.float32, device=dev)
     ws = _workspace(lib.aecf_pool_bwd_workspace_bytes(C.byref(desc)), dev)
-    with _prof("pool_bwd"):
-        rc = lib.aecf_pool_bwd(C.byref(desc), q.data_ptr(), kv.data_ptr(), _lib.ptr(score_bias), d_ctx.data_ptr(),
-                               _lib.ptr(d_pooled), _lib.ptr(d_entropy), d_kv.data_ptr(), d_q.data_ptr(),
-                               d_bias_kv.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev))
+    rc = lib.aecf_pool_bwd(C.byref(desc), q.data_ptr(), kv.data_ptr(), _lib.ptr(score_bias), d_ctx.data_ptr(),
+                           _lib.ptr(d_pooled), _lib.ptr(d_entropy), d_kv.data_ptr(), d_q.data_ptr(),
+                           d_bias_kv.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev))
     _lib.check(rc, f"aecf_pool_bwd B={B} M={M} D={D} H={desc.num_heads}")
     return d_kv, d_q, d_bias_kv
 
@@ -217,9 +197,8 @@ def pool_bwd(desc: _lib.PoolDesc, q: torch.Tensor, kv: torch.Tensor, score_bias:
 def entropy_loss_fwd(entropy: torch.Tensor, target: float) -> torch.Tensor:
     dev = require_cuda(entropy)
     loss = torch.empty((), dtype=torch.float32, device=dev)
-    with _prof("entropy_loss_fwd"):
-        rc = _lib.load().aecf_entropy_loss_fwd(dev.index or 0, entropy.data_ptr(), entropy.numel(), float(target),
-                                               loss.data_ptr(), _stream(dev))
+    rc = _lib.load().aecf_entropy_loss_fwd(dev.index or 0, entropy.data_ptr(), entropy.numel(), float(target),
+                                           loss.data_ptr(), _stream(dev))
     _lib.check(rc, "aecf_entropy_loss_fwd")
     return loss
 
@@ -227,9 +206,8 @@ def entropy_loss_fwd(entropy: torch.Tensor, target: float) -> torch.Tensor:
 def entropy_loss_bwd(entropy: torch.Tensor, target: float, d_loss: torch.Tensor) -> torch.Tensor:
     dev = require_cuda(entropy, d_loss)
     d_e = torch.empty_like(entropy)
-    with _prof("entropy_loss_bwd"):
-        rc = _lib.load().aecf_entropy_loss_bwd(dev.index or 0, entropy.data_ptr(), entropy.numel(), float(target),
-                                               d_loss.data_ptr(), d_e.data_ptr(), _stream(dev))
+    rc = _lib.load().aecf_entropy_loss_bwd(dev.index or 0, entropy.data_ptr(), entropy.numel(), float(target),
+                                           d_loss.data_ptr(), d_e.data_ptr(), _stream(dev))
     _lib.check(rc, "aecf_entropy_loss_bwd")
     return d_e
 
@@ -239,9 +217,8 @@ def sdpa_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
     B, S, D = q.shape
     T = k.shape[1]
     out = torch.empty_like(q)
-    with _prof("sdpa_fwd"):
-        rc = _lib.load().aecf_sdpa_fwd(dev.index or 0, dtype_code(q.dtype), q.data_ptr(), k.data_ptr(), v.data_ptr(),
-                                       out.data_ptr(), B, S, T, D, _stream(dev))
+    rc = _lib.load().aecf_sdpa_fwd(dev.index or 0, dtype_code(q.dtype), q.data_ptr(), k.data_ptr(), v.data_ptr(),
+                                   out.data_ptr(), B, S, T, D, _stream(dev))
     _lib.check(rc, f"aecf_sdpa_fwd B={B} S={S} T={T} D={D}")
     return out
 
@@ -254,11 +231,10 @@ def curriculum_mask(weights2d: torch.Tensor, mode: int, *, base_mask_prob: float
     masked = torch.empty_like(weights2d) if want_masked else None
     entropy = torch.empty((rows,), dtype=torch.float32, device=dev)
     mask_rate = torch.empty((rows,), dtype=torch.float32, device=dev)
-    with _prof("curriculum_mask"):
-        rc = _lib.load().aecf_curriculum_mask(dev.index or 0, weights2d.data_ptr(), rows, length, mode,
-                                              float(base_mask_prob), int(min_active), seed & 0xFFFFFFFFFFFFFFFF,
-                                              offset & 0xFFFFFFFF, row0, _lib.ptr(masked), entropy.data_ptr(),
-                                              mask_rate.data_ptr(), _stream(dev))
+    rc = _lib.load().aecf_curriculum_mask(dev.index or 0, weights2d.data_ptr(), rows, length, mode,
+                                          float(base_mask_prob), int(min_active), seed & 0xFFFFFFFFFFFFFFFF,
+                                          offset & 0xFFFFFFFF, row0, _lib.ptr(masked), entropy.data_ptr(),
+                                          mask_rate.data_ptr(), _stream(dev))
     _lib.check(rc, f"aecf_curriculum_mask rows={rows} len={length}")
     return masked, entropy, mask_rate
 
@@ -267,9 +243,8 @@ def entropy_bwd(weights2d: torch.Tensor, d_entropy: torch.Tensor) -> torch.Tenso
     dev = require_cuda(weights2d, d_entropy)
     rows, length = weights2d.shape
     d_w = torch.empty_like(weights2d)
-    with _prof("entropy_bwd"):
-        rc = _lib.load().aecf_entropy_bwd(dev.index or 0, weights2d.data_ptr(), rows, length, d_entropy.data_ptr(),
-                                          d_w.data_ptr(), _stream(dev))
+    rc = _lib.load().aecf_entropy_bwd(dev.index or 0, weights2d.data_ptr(), rows, length, d_entropy.data_ptr(),
+                                      d_w.data_ptr(), _stream(dev))
     _lib.check(rc, "aecf_entropy_bwd")
     return d_w
 

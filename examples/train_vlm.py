@@ -5,7 +5,8 @@
     python examples/train_vlm.py --steps 30
     python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 examples/train_vlm.py --steps 30
 
-The fusion parameters go through aecf_b200.dp.GradientSync (bucketed, overlapped with the fused backward);
+The fusion parameters go through aecf_b200.dp.GradientSync (written in place into one bucket by the fused backward,
+one all-reduce per step);
 the encoders and the head are ordinary torch modules whose gradients are all-reduced in one flat call.
 Prints one JSON line with samples/s (synthetic features, random-init weights).
 """

@@ -250,7 +250,7 @@ typedef struct aecf_fusion_tensors {
     const float* score_bias;       /* nullable, see aecf_pool_fwd */
     /* forward results that the backward reads again (the caller keeps them alive) */
     void*  q_proj;                 /* q_is_shared ? [D] fp32 : [B, D] */
-    void*  kv;                     /* [B*M, 2D] */
+    void*  kv;                     /* [B*M, 2D]; folded key projection: [B*M, D] (the values only) */
     void*  ctx;                    /* [B, D] */
     /* forward outputs */
     void*    out;                  /* [B, D] */
@@ -271,7 +271,7 @@ typedef struct aecf_fusion_grads {
     const float* d_entropy;        /* [B] fp32, nullable (eval mode) */
     /* scratch the caller provides */
     void* d_ctx;                   /* [B, D] */
-    void* d_kv;                    /* [B*M, 2D] */
+    void* d_kv;                    /* [B*M, 2D]; folded key projection: [B*M, D + HSP] (= [dV | ds]) */
     void* d_q_rows;                /* [B, D]; only when !q_is_shared */
     /* results; a null pointer skips that gradient */
     void* d_key;                   /* [B*M, D] */
