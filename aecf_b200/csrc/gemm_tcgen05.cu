@@ -255,7 +255,12 @@ __device__ __forceinline__ WorkItem decode(const Params& p, int item, int cta_ra
     return w;
 }
 
-template <int BN, int CL>
+// EPI selects the epilogue of the bf16-output path: 1 = the measured one (load a 32-column group, convert, stage; drain
+// both staging boxes before refilling them); 2 = EXPERIMENTAL, opt-in with AECF_GEMM_EPI=2 and not yet run on hardware
+// (profiles/r1_gemm_experiments.md, "round-2 order of attack"): the next group's tcgen05.ld is in flight while the
+// current group is converted, and the two staging boxes alternate with `wait_group.read 1`, so neither the TMEM
+// read latency nor the previous store's shared-memory read is exposed.
+template <int BN, int CL, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_c, const Params p) {
@@ -374,6 +379,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int quad = warp & 3;                   // TMEM lane quadrant this warp may read
         const int ew = warp - 2;                     // 0..3: staging slot
         uint8_t* wbuf = epi_base + ew * (2 * 32 * 128);
+        [[maybe_unused]] int box_it = 0;             // EPI == 2: boxes stored so far by this warp
         int tile_it = 0;
         for (int item = first_item; item < items; item += item_stride, ++tile_it) {
             const WorkItem w = decode<CL>(p, item, cta_rank);
@@ -401,6 +407,67 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
             const uint32_t t_row = tmem_base + as * C::ACC_STRIDE + (static_cast<uint32_t>(quad * 32) << 16);
             const int out_row0 = (direct ? 0 : w.split * p.partial_rows) + m0 + quad * 32;
+            if constexpr (EPI == 2) {
+                if (!p.c_is_f32) {
+                    // ---- pipelined bf16 epilogue: group g+1 is being read out of TMEM while group g is converted; box
+                    // (g / 2) % 2 is refilled as soon as the store issued two boxes ago has read it (one may stay pending)
+                    constexpr int GROUPS = BN / 32;
+                    uint32_t r[2][32];
+                    tmem_ld_32x32(t_row, r[0]);
+#pragma unroll
+                    for (int g = 0; g < GROUPS; ++g) {
+                        tmem_ld_wait();                                        // r[g & 1] has landed
+                        if (g + 1 < GROUPS) tmem_ld_32x32(t_row + (g + 1) * 32, r[(g + 1) & 1]);
+                        else {                                                 // every TMEM read of this tile is done
+                            tc_fence_before();
+                            mbar_arrive(&tmem_empty[as]);
+                        }
+                        // boxes alternate ACROSS tiles too (a 192-wide tile fills three), so the box being refilled is
+                        // always the one stored two commits ago
+                        uint8_t* box_base = wbuf + ((box_it + (g >> 1)) & 1) * (32 * 128);
+                        uint8_t* box = box_base + lane * 128;
+                        if ((g & 1) == 0) {
+                            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                            __syncwarp();
+                        }
+                        float v[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            v[i] = __uint_as_float(r[g & 1][i]);
+                            if (direct && p.has_bias) v[i] += wbias[g * 32 + i];
+                        }
+                        if (p.aux != nullptr && n0 + g * 32 == p.c_cols) {
+                            const int row = m0 + quad * 32 + lane;
+                            if (tile_valid && row < p.m) {
+                                float4* dst = reinterpret_cast<float4*>(p.aux + static_cast<long long>(row) * p.aux_ld);
+#pragma unroll
+                                for (int c = 0; c < 8; ++c)
+                                    if (4 * c < p.aux_cols) dst[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                            }
+                        }
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const int chunk = (g & 1) * 4 + c;
+                            *reinterpret_cast<uint4*>(box + ((chunk ^ (lane & 7)) << 4)) =
+                                make_uint4(Vec<__nv_bfloat16>::pack2(v[8 * c], v[8 * c + 1]),
+                                           Vec<__nv_bfloat16>::pack2(v[8 * c + 2], v[8 * c + 3]),
+                                           Vec<__nv_bfloat16>::pack2(v[8 * c + 4], v[8 * c + 5]),
+                                           Vec<__nv_bfloat16>::pack2(v[8 * c + 6], v[8 * c + 7]));
+                        }
+                        if ((g & 1) == 1 || g == GROUPS - 1) {                 // a 64-column box is complete: store it
+                            fence_proxy_async();
+                            __syncwarp();
+                            const int col0 = n0 + (g >> 1) * 64;
+                            if (lane == 0) {
+                                if (tile_valid && col0 < p.c_cols) tma_store_2d(&map_c, box_base, col0, out_row0);
+                                tma_store_commit();                            // one group per box, stored or not
+                            }
+                        }
+                    }
+                    box_it += (GROUPS + 1) / 2;
+                    continue;
+                }
+            }
             // the staging area holds 128 bf16 columns or 64 fp32 columns per round
             const int cols_per_round = p.c_is_f32 ? 64 : 128;
             const int rounds = (BN + cols_per_round - 1) / cols_per_round;
@@ -861,9 +928,10 @@ int gemm_tcgen05(const aecf_gemm_desc* d, const void* A, const void* B, const vo
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    static const bool pipelined_epilogue = [] { const char* e = getenv("AECF_GEMM_EPI"); return e && e[0] == '2'; }();
 #define AECF_TC_LAUNCH(BN_, CL_)                                                                                  \
     do {                                                                                                          \
-        auto kernel = gemm_tcgen05_kernel<BN_, CL_>;                                                              \
+        auto kernel = pipelined_epilogue ? gemm_tcgen05_kernel<BN_, CL_, 2> : gemm_tcgen05_kernel<BN_, CL_, 1>;   \
         cfg.dynamicSmemBytes = Cfg<BN_>::SMEM_BYTES;                                                              \
         AECF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN_>::SMEM_BYTES)); \
         AECF_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, map_a, map_b, map_c, p));                                   \

@@ -1,0 +1,36 @@
+"""Opt-in variants that have NOT yet been run on hardware (round-2 candidates, profiles/r1_gemm_experiments.md).
+Skipped unless AECF_TEST_EXPERIMENTAL=1: the driver's `pytest -m gpu` must only see measured code paths.
+Each variant is selected by an environment variable the library reads once per process, hence the subprocesses.
+
+    AECF_TEST_EXPERIMENTAL=1 python -m pytest tests/test_gpu_experimental.py -m gpu -q
+"""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("AECF_TEST_EXPERIMENTAL") != "1", reason="opt-in: AECF_TEST_EXPERIMENTAL=1")]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _pytest_with(env, selection):
+    e = dict(os.environ)
+    e.update(env)
+    e.pop("AECF_TEST_EXPERIMENTAL", None)
+    res = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", "--timeout", "300"]
+                         + selection, capture_output=True, text=True, timeout=1500, env=e, cwd=ROOT)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-1000:]
+
+
+def test_pipelined_gemm_epilogue_passes_the_gemm_and_parity_suites():
+    """AECF_GEMM_EPI=2: next tcgen05.ld in flight during the conversion, staging boxes alternating with wait_group.read 1."""
+    _pytest_with({"AECF_GEMM_EPI": "2"},
+                 ["tests/test_gpu_gemm_tcgen05.py", "tests/test_gpu_parity.py", "-k",
+                  "gemm or side_output or bf16 or folded or headline or sharding"])
+
+
+def test_streaming_pool_backward_passes_the_parity_suite():
+    """AECF_POOL_BWD_STREAM=1: cp.async double-buffered rows in the folded backward."""
+    _pytest_with({"AECF_POOL_BWD_STREAM": "1"}, ["tests/test_gpu_parity.py", "tests/test_gpu_graphs.py"])
