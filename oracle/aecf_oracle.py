@@ -146,7 +146,9 @@ def pool_forward(query: Tensor, key: Tensor, value: Optional[Tensor],
     """MultimodalAttentionPool.forward, batch_first -- reference aecf/AECFLayer.py:409-547
     over torch/nn/functional.py:5847-5865 and :6630-6659.
 
-    query [B,S,D] (an expand of [1,1,D] is fine), key/value [B,M,D].
+    query [B,S,D] (an expand of [1,1,D] is fine; S > 1 fusion queries per sample are covered, each (b, s)
+    pair is a row of its own for the softmax, the dropout draws u_drop [B,H,S,M] and the mask draws
+    u_mask [B,S,M]), key/value [B,M,D].
     ``score_bias`` is the additive float mask torch builds from key_padding_mask
     and attn_mask (functional.py:6608-6620), broadcastable to [B,H,S,M].
     ``masking`` = dict(base_mask_prob, entropy_target, min_active) or None.
@@ -194,7 +196,7 @@ def pool_forward(query: Tensor, key: Tensor, value: Optional[Tensor],
             keep = torch.zeros_like(w)
             wd = w * 0.0
         else:
-            keep = (u_drop.view(B, H, 1, M).to(w.dtype) >= dropout_p).to(w.dtype).expand_as(w)
+            keep = (u_drop.view(B, H, S, M).to(w.dtype) >= dropout_p).to(w.dtype)
             wd = w * keep / (1.0 - dropout_p)
     else:
         keep = torch.ones_like(w)
@@ -208,7 +210,7 @@ def pool_forward(query: Tensor, key: Tensor, value: Optional[Tensor],
     res.saved = dict(qp=qp, k=k, v=v, w=w, wd=wd, keep=keep, ctx=ctx)
     res.info["attention_weights"] = pooled                       # AECFLayer.py:538
     if masking is not None:
-        cm = curriculum_mask(pooled, None if u_mask is None else u_mask.view(B, 1, M).expand(B, S, M),
+        cm = curriculum_mask(pooled, None if u_mask is None else u_mask.view(B, S, M),
                              training=training, **masking)       # :534
         for name in ("entropy", "mask_rate", "target_entropy"):
             if name in cm:
@@ -231,7 +233,7 @@ def pool_backward(query: Tensor, key: Tensor, value: Optional[Tensor],
     The reference has no backward source: it is autograd over
     torch/nn/functional.py:5847-5865, 6630-6659.  tests/test_oracle_golden.py
     checks this against autograd of the reference itself.
-    Single-query form (S == 1), which is the hot path.
+    Covers S >= 1 fusion queries per sample (S == 1 is the hot path): dK and dV sum over the queries of a sample.
     ``fold_key``: the association the CUDA path's folded key projection uses (one shared query): dK is never
     formed; with ds the score gradient, Qk[h] = scale * Wk_h^T q_h and R[h] = sum_{b,m} ds[b,h,m] x[b,m],
         dX   = dV Wv + ds Qk            dWk[h*hd + j] = scale * q[h*hd + j] * R[h]
@@ -242,57 +244,58 @@ def pool_backward(query: Tensor, key: Tensor, value: Optional[Tensor],
     if value is None:
         value = key
     B, S, D = query.shape
-    assert S == 1, "closed-form backward covers the single fusion query"
     M = key.shape[1]
     H = num_heads
     hd = D // H
     scale = math.sqrt(1.0 / float(hd))
     Wq, Wk, Wv = in_proj_weight[:D], in_proj_weight[D:2 * D], in_proj_weight[2 * D:]
-    w, wd, keep = saved["w"][:, :, 0], saved["wd"][:, :, 0], saved["keep"][:, :, 0]   # [B,H,M]
-    qp = saved["qp"].reshape(B, H, hd)
+    w, wd, keep = saved["w"], saved["wd"], saved["keep"]              # [B,H,S,M]
+    qp = saved["qp"].reshape(B, S, H, hd)
     kh = saved["k"].view(B, M, H, hd)
     vh = saved["v"].view(B, M, H, hd)
-    ctx = saved["ctx"].reshape(B, D)
-    g = grad_out.reshape(B, D)
+    ctx = saved["ctx"].reshape(B * S, D)
+    g = grad_out.reshape(B * S, D)
 
     d_wo = g.t() @ ctx
     d_bo = g.sum(0)
-    d_ctx = _round(g @ out_proj_weight, storage).view(B, H, hd)
-    d_wd = torch.einsum("bhe,bmhe->bhm", d_ctx, vh)
-    d_pooled = None if grad_pooled is None else grad_pooled.reshape(B, M)
+    d_ctx = _round(g @ out_proj_weight, storage).view(B, S, H, hd)
+    d_wd = torch.einsum("bshe,bmhe->bhsm", d_ctx, vh)
+    d_pooled = None if grad_pooled is None else grad_pooled.reshape(B, S, M)
     if grad_entropy is not None:
         # eval mode only: entropy = clamp(-sum xlogy(p, p), 0, log M) stays attached
         # (reference aecf/AECFLayer.py:151-156); d/dp = -(log p + 1) inside the clamp.
-        pooled = wd.mean(dim=1)
+        pooled = wd.mean(dim=1)                                       # [B,S,M]
         raw = -torch.xlogy(pooled, pooled).sum(-1, keepdim=True)
         inside = (raw >= 0.0) & (raw <= math.log(M))
         d_h = torch.where(inside, -(pooled.log() + 1.0), torch.zeros((), dtype=pooled.dtype))
-        d_h = d_h * grad_entropy.reshape(B, 1)
+        d_h = d_h * grad_entropy.reshape(B, S, 1)
         d_pooled = d_h if d_pooled is None else d_pooled + d_h
     if d_pooled is not None:
-        d_wd = d_wd + d_pooled.reshape(B, 1, M) / H
-    d_v = torch.einsum("bhm,bhe->bmhe", wd, d_ctx)
+        d_wd = d_wd + d_pooled.reshape(B, 1, S, M) / H
+    d_v = torch.einsum("bhsm,bshe->bmhe", wd, d_ctx)
     if training and dropout_p > 0.0:
         d_w = d_wd * keep * (0.0 if dropout_p >= 1.0 else 1.0 / (1.0 - dropout_p))
     else:
         d_w = d_wd
     d_s = w * (d_w - (w * d_w).sum(-1, keepdim=True))
     if fold_key:
-        return _folded_input_grads(query, key, in_proj_weight, saved, d_s, d_v, d_wo, d_bo, scale, H, has_bias, storage)
-    d_qh = scale * torch.einsum("bhm,bmhe->bhe", d_s, kh)
-    d_k = scale * torch.einsum("bhm,bhe->bmhe", d_s, qp)
+        assert S == 1, "the folded association needs one query per sample"
+        return _folded_input_grads(query, key, in_proj_weight, saved, d_s[:, :, 0], d_v, d_wo, d_bo, scale, H,
+                                   has_bias, storage)
+    d_qh = scale * torch.einsum("bhsm,bmhe->bshe", d_s, kh)
+    d_k = scale * torch.einsum("bhsm,bshe->bmhe", d_s, qp)
     d_k = _round(d_k.reshape(B, M, D), storage)
     d_v = _round(d_v.reshape(B, M, D), storage)
-    d_qp = d_qh.reshape(B, D)
+    d_qp = d_qh.reshape(B * S, D)
 
     grads = {
         "out_proj.weight": d_wo, "out_proj.bias": d_bo,
         "key": d_k @ Wk, "value": d_v @ Wv,
-        "query": (d_qp @ Wq).view(B, 1, D),
+        "query": (d_qp @ Wq).view(B, S, D),
     }
     if value is key:
         grads["key"] = grads["key"] + grads.pop("value")
-    x_q = query.reshape(B, D)
+    x_q = query.reshape(B * S, D)
     d_wq = d_qp.t() @ x_q
     d_wk = d_k.reshape(B * M, D).t() @ key.reshape(B * M, D)
     d_wv = d_v.reshape(B * M, D).t() @ value.reshape(B * M, D)

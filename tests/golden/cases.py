@@ -41,6 +41,7 @@ class Case:
     row0: int = 0                 # global index of the first row
     data_seed: int = 1
     full_grads: bool = True       # store complete weight gradients in the fixture
+    S: int = 1                    # fusion queries per sample; S > 1: every (b, s) has its own query vector
 
     def meta(self) -> dict:
         return asdict(self)
@@ -62,7 +63,14 @@ CASES = [
     Case("d32_h1_m1_single_token", B=8, M=1, D=32, H=1, data_seed=21),
     Case("d256_h16_m6", B=20, M=6, D=256, H=16, dropout=0.05, min_active=3, base_mask_prob=0.5, data_seed=22),
 ]
-CASES_BY_NAME = {c.name: c for c in CASES}
+# several fusion queries per sample (target length S > 1): per-(b, s) queries
+MULTI_QUERY_CASES = [
+    Case("s2_d64_h8_m3_dropout", B=24, S=2, M=3, D=64, H=8, dropout=0.1, pooled_grad=True, offset=5, data_seed=23),
+    Case("s3_d128_h4_m5_minactive2", B=16, S=3, M=5, D=128, H=4, base_mask_prob=0.8, min_active=2, row0=70, data_seed=24),
+    Case("s2_d64_h4_m4_kpm_eval", B=12, S=2, M=4, D=64, H=4, kpm=True, training=False, pooled_grad=True, data_seed=25),
+    Case("s4_d256_h2_m2", B=10, S=4, M=2, D=256, H=2, base_mask_prob=0.5, peak=1.0, data_seed=26, full_grads=False),
+]
+CASES_BY_NAME = {c.name: c for c in CASES + MULTI_QUERY_CASES}
 
 
 def _t(a: np.ndarray, dtype: torch.dtype) -> torch.Tensor:
@@ -72,7 +80,7 @@ def _t(a: np.ndarray, dtype: torch.dtype) -> torch.Tensor:
 def build_inputs(case: Case, dtype: Optional[torch.dtype] = None) -> Dict[str, torch.Tensor]:
     """Parameters, fusion query, modality tokens, upstream gradients and the injected uniforms."""
     dt = dtype if dtype is not None else getattr(torch, case.dtype)
-    D, M, B, H = case.D, case.M, case.B, case.H
+    D, M, B, H, S = case.D, case.M, case.B, case.H, case.S
     s = case.data_seed * 1000
     Wi = philox.normal(s + 1, (3 * D, D)) * math.sqrt(2.0 / (4 * D))     # ~xavier scale of MHA init
     bi = philox.normal(s + 2, (3 * D,)) * 0.05
@@ -94,11 +102,17 @@ def build_inputs(case: Case, dtype: Optional[torch.dtype] = None) -> Dict[str, t
         "in_proj_weight": _t(Wi, dt), "in_proj_bias": _t(bi, dt),
         "out_proj.weight": _t(Wo, dt), "out_proj.bias": _t(bo, dt),
         "query0": _t(q0, dt), "x": _t(x, dt),
-        "grad_out": _t(philox.normal(s + 8, (B, 1, D)), dt),
-        "grad_pooled": _t(philox.normal(s + 9, (B, 1, M)), dt),
-        "u_mask": torch.from_numpy(philox.mask_uniforms(PHILOX_SEED, case.offset, case.row0, B, M)),
-        "u_drop": torch.from_numpy(philox.dropout_uniforms(PHILOX_SEED, case.offset, case.row0, B, H, M)),
+        "grad_out": _t(philox.normal(s + 8, (B, S, D)), dt),
+        "grad_pooled": _t(philox.normal(s + 9, (B, S, M)), dt),
+        # one Philox row per (b, s) pair: global row (row0 + b) * S + s  (include/aecf_b200.h)
+        "u_mask": torch.from_numpy(philox.mask_uniforms(PHILOX_SEED, case.offset, case.row0 * S, B * S, M)
+                                   .reshape((B, S, M) if S > 1 else (B, M))),
+        "u_drop": torch.from_numpy(np.ascontiguousarray(
+            philox.dropout_uniforms(PHILOX_SEED, case.offset, case.row0 * S, B * S, H, M)
+            .reshape(B, S, H, M).transpose(0, 2, 1, 3)).reshape((B, H, S, M) if S > 1 else (B, H, M))),
     }
+    if S > 1:   # per-(b, s) queries around the fusion query (which alone fixes the peaked direction above)
+        out["query"] = _t(q0 + philox.normal(s + 12, (B, S, D)) * math.sqrt(2.0 / D), dt)
     if case.separate_value:
         out["value"] = _t(philox.normal(s + 10, (B, M, D)), dt)
     if case.kpm:

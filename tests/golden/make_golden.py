@@ -26,7 +26,7 @@ sys.path.insert(0, REFERENCE)
 
 import aecf as ref  # noqa: E402  (the reference package)
 
-from tests.golden.cases import CASES, Case, build_inputs, masking_kwargs  # noqa: E402
+from tests.golden.cases import CASES, MULTI_QUERY_CASES, Case, build_inputs, masking_kwargs  # noqa: E402
 
 
 class inject_uniforms:
@@ -72,13 +72,14 @@ def run_reference(case: Case):
         pool.attention.out_proj.weight.copy_(inp["out_proj.weight"])
         pool.attention.out_proj.bias.copy_(inp["out_proj.bias"])
     pool.train(case.training)
-    query0 = torch.nn.Parameter(inp["query0"].clone())
+    multi = case.S > 1
+    query0 = torch.nn.Parameter((inp["query"] if multi else inp["query0"]).clone())
     x = inp["x"].clone().requires_grad_(True)
     value = inp["value"].clone().requires_grad_(True) if case.separate_value else None
     kpm = inp.get("key_padding_mask")
 
     with inject_uniforms(inp["u_mask"], inp["u_drop"]):
-        out, info = pool(query0.expand(case.B, -1, -1), x, value, key_padding_mask=kpm,
+        out, info = pool(query0 if multi else query0.expand(case.B, -1, -1), x, value, key_padding_mask=kpm,
                          return_info=True)
     ent_loss = cm.entropy_loss(info["entropy"])
     loss = (out * inp["grad_out"]).sum()
@@ -93,7 +94,7 @@ def run_reference(case: Case):
         "entropy": info["entropy"], "mask_rate": info["mask_rate"],
         "masked_attention_weights": info["masked_attention_weights"],
         "entropy_loss": ent_loss, "last_seq_len": torch.tensor(cm._last_seq_len),
-        "grad_x": x.grad, "grad_query0": query0.grad,
+        "grad_x": x.grad, ("grad_query" if multi else "grad_query0"): query0.grad,
         "grad_in_proj_bias": pool.attention.in_proj_bias.grad,
         "grad_out_proj_bias": pool.attention.out_proj.bias.grad,
     }
@@ -118,7 +119,7 @@ def run_reference(case: Case):
 
 def main():
     torch.set_num_threads(1)
-    for case in CASES:
+    for case in CASES + MULTI_QUERY_CASES:
         arrays = run_reference(case)
         path = os.path.join(HERE, case.name + ".npz")
         np.savez_compressed(path, **arrays)

@@ -33,8 +33,8 @@ def run_oracle(case: Case, inp: Optional[dict] = None, dtype: Optional[torch.dty
                storage: Optional[torch.dtype] = None, fold_key: bool = False):
     """Oracle forward + closed-form backward on a golden case; returns (forward result, grads)."""
     inp = inp if inp is not None else build_inputs(case, dtype)
-    B, D = case.B, case.D
-    q = inp["query0"].expand(B, 1, D)
+    B, D, S = case.B, case.D, case.S
+    q = inp["query"] if S > 1 else inp["query0"].expand(B, 1, D)       # S > 1: a query vector per (b, s)
     value = inp.get("value")
     fwd = oracle.pool_forward(
         q, inp["x"], value, inp["in_proj_weight"], inp["in_proj_bias"],
@@ -45,9 +45,10 @@ def run_oracle(case: Case, inp: Optional[dict] = None, dtype: Optional[torch.dty
     grads = oracle.pool_backward(
         q, inp["x"], value, inp["in_proj_weight"], inp["out_proj.weight"], case.H, fwd.saved,
         inp["grad_out"], grad_pooled=inp["grad_pooled"] if case.pooled_grad else None,
-        grad_entropy=None if case.training else torch.full((B, 1), 0.5, dtype=inp["x"].dtype),
+        grad_entropy=None if case.training else torch.full((B, S), 0.5, dtype=inp["x"].dtype),
         dropout_p=case.dropout, training=case.training, storage=storage, fold_key=fold_key)
-    grads["query0"] = grads.pop("query").sum(0, keepdim=True)
+    if S == 1:
+        grads["query0"] = grads.pop("query").sum(0, keepdim=True)
     return fwd, grads
 
 

@@ -8,7 +8,7 @@ import torch
 
 from oracle import aecf_oracle as oracle
 from oracle import philox
-from tests.golden.cases import CASES, build_inputs
+from tests.golden.cases import CASES, MULTI_QUERY_CASES, build_inputs
 from tests.helpers import assert_close, load_golden, run_oracle
 
 
@@ -16,7 +16,7 @@ def _tol(case):
     return 1e-12 if case.dtype == "float64" else 2e-6
 
 
-@pytest.mark.parametrize("case", CASES, ids=lambda c: c.name)
+@pytest.mark.parametrize("case", CASES + MULTI_QUERY_CASES, ids=lambda c: c.name)
 def test_forward_matches_reference(case):
     g = load_golden(case)
     fwd, _ = run_oracle(case)
@@ -72,7 +72,7 @@ def test_folded_key_projection_matches_reference(case):
         assert_close("grad_in_proj_weight_rowsum", grads["in_proj_weight"].sum(1), g["grad_in_proj_weight_rowsum"], gtol)
 
 
-@pytest.mark.parametrize("case", CASES, ids=lambda c: c.name)
+@pytest.mark.parametrize("case", CASES + MULTI_QUERY_CASES, ids=lambda c: c.name)
 def test_backward_matches_reference_autograd(case):
     g = load_golden(case)
     _, grads = run_oracle(case)
@@ -80,7 +80,10 @@ def test_backward_matches_reference_autograd(case):
     assert_close("grad_x", grads["key"], g["grad_x"], tol)
     if case.separate_value:
         assert_close("grad_value", grads["value"], g["grad_value"], tol)
-    assert_close("grad_query0", grads["query0"], g["grad_query0"], tol)
+    if case.S > 1:
+        assert_close("grad_query", grads["query"], g["grad_query"], tol)
+    else:
+        assert_close("grad_query0", grads["query0"], g["grad_query0"], tol)
     assert_close("grad_out_proj_bias", grads["out_proj.bias"], g["grad_out_proj_bias"], tol)
     # the K-bias gradient is analytically zero (softmax shift invariance): compare on the V/Q scale
     scale = float(np.abs(g["grad_in_proj_bias"]).max())
