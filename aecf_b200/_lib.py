@@ -12,7 +12,7 @@ from typing import Optional
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libaecf_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # enums of include/aecf_b200.h
 F32, BF16 = 0, 1
@@ -43,8 +43,9 @@ class PoolDesc(C.Structure):
         ("seed", C.c_uint64), ("offset", C.c_uint64), ("row0", C.c_uint64),
         ("bias_stride_b", C.c_int64), ("bias_stride_h", C.c_int64),
         ("kv_stride_b", C.c_int64), ("kv_stride_m", C.c_int64),
-        ("fold_key", C.c_int32), ("reserved", C.c_int32),
+        ("fold_key", C.c_int32), ("tgt_len", C.c_int32),
         ("rng_state", C.c_void_p),
+        ("q_stride_b", C.c_int64), ("q_stride_s", C.c_int64), ("bias_stride_s", C.c_int64),
     ]
 
 

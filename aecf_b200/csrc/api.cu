@@ -71,8 +71,9 @@ pool_bwd_finalize_kernel(const float* __restrict__ partials, int blocks, int D, 
 
 struct PoolPlan {
     PoolParams p;
+    MultiQuery mq;          // several queries per sample (desc.tgt_len > 1), pool_multi.cuh
     int M, J;
-    bool drop, bf16, fold;
+    bool drop, bf16, fold, multi;
 };
 
 // Validate a descriptor and derive the lane/head geometry (pool_core.cuh).  `fold`: the folded-key-projection
@@ -136,6 +137,19 @@ static int make_plan(const aecf_pool_desc* d, PoolPlan* plan, bool fold = false)
         p.kv_sb = d->kv_stride_b; p.kv_sm = d->kv_stride_m;
         p.dkv_sb = p.kv_sb; p.dkv_sm = p.kv_sm;
     }
+    const int S = d->tgt_len > 1 ? d->tgt_len : 1;
+    plan->multi = S > 1;
+    std::memset(&plan->mq, 0, sizeof(plan->mq));
+    if (plan->multi) {
+        if (fold || d->q_is_shared) return AECF_ERR_UNSUPPORTED;    // per-row queries, unfolded key projection
+        long long rb = d->q_stride_b, rs = d->q_stride_s;
+        if (rb == 0 && rs == 0) { rb = S; rs = 1; }                 // batch-first [B, S, D]
+        if (rb < 1 || rs < 1 || d->bias_stride_s < 0) return AECF_ERR_INVALID;
+        if (d->batch > (1LL << 40) / S) return AECF_ERR_INVALID;
+        plan->mq.S = S; plan->mq.q_rb = rb; plan->mq.q_rs = rs;
+        plan->mq.bias_sb = d->bias_stride_b; plan->mq.bias_sh = d->bias_stride_h; plan->mq.bias_ss = d->bias_stride_s;
+        p.rng.row0 = d->row0 * static_cast<unsigned long long>(S);  // Philox row of (b, s): (row0 + b) * S + s
+    }
     plan->fold = fold;
     plan->M = d->num_tokens; plan->J = J;
     plan->drop = d->training && d->dropout_p > 0.f;
@@ -169,6 +183,8 @@ const char* aecf_build_info(void) {
     return "aecf_b200 abi " AECF_STR(AECF_ABI_VERSION) ", sm_100a, nvcc " AECF_STR(__CUDACC_VER_MAJOR__) "." AECF_STR(__CUDACC_VER_MINOR__);
 }
 
+}  // extern "C"
+
 static int pool_fwd_impl(const aecf_pool_desc* desc, bool fold, const void* q, const float* scores, const void* kv,
                          const float* score_bias, void* ctx, float* pooled, float* entropy, float* mask_rate,
                          float* masked, uint8_t* mask_bits, void* stream) {
@@ -183,9 +199,19 @@ static int pool_fwd_impl(const aecf_pool_desc* desc, bool fold, const void* q, c
     p.q = q; p.kv = kv; p.bias = score_bias; p.scores = scores;
     p.ctx = ctx; p.pooled = pooled; p.entropy = entropy; p.mask_rate = mask_rate; p.masked = masked;
     p.mask_bits = mask_bits;
-    const int grid = static_cast<int>((p.B + p.SPC - 1) / p.SPC);
     const int sms = sm_count(desc->device);
     TimedLaunch timed(static_cast<cudaStream_t>(stream));
+    if (plan.multi) {                                   // one warp slice per (b, s) row; the bias travels in mq
+        plan.mq.bias = score_bias;
+        p.bias = nullptr;
+        const int rows_grid = static_cast<int>((p.B * plan.mq.S + p.SPC - 1) / p.SPC);
+        if (plan.bf16)
+            return plan.drop ? launch_pool_fwd_multi<__nv_bfloat16, true>(plan.M, plan.J, p, plan.mq, rows_grid, stream)
+                             : launch_pool_fwd_multi<__nv_bfloat16, false>(plan.M, plan.J, p, plan.mq, rows_grid, stream);
+        return plan.drop ? launch_pool_fwd_multi<float, true>(plan.M, plan.J, p, plan.mq, rows_grid, stream)
+                         : launch_pool_fwd_multi<float, false>(plan.M, plan.J, p, plan.mq, rows_grid, stream);
+    }
+    const int grid = static_cast<int>((p.B + p.SPC - 1) / p.SPC);
     if (plan.bf16)
         return plan.drop ? launch_pool_fwd<__nv_bfloat16, true>(plan.M, plan.J, p, grid, sms, fold, stream)
                          : launch_pool_fwd<__nv_bfloat16, false>(plan.M, plan.J, p, grid, sms, fold, stream);
@@ -212,12 +238,12 @@ int aecf_pool_fwd_folded(const aecf_pool_desc* desc, const float* scores, const 
     return pool_fwd_impl(desc, true, nullptr, scores, v, score_bias, ctx, pooled, entropy, mask_rate, masked, mask_bits, stream);
 }
 
-}  // extern "C"
-
 size_t aecf_pool_bwd_workspace_bytes(const aecf_pool_desc* desc) {
     if (desc == nullptr || desc->embed_dim <= 0) return 0;
     return static_cast<size_t>(POOL_BWD_MAX_BLOCKS) * 3 * desc->embed_dim * sizeof(float);
 }
+
+}  // extern "C"
 
 static int pool_bwd_impl(const aecf_pool_desc* desc, bool fold, const void* q, const float* scores, const void* kv,
                          const float* score_bias, const void* d_ctx, const float* d_pooled, const float* d_entropy,
@@ -238,7 +264,8 @@ static int pool_bwd_impl(const aecf_pool_desc* desc, bool fold, const void* q, c
     p.partials = static_cast<float*>(workspace);
 
     int per_sm;
-    if (plan.bf16) per_sm = plan.drop ? pool_bwd_blocks_per_sm<__nv_bfloat16, true>(plan.M, plan.J, fold)
+    if (plan.multi) per_sm = 1;                         // pool_bwd_multi_kernel: __launch_bounds__(256, 1)
+    else if (plan.bf16) per_sm = plan.drop ? pool_bwd_blocks_per_sm<__nv_bfloat16, true>(plan.M, plan.J, fold)
                                       : pool_bwd_blocks_per_sm<__nv_bfloat16, false>(plan.M, plan.J, fold);
     else per_sm = plan.drop ? pool_bwd_blocks_per_sm<float, true>(plan.M, plan.J, fold)
                             : pool_bwd_blocks_per_sm<float, false>(plan.M, plan.J, fold);
@@ -251,7 +278,16 @@ static int pool_bwd_impl(const aecf_pool_desc* desc, bool fold, const void* q, c
 
     {
         TimedLaunch timed(static_cast<cudaStream_t>(stream));
-        if (plan.bf16)
+        if (plan.multi) {
+            plan.mq.bias = score_bias;
+            p.bias = nullptr;
+            if (plan.bf16)
+                rc = plan.drop ? launch_pool_bwd_multi<__nv_bfloat16, true>(plan.M, plan.J, p, plan.mq, grid, stream)
+                               : launch_pool_bwd_multi<__nv_bfloat16, false>(plan.M, plan.J, p, plan.mq, grid, stream);
+            else
+                rc = plan.drop ? launch_pool_bwd_multi<float, true>(plan.M, plan.J, p, plan.mq, grid, stream)
+                               : launch_pool_bwd_multi<float, false>(plan.M, plan.J, p, plan.mq, grid, stream);
+        } else if (plan.bf16)
             rc = plan.drop ? launch_pool_bwd<__nv_bfloat16, true>(plan.M, plan.J, p, grid, fold, stream)
                            : launch_pool_bwd<__nv_bfloat16, false>(plan.M, plan.J, p, grid, fold, stream);
         else
@@ -286,5 +322,3 @@ int aecf_pool_bwd_folded(const aecf_pool_desc* desc, const void* q_proj, const f
 }
 
 }  // extern "C"
-
-}  // extern "C" (opened above aecf_abi_version)

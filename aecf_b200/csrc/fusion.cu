@@ -17,7 +17,7 @@ __global__ void pack_in_bias_kernel(const float* __restrict__ d_q, const float* 
 }
 
 struct Geometry {
-    long long B, rows;
+    long long B, rows, QR;     // samples, key/value rows (B * M), query rows (B * S)
     int M, D, H, es, dt;
     bool shared, fold;
     int HS, HSP;       // folded key projection: score columns (fp32, H rounded up to 4) / score-gradient columns (dt, 16-byte multiple)
@@ -27,10 +27,12 @@ static int geometry(const aecf_pool_desc* d, Geometry* g) {
     if (!d || d->batch < 0 || d->embed_dim <= 0 || d->num_tokens <= 0) return AECF_ERR_INVALID;
     if (d->dtype != AECF_F32 && d->dtype != AECF_BF16) return AECF_ERR_INVALID;
     g->B = d->batch; g->M = d->num_tokens; g->D = d->embed_dim; g->rows = g->B * g->M;
+    g->QR = g->B * (d->tgt_len > 1 ? d->tgt_len : 1);
     g->dt = d->dtype; g->es = d->dtype == AECF_BF16 ? 2 : 4; g->shared = d->q_is_shared != 0;
     g->H = d->num_heads; g->fold = d->fold_key != 0;
     g->HS = (g->H + 3) & ~3; g->HSP = aecf_fold_score_cols(d->dtype, g->H);
     if (g->fold && (!g->shared || g->H <= 0 || g->H > 32)) return AECF_ERR_UNSUPPORTED;
+    if (d->tgt_len > 1 && (g->shared || g->fold)) return AECF_ERR_UNSUPPORTED;   // several queries per sample: per-row, unfolded
     return AECF_OK;
 }
 
@@ -68,7 +70,7 @@ static size_t max_gemm_workspace(const aecf_pool_desc* d, const Geometry& g) {
     const aecf_gemm_desc probes[] = {
         gemm_desc(d->device, dt, dt, dt, dt, AECF_MN_MAJOR, AECF_MN_MAJOR, 2 * D, D, g.rows, 2 * D, D, D),   // dW_kv
         gemm_desc(d->device, dt, dt, dt, dt, AECF_MN_MAJOR, AECF_MN_MAJOR, D, D, g.rows, 2 * D, D, D),       // dW_k / dW_v
-        gemm_desc(d->device, dt, dt, dt, dt, AECF_MN_MAJOR, AECF_MN_MAJOR, D, D, g.B, D, D, D),              // dW_o, dW_q
+        gemm_desc(d->device, dt, dt, dt, dt, AECF_MN_MAJOR, AECF_MN_MAJOR, D, D, g.QR, D, D, D),             // dW_o, dW_q
         gemm_desc(d->device, dt, dt, dt, dt, AECF_K_MAJOR, AECF_K_MAJOR, g.rows, 2 * D, D, D, D, 2 * D),     // kv
         gemm_desc(d->device, dt, dt, dt, dt, AECF_K_MAJOR, AECF_MN_MAJOR, g.rows, D, 2 * D, 2 * D, D, D),    // dX
         gemm_desc(d->device, dt, dt, AECF_F32, dt, AECF_MN_MAJOR, AECF_MN_MAJOR, D + g.HSP, D, g.rows, D + g.HSP, D, D),   // folded [dWv ; R]
@@ -85,7 +87,7 @@ static size_t max_gemm_workspace(const aecf_pool_desc* d, const Geometry& g) {
 static int carve(const aecf_pool_desc* d, const Geometry& g, void* base, Workspace* w) {
     w->gemm_bytes = align256(max_gemm_workspace(d, g));
     w->pool_bytes = align256(aecf_pool_bwd_workspace_bytes(d));
-    w->colsum_bytes = align256(aecf_colsum_workspace_bytes(g.B, g.D));
+    w->colsum_bytes = align256(aecf_colsum_workspace_bytes(g.QR, g.D));
     size_t off = 0;
     char* b = static_cast<char*>(base);
     w->gemm = b + off; off += w->gemm_bytes;
@@ -139,7 +141,7 @@ int aecf_fusion_fwd(const aecf_pool_desc* desc, const aecf_fusion_tensors* t, vo
         ScopedSite site(AECF_SITE_Q_PROJ);
         const aecf_gemm_desc q = g.shared
             ? gemm_desc(dev, dt, dt, AECF_F32, dt, AECF_K_MAJOR, AECF_K_MAJOR, 1, D, D, D, D, D)
-            : gemm_desc(dev, dt, dt, dt, dt, AECF_K_MAJOR, AECF_K_MAJOR, g.B, D, D, D, D, D);
+            : gemm_desc(dev, dt, dt, dt, dt, AECF_K_MAJOR, AECF_K_MAJOR, g.QR, D, D, D, D, D);
         AECF_TRY(aecf_gemm(&q, t->query, t->in_proj_weight, t->in_proj_bias, t->q_proj, w.gemm, w.gemm_bytes, stream));
     }
     if (g.fold) {
@@ -183,7 +185,7 @@ int aecf_fusion_fwd(const aecf_pool_desc* desc, const aecf_fusion_tensors* t, vo
     }
     {   // out projection (:6653)
         ScopedSite site(AECF_SITE_OUT_PROJ);
-        const aecf_gemm_desc o = gemm_desc(dev, dt, dt, dt, dt, AECF_K_MAJOR, AECF_K_MAJOR, g.B, D, D, D, D, D);
+        const aecf_gemm_desc o = gemm_desc(dev, dt, dt, dt, dt, AECF_K_MAJOR, AECF_K_MAJOR, g.QR, D, D, D, D, D);
         AECF_TRY(aecf_gemm(&o, t->ctx, t->out_proj_weight, t->out_proj_bias, t->out, w.gemm, w.gemm_bytes, stream));
     }
     return AECF_OK;
@@ -210,16 +212,16 @@ int aecf_fusion_bwd(const aecf_pool_desc* desc, const aecf_fusion_tensors* t, co
         // ---- out-projection backward: its two parameter gradients are final first -------------------
         if (gr->d_out_proj_bias) {
             ScopedSite site(AECF_SITE_D_OUT_BIAS);
-            AECF_TRY(aecf_colsum(dev, dt, dt, gr->d_out, g.B, D, D, gr->d_out_proj_bias, w.colsum, w.colsum_bytes, stream));
+            AECF_TRY(aecf_colsum(dev, dt, dt, gr->d_out, g.QR, D, D, gr->d_out_proj_bias, w.colsum, w.colsum_bytes, stream));
         }
         if (gr->d_out_proj_weight) {                         // dWo = g^T ctx
             ScopedSite site(AECF_SITE_D_OUT_WEIGHT);
-            const aecf_gemm_desc d = gemm_desc(dev, dt, dt, dt, dt, AECF_MN_MAJOR, AECF_MN_MAJOR, D, D, g.B, D, D, D);
+            const aecf_gemm_desc d = gemm_desc(dev, dt, dt, dt, dt, AECF_MN_MAJOR, AECF_MN_MAJOR, D, D, g.QR, D, D, D);
             AECF_TRY(aecf_gemm(&d, gr->d_out, t->ctx, nullptr, gr->d_out_proj_weight, w.gemm, w.gemm_bytes, stream));
         }
         {                                                    // d_ctx = g Wo
             ScopedSite site(AECF_SITE_D_CTX);
-            const aecf_gemm_desc d = gemm_desc(dev, dt, dt, dt, dt, AECF_K_MAJOR, AECF_MN_MAJOR, g.B, D, D, D, D, D);
+            const aecf_gemm_desc d = gemm_desc(dev, dt, dt, dt, dt, AECF_K_MAJOR, AECF_MN_MAJOR, g.QR, D, D, D, D, D);
             AECF_TRY(aecf_gemm(&d, gr->d_out, t->out_proj_weight, nullptr, gr->d_ctx, w.gemm, w.gemm_bytes, stream));
         }
         if (phase == AECF_BWD_OUT_PROJ) return AECF_OK;
@@ -298,17 +300,17 @@ int aecf_fusion_bwd(const aecf_pool_desc* desc, const aecf_fusion_tensors* t, co
     }
     if (gr->d_in_proj_weight) {   // ---- query rows of the in-projection weight gradient: dW_q = d_q^T Q -------------
         ScopedSite site(AECF_SITE_D_Q_WEIGHT);
-        const aecf_gemm_desc d = gemm_desc(dev, dt, dt, dt, dt, AECF_MN_MAJOR, AECF_MN_MAJOR, D, D, g.B, D, D, D);
+        const aecf_gemm_desc d = gemm_desc(dev, dt, dt, dt, dt, AECF_MN_MAJOR, AECF_MN_MAJOR, D, D, g.QR, D, D, D);
         AECF_TRY(aecf_gemm(&d, gr->d_q_rows, t->query, nullptr, gr->d_in_proj_weight, w.gemm, w.gemm_bytes, stream));
     }
     if (gr->d_query) {                // ---- gradient of the (unprojected) per-row queries ------------------------
         ScopedSite site(AECF_SITE_D_QUERY);
-        const aecf_gemm_desc d = gemm_desc(dev, dt, dt, dt, dt, AECF_K_MAJOR, AECF_MN_MAJOR, g.B, D, D, D, D, D);
+        const aecf_gemm_desc d = gemm_desc(dev, dt, dt, dt, dt, AECF_K_MAJOR, AECF_MN_MAJOR, g.QR, D, D, D, D, D);
         AECF_TRY(aecf_gemm(&d, gr->d_q_rows, t->in_proj_weight, nullptr, gr->d_query, w.gemm, w.gemm_bytes, stream));
     }
     if (gr->d_in_proj_bias) {         // ---- [d_bq | d_bk | d_bv] in the parameter dtype ------------------------
         ScopedSite site(AECF_SITE_D_IN_BIAS);
-        AECF_TRY(aecf_colsum(dev, dt, AECF_F32, gr->d_q_rows, g.B, D, D, w.d_bq, w.colsum, w.colsum_bytes, stream));
+        AECF_TRY(aecf_colsum(dev, dt, AECF_F32, gr->d_q_rows, g.QR, D, D, w.d_bq, w.colsum, w.colsum_bytes, stream));
         TimedLaunch timed(s);
         const int n = 3 * D;
         if (dt == AECF_BF16)

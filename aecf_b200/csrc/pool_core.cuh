@@ -54,6 +54,16 @@ struct PoolParams {
     float* partials;                        // [grid][3][D] fp32: dq | dbv | dbk
 };
 
+// Several fusion queries per sample (pool_multi.cuh): the S rows (b, 0 .. S-1) share the kv rows of sample b.
+// Info outputs, d_pooled, d_entropy and the Philox row are indexed b*S + s.  A second kernel argument, so that
+// PoolParams -- and with it the parameter layout of the single-query kernels -- stays as measured.
+struct MultiQuery {
+    int S;
+    long long q_rb, q_rs;                   // row of (b, s) in q / ctx / d_ctx / d_q: b*q_rb + s*q_rs
+    const float* bias;                      // additive score bias (PoolParams::bias stays null in this mode) ...
+    long long bias_sb, bias_sh, bias_ss;    // ... element (b, h, s, m) at b*bias_sb + h*bias_sh + s*bias_ss + m
+};
+
 template <typename T, int M, int J, bool DROP>
 struct PoolCore {
     static constexpr int V = Vec<T>::N;

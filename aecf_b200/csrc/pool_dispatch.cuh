@@ -33,5 +33,8 @@ namespace aecf {
 template <typename T, bool DROP> int launch_pool_fwd(int M, int J, const PoolParams& p, int grid, int sms, bool fold, void* stream);
 template <typename T, bool DROP> int launch_pool_bwd(int M, int J, const PoolParams& p, int grid, bool fold, void* stream);
 template <typename T, bool DROP> int pool_bwd_blocks_per_sm(int M, int J, bool fold);
+// several fusion queries per sample (pool_multi.cuh); the backward runs one CTA per SM
+template <typename T, bool DROP> int launch_pool_fwd_multi(int M, int J, const PoolParams& p, const MultiQuery& mq, int grid, void* stream);
+template <typename T, bool DROP> int launch_pool_bwd_multi(int M, int J, const PoolParams& p, const MultiQuery& mq, int grid, void* stream);
 
 }  // namespace aecf

@@ -37,7 +37,8 @@ class PoolConfig:
     seq_first: bool = False     # key/value are [M, B, D] (batch_first=False), used in place
     fold: bool = False          # folded key projection (include/aecf_b200.h): shared query, key is value
     want_mask_bits: bool = False
-    bias_strides: tuple = (0, 0)
+    bias_strides: tuple = (0, 0)        # (batch, head[, query]) element strides of the additive score bias
+    tgt_len: int = 1            # fusion queries per sample; > 1: per-row queries [B, S, D] / [S, B, D], rows (b, s)
     # data-parallel hook: called in backward with (name, grad tensor) as soon as a parameter
     # gradient is final, so that its all-reduce overlaps the rest of the backward
     grad_ready: Optional[Callable[[str, torch.Tensor], None]] = None
@@ -72,27 +73,30 @@ class FusedPoolFunction(torch.autograd.Function):
             kv_strides = (0, 0)
         H = cfg.num_heads
         hs, hsp = ops.fold_score_cols(dt, H)
+        S = int(cfg.tgt_len)
+        R = B * S                       # query rows (b, s): b-major for batch-first input, s-major for sequence-first
         desc = ops.make_pool_desc(
             dev, dt, batch=B, num_tokens=M, embed_dim=D, num_heads=cfg.num_heads, training=cfg.training,
             masking=cfg.masking, min_active=cfg.min_active, q_is_shared=cfg.q_shared,
             base_mask_prob=cfg.base_mask_prob, entropy_target=cfg.entropy_target, dropout_p=cfg.dropout_p,
             seed=cfg.seed, offset=cfg.offset, row0=cfg.row0, bias_strides=cfg.bias_strides, kv_strides=kv_strides,
-            fold_key=fold, rng_state=cfg.rng_state)
+            fold_key=fold, rng_state=cfg.rng_state, tgt_len=S,
+            q_strides=(1, B) if (S > 1 and cfg.seq_first) else (0, 0))
 
-        q_in = q_src.reshape(D) if cfg.q_shared else q_src.reshape(B, D)
+        q_in = q_src.reshape(D) if cfg.q_shared else q_src.reshape(R, D)
         if not q_in.is_contiguous():
             q_in = q_in.contiguous()
-        qp = torch.empty((D,), dtype=torch.float32, device=dev) if cfg.q_shared else torch.empty((B, D), dtype=dt, device=dev)
+        qp = torch.empty((D,), dtype=torch.float32, device=dev) if cfg.q_shared else torch.empty((R, D), dtype=dt, device=dev)
         kv = torch.empty((B * M, D if fold else 2 * D), dtype=dt, device=dev)     # folded: the values only
         scores = torch.empty((B * M, hs), dtype=torch.float32, device=dev) if fold else None
         folded_w = torch.empty((D + hsp, D), dtype=dt, device=dev) if fold else None
-        attn = torch.empty((B, D), dtype=dt, device=dev)
-        out = torch.empty((B, D), dtype=dt, device=dev)
-        pooled = torch.empty((B, M), dtype=torch.float32, device=dev)
-        entropy = torch.empty((B,), dtype=torch.float32, device=dev)
-        mask_rate = torch.empty((B,), dtype=torch.float32, device=dev)
-        masked = torch.empty((B, M), dtype=torch.float32, device=dev)
-        bits = torch.empty((B if cfg.want_mask_bits else 0,), dtype=torch.uint8, device=dev)
+        attn = torch.empty((R, D), dtype=dt, device=dev)
+        out = torch.empty((R, D), dtype=dt, device=dev)
+        pooled = torch.empty((R, M), dtype=torch.float32, device=dev)        # info tensors: rows b*S + s always
+        entropy = torch.empty((R,), dtype=torch.float32, device=dev)
+        mask_rate = torch.empty((R,), dtype=torch.float32, device=dev)
+        masked = torch.empty((R, M), dtype=torch.float32, device=dev)
+        bits = torch.empty((R if cfg.want_mask_bits else 0,), dtype=torch.uint8, device=dev)
         p = _lib.ptr
         tensors = _lib.FusionTensors(
             query=p(q_in), key=p(key), value=p(value), in_proj_weight=p(in_w), in_proj_bias=p(in_b),
@@ -107,6 +111,7 @@ class FusedPoolFunction(torch.autograd.Function):
         # no fill kernels, and the backward kernel skips the d_pooled / d_entropy terms altogether
         ctx.set_materialize_grads(False)
         ctx.shape = (B, M, D)
+        ctx.query_rows = R
         ctx.q_shape = q_src.shape
         ctx.save_for_backward(q_in, key, value, in_w, in_b, out_w, out_b, qp, kv, attn, score_bias, scores, folded_w)
         if cfg.masking != 2:                            # entropy is detached in training mode (reference :278)
@@ -120,28 +125,29 @@ class FusedPoolFunction(torch.autograd.Function):
         cfg: PoolConfig = ctx.cfg
         q_in, key, value, in_w, in_b, out_w, out_b, qp, kv, attn, score_bias, scores, folded_w = ctx.saved_tensors
         B, M, D = ctx.shape
+        R = ctx.query_rows
         dev, dt = key.device, key.dtype
         need_q, need_key, need_value, need_in_w, need_in_b, need_out_w, need_out_b = ctx.needs_input_grad[:7]
         notify = cfg.grad_ready
 
         if g_out is None:
-            g = torch.zeros((B, D), dtype=dt, device=dev)
+            g = torch.zeros((R, D), dtype=dt, device=dev)
         else:
-            g = g_out.reshape(B, D)
+            g = g_out.reshape(R, D)
             if g.dtype != dt or not g.is_contiguous():
                 g = g.to(dt).contiguous()
         d_pooled = None
         if g_pooled is not None:
-            d_pooled = g_pooled.reshape(B, M).to(torch.float32).contiguous()
+            d_pooled = g_pooled.reshape(R, M).to(torch.float32).contiguous()
         d_entropy = None
         if g_entropy is not None and cfg.masking == 2:
-            d_entropy = g_entropy.reshape(B).to(torch.float32).contiguous()
+            d_entropy = g_entropy.reshape(R).to(torch.float32).contiguous()
 
         new = lambda shape, dtype=dt: torch.empty(shape, dtype=dtype, device=dev)
         # folded: rows of d_kv are [dV (D) | ds (HSP)]
         d_kv_cols = D + ops.fold_score_cols(dt, cfg.num_heads)[1] if cfg.fold else 2 * D
-        d_ctx, d_kv = new((B, D)), new((B * M, d_kv_cols))
-        d_q_rows = None if cfg.q_shared else new((B, D))
+        d_ctx, d_kv = new((R, D)), new((B * M, d_kv_cols))
+        d_q_rows = None if cfg.q_shared else new((R, D))
         d_key = new(key.shape) if need_key else None
         d_value = new(value.shape) if (value is not None and need_value) else None
         bufs = cfg.grad_buffers or {}

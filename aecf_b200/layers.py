@@ -292,40 +292,41 @@ class MultimodalAttentionPool(nn.Module):
             return base                      # the Parameter itself: its gradient arrives already reduced
         return query.narrow(bdim, 0, 1)      # generic stride-0 view: autograd expands the reduced gradient
 
-    def _score_bias(self, key_padding_mask, attn_mask, batch, tokens, device):
+    def _score_bias(self, key_padding_mask, attn_mask, batch, tokens, device, tgt_len=1):
         """Merge key_padding_mask and attn_mask into one additive fp32 bias the way torch does
-        (torch/nn/functional.py:6608-6620).  Returns (tensor or None, (stride_b, stride_h))."""
+        (torch/nn/functional.py:6608-6620).  Returns (tensor or None, (stride_b, stride_h, stride_s)): a contiguous
+        [b, h, s, tokens] tensor whose broadcast dimensions have size 1 and stride 0."""
         def as_float(mask):
             if mask.dtype == torch.bool:
                 return torch.zeros(mask.shape, dtype=torch.float32, device=device).masked_fill_(mask, float("-inf"))
             return mask.to(torch.float32)
 
-        H = self.num_heads
+        H, S = self.num_heads, tgt_len
         bias = None
         if attn_mask is not None:
             am = as_float(attn_mask.to(device))
             if am.dim() == 2:
-                if am.shape != (1, tokens):
-                    raise RuntimeError(f"The shape of the 2D attn_mask is {tuple(am.shape)}, but should be {(1, tokens)}.")
-                bias = am.reshape(1, 1, tokens)
+                if am.shape != (S, tokens):
+                    raise RuntimeError(f"The shape of the 2D attn_mask is {tuple(am.shape)}, but should be {(S, tokens)}.")
+                bias = am.reshape(1, 1, S, tokens)
             elif am.dim() == 3:
-                if am.shape != (batch * H, 1, tokens):
+                if am.shape != (batch * H, S, tokens):
                     raise RuntimeError(
-                        f"The shape of the 3D attn_mask is {tuple(am.shape)}, but should be {(batch * H, 1, tokens)}.")
-                bias = am.reshape(batch, H, tokens)
+                        f"The shape of the 3D attn_mask is {tuple(am.shape)}, but should be {(batch * H, S, tokens)}.")
+                bias = am.reshape(batch, H, S, tokens)
             else:
                 raise RuntimeError(f"attn_mask's dimension {am.dim()} is not supported")
         if key_padding_mask is not None:
             if key_padding_mask.shape != (batch, tokens):
                 raise RuntimeError(
                     f"expecting key_padding_mask shape of {(batch, tokens)}, but got {tuple(key_padding_mask.shape)}")
-            kpm = as_float(key_padding_mask.to(device)).reshape(batch, 1, tokens)
+            kpm = as_float(key_padding_mask.to(device)).reshape(batch, 1, 1, tokens)
             bias = kpm if bias is None else bias + kpm
         if bias is None:
-            return None, (0, 0)
+            return None, (0, 0, 0)
         bias = bias.contiguous()
-        b, h, _ = bias.shape
-        return bias, (h * tokens if b > 1 else 0, tokens if h > 1 else 0)
+        b, h, s, _ = bias.shape
+        return bias, (h * s * tokens if b > 1 else 0, s * tokens if h > 1 else 0, tokens if s > 1 else 0)
 
     def forward(self, query: torch.Tensor, key: torch.Tensor, value: Optional[torch.Tensor] = None,
                 key_padding_mask: Optional[torch.Tensor] = None, attn_mask: Optional[torch.Tensor] = None,
@@ -337,7 +338,10 @@ class MultimodalAttentionPool(nn.Module):
         ops.require_cuda(query, key, value, self.attention.in_proj_weight)
         if embed != self.embed_dim:
             raise RuntimeError(f"was expecting embedding dimension of {self.embed_dim}, but got {embed}")
-        if tgt_len != 1:
+        # several queries per sample run on their own kernels (csrc/pool_multi.cuh), which have not been run on
+        # hardware yet: opt-in with AECF_MULTI_QUERY=1 until tests/test_gpu_multi_query.py has passed on a B200
+        multi = tgt_len > 1 and os.environ.get("AECF_MULTI_QUERY") == "1"
+        if tgt_len != 1 and not multi:
             raise ops._lib.UnsupportedShapeError(
                 ops._lib.ERR_UNSUPPORTED, "MultimodalAttentionPool",
                 f"the fused pool covers one fusion query per sample (target length 1), got {tgt_len}")
@@ -347,13 +351,15 @@ class MultimodalAttentionPool(nn.Module):
             raise RuntimeError(f"expected query/key/value of dtype {dt} (the module's parameter dtype), "
                                f"got {query.dtype}/{key.dtype}")
 
-        q_src = self._shared_query_source(query, batch)
+        q_src = None if multi else self._shared_query_source(query, batch)
         q_shared = q_src is not None
-        if not q_shared:
+        if multi:
+            q_src = query.contiguous()             # [B, S, D] or [S, B, D], used in place (rows (b, s) by strides)
+        elif not q_shared:
             q_src = (query if self.batch_first else query.transpose(0, 1)).contiguous()
         key_c = key.contiguous()
         value_c = None if value is None else value.contiguous()
-        bias, bias_strides = self._score_bias(key_padding_mask, attn_mask, batch, tokens, key.device)
+        bias, bias_strides = self._score_bias(key_padding_mask, attn_mask, batch, tokens, key.device, tgt_len)
 
         cm = self.curriculum_masking
         fused_cm = cm is not None and type(cm).forward is CurriculumMasking.forward
@@ -362,7 +368,7 @@ class MultimodalAttentionPool(nn.Module):
             masking = 1 if cm.training else 2
             if cm.training and tokens > 1:
                 cm._last_seq_len = tokens                               # reference :187
-        can_fold = q_shared and value_c is None and self.num_heads <= 32
+        can_fold = q_shared and value_c is None and self.num_heads <= 32 and not multi
         if self.fold_key_projection is None:
             fold = can_fold and dt == torch.bfloat16 and os.environ.get("AECF_FOLD", "1") != "0"
         else:
@@ -380,22 +386,22 @@ class MultimodalAttentionPool(nn.Module):
             min_active=cm.min_active if fused_cm else 1,
             seed=seed, offset=offset, rng_state=rng_state, row0=int(self.row_offset), q_shared=q_shared,
             seq_first=not self.batch_first, fold=fold, want_mask_bits=self._want_mask_bits, bias_strides=bias_strides,
-            grad_ready=self._grad_ready, grad_buffers=self._grad_buffers)
+            tgt_len=tgt_len, grad_ready=self._grad_ready, grad_buffers=self._grad_buffers)
         out, pooled, entropy, mask_rate, masked, bits = FusedPoolFunction.apply(
             q_src, key_c, value_c, att.in_proj_weight, att.in_proj_bias, att.out_proj.weight, att.out_proj.bias,
             bias, cfg)
 
-        attn_output = out.reshape(batch, 1, embed) if self.batch_first else out.reshape(1, batch, embed)
-        pooled_weights = pooled.reshape(batch, 1, tokens)
+        attn_output = out.reshape(batch, tgt_len, embed) if self.batch_first else out.reshape(tgt_len, batch, embed)
+        pooled_weights = pooled.reshape(batch, tgt_len, tokens)         # [B, S, M] whatever batch_first (functional.py:6657)
         info: Dict[str, Any] = {}
         if cm is not None:
             if fused_cm:
-                info["entropy"] = entropy.reshape(batch, 1)
-                info["mask_rate"] = mask_rate.reshape(batch, 1)
+                info["entropy"] = entropy.reshape(batch, tgt_len)
+                info["mask_rate"] = mask_rate.reshape(batch, tgt_len)
                 if cm.training:                                         # eval mode has no target (:153-156)
                     target = math.log(float(tokens)) * cm.entropy_target if tokens > 1 else 0.0
                     info["target_entropy"] = torch.full_like(info["entropy"], target)
-                masked_weights = masked.reshape(batch, 1, tokens)
+                masked_weights = masked.reshape(batch, tgt_len, tokens)
             else:
                 masked_weights, mask_info = cm(pooled_weights)          # user-overridden forward (README.md:341-350)
                 info.update(mask_info)
@@ -403,7 +409,7 @@ class MultimodalAttentionPool(nn.Module):
             if return_info:
                 info["masked_attention_weights"] = masked_weights.detach()
                 if self._want_mask_bits:
-                    info["mask_bits"] = bits
+                    info["mask_bits"] = bits.reshape(batch, tgt_len) if multi else bits
         elif return_info:
             info["attention_weights"] = pooled_weights
         if return_info:

@@ -114,17 +114,22 @@ def colsum(x2d: torch.Tensor, out_dtype: Optional[torch.dtype] = None, name="col
 def make_pool_desc(dev: torch.device, dtype: torch.dtype, *, batch: int, num_tokens: int, embed_dim: int,
                    num_heads: int, training: bool, masking: int, min_active: int, q_is_shared: bool,
                    base_mask_prob: float, entropy_target: float, dropout_p: float, seed: int, offset: int,
-                   row0: int, bias_strides: Tuple[int, int] = (0, 0),
+                   row0: int, bias_strides: Tuple[int, ...] = (0, 0),
                    kv_strides: Tuple[int, int] = (0, 0), fold_key: bool = False,
-                   rng_state: Optional[torch.Tensor] = None) -> _lib.PoolDesc:
+                   rng_state: Optional[torch.Tensor] = None, tgt_len: int = 1,
+                   q_strides: Tuple[int, int] = (0, 0)) -> _lib.PoolDesc:
+    """``bias_strides`` = (batch, head[, query]) element strides of the additive score bias; ``tgt_len`` > 1 and
+    ``q_strides`` (rows of query (b, s): b*q_strides[0] + s*q_strides[1]) describe several queries per sample."""
     return _lib.PoolDesc(device=dev.index or 0, dtype=dtype_code(dtype), batch=batch, num_tokens=num_tokens,
                          embed_dim=embed_dim, num_heads=num_heads, training=int(training), masking=int(masking),
                          min_active=int(min_active), q_is_shared=int(q_is_shared),
                          base_mask_prob=float(base_mask_prob), entropy_target=float(entropy_target),
                          dropout_p=float(dropout_p), seed=seed & 0xFFFFFFFFFFFFFFFF, offset=offset & 0xFFFFFFFF,
                          row0=row0, bias_stride_b=bias_strides[0], bias_stride_h=bias_strides[1],
-                         kv_stride_b=kv_strides[0], kv_stride_m=kv_strides[1], fold_key=int(fold_key), reserved=0,
-                         rng_state=None if rng_state is None else rng_state.data_ptr())
+                         kv_stride_b=kv_strides[0], kv_stride_m=kv_strides[1], fold_key=int(fold_key),
+                         tgt_len=int(tgt_len), rng_state=None if rng_state is None else rng_state.data_ptr(),
+                         q_stride_b=q_strides[0], q_stride_s=q_strides[1],
+                         bias_stride_s=bias_strides[2] if len(bias_strides) > 2 else 0)
 
 
 def fold_score_cols(dtype: torch.dtype, num_heads: int) -> Tuple[int, int]:

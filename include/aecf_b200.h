@@ -45,7 +45,7 @@ extern "C" {
 #define AECF_API
 #endif
 
-#define AECF_ABI_VERSION 2
+#define AECF_ABI_VERSION 3
 #define AECF_MAX_TOKENS 8
 
 typedef enum aecf_status {
@@ -89,12 +89,27 @@ typedef struct aecf_pool_desc {
     int64_t  kv_stride_b;     /* kv / d_kv strides in elements between rows and between tokens; 0, 0 means the */
     int64_t  kv_stride_m;     /* packed [B, M, 2D] layout (M*2D, 2D); a sequence-first [M, B, 2D] buffer is (2D, B*2D) */
     int32_t  fold_key;        /* whole-step entry points only: 1 = folded key projection (see "folded key projection") */
-    int32_t  reserved;        /* 0 */
+    int32_t  tgt_len;         /* S: fusion queries per sample; 0 or 1 = one (the hot path), see "several queries" below */
     /* CUDA-graph capture: a by-value (seed, offset) would be frozen into the graph.  When non-null, this DEVICE
      * pointer to {seed, offset} (two uint64) is read by the kernels at run time instead: key = seed, call offset =
      * low 32 bits of (offset + desc.offset); the caller advances the device-side offset between replays. */
     const uint64_t* rng_state;
+    /* several queries per sample (tgt_len > 1) only */
+    int64_t  q_stride_b;      /* ROW of query (b, s) in q / ctx / d_ctx / d_q and in the whole-step query / out / d_out: */
+    int64_t  q_stride_s;      /*   b*q_stride_b + s*q_stride_s; (0, 0) = batch-first (S, 1); sequence-first is (1, B) */
+    int64_t  bias_stride_s;   /* score_bias stride between the queries of a sample (0 broadcasts) */
 } aecf_pool_desc;
+
+/* Several queries per sample (tgt_len = S > 1; reference aecf/AECFLayer.py:415 takes any [B, S, D] query).  Every
+ * (b, s) pair is a row of its own for the softmax, the dropout draws, the head mean and the CurriculumMasking
+ * stage; the S rows of a sample share its M keys and values, whose gradients sum over them.  In this mode
+ *   - the query is per row (q_is_shared = 0) and the key projection is not folded (fold_key = 0);
+ *   - q / ctx / d_ctx / d_q hold B*S rows of D at b*q_stride_b + s*q_stride_s;
+ *   - pooled / masked are [B, S, M], entropy / mask_rate / mask_bits / d_entropy [B, S], d_pooled [B, S, M], all
+ *     b-major whatever the query layout (torch returns the weights as [B, S, M], functional.py:6657);
+ *   - the Philox row of (b, s) is (row0 + b) * S + s, so S == 1 is the contract above unchanged;
+ *   - score_bias element (b, h, s, m) sits at b*bias_stride_b + h*bias_stride_h + s*bias_stride_s + m.
+ * kv / d_kv keep their [B, M, 2D] layout and strides. */
 
 /* Forward: scale, per-head scores, softmax, dropout, weighted value sum, head mean, and the whole
  * CurriculumMasking stage.  Replaces torch/nn/functional.py:6632-6647, 6657-6659 and reference

@@ -21,11 +21,36 @@ def test_library_loads_and_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.aecf_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.aecf_abi_version() == _lib.ABI_VERSION == 3
     assert b"sm_100a" in lib.aecf_build_info()
     assert lib.aecf_strerror(-2).decode().startswith("shape or dtype outside")
-    # structs mirror the header: sizes are what the C compiler lays out (natural alignment)
-    assert ctypes.sizeof(_lib.PoolDesc) == 128 and ctypes.sizeof(_lib.GemmDesc) == 88
+
+
+def test_ctypes_structs_mirror_the_header_layout(tmp_path):
+    """Every ctypes mirror in _lib.py against what gcc lays out from include/aecf_b200.h: size and the offset of
+    each field, by name."""
+    import subprocess
+    structs = {"aecf_pool_desc": _lib.PoolDesc, "aecf_gemm_desc": _lib.GemmDesc, "aecf_peer_desc": _lib.PeerDesc,
+               "aecf_fusion_tensors": _lib.FusionTensors, "aecf_fusion_grads": _lib.FusionGrads}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "aecf_b200.h"', 'int main(void) {']
+    for cname, mirror in structs.items():
+        lines.append(f'printf("{cname} size %zu\\n", sizeof({cname}));')
+        for field, _ in mirror._fields_:
+            lines.append(f'printf("{cname} {field} %zu\\n", offsetof({cname}, {field}));')
+    lines += ["return 0; }"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    seen = 0
+    for line in filter(None, out):
+        cname, field, value = line.split()
+        mirror = structs[cname]
+        want = ctypes.sizeof(mirror) if field == "size" else getattr(mirror, field).offset
+        assert int(value) == want, f"{cname}.{field}: header {value}, ctypes {want}"
+        seen += 1
+    assert seen == sum(len(m._fields_) + 1 for m in structs.values())
 
 
 def test_descriptor_validation_needs_no_gpu():
@@ -195,3 +220,60 @@ def test_pool_exposes_the_fold_switch():
     assert pool.fold_key_projection is None                              # automatic: on for bf16 with a shared query
     pool.fold_key_projection = False
     assert "fold" not in repr(pool)                                      # extra_repr stays the reference's
+
+
+def test_multi_query_descriptors_validate_without_a_gpu():
+    """Several queries per sample (desc.tgt_len > 1): per-row queries only, no folded key projection, sane strides."""
+    lib = _lib.load()
+    d = _lib.PoolDesc(device=0, dtype=_lib.F32, batch=4, num_tokens=3, embed_dim=64, num_heads=8, q_is_shared=1, tgt_len=2)
+    args = (16, 16, None, 16, 16, None, None, None, None, None)
+    assert lib.aecf_pool_fwd(ctypes.byref(d), *args) == _lib.ERR_UNSUPPORTED        # one shared query and S > 1
+    d.q_is_shared = 0
+    d.q_stride_b, d.q_stride_s = -1, 1
+    assert lib.aecf_pool_fwd(ctypes.byref(d), *args) == _lib.ERR_INVALID
+    d.q_stride_b, d.q_stride_s = 0, 0
+    assert lib.aecf_pool_fwd(ctypes.byref(d), 8, 16, None, 16, 16, None, None, None, None, None) == _lib.ERR_ALIGNMENT
+    assert lib.aecf_pool_fwd_folded(ctypes.byref(d), *args) == _lib.ERR_UNSUPPORTED
+    t = _lib.FusionTensors()
+    d.q_is_shared = 1
+    assert lib.aecf_fusion_fwd(ctypes.byref(d), ctypes.byref(t), 16, 1 << 30, None) == _lib.ERR_UNSUPPORTED
+    one = _lib.PoolDesc(device=0, dtype=_lib.F32, batch=4, num_tokens=3, embed_dim=64, num_heads=8, q_is_shared=0)
+    two = _lib.PoolDesc(device=0, dtype=_lib.F32, batch=4, num_tokens=3, embed_dim=64, num_heads=8, q_is_shared=0, tgt_len=4)
+    assert lib.aecf_fusion_workspace_bytes(ctypes.byref(two)) >= lib.aecf_fusion_workspace_bytes(ctypes.byref(one)) > 0
+
+
+@pytest.mark.parametrize("batch_first", [True, False])
+def test_multi_query_host_plumbing(monkeypatch, batch_first):
+    """What the module hands to the C ABI for a [B, S, D] query, with the native calls recorded instead of run: the
+    descriptor (tgt_len, query row strides, bias strides), buffer shapes, the shapes that come back, and the gate."""
+    B, S, M, D, H = 6, 3, 4, 32, 4
+    calls = {}
+    monkeypatch.setattr(ops, "require_cuda", lambda *t: torch.device("cpu"))
+    monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)
+    monkeypatch.setattr(ops, "fusion_workspace", lambda desc, dev: torch.empty(1))
+    monkeypatch.setattr(ops, "fusion_fwd", lambda desc, tensors, dev: calls.setdefault("fwd", (desc, tensors)))
+    monkeypatch.setattr(ops, "fusion_bwd", lambda desc, tensors, grads, phase, ws, dev: calls.setdefault("bwd", (desc, grads, phase)))
+    pool = aecf.MultimodalAttentionPool(D, num_heads=H, curriculum_masking=aecf.CurriculumMasking(), batch_first=batch_first)
+    q = torch.randn(B, S, D, requires_grad=True) if batch_first else torch.randn(S, B, D, requires_grad=True)
+    k = torch.randn(B, M, D, requires_grad=True) if batch_first else torch.randn(M, B, D, requires_grad=True)
+    kpm = torch.zeros(B, M, dtype=torch.bool)
+    am = torch.zeros(S, M)
+    with pytest.raises(_lib.UnsupportedShapeError, match="target length 1"):           # opt-in until run on hardware
+        pool(q, k, return_info=True)
+    monkeypatch.setenv("AECF_MULTI_QUERY", "1")
+    out, info = pool(q, k, key_padding_mask=kpm, attn_mask=am, return_info=True)
+    desc, tensors = calls["fwd"]
+    assert (desc.batch, desc.tgt_len, desc.num_tokens, desc.q_is_shared, desc.fold_key) == (B, S, M, 0, 0)
+    assert (desc.q_stride_b, desc.q_stride_s) == ((0, 0) if batch_first else (1, B))
+    assert (desc.bias_stride_b, desc.bias_stride_h, desc.bias_stride_s) == (S * M, 0, M)   # [B, 1, S, M] merged bias
+    assert (desc.kv_stride_b, desc.kv_stride_m) == ((0, 0) if batch_first else (2 * D, B * 2 * D))
+    assert out.shape == ((B, S, D) if batch_first else (S, B, D))
+    assert info["attention_weights"].shape == (B, S, M) and info["masked_attention_weights"].shape == (B, S, M)
+    assert info["entropy"].shape == info["mask_rate"].shape == info["target_entropy"].shape == (B, S)
+    (out.sum() + info["attention_weights"].sum()).backward()
+    desc_b, grads, phase = calls["bwd"]
+    assert desc_b is desc and phase == _lib.BWD_ALL and grads.d_q_rows and grads.d_pooled and grads.d_query
+    assert q.grad.shape == q.shape and k.grad.shape == k.shape
+    assert pool.attention.in_proj_weight.grad.shape == (3 * D, D)
+    with pytest.raises(RuntimeError, match=r"2D attn_mask is \(1, 4\), but should be \(3, 4\)"):
+        pool(q, k, attn_mask=torch.zeros(1, M))
