@@ -149,6 +149,16 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
         : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// The same wait, naming the registers an earlier tcgen05.ld is still filling as read-write operands: nothing that
+// consumes them can be scheduled above the wait, however far the load was issued ahead (experimental epilogues).
+__device__ __forceinline__ void tmem_ld_wait_on(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
+}
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, leading/stride byte
 // offsets in 16-byte units, version 1 (Blackwell), layout type 2 = SWIZZLE_128B.
@@ -260,8 +270,13 @@ __device__ __forceinline__ WorkItem decode(const Params& p, int item, int cta_ra
 // (profiles/r1_gemm_experiments.md, "round-2 order of attack"): the next group's tcgen05.ld is in flight while the
 // current group is converted, and the two staging boxes alternate with `wait_group.read 1`, so neither the TMEM
 // read latency nor the previous store's shared-memory read is exposed.
+// 3 = EXPERIMENTAL, AECF_GEMM_EPI=3, not yet run on hardware: EIGHT epilogue warps (320 threads), two per TMEM lane
+// quadrant, each converting and storing every other 64-column box of its 32 rows -- two warps per scheduler instead
+// of one, so the ~6 clk/instruction dependent-issue latency of the conversion is hidden; bf16 direct output only (the
+// host keeps EPI 1 for fp32 / split-K output).
+constexpr int epi_warps(int epi) { return epi == 3 ? 8 : 4; }
 template <int BN, int CL, int EPI>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(64 + 32 * epi_warps(EPI), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_c, const Params p) {
     using C = Cfg<BN>;
@@ -286,7 +301,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_a); prefetch_tmap(&map_b); prefetch_tmap(&map_c);
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CL); }   // every CTA's MMA frees a slot
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EPI_THREADS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 32 * epi_warps(EPI)); }
         fence_barrier_init();
     }
     if (warp == 1) {                                  // one warp allocates TMEM and owns the dealloc
@@ -407,6 +422,66 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
             const uint32_t t_row = tmem_base + as * C::ACC_STRIDE + (static_cast<uint32_t>(quad * 32) << 16);
             const int out_row0 = (direct ? 0 : w.split * p.partial_rows) + m0 + quad * 32;
+            if constexpr (EPI == 3) {
+                // ---- eight warps: warp (quad, half) owns the boxes half, half + 2, ... of its 32 rows and one private
+                // [32 rows x 128 B] staging box; both 32-column TMEM reads of a box are issued before either is used
+                constexpr int BOXES = BN / 64;
+                uint8_t* box_base = epi_base + ew * (32 * 128);
+                uint8_t* box = box_base + lane * 128;
+#pragma unroll 1
+                for (int bx = ew >> 2; bx < BOXES; bx += 2) {
+                    uint32_t r[2][32];
+                    tmem_ld_32x32(t_row + bx * 64, r[0]);
+                    tmem_ld_32x32(t_row + bx * 64 + 32, r[1]);
+                    if (lane == 0) tma_store_wait_read();                      // my previous store has read the box
+                    tmem_ld_wait_on(r[0]);
+                    tmem_ld_wait_on(r[1]);
+                    __syncwarp();
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int col_in_tile = bx * 64 + h * 32;
+                        float v[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[h][i]);
+                        if (p.has_bias) {
+                            const float4* b4 = reinterpret_cast<const float4*>(wbias + col_in_tile);   // 128-byte aligned
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                const float4 t = b4[c];
+                                v[4 * c] += t.x; v[4 * c + 1] += t.y; v[4 * c + 2] += t.z; v[4 * c + 3] += t.w;
+                            }
+                        }
+                        if (p.aux != nullptr && n0 + col_in_tile == p.c_cols) {
+                            const int row = m0 + quad * 32 + lane;
+                            if (tile_valid && row < p.m) {
+                                float4* dst = reinterpret_cast<float4*>(p.aux + static_cast<long long>(row) * p.aux_ld);
+#pragma unroll
+                                for (int c = 0; c < 8; ++c)
+                                    if (4 * c < p.aux_cols) dst[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                            }
+                        }
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const int chunk = h * 4 + c;
+                            *reinterpret_cast<uint4*>(box + ((chunk ^ (lane & 7)) << 4)) =
+                                make_uint4(Vec<__nv_bfloat16>::pack2(v[8 * c], v[8 * c + 1]),
+                                           Vec<__nv_bfloat16>::pack2(v[8 * c + 2], v[8 * c + 3]),
+                                           Vec<__nv_bfloat16>::pack2(v[8 * c + 4], v[8 * c + 5]),
+                                           Vec<__nv_bfloat16>::pack2(v[8 * c + 6], v[8 * c + 7]));
+                        }
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    const int col0 = n0 + bx * 64;
+                    if (lane == 0) {
+                        if (tile_valid && col0 < p.c_cols) tma_store_2d(&map_c, box_base, col0, out_row0);
+                        tma_store_commit();
+                    }
+                }
+                tc_fence_before();                                             // this warp's TMEM and bias reads are done
+                mbar_arrive(&tmem_empty[as]);
+                continue;
+            }
             if constexpr (EPI == 2) {
                 if (!p.c_is_f32) {
                     // ---- pipelined bf16 epilogue: group g+1 is being read out of TMEM while group g is converted; box
@@ -416,12 +491,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     tmem_ld_32x32(t_row, r[0]);
 #pragma unroll
                     for (int g = 0; g < GROUPS; ++g) {
-                        tmem_ld_wait();                                        // r[g & 1] has landed
+                        tmem_ld_wait_on(r[g & 1]);                             // r[g & 1] has landed
                         if (g + 1 < GROUPS) tmem_ld_32x32(t_row + (g + 1) * 32, r[(g + 1) & 1]);
-                        else {                                                 // every TMEM read of this tile is done
-                            tc_fence_before();
-                            mbar_arrive(&tmem_empty[as]);
-                        }
                         // boxes alternate ACROSS tiles too (a 192-wide tile fills three), so the box being refilled is
                         // always the one stored two commits ago
                         uint8_t* box_base = wbuf + ((box_it + (g >> 1)) & 1) * (32 * 128);
@@ -435,6 +506,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         for (int i = 0; i < 32; ++i) {
                             v[i] = __uint_as_float(r[g & 1][i]);
                             if (direct && p.has_bias) v[i] += wbias[g * 32 + i];
+                        }
+                        if (g == GROUPS - 1) {                                 // every TMEM and bias read of this tile is done
+                            tc_fence_before();
+                            mbar_arrive(&tmem_empty[as]);
                         }
                         if (p.aux != nullptr && n0 + g * 32 == p.c_cols) {
                             const int row = m0 + quad * 32 + lane;
@@ -928,10 +1003,14 @@ int gemm_tcgen05(const aecf_gemm_desc* d, const void* A, const void* B, const vo
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    static const bool pipelined_epilogue = [] { const char* e = getenv("AECF_GEMM_EPI"); return e && e[0] == '2'; }();
+    // AECF_GEMM_EPI=2 / 3 select the experimental epilogues (see gemm_tcgen05_kernel); 3 applies to direct bf16 output only
+    static const int epi_env = [] { const char* e = getenv("AECF_GEMM_EPI"); return (e && (e[0] == '2' || e[0] == '3')) ? e[0] - '0' : 1; }();
+    const int epi = (epi_env == 3 && (c_f32 || pl.two_sm)) ? 1 : epi_env;
+    if (epi == 3) cfg.blockDim = dim3(64 + 32 * epi_warps(3));
 #define AECF_TC_LAUNCH(BN_, CL_)                                                                                  \
     do {                                                                                                          \
-        auto kernel = pipelined_epilogue ? gemm_tcgen05_kernel<BN_, CL_, 2> : gemm_tcgen05_kernel<BN_, CL_, 1>;   \
+        auto kernel = epi == 3 ? gemm_tcgen05_kernel<BN_, CL_, 3>                                                 \
+                               : (epi == 2 ? gemm_tcgen05_kernel<BN_, CL_, 2> : gemm_tcgen05_kernel<BN_, CL_, 1>); \
         cfg.dynamicSmemBytes = Cfg<BN_>::SMEM_BYTES;                                                              \
         AECF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN_>::SMEM_BYTES)); \
         AECF_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, map_a, map_b, map_c, p));                                   \

@@ -31,6 +31,8 @@ def test_pipelined_gemm_epilogue_passes_the_gemm_and_parity_suites():
                   "gemm or side_output or bf16 or folded or headline or sharding"])
 
 
-def test_streaming_pool_backward_passes_the_parity_suite():
-    """AECF_POOL_BWD_STREAM=1: cp.async double-buffered rows in the folded backward."""
-    _pytest_with({"AECF_POOL_BWD_STREAM": "1"}, ["tests/test_gpu_parity.py", "tests/test_gpu_graphs.py"])
+def test_eight_warp_gemm_epilogue_passes_the_gemm_and_parity_suites():
+    """AECF_GEMM_EPI=3: eight epilogue warps (two per TMEM lane quadrant), direct bf16 output only."""
+    _pytest_with({"AECF_GEMM_EPI": "3"},
+                 ["tests/test_gpu_gemm_tcgen05.py", "tests/test_gpu_parity.py", "-k",
+                  "gemm or side_output or bf16 or folded or headline or sharding"])
