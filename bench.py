@@ -43,6 +43,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--batch", type=int, default=65536, help="rows per GPU (weak scaling)")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="strong scaling: this many rows in total, sharded over the ranks (overrides --batch); the timed "
+                         "steps rotate over enough input buffers to exceed the L2 when one shard fits in it")
     ap.add_argument("--tokens", type=int, default=3)
     ap.add_argument("--dim", type=int, default=512)
     ap.add_argument("--heads", type=int, default=8)
@@ -199,13 +202,31 @@ def cpu_model():
     return "unknown"
 
 
+L2_BYTES = 126 * 1024 * 1024
+
+
+def input_buffers_needed(x_bytes: int) -> int:
+    """How many distinct input batches the timed steps must rotate over so that a step never finds its input in
+    the 126 MB L2: 1 when one batch is larger than the L2 (the default workload), else enough to exceed twice the L2."""
+    return 1 if x_bytes > L2_BYTES else min(32, -(-2 * L2_BYTES // max(x_bytes, 1)))
+
+
 def workload_config(args, n_gpus):
+    es = 2 if args.dtype == "bf16" else 4
+    x_mb = args.batch * args.tokens * args.dim * es / 1e6
+    strong = getattr(args, "global_batch", 0) > 0
+    rot = input_buffers_needed(int(x_mb * 1e6))
+    l2 = (f"inputs larger than L2 (x {x_mb:.0f} MB, values {x_mb:.0f} MB per step vs 126 MB L2); no flush needed" if rot == 1 else
+          f"one shard's input ({x_mb:.0f} MB) fits in the 126 MB L2: the timed steps rotate over {rot} input batches "
+          f"({rot * x_mb:.0f} MB), so no step finds its input in L2")
     return {"workload": f"MultimodalAttentionPool D={args.dim} H={args.heads} M={args.tokens} with CurriculumMasking, "
-                        f"B={args.batch} per GPU, {args.dtype} (BASELINE.json configs[1])",
-            "global_batch": args.batch * n_gpus, "tokens": args.tokens, "embed_dim": args.dim, "heads": args.heads,
+                        + (f"B={args.global_batch} in total over {n_gpus} GPUs" if strong else f"B={args.batch} per GPU")
+                        + f", {args.dtype} (BASELINE.json configs[1])",
+            "global_batch": args.global_batch if strong else args.batch * n_gpus,
+            "tokens": args.tokens, "embed_dim": args.dim, "heads": args.heads,
             "dropout": args.dropout, "parallelism": f"dp{n_gpus}",
             "fold_key_projection": bool(getattr(args, "folded", False)),
-            "l2": "inputs larger than L2 (x 201 MB, values 201 MB per step vs 126 MB L2); no flush needed",
+            "l2": l2,
             "step": "forward(return_info) + entropy_loss + backward(d_out), public module API"
                     + (", captured once with aecf_b200.graphs.GraphedStep and replayed" if getattr(args, "graph", "off") == "on"
                        and getattr(args, "impl", "b200") == "b200" else "")}
@@ -275,7 +296,14 @@ def run_b200(args):
         guard.start()
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     es = 2 if dtype == torch.bfloat16 else 4
+    strong = args.global_batch > 0
+    if strong:                                         # strong scaling: a fixed global batch, sharded over the ranks
+        from aecf_b200.dp import shard_rows
+        args.batch = shard_rows(args.global_batch, rank, world)[1]
+        if args.batch == 0:
+            raise SystemExit(f"--global-batch {args.global_batch} leaves rank {rank} of {world} without rows")
     B, M, D, H = args.batch, args.tokens, args.dim, args.heads
+    total_rows = args.global_batch if strong else B * world
 
     torch.manual_seed(0)
     query, pool = aecf_b200.create_fusion_pool(D, M, 0.15, num_heads=H, dropout=args.dropout, device=dev, dtype=dtype)
@@ -283,9 +311,13 @@ def run_b200(args):
     pool.fold_key_projection = {"auto": None, "on": True, "off": False}[args.fold]
     args.folded = (dtype == torch.bfloat16 and os.environ.get("AECF_FOLD", "1") != "0") if args.fold == "auto" else args.fold == "on"
     sync = GradientSync(pool, query).attach()
-    sync.set_shard(B * world)                                     # Philox keyed on the global row
+    sync.set_shard(total_rows)                                    # Philox keyed on the global row
     torch.manual_seed(1234 + rank)
-    x = torch.randn(B, M, D, device=dev, dtype=dtype).requires_grad_(True)
+    # one input batch when it is larger than the L2 (the default workload); otherwise the timed steps rotate over
+    # enough batches that none is found in L2 (input_buffers_needed)
+    rot = input_buffers_needed(B * M * D * es)
+    xs = [torch.randn(B, M, D, device=dev, dtype=dtype).requires_grad_(True) for _ in range(rot)]
+    x = xs[0]
     d_out = torch.randn(B, 1, D, device=dev, dtype=dtype)
 
     def step(xin):
@@ -296,7 +328,8 @@ def run_b200(args):
         return loss
 
     def clear():
-        x.grad = None
+        for xi in xs:
+            xi.grad = None
         query.grad = None
         pool.zero_grad(set_to_none=True)
 
@@ -316,15 +349,23 @@ def run_b200(args):
         step(x); clear()
     barrier()
     launches0 = _lib.launch_count()
+    turn = [0]
     if use_graph:
-        graphed = aecf_b200.graphs.GraphedStep(lambda: step(x), reset=clear, warmup=0, device=dev)
-        launches_per_step = _lib.launch_count() - launches0              # counted while capturing one step
-        for _ in range(args.warmup):
-            graphed()
-        run_step = graphed
+        graphs = []                                                      # one graph per input batch
+        for xi in xs:
+            graphs.append(aecf_b200.graphs.GraphedStep(lambda xi=xi: step(xi), reset=clear, warmup=0, device=dev))
+            if len(graphs) == 1:
+                launches_per_step = _lib.launch_count() - launches0      # counted while capturing one step
+        for i in range(max(args.warmup, rot)):
+            graphs[i % rot]()
+
+        def run_step():
+            graphs[turn[0] % rot]()
+            turn[0] += 1
     else:
         def run_step():
-            step(x); clear()
+            step(xs[turn[0] % rot]); clear()
+            turn[0] += 1
     barrier()
     launches0 = _lib.launch_count()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -342,8 +383,8 @@ def run_b200(args):
         _lib.timing_enable(True)
         start_b, end_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start_b.record()
-        for _ in range(args.steps):
-            step(x); clear()
+        for i in range(args.steps):
+            step(xs[i % rot]); clear()
         end_b.record()
         barrier()
     ms_with_events = start_b.elapsed_time(end_b) / args.steps
@@ -391,12 +432,12 @@ def run_b200(args):
             other = variant(lambda: setattr(sync, "overlap", not was), lambda: setattr(sync, "overlap", was))
             dp_info["other_mode"] = {"all_reduce": "one call after the backward" if was else "overlapped on a side stream",
                                      "per_rank_ms": other, "ms_per_step": max(other),
-                                     "value": B * world / (max(other) * 1e-3)}
+                                     "value": total_rows / (max(other) * 1e-3)}
             # no collective at all: what rank-to-rank variance alone costs
             alone = variant(lambda: setattr(sync, "enabled", False), lambda: setattr(sync, "enabled", True))
             dp_info["no_all_reduce"] = {"per_rank_ms": alone, "ms_per_step": max(alone),
-                                        "value": B * world / (max(alone) * 1e-3)}
-    value = B * world / (ms * 1e-3)
+                                        "value": total_rows / (max(alone) * 1e-3)}
+    value = total_rows / (ms * 1e-3)
 
     # ---- end to end: batch starts in pinned host memory every step -----------------------------
     e2e = None
@@ -459,8 +500,8 @@ def run_b200(args):
             t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_ms = float(t.item())
-        e2e = {"value": B * world / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": B * M * D * es * world, "d2h_bytes_per_step": 4 * world,
+        e2e = {"value": total_rows / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": total_rows * M * D * es, "d2h_bytes_per_step": 4 * world,
                "note": "host batch -> double-buffered H2D on a copy stream -> step -> loss scalar D2H"}
 
     if rank != 0:
@@ -510,7 +551,7 @@ def run_b200(args):
     pool_ms = sum(kernels[k]["ms"] for k in ("pool_fwd", "pool_bwd") if k in kernels)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "bf16" if dtype == torch.bfloat16 else "f32", "data": "synthetic",
             "config": workload_config(args, world), "impl": "b200",
             "roofline": roof, "roofline_pool_fwd": hbm("pool_fwd", fwd_bytes),
