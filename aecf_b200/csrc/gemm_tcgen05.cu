@@ -645,212 +645,24 @@ template <int BN> struct Cfg2 {
     static constexpr int SMEM_BYTES = STAGES_2SM * STAGE_BYTES + EPI_BYTES + 1024 + 256;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tcgen05_2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                        const __grid_constant__ CUtensorMap map_c, const Params p) {
-    using C = Cfg2<BN>;
-    constexpr int S = STAGES_2SM;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* stage_base = smem;
-    uint8_t* epi_base = smem + S * C::STAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_base + C::EPI_BYTES);
-    uint64_t* full = bars;                    // [S]  leader's copy is the live one: bytes of BOTH CTAs' loads
-    uint64_t* empty = bars + S;               // [S]  per CTA, freed by the leader's MMA commit (multicast)
-    uint64_t* tmem_full = bars + 2 * S;       // [2]  per CTA, leader's MMA commit (multicast)
-    uint64_t* tmem_empty = bars + 2 * S + 2;  // [2]  leader's copy: both CTAs' epilogue threads arrive
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
-    __shared__ float bias_tile[BN];
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int items = p.groups_m * p.tiles_n * p.splits;
-    const int cta_rank = static_cast<int>(cluster_ctarank());
-    const bool leader = cta_rank == 0;
-    const int first_item = blockIdx.x / 2, item_stride = gridDim.x / 2;
-
-    if (warp == 0 && lane == 0) {
-        prefetch_tmap(&map_a); prefetch_tmap(&map_b); prefetch_tmap(&map_c);
-        for (int i = 0; i < S; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * EPI_THREADS); }
-        fence_barrier_init();
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
-                     :: "r"(smem_u32(tmem_slot)), "r"(static_cast<uint32_t>(C::TMEM_COLS)) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync_all();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    pdl_wait();
-
-    if (warp == 0) {
-        // ===== TMA producer (both CTAs; the leader also arms the barrier for both CTAs' bytes); whole warp, one elected lane =====
-        int it = 0;
-        for (int item = first_item; item < items; item += item_stride) {
-            const WorkItem w = decode<2>(p, item, cta_rank);
-            for (int kb = 0; kb < w.kb_count; ++kb, ++it) {
-                const int s = it % S;
-                mbar_wait_cluster(&empty[s], ((it / S) & 1) ^ 1);
-                if (elect_one()) {
-                    uint8_t* a_dst = stage_base + s * C::STAGE_BYTES;
-                    uint8_t* b_dst = a_dst + C::A_BYTES;
-                    if (leader) mbar_expect_tx(&full[s], 2 * C::STAGE_BYTES);
-                    const int k0 = (w.kb_begin + kb) * BK;
-                    if (!p.a_mn_major) {
-                        tma_load_2d_2sm(&map_a, &full[s], a_dst, k0, w.m_blk * BM);
-                    } else {
-#pragma unroll
-                        for (int a = 0; a < BM / 64; ++a)
-                            tma_load_2d_2sm(&map_a, &full[s], a_dst + a * (BK * 128), w.m_blk * BM + a * 64, k0);
-                    }
-                    const int n_half = w.n_blk * BN + cta_rank * (BN / 2);
-                    if (!p.b_mn_major) {
-                        tma_load_2d_2sm(&map_b, &full[s], b_dst, k0, n_half);
-                    } else {
-#pragma unroll
-                        for (int a = 0; a < BN / 128; ++a)
-                            tma_load_2d_2sm(&map_b, &full[s], b_dst + a * (BK * 128), n_half + a * 64, k0);
-                    }
-                }
-                __syncwarp();
-            }
-        }
-    } else if (warp == 1) {
-        // ===== MMA issuer: leader CTA only, one instruction drives both SMs' tensor cores; whole warp, one elected lane =====
-        if (leader) {
-            // M = 256: m_dim field = 256 >> 4
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(p.a_mn_major) << 15) |
-                                   (static_cast<uint32_t>(p.b_mn_major) << 16) | (static_cast<uint32_t>(BN >> 3) << 17) |
-                                   (static_cast<uint32_t>(256 >> 4) << 24);
-            const uint32_t stage0 = smem_u32(stage_base);
-            const uint64_t a_desc0 = operand_desc(stage0, p.a_mn_major, 0);
-            const uint64_t b_desc0 = operand_desc(stage0 + C::A_BYTES, p.b_mn_major, 0);
-            const uint32_t a_ks = k_slice_bytes(p.a_mn_major), b_ks = k_slice_bytes(p.b_mn_major);
-            int it = 0, tile_it = 0;
-            for (int item = first_item; item < items; item += item_stride, ++tile_it) {
-                const WorkItem w = decode<2>(p, item, cta_rank);
-                const int as = tile_it & 1;
-                mbar_wait_cluster(&tmem_empty[as], ((tile_it >> 1) & 1) ^ 1);   // both CTAs drained this accumulator
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + as * BN;
-                for (int kb = 0; kb < w.kb_count; ++kb, ++it) {
-                    const int s = it % S;
-                    mbar_wait_cluster(&full[s], (it / S) & 1);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        const uint64_t a_d = desc_advance(a_desc0, s * C::STAGE_BYTES);
-                        const uint64_t b_d = desc_advance(b_desc0, s * C::STAGE_BYTES);
-#pragma unroll
-                        for (int ks = 0; ks < BK / UMMA_K; ++ks)
-                            umma_bf16_2sm(tmem_d, desc_advance(a_d, ks * a_ks), desc_advance(b_d, ks * b_ks), idesc,
-                                          (kb | ks) != 0 ? 1u : 0u);
-                        umma_commit_2sm(&empty[s], 0b11);                          // frees the slot in both CTAs
-                    }
-                    __syncwarp();
-                }
-                if (elect_one()) umma_commit_2sm(&tmem_full[as], 0b11);            // accumulator complete in both CTAs
-                __syncwarp();
-            }
-        }
-    } else {
-        // ===== epilogue: each CTA drains its own 128 rows =====
-        const int quad = warp & 3;
-        const int row = quad * 32 + lane;
-        const int et = threadIdx.x - 64;
-        int tile_it = 0, round_it = 0;
-        for (int item = first_item; item < items; item += item_stride, ++tile_it) {
-            const WorkItem w = decode<2>(p, item, cta_rank);
-            const int as = tile_it & 1;
-            const int n0 = w.n_blk * BN, m0 = w.m_blk * BM;
-            const bool tile_valid = w.m_blk < p.tiles_m;
-            const bool direct = (p.splits == 1);
-            if (direct && p.has_bias) {
-                for (int i = et; i < BN; i += EPI_THREADS) {
-                    const int col = n0 + i;
-                    float b = 0.f;
-                    if (col < p.c_cols)
-                        b = p.bias_is_bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(p.bias)[col])
-                                           : static_cast<const float*>(p.bias)[col];
-                    bias_tile[i] = b;
-                }
-            }
-            mbar_wait_cluster(&tmem_full[as], (tile_it >> 1) & 1);
-            tc_fence_after();
-            const uint32_t t_row = tmem_base + as * BN + (static_cast<uint32_t>(quad * 32) << 16);
-            const int out_row0 = (direct ? 0 : w.split * p.partial_rows) + m0;
-            const int cols_per_round = p.c_is_f32 ? 64 : 128;
-            const int rounds = BN / cols_per_round;
-#pragma unroll 1
-            for (int rd = 0; rd < rounds; ++rd, ++round_it) {
-                uint8_t* stage_buf = epi_base + (round_it & 1) * C::EPI_BUF;
-                if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store 2 rounds ago has left this buffer
-                asm volatile("bar.sync 1, %0;" :: "n"(EPI_THREADS) : "memory");
-                const int col_in_tile = rd * cols_per_round;
-#pragma unroll 1
-                for (int g = 0; g < cols_per_round / 32; ++g) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(t_row + col_in_tile + g * 32, r);
-                    tmem_ld_wait();
-                    float v[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        v[i] = __uint_as_float(r[i]);
-                        if (direct && p.has_bias) v[i] += bias_tile[col_in_tile + g * 32 + i];
-                    }
-                    if (p.c_is_f32) {
-                        uint8_t* box = stage_buf + g * (BM * 128) + row * 128;
-#pragma unroll
-                        for (int c = 0; c < 8; ++c)
-                            *reinterpret_cast<uint4*>(box + ((c ^ (row & 7)) << 4)) =
-                                make_uint4(__float_as_uint(v[4 * c]), __float_as_uint(v[4 * c + 1]),
-                                           __float_as_uint(v[4 * c + 2]), __float_as_uint(v[4 * c + 3]));
-                    } else {
-                        uint8_t* box = stage_buf + (g >> 1) * (BM * 128) + row * 128;
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const int chunk = (g & 1) * 4 + c;
-                            *reinterpret_cast<uint4*>(box + ((chunk ^ (row & 7)) << 4)) =
-                                make_uint4(Vec<__nv_bfloat16>::pack2(v[8 * c], v[8 * c + 1]),
-                                           Vec<__nv_bfloat16>::pack2(v[8 * c + 2], v[8 * c + 3]),
-                                           Vec<__nv_bfloat16>::pack2(v[8 * c + 4], v[8 * c + 5]),
-                                           Vec<__nv_bfloat16>::pack2(v[8 * c + 6], v[8 * c + 7]));
-                        }
-                    }
-                }
-                if (rd == rounds - 1) {                      // this thread's TMEM reads are done: tell the LEADER's MMA
-                    tc_fence_before();
-                    mbar_arrive_on_cta(&tmem_empty[as], 0);
-                }
-                fence_proxy_async();
-                asm volatile("bar.sync 1, %0;" :: "n"(EPI_THREADS) : "memory");
-                if (et == 0 && tile_valid) {
-                    const int col0 = n0 + col_in_tile;
-                    const int box_cols = p.c_is_f32 ? 32 : 64;
-#pragma unroll
-                    for (int g = 0; g < 2; ++g)
-                        if (col0 + g * box_cols < p.c_cols)
-                            tma_store_2d(&map_c, stage_buf + g * (BM * 128), col0 + g * box_cols, out_row0);
-                    tma_store_commit();
-                }
-            }
-        }
-        if (et == 0) tma_store_wait_all();
-    }
-
-    __syncwarp();
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync_all();
-    if (warp == 1) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;"
-                     :: "r"(tmem_base), "r"(static_cast<uint32_t>(C::TMEM_COLS)) : "memory");
-    }
-}
+#define AECF_2SM_KERNEL gemm_tcgen05_2sm_kernel
+#define AECF_2SM_THREADS NUM_THREADS
+#define AECF_2SM_EW 4
+#define AECF_2SM_EPI_T EPI_THREADS
+#include "gemm_tcgen05_2sm.inc"
+#undef AECF_2SM_KERNEL
+#undef AECF_2SM_THREADS
+#undef AECF_2SM_EW
+#undef AECF_2SM_EPI_T
+#define AECF_2SM_KERNEL gemm_tcgen05_2sm_ew8_kernel
+#define AECF_2SM_THREADS (NUM_THREADS + 128)
+#define AECF_2SM_EW 8
+#define AECF_2SM_EPI_T 256
+#include "gemm_tcgen05_2sm.inc"
+#undef AECF_2SM_KERNEL
+#undef AECF_2SM_THREADS
+#undef AECF_2SM_EW
+#undef AECF_2SM_EPI_T
 
 // ---- host side -------------------------------------------------------------------------------
 using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -1015,8 +827,10 @@ int gemm_tcgen05(const aecf_gemm_desc* d, const void* A, const void* B, const vo
         AECF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN_>::SMEM_BYTES)); \
         AECF_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, map_a, map_b, map_c, p));                                   \
     } while (0)
+    static const bool two_sm_ew8 = [] { const char* e = getenv("AECF_GEMM_2SM_EW"); return e && e[0] == '8'; }();
     if (pl.two_sm) {
-        auto kernel = gemm_tcgen05_2sm_kernel<256>;
+        auto kernel = two_sm_ew8 ? gemm_tcgen05_2sm_ew8_kernel<256> : gemm_tcgen05_2sm_kernel<256>;
+        if (two_sm_ew8) cfg.blockDim = dim3(NUM_THREADS + 128);
         cfg.dynamicSmemBytes = Cfg2<256>::SMEM_BYTES;
         AECF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<256>::SMEM_BYTES));
         AECF_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, map_a, map_b, map_c, p));

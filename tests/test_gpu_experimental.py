@@ -36,3 +36,10 @@ def test_eight_warp_gemm_epilogue_passes_the_gemm_and_parity_suites():
     _pytest_with({"AECF_GEMM_EPI": "3"},
                  ["tests/test_gpu_gemm_tcgen05.py", "tests/test_gpu_parity.py", "-k",
                   "gemm or side_output or bf16 or folded or headline or sharding"])
+
+
+def test_eight_warp_epilogue_of_the_cta_pair_kernel_passes_the_gemm_and_parity_suites():
+    """AECF_GEMM_2SM_EW=8: the cta_group::2 kernel with two epilogue warps per TMEM lane quadrant (gemm_tcgen05_2sm.inc)."""
+    _pytest_with({"AECF_GEMM_2SM_EW": "8"},
+                 ["tests/test_gpu_gemm_tcgen05.py", "tests/test_gpu_parity.py", "-k",
+                  "gemm or side_output or bf16 or folded or headline or sharding"])
