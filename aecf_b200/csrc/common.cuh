@@ -1,8 +1,16 @@
 // Shared device/host helpers for the aecf_b200 kernels (sm_100a only).
 #pragma once
 
+// AECF_CUDA_EMU: the test-only host emulation of tests/cuda_emu (these sources compiled by g++ and run as fibers on
+// the CPU, so that `-m "not gpu"` tests exercise the kernels' logic and the host code around them).  It is never
+// defined in the library build; every `#ifdef AECF_CUDA_EMU` below is the emulation's stand-in for an inline-PTX
+// wrapper or a launch, and the other branch is the product, token for token what it was before the split.
+#ifdef AECF_CUDA_EMU
+#include "cuda_emu.h"
+#else
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#endif
 #include <stdint.h>
 #include <math.h>
 
@@ -53,6 +61,18 @@ int launch_query_tail(int dtype, int D, const float* d_qp, const void* q0, const
 // overlap that tail), but nothing touches global memory before the previous kernel has completed and
 // flushed.  AECF_PDL=0 in the environment falls back to ordinary launches.
 bool pdl_enabled();
+#ifdef AECF_CUDA_EMU
+__device__ __forceinline__ void pdl_wait() {}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t, Args&&... args) {
+    return cuda_emu::launch(kernel, grid, block, smem, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_plain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t, Args&&... args) {
+    return cuda_emu::launch(kernel, grid, block, smem, static_cast<KArgs>(args)...);
+}
+#else
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 template <typename... KArgs, typename... Args>
@@ -67,6 +87,23 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+// An ordinary launch (kernels that do not start with pdl_wait()).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_plain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                Args&&... args) {
+    kernel<<<grid, block, smem, stream>>>(static_cast<KArgs>(args)...);
+    return cudaGetLastError();
+}
+#endif
+
+// Dynamic shared memory of a kernel.  The emulation points it at one host buffer (blocks run one at a time).
+#ifdef AECF_CUDA_EMU
+#define AECF_DYNAMIC_SMEM(type, name) type* name = reinterpret_cast<type*>(cuda_emu::dynamic_smem())
+#define AECF_DYNAMIC_SMEM_ALIGNED16(type, name) type* name = reinterpret_cast<type*>(cuda_emu::dynamic_smem())
+#else
+#define AECF_DYNAMIC_SMEM(type, name) extern __shared__ type name[]
+#define AECF_DYNAMIC_SMEM_ALIGNED16(type, name) extern __shared__ __align__(16) type name[]
+#endif
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -96,15 +133,26 @@ template <> struct Vec<__nv_bfloat16> {
         }
     }
     static __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+#ifdef AECF_CUDA_EMU
+        return cuda_emu::bf16_bits(lo) | (cuda_emu::bf16_bits(hi) << 16);
+#else
         uint32_t r;   // cvt.rn.bf16x2.f32 d, a, b  puts a in the upper half
         asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
         return r;
+#endif
     }
     static __device__ __forceinline__ uint4 pack(const float (&f)[8]) {
         return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
     }
 };
 
+#ifdef AECF_CUDA_EMU
+__device__ __forceinline__ uint4 ldg_stream(const void* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void stg_stream(void* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) { memcpy(smem_dst, gmem_src, 16); }
+__device__ __forceinline__ void cp_async_commit() {}
+template <int N> __device__ __forceinline__ void cp_async_wait() {}
+#else
 // Streaming 128-bit load of read-once data: read-only path, do not allocate in L1.
 __device__ __forceinline__ uint4 ldg_stream(const void* p) {
     uint4 r;
@@ -112,12 +160,14 @@ __device__ __forceinline__ uint4 ldg_stream(const void* p) {
         : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
+#endif
 __device__ __forceinline__ uint4 ldg_cached(const void* p) {
     return __ldg(reinterpret_cast<const uint4*>(p));
 }
 __device__ __forceinline__ void stg_vec(void* p, const uint4& v) {
     *reinterpret_cast<uint4*>(p) = v;
 }
+#ifndef AECF_CUDA_EMU
 // Streaming store: written once, consumed by a later kernel from HBM/L2.
 __device__ __forceinline__ void stg_stream(void* p, const uint4& v) {
     asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};"
@@ -131,6 +181,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+#endif
 
 template <typename T> __device__ __forceinline__ float to_float(T v);
 template <> __device__ __forceinline__ float to_float<float>(float v) { return v; }

@@ -292,8 +292,8 @@ static int launch_sdpa(const void* q, const void* k, const void* v, void* out, l
     const float scale = static_cast<float>(1.0 / std::sqrt(static_cast<double>(D)));   // query.size(-1) ** -0.5 (:574)
     const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
 #define AECF_SDPA(JM)                                                                                        \
-    sdpa_fwd_kernel<T, JM><<<grid, 256, 0, s>>>(static_cast<const T*>(q), static_cast<const T*>(k),           \
-                                               static_cast<const T*>(v), static_cast<T*>(out), rows, tgt, src, D, scale)
+    AECF_CUDA_OK(launch_plain(sdpa_fwd_kernel<T, JM>, dim3(grid), dim3(256), 0, s, static_cast<const T*>(q),   \
+                              static_cast<const T*>(k), static_cast<const T*>(v), static_cast<T*>(out), rows, tgt, src, D, scale))
     if (NC <= 32) AECF_SDPA(1);
     else if (NC <= 64) AECF_SDPA(2);
     else if (NC <= 128) AECF_SDPA(4);
@@ -301,7 +301,6 @@ static int launch_sdpa(const void* q, const void* k, const void* v, void* out, l
     else return AECF_ERR_UNSUPPORTED;
 #undef AECF_SDPA
     count_launch();
-    AECF_CUDA_OK(cudaGetLastError());
     return AECF_OK;
 }
 
@@ -365,10 +364,9 @@ int aecf_entropy_loss_bwd(int32_t device, const float* entropy, int64_t n, float
     if (!entropy || !d_loss || !d_entropy || n <= 0) return AECF_ERR_INVALID;
     int rc = use_device(device);
     if (rc != AECF_OK) return rc;
-    entropy_loss_bwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        entropy, n, target, d_loss, d_entropy);
+    AECF_CUDA_OK(launch_plain(entropy_loss_bwd_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0,
+                              static_cast<cudaStream_t>(stream), entropy, static_cast<long long>(n), target, d_loss, d_entropy));
     count_launch();
-    AECF_CUDA_OK(cudaGetLastError());
     return AECF_OK;
 }
 
@@ -384,10 +382,10 @@ int aecf_curriculum_mask(int32_t device, const float* weights, int64_t rows, int
     rng.k0 = static_cast<uint32_t>(seed); rng.k1 = static_cast<uint32_t>(seed >> 32);
     rng.offset = static_cast<uint32_t>(offset); rng.row0 = row0;
     const float log_len = static_cast<float>(std::log(static_cast<double>(len)));
-    curriculum_mask_kernel<<<static_cast<unsigned>((rows + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-        weights, rows, len, mode, base_mask_prob, min_active, log_len, rng, masked, entropy, mask_rate);
+    AECF_CUDA_OK(launch_plain(curriculum_mask_kernel, dim3(static_cast<unsigned>((rows + 127) / 128)), dim3(128), 0,
+                              static_cast<cudaStream_t>(stream), weights, static_cast<long long>(rows), len, mode, base_mask_prob,
+                              min_active, log_len, rng, masked, entropy, mask_rate));
     count_launch();
-    AECF_CUDA_OK(cudaGetLastError());
     return AECF_OK;
 }
 
@@ -399,10 +397,10 @@ int aecf_entropy_bwd(int32_t device, const float* weights, int64_t rows, int32_t
     int rc = use_device(device);
     if (rc != AECF_OK) return rc;
     const float log_len = static_cast<float>(std::log(static_cast<double>(len)));
-    entropy_bwd_kernel<<<static_cast<unsigned>((rows + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-        weights, rows, len, log_len, d_entropy, d_weights);
+    AECF_CUDA_OK(launch_plain(entropy_bwd_kernel, dim3(static_cast<unsigned>((rows + 127) / 128)), dim3(128), 0,
+                              static_cast<cudaStream_t>(stream), weights, static_cast<long long>(rows), len, log_len, d_entropy,
+                              d_weights));
     count_launch();
-    AECF_CUDA_OK(cudaGetLastError());
     return AECF_OK;
 }
 

@@ -45,7 +45,7 @@ pool_bwd_kernel(const PoolParams p) {
     // backward; it is re-read through L1 (the first read allocates there) rather than held in registers.
     constexpr bool PRELOAD_V = (M * J <= 8);
 
-    extern __shared__ __align__(16) float smem[];
+    AECF_DYNAMIC_SMEM_ALIGNED16(float, smem);
     float* xchg = smem;                                               // [POOL_WARPS][M]
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;

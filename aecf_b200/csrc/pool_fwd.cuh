@@ -169,11 +169,16 @@ pool_fwd_kernel(const PoolParams p) {
 #pragma unroll
         for (int m = 0; m < M; ++m) head_sums[slot * M + m] = total[m];
     }
+#ifdef AECF_CUDA_EMU
+    if (warp != 0) { cuda_emu::named_barrier(1, POOL_WARPS * 32, false); return; }
+    cuda_emu::named_barrier(1, POOL_WARPS * 32, true);
+#else
     if (warp != 0) {                                   // hand over and retire; warp 0 finishes the CTA's samples
         asm volatile("bar.arrive 1, %0;" :: "n"(POOL_WARPS * 32) : "memory");
         return;
     }
     asm volatile("bar.sync 1, %0;" :: "n"(POOL_WARPS * 32) : "memory");
+#endif
 
     // ---- head mean (torch/nn/functional.py:6657-6659) and CurriculumMasking, one sample per lane -------
     const long long my_row = row0 + lane;
@@ -209,7 +214,7 @@ pool_fwd_stream_kernel(const PoolParams p, const long long rows_per_warp) {
     constexpr int HALVES = FOLD ? 1 : 2;                // folded: only the values are staged
     constexpr int VHALF = FOLD ? 0 : 1;
     constexpr int CH = M * HALVES * J;                  // 16-byte chunks per lane per sample
-    extern __shared__ uint4 ring[];                     // [warps][2 stages][CH][32 lanes]
+    AECF_DYNAMIC_SMEM(uint4, ring);                     // [warps][2 stages][CH][32 lanes]
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const long long gw = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp;

@@ -133,7 +133,7 @@ pool_bwd_multi_kernel(const PoolParams p, const MultiQuery mq) {
     constexpr int V = Core::V;
     constexpr int Q4 = V / 4;
 
-    extern __shared__ __align__(16) float smem[];
+    AECF_DYNAMIC_SMEM_ALIGNED16(float, smem);
     float* xchg = smem;                                               // [POOL_WARPS][M]
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;

@@ -142,7 +142,8 @@ def pool_forward(query: Tensor, key: Tensor, value: Optional[Tensor],
                  u_drop: Optional[Tensor] = None, u_mask: Optional[Tensor] = None,
                  score_bias: Optional[Tensor] = None,
                  masking: Optional[dict] = None,
-                 storage: Optional[torch.dtype] = None, fold_key: bool = False) -> PoolResult:
+                 storage: Optional[torch.dtype] = None, fold_key: bool = False,
+                 per_row_query_storage: bool = False) -> PoolResult:
     """MultimodalAttentionPool.forward, batch_first -- reference aecf/AECFLayer.py:409-547
     over torch/nn/functional.py:5847-5865 and :6630-6659.
 
@@ -159,6 +160,8 @@ def pool_forward(query: Tensor, key: Tensor, value: Optional[Tensor],
     scores are associated as x . (scale * Wk_h^T q_h) with that per-head vector rounded to ``storage``
     and the key bias dropped (it shifts every token of a head alike, so the softmax does not see it);
     mathematically identical to the reference's (x Wk^T + bk) . (scale q_h), the rounding differs.
+    ``per_row_query_storage``: with per-row queries the CUDA path keeps the projected queries (and, in the backward,
+    their gradients) in ``storage`` too; the one shared fusion query of the hot path stays fp32.
     """
     if value is None:
         value = key
@@ -174,6 +177,8 @@ def pool_forward(query: Tensor, key: Tensor, value: Optional[Tensor],
 
     lin = torch.nn.functional.linear
     qp = lin(query, Wq, bq)                                      # functional.py:5854
+    if per_row_query_storage:
+        qp = _round(qp, storage)
     k = _round(lin(key, Wk, bk), storage)                        # :5855 (K half)
     v = _round(lin(value, Wv, bv), storage)                      # :5855 (V half)
 
@@ -227,7 +232,8 @@ def pool_backward(query: Tensor, key: Tensor, value: Optional[Tensor],
                   saved: Dict[str, Tensor], grad_out: Tensor, *,
                   grad_pooled: Optional[Tensor] = None, grad_entropy: Optional[Tensor] = None,
                   dropout_p: float = 0.0, training: bool = True, has_bias: bool = True,
-                  storage: Optional[torch.dtype] = None, fold_key: bool = False) -> Dict[str, Tensor]:
+                  storage: Optional[torch.dtype] = None, fold_key: bool = False,
+                  per_row_query_storage: bool = False) -> Dict[str, Tensor]:
     """Closed-form backward of pool_forward.
 
     The reference has no backward source: it is autograd over
@@ -287,6 +293,8 @@ def pool_backward(query: Tensor, key: Tensor, value: Optional[Tensor],
     d_k = _round(d_k.reshape(B, M, D), storage)
     d_v = _round(d_v.reshape(B, M, D), storage)
     d_qp = d_qh.reshape(B * S, D)
+    if per_row_query_storage:
+        d_qp = _round(d_qp, storage)
 
     grads = {
         "out_proj.weight": d_wo, "out_proj.bias": d_bo,

@@ -41,12 +41,13 @@ def run_oracle(case: Case, inp: Optional[dict] = None, dtype: Optional[torch.dty
         inp["out_proj.weight"], inp["out_proj.bias"], case.H,
         dropout_p=case.dropout, training=case.training, u_drop=inp["u_drop"], u_mask=inp["u_mask"],
         score_bias=score_bias_from_kpm(inp.get("key_padding_mask"), inp["x"].dtype),
-        masking=masking_kwargs(case), storage=storage, fold_key=fold_key)
+        masking=masking_kwargs(case), storage=storage, fold_key=fold_key, per_row_query_storage=S > 1)
     grads = oracle.pool_backward(
         q, inp["x"], value, inp["in_proj_weight"], inp["out_proj.weight"], case.H, fwd.saved,
         inp["grad_out"], grad_pooled=inp["grad_pooled"] if case.pooled_grad else None,
         grad_entropy=None if case.training else torch.full((B, S), 0.5, dtype=inp["x"].dtype),
-        dropout_p=case.dropout, training=case.training, storage=storage, fold_key=fold_key)
+        dropout_p=case.dropout, training=case.training, storage=storage, fold_key=fold_key,
+        per_row_query_storage=S > 1)
     if S == 1:
         grads["query0"] = grads.pop("query").sum(0, keepdim=True)
     return fwd, grads

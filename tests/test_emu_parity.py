@@ -1,0 +1,138 @@
+"""The CUDA sources, run on the CPU by the host emulation (tests/cuda_emu), through the public module API and the
+C ABI, against the oracle and the reference's fixtures: the bodies of the GPU parity tests, called on CPU tensors.
+
+Covers what the emulation can see -- indexing, lane/head geometry for every (M, J, warps-per-sample) the cases reach,
+reductions, the masking stage bit for bit, the Philox stream, the host-side sequencing of the whole-step entry points
+(folded and unfolded, one and several queries per sample), the SIMT GEMM / GEMV kernels -- and nothing it cannot
+(tcgen05 / TMA, memory-model races, performance).  Small shapes: a block's threads are fibers.
+"""
+import pytest
+import torch
+
+import aecf_b200
+from aecf_b200 import _lib
+from oracle import aecf_oracle as oracle
+from oracle import philox
+from tests import test_gpu_multi_query as MQ
+from tests import test_gpu_parity as P
+from tests.emu_support import cuda_emulation  # noqa: F401  (fixture)
+from tests.golden.cases import MULTI_QUERY_CASES
+from tests.helpers import assert_close
+
+pytestmark = pytest.mark.usefixtures("cuda_emulation")
+
+
+@pytest.fixture(autouse=True)
+def _cpu_stands_in_for_the_device(monkeypatch):
+    """The GPU tests say ``t.to(DEV)`` and get a copy; ``t.to("cpu")`` of a CPU tensor is the tensor itself, which would
+    alias a case's inputs with the tensors that collect gradients.  Make it a copy here too."""
+    monkeypatch.setattr(P, "DEV", "cpu")
+    monkeypatch.setattr(MQ, "DEV", "cpu")
+    plain_to = torch.Tensor.to
+
+    def to_copy(self, *args, **kwargs):
+        moved = plain_to(self, *args, **kwargs)
+        return moved.clone() if moved is self else moved
+
+    monkeypatch.setattr(torch.Tensor, "to", to_copy)
+
+
+by_name = lambda c: c.name   # noqa: E731
+
+
+# ---- one fusion query per sample (the hot path's kernels) --------------------------------------------------------
+@pytest.mark.parametrize("case", P.FP32_CASES, ids=by_name)
+def test_fp32_matches_oracle(case):
+    P.test_fp32_matches_oracle(case)
+
+
+@pytest.mark.parametrize("case", P.FP32_CASES[1:6], ids=by_name)
+def test_fp32_matches_reference_golden(case):
+    P.test_fp32_matches_reference_golden(case)
+
+
+@pytest.mark.parametrize("case", P.FOLDABLE_FP32_CASES, ids=by_name)
+def test_fp32_folded_key_projection_matches_oracle(case):
+    P.test_fp32_folded_key_projection_matches_oracle(case)
+
+
+@pytest.mark.parametrize("fold", [True, False], ids=["folded", "unfolded"])
+@pytest.mark.parametrize("case", P.BF16_CASES, ids=by_name)
+def test_bf16_masks_exact_against_stage_rounded_oracle(case, fold):
+    P.test_bf16_masks_exact_against_stage_rounded_oracle(case, fold)
+
+
+@pytest.mark.parametrize("fold", [True, False], ids=["folded", "unfolded"])
+@pytest.mark.parametrize("case", P.BF16_CASES[1:4], ids=by_name)
+def test_bf16_matches_fp32_math_oracle(case, fold):
+    P.test_bf16_matches_fp32_math_oracle(case, fold)
+
+
+WIDE = {c.name: c for c in P.WIDE_CASES}
+
+
+@pytest.mark.parametrize("name,dtype", [("wide_d1024_h8_m3", torch.float32), ("wide_d1024_h8_m3", torch.bfloat16),
+                                        ("wide_d1024_h4_m4_eval", torch.bfloat16), ("wide_d512_h8_m5_kpm", torch.float32),
+                                        ("wide_d512_h8_m5_kpm", torch.bfloat16)])
+def test_rows_spanning_several_warps(name, dtype):
+    P.test_wide_rows_span_several_warps(WIDE[name], dtype)
+
+
+@pytest.mark.parametrize("name", ["wide_d1024_h4_m4_eval", "wide_d512_h8_m5_kpm"])
+def test_rows_spanning_several_warps_folded_fp32(name):
+    P.test_wide_rows_folded_fp32(WIDE[name])
+
+
+@pytest.mark.parametrize("test", [P.test_sequence_first_layout_matches_batch_first, P.test_per_row_queries_match_oracle,
+                                  P.test_attn_mask_forms_match_oracle, P.test_no_masking_module_and_plain_output,
+                                  P.test_standalone_masking_and_entropy, P.test_entropy_loss_gradient_in_eval_mode,
+                                  P.test_colsum], ids=lambda f: f.__name__[5:])
+def test_module_surface(test):
+    test()
+
+
+def test_functional_fast_path():
+    q = torch.from_numpy(philox.normal(1, (6, 2, 64))).float()
+    k = torch.from_numpy(philox.normal(2, (6, 5, 64))).float()
+    assert_close("sdpa", aecf_b200.multimodal_attention_pool(q, k), oracle.sdpa_single_head(q, k, k), 1e-5)
+    got = aecf_b200.multimodal_attention_pool(q.bfloat16(), k.bfloat16()).float()
+    assert_close("sdpa bf16", got, oracle.sdpa_single_head(q.bfloat16().float(), k.bfloat16().float(), k.bfloat16().float()), 2e-2)
+
+
+# ---- several fusion queries per sample (csrc/pool_multi.cuh) --------------------------------------------------------
+@pytest.fixture
+def multi_query(monkeypatch):
+    monkeypatch.setenv("AECF_MULTI_QUERY", "1")
+
+
+@pytest.mark.parametrize("batch_first", [True, False], ids=["batch_first", "seq_first"])
+@pytest.mark.parametrize("case", MULTI_QUERY_CASES, ids=by_name)
+def test_multi_query_fp32_matches_oracle(multi_query, case, batch_first):
+    MQ.test_fp32_matches_oracle(case, batch_first)
+
+
+@pytest.mark.parametrize("case", MULTI_QUERY_CASES, ids=by_name)
+def test_multi_query_fp32_matches_reference_golden(multi_query, case):
+    MQ.test_fp32_matches_reference_golden(case)
+
+
+@pytest.mark.parametrize("case", MULTI_QUERY_CASES, ids=by_name)
+def test_multi_query_bf16_masks_exact_against_stage_rounded_oracle(multi_query, case):
+    MQ.test_bf16_masks_exact_against_stage_rounded_oracle(case)
+
+
+def test_multi_query_shards_and_attn_mask(multi_query):
+    MQ.test_batch_shards_reproduce_the_full_batch()
+    MQ.test_attn_mask_per_query()
+
+
+# ---- the SIMT GEMM / GEMV kernels and the side output's two-launch form -------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("shape", [(200, 136, 72), (1, 512, 512), (512, 512, 1)], ids=lambda s: "x".join(map(str, s)))
+def test_simt_gemm_layouts(dtype, shape):
+    P.test_gemm_layouts(_lib.GEMM_AUTO, dtype, shape)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_gemm_with_side_output(dtype):
+    P.test_gemm_with_side_output((96, 64, 64, 1), dtype)
