@@ -50,3 +50,14 @@ def cuda_emulation(monkeypatch):
     monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
     return lib
+
+
+def enable_in_this_process():
+    """The fixture's patches without pytest, for worker processes (tests/test_emu_dp_gloo.py): permanent."""
+    lib = load_emulation()
+    _lib._lib = lib
+    ops.require_cuda = lambda *tensors: torch.device("cpu")
+    ops._stream = lambda dev: None
+    torch.cuda.is_current_stream_capturing = lambda: False
+    torch.cuda.synchronize = lambda *a, **k: None
+    return lib
