@@ -99,7 +99,13 @@ static int make_plan(const aecf_pool_desc* d, PoolPlan* plan, bool fold = false)
     int J = NC > 32 ? 2 : 1;
     if (J < R) J = R;
     if (J > 4) return AECF_ERR_UNSUPPORTED;          // head_dim > 128 * V elements
-    const int WPS = (NC + 32 * J - 1) / (32 * J);
+    int WPS = (NC + 32 * J - 1) / (32 * J);
+    // a row must split over a power-of-two number of warps: rows of 3 * 2^k slices (D = 768 in fp32, 1536 in bf16)
+    // take wider slices instead, whose last warp is then partly idle
+    while ((WPS > POOL_WARPS || !is_pow2(WPS)) && J < 4) {
+        J *= 2;
+        WPS = (NC + 32 * J - 1) / (32 * J);
+    }
     if (WPS > POOL_WARPS || !is_pow2(WPS)) return AECF_ERR_UNSUPPORTED;
 
     PoolParams& p = plan->p;

@@ -83,6 +83,13 @@ def test_rows_spanning_several_warps_folded_fp32(name):
     P.test_wide_rows_folded_fp32(WIDE[name])
 
 
+def test_rows_of_three_slices():
+    """D = 768 in fp32 is 192 sixteen-byte slices: J = 4, two warps per sample, the second half idle."""
+    case = P.THREE_SLICE_CASES[0]
+    P.test_fp32_matches_oracle(case)
+    P.test_bf16_masks_exact_against_stage_rounded_oracle(case, True)
+
+
 @pytest.mark.parametrize("test", [P.test_sequence_first_layout_matches_batch_first, P.test_per_row_queries_match_oracle,
                                   P.test_attn_mask_forms_match_oracle, P.test_no_masking_module_and_plain_output,
                                   P.test_standalone_masking_and_entropy, P.test_entropy_loss_gradient_in_eval_mode,
