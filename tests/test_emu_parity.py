@@ -143,3 +143,47 @@ def test_simt_gemm_layouts(dtype, shape):
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
 def test_gemm_with_side_output(dtype):
     P.test_gemm_with_side_output((96, 64, 64, 1), dtype)
+
+
+# ---- seeded random shapes and options (a slice of the offline fuzz runs that found the 3 * 2^k slice gap) -------------
+def _random_case(rng, name, multi):
+    from tests.golden.cases import Case
+    while True:
+        hd, heads = rng.choice([8, 16, 32, 64, 128]), rng.choice([1, 2, 3, 4, 6, 8, 12])
+        if hd * heads <= 384:
+            break
+    tokens = rng.randint(2 if multi else 1, 8)
+    return Case(name, B=rng.choice([1, 2, 5, 9, 17]), S=rng.randint(2, 4) if multi else 1, M=tokens, D=hd * heads, H=heads,
+                dropout=rng.choice([0.0, 0.1, 0.5]), base_mask_prob=rng.choice([0.15, 0.5, 1.0]), min_active=rng.choice([1, 2, 9]),
+                training=rng.random() < 0.8, kpm=rng.random() < 0.3 and tokens > 1, pooled_grad=rng.random() < 0.5,
+                offset=rng.randint(0, 1000), row0=rng.choice([0, 7, 123456789012]), data_seed=rng.randint(500, 10 ** 6),
+                peak=rng.choice([0.5, 1.0, 2.0]))
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_single_query_cases(seed):
+    import random
+    case = _random_case(random.Random(1000 + seed), f"random{seed}", multi=False)
+    inp = P.build_inputs(case)
+    ref, ref_grads = P.run_oracle(case, inp)
+    for fold in (False, True):
+        out, info, _, grads, _ = P.run_cuda(case, inp, torch.float32, fold=fold)
+        assert (info["mask_bits"].numpy() == P.expected_bits(ref.info["mask"])).all(), (case, fold)
+        assert_close("out", out, ref.out, 2e-5)
+        P.check_grads(case, grads, ref_grads, 3e-5)          # peaked rows cancel in the softmax backward: a little slack
+    if case.D // case.H % 8 == 0:
+        P.test_bf16_masks_exact_against_stage_rounded_oracle(case, True)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_multi_query_cases(multi_query, seed):
+    import random
+    from tests.helpers import run_oracle
+    rng = random.Random(2000 + seed)
+    case = _random_case(rng, f"random_mq{seed}", multi=True)
+    inp = MQ.build_inputs(case)
+    ref, ref_grads = run_oracle(case, inp)
+    out, info, ent_loss, grads, _ = MQ.run_cuda(case, inp, torch.float32, batch_first=rng.random() < 0.5)
+    MQ.check_against_oracle(case, out, info, ent_loss, grads, ref, ref_grads, 3e-5)
+    if case.D // case.H % 8 == 0:
+        MQ.test_bf16_masks_exact_against_stage_rounded_oracle(case)
