@@ -282,9 +282,21 @@ static int pool_bwd_impl(const aecf_pool_desc* desc, bool fold, const void* q, c
     int grid = static_cast<int>(want < cap ? want : cap);
     if (grid < 1) grid = 1;
 
+    // EXPERIMENTAL (AECF_POOL_BWD_STREAM=1, logic verified under the host emulation, not yet run on hardware): the
+    // folded backward with cp.async-staged rows, pool_bwd_stream_kernel; read per call so that tests can switch it
+    const char* stream_env = getenv("AECF_POOL_BWD_STREAM");
+    const bool stream_variant = fold && !plan.multi && p.WPS == 1 && stream_env && stream_env[0] == '1';
     {
         TimedLaunch timed(static_cast<cudaStream_t>(stream));
-        if (plan.multi) {
+        if (stream_variant) {
+            const int sms = sm_count(desc->device);
+            if (plan.bf16)
+                rc = plan.drop ? launch_pool_bwd_stream<__nv_bfloat16, true>(plan.M, plan.J, p, sms, &grid, stream)
+                               : launch_pool_bwd_stream<__nv_bfloat16, false>(plan.M, plan.J, p, sms, &grid, stream);
+            else
+                rc = plan.drop ? launch_pool_bwd_stream<float, true>(plan.M, plan.J, p, sms, &grid, stream)
+                               : launch_pool_bwd_stream<float, false>(plan.M, plan.J, p, sms, &grid, stream);
+        } else if (plan.multi) {
             plan.mq.bias = score_bias;
             p.bias = nullptr;
             if (plan.bf16)
