@@ -216,9 +216,14 @@ def workload_config(args, n_gpus):
     x_mb = args.batch * args.tokens * args.dim * es / 1e6
     strong = getattr(args, "global_batch", 0) > 0
     rot = input_buffers_needed(int(x_mb * 1e6))
-    l2 = (f"inputs larger than L2 (x {x_mb:.0f} MB, values {x_mb:.0f} MB per step vs 126 MB L2); no flush needed" if rot == 1 else
-          f"one shard's input ({x_mb:.0f} MB) fits in the 126 MB L2: the timed steps rotate over {rot} input batches "
-          f"({rot * x_mb:.0f} MB), so no step finds its input in L2")
+    if rot == 1:
+        l2 = f"inputs larger than L2 (x {x_mb:.0f} MB, values {x_mb:.0f} MB per step vs 126 MB L2); no flush needed"
+    elif rot * x_mb * 1e6 > L2_BYTES:
+        l2 = (f"one shard's input ({x_mb:.0f} MB) fits in the 126 MB L2: the timed steps rotate over {rot} input batches "
+              f"({rot * x_mb:.0f} MB), so no step finds its input in L2")
+    else:
+        l2 = (f"L2-RESIDENT: {rot} input batches of {x_mb:.2f} MB are smaller than the 126 MB L2 together; "
+              "not a bandwidth measurement")
     return {"workload": f"MultimodalAttentionPool D={args.dim} H={args.heads} M={args.tokens} with CurriculumMasking, "
                         + (f"B={args.global_batch} in total over {n_gpus} GPUs" if strong else f"B={args.batch} per GPU")
                         + f", {args.dtype} (BASELINE.json configs[1])",
