@@ -216,3 +216,28 @@ def test_streaming_backward_is_bit_identical_to_the_default(monkeypatch):
     new = P.run_cuda(case, inp, torch.float32, fold=True)
     assert torch.equal(base[3]["key"], new[3]["key"])
     assert_close("in_proj_bias", new[3]["in_proj_bias"], base[3]["in_proj_bias"], 1e-6)
+
+
+# ---- the device-side Philox pair a CUDA-graph capture reads (aecf_pool_desc::rng_state) ------------------------------
+@pytest.mark.parametrize("fold", [False, True], ids=["unfolded", "folded"])
+def test_device_side_philox_state_reproduces_the_by_value_pair(monkeypatch, fold):
+    """What tests/test_gpu_graphs.py checks with real captures: a forward that reads {seed, offset} from device memory
+    draws what the by-value call draws, and the offset advances on the device between calls."""
+    import dataclasses
+
+    from aecf_b200 import graphs
+    from tests.golden.cases import CASES_BY_NAME, PHILOX_SEED, build_inputs
+    case = CASES_BY_NAME["d64_h8_m3_dropout"]
+    inp = build_inputs(case)
+    eager = [P.run_cuda(dataclasses.replace(case, offset=case.offset + i), inp, torch.float32, fold=fold) for i in range(2)]
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    aecf_b200.set_rng_state(PHILOX_SEED, case.offset)
+    state = graphs.prepare(torch.device("cpu"))
+    aecf_b200.set_rng_state(None)
+    monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: True)
+    for i in range(2):
+        got = P.run_cuda(case, inp, torch.float32, fold=fold)           # its by-value pair is ignored while "capturing"
+        assert torch.equal(got[0], eager[i][0]) and torch.equal(got[1]["mask_bits"], eager[i][1]["mask_bits"]), i
+        assert torch.equal(got[3]["key"], eager[i][3]["key"]), i
+        assert int(state[1]) == case.offset + i + 1
+    assert not torch.equal(eager[0][1]["mask_bits"], eager[1][1]["mask_bits"])
