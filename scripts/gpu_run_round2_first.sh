@@ -7,7 +7,7 @@
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider --timeout 300 > gpurun_out/r2_tests_default.log 2>&1
 echo "pytest default exit $?" >> gpurun_out/r2_tests_default.log
-AECF_TEST_EXPERIMENTAL=1 timeout 400 python -m pytest tests/test_gpu_multi_query.py tests/test_gpu_parity.py -k "multi_query or three_slices" \
+AECF_TEST_EXPERIMENTAL=1 timeout 400 python -m pytest tests/test_gpu_multi_query.py tests/test_gpu_parity.py -k "multi_query or three_slices or without_biases" \
     -m gpu -q --tb=short -p no:cacheprovider --timeout 120 > gpurun_out/r2_tests_multi_query.log 2>&1
 echo "pytest multi-query exit $?" >> gpurun_out/r2_tests_multi_query.log
 for v in "epi2 AECF_GEMM_EPI=2" "epi3 AECF_GEMM_EPI=3" "2sm_ew8 AECF_GEMM_2SM_EW=8" "bwd_stream AECF_POOL_BWD_STREAM=1"; do

@@ -98,6 +98,12 @@ def test_module_surface(test):
     test()
 
 
+@pytest.mark.parametrize("dtype,fold", [(torch.float32, False), (torch.float32, True), (torch.bfloat16, True), (torch.bfloat16, False)],
+                         ids=["fp32_unfolded", "fp32_folded", "bf16_folded", "bf16_unfolded"])
+def test_module_without_biases(dtype, fold):
+    P.test_module_without_biases(dtype, fold)
+
+
 def test_functional_fast_path():
     q = torch.from_numpy(philox.normal(1, (6, 2, 64))).float()
     k = torch.from_numpy(philox.normal(2, (6, 5, 64))).float()

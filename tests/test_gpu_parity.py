@@ -540,6 +540,49 @@ def test_no_masking_module_and_plain_output():
     assert_close("out", out.cpu(), ref.out, FP32_TOL)
 
 
+@pytest.mark.skipif(__import__("os").environ.get("AECF_TEST_EXPERIMENTAL") != "1",
+                    reason="added at the end of round 1 without a GPU (host emulation only): AECF_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("dtype,fold", [(torch.float32, False), (torch.float32, True), (torch.bfloat16, True), (torch.bfloat16, False)],
+                         ids=["fp32_unfolded", "fp32_folded", "bf16_folded", "bf16_unfolded"])
+def test_module_without_biases(dtype, fold):
+    """bias=False (reference aecf/AECFLayer.py:377): no in_proj_bias / out_proj.bias, null bias pointers through the ABI."""
+    case = CASES_BY_NAME["d64_h8_m3_dropout"]
+    inp = build_inputs(case)
+    if dtype == torch.bfloat16:
+        inp = {k: (v.bfloat16().float() if v.is_floating_point() and k not in ("u_mask", "u_drop") else v) for k, v in inp.items()}
+    pool = aecf_b200.MultimodalAttentionPool(case.D, num_heads=case.H, dropout=case.dropout, bias=False,
+                                             curriculum_masking=aecf_b200.CurriculumMasking(**masking_kwargs(case)),
+                                             device=DEV, dtype=dtype)
+    assert pool.attention.in_proj_bias is None and pool.attention.out_proj.bias is None
+    with torch.no_grad():
+        pool.attention.in_proj_weight.copy_(inp["in_proj_weight"])
+        pool.attention.out_proj.weight.copy_(inp["out_proj.weight"])
+    pool.fold_key_projection, pool._want_mask_bits = fold, True
+    query0 = torch.nn.Parameter(inp["query0"].to(DEV, dtype))
+    x = inp["x"].to(DEV, dtype).requires_grad_(True)
+    aecf_b200.set_rng_state(PHILOX_SEED, case.offset)
+    try:
+        out, info = pool(query0.expand(case.B, -1, -1), x, return_info=True)
+    finally:
+        aecf_b200.set_rng_state(None)
+    (out.float() * inp["grad_out"].to(DEV)).sum().backward()
+    storage = torch.bfloat16 if dtype == torch.bfloat16 else None
+    q = inp["query0"].expand(case.B, 1, case.D)
+    ref = oracle.pool_forward(q, inp["x"], None, inp["in_proj_weight"], None, inp["out_proj.weight"], None, case.H,
+                              dropout_p=case.dropout, training=True, u_drop=inp["u_drop"], u_mask=inp["u_mask"],
+                              masking=masking_kwargs(case), storage=storage, fold_key=fold and storage is not None)
+    grads = oracle.pool_backward(q, inp["x"], None, inp["in_proj_weight"], inp["out_proj.weight"], case.H, ref.saved, inp["grad_out"],
+                                 dropout_p=case.dropout, training=True, has_bias=False, storage=storage,
+                                 fold_key=fold and storage is not None)
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    assert np.array_equal(info["mask_bits"].cpu().numpy(), expected_bits(ref.info["mask"])), "mask bits differ"
+    assert_close("out", out.float().cpu(), ref.out, tol)
+    assert_close("grad key", x.grad.float().cpu(), grads["key"], tol)
+    assert_close("grad in_proj_weight", pool.attention.in_proj_weight.grad.float().cpu(), grads["in_proj_weight"], tol)
+    assert_close("grad out_proj.weight", pool.attention.out_proj.weight.grad.float().cpu(), grads["out_proj.weight"], tol)
+    assert_close("grad query0", query0.grad.float().cpu(), grads["query"].sum(0, keepdim=True), tol)
+
+
 def test_unsupported_shapes_fail_loudly():
     pool = aecf_b200.MultimodalAttentionPool(64, num_heads=4, device=DEV)
     x = torch.randn(4, 3, 64, device=DEV)
