@@ -2,6 +2,8 @@
 
     python scripts/sass_diff.py snapshot DIR          # cuobjdump -sass of every aecf_b200/csrc/build/*.o into DIR
     python scripts/sass_diff.py compare BEFORE AFTER   # functions whose instruction stream differs, added, removed
+    python scripts/sass_diff.py manifest DIR OUT.json  # {demangled function: [sha1, instructions]} of a snapshot
+    python scripts/sass_diff.py check OUT.json DIR     # a snapshot against a committed manifest (exit 1 on a change)
 
 Instruction text only (addresses, encodings and comments are dropped), keyed by mangled function name.
 """
@@ -68,10 +70,44 @@ def compare(before, after):
     return 1 if (changed or removed) else 0
 
 
+def demangle_all(names):
+    out = subprocess.run(["c++filt"], input="\n".join(names), capture_output=True, text=True).stdout.split("\n")
+    return dict(zip(names, out))
+
+
+def manifest(directory, out_path):
+    import json
+    table = load(directory)
+    names = demangle_all(sorted(table))
+    with open(out_path, "w") as f:
+        json.dump({names[k]: list(v) for k, v in sorted(table.items())}, f, indent=0, sort_keys=True)
+    print(f"{len(table)} functions -> {out_path}")
+
+
+def check(manifest_path, directory):
+    import json
+    want = json.load(open(manifest_path))
+    table = load(directory)
+    names = demangle_all(sorted(table))
+    got = {names[k]: list(v) for k, v in table.items()}
+    changed = sorted(k for k in want if k in got and got[k] != want[k])
+    removed = sorted(k for k in want if k not in got)
+    added = sorted(k for k in got if k not in want)
+    print(f"{len(want)} functions in the manifest, {len(got)} in the build: {len(changed)} changed, {len(removed)} removed, {len(added)} added")
+    for title, group in (("changed", changed), ("removed", removed), ("added", added)):
+        for k in group[:40]:
+            print(f"  {title}: {k[:150]}")
+    return 1 if (changed or removed) else 0
+
+
 if __name__ == "__main__":
     if len(sys.argv) >= 3 and sys.argv[1] == "snapshot":
         snapshot(sys.argv[2])
     elif len(sys.argv) >= 4 and sys.argv[1] == "compare":
         sys.exit(compare(sys.argv[2], sys.argv[3]))
+    elif len(sys.argv) >= 4 and sys.argv[1] == "manifest":
+        manifest(sys.argv[2], sys.argv[3])
+    elif len(sys.argv) >= 4 and sys.argv[1] == "check":
+        sys.exit(check(sys.argv[2], sys.argv[3]))
     else:
         sys.exit(__doc__)
