@@ -6,6 +6,9 @@
 // defined in the library build; every `#ifdef AECF_CUDA_EMU` below is the emulation's stand-in for an inline-PTX
 // wrapper or a launch, and the other branch is the product, token for token what it was before the split.
 #ifdef AECF_CUDA_EMU
+#ifdef __CUDACC__
+#error "AECF_CUDA_EMU is the g++ test build of tests/cuda_emu; the library itself is never built with it"
+#endif
 #include "cuda_emu.h"
 #else
 #include <cuda_runtime.h>
