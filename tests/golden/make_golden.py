@@ -29,35 +29,7 @@ import aecf as ref  # noqa: E402  (the reference package)
 from tests.golden.cases import CASES, MULTI_QUERY_CASES, Case, build_inputs, masking_kwargs  # noqa: E402
 
 
-class inject_uniforms:
-    """Context manager replacing the reference's two RNG draws by injected uniforms."""
-
-    def __init__(self, u_mask: torch.Tensor, u_drop: torch.Tensor):
-        self.u_mask, self.u_drop = u_mask, u_drop
-
-    def __enter__(self):
-        self._bern = torch.bernoulli
-        self._drop = torch.nn.functional.dropout
-        u_mask, u_drop = self.u_mask, self.u_drop
-
-        def bernoulli(p, *a, **k):
-            return (u_mask.view(p.shape).to(p.dtype) <= p).to(p.dtype)
-
-        def dropout(w, p=0.5, training=True, inplace=False):
-            if not training or p == 0.0:
-                return w
-            if p >= 1.0:
-                return w * 0.0
-            keep = (u_drop.reshape(w.shape).to(w.dtype) >= p).to(w.dtype)
-            return w * keep / (1.0 - p)
-
-        torch.bernoulli = bernoulli
-        torch.nn.functional.dropout = dropout
-        return self
-
-    def __exit__(self, *exc):
-        torch.bernoulli = self._bern
-        torch.nn.functional.dropout = self._drop
+from tests.golden.injection import inject_uniforms  # noqa: E402,F401
 
 
 def run_reference(case: Case):
