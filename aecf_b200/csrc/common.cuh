@@ -103,9 +103,11 @@ inline cudaError_t launch_plain(void (*kernel)(KArgs...), dim3 grid, dim3 block,
 #ifdef AECF_CUDA_EMU
 #define AECF_DYNAMIC_SMEM(type, name) type* name = reinterpret_cast<type*>(cuda_emu::dynamic_smem())
 #define AECF_DYNAMIC_SMEM_ALIGNED16(type, name) type* name = reinterpret_cast<type*>(cuda_emu::dynamic_smem())
+#define AECF_DYNAMIC_SMEM_ALIGNED1024(type, name) type* name = reinterpret_cast<type*>(cuda_emu::dynamic_smem())
 #else
 #define AECF_DYNAMIC_SMEM(type, name) extern __shared__ type name[]
 #define AECF_DYNAMIC_SMEM_ALIGNED16(type, name) extern __shared__ __align__(16) type name[]
+#define AECF_DYNAMIC_SMEM_ALIGNED1024(type, name) extern __shared__ __align__(1024) type name[]
 #endif
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

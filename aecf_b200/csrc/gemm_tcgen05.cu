@@ -59,6 +59,9 @@ struct Params {
     float* aux;
 };
 
+#ifdef AECF_CUDA_EMU
+#include "tcgen05_emu_wrappers.h"     // functional stand-ins for every inline-PTX wrapper below (tests/cuda_emu)
+#else
 // ---- raw PTX wrappers -----------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -159,6 +162,7 @@ __device__ __forceinline__ void tmem_ld_wait_on(uint32_t (&r)[32]) {
                    "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
                  :: "memory");
 }
+#endif  // AECF_CUDA_EMU
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, leading/stride byte
 // offsets in 16-byte units, version 1 (Blackwell), layout type 2 = SWIZZLE_128B.
@@ -188,6 +192,7 @@ __device__ __forceinline__ uint32_t make_idesc(int bn, int a_mn, int b_mn) {
 }
 
 // ---- cta_group::2 helpers: a pair of CTAs (one cluster) works on one 256-row tile -------------------------
+#ifndef AECF_CUDA_EMU
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;     // clears the CTA-rank bit of a shared::cluster address -> leader CTA
 __device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
     // lands in THIS CTA's shared memory, completes bytes on the LEADER CTA's barrier at the same offset
@@ -228,11 +233,13 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         if (clock64() - t0 > SPIN_LIMIT) __trap();
     }
 }
+#endif
 
 // One lane of a fully active warp (the lowest).  The producer and the MMA issuer walk their loops with the WHOLE warp
 // and elect inside: under `if (lane == 0)` the compiler has to emulate every uniform-datapath instruction (UTMALDG,
 // UTCHMMA, UTCBAR) of the divergent region with an election loop plus vector->uniform register moves -- 38
 // instructions per tcgen05.mma in r1 run 18's SASS, more issue latency than the MMA takes to execute.
+#ifndef AECF_CUDA_EMU
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(
@@ -242,6 +249,7 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(pred));
     return pred != 0;
 }
+#endif
 // Advancing a shared-memory descriptor by `bytes` is an add on its 14-bit start-address field (16-byte units); every
 // address stays inside the 227 KB of shared memory, so the field never carries into its neighbours.
 __device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (bytes >> 4); }
@@ -280,7 +288,7 @@ __global__ void __launch_bounds__(64 + 32 * epi_warps(EPI), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_c, const Params p) {
     using C = Cfg<BN>;
-    extern __shared__ __align__(1024) uint8_t smem[];                          // swizzle-128B tiles need 1024-byte alignment
+    AECF_DYNAMIC_SMEM_ALIGNED1024(uint8_t, smem);                              // swizzle-128B tiles need 1024-byte alignment
     if (smem_u32(smem) & 1023u) __trap();
     uint8_t* stage_base = smem;
     uint8_t* epi_base = smem + STAGES * C::STAGE_BYTES;                       // 1024-aligned (stage sizes are)
@@ -305,9 +313,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         fence_barrier_init();
     }
     if (warp == 1) {                                  // one warp allocates TMEM and owns the dealloc
+#ifdef AECF_CUDA_EMU
+        if (lane == 0) cuda_emu::tc::tmem_alloc(tmem_slot, C::TMEM_COLS);
+#else
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      :: "r"(smem_u32(tmem_slot)), "r"(static_cast<uint32_t>(C::TMEM_COLS)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+#endif
     }
     tc_fence_before();
     __syncthreads();
@@ -498,7 +510,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         uint8_t* box_base = wbuf + ((box_it + (g >> 1)) & 1) * (32 * 128);
                         uint8_t* box = box_base + lane * 128;
                         if ((g & 1) == 0) {
+#ifndef AECF_CUDA_EMU
                             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+#endif
                             __syncwarp();
                         }
                         float v[32];
@@ -621,8 +635,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (CL > 1) cluster_sync_all();                  // nobody leaves while a peer may still multicast into it
     if (warp == 1) {
         tc_fence_after();
+#ifndef AECF_CUDA_EMU
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
                      :: "r"(tmem_base), "r"(static_cast<uint32_t>(C::TMEM_COLS)) : "memory");
+#endif
     }
 }
 
@@ -670,6 +686,9 @@ using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, voi
                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static EncodeFn encode_fn() {
+#ifdef AECF_CUDA_EMU
+    return &cuda_emu::tc::encode_tiled;
+#endif
     static EncodeFn fn = nullptr;
     static std::once_flag once;
     std::call_once(once, [] {

@@ -9,29 +9,36 @@
 
 #include "../../include/aecf_b200.h"
 
+dim3 blockDim, gridDim;
+
 namespace cuda_emu {
 namespace {
 
 constexpr size_t STACK_BYTES = 1 << 20;
 constexpr int MAX_THREADS = 1024, MAX_WARPS = 32, NAMED_BARRIERS = 16;
-constexpr size_t SMEM_BYTES = 232448;                    // the 227 KB a CTA can opt into on sm_100
 
-struct Fiber { ThreadState ts; ucontext_t ctx; bool done; };
+struct Fiber { ThreadState ts; ucontext_t ctx; bool done; int cta; };
 struct Warp { uint32_t slot[32]; int arrived; unsigned generation; int live; };
 struct Barrier { int arrived; unsigned generation; int count; };
-
-struct Engine {
+struct Cta {                                             // one thread block of the cluster that is running
     BlockState bs{};
-    std::vector<Fiber> fibers;
     Warp warps[MAX_WARPS]{};
     Barrier barriers[NAMED_BARRIERS]{};
     int live = 0;
+};
+
+struct Engine {
+    Cta ctas[MAX_CLUSTER];
+    int cluster = 1;
+    Barrier cluster_barrier{};
+    int cluster_live = 0;
+    std::vector<Fiber> fibers;
     Fiber* current = nullptr;
     ucontext_t scheduler{};
     const std::function<void()>* body = nullptr;
     unsigned long progress = 0;
     unsigned char* stacks = nullptr;
-    alignas(1024) unsigned char smem[SMEM_BYTES];
+    unsigned char* smem = nullptr;                       // MAX_CLUSTER windows of SMEM_BYTES, 1024-byte aligned
     std::mutex lock;
 };
 
@@ -40,13 +47,8 @@ Engine& engine() {
     return *e;
 }
 
-void yield() {
-    Engine& e = engine();
-    swapcontext(&e.current->ctx, &e.scheduler);
-}
-
-void try_release(Engine& e, Barrier& b) {
-    const int need = b.count > 0 ? b.count : e.live;
+void try_release(int live, Barrier& b, Engine& e) {
+    const int need = b.count > 0 ? b.count : live;
     if (b.arrived > 0 && b.arrived >= need) { b.arrived = 0; ++b.generation; ++e.progress; }
 }
 
@@ -58,33 +60,43 @@ void fiber_main() {
     Engine& e = engine();
     (*e.body)();
     Fiber& f = *e.current;
+    Cta& c = e.ctas[f.cta];
     f.done = true;
     ++e.progress;
-    --e.live;
-    --e.warps[f.ts.warp].live;
-    try_release(e, e.warps[f.ts.warp]);                  // an exited lane no longer takes part in __syncwarp / shuffles
-    try_release(e, e.barriers[0]);                       // ... nor in __syncthreads
+    --c.live;
+    --e.cluster_live;
+    --c.warps[f.ts.warp].live;
+    try_release(e, c.warps[f.ts.warp]);                  // an exited lane no longer takes part in __syncwarp / shuffles
+    try_release(c.live, c.barriers[0], e);               // ... nor in __syncthreads
+    try_release(e.cluster_live, e.cluster_barrier, e);
 }
 
-void run_block(Engine& e, dim3 block_dim) {
+void run_cluster(Engine& e, dim3 block_dim) {
     const int n = static_cast<int>(block_dim.x * block_dim.y * block_dim.z);
-    e.fibers.assign(n, Fiber{});
-    for (Warp& w : e.warps) w = Warp{};
-    for (Barrier& b : e.barriers) b = Barrier{};
-    e.live = n;
-    for (int i = 0; i < n; ++i) {
-        Fiber& f = e.fibers[i];
-        f.ts.linear = i; f.ts.lane = i & 31; f.ts.warp = i >> 5;
-        f.ts.tid = make_uint3(i % block_dim.x, (i / block_dim.x) % block_dim.y, i / (block_dim.x * block_dim.y));
-        f.done = false;
-        ++e.warps[f.ts.warp].live;
-        getcontext(&f.ctx);
-        f.ctx.uc_stack.ss_sp = e.stacks + static_cast<size_t>(i) * STACK_BYTES;
-        f.ctx.uc_stack.ss_size = STACK_BYTES;
-        f.ctx.uc_link = &e.scheduler;
-        makecontext(&f.ctx, fiber_main, 0);
+    e.fibers.assign(static_cast<size_t>(n) * e.cluster, Fiber{});
+    e.cluster_barrier = Barrier{};
+    e.cluster_live = n * e.cluster;
+    for (int c = 0; c < e.cluster; ++c) {
+        Cta& cta = e.ctas[c];
+        for (Warp& w : cta.warps) w = Warp{};
+        for (Barrier& b : cta.barriers) b = Barrier{};
+        cta.live = n;
+        for (int i = 0; i < n; ++i) {
+            Fiber& f = e.fibers[static_cast<size_t>(c) * n + i];
+            f.cta = c;
+            f.ts.linear = i; f.ts.lane = i & 31; f.ts.warp = i >> 5;
+            f.ts.tid = make_uint3(i % block_dim.x, (i / block_dim.x) % block_dim.y, i / (block_dim.x * block_dim.y));
+            f.done = false;
+            ++cta.warps[f.ts.warp].live;
+            getcontext(&f.ctx);
+            f.ctx.uc_stack.ss_sp = e.stacks + (static_cast<size_t>(c) * MAX_THREADS + i) * STACK_BYTES;
+            f.ctx.uc_stack.ss_size = STACK_BYTES;
+            f.ctx.uc_link = &e.scheduler;
+            makecontext(&f.ctx, fiber_main, 0);
+        }
     }
-    while (e.live > 0) {
+    reset_block_resources(e.cluster);                    // tcgen05_emu.cpp: mbarriers, tensor memory, bulk-copy state
+    while (e.cluster_live > 0) {
         const unsigned long before = e.progress;
         for (Fiber& f : e.fibers) {
             if (f.done) continue;
@@ -92,8 +104,9 @@ void run_block(Engine& e, dim3 block_dim) {
             swapcontext(&e.scheduler, &f.ctx);
         }
         if (e.progress == before) {
-            std::fprintf(stderr, "cuda_emu: deadlock in block (%u,%u,%u): %d threads wait on barriers nobody else reaches\n",
-                         e.bs.block_idx.x, e.bs.block_idx.y, e.bs.block_idx.z, e.live);
+            const BlockState& bs = e.ctas[0].bs;
+            std::fprintf(stderr, "cuda_emu: deadlock in the cluster of block (%u,%u,%u): %d threads wait on barriers nobody else reaches\n",
+                         bs.block_idx.x, bs.block_idx.y, bs.block_idx.z, e.cluster_live);
             std::abort();
         }
     }
@@ -101,24 +114,44 @@ void run_block(Engine& e, dim3 block_dim) {
 
 }  // namespace
 
+void yield() {
+    Engine& e = engine();
+    swapcontext(&e.current->ctx, &e.scheduler);
+}
+void made_progress() { ++engine().progress; }
+
 ThreadState& thread() { return engine().current->ts; }
-BlockState& block() { return engine().bs; }
-void* dynamic_smem() { return engine().smem; }
+BlockState& block() { return engine().ctas[engine().current->cta].bs; }
+int cta_rank() { return engine().current->cta; }
+int cluster_size() { return engine().cluster; }
+unsigned char* smem_window(int cta) { return engine().smem + static_cast<size_t>(cta) * SMEM_BYTES; }
+void* dynamic_smem() { return smem_window(engine().current->cta); }
 
 void named_barrier(int id, int count, bool wait) {
     Engine& e = engine();
-    Barrier& b = e.barriers[id];
+    Cta& c = e.ctas[e.current->cta];
+    Barrier& b = c.barriers[id];
     const unsigned generation = b.generation;
     ++b.arrived;
     b.count = count;
-    try_release(e, b);
+    try_release(c.live, b, e);
     if (!wait) return;
+    while (b.generation == generation) yield();
+}
+
+void cluster_barrier() {
+    Engine& e = engine();
+    Barrier& b = e.cluster_barrier;
+    const unsigned generation = b.generation;
+    ++b.arrived;
+    b.count = 0;
+    try_release(e.cluster_live, b, e);
     while (b.generation == generation) yield();
 }
 
 void warp_barrier() {
     Engine& e = engine();
-    Warp& w = e.warps[e.current->ts.warp];
+    Warp& w = e.ctas[e.current->cta].warps[e.current->ts.warp];
     const unsigned generation = w.generation;
     ++w.arrived;
     try_release(e, w);
@@ -127,7 +160,7 @@ void warp_barrier() {
 
 uint32_t warp_exchange(uint32_t value, int source_lane) {
     Engine& e = engine();
-    Warp& w = e.warps[e.current->ts.warp];
+    Warp& w = e.ctas[e.current->cta].warps[e.current->ts.warp];
     w.slot[e.current->ts.lane] = value;
     warp_barrier();
     const uint32_t got = w.slot[source_lane];
@@ -135,27 +168,37 @@ uint32_t warp_exchange(uint32_t value, int source_lane) {
     return got;
 }
 
-void run_grid(const std::function<void()>& body, dim3 grid, dim3 block_dim, size_t smem_bytes) {
+void run_grid(const std::function<void()>& body, dim3 grid, dim3 block_dim, size_t smem_bytes, int cluster) {
     Engine& e = engine();
     std::lock_guard<std::mutex> guard(e.lock);
     const size_t threads = static_cast<size_t>(block_dim.x) * block_dim.y * block_dim.z;
-    if (threads == 0 || threads > MAX_THREADS || smem_bytes > SMEM_BYTES) {
-        std::fprintf(stderr, "cuda_emu: launch of %zu threads / %zu bytes of shared memory is outside the model\n", threads, smem_bytes);
+    if (threads == 0 || threads > MAX_THREADS || smem_bytes > SMEM_BYTES || cluster < 1 || cluster > MAX_CLUSTER ||
+        grid.x % cluster != 0) {
+        std::fprintf(stderr, "cuda_emu: launch of %zu threads / %zu bytes of shared memory / cluster %d is outside the model\n",
+                     threads, smem_bytes, cluster);
         std::abort();
     }
     if (e.stacks == nullptr) {
-        void* p = mmap(nullptr, MAX_THREADS * STACK_BYTES, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
-        if (p == MAP_FAILED) { std::perror("cuda_emu: mmap"); std::abort(); }
+        void* p = mmap(nullptr, MAX_CLUSTER * MAX_THREADS * STACK_BYTES, PROT_READ | PROT_WRITE,
+                       MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+        void* s = mmap(nullptr, MAX_CLUSTER * SMEM_BYTES + 1024, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (p == MAP_FAILED || s == MAP_FAILED) { std::perror("cuda_emu: mmap"); std::abort(); }
         e.stacks = static_cast<unsigned char*>(p);
+        e.smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(s) + 1023) & ~static_cast<uintptr_t>(1023));
     }
     e.body = &body;
-    e.bs.grid_dim = grid;
-    e.bs.block_dim = block_dim;
+    e.cluster = cluster;
+    ::gridDim = grid;
+    ::blockDim = block_dim;
     for (unsigned z = 0; z < grid.z; ++z)
         for (unsigned y = 0; y < grid.y; ++y)
-            for (unsigned x = 0; x < grid.x; ++x) {
-                e.bs.block_idx = make_uint3(x, y, z);
-                run_block(e, block_dim);
+            for (unsigned x = 0; x < grid.x; x += cluster) {
+                for (int c = 0; c < cluster; ++c) {
+                    e.ctas[c].bs.grid_dim = grid;
+                    e.ctas[c].bs.block_dim = block_dim;
+                    e.ctas[c].bs.block_idx = make_uint3(x + c, y, z);
+                }
+                run_cluster(e, block_dim);
             }
     e.body = nullptr;
 }
@@ -174,17 +217,8 @@ cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
 
-// entry points of the translation units that are not emulated (NVLink peer memory)
+// entry points of the translation unit that is not emulated (NVLink peer memory)
 size_t aecf_peer_flag_bytes(void) { return 256; }
 int aecf_peer_enable_access(int32_t, int32_t) { return AECF_ERR_UNSUPPORTED; }
 int aecf_peer_allreduce(const aecf_peer_desc*, void* const*, void* const*, void*) { return AECF_ERR_UNSUPPORTED; }
 }
-
-// gemm_tcgen05.cu (TMA / TMEM / tcgen05) is not emulated: the dispatcher falls through to the SIMT kernel
-namespace aecf {
-int gemm_tcgen05(const aecf_gemm_desc*, const void*, const void*, const void*, void*, void*, size_t, cudaStream_t, float*, int,
-                 long long) {
-    return AECF_ERR_UNSUPPORTED;
-}
-size_t gemm_tcgen05_workspace_bytes(const aecf_gemm_desc*) { return 0; }
-}  // namespace aecf

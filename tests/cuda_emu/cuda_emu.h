@@ -51,18 +51,34 @@ struct BlockState {
     uint3 block_idx;
 };
 
+constexpr int MAX_CLUSTER = 2;                          // thread-block clusters: the CTAs of one cluster run together
+constexpr size_t SMEM_BYTES = 232448;                   // the 227 KB a CTA can opt into on sm_100
+
 ThreadState& thread();
 BlockState& block();
+int cta_rank();                                         // %cluster_ctarank of the running thread
+int cluster_size();
+unsigned char* smem_window(int cta);                    // shared memory of CTA `cta` of the running cluster (1024-byte aligned)
 void* dynamic_smem();
 void named_barrier(int id, int count, bool wait);      // count == 0: every thread of the block that has not exited
+void cluster_barrier();                                 // barrier.cluster.arrive + wait
 void warp_barrier();
 uint32_t warp_exchange(uint32_t value, int source_lane);
-void run_grid(const std::function<void()>& body, dim3 grid, dim3 block_dim, size_t smem_bytes);
+void yield();                                           // let the other fibers run (inside a wait loop)
+void made_progress();                                   // a wait condition changed: the deadlock detector's heartbeat
+void reset_block_resources(int cluster);                // tcgen05_emu.cpp: per-cluster mbarrier / tensor-memory state
+void run_grid(const std::function<void()>& body, dim3 grid, dim3 block_dim, size_t smem_bytes, int cluster = 1);
 
 template <typename... KArgs>
 inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block_dim, size_t smem, KArgs... args) {
     std::tuple<KArgs...> copy(args...);                  // kernel parameters are passed by value
     run_grid([&] { std::apply(kernel, copy); }, grid, block_dim, smem);
+    return cudaSuccess;
+}
+template <typename... KArgs>
+inline cudaError_t launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block_dim, size_t smem, int cluster, KArgs... args) {
+    std::tuple<KArgs...> copy(args...);
+    run_grid([&] { std::apply(kernel, copy); }, grid, block_dim, smem, cluster);
     return cudaSuccess;
 }
 
@@ -77,8 +93,8 @@ inline uint32_t bf16_bits(float f) {                    // round to nearest even
 
 #define threadIdx (cuda_emu::thread().tid)
 #define blockIdx (cuda_emu::block().block_idx)
-#define blockDim (cuda_emu::block().block_dim)
-#define gridDim (cuda_emu::block().grid_dim)
+// the same for every thread of a launch, and member names of cudaLaunchConfig_t: plain variables, not macros
+extern dim3 blockDim, gridDim;
 
 // ---- synchronisation and warp primitives ------------------------------------------------------------------
 inline void __syncthreads() { cuda_emu::named_barrier(0, 0, true); }
@@ -131,3 +147,12 @@ inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned old = *p; *p
 // ---- runtime API pieces that cuda_runtime.h only provides under nvcc -----------------------------------------
 template <typename K> inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return cudaSuccess; }
 template <typename K> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, K, int, size_t) { *n = 2; return cudaSuccess; }
+template <typename... KArgs, typename... Args>
+inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t* cfg, void (*kernel)(KArgs...), Args&&... args) {
+    int cluster = 1;
+    for (unsigned i = 0; i < cfg->numAttrs; ++i)
+        if (cfg->attrs[i].id == cudaLaunchAttributeClusterDimension) cluster = static_cast<int>(cfg->attrs[i].val.clusterDim.x);
+    return cuda_emu::launch_cluster(kernel, cfg->gridDim, cfg->blockDim, cfg->dynamicSmemBytes, cluster, static_cast<KArgs>(args)...);
+}
+
+#include "tcgen05_emu.h"

@@ -1,0 +1,77 @@
+"""The tcgen05 / TMEM / TMA projection GEMM on the CPU: gemm_tcgen05.cu compiled for the host emulation, with the
+functional model of tests/cuda_emu/tcgen05_emu.h behind its inline-PTX wrappers (mbarriers, tiled TMA with the 128-byte
+swizzle, cluster multicast, tensor memory, tcgen05.mma through the shared-memory / instruction descriptors,
+cta_group::2).  The model's layouts are validated by the kernels measured on hardware computing correct products under
+it; with that, the epilogue variants that have NOT run on hardware yet (AECF_GEMM_EPI=2 / 3, AECF_GEMM_2SM_EW=8) are
+checked for what a functional model can see -- barrier counts and phases (a wrong count deadlocks the emulation), tile /
+box / column indexing, staging layout -- not for missing waits or fences, and not for speed.
+"""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from aecf_b200 import _lib
+from tests import test_gpu_gemm_tcgen05 as G
+from tests import test_gpu_parity as P
+from tests.emu_support import cuda_emulation  # noqa: F401  (fixture)
+from tests.golden.cases import Case
+
+pytestmark = pytest.mark.usefixtures("cuda_emulation")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+# one tile; BN = 256; a cluster of two with multicast; ragged everywhere (zero fill, clipped stores); three 256-wide column
+# tiles and three tiles per CTA (both accumulators re-used); cta_group::2 (10 k-blocks); split-K with a ragged k tail
+SHAPES = [(128, 128, 64), (256, 256, 64), (384, 256, 128), (200, 136, 72), (392, 520, 200), (512, 256, 640), (300, 512, 4100)]
+LAYOUTS = [(_lib.K_MAJOR, _lib.K_MAJOR), (_lib.K_MAJOR, _lib.MN_MAJOR), (_lib.MN_MAJOR, _lib.MN_MAJOR), (_lib.MN_MAJOR, _lib.K_MAJOR)]
+
+
+@pytest.fixture(autouse=True)
+def _cpu_stands_in_for_the_device(monkeypatch):
+    monkeypatch.setattr(G, "DEV", "cpu")
+    monkeypatch.setattr(P, "DEV", "cpu")
+    plain_to = torch.Tensor.to
+    monkeypatch.setattr(torch.Tensor, "to", lambda self, *a, **k: (lambda r: r.clone() if r is self else r)(plain_to(self, *a, **k)))
+
+
+@pytest.mark.parametrize("layouts", LAYOUTS, ids=["aK_bK", "aK_bMN", "aMN_bMN", "aMN_bK"])
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_kernels(shape, layouts):
+    G.test_tcgen05_gemm(shape, *layouts)
+
+
+def test_strided_operands_and_kernel_choice():
+    G.test_tcgen05_strided_output_and_operand_views()
+    G.test_tcgen05_is_what_auto_picks_for_the_projection_shapes()
+
+
+@pytest.mark.parametrize("shape", [(640, 512, 512, 8), (300, 256, 128, 4)], ids=lambda s: "x".join(map(str, s)))
+def test_side_output(shape):
+    P.test_gemm_with_side_output(shape, torch.bfloat16)
+
+
+def test_whole_step_on_the_tensor_core_gemms():
+    """B*M = 480 rows: the folded forward (192-wide tiles, fp32 score side output), the K = D + 8 contraction of dX and the
+    split-K weight gradients all take the tcgen05 kernels, against the stage-rounded oracle with bit-exact masks."""
+    case = Case("emu_d256_h8_m3_b160", B=160, M=3, D=256, H=8, dropout=0.1, pooled_grad=True, data_seed=77, offset=4)
+    P.test_bf16_masks_exact_against_stage_rounded_oracle(case, True)
+    P.test_bf16_masks_exact_against_stage_rounded_oracle(case, False)
+
+
+VARIANTS = {"pipelined_epilogue": {"AECF_GEMM_EPI": "2"},
+            "eight_warp_epilogues": {"AECF_GEMM_EPI": "3", "AECF_GEMM_2SM_EW": "8"},          # 1SM (cluster of two) and cta_group::2
+            "eight_warp_epilogue_no_cluster": {"AECF_GEMM_EPI": "3", "AECF_GEMM_CLUSTER": "1"}}
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+def test_epilogue_variant(variant):
+    """The library reads these switches once per process, hence a child pytest running the tests above with them set."""
+    if os.environ.get("AECF_EMU_GEMM_CHILD") == "1":
+        pytest.skip("already inside a variant run")
+    env = dict(os.environ, AECF_EMU_GEMM_CHILD="1", **VARIANTS[variant])
+    res = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", os.path.abspath(__file__), "-k",
+                          "(test_kernels and (384x256x128 or 392x520x200 or 512x256x640)) or side_output or whole_step"], capture_output=True, text=True, timeout=1500,
+                         env=env, cwd=ROOT)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
