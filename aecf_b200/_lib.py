@@ -30,6 +30,7 @@ EXPORTS = (
     "aecf_peer_flag_bytes", "aecf_peer_enable_access", "aecf_peer_allreduce",
     "aecf_timing_enable", "aecf_timing_collect", "aecf_timing_site_name",
     "aecf_abi_version", "aecf_strerror", "aecf_last_cuda_error", "aecf_launch_count", "aecf_build_info",
+    "aecf_gemm_last_kernel",
 )
 
 
@@ -166,6 +167,8 @@ def _declare(lib):
     lib.aecf_launch_count.argtypes = []
     lib.aecf_build_info.restype = C.c_char_p
     lib.aecf_build_info.argtypes = []
+    lib.aecf_gemm_last_kernel.restype = C.c_char_p
+    lib.aecf_gemm_last_kernel.argtypes = []
 
 
 def load():
@@ -205,6 +208,11 @@ def check(status: int, what: str) -> None:
 
 def launch_count() -> int:
     return int(load().aecf_launch_count())
+
+
+def gemm_last_kernel() -> str:
+    """Which kernel the last aecf_gemm / aecf_gemm_aux call of this thread launched (diagnostics, A/B runs)."""
+    return load().aecf_gemm_last_kernel().decode()
 
 
 def build_info() -> str:

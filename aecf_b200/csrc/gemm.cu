@@ -1,9 +1,20 @@
 // aecf_gemm: C[m,n] = sum_k A[m,k] B[n,k] (+ bias[n]) (+ C).  Dispatches to the tcgen05/TMEM/TMA
 // kernel (gemm_tcgen05.cu) for bf16 operands and to the SIMT kernel below otherwise (fp32 parity
 // path, tiny GEMV-shaped products such as the shared-query projection, ragged shapes).
+#include <cstdarg>
+#include <cstdio>
+
 #include "gemm.cuh"
 
 namespace aecf {
+
+static thread_local char g_last_gemm_kernel[96] = "";
+void note_gemm_kernel(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    std::vsnprintf(g_last_gemm_kernel, sizeof(g_last_gemm_kernel), fmt, ap);
+    va_end(ap);
+}
 
 // ---- SIMT tile kernel: 64x64x16, 256 threads, 4x4 per thread, fp32 accumulate ---------------
 constexpr int SBM = 64, SBN = 64, SBK = 16;
@@ -182,6 +193,7 @@ static int gemm_simt(const aecf_gemm_desc* d, const void* A, const void* B, cons
                      void* workspace, size_t workspace_bytes, cudaStream_t s, bool allow_split = true) {
     GemmEpilogue ep = make_epilogue(d, bias, C);
     const bool a16 = d->dtype_a == AECF_BF16, b16 = d->dtype_b == AECF_BF16;
+    note_gemm_kernel(d->m == 1 ? "gemv" : "simt");
     if (d->m == 1) {
         if (a16 && b16) return launch_gemv<__nv_bfloat16, __nv_bfloat16>(d, A, B, ep, s);
         if (a16) return launch_gemv<__nv_bfloat16, float>(d, A, B, ep, s);
@@ -223,6 +235,8 @@ static int check_desc(const aecf_gemm_desc* d) {
 using namespace aecf;
 
 extern "C" {
+
+const char* aecf_gemm_last_kernel(void) { return g_last_gemm_kernel; }
 
 size_t aecf_gemm_workspace_bytes(const aecf_gemm_desc* d) {
     if (check_desc(d) != AECF_OK) return 0;

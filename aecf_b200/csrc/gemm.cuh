@@ -52,5 +52,6 @@ int gemm_tcgen05(const aecf_gemm_desc* d, const void* A, const void* B, const vo
                  void* workspace, size_t workspace_bytes, cudaStream_t s, float* aux = nullptr, int aux_cols = 0,
                  long long aux_ld = 0);
 size_t gemm_tcgen05_workspace_bytes(const aecf_gemm_desc* d);
+void note_gemm_kernel(const char* fmt, ...);          // gemm.cu: records what aecf_gemm_last_kernel() reports
 
 }  // namespace aecf

@@ -657,7 +657,8 @@ template <int BN> struct Cfg2 {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int EPI_BUF = 2 * BM * 128;                // one staging buffer: two [128 rows x 128 B] boxes
     static constexpr int EPI_BYTES = 2 * EPI_BUF;               // double buffered: convert round r+1 while round r is stored
-    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int ACC_STRIDE = BN > 128 ? 256 : 128;     // TMEM column stride between the two accumulators
+    static constexpr int TMEM_COLS = 2 * ACC_STRIDE;            // a power of two (= 2 * BN for the 256-wide tiles)
     static constexpr int SMEM_BYTES = STAGES_2SM * STAGE_BYTES + EPI_BYTES + 1024 + 256;
 };
 
@@ -665,20 +666,47 @@ template <int BN> struct Cfg2 {
 #define AECF_2SM_THREADS NUM_THREADS
 #define AECF_2SM_EW 4
 #define AECF_2SM_EPI_T EPI_THREADS
+#define AECF_2SM_AUX 0
 #include "gemm_tcgen05_2sm.inc"
 #undef AECF_2SM_KERNEL
 #undef AECF_2SM_THREADS
 #undef AECF_2SM_EW
 #undef AECF_2SM_EPI_T
+#undef AECF_2SM_AUX
 #define AECF_2SM_KERNEL gemm_tcgen05_2sm_ew8_kernel
 #define AECF_2SM_THREADS (NUM_THREADS + 128)
 #define AECF_2SM_EW 8
 #define AECF_2SM_EPI_T 256
+#define AECF_2SM_AUX 0
 #include "gemm_tcgen05_2sm.inc"
 #undef AECF_2SM_KERNEL
 #undef AECF_2SM_THREADS
 #undef AECF_2SM_EW
 #undef AECF_2SM_EPI_T
+#undef AECF_2SM_AUX
+// the folded forward's 192-wide tiles with the fp32 score side output on CTA pairs (AECF_GEMM_2SM_AUX=1), both widths
+#define AECF_2SM_KERNEL gemm_tcgen05_2sm_aux_kernel
+#define AECF_2SM_THREADS NUM_THREADS
+#define AECF_2SM_EW 4
+#define AECF_2SM_EPI_T 128
+#define AECF_2SM_AUX 1
+#include "gemm_tcgen05_2sm.inc"
+#undef AECF_2SM_KERNEL
+#undef AECF_2SM_THREADS
+#undef AECF_2SM_EW
+#undef AECF_2SM_EPI_T
+#undef AECF_2SM_AUX
+#define AECF_2SM_KERNEL gemm_tcgen05_2sm_aux_ew8_kernel
+#define AECF_2SM_THREADS (NUM_THREADS + 128)
+#define AECF_2SM_EW 8
+#define AECF_2SM_EPI_T 256
+#define AECF_2SM_AUX 1
+#include "gemm_tcgen05_2sm.inc"
+#undef AECF_2SM_KERNEL
+#undef AECF_2SM_THREADS
+#undef AECF_2SM_EW
+#undef AECF_2SM_EPI_T
+#undef AECF_2SM_AUX
 
 // ---- host side -------------------------------------------------------------------------------
 using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -767,6 +795,10 @@ static Plan make_plan(const aecf_gemm_desc* d, int aux_cols = 0) {
     static const int force_2sm = [] { const char* e = getenv("AECF_GEMM_2SM"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
     const bool long_k = pl.kb_per_split >= 9;
     pl.two_sm = pl.cluster == 2 && pl.bn == 256 && (force_2sm < 0 ? long_k : force_2sm == 1);
+    // EXPERIMENTAL (AECF_GEMM_2SM_AUX=1, functional emulation only so far): the side-output product (192-wide tiles) on
+    // CTA pairs too -- each CTA then stages 96 of the 192 B rows, 224 KB of operands per 128 x 192 x 512 tile instead of 320
+    static const bool two_sm_aux = [] { const char* e = getenv("AECF_GEMM_2SM_AUX"); return e && e[0] == '1'; }();
+    if (aux_cols > 0 && two_sm_aux && pl.cluster == 2 && pl.splits == 1) pl.two_sm = true;
     if (aux_cols > 0 && pl.splits != 1) return pl;       // the side output is written by the direct epilogue only
     pl.ok = true;
     return pl;
@@ -847,7 +879,15 @@ int gemm_tcgen05(const aecf_gemm_desc* d, const void* A, const void* B, const vo
         AECF_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, map_a, map_b, map_c, p));                                   \
     } while (0)
     static const bool two_sm_ew8 = [] { const char* e = getenv("AECF_GEMM_2SM_EW"); return e && e[0] == '8'; }();
-    if (pl.two_sm) {
+    if (pl.two_sm) note_gemm_kernel("tcgen05 2sm bn%d ew%d%s splits%d", pl.bn, two_sm_ew8 ? 8 : 4, pl.bn == 192 ? " aux" : "", pl.splits);
+    else note_gemm_kernel("tcgen05 1sm bn%d cluster%d epi%d splits%d", pl.bn, pl.cluster, epi, pl.splits);
+    if (pl.two_sm && pl.bn == 192) {
+        auto kernel = two_sm_ew8 ? gemm_tcgen05_2sm_aux_ew8_kernel<192> : gemm_tcgen05_2sm_aux_kernel<192>;
+        if (two_sm_ew8) cfg.blockDim = dim3(NUM_THREADS + 128);
+        cfg.dynamicSmemBytes = Cfg2<192>::SMEM_BYTES;
+        AECF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<192>::SMEM_BYTES));
+        AECF_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, map_a, map_b, map_c, p));
+    } else if (pl.two_sm) {
         auto kernel = two_sm_ew8 ? gemm_tcgen05_2sm_ew8_kernel<256> : gemm_tcgen05_2sm_kernel<256>;
         if (two_sm_ew8) cfg.blockDim = dim3(NUM_THREADS + 128);
         cfg.dynamicSmemBytes = Cfg2<256>::SMEM_BYTES;

@@ -346,6 +346,8 @@ AECF_API const char* aecf_strerror(int status);
 AECF_API const char* aecf_last_cuda_error(void);      /* host string, thread-local */
 AECF_API uint64_t    aecf_launch_count(void);         /* kernels launched by this library since load */
 AECF_API const char* aecf_build_info(void);           /* "sm_100a nvcc 12.9 ..." */
+AECF_API const char* aecf_gemm_last_kernel(void);     /* host string, thread-local: which kernel the last aecf_gemm[_aux] call of this
+                                                         thread launched, e.g. "tcgen05 1sm bn192 cluster2 epi1", "tcgen05 2sm bn256 ew4", "simt" */
 
 #ifdef __cplusplus
 }

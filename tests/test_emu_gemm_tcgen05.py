@@ -2,7 +2,7 @@
 functional model of tests/cuda_emu/tcgen05_emu.h behind its inline-PTX wrappers (mbarriers, tiled TMA with the 128-byte
 swizzle, cluster multicast, tensor memory, tcgen05.mma through the shared-memory / instruction descriptors,
 cta_group::2).  The model's layouts are validated by the kernels measured on hardware computing correct products under
-it; with that, the epilogue variants that have NOT run on hardware yet (AECF_GEMM_EPI=2 / 3, AECF_GEMM_2SM_EW=8) are
+it; with that, the variants that have NOT run on hardware yet (AECF_GEMM_EPI=2 / 3, AECF_GEMM_2SM_EW=8, AECF_GEMM_2SM_AUX=1) are
 checked for what a functional model can see -- barrier counts and phases (a wrong count deadlocks the emulation), tile /
 box / column indexing, staging layout -- not for missing waits or fences, and not for speed.
 """
@@ -60,9 +60,34 @@ def test_whole_step_on_the_tensor_core_gemms():
     P.test_bf16_masks_exact_against_stage_rounded_oracle(case, False)
 
 
+def test_reported_kernel_follows_the_switches():
+    """aecf_gemm_last_kernel() names what ran, so an A/B run (and the variant runs below) can check that a switch took."""
+    from aecf_b200 import ops
+    env = os.environ
+    ew = "8" if env.get("AECF_GEMM_2SM_EW") == "8" else "4"
+    epi = env.get("AECF_GEMM_EPI", "1")
+    cluster = "1" if env.get("AECF_GEMM_CLUSTER") == "1" else "2"
+    bf = torch.bfloat16
+    a, b = torch.randn(512, 128, dtype=bf), torch.randn(256, 128, dtype=bf)
+    ops.gemm(a, b, m=512, n=256, k=128, a_layout=_lib.K_MAJOR, b_layout=_lib.K_MAJOR, lda=128, ldb=128)           # 2 k-blocks
+    assert _lib.gemm_last_kernel() == f"tcgen05 1sm bn256 cluster{cluster} epi{epi} splits1"
+    ops.gemm(a, b, m=512, n=256, k=128, a_layout=_lib.K_MAJOR, b_layout=_lib.K_MAJOR, lda=128, ldb=128, out_dtype=torch.float32)
+    assert _lib.gemm_last_kernel() == f"tcgen05 1sm bn256 cluster{cluster} epi{'1' if epi == '3' else epi} splits1"   # EPI 3: bf16 output only
+    a, b = torch.randn(512, 640, dtype=bf), torch.randn(256, 640, dtype=bf)
+    ops.gemm(a, b, m=512, n=256, k=640, a_layout=_lib.K_MAJOR, b_layout=_lib.K_MAJOR, lda=640, ldb=640)           # 10 k-blocks
+    assert _lib.gemm_last_kernel() == (f"tcgen05 2sm bn256 ew{ew} splits1" if cluster == "2" else f"tcgen05 1sm bn256 cluster1 epi{epi} splits1")
+    a, b = torch.randn(640, 512, dtype=bf), torch.randn(520, 512, dtype=bf)
+    ops.gemm_aux(a, b, m=640, n=512, k=512, aux_cols=8)
+    want = f"tcgen05 2sm bn192 ew{ew} aux splits1" if (env.get("AECF_GEMM_2SM_AUX") == "1" and cluster == "2") else f"tcgen05 1sm bn192 cluster{cluster} epi{epi} splits1"
+    assert _lib.gemm_last_kernel() == want
+    ops.gemm(a[:64].float(), b[:64].float(), m=64, n=64, k=512, a_layout=_lib.K_MAJOR, b_layout=_lib.K_MAJOR, lda=512, ldb=512)
+    assert _lib.gemm_last_kernel() == "simt"
+
+
 VARIANTS = {"pipelined_epilogue": {"AECF_GEMM_EPI": "2"},
             "eight_warp_epilogues": {"AECF_GEMM_EPI": "3", "AECF_GEMM_2SM_EW": "8"},          # 1SM (cluster of two) and cta_group::2
-            "eight_warp_epilogue_no_cluster": {"AECF_GEMM_EPI": "3", "AECF_GEMM_CLUSTER": "1"}}
+            "eight_warp_epilogue_no_cluster": {"AECF_GEMM_EPI": "3", "AECF_GEMM_CLUSTER": "1"},
+            "side_output_on_cta_pairs": {"AECF_GEMM_2SM_AUX": "1", "AECF_GEMM_2SM_EW": "8"}}
 
 
 @pytest.mark.parametrize("variant", sorted(VARIANTS))
@@ -72,6 +97,6 @@ def test_epilogue_variant(variant):
         pytest.skip("already inside a variant run")
     env = dict(os.environ, AECF_EMU_GEMM_CHILD="1", **VARIANTS[variant])
     res = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", os.path.abspath(__file__), "-k",
-                          "(test_kernels and (384x256x128 or 392x520x200 or 512x256x640)) or side_output or whole_step"], capture_output=True, text=True, timeout=1500,
+                          "(test_kernels and (384x256x128 or 392x520x200 or 512x256x640)) or side_output or whole_step or reported_kernel"], capture_output=True, text=True, timeout=1500,
                          env=env, cwd=ROOT)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]

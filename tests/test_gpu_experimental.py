@@ -48,3 +48,10 @@ def test_eight_warp_epilogue_of_the_cta_pair_kernel_passes_the_gemm_and_parity_s
 def test_streaming_pool_backward_passes_the_parity_and_graph_suites():
     """AECF_POOL_BWD_STREAM=1: the folded backward with cp.async-staged rows (pool_bwd_stream_kernel)."""
     _pytest_with({"AECF_POOL_BWD_STREAM": "1"}, ["tests/test_gpu_parity.py", "tests/test_gpu_graphs.py", "-k", "bf16 or folded or headline or sharding or graph"])
+
+
+def test_side_output_product_on_cta_pairs_passes_the_gemm_and_parity_suites():
+    """AECF_GEMM_2SM_AUX=1: the folded forward's 192-wide tiles with the fp32 score side output on the cta_group::2 kernel."""
+    _pytest_with({"AECF_GEMM_2SM_AUX": "1"},
+                 ["tests/test_gpu_gemm_tcgen05.py", "tests/test_gpu_parity.py", "-k",
+                  "gemm or side_output or bf16 or folded or headline or sharding"])
