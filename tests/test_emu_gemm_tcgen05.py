@@ -87,16 +87,33 @@ def test_reported_kernel_follows_the_switches():
 VARIANTS = {"pipelined_epilogue": {"AECF_GEMM_EPI": "2"},
             "eight_warp_epilogues": {"AECF_GEMM_EPI": "3", "AECF_GEMM_2SM_EW": "8"},          # 1SM (cluster of two) and cta_group::2
             "eight_warp_epilogue_no_cluster": {"AECF_GEMM_EPI": "3", "AECF_GEMM_CLUSTER": "1"},
-            "side_output_on_cta_pairs": {"AECF_GEMM_2SM_AUX": "1", "AECF_GEMM_2SM_EW": "8"}}
+            "score_columns_on_cta_pairs": {"AECF_GEMM_2SM_AUX": "1", "AECF_GEMM_2SM_EW": "8"}}
+
+
+@pytest.fixture(scope="module")
+def variant_runs():
+    """The library reads these switches once per process, hence one child pytest per variant, running the tests above with
+    the switches set; all children are started together and each test below waits for its own."""
+    if os.environ.get("AECF_EMU_GEMM_CHILD") == "1":
+        yield {}
+        return
+    from tests.emu_support import load_emulation
+    load_emulation()                                     # build once, before the children race for it
+    select = "(test_kernels and (384x256x128 or 392x520x200 or 512x256x640)) or side_output or whole_step or reported_kernel"
+    runs = {}
+    for name, switches in VARIANTS.items():
+        env = dict(os.environ, AECF_EMU_GEMM_CHILD="1", **switches)
+        runs[name] = subprocess.Popen([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", os.path.abspath(__file__),
+                                       "-k", select], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, cwd=ROOT)
+    yield runs
+    for proc in runs.values():
+        if proc.poll() is None:
+            proc.kill()
 
 
 @pytest.mark.parametrize("variant", sorted(VARIANTS))
-def test_epilogue_variant(variant):
-    """The library reads these switches once per process, hence a child pytest running the tests above with them set."""
+def test_epilogue_variant(variant_runs, variant):
     if os.environ.get("AECF_EMU_GEMM_CHILD") == "1":
         pytest.skip("already inside a variant run")
-    env = dict(os.environ, AECF_EMU_GEMM_CHILD="1", **VARIANTS[variant])
-    res = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", os.path.abspath(__file__), "-k",
-                          "(test_kernels and (384x256x128 or 392x520x200 or 512x256x640)) or side_output or whole_step or reported_kernel"], capture_output=True, text=True, timeout=1500,
-                         env=env, cwd=ROOT)
-    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
+    out, _ = variant_runs[variant].communicate(timeout=1500)
+    assert variant_runs[variant].returncode == 0, out[-4000:]
