@@ -72,8 +72,8 @@ def _worker(rank, port, out_dir, dtype, fold, overlap):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("dtype,fold,overlap", [(torch.float32, False, False), (torch.float32, True, True), (torch.bfloat16, None, False)],
-                         ids=["fp32_unfolded", "fp32_folded_overlapped", "bf16_default"])
+@pytest.mark.parametrize("dtype,fold,overlap", [(torch.float32, True, True), (torch.bfloat16, None, False)],
+                         ids=["fp32_folded_overlapped", "bf16_default"])
 def test_two_emulated_ranks_reproduce_one(tmp_path, dtype, fold, overlap):
     from tests.emu_support import enable_in_this_process, load_emulation
     load_emulation()                                     # build once, before the workers race for it

@@ -71,7 +71,7 @@ def test_bf16_matches_fp32_math_oracle(case, fold):
 WIDE = {c.name: c for c in P.WIDE_CASES}
 
 
-@pytest.mark.parametrize("name,dtype", [("wide_d1024_h8_m3", torch.float32), ("wide_d1024_h8_m3", torch.bfloat16),
+@pytest.mark.parametrize("name,dtype", [("wide_d1024_h8_m3", torch.bfloat16),
                                         ("wide_d1024_h4_m4_eval", torch.bfloat16), ("wide_d512_h8_m5_kpm", torch.float32),
                                         ("wide_d512_h8_m5_kpm", torch.bfloat16)])
 def test_rows_spanning_several_warps(name, dtype):
@@ -166,7 +166,7 @@ def _random_case(rng, name, multi):
                 peak=rng.choice([0.5, 1.0, 2.0]))
 
 
-@pytest.mark.parametrize("seed", range(8))
+@pytest.mark.parametrize("seed", range(6))
 def test_random_single_query_cases(seed):
     import random
     case = _random_case(random.Random(1000 + seed), f"random{seed}", multi=False)
@@ -181,7 +181,7 @@ def test_random_single_query_cases(seed):
         P.test_bf16_masks_exact_against_stage_rounded_oracle(case, True)
 
 
-@pytest.mark.parametrize("seed", range(8))
+@pytest.mark.parametrize("seed", range(6))
 def test_random_multi_query_cases(multi_query, seed):
     import random
     from tests.helpers import run_oracle
