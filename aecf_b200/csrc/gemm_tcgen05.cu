@@ -440,8 +440,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 constexpr int BOXES = BN / 64;
                 uint8_t* box_base = epi_base + ew * (32 * 128);
                 uint8_t* box = box_base + lane * 128;
+                // an odd number of boxes (192-wide tiles: three) alternates which warp of the pair takes two of them, so that
+                // over two tiles -- the slack the double-buffered accumulator gives -- both do three
+                const int first_box = (ew >> 2) ^ ((BOXES & 1) ? (tile_it & 1) : 0);
 #pragma unroll 1
-                for (int bx = ew >> 2; bx < BOXES; bx += 2) {
+                for (int bx = first_box; bx < BOXES; bx += 2) {
                     uint32_t r[2][32];
                     tmem_ld_32x32(t_row + bx * 64, r[0]);
                     tmem_ld_32x32(t_row + bx * 64 + 32, r[1]);
