@@ -687,6 +687,38 @@ template <int BN> struct Cfg2 {
 #undef AECF_2SM_EW
 #undef AECF_2SM_EPI_T
 #undef AECF_2SM_AUX
+// A-resident CTA-pair kernel (AECF_GEMM_APANEL=1), see gemm_tcgen05_apanel.inc
+template <int BN> struct CfgAP {
+    static constexpr int PANEL_KB = 8;                          // k-blocks of A kept resident: K <= 512
+    static constexpr int STAGES = 4;                            // B ring
+    static constexpr int A_BYTES = BM * BK * 2;                 // 16 KB per panel slot
+    static constexpr int B_BYTES = (BN / 2) * BK * 2;           // this CTA's half of the B tile
+    static constexpr int EPI_BUF = 2 * BM * 128;
+    static constexpr int EPI_BYTES = EPI_BUF;                   // ONE staging buffer
+    static constexpr int ACC_STRIDE = BN > 128 ? 256 : 128;
+    static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+    static constexpr int SMEM_BYTES = PANEL_KB * A_BYTES + STAGES * B_BYTES + EPI_BYTES + 1024 /*alignment*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
+};
+static_assert(CfgAP<256>::SMEM_BYTES <= 232448, "A panel + ring + staging must fit the 227 KB a CTA can opt into");
+#define AECF_AP_KERNEL gemm_tcgen05_apanel_kernel
+#define AECF_AP_THREADS NUM_THREADS
+#define AECF_AP_EW 4
+#define AECF_AP_EPI_T 128
+#include "gemm_tcgen05_apanel.inc"
+#undef AECF_AP_KERNEL
+#undef AECF_AP_THREADS
+#undef AECF_AP_EW
+#undef AECF_AP_EPI_T
+#define AECF_AP_KERNEL gemm_tcgen05_apanel_ew8_kernel
+#define AECF_AP_THREADS (NUM_THREADS + 128)
+#define AECF_AP_EW 8
+#define AECF_AP_EPI_T 256
+#include "gemm_tcgen05_apanel.inc"
+#undef AECF_AP_KERNEL
+#undef AECF_AP_THREADS
+#undef AECF_AP_EW
+#undef AECF_AP_EPI_T
+
 // the folded forward's 192-wide tiles with the fp32 score side output on CTA pairs (AECF_GEMM_2SM_AUX=1), both widths
 #define AECF_2SM_KERNEL gemm_tcgen05_2sm_aux_kernel
 #define AECF_2SM_THREADS NUM_THREADS
@@ -747,7 +779,7 @@ static bool make_map(CUtensorMap* map, const void* ptr, CUtensorMapDataType dt, 
            CUDA_SUCCESS;
 }
 
-struct Plan { bool ok, two_sm; int bn, cluster, tiles_m, tiles_n, groups_m, splits, kb_per_split, kb_total; };
+struct Plan { bool ok, two_sm, apanel; int bn, cluster, tiles_m, tiles_n, groups_m, splits, kb_per_split, kb_total; };
 
 // rows of B that carry the side output: aux_cols rounded up to 16 bytes of bf16
 static int aux_rows_of(int aux_cols) { return (aux_cols + 7) & ~7; }
@@ -802,6 +834,12 @@ static Plan make_plan(const aecf_gemm_desc* d, int aux_cols = 0) {
     // CTA pairs too -- each CTA then stages 96 of the 192 B rows, 224 KB of operands per 128 x 192 x 512 tile instead of 320
     static const bool two_sm_aux = [] { const char* e = getenv("AECF_GEMM_2SM_AUX"); return e && e[0] == '1'; }();
     if (aux_cols > 0 && two_sm_aux && pl.cluster == 2 && pl.splits == 1) pl.two_sm = true;
+    // EXPERIMENTAL (AECF_GEMM_APANEL=1, functional emulation only so far): CTA pairs that keep their A panel resident over all
+    // column tiles of a row block (gemm_tcgen05_apanel.inc) for the K <= 512 products
+    static const bool apanel = [] { const char* e = getenv("AECF_GEMM_APANEL"); return e && e[0] == '1'; }();
+    pl.apanel = apanel && pl.cluster == 2 && pl.splits == 1 && pl.kb_total <= 8 && (pl.bn == 256 || pl.bn == 192) &&
+                (pl.bn == 256 || d->b_layout == AECF_K_MAJOR);
+    if (pl.apanel) pl.two_sm = true;                     // same tensor-map boxes (128-row stores) as the CTA-pair kernel
     if (aux_cols > 0 && pl.splits != 1) return pl;       // the side output is written by the direct epilogue only
     pl.ok = true;
     return pl;
@@ -854,7 +892,8 @@ int gemm_tcgen05(const aecf_gemm_desc* d, const void* A, const void* B, const vo
     p.has_bias = bias != nullptr; p.bias_is_bf16 = d->dtype_bias == AECF_BF16; p.bias = bias;
     p.partial_rows = pl.tiles_m * BM;              // padded: a ragged last row block must not spill into the next split
 
-    const long long items = static_cast<long long>(pl.groups_m) * pl.tiles_n * pl.splits;     // one per cluster
+    const long long items = pl.apanel ? pl.groups_m                                            // a CTA pair takes whole row blocks
+                                      : static_cast<long long>(pl.groups_m) * pl.tiles_n * pl.splits;     // one per cluster
     const int sms = sm_count(d->device);
     long long ctas = items * pl.cluster;
     const long long cap = sms / pl.cluster * pl.cluster;
@@ -882,9 +921,20 @@ int gemm_tcgen05(const aecf_gemm_desc* d, const void* A, const void* B, const vo
         AECF_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, map_a, map_b, map_c, p));                                   \
     } while (0)
     static const bool two_sm_ew8 = [] { const char* e = getenv("AECF_GEMM_2SM_EW"); return e && e[0] == '8'; }();
-    if (pl.two_sm) note_gemm_kernel("tcgen05 2sm bn%d ew%d%s splits%d", pl.bn, two_sm_ew8 ? 8 : 4, pl.bn == 192 ? " aux" : "", pl.splits);
+    if (pl.apanel) note_gemm_kernel("tcgen05 apanel bn%d ew%d", pl.bn, two_sm_ew8 ? 8 : 4);
+    else if (pl.two_sm) note_gemm_kernel("tcgen05 2sm bn%d ew%d%s splits%d", pl.bn, two_sm_ew8 ? 8 : 4, pl.bn == 192 ? " aux" : "", pl.splits);
     else note_gemm_kernel("tcgen05 1sm bn%d cluster%d epi%d splits%d", pl.bn, pl.cluster, epi, pl.splits);
-    if (pl.two_sm && pl.bn == 192) {
+#define AECF_AP_LAUNCH(BN_)                                                                                          \
+    do {                                                                                                              \
+        auto kernel = two_sm_ew8 ? gemm_tcgen05_apanel_ew8_kernel<BN_> : gemm_tcgen05_apanel_kernel<BN_>;             \
+        if (two_sm_ew8) cfg.blockDim = dim3(NUM_THREADS + 128);                                                       \
+        cfg.dynamicSmemBytes = CfgAP<BN_>::SMEM_BYTES;                                                                \
+        AECF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgAP<BN_>::SMEM_BYTES)); \
+        AECF_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, map_a, map_b, map_c, p));                                       \
+    } while (0)
+    if (pl.apanel) {
+        if (pl.bn == 192) AECF_AP_LAUNCH(192); else AECF_AP_LAUNCH(256);
+    } else if (pl.two_sm && pl.bn == 192) {
         auto kernel = two_sm_ew8 ? gemm_tcgen05_2sm_aux_ew8_kernel<192> : gemm_tcgen05_2sm_aux_kernel<192>;
         if (two_sm_ew8) cfg.blockDim = dim3(NUM_THREADS + 128);
         cfg.dynamicSmemBytes = Cfg2<192>::SMEM_BYTES;
@@ -900,6 +950,7 @@ int gemm_tcgen05(const aecf_gemm_desc* d, const void* A, const void* B, const vo
     else if (pl.bn == 192) { if (pl.cluster == 2) AECF_TC_LAUNCH(192, 2); else AECF_TC_LAUNCH(192, 1); }
     else { if (pl.cluster == 2) AECF_TC_LAUNCH(128, 2); else AECF_TC_LAUNCH(128, 1); }
 #undef AECF_TC_LAUNCH
+#undef AECF_AP_LAUNCH
     count_launch();
     AECF_CUDA_OK(cudaGetLastError());
     if (!partial) return AECF_OK;

@@ -55,3 +55,10 @@ def test_side_output_product_on_cta_pairs_passes_the_gemm_and_parity_suites():
     _pytest_with({"AECF_GEMM_2SM_AUX": "1"},
                  ["tests/test_gpu_gemm_tcgen05.py", "tests/test_gpu_parity.py", "-k",
                   "gemm or side_output or bf16 or folded or headline or sharding"])
+
+
+def test_resident_a_panel_kernel_passes_the_gemm_and_parity_suites():
+    """AECF_GEMM_APANEL=1: CTA pairs that keep their 128 x K panel of A in shared memory over all column tiles (K <= 512)."""
+    _pytest_with({"AECF_GEMM_APANEL": "1"},
+                 ["tests/test_gpu_gemm_tcgen05.py", "tests/test_gpu_parity.py", "-k",
+                  "gemm or side_output or bf16 or folded or headline or sharding"])
