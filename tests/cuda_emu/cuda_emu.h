@@ -25,6 +25,9 @@
 
 // host_defines.h turns __shared__ into an (ignored) attribute for a host compiler; here a block's shared variables are
 // function-local statics: blocks run one at a time, so one instance per kernel instantiation is exactly one block's copy.
+// LIMIT: the CTAs of a CLUSTER run together and would share that one instance, so a kernel launched in clusters takes
+// such arrays from its dynamic shared memory when built for the emulation (bias_tile of gemm_tcgen05_2sm.inc); dynamic
+// shared memory is per CTA here as on the device.
 #undef __shared__
 #define __shared__ static
 #undef __global__
