@@ -28,7 +28,7 @@ EXPORTS = (
     "aecf_entropy_loss_fwd", "aecf_entropy_loss_bwd", "aecf_curriculum_mask", "aecf_entropy_bwd", "aecf_sdpa_fwd",
     "aecf_fusion_fwd", "aecf_fusion_bwd", "aecf_fusion_workspace_bytes",
     "aecf_peer_flag_bytes", "aecf_peer_enable_access", "aecf_peer_allreduce",
-    "aecf_timing_enable", "aecf_timing_collect", "aecf_timing_site_name",
+    "aecf_timing_enable", "aecf_timing_collect", "aecf_timing_site_name", "aecf_timing_site_gemm_kernel",
     "aecf_abi_version", "aecf_strerror", "aecf_last_cuda_error", "aecf_launch_count", "aecf_build_info",
     "aecf_gemm_last_kernel",
 )
@@ -157,6 +157,8 @@ def _declare(lib):
     lib.aecf_timing_collect.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_int32)]
     lib.aecf_timing_site_name.restype = C.c_char_p
     lib.aecf_timing_site_name.argtypes = [C.c_int32]
+    lib.aecf_timing_site_gemm_kernel.restype = C.c_char_p
+    lib.aecf_timing_site_gemm_kernel.argtypes = [C.c_int32]
     lib.aecf_abi_version.restype = C.c_int
     lib.aecf_abi_version.argtypes = []
     lib.aecf_strerror.restype = C.c_char_p
@@ -230,6 +232,17 @@ def timing_collect() -> dict:
     n = (C.c_int32 * SITE_COUNT)()
     check(lib.aecf_timing_collect(ms, n), "aecf_timing_collect")
     return {lib.aecf_timing_site_name(i).decode(): (float(ms[i]), int(n[i])) for i in range(SITE_COUNT) if n[i]}
+
+
+def site_gemm_kernels() -> dict:
+    """{launch site: the GEMM kernel it launched last} for the sites that launched one (diagnostics, A/B runs)."""
+    lib = load()
+    out = {}
+    for i in range(SITE_COUNT):
+        k = lib.aecf_timing_site_gemm_kernel(i).decode()
+        if k:
+            out[lib.aecf_timing_site_name(i).decode()] = k
+    return out
 
 
 def ptr(t) -> Optional[int]:

@@ -35,6 +35,7 @@ int sm_count(int device);
 // per-kernel timing (timing.cu): the current site is thread-local, set by the whole-step entry points
 int  timing_begin(cudaStream_t s, int site_override = -1);   // returns a record index or -1 when disabled
 void timing_end(int record, cudaStream_t s);
+void note_site_gemm_kernel(const char* name);                // remembers the GEMM kernel launched from the current site
 struct ScopedSite {
     int previous;
     explicit ScopedSite(int site);

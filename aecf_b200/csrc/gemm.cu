@@ -14,6 +14,7 @@ void note_gemm_kernel(const char* fmt, ...) {
     va_start(ap, fmt);
     std::vsnprintf(g_last_gemm_kernel, sizeof(g_last_gemm_kernel), fmt, ap);
     va_end(ap);
+    note_site_gemm_kernel(g_last_gemm_kernel);
 }
 
 // ---- SIMT tile kernel: 64x64x16, 256 threads, 4x4 per thread, fp32 accumulate ---------------

@@ -1,4 +1,5 @@
 // Optional per-kernel timing: CUDA events recorded immediately around each launch, on the launching stream.
+#include <cstdio>
 #include <mutex>
 #include <vector>
 
@@ -29,7 +30,13 @@ const char* kSiteNames[AECF_SITE_COUNT] = {
     "other", "q_proj", "kv_proj", "pool_fwd", "out_proj", "d_out_bias", "d_out_weight", "d_ctx", "pool_bwd",
     "pool_bwd_finalize", "d_x", "d_kv_weight", "d_q_weight", "d_query", "d_in_bias", "entropy_loss", "fold_prepare",
     "fold_finish"};
+char g_site_gemm[AECF_SITE_COUNT][96];                 // the GEMM kernel last launched from each site (diagnostics)
 }  // namespace
+
+void note_site_gemm_kernel(const char* name) {
+    std::lock_guard<std::mutex> lock(g_timing.mu);
+    std::snprintf(g_site_gemm[g_site], sizeof(g_site_gemm[0]), "%s", name);
+}
 
 ScopedSite::ScopedSite(int site) : previous(g_site) { g_site = site; }
 ScopedSite::~ScopedSite() { g_site = previous; }
@@ -81,6 +88,10 @@ int aecf_timing_collect(float* total_ms, int32_t* launches) {
     g_timing.records.clear();
     g_timing.pool_used = 0;
     return AECF_OK;
+}
+
+const char* aecf_timing_site_gemm_kernel(int32_t site) {
+    return (site >= 0 && site < AECF_SITE_COUNT) ? g_site_gemm[site] : "";
 }
 
 const char* aecf_timing_site_name(int32_t site) {

@@ -568,9 +568,9 @@ def run_b200(args):
             "kernel_ms_sum": sum(k["ms"] * k["calls_per_step"] for k in kernels.values()),
             "e2e": e2e, "gpu_launches": launches, "cuda_graph": use_graph, "clocks": clocks.summary(),
             "library": _lib.build_info(),
-            # opt-in kernel variants in effect (A/B runs are self-describing); the last GEMM of the step as a spot check
+            # opt-in kernel variants in effect and the GEMM kernel each launch site used: A/B runs are self-describing
             "switches": {k: v for k, v in sorted(os.environ.items()) if k.startswith("AECF_")},
-            "last_gemm_kernel": _lib.gemm_last_kernel()}
+            "gemm_kernels": _lib.site_gemm_kernels()}
     if dp_info is not None:
         line["data_parallel"] = dp_info
 

@@ -339,6 +339,7 @@ typedef enum aecf_site {
 AECF_API int         aecf_timing_enable(int32_t enable);                    /* clears earlier records */
 AECF_API int         aecf_timing_collect(float* total_ms, int32_t* launches); /* arrays of AECF_SITE_COUNT; syncs */
 AECF_API const char* aecf_timing_site_name(int32_t site);
+AECF_API const char* aecf_timing_site_gemm_kernel(int32_t site);            /* which GEMM kernel that site launched last ("" if none) */
 
 /* ---- diagnostics ----------------------------------------------------------------------- */
 AECF_API int         aecf_abi_version(void);
