@@ -688,9 +688,9 @@ template <int BN> struct Cfg2 {
 #undef AECF_2SM_EPI_T
 #undef AECF_2SM_AUX
 // A-resident CTA-pair kernel (AECF_GEMM_APANEL=1), see gemm_tcgen05_apanel.inc
-template <int BN> struct CfgAP {
-    static constexpr int PANEL_KB = 8;                          // k-blocks of A kept resident: K <= 512
-    static constexpr int STAGES = 4;                            // B ring
+template <int BN, int PKB> struct CfgAP {
+    static constexpr int PANEL_KB = PKB;                        // k-blocks of A kept resident: 8 (K <= 512) or 9 (K = 520, dX)
+    static constexpr int STAGES = PKB > 8 ? 3 : 4;              // B ring: one stage fewer pays for the ninth panel slot
     static constexpr int A_BYTES = BM * BK * 2;                 // 16 KB per panel slot
     static constexpr int B_BYTES = (BN / 2) * BK * 2;           // this CTA's half of the B tile
     static constexpr int EPI_BUF = 2 * BM * 128;
@@ -699,7 +699,8 @@ template <int BN> struct CfgAP {
     static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
     static constexpr int SMEM_BYTES = PANEL_KB * A_BYTES + STAGES * B_BYTES + EPI_BYTES + 1024 /*alignment*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
 };
-static_assert(CfgAP<256>::SMEM_BYTES <= 232448, "A panel + ring + staging must fit the 227 KB a CTA can opt into");
+static_assert(CfgAP<256, 8>::SMEM_BYTES <= 232448 && CfgAP<256, 9>::SMEM_BYTES <= 232448,
+              "A panel + ring + staging must fit the 227 KB a CTA can opt into");
 #define AECF_AP_KERNEL gemm_tcgen05_apanel_kernel
 #define AECF_AP_THREADS NUM_THREADS
 #define AECF_AP_EW 4
@@ -837,7 +838,7 @@ static Plan make_plan(const aecf_gemm_desc* d, int aux_cols = 0) {
     // EXPERIMENTAL (AECF_GEMM_APANEL=1, functional emulation only so far): CTA pairs that keep their A panel resident over all
     // column tiles of a row block (gemm_tcgen05_apanel.inc) for the K <= 512 products
     static const bool apanel = [] { const char* e = getenv("AECF_GEMM_APANEL"); return e && e[0] == '1'; }();
-    pl.apanel = apanel && pl.cluster == 2 && pl.splits == 1 && pl.kb_total <= 8 && (pl.bn == 256 || pl.bn == 192) &&
+    pl.apanel = apanel && pl.cluster == 2 && pl.splits == 1 && (pl.bn == 256 ? pl.kb_total <= 9 : (pl.bn == 192 && pl.kb_total <= 8)) &&
                 (pl.bn == 256 || d->b_layout == AECF_K_MAJOR);
     if (pl.apanel) pl.two_sm = true;                     // same tensor-map boxes (128-row stores) as the CTA-pair kernel
     if (aux_cols > 0 && pl.splits != 1) return pl;       // the side output is written by the direct epilogue only
@@ -921,19 +922,21 @@ int gemm_tcgen05(const aecf_gemm_desc* d, const void* A, const void* B, const vo
         AECF_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, map_a, map_b, map_c, p));                                   \
     } while (0)
     static const bool two_sm_ew8 = [] { const char* e = getenv("AECF_GEMM_2SM_EW"); return e && e[0] == '8'; }();
-    if (pl.apanel) note_gemm_kernel("tcgen05 apanel bn%d ew%d", pl.bn, two_sm_ew8 ? 8 : 4);
+    if (pl.apanel) note_gemm_kernel("tcgen05 apanel bn%d ew%d kb%d", pl.bn, two_sm_ew8 ? 8 : 4, pl.kb_total > 8 ? 9 : 8);
     else if (pl.two_sm) note_gemm_kernel("tcgen05 2sm bn%d ew%d%s splits%d", pl.bn, two_sm_ew8 ? 8 : 4, pl.bn == 192 ? " aux" : "", pl.splits);
     else note_gemm_kernel("tcgen05 1sm bn%d cluster%d epi%d splits%d", pl.bn, pl.cluster, epi, pl.splits);
-#define AECF_AP_LAUNCH(BN_)                                                                                          \
+#define AECF_AP_LAUNCH(BN_, PKB_)                                                                                    \
     do {                                                                                                              \
-        auto kernel = two_sm_ew8 ? gemm_tcgen05_apanel_ew8_kernel<BN_> : gemm_tcgen05_apanel_kernel<BN_>;             \
+        auto kernel = two_sm_ew8 ? gemm_tcgen05_apanel_ew8_kernel<BN_, PKB_> : gemm_tcgen05_apanel_kernel<BN_, PKB_>; \
         if (two_sm_ew8) cfg.blockDim = dim3(NUM_THREADS + 128);                                                       \
-        cfg.dynamicSmemBytes = CfgAP<BN_>::SMEM_BYTES;                                                                \
-        AECF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgAP<BN_>::SMEM_BYTES)); \
+        cfg.dynamicSmemBytes = CfgAP<BN_, PKB_>::SMEM_BYTES;                                                          \
+        AECF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgAP<BN_, PKB_>::SMEM_BYTES)); \
         AECF_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, map_a, map_b, map_c, p));                                       \
     } while (0)
     if (pl.apanel) {
-        if (pl.bn == 192) AECF_AP_LAUNCH(192); else AECF_AP_LAUNCH(256);
+        if (pl.bn == 192) AECF_AP_LAUNCH(192, 8);
+        else if (pl.kb_total > 8) AECF_AP_LAUNCH(256, 9);
+        else AECF_AP_LAUNCH(256, 8);
     } else if (pl.two_sm && pl.bn == 192) {
         auto kernel = two_sm_ew8 ? gemm_tcgen05_2sm_aux_ew8_kernel<192> : gemm_tcgen05_2sm_aux_kernel<192>;
         if (two_sm_ew8) cfg.blockDim = dim3(NUM_THREADS + 128);

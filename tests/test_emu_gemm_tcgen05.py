@@ -26,7 +26,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # tiles and three tiles per CTA (both accumulators re-used); cta_group::2 (10 k-blocks); split-K with a ragged k tail
 # several row-block groups per CTA pair with two column tiles each (the resident-A-panel kernel's slot hand-over)
 SHAPES = [(128, 128, 64), (256, 256, 64), (384, 256, 128), (200, 136, 72), (392, 520, 200), (512, 256, 640), (300, 512, 4100),
-          (1024, 512, 128)]
+          (1024, 512, 128), (512, 512, 520)]         # ... and nine k-blocks, the last one ragged: the dX contraction
 LAYOUTS = [(_lib.K_MAJOR, _lib.K_MAJOR), (_lib.K_MAJOR, _lib.MN_MAJOR), (_lib.MN_MAJOR, _lib.MN_MAJOR), (_lib.MN_MAJOR, _lib.K_MAJOR)]
 
 
@@ -73,9 +73,9 @@ def test_reported_kernel_follows_the_switches():
     a, b = torch.randn(512, 128, dtype=bf), torch.randn(256, 128, dtype=bf)
     apanel = env.get("AECF_GEMM_APANEL") == "1" and cluster == "2"
     ops.gemm(a, b, m=512, n=256, k=128, a_layout=_lib.K_MAJOR, b_layout=_lib.K_MAJOR, lda=128, ldb=128)           # 2 k-blocks
-    assert _lib.gemm_last_kernel() == (f"tcgen05 apanel bn256 ew{ew}" if apanel else f"tcgen05 1sm bn256 cluster{cluster} epi{epi} splits1")
+    assert _lib.gemm_last_kernel() == (f"tcgen05 apanel bn256 ew{ew} kb8" if apanel else f"tcgen05 1sm bn256 cluster{cluster} epi{epi} splits1")
     ops.gemm(a, b, m=512, n=256, k=128, a_layout=_lib.K_MAJOR, b_layout=_lib.K_MAJOR, lda=128, ldb=128, out_dtype=torch.float32)
-    assert _lib.gemm_last_kernel() == (f"tcgen05 apanel bn256 ew{ew}" if apanel else
+    assert _lib.gemm_last_kernel() == (f"tcgen05 apanel bn256 ew{ew} kb8" if apanel else
                                        f"tcgen05 1sm bn256 cluster{cluster} epi{'1' if epi == '3' else epi} splits1")   # EPI 3: bf16 output only
     a, b = torch.randn(512, 640, dtype=bf), torch.randn(256, 640, dtype=bf)
     ops.gemm(a, b, m=512, n=256, k=640, a_layout=_lib.K_MAJOR, b_layout=_lib.K_MAJOR, lda=640, ldb=640)           # 10 k-blocks
@@ -84,7 +84,7 @@ def test_reported_kernel_follows_the_switches():
     ops.gemm_aux(a, b, m=640, n=512, k=512, aux_cols=8)
     want = f"tcgen05 2sm bn192 ew{ew} aux splits1" if (env.get("AECF_GEMM_2SM_AUX") == "1" and cluster == "2") else f"tcgen05 1sm bn192 cluster{cluster} epi{epi} splits1"
     if apanel:
-        want = f"tcgen05 apanel bn192 ew{ew}"                              # K = 512: eight k-blocks, the panel fits
+        want = f"tcgen05 apanel bn192 ew{ew} kb8"                              # K = 512: eight k-blocks, the panel fits
     assert _lib.gemm_last_kernel() == want
     ops.gemm(a[:64].float(), b[:64].float(), m=64, n=64, k=512, a_layout=_lib.K_MAJOR, b_layout=_lib.K_MAJOR, lda=512, ldb=512)
     assert _lib.gemm_last_kernel() == "simt"
@@ -94,8 +94,7 @@ VARIANTS = {"pipelined_epilogue": {"AECF_GEMM_EPI": "2"},
             "eight_warp_epilogues": {"AECF_GEMM_EPI": "3", "AECF_GEMM_2SM_EW": "8"},          # 1SM (cluster of two) and cta_group::2
             "eight_warp_epilogue_no_cluster": {"AECF_GEMM_EPI": "3", "AECF_GEMM_CLUSTER": "1"},
             "score_columns_on_cta_pairs": {"AECF_GEMM_2SM_AUX": "1", "AECF_GEMM_2SM_EW": "8"},
-            "resident_a_panel": {"AECF_GEMM_APANEL": "1"},
-            "resident_a_panel_eight_warps": {"AECF_GEMM_APANEL": "1", "AECF_GEMM_2SM_EW": "8"}}
+            "resident_a_panel": {"AECF_GEMM_APANEL": "1", "AECF_GEMM_2SM_EW": "8"}}     # four epilogue warps: checked by hand runs
 
 
 @pytest.fixture(scope="module")
@@ -107,7 +106,7 @@ def variant_runs():
         return
     from tests.emu_support import load_emulation
     load_emulation()                                     # build once, before the children race for it
-    select = "(test_kernels and (384x256x128 or 392x520x200 or 512x256x640 or 1024x512x128)) or side_output or whole_step or reported_kernel"
+    select = "(test_kernels and (384x256x128 or 392x520x200 or 512x256x640 or 1024x512x128 or 512x512x520)) or side_output or whole_step or reported_kernel"
     runs = {}
     for name, switches in VARIANTS.items():
         env = dict(os.environ, AECF_EMU_GEMM_CHILD="1", **switches)
