@@ -513,7 +513,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         uint8_t* box_base = wbuf + ((box_it + (g >> 1)) & 1) * (32 * 128);
                         uint8_t* box = box_base + lane * 128;
                         if ((g & 1) == 0) {
-#ifndef AECF_CUDA_EMU
+#ifdef AECF_CUDA_EMU
+                            if (lane == 0) cuda_emu::tc::store_wait_read(1);
+#else
                             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
 #endif
                             __syncwarp();

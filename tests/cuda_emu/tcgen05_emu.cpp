@@ -4,6 +4,8 @@
 
 #include <cuda_bf16.h>
 
+#include <vector>
+
 namespace cuda_emu {
 namespace tc {
 namespace {
@@ -20,6 +22,11 @@ static_assert(sizeof(TensorMap) <= sizeof(CUtensorMap), "the emulated tensor map
 
 MBar g_bars[MAX_CLUSTER][SMEM_BYTES / 8];
 float g_tmem[MAX_CLUSTER][128][512];
+
+// bulk async-groups are per thread: stores issued, groups committed, not yet read out of shared memory
+struct PendingStore { TensorMap map; int cta; size_t src_off; int c0, c1; };
+struct StoreQueue { std::vector<PendingStore> open; std::vector<std::vector<PendingStore>> committed; };
+StoreQueue g_stores[MAX_CLUSTER][1024];
 
 [[noreturn]] void fail(const char* what) {
     std::fprintf(stderr, "cuda_emu/tcgen05: %s\n", what);
@@ -134,11 +141,12 @@ void tma_load(const CUtensorMap* map, const void* bar, int bar_cta, void* dst, i
     }
 }
 
-void tma_store(const CUtensorMap* map, const void* src, int c0, int c1) {
-    const TensorMap& t = view(map);
-    int cta; size_t src_off;
-    locate(src, &cta, &src_off);
-    if (t.box_inner * t.element_bytes != 128 || src_off % 1024 != 0) fail("TMA store box is not one 1024-aligned 128-byte swizzle atom wide");
+namespace {
+void perform_store(const PendingStore& ps) {
+    const TensorMap& t = ps.map;
+    const int cta = ps.cta;
+    const size_t src_off = ps.src_off;
+    const int c0 = ps.c0, c1 = ps.c1;
     const unsigned char* window = smem_window(cta);
     for (uint32_t r = 0; r < t.box_outer; ++r)
         for (uint32_t i = 0; i < t.box_inner; ++i) {
@@ -147,6 +155,30 @@ void tma_store(const CUtensorMap* map, const void* src, int c0, int c1) {
             std::memcpy(t.base + row * t.row_stride_bytes + col * t.element_bytes,
                         window + swizzle128(src_off + static_cast<size_t>(r) * 128 + static_cast<size_t>(i) * t.element_bytes), t.element_bytes);
         }
+}
+StoreQueue& my_stores() { return g_stores[cta_rank()][thread().linear]; }
+}  // namespace
+
+void tma_store(const CUtensorMap* map, const void* src, int c0, int c1) {
+    const TensorMap& t = view(map);
+    int cta; size_t src_off;
+    locate(src, &cta, &src_off);
+    if (t.box_inner * t.element_bytes != 128 || src_off % 1024 != 0) fail("TMA store box is not one 1024-aligned 128-byte swizzle atom wide");
+    my_stores().open.push_back(PendingStore{t, cta, src_off, c0, c1});      // shared memory is read when the group retires
+}
+
+void store_commit() {
+    StoreQueue& q = my_stores();
+    q.committed.push_back(std::move(q.open));
+    q.open.clear();
+}
+
+void store_wait_read(int pending_allowed) {
+    StoreQueue& q = my_stores();
+    while (static_cast<int>(q.committed.size()) > pending_allowed) {
+        for (const PendingStore& ps : q.committed.front()) perform_store(ps);
+        q.committed.erase(q.committed.begin());
+    }
 }
 
 void tmem_alloc(uint32_t* slot, uint32_t columns) {
@@ -205,8 +237,11 @@ CUresult encode_tiled(CUtensorMap* map, CUtensorMapDataType dt, cuuint32_t rank,
 }  // namespace tc
 
 void reset_block_resources(int cluster) {
-    for (int c = 0; c < cluster; ++c)
+    for (int c = 0; c < cluster; ++c) {
         for (auto& b : tc::g_bars[c]) b.live = false;
+        for (auto& q : tc::g_stores[c])
+            if (!q.open.empty() || !q.committed.empty()) tc::fail("the previous kernel exited with TMA stores it never waited for");
+    }
 }
 
 }  // namespace cuda_emu

@@ -26,9 +26,9 @@ inline void tma_load_2d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, in
     ::cuda_emu::tc::tma_load(map, bar, 0, dst, c0, c1, 1u << ::cuda_emu::cta_rank());   // bytes complete on the LEADER's barrier
 }
 inline void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) { ::cuda_emu::tc::tma_store(map, src, c0, c1); }
-inline void tma_store_commit() {}
-inline void tma_store_wait_read() {}
-inline void tma_store_wait_all() {}
+inline void tma_store_commit() { ::cuda_emu::tc::store_commit(); }
+inline void tma_store_wait_read() { ::cuda_emu::tc::store_wait_read(0); }
+inline void tma_store_wait_all() { ::cuda_emu::tc::store_wait_read(0); }
 inline void prefetch_tmap(const CUtensorMap*) {}
 
 inline void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {

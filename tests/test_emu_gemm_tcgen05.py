@@ -44,6 +44,26 @@ def test_kernels(shape, layouts):
     G.test_tcgen05_gemm(shape, *layouts)
 
 
+@pytest.mark.xfail(strict=True, reason="latent staging hazard of the measured cta_group::2 instantiation with an ODD number of row "
+                                      "blocks (gemm_tcgen05_2sm.inc): kept token-identical until it can be re-measured; the fix is "
+                                      "in every other instantiation and replaces it at the first GPU run of round 2")
+def test_measured_cta_pair_kernel_with_an_odd_number_of_row_blocks():
+    """TMA stores of the emulation read their staging box at the latest moment the kernel allows.  Five row blocks on CTA
+    pairs leave a filler tile whose rounds commit no bulk group, so `wait_group.read 1` no longer protects the buffer of the
+    previous tile's last store.  (Benign on hardware so far: a whole tile's main loop lies in between.)"""
+    if os.environ.get("AECF_GEMM_2SM_EW") == "8":
+        pytest.skip("the eight-warp instantiation carries the fix: see test_fixed_cta_pair_kernels_with_an_odd_number_of_row_blocks")
+    if os.environ.get("AECF_GEMM_CLUSTER") == "1":
+        pytest.skip("without clusters the product runs on the single-CTA kernel")
+    G.test_tcgen05_gemm((640, 256, 640), _lib.K_MAJOR, _lib.K_MAJOR)
+
+
+def test_fixed_cta_pair_kernels_with_an_odd_number_of_row_blocks():
+    if os.environ.get("AECF_GEMM_2SM_EW") != "8":
+        pytest.skip("runs in the variant children with AECF_GEMM_2SM_EW=8")
+    G.test_tcgen05_gemm((640, 256, 640), _lib.K_MAJOR, _lib.K_MAJOR)
+
+
 def test_strided_operands_and_kernel_choice():
     G.test_tcgen05_strided_output_and_operand_views()
     G.test_tcgen05_is_what_auto_picks_for_the_projection_shapes()
@@ -106,7 +126,7 @@ def variant_runs():
         return
     from tests.emu_support import load_emulation
     load_emulation()                                     # build once, before the children race for it
-    select = "(test_kernels and (384x256x128 or 392x520x200 or 512x256x640 or 1024x512x128 or 512x512x520)) or side_output or whole_step or reported_kernel"
+    select = "(test_kernels and (384x256x128 or 392x520x200 or 512x256x640 or 1024x512x128 or 512x512x520)) or side_output or whole_step or reported_kernel or odd_number_of_row_blocks"
     runs = {}
     for name, switches in VARIANTS.items():
         env = dict(os.environ, AECF_EMU_GEMM_CHILD="1", **switches)
