@@ -155,9 +155,10 @@ template <> struct Vec<__nv_bfloat16> {
 #ifdef AECF_CUDA_EMU
 __device__ __forceinline__ uint4 ldg_stream(const void* p) { return *reinterpret_cast<const uint4*>(p); }
 __device__ __forceinline__ void stg_stream(void* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) { memcpy(smem_dst, gmem_src, 16); }
-__device__ __forceinline__ void cp_async_commit() {}
-template <int N> __device__ __forceinline__ void cp_async_wait() {}
+// deferred like the emulation's TMA stores: the 16 bytes land when cp.async.wait_group retires their group, not before
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) { cuda_emu::cp_async_enqueue(smem_dst, gmem_src); }
+__device__ __forceinline__ void cp_async_commit() { cuda_emu::cp_async_commit_group(); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { cuda_emu::cp_async_wait_group(N); }
 #else
 // Streaming 128-bit load of read-once data: read-only path, do not allocate in L1.
 __device__ __forceinline__ uint4 ldg_stream(const void* p) {

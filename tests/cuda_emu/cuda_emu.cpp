@@ -17,7 +17,12 @@ namespace {
 constexpr size_t STACK_BYTES = 1 << 20;
 constexpr int MAX_THREADS = 1024, MAX_WARPS = 32, NAMED_BARRIERS = 16;
 
-struct Fiber { ThreadState ts; ucontext_t ctx; bool done; int cta; };
+struct AsyncCopy { void* dst; const void* src; };
+struct Fiber {
+    ThreadState ts; ucontext_t ctx; bool done; int cta;
+    std::vector<AsyncCopy> open_copies;                   // cp.async issued since the last commit_group
+    std::vector<std::vector<AsyncCopy>> copy_groups;      // committed, not yet waited for
+};
 struct Warp { uint32_t slot[32]; int arrived; unsigned generation; int live; };
 struct Barrier { int arrived; unsigned generation; int count; };
 struct Cta {                                             // one thread block of the cluster that is running
@@ -60,6 +65,9 @@ void fiber_main() {
     Engine& e = engine();
     (*e.body)();
     Fiber& f = *e.current;
+    for (const auto& group : f.copy_groups)               // a thread that exits lets its outstanding copies land
+        for (const AsyncCopy& c : group) std::memcpy(c.dst, c.src, 16);
+    for (const AsyncCopy& c : f.open_copies) std::memcpy(c.dst, c.src, 16);
     Cta& c = e.ctas[f.cta];
     f.done = true;
     ++e.progress;
@@ -113,6 +121,20 @@ void run_cluster(Engine& e, dim3 block_dim) {
 }
 
 }  // namespace
+
+void cp_async_enqueue(void* smem_dst, const void* gmem_src) { engine().current->open_copies.push_back({smem_dst, gmem_src}); }
+void cp_async_commit_group() {
+    Fiber& f = *engine().current;
+    f.copy_groups.push_back(std::move(f.open_copies));
+    f.open_copies.clear();
+}
+void cp_async_wait_group(int pending_allowed) {
+    Fiber& f = *engine().current;
+    while (static_cast<int>(f.copy_groups.size()) > pending_allowed) {
+        for (const AsyncCopy& c : f.copy_groups.front()) std::memcpy(c.dst, c.src, 16);
+        f.copy_groups.erase(f.copy_groups.begin());
+    }
+}
 
 void yield() {
     Engine& e = engine();

@@ -67,6 +67,11 @@ void named_barrier(int id, int count, bool wait);      // count == 0: every thre
 void cluster_barrier();                                 // barrier.cluster.arrive + wait
 void warp_barrier();
 uint32_t warp_exchange(uint32_t value, int source_lane);
+// cp.async (LDGSTS) with the copies DEFERRED until the issuing thread's wait_group retires their group: staged data read
+// before its wait is stale here, as it may be on the device
+void cp_async_enqueue(void* smem_dst, const void* gmem_src);
+void cp_async_commit_group();
+void cp_async_wait_group(int pending_allowed);
 void yield();                                           // let the other fibers run (inside a wait loop)
 void made_progress();                                   // a wait condition changed: the deadlock detector's heartbeat
 void reset_block_resources(int cluster);                // tcgen05_emu.cpp: per-cluster mbarrier / tensor-memory state
