@@ -213,12 +213,29 @@ void mma_f16(int cta_group, uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, u
     }
 }
 
+// tcgen05.ld is asynchronous: the destination registers hold the data only after tcgen05.wait::ld.  Until then they are
+// poisoned here (a quiet NaN pattern), and the values are delivered by the wait.
+namespace {
+struct PendingLoad { uint32_t* dst; uint32_t values[32]; };
+std::vector<PendingLoad> g_loads[MAX_CLUSTER][1024];
+}  // namespace
+
 void tmem_load_32x32(uint32_t taddr, uint32_t* out32) {
     const int lane_base = static_cast<int>(taddr >> 16), col = static_cast<int>(taddr & 0xFFFF);
     const ThreadState& t = thread();
     if (lane_base != (t.warp % 4) * 32) fail("tcgen05.ld: a warp may only read the TMEM lane quadrant warp_id % 4");
     if (col + 32 > 512) fail("tcgen05.ld beyond column 511");
-    std::memcpy(out32, &g_tmem[cta_rank()][lane_base + t.lane][col], 32 * sizeof(float));
+    PendingLoad p;
+    p.dst = out32;
+    std::memcpy(p.values, &g_tmem[cta_rank()][lane_base + t.lane][col], 32 * sizeof(float));
+    for (int i = 0; i < 32; ++i) out32[i] = 0x7FC0DEADu;
+    g_loads[cta_rank()][t.linear].push_back(p);
+}
+
+void tmem_load_wait() {
+    auto& q = g_loads[cta_rank()][thread().linear];
+    for (const PendingLoad& p : q) std::memcpy(p.dst, p.values, sizeof(p.values));
+    q.clear();
 }
 
 CUresult encode_tiled(CUtensorMap* map, CUtensorMapDataType dt, cuuint32_t rank, void* ptr, const cuuint64_t* dims,
@@ -241,6 +258,7 @@ void reset_block_resources(int cluster) {
         for (auto& b : tc::g_bars[c]) b.live = false;
         for (auto& q : tc::g_stores[c])
             if (!q.open.empty() || !q.committed.empty()) tc::fail("the previous kernel exited with TMA stores it never waited for");
+        for (auto& q : tc::g_loads[c]) q.clear();
     }
 }
 

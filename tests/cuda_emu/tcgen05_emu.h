@@ -9,8 +9,8 @@
 // a store reads its shared-memory box only when the issuing thread's wait_group[.read] retires its bulk group -- so a
 // staging box that is refilled before the wait that protects it produces wrong output, and a kernel that exits with
 // stores it never waited for is an error.  What it can catch is therefore logic -- barrier counts and phases, tile / box /
-// column indexing, descriptor arithmetic, who arrives where -- and that one class of missing wait; not fences, not the
-// other asynchronous hazards.
+// column indexing, descriptor arithmetic, who arrives where -- and two classes of missing wait (that one, and tcgen05.ld registers used
+// before tcgen05.wait::ld: they are poisoned until the wait); not fences, not the other asynchronous hazards.
 // Its layouts are validated by the kernels that were measured on hardware producing correct products under it.
 #pragma once
 
@@ -27,7 +27,8 @@ void store_commit();                                    // cp.async.bulk.commit_
 void store_wait_read(int pending_allowed);              // cp.async.bulk.wait_group[.read] N: older groups read shared memory NOW
 void tmem_alloc(uint32_t* slot, uint32_t columns);
 void mma_f16(int cta_group, uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate);
-void tmem_load_32x32(uint32_t taddr, uint32_t* out32);
+void tmem_load_32x32(uint32_t taddr, uint32_t* out32);   // registers are poisoned until tmem_load_wait()
+void tmem_load_wait();                                  // tcgen05.wait::ld
 CUresult encode_tiled(CUtensorMap* map, CUtensorMapDataType dt, cuuint32_t rank, void* ptr, const cuuint64_t* dims,
                       const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* element_strides, CUtensorMapInterleave,
                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

@@ -44,5 +44,5 @@ inline void umma_commit_mc(uint64_t* bar, uint16_t mask) {
 }
 inline void umma_commit_2sm(uint64_t* bar, uint16_t mask) { umma_commit_mc(bar, mask); }
 inline void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) { ::cuda_emu::tc::tmem_load_32x32(taddr, r); }
-inline void tmem_ld_wait() {}
-inline void tmem_ld_wait_on(uint32_t (&)[32]) {}
+inline void tmem_ld_wait() { ::cuda_emu::tc::tmem_load_wait(); }
+inline void tmem_ld_wait_on(uint32_t (&)[32]) { ::cuda_emu::tc::tmem_load_wait(); }
