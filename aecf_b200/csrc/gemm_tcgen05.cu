@@ -672,23 +672,27 @@ template <int BN> struct Cfg2 {
 #define AECF_2SM_EW 4
 #define AECF_2SM_EPI_T EPI_THREADS
 #define AECF_2SM_AUX 0
+#define AECF_2SM_FIXED 0
 #include "gemm_tcgen05_2sm.inc"
 #undef AECF_2SM_KERNEL
 #undef AECF_2SM_THREADS
 #undef AECF_2SM_EW
 #undef AECF_2SM_EPI_T
 #undef AECF_2SM_AUX
+#undef AECF_2SM_FIXED
 #define AECF_2SM_KERNEL gemm_tcgen05_2sm_ew8_kernel
 #define AECF_2SM_THREADS (NUM_THREADS + 128)
 #define AECF_2SM_EW 8
 #define AECF_2SM_EPI_T 256
 #define AECF_2SM_AUX 0
+#define AECF_2SM_FIXED 0
 #include "gemm_tcgen05_2sm.inc"
 #undef AECF_2SM_KERNEL
 #undef AECF_2SM_THREADS
 #undef AECF_2SM_EW
 #undef AECF_2SM_EPI_T
 #undef AECF_2SM_AUX
+#undef AECF_2SM_FIXED
 // A-resident CTA-pair kernel (AECF_GEMM_APANEL=1), see gemm_tcgen05_apanel.inc
 template <int BN, int PKB> struct CfgAP {
     static constexpr int PANEL_KB = PKB;                        // k-blocks of A kept resident: 8 (K <= 512) or 9 (K = 520, dX)
@@ -722,29 +726,47 @@ static_assert(CfgAP<256, 8>::SMEM_BYTES <= 232448 && CfgAP<256, 9>::SMEM_BYTES <
 #undef AECF_AP_EW
 #undef AECF_AP_EPI_T
 
+// the measured four-warp kernel with the bulk-group fix (AECF_GEMM_2SM_FIX=1), to become the default once re-measured
+#define AECF_2SM_KERNEL gemm_tcgen05_2sm_fixed_kernel
+#define AECF_2SM_THREADS NUM_THREADS
+#define AECF_2SM_EW 4
+#define AECF_2SM_EPI_T EPI_THREADS
+#define AECF_2SM_AUX 0
+#define AECF_2SM_FIXED 1
+#include "gemm_tcgen05_2sm.inc"
+#undef AECF_2SM_KERNEL
+#undef AECF_2SM_THREADS
+#undef AECF_2SM_EW
+#undef AECF_2SM_EPI_T
+#undef AECF_2SM_AUX
+#undef AECF_2SM_FIXED
 // the folded forward's 192-wide tiles with the fp32 score side output on CTA pairs (AECF_GEMM_2SM_AUX=1), both widths
 #define AECF_2SM_KERNEL gemm_tcgen05_2sm_aux_kernel
 #define AECF_2SM_THREADS NUM_THREADS
 #define AECF_2SM_EW 4
 #define AECF_2SM_EPI_T 128
 #define AECF_2SM_AUX 1
+#define AECF_2SM_FIXED 0
 #include "gemm_tcgen05_2sm.inc"
 #undef AECF_2SM_KERNEL
 #undef AECF_2SM_THREADS
 #undef AECF_2SM_EW
 #undef AECF_2SM_EPI_T
 #undef AECF_2SM_AUX
+#undef AECF_2SM_FIXED
 #define AECF_2SM_KERNEL gemm_tcgen05_2sm_aux_ew8_kernel
 #define AECF_2SM_THREADS (NUM_THREADS + 128)
 #define AECF_2SM_EW 8
 #define AECF_2SM_EPI_T 256
 #define AECF_2SM_AUX 1
+#define AECF_2SM_FIXED 0
 #include "gemm_tcgen05_2sm.inc"
 #undef AECF_2SM_KERNEL
 #undef AECF_2SM_THREADS
 #undef AECF_2SM_EW
 #undef AECF_2SM_EPI_T
 #undef AECF_2SM_AUX
+#undef AECF_2SM_FIXED
 
 // ---- host side -------------------------------------------------------------------------------
 using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -946,7 +968,8 @@ int gemm_tcgen05(const aecf_gemm_desc* d, const void* A, const void* B, const vo
         AECF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<192>::SMEM_BYTES));
         AECF_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, map_a, map_b, map_c, p));
     } else if (pl.two_sm) {
-        auto kernel = two_sm_ew8 ? gemm_tcgen05_2sm_ew8_kernel<256> : gemm_tcgen05_2sm_kernel<256>;
+        static const bool two_sm_fix = [] { const char* e = getenv("AECF_GEMM_2SM_FIX"); return e && e[0] == '1'; }();
+        auto kernel = two_sm_ew8 ? gemm_tcgen05_2sm_ew8_kernel<256> : (two_sm_fix ? gemm_tcgen05_2sm_fixed_kernel<256> : gemm_tcgen05_2sm_kernel<256>);
         if (two_sm_ew8) cfg.blockDim = dim3(NUM_THREADS + 128);
         cfg.dynamicSmemBytes = Cfg2<256>::SMEM_BYTES;
         AECF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<256>::SMEM_BYTES));

@@ -51,16 +51,16 @@ def test_measured_cta_pair_kernel_with_an_odd_number_of_row_blocks():
     """TMA stores of the emulation read their staging box at the latest moment the kernel allows.  Five row blocks on CTA
     pairs leave a filler tile whose rounds commit no bulk group, so `wait_group.read 1` no longer protects the buffer of the
     previous tile's last store.  (Benign on hardware so far: a whole tile's main loop lies in between.)"""
-    if os.environ.get("AECF_GEMM_2SM_EW") == "8":
-        pytest.skip("the eight-warp instantiation carries the fix: see test_fixed_cta_pair_kernels_with_an_odd_number_of_row_blocks")
+    if os.environ.get("AECF_GEMM_2SM_EW") == "8" or os.environ.get("AECF_GEMM_2SM_FIX") == "1":
+        pytest.skip("these instantiations carry the fix: see test_fixed_cta_pair_kernels_with_an_odd_number_of_row_blocks")
     if os.environ.get("AECF_GEMM_CLUSTER") == "1":
         pytest.skip("without clusters the product runs on the single-CTA kernel")
     G.test_tcgen05_gemm((640, 256, 640), _lib.K_MAJOR, _lib.K_MAJOR)
 
 
 def test_fixed_cta_pair_kernels_with_an_odd_number_of_row_blocks():
-    if os.environ.get("AECF_GEMM_2SM_EW") != "8":
-        pytest.skip("runs in the variant children with AECF_GEMM_2SM_EW=8")
+    if os.environ.get("AECF_GEMM_2SM_EW") != "8" and os.environ.get("AECF_GEMM_2SM_FIX") != "1":
+        pytest.skip("runs in the variant children with AECF_GEMM_2SM_EW=8 or AECF_GEMM_2SM_FIX=1")
     G.test_tcgen05_gemm((640, 256, 640), _lib.K_MAJOR, _lib.K_MAJOR)
 
 
@@ -110,7 +110,7 @@ def test_reported_kernel_follows_the_switches():
     assert _lib.gemm_last_kernel() == "simt"
 
 
-VARIANTS = {"pipelined_epilogue": {"AECF_GEMM_EPI": "2"},
+VARIANTS = {"pipelined_epilogue_and_fixed_cta_pairs": {"AECF_GEMM_EPI": "2", "AECF_GEMM_2SM_FIX": "1"},
             "eight_warp_epilogues": {"AECF_GEMM_EPI": "3", "AECF_GEMM_2SM_EW": "8"},          # 1SM (cluster of two) and cta_group::2
             "eight_warp_epilogue_no_cluster": {"AECF_GEMM_EPI": "3", "AECF_GEMM_CLUSTER": "1"},
             "score_columns_on_cta_pairs": {"AECF_GEMM_2SM_AUX": "1", "AECF_GEMM_2SM_EW": "8"},

@@ -62,3 +62,10 @@ def test_resident_a_panel_kernel_passes_the_gemm_and_parity_suites():
     _pytest_with({"AECF_GEMM_APANEL": "1"},
                  ["tests/test_gpu_gemm_tcgen05.py", "tests/test_gpu_parity.py", "-k",
                   "gemm or side_output or bf16 or folded or headline or sharding"])
+
+
+def test_cta_pair_kernel_with_the_bulk_group_fix_passes_the_gemm_and_parity_suites():
+    """AECF_GEMM_2SM_FIX=1: the measured cta_group::2 kernel committing one bulk group per epilogue round, stored or not."""
+    _pytest_with({"AECF_GEMM_2SM_FIX": "1"},
+                 ["tests/test_gpu_gemm_tcgen05.py", "tests/test_gpu_parity.py", "-k",
+                  "gemm or side_output or bf16 or folded or headline or sharding"])
