@@ -968,7 +968,9 @@ int gemm_tcgen05(const aecf_gemm_desc* d, const void* A, const void* B, const vo
         AECF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<192>::SMEM_BYTES));
         AECF_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, map_a, map_b, map_c, p));
     } else if (pl.two_sm) {
-        static const bool two_sm_fix = [] { const char* e = getenv("AECF_GEMM_2SM_FIX"); return e && e[0] == '1'; }();
+        // default: the kernel that commits one bulk group per epilogue round; AECF_GEMM_2SM_FIX=0 selects the round-1
+        // instantiation without it for ONE same-box A/B (r2 run 1), after which that instantiation is deleted
+        static const bool two_sm_fix = [] { const char* e = getenv("AECF_GEMM_2SM_FIX"); return !(e && e[0] == '0'); }();
         auto kernel = two_sm_ew8 ? gemm_tcgen05_2sm_ew8_kernel<256> : (two_sm_fix ? gemm_tcgen05_2sm_fixed_kernel<256> : gemm_tcgen05_2sm_kernel<256>);
         if (two_sm_ew8) cfg.blockDim = dim3(NUM_THREADS + 128);
         cfg.dynamicSmemBytes = Cfg2<256>::SMEM_BYTES;

@@ -222,7 +222,8 @@ class MultimodalAttentionPool(nn.Module):
     """Attention pooling over modality tokens (reference ``aecf/AECFLayer.py:322-552``).
 
     ``forward(query, key, value=None, key_padding_mask=None, attn_mask=None, return_info=False,
-    use_checkpoint=False)``; ``query`` must hold a single fusion token per sample (target length 1).
+    use_checkpoint=False)``; ``query`` is ``[B, S, D]`` -- S = 1 (one fusion token per sample, usually an expand of
+    one ``[1, 1, D]`` parameter) is the hot path, S > 1 runs the multi-query kernels.
     """
 
     def __init__(self, embed_dim: int, num_heads: int = 1, dropout: float = 0.0, bias: bool = True,
@@ -338,13 +339,8 @@ class MultimodalAttentionPool(nn.Module):
         ops.require_cuda(query, key, value, self.attention.in_proj_weight)
         if embed != self.embed_dim:
             raise RuntimeError(f"was expecting embedding dimension of {self.embed_dim}, but got {embed}")
-        # several queries per sample run on their own kernels (csrc/pool_multi.cuh), which have not been run on
-        # hardware yet: opt-in with AECF_MULTI_QUERY=1 until tests/test_gpu_multi_query.py has passed on a B200
-        multi = tgt_len > 1 and os.environ.get("AECF_MULTI_QUERY") == "1"
-        if tgt_len != 1 and not multi:
-            raise ops._lib.UnsupportedShapeError(
-                ops._lib.ERR_UNSUPPORTED, "MultimodalAttentionPool",
-                f"the fused pool covers one fusion query per sample (target length 1), got {tgt_len}")
+        # several queries per sample run on their own kernels (csrc/pool_multi.cuh)
+        multi = tgt_len > 1
         att = self.attention
         dt = att.in_proj_weight.dtype
         if query.dtype != dt or key.dtype != dt or (value is not None and value.dtype != dt):

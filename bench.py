@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument("--heads", type=int, default=8)
     ap.add_argument("--dtype", choices=["bf16", "fp32"], default="bf16")
     ap.add_argument("--dropout", type=float, default=0.0)
-    ap.add_argument("--cpu-sample", type=int, default=4096, help="rows of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="rows of the CPU-baseline sample (0: the full batch, halved only if 4 steps would take > 40 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--dp-study", action="store_true",
@@ -146,9 +146,51 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU baseline: the oracle port of the reference path, all host threads, bounded sample
+# The reference arm and the CPU baseline: the UNMODIFIED reference from baseline/_ref (installed there with
+# `pip install --no-index --no-deps --target baseline/_ref`), stock autograd, all host threads;
+# the oracle port only where baseline/_ref is absent (kind says which).
 # ------------------------------------------------------------------------------------------------
-def cpu_step_fn(args, rows):
+def load_reference():
+    """The reference package as installed under baseline/_ref, imported under a private name (the repo's own drop-in
+    alias package is also called `aecf`).  None when it is not there."""
+    init = os.path.join(ROOT, "baseline", "_ref", "aecf", "__init__.py")
+    if not os.path.exists(init):
+        return None
+    if "aecf_reference_unmodified" in sys.modules:
+        return sys.modules["aecf_reference_unmodified"]
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("aecf_reference_unmodified", init,
+                                                  submodule_search_locations=[os.path.dirname(init)])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["aecf_reference_unmodified"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def reference_step_fn(ref, args, rows, device, dtype):
+    """create_fusion_pool(D, M, 0.15, num_heads=H) default init, x = randn(rows, M, D), one step =
+    forward(return_info=True) + entropy_loss + autograd backward of out.pow(2).mean() + 0.01 * entropy_loss."""
+    import torch
+    torch.manual_seed(0)
+    M, D, H = args.tokens, args.dim, args.heads
+    query, pool = ref.create_fusion_pool(D, M, 0.15, num_heads=H, dropout=args.dropout)
+    pool = pool.to(device=device, dtype=dtype)
+    query = torch.nn.Parameter(query.detach().to(device=device, dtype=dtype))
+    x = torch.randn(rows, M, D).to(device=device, dtype=dtype).requires_grad_(True)
+    params = [query, x] + list(pool.parameters())
+
+    def step():
+        out, info = pool(query.expand(rows, -1, -1), x, return_info=True)
+        loss = out.float().pow(2).mean() + 0.01 * pool.curriculum_masking.entropy_loss(info["entropy"])
+        loss.backward()
+        for t in params:
+            t.grad = None
+        return loss
+    return step
+
+
+def port_step_fn(args, rows):
+    """Fallback when baseline/_ref is absent: the oracle port (closed-form backward, no autograd)."""
     import torch
     from oracle import aecf_oracle as oracle
     from oracle import philox
@@ -177,18 +219,61 @@ def cpu_step_fn(args, rows):
     return step
 
 
-def time_cpu(args, rows, steps, warmup):
+def time_cpu(args, rows, steps, warmup, budget_s=240.0):
+    """(samples/s, ms per step, threads, kind, rows timed).  The full batch unless (warmup + steps) steps of it would not
+    finish inside `budget_s` on this host, in which case the rows are halved until they do (and the line says so)."""
     import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    step = cpu_step_fn(args, rows)
-    for _ in range(warmup):
+    ref = load_reference()
+    kind = "reference" if ref is not None else "port"
+    make = (lambda r: reference_step_fn(ref, args, r, "cpu", torch.float32)) if ref is not None else (lambda r: port_step_fn(args, r))
+    step = make(rows)
+    t0 = time.perf_counter()
+    step()                                              # first warm-up step doubles as the probe
+    probe = time.perf_counter() - t0
+    while probe * (warmup + steps) > budget_s and rows > 1024:
+        rows //= 2
+        step = make(rows)
+        t0 = time.perf_counter()
+        step()
+        probe = time.perf_counter() - t0
+    for _ in range(max(0, warmup - 1)):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / steps
-    return rows / dt, dt * 1e3, cores
+    return rows / dt, dt * 1e3, cores, kind, rows
+
+
+def time_reference_gpu_eager(args, dev, steps=10, warmup=3):
+    """the unmodified reference on THIS B200 (stock PyTorch eager: cuBLAS + ~35 ATen ops and >= 5
+    host syncs per forward), same rows and dtype as the measured arm, CUDA events.  None without baseline/_ref."""
+    import torch
+    ref = load_reference()
+    if ref is None:
+        return None
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    try:
+        step = reference_step_fn(ref, args, args.batch, dev, dtype)
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            step()
+        b.record()
+        torch.cuda.synchronize(dev)
+        ms = a.elapsed_time(b) / steps
+        del step
+        torch.cuda.empty_cache()
+        return {"value": args.batch / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "warmup": warmup,
+                "dtype": args.dtype, "rows": args.batch,
+                "kind": "reference (baseline/_ref, unmodified) in stock PyTorch eager on this GPU, autograd backward"}
+    except Exception as e:                              # a baseline for context must never take the measurement down
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
 
 
 def cpu_model():
@@ -226,32 +311,31 @@ def workload_config(args, n_gpus):
               "not a bandwidth measurement")
     return {"workload": f"MultimodalAttentionPool D={args.dim} H={args.heads} M={args.tokens} with CurriculumMasking, "
                         + (f"B={args.global_batch} in total over {n_gpus} GPUs" if strong else f"B={args.batch} per GPU")
-                        + f", {args.dtype} (BASELINE.json configs[1])",
+                        + " (BASELINE.json configs[1]; arithmetic type in `dtype`)",
             "global_batch": args.global_batch if strong else args.batch * n_gpus,
             "tokens": args.tokens, "embed_dim": args.dim, "heads": args.heads,
             "dropout": args.dropout, "parallelism": f"dp{n_gpus}",
-            "fold_key_projection": bool(getattr(args, "folded", False)),
             "l2": l2,
-            "step": "forward(return_info) + entropy_loss + backward(d_out), public module API"
-                    + (", captured once with aecf_b200.graphs.GraphedStep and replayed" if getattr(args, "graph", "off") == "on"
-                       and getattr(args, "impl", "b200") == "b200" else "")}
+            "step": "forward(return_info) + entropy_loss + backward, public module API"}
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path (oracle port; the reference itself is pure Python over
-    torch and /root/reference is not on the GPU box), all host threads, bounded sample per step."""
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores -- the unmodified
+    package from baseline/_ref through its public API with autograd (the oracle port only if that install is absent),
+    all host threads, the arm's own workload (B rows, fp32 as BASELINE.md section 5 prescribes), --steps / --warmup honoured."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    rows = args.cpu_sample
-    value, ms, cores = time_cpu(args, rows, max(1, min(args.steps, 5)), max(1, min(args.warmup, 2)))
+    value, ms, cores, kind, rows = time_cpu(args, args.batch, max(1, args.steps), max(1, args.warmup))
+    cfg = workload_config(args, args.gpus)
+    sample = (f"{rows} rows per step" + ("" if rows == args.batch else f" (halved from {args.batch} to fit the time budget)")
+              + f", fp32, {'unmodified reference from baseline/_ref, autograd' if kind == 'reference' else 'oracle port, closed-form backward'}"
+              + f", {cores} threads ({cpu_model()})")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": max(1, min(args.steps, 5)), "warmup": max(1, min(args.warmup, 2)), "ms_per_step": ms,
+            "steps": max(1, args.steps), "warmup": max(1, args.warmup), "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, args.gpus),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{rows} rows of the same workload per step, fp32, torch CPU ops "
-                                       f"({cpu_model()})"},
+            "config": cfg, "same_config": rows == args.batch,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -559,6 +643,8 @@ def run_b200(args):
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "bf16" if dtype == torch.bfloat16 else "f32", "data": "synthetic",
             "config": workload_config(args, world), "impl": "b200",
+            "implementation": {"fold_key_projection": bool(args.folded),
+                               "cuda_graph": "step captured once with aecf_b200.graphs.GraphedStep and replayed" if use_graph else "eager"},
             "roofline": roof, "roofline_pool_fwd": hbm("pool_fwd", fwd_bytes),
             "pool_kernels_only": {"value": B / (pool_ms * 1e-3) if pool_ms else None, "unit": UNIT, "ms": pool_ms,
                                   "bytes_per_sample": (fwd_bytes + bwd_bytes) // B,
@@ -575,10 +661,13 @@ def run_b200(args):
         line["data_parallel"] = dp_info
 
     if world == 1 and not args.no_cpu_baseline:
-        cpu_value, cpu_ms, cores = time_cpu(args, args.cpu_sample, 3, 1)
-        line["cpu_baseline"] = {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"{args.cpu_sample} rows of the same workload per step, 3 steps, fp32, "
-                                          f"torch CPU ops ({cpu_model()})", "ms_per_step": cpu_ms}
+        line["reference_gpu_eager"] = time_reference_gpu_eager(args, dev)
+        cpu_value, cpu_ms, cores, kind, rows = time_cpu(args, args.cpu_sample or B, 3, 1, budget_s=40.0)
+        line["cpu_baseline"] = {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": kind,
+                                "sample": f"{rows} rows of the same workload per step, 1 warm-up + 3 timed steps, fp32, "
+                                          + ("unmodified reference (baseline/_ref), autograd" if kind == "reference"
+                                             else "oracle port, closed-form backward")
+                                          + f" ({cpu_model()})", "ms_per_step": cpu_ms}
     print(json.dumps(line))
     barrier()
     finish_process(world)

@@ -3,7 +3,6 @@
 import os, random, sys, time
 import torch
 sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
-os.environ["AECF_MULTI_QUERY"] = "1"
 from tests import test_gpu_multi_query as MQ
 from tests.golden.cases import Case, build_inputs
 from tests.helpers import run_oracle

@@ -47,7 +47,6 @@ from tests import test_gpu_parity as P
 from tests import test_gpu_multi_query as MQ
 from tests.golden.cases import Case, MULTI_QUERY_CASES
 P.DEV = "cpu"; MQ.DEV = "cpu"
-os.environ["AECF_MULTI_QUERY"] = "1"
 cases = [c for c in P.FP32_CASES if c.D <= 256] + [Case("tail7", B=7, M=3, D=64, H=8, dropout=0.1, data_seed=901), Case("one", B=1, M=8, D=32, H=1, data_seed=902),
          Case("b33", B=33, M=5, D=128, H=4, kpm=True, data_seed=903)]
 n = 0

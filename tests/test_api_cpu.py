@@ -258,9 +258,6 @@ def test_multi_query_host_plumbing(monkeypatch, batch_first):
     k = torch.randn(B, M, D, requires_grad=True) if batch_first else torch.randn(M, B, D, requires_grad=True)
     kpm = torch.zeros(B, M, dtype=torch.bool)
     am = torch.zeros(S, M)
-    with pytest.raises(_lib.UnsupportedShapeError, match="target length 1"):           # opt-in until run on hardware
-        pool(q, k, return_info=True)
-    monkeypatch.setenv("AECF_MULTI_QUERY", "1")
     out, info = pool(q, k, key_padding_mask=kpm, attn_mask=am, return_info=True)
     desc, tensors = calls["fwd"]
     assert (desc.batch, desc.tgt_len, desc.num_tokens, desc.q_is_shared, desc.fold_key) == (B, S, M, 0, 0)

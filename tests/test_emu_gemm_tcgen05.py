@@ -44,23 +44,12 @@ def test_kernels(shape, layouts):
     G.test_tcgen05_gemm(shape, *layouts)
 
 
-@pytest.mark.xfail(strict=True, reason="latent staging hazard of the measured cta_group::2 instantiation with an ODD number of row "
-                                      "blocks (gemm_tcgen05_2sm.inc): kept token-identical until it can be re-measured; the fix is "
-                                      "in every other instantiation and replaces it at the first GPU run of round 2")
-def test_measured_cta_pair_kernel_with_an_odd_number_of_row_blocks():
+def test_cta_pair_kernels_with_an_odd_number_of_row_blocks():
     """TMA stores of the emulation read their staging box at the latest moment the kernel allows.  Five row blocks on CTA
-    pairs leave a filler tile whose rounds commit no bulk group, so `wait_group.read 1` no longer protects the buffer of the
-    previous tile's last store.  (Benign on hardware so far: a whole tile's main loop lies in between.)"""
-    if os.environ.get("AECF_GEMM_2SM_EW") == "8" or os.environ.get("AECF_GEMM_2SM_FIX") == "1":
-        pytest.skip("these instantiations carry the fix: see test_fixed_cta_pair_kernels_with_an_odd_number_of_row_blocks")
+    pairs leave a filler tile; every epilogue round commits one (possibly empty) bulk group, so `wait_group.read 1` keeps
+    protecting the buffer of the previous tile's last store.  (The round-1 instantiation without that commit failed here.)"""
     if os.environ.get("AECF_GEMM_CLUSTER") == "1":
         pytest.skip("without clusters the product runs on the single-CTA kernel")
-    G.test_tcgen05_gemm((640, 256, 640), _lib.K_MAJOR, _lib.K_MAJOR)
-
-
-def test_fixed_cta_pair_kernels_with_an_odd_number_of_row_blocks():
-    if os.environ.get("AECF_GEMM_2SM_EW") != "8" and os.environ.get("AECF_GEMM_2SM_FIX") != "1":
-        pytest.skip("runs in the variant children with AECF_GEMM_2SM_EW=8 or AECF_GEMM_2SM_FIX=1")
     G.test_tcgen05_gemm((640, 256, 640), _lib.K_MAJOR, _lib.K_MAJOR)
 
 

@@ -82,8 +82,6 @@ def test_random_cases_against_the_live_reference(monkeypatch, seed):
                 dropout=rng.choice([0.0, 0.1, 0.3]), base_mask_prob=rng.choice([0.15, 0.6, 1.0]), min_active=rng.choice([1, 2, 3]),
                 training=rng.random() < 0.8, kpm=rng.random() < 0.3, pooled_grad=rng.random() < 0.5, offset=rng.randint(0, 99),
                 row0=rng.choice([0, 11]), data_seed=rng.randint(1000, 10 ** 6), peak=rng.choice([0.5, 1.0, 2.0]))
-    if multi:
-        monkeypatch.setenv("AECF_MULTI_QUERY", "1")
     inp = build_inputs(case)
 
     ref_cm = ref_mod.CurriculumMasking(**masking_kwargs(case))

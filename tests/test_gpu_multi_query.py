@@ -1,10 +1,5 @@
 """Several fusion queries per sample (target length S > 1; csrc/pool_multi.cuh) against the oracle and the
 reference's own outputs (tests/golden/s*.npz).
-
-NOT YET RUN ON HARDWARE: the module raises for S > 1 unless AECF_MULTI_QUERY=1, and these tests are skipped unless
-AECF_TEST_EXPERIMENTAL=1, so that the driver's `pytest -m gpu` only sees measured code paths.
-
-    AECF_TEST_EXPERIMENTAL=1 python -m pytest tests/test_gpu_multi_query.py -m gpu -q
 """
 import os
 
@@ -17,16 +12,10 @@ from oracle import aecf_oracle as oracle
 from tests.golden.cases import MULTI_QUERY_CASES, PHILOX_SEED, Case, build_inputs, masking_kwargs
 from tests.helpers import assert_close, load_golden, run_oracle
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("AECF_TEST_EXPERIMENTAL") != "1", reason="opt-in: AECF_TEST_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 FP32_TOL = 1e-5
 BF16_TOL = 2e-2
-
-
-@pytest.fixture(autouse=True)
-def _enable_multi_query(monkeypatch):
-    monkeypatch.setenv("AECF_MULTI_QUERY", "1")
 
 
 def expected_bits(mask: torch.Tensor) -> np.ndarray:
@@ -188,15 +177,3 @@ def test_attn_mask_per_query():
         assert_close("attention_weights", info["attention_weights"].cpu(), ref.info["attention_weights"], FP32_TOL, atol=FP32_TOL)
         assert np.array_equal(info["mask_bits"].cpu().numpy().reshape(-1), expected_bits(ref.info["mask"]))
         assert float(info["attention_weights"][:, 0, 1].abs().max()) == 0.0
-
-
-def test_single_query_is_unchanged_by_the_switch():
-    """AECF_MULTI_QUERY=1 does not touch target length 1: same kernels, same bits as the default path."""
-    from tests.golden.cases import CASES_BY_NAME
-    from tests.test_gpu_parity import run_cuda as run_single
-    case = CASES_BY_NAME["d64_h8_m3_dropout"]
-    inp = build_inputs(case)
-    a = run_single(case, inp, torch.float32)
-    os.environ.pop("AECF_MULTI_QUERY")
-    b = run_single(case, inp, torch.float32)
-    assert torch.equal(a[0], b[0]) and torch.equal(a[3]["key"], b[3]["key"])
