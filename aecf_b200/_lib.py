@@ -12,7 +12,7 @@ from typing import Optional
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libaecf_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # enums of include/aecf_b200.h
 F32, BF16 = 0, 1
@@ -22,11 +22,13 @@ OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_ALIGNMENT, ERR_WORKSPACE, ERR_CUDA = 0, -1
 
 EXPORTS = (
     "aecf_pool_fwd", "aecf_pool_bwd", "aecf_pool_bwd_workspace_bytes",
-    "aecf_fold_score_cols", "aecf_pool_fwd_folded", "aecf_pool_bwd_folded", "aecf_fold_prepare", "aecf_fold_finish",
+    "aecf_pool_loss_workspace_bytes", "aecf_pool_fwd_has_loss",
+    "aecf_fold_score_cols", "aecf_pool_fwd_folded", "aecf_pool_bwd_folded", "aecf_fold_prepare", "aecf_fold_prepare_query",
+    "aecf_fold_finish",
     "aecf_gemm", "aecf_gemm_aux", "aecf_gemm_workspace_bytes",
     "aecf_colsum", "aecf_colsum_workspace_bytes",
     "aecf_entropy_loss_fwd", "aecf_entropy_loss_bwd", "aecf_curriculum_mask", "aecf_entropy_bwd", "aecf_sdpa_fwd",
-    "aecf_fusion_fwd", "aecf_fusion_bwd", "aecf_fusion_workspace_bytes",
+    "aecf_fusion_fwd", "aecf_fusion_bwd", "aecf_fusion_workspace_bytes", "aecf_fusion_grad_sums_bytes",
     "aecf_peer_flag_bytes", "aecf_peer_enable_access", "aecf_peer_allreduce",
     "aecf_timing_enable", "aecf_timing_collect", "aecf_timing_site_name", "aecf_timing_site_gemm_kernel",
     "aecf_abi_version", "aecf_strerror", "aecf_last_cuda_error", "aecf_launch_count", "aecf_build_info",
@@ -47,6 +49,7 @@ class PoolDesc(C.Structure):
         ("fold_key", C.c_int32), ("tgt_len", C.c_int32),
         ("rng_state", C.c_void_p),
         ("q_stride_b", C.c_int64), ("q_stride_s", C.c_int64), ("bias_stride_s", C.c_int64),
+        ("loss_out", C.c_void_p), ("loss_workspace", C.c_void_p), ("loss_target", C.c_float), ("reserved0", C.c_int32),
     ]
 
 
@@ -72,14 +75,21 @@ class FusionTensors(C.Structure):
         "q_proj", "kv", "ctx", "out", "pooled", "entropy", "mask_rate", "masked", "mask_bits", "scores", "folded_w")]
 
 
+class DpDesc(C.Structure):
+    """aecf_dp_desc: the cross-rank gradient sum inside the backward (host arrays of `world` device pointers)."""
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("average", C.c_int32), ("reserved0", C.c_int32),
+                ("sums", C.POINTER(C.c_void_p)), ("reduced", C.POINTER(C.c_void_p)), ("flags", C.POINTER(C.c_void_p))]
+
+
 class FusionGrads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "d_out", "d_pooled", "d_entropy", "d_ctx", "d_kv", "d_q_rows",
-        "d_key", "d_value", "d_query", "d_in_proj_weight", "d_in_proj_bias", "d_out_proj_weight", "d_out_proj_bias")]
+        "d_key", "d_value", "d_query", "d_in_proj_weight", "d_in_proj_bias", "d_out_proj_weight", "d_out_proj_bias",
+        "side_stream", "fork_event", "join_event")] + [("dp", C.POINTER(DpDesc))]
 
 
 BWD_ALL, BWD_OUT_PROJ, BWD_REST = 0, 1, 2
-SITE_COUNT = 18
+SITE_COUNT = 21
 
 
 class AecfError(RuntimeError):
@@ -114,6 +124,14 @@ def _declare(lib):
     lib.aecf_pool_bwd_folded.argtypes = [C.POINTER(PoolDesc), vp, f32p, vp, f32p, vp, f32p, f32p, vp, f32p, vp, C.c_size_t, vp]
     lib.aecf_fold_prepare.restype = C.c_int
     lib.aecf_fold_prepare.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, f32p, vp, vp, vp]
+    lib.aecf_fold_prepare_query.restype = C.c_int
+    lib.aecf_fold_prepare_query.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, f32p, vp, vp]
+    lib.aecf_pool_loss_workspace_bytes.restype = C.c_size_t
+    lib.aecf_pool_loss_workspace_bytes.argtypes = []
+    lib.aecf_pool_fwd_has_loss.restype = C.c_int
+    lib.aecf_pool_fwd_has_loss.argtypes = [C.POINTER(PoolDesc), C.c_int32]
+    lib.aecf_fusion_grad_sums_bytes.restype = C.c_size_t
+    lib.aecf_fusion_grad_sums_bytes.argtypes = [C.POINTER(PoolDesc)]
     lib.aecf_fold_finish.restype = C.c_int
     lib.aecf_fold_finish.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, f32p, f32p, vp, vp, f32p, vp]
     lib.aecf_gemm_aux.restype = C.c_int

@@ -191,6 +191,11 @@ const char* aecf_build_info(void) {
 
 }  // extern "C"
 
+// the streaming forward kernel (one warp per sample, at most one CTA per SM) carries the fused entropy_loss term
+static bool pool_fwd_carries_loss(const PoolPlan& plan, const aecf_pool_desc& d) {
+    return !plan.multi && plan.p.WPS == 1 && d.masking == 1 && sm_count(d.device) <= POOL_LOSS_MAX_CTAS;
+}
+
 static int pool_fwd_impl(const aecf_pool_desc* desc, bool fold, const void* q, const float* scores, const void* kv,
                          const float* score_bias, void* ctx, float* pooled, float* entropy, float* mask_rate,
                          float* masked, uint8_t* mask_bits, void* stream) {
@@ -206,6 +211,13 @@ static int pool_fwd_impl(const aecf_pool_desc* desc, bool fold, const void* q, c
     p.ctx = ctx; p.pooled = pooled; p.entropy = entropy; p.mask_rate = mask_rate; p.masked = masked;
     p.mask_bits = mask_bits;
     const int sms = sm_count(desc->device);
+    if (desc->loss_out != nullptr && pool_fwd_carries_loss(plan, *desc)) {
+        if (desc->loss_workspace == nullptr || !aligned16(desc->loss_workspace)) return AECF_ERR_INVALID;
+        p.loss_out = desc->loss_out;
+        p.loss_partials = static_cast<float*>(desc->loss_workspace);
+        p.loss_ticket = reinterpret_cast<unsigned*>(p.loss_partials + POOL_LOSS_MAX_CTAS);
+        p.loss_target = desc->loss_target;
+    }
     TimedLaunch timed(static_cast<cudaStream_t>(stream));
     if (plan.multi) {                                   // one warp slice per (b, s) row; the bias travels in mq
         plan.mq.bias = score_bias;
@@ -238,6 +250,14 @@ int aecf_pool_fwd(const aecf_pool_desc* desc, const void* q, const void* kv, con
     return pool_fwd_impl(desc, false, q, nullptr, kv, score_bias, ctx, pooled, entropy, mask_rate, masked, mask_bits, stream);
 }
 
+size_t aecf_pool_loss_workspace_bytes(void) { return POOL_LOSS_MAX_CTAS * sizeof(float) + 64; }
+
+int aecf_pool_fwd_has_loss(const aecf_pool_desc* desc, int32_t folded) {
+    PoolPlan plan;
+    if (make_plan(desc, &plan, folded != 0) != AECF_OK) return 0;
+    return pool_fwd_carries_loss(plan, *desc) ? 1 : 0;
+}
+
 int aecf_pool_fwd_folded(const aecf_pool_desc* desc, const float* scores, const void* v, const float* score_bias,
                          void* ctx, float* pooled, float* entropy, float* mask_rate, float* masked,
                          uint8_t* mask_bits, void* stream) {
@@ -253,7 +273,8 @@ size_t aecf_pool_bwd_workspace_bytes(const aecf_pool_desc* desc) {
 
 static int pool_bwd_impl(const aecf_pool_desc* desc, bool fold, const void* q, const float* scores, const void* kv,
                          const float* score_bias, const void* d_ctx, const float* d_pooled, const float* d_entropy,
-                         void* d_kv, void* d_q, float* d_bias_kv, void* workspace, size_t workspace_bytes, void* stream) {
+                         void* d_kv, void* d_q, float* d_bias_kv, void* workspace, size_t workspace_bytes, void* stream,
+                         int* blocks_out = nullptr) {
     PoolPlan plan;
     int rc = make_plan(desc, &plan, fold);
     if (rc != AECF_OK) return rc;
@@ -282,21 +303,9 @@ static int pool_bwd_impl(const aecf_pool_desc* desc, bool fold, const void* q, c
     int grid = static_cast<int>(want < cap ? want : cap);
     if (grid < 1) grid = 1;
 
-    // EXPERIMENTAL (AECF_POOL_BWD_STREAM=1, logic verified under the host emulation, not yet run on hardware): the
-    // folded backward with cp.async-staged rows, pool_bwd_stream_kernel; read per call so that tests can switch it
-    const char* stream_env = getenv("AECF_POOL_BWD_STREAM");
-    const bool stream_variant = fold && !plan.multi && p.WPS == 1 && stream_env && stream_env[0] == '1';
     {
         TimedLaunch timed(static_cast<cudaStream_t>(stream));
-        if (stream_variant) {
-            const int sms = sm_count(desc->device);
-            if (plan.bf16)
-                rc = plan.drop ? launch_pool_bwd_stream<__nv_bfloat16, true>(plan.M, plan.J, p, sms, &grid, stream)
-                               : launch_pool_bwd_stream<__nv_bfloat16, false>(plan.M, plan.J, p, sms, &grid, stream);
-            else
-                rc = plan.drop ? launch_pool_bwd_stream<float, true>(plan.M, plan.J, p, sms, &grid, stream)
-                               : launch_pool_bwd_stream<float, false>(plan.M, plan.J, p, sms, &grid, stream);
-        } else if (plan.multi) {
+        if (plan.multi) {
             plan.mq.bias = score_bias;
             p.bias = nullptr;
             if (plan.bf16)
@@ -313,6 +322,10 @@ static int pool_bwd_impl(const aecf_pool_desc* desc, bool fold, const void* q, c
                            : launch_pool_bwd<float, false>(plan.M, plan.J, p, grid, fold, stream);
     }
     if (rc != AECF_OK) return rc;
+    if (blocks_out != nullptr) {                        // the caller folds the per-CTA partials itself (grad_tail.cu)
+        *blocks_out = grid;
+        return AECF_OK;
+    }
     const int n = 3 * p.D;
     TimedLaunch timed_finalize(static_cast<cudaStream_t>(stream), AECF_SITE_POOL_BWD_FINALIZE);
     AECF_CUDA_OK(launch_pdl(pool_bwd_finalize_kernel, dim3((n + 31) / 32), dim3(1024), 0, static_cast<cudaStream_t>(stream),
@@ -321,6 +334,16 @@ static int pool_bwd_impl(const aecf_pool_desc* desc, bool fold, const void* q, c
     count_launch();
     return AECF_OK;
 }
+
+namespace aecf {
+// fusion.cu: the folded backward without the finalize launch; *blocks = CTAs that wrote [3 D] partials into `workspace`
+int pool_bwd_folded_partials(const aecf_pool_desc* desc, const void* q_proj, const float* scores, const void* v,
+                             const float* score_bias, const void* d_ctx, const float* d_pooled, const float* d_entropy,
+                             void* d_vs, void* workspace, size_t workspace_bytes, void* stream, int* blocks) {
+    return pool_bwd_impl(desc, true, q_proj, scores, v, score_bias, d_ctx, d_pooled, d_entropy, d_vs, nullptr, nullptr,
+                         workspace, workspace_bytes, stream, blocks);
+}
+}  // namespace aecf
 
 extern "C" {
 

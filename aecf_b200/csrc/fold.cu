@@ -47,6 +47,64 @@ fold_prepare_kernel(const float* __restrict__ q_proj, const T* __restrict__ in_p
     for (size_t i = static_cast<size_t>(blockIdx.x - fold_blocks) * 256 + threadIdx.x; i < n16; i += stride) dst[i] = src[i];
 }
 
+// The same, starting from the UNPROJECTED fusion query: q_proj = Wq q0 + bq (torch/nn/functional.py:5854) is computed here,
+// so the forward of a shared query pays one launch before its GEMM instead of two (GEMV, then the fold).  Every block of
+// head r first forms that head's head_dim entries of q_proj in shared memory (one warp per entry, lanes along D, fixed
+// xor-shuffle order; 16 blocks repeat the same 64 dots of a 512-vector -- cheaper than a launch boundary); the block of
+// strip 0 also writes them out, the backward needs q_proj.
+template <typename T>
+__global__ void __launch_bounds__(256)
+fold_prepare_query_kernel(const T* __restrict__ query, const T* __restrict__ in_proj_weight, const T* __restrict__ in_proj_bias,
+                          int D, int H, int HSP, float scale, int fold_blocks, float* __restrict__ q_proj,
+                          T* __restrict__ folded_w) {
+    __shared__ float red[8][33];
+    AECF_DYNAMIC_SMEM(float, qh);                                 // [head_dim]
+    pdl_wait();
+    const int hd = D / H;
+    if (static_cast<int>(blockIdx.x) < fold_blocks) {
+        const int strips = (D + 31) / 32;
+        const int r = blockIdx.x / strips;
+        const int strip = blockIdx.x - r * strips;
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (r < H) {
+            for (int j = warp; j < hd; j += 8) {
+                const T* wq = in_proj_weight + static_cast<size_t>(r * hd + j) * D;
+                float acc = 0.f;
+                for (int k = lane; k < D; k += 32) acc = fmaf(to_float<T>(query[k]), to_float<T>(wq[k]), acc);
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(FULL_MASK, acc, off);
+                if (in_proj_bias != nullptr) acc += to_float<T>(in_proj_bias[r * hd + j]);
+                if (lane == 0) {
+                    qh[j] = acc;
+                    if (strip == 0) q_proj[r * hd + j] = acc;
+                }
+            }
+        }
+        __syncthreads();
+        const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+        const int d = strip * 32 + x;
+        float acc = 0.f;
+        if (r < H && d < D) {
+            const T* wk = in_proj_weight + (static_cast<size_t>(D) + static_cast<size_t>(r) * hd) * D + d;
+#pragma unroll 4
+            for (int j = y; j < hd; j += 8) acc = fmaf(qh[j], to_float<T>(wk[static_cast<size_t>(j) * D]), acc);
+        }
+        red[y][x] = acc;
+        __syncthreads();
+        if (y != 0 || d >= D) return;
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += red[k][x];
+        folded_w[(static_cast<size_t>(D) + r) * D + d] = from_float<T>(s * scale);
+        return;
+    }
+    const uint4* src = reinterpret_cast<const uint4*>(in_proj_weight + 2 * static_cast<size_t>(D) * D);
+    uint4* dst = reinterpret_cast<uint4*>(folded_w);
+    const size_t n16 = static_cast<size_t>(D) * D * sizeof(T) / 16;
+    const size_t stride = static_cast<size_t>(gridDim.x - fold_blocks) * 256;
+    for (size_t i = static_cast<size_t>(blockIdx.x - fold_blocks) * 256 + threadIdx.x; i < n16; i += stride) dst[i] = src[i];
+}
+
 // g = [dWv (D rows) ; R (H rows) ; ...] fp32, each row D wide; one warp per in-projection row i (head h = i / hd):
 //   dWv[i, :] = g[i, :]              dWk[i, :] = scale * q[i] * R[h, :]        d_q[i] = scale * Wk[i, :] . R[h, :]
 template <typename T>
@@ -169,6 +227,35 @@ int aecf_fold_prepare(int32_t device, int32_t dtype, int32_t embed_dim, int32_t 
     else
         AECF_CUDA_OK(launch_pdl(fold_prepare_kernel<float>, dim3(fold_blocks + copy_blocks), dim3(256), 0, s, q_proj,
                                 static_cast<const float*>(in_proj_weight), D, H, hsp, scale, fold_blocks,
+                                static_cast<float*>(folded_w)));
+    count_launch();
+    return AECF_OK;
+}
+
+int aecf_fold_prepare_query(int32_t device, int32_t dtype, int32_t embed_dim, int32_t num_heads, const void* query,
+                            const void* in_proj_weight, const void* in_proj_bias, float* q_proj, void* folded_w, void* stream) {
+    int rc = fold_check(dtype, embed_dim, num_heads);
+    if (rc != AECF_OK) return rc;
+    if (!query || !in_proj_weight || !q_proj || !folded_w) return AECF_ERR_INVALID;
+    if (!aligned16(in_proj_weight) || !aligned16(folded_w)) return AECF_ERR_ALIGNMENT;
+    if ((rc = use_device(device)) != AECF_OK) return rc;
+    const int D = embed_dim, H = num_heads, hsp = aecf_fold_score_cols(dtype, H);
+    const float scale = static_cast<float>(sqrt(1.0 / static_cast<double>(D / H)));
+    const int fold_blocks = hsp * ((D + 31) / 32);
+    const int copy_blocks = 128;
+    const size_t smem = static_cast<size_t>(D / H) * sizeof(float);
+    if (smem > 48 * 1024) return AECF_ERR_UNSUPPORTED;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    TimedLaunch timed(s);
+    if (dtype == AECF_BF16)
+        AECF_CUDA_OK(launch_pdl(fold_prepare_query_kernel<__nv_bfloat16>, dim3(fold_blocks + copy_blocks), dim3(256), smem, s,
+                                static_cast<const __nv_bfloat16*>(query), static_cast<const __nv_bfloat16*>(in_proj_weight),
+                                static_cast<const __nv_bfloat16*>(in_proj_bias), D, H, hsp, scale, fold_blocks, q_proj,
+                                static_cast<__nv_bfloat16*>(folded_w)));
+    else
+        AECF_CUDA_OK(launch_pdl(fold_prepare_query_kernel<float>, dim3(fold_blocks + copy_blocks), dim3(256), smem, s,
+                                static_cast<const float*>(query), static_cast<const float*>(in_proj_weight),
+                                static_cast<const float*>(in_proj_bias), D, H, hsp, scale, fold_blocks, q_proj,
                                 static_cast<float*>(folded_w)));
     count_launch();
     return AECF_OK;

@@ -3,6 +3,7 @@
 // call chain implies (reference aecf/AECFLayer.py:515-541 over torch/nn/functional.py:5847-5865,
 // 6630-6659; backward per SURVEY.md Appendix B), so the host pays one FFI crossing per direction.
 #include "common.cuh"
+#include "grad_tail.cuh"
 
 namespace aecf {
 
@@ -41,6 +42,11 @@ static const void* at(const void* p, long long elems, int es) {
 }
 static void* at(void* p, long long elems, int es) { return p ? static_cast<char*>(p) + elems * es : nullptr; }
 
+// api.cu
+int pool_bwd_folded_partials(const aecf_pool_desc* desc, const void* q_proj, const float* scores, const void* v,
+                             const float* score_bias, const void* d_ctx, const float* d_pooled, const float* d_entropy,
+                             void* d_vs, void* workspace, size_t workspace_bytes, void* stream, int* blocks);
+
 struct Workspace {
     char* gemm; size_t gemm_bytes;
     char* pool; size_t pool_bytes;
@@ -49,8 +55,20 @@ struct Workspace {
     float* d_bias_kv;  // [2D]
     float* d_bq;       // [D] (per-row query)
     float* fold_g;     // [D + HSP, D] fp32: [dWv ; R] of the folded backward
+    // folded backward with the fused gradient tail (grad_tail.cu): the two weight-gradient products leave their split-K
+    // partials side by side, then the raw sums and the tail's scratch
+    char* gemm_o; size_t gemm_o_bytes;
+    char* gemm_g; size_t gemm_g_bytes;
+    float* sums;
+    char* tail; size_t tail_bytes;
     size_t total;
 };
+
+#define AECF_TRY(expr)                   \
+    do {                                 \
+        const int rc__ = (expr);         \
+        if (rc__ != AECF_OK) return rc__; \
+    } while (0)
 
 static size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
@@ -76,6 +94,10 @@ static size_t max_gemm_workspace(const aecf_pool_desc* d, const Geometry& g) {
         gemm_desc(d->device, dt, dt, AECF_F32, dt, AECF_MN_MAJOR, AECF_MN_MAJOR, D + g.HSP, D, g.rows, D + g.HSP, D, D),   // folded [dWv ; R]
         gemm_desc(d->device, dt, dt, dt, dt, AECF_K_MAJOR, AECF_MN_MAJOR, g.rows, D, D + g.HSP, D + g.HSP, D, D),          // folded dX
         gemm_desc(d->device, dt, dt, dt, dt, AECF_K_MAJOR, AECF_K_MAJOR, g.rows, D, D, D, D, D),                           // folded V
+        // the [query rows, D] x [D, D] products: per-row q_proj, out_proj / d_ctx, d_query (split-K at D = 2048, small batch)
+        gemm_desc(d->device, dt, dt, dt, dt, AECF_K_MAJOR, AECF_K_MAJOR, g.QR, D, D, D, D, D),
+        gemm_desc(d->device, dt, dt, dt, dt, AECF_K_MAJOR, AECF_MN_MAJOR, g.QR, D, D, D, D, D),
+        gemm_desc(d->device, dt, dt, AECF_F32, dt, AECF_K_MAJOR, AECF_K_MAJOR, 1, D, D, D, D, D),                          // shared query
     };
     for (const aecf_gemm_desc& p : probes) {
         const size_t w = aecf_gemm_workspace_bytes(&p);
@@ -98,21 +120,107 @@ static int carve(const aecf_pool_desc* d, const Geometry& g, void* base, Workspa
     w->d_bq = reinterpret_cast<float*>(b + off); off += align256(sizeof(float) * g.D);
     w->fold_g = reinterpret_cast<float*>(b + off);
     if (g.fold) off += align256(sizeof(float) * (g.D + g.HSP) * g.D);
+    w->gemm_o = w->gemm_g = w->tail = nullptr; w->sums = nullptr;
+    w->gemm_o_bytes = w->gemm_g_bytes = w->tail_bytes = 0;
+    if (g.fold) {
+        const int dt = g.dt, D = g.D, KF = g.D + g.HSP;
+        const aecf_gemm_desc o = gemm_desc(d->device, dt, dt, AECF_F32, dt, AECF_MN_MAJOR, AECF_MN_MAJOR, D, D, g.QR, D, D, D);
+        const aecf_gemm_desc kv = gemm_desc(d->device, dt, dt, AECF_F32, dt, AECF_MN_MAJOR, AECF_MN_MAJOR, KF, D, g.rows, KF, D, D);
+        w->gemm_o_bytes = align256(gemm_partials_workspace_bytes(&o));
+        w->gemm_g_bytes = align256(gemm_partials_workspace_bytes(&kv));
+        w->tail_bytes = align256(grad_tail_scratch_bytes(D, sm_count(d->device)));
+        w->gemm_o = b + off; off += w->gemm_o_bytes;
+        w->gemm_g = b + off; off += w->gemm_g_bytes;
+        w->sums = reinterpret_cast<float*>(b + off); off += align256(sizeof(float) * tail_layout(D, g.HSP).total);
+        w->tail = b + off; off += w->tail_bytes;
+    }
     w->total = off;
     return AECF_OK;
 }
 
-#define AECF_TRY(expr)                   \
-    do {                                 \
-        const int rc__ = (expr);         \
-        if (rc__ != AECF_OK) return rc__; \
-    } while (0)
+// ---- the folded backward, whole (phase AECF_BWD_ALL): five launches on `s`, the gradient tail next to the last one ----
+//   s    : dWo partials -> d_ctx -> pool backward -> [dWv ; R] partials -> (fork) -> dX -> (join)
+//   side :                                                              gather -> [peer sum] -> finish
+static int folded_backward(const aecf_pool_desc* desc, const Geometry& g, const aecf_fusion_tensors* t,
+                           const aecf_fusion_grads* gr, const Workspace& w, cudaStream_t s) {
+    const int dt = g.dt, D = g.D, dev = desc->device, KF = g.D + g.HSP;
+    const bool want_in = gr->d_in_proj_weight || gr->d_query || gr->d_in_proj_bias;
+    const bool want_tail = want_in || gr->d_out_proj_weight || gr->d_out_proj_bias;
+    const aecf_dp_desc* dp = (gr->dp != nullptr && gr->dp->world > 1) ? gr->dp : nullptr;
+    if (dp != nullptr && (dp->rank < 0 || dp->rank >= dp->world || dp->world > 8 || !dp->sums || !dp->reduced || !dp->flags))
+        return AECF_ERR_INVALID;
+    const bool forked = gr->side_stream != nullptr && gr->fork_event != nullptr && gr->join_event != nullptr && want_tail;
+    cudaStream_t side = forked ? static_cast<cudaStream_t>(gr->side_stream) : s;
+    GradTailArgs a{};
+    a.dtype = dt; a.D = D; a.H = g.H; a.HSP = g.HSP; a.sms = sm_count(dev);
+    a.scratch = w.tail;
+    a.sums = dp ? static_cast<float*>(dp->sums[dp->rank]) : w.sums;
+    a.q_proj = static_cast<const float*>(t->q_proj); a.in_proj_weight = t->in_proj_weight; a.query = t->query;
+    a.d_in_w = gr->d_in_proj_weight; a.d_in_b = gr->d_in_proj_bias; a.d_out_w = gr->d_out_proj_weight;
+    a.d_out_b = gr->d_out_proj_bias; a.d_query = gr->d_query;
+
+    if (gr->d_out_proj_weight) {                             // dWo = g^T ctx, left as split-K partials
+        ScopedSite site(AECF_SITE_D_OUT_WEIGHT);
+        const aecf_gemm_desc d = gemm_desc(dev, dt, dt, AECF_F32, dt, AECF_MN_MAJOR, AECF_MN_MAJOR, D, D, g.QR, D, D, D);
+        AECF_TRY(gemm_partials(&d, gr->d_out, t->ctx, w.gemm_o, w.gemm_o_bytes, s, &a.o));
+    }
+    {                                                        // d_ctx = g Wo
+        ScopedSite site(AECF_SITE_D_CTX);
+        const aecf_gemm_desc d = gemm_desc(dev, dt, dt, dt, dt, AECF_K_MAJOR, AECF_MN_MAJOR, g.QR, D, D, D, D, D);
+        AECF_TRY(aecf_gemm(&d, gr->d_out, t->out_proj_weight, nullptr, gr->d_ctx, w.gemm, w.gemm_bytes, s));
+    }
+    {
+        ScopedSite site(AECF_SITE_POOL_BWD);
+        AECF_TRY(pool_bwd_folded_partials(desc, t->q_proj, t->scores, t->kv, t->score_bias, gr->d_ctx, gr->d_pooled,
+                                          gr->d_entropy, gr->d_kv, w.pool, w.pool_bytes, s, &a.pool_blocks));
+        a.pool_part = reinterpret_cast<const float*>(w.pool);
+    }
+    if (want_in) {                                           // [dWv ; R] = [dV | ds]^T X, left as split-K partials
+        ScopedSite site(AECF_SITE_D_KV_WEIGHT);
+        const aecf_gemm_desc d = gemm_desc(dev, dt, dt, AECF_F32, dt, AECF_MN_MAJOR, AECF_MN_MAJOR, KF, D, g.rows, KF, D, D);
+        AECF_TRY(gemm_partials(&d, gr->d_kv, t->key, w.gemm_g, w.gemm_g_bytes, s, &a.g));
+    }
+    auto tail = [&]() -> int {
+        if (!want_tail) return AECF_OK;
+        a.d_out = gr->d_out_proj_bias ? gr->d_out : nullptr; a.rows = g.QR;
+        // the two "last block" counters at the end of the scratch: cleared here, so the caller's workspace needs no set-up
+        AECF_CUDA_OK(cudaMemsetAsync(w.tail + w.tail_bytes - 256, 0, 256, side));
+        AECF_TRY(launch_grad_gather(a, side));
+        const float* final_sums = a.sums;
+        if (dp != nullptr) {
+            AECF_TRY(launch_peer_sum(dev, dp, tail_layout(D, g.HSP).total, side));
+            final_sums = static_cast<const float*>(dp->reduced[dp->rank]);
+        }
+        return launch_grad_finish(a, final_sums, side);
+    };
+    if (forked) {
+        AECF_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(gr->fork_event), s));
+        AECF_CUDA_OK(cudaStreamWaitEvent(side, static_cast<cudaEvent_t>(gr->fork_event), 0));
+        AECF_TRY(tail());
+        AECF_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(gr->join_event), side));
+    }
+    if (gr->d_key) {                                         // dX = [dV | ds] . [Wv ; Qk]
+        ScopedSite site(AECF_SITE_D_X);
+        const aecf_gemm_desc d = gemm_desc(dev, dt, dt, dt, dt, AECF_K_MAJOR, AECF_MN_MAJOR, g.rows, D, KF, KF, D, D);
+        AECF_TRY(aecf_gemm(&d, gr->d_kv, t->folded_w, nullptr, gr->d_key, w.gemm, w.gemm_bytes, s));
+    }
+    if (forked) AECF_CUDA_OK(cudaStreamWaitEvent(s, static_cast<cudaEvent_t>(gr->join_event), 0));
+    else AECF_TRY(tail());
+    return AECF_OK;
+}
+
 
 }  // namespace aecf
 
 using namespace aecf;
 
 extern "C" {
+
+size_t aecf_fusion_grad_sums_bytes(const aecf_pool_desc* desc) {
+    Geometry g;
+    if (geometry(desc, &g) != AECF_OK || !g.fold) return 0;
+    return static_cast<size_t>(tail_layout(g.D, g.HSP).total) * sizeof(float);
+}
 
 size_t aecf_fusion_workspace_bytes(const aecf_pool_desc* desc) {
     Geometry g;
@@ -137,7 +245,7 @@ int aecf_fusion_fwd(const aecf_pool_desc* desc, const aecf_fusion_tensors* t, vo
     const bool bias = t->in_proj_bias != nullptr;
     const long long DD = static_cast<long long>(D) * D;
 
-    {   // query projection (torch/nn/functional.py:5854); a shared query is projected once, in fp32
+    if (!g.fold) {   // query projection (torch/nn/functional.py:5854); a shared query is projected once, in fp32
         ScopedSite site(AECF_SITE_Q_PROJ);
         const aecf_gemm_desc q = g.shared
             ? gemm_desc(dev, dt, dt, AECF_F32, dt, AECF_K_MAJOR, AECF_K_MAJOR, 1, D, D, D, D, D)
@@ -147,9 +255,10 @@ int aecf_fusion_fwd(const aecf_pool_desc* desc, const aecf_fusion_tensors* t, vo
     if (g.fold) {
         // folded key projection: no K.  [Wv ; Qk] -> values + per-head scores in one pass over x -> pool -> out
         if (t->value || !t->scores || !t->folded_w) return AECF_ERR_INVALID;
-        {
+        {   // q_proj = Wq q0 + bq and [Wv ; Qk] in one launch
             ScopedSite site(AECF_SITE_FOLD_PREPARE);
-            AECF_TRY(aecf_fold_prepare(dev, dt, D, g.H, static_cast<const float*>(t->q_proj), t->in_proj_weight, t->folded_w, stream));
+            AECF_TRY(aecf_fold_prepare_query(dev, dt, D, g.H, t->query, t->in_proj_weight, t->in_proj_bias,
+                                             static_cast<float*>(t->q_proj), t->folded_w, stream));
         }
         {
             ScopedSite site(AECF_SITE_KV_PROJ);
@@ -208,6 +317,10 @@ int aecf_fusion_bwd(const aecf_pool_desc* desc, const aecf_fusion_tensors* t, co
     const long long DD = static_cast<long long>(D) * D;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
 
+    if (g.fold && phase == AECF_BWD_ALL) {
+        if (t->value || !t->scores || !t->folded_w) return AECF_ERR_INVALID;
+        return folded_backward(desc, g, t, gr, w, s);
+    }
     if (phase != AECF_BWD_REST) {
         // ---- out-projection backward: its two parameter gradients are final first -------------------
         if (gr->d_out_proj_bias) {

@@ -191,7 +191,8 @@ static int launch_gemv(const aecf_gemm_desc* d, const void* A, const void* B, co
 }
 
 static int gemm_simt(const aecf_gemm_desc* d, const void* A, const void* B, const void* bias, void* C,
-                     void* workspace, size_t workspace_bytes, cudaStream_t s, bool allow_split = true) {
+                     void* workspace, size_t workspace_bytes, cudaStream_t s, bool allow_split = true,
+                     GemmPartials* defer = nullptr) {
     GemmEpilogue ep = make_epilogue(d, bias, C);
     const bool a16 = d->dtype_a == AECF_BF16, b16 = d->dtype_b == AECF_BF16;
     note_gemm_kernel(d->m == 1 ? "gemv" : "simt");
@@ -212,6 +213,10 @@ static int gemm_simt(const aecf_gemm_desc* d, const void* A, const void* B, cons
     else if (a16) rc = launch_simt<__nv_bfloat16, float>(d, A, B, ep, splits, s);
     else if (b16) rc = launch_simt<float, __nv_bfloat16>(d, A, B, ep, splits, s);
     else rc = launch_simt<float, float>(d, A, B, ep, splits, s);
+    if (rc == AECF_OK && defer != nullptr) {
+        *defer = splits > 1 ? GemmPartials{ep.partial, splits, d->m * d->n} : GemmPartials{static_cast<const float*>(C), 1, 0};
+        return rc;
+    }
     if (rc != AECF_OK || splits == 1) return rc;
     return launch_splitk_reduce(ep.partial, d->m, d->n, splits, d->m * d->n, ep, s);
 }
@@ -229,6 +234,37 @@ static int check_desc(const aecf_gemm_desc* d) {
     if (d->ldb < (d->b_layout == AECF_K_MAJOR ? d->k : d->n)) return AECF_ERR_INVALID;
     if (d->ldc < d->n) return AECF_ERR_INVALID;
     return AECF_OK;
+}
+
+// workspace layout: [ product m x n fp32 (used when the kernel does not split) | split-K partials ]
+static size_t partials_head_bytes(const aecf_gemm_desc* d) {
+    return (static_cast<size_t>(d->m) * d->n * sizeof(float) + 255) & ~static_cast<size_t>(255);
+}
+
+size_t gemm_partials_workspace_bytes(const aecf_gemm_desc* d) {
+    aecf_gemm_desc f = *d;
+    f.dtype_c = AECF_F32; f.ldc = d->n; f.accumulate = 0;
+    return partials_head_bytes(d) + aecf_gemm_workspace_bytes(&f);
+}
+
+int gemm_partials(const aecf_gemm_desc* d, const void* A, const void* B, void* workspace, size_t workspace_bytes,
+                  cudaStream_t s, GemmPartials* out) {
+    aecf_gemm_desc f = *d;
+    f.dtype_c = AECF_F32; f.ldc = d->n; f.accumulate = 0;
+    int rc = check_desc(&f);
+    if (rc != AECF_OK) return rc;
+    if (!A || !B || !workspace || !out) return AECF_ERR_INVALID;
+    if (workspace_bytes < gemm_partials_workspace_bytes(d)) return AECF_ERR_WORKSPACE;
+    if ((rc = use_device(d->device)) != AECF_OK) return rc;
+    char* head = static_cast<char*>(workspace);
+    char* tail = head + partials_head_bytes(d);
+    const size_t tail_bytes = workspace_bytes - partials_head_bytes(d);
+    TimedLaunch timed(s);
+    if (d->impl != AECF_GEMM_SIMT) {
+        rc = gemm_tcgen05(&f, A, B, nullptr, head, tail, tail_bytes, s, nullptr, 0, 0, out);
+        if (rc != AECF_ERR_UNSUPPORTED || d->impl == AECF_GEMM_TCGEN05) return rc;
+    }
+    return gemm_simt(&f, A, B, nullptr, head, tail, tail_bytes, s, true, out);
 }
 
 }  // namespace aecf

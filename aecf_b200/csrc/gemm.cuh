@@ -46,11 +46,21 @@ inline GemmEpilogue make_epilogue(const aecf_gemm_desc* d, const void* bias, voi
 int launch_splitk_reduce(const float* partial, long long M, long long N, int splits, long long split_stride,
                          const GemmEpilogue& ep, cudaStream_t s);
 
+// A product whose split-K fold is left to the caller: `splits` fp32 [m, n] slabs, `stride` elements apart (splits == 1:
+// the product itself).  grad_tail.cu folds the weight-gradient products together with the other batch reductions of
+// the backward instead of paying one reduce launch per product.
+struct GemmPartials { const float* partial; int splits; long long stride; };
+// fp32 product of `d` (dtype_c / ldc of the descriptor are ignored: fp32, ldc = n) left as partials inside `workspace`
+int gemm_partials(const aecf_gemm_desc* d, const void* A, const void* B, void* workspace, size_t workspace_bytes,
+                  cudaStream_t s, GemmPartials* out);
+size_t gemm_partials_workspace_bytes(const aecf_gemm_desc* d);
+
 // gemm_tcgen05.cu: returns AECF_ERR_UNSUPPORTED when the shape/dtype is outside what it covers.
 // aux != nullptr: the side output of aecf_gemm_aux (B then has d->n + roundup8(aux_cols) rows).
+// defer != nullptr: no split-K reduce launch; *defer says where the partials (or, unsplit, the product in C) are.
 int gemm_tcgen05(const aecf_gemm_desc* d, const void* A, const void* B, const void* bias, void* C,
                  void* workspace, size_t workspace_bytes, cudaStream_t s, float* aux = nullptr, int aux_cols = 0,
-                 long long aux_ld = 0);
+                 long long aux_ld = 0, GemmPartials* defer = nullptr);
 size_t gemm_tcgen05_workspace_bytes(const aecf_gemm_desc* d);
 void note_gemm_kernel(const char* fmt, ...);          // gemm.cu: records what aecf_gemm_last_kernel() reports
 

@@ -57,6 +57,10 @@ struct Params {
     int c_cols, aux_cols;
     long long aux_ld;
     float* aux;
+    // MEASUREMENT ONLY (AECF_GEMM_DEBUG_SKIP, scripts/gemm_bench.py): bit 0 = no operand loads and no MMAs (the epilogue
+    // alone, on whatever the accumulator holds), bit 1 = no epilogue (the main loop alone, nothing stored).  Results are
+    // garbage; the two times say which half of a kernel bounds it.
+    int debug_skip;
 };
 
 #ifdef AECF_CUDA_EMU
@@ -273,18 +277,13 @@ __device__ __forceinline__ WorkItem decode(const Params& p, int item, int cta_ra
     return w;
 }
 
-// EPI selects the epilogue of the bf16-output path: 1 = the measured one (load a 32-column group, convert, stage; drain
-// both staging boxes before refilling them); 2 = EXPERIMENTAL, opt-in with AECF_GEMM_EPI=2 and not yet run on hardware
-// (profiles/r1_gemm_experiments.md, "round-2 order of attack"): the next group's tcgen05.ld is in flight while the
-// current group is converted, and the two staging boxes alternate with `wait_group.read 1`, so neither the TMEM
-// read latency nor the previous store's shared-memory read is exposed.
-// 3 = EXPERIMENTAL, AECF_GEMM_EPI=3, not yet run on hardware: EIGHT epilogue warps (320 threads), two per TMEM lane
-// quadrant, each converting and storing every other 64-column box of its 32 rows -- two warps per scheduler instead
-// of one, so the ~6 clk/instruction dependent-issue latency of the conversion is hidden; bf16 direct output only (the
-// host keeps EPI 1 for fp32 / split-K output).
-constexpr int epi_warps(int epi) { return epi == 3 ? 8 : 4; }
-template <int BN, int CL, int EPI>
-__global__ void __launch_bounds__(64 + 32 * epi_warps(EPI), 1)
+// Epilogue of the bf16-output path: the next 32-column group's tcgen05.ld is in flight while the current group is
+// converted, and the two staging boxes alternate with `wait_group.read 1`, so neither the TMEM read latency nor the
+// previous store's shared-memory read is exposed (r2 run 1, same-box A/B against the serial epilogue: the values
+// product 113.0 -> 110.2 us, out_proj 38.9 -> 37.3 us, d_ctx 37.4 -> 36.4 us; the eight-warp variant was neutral and
+// is gone).  fp32 output (split-K partials, fp32 C) keeps the serial rounds below.
+template <int BN, int CL>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_c, const Params p) {
     using C = Cfg<BN>;
@@ -309,7 +308,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_a); prefetch_tmap(&map_b); prefetch_tmap(&map_c);
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CL); }   // every CTA's MMA frees a slot
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 32 * epi_warps(EPI)); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], EPI_THREADS); }
         fence_barrier_init();
     }
     if (warp == 1) {                                  // one warp allocates TMEM and owns the dealloc
@@ -332,7 +331,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         // ===== TMA producer: the whole warp walks the loop, one elected lane issues (see elect_one) =====
         constexpr int PART = BN / CL;                 // this CTA's share of the B tile
         int it = 0;
-        for (int item = first_item; item < items; item += item_stride) {
+        for (int item = first_item; item < items && !(p.debug_skip & 1); item += item_stride) {
             const WorkItem w = decode<CL>(p, item, cta_rank);
             for (int kb = 0; kb < w.kb_count; ++kb, ++it) {
                 const int s = it % STAGES;
@@ -380,7 +379,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             mbar_wait(&tmem_empty[as], ((tile_it >> 1) & 1) ^ 1);          // epilogue drained this accumulator
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + as * C::ACC_STRIDE;
-            for (int kb = 0; kb < w.kb_count; ++kb, ++it) {
+            for (int kb = 0; kb < w.kb_count && !(p.debug_skip & 1); ++kb, ++it) {
                 const int s = it % STAGES;
                 mbar_wait(&full[s], (it / STAGES) & 1);
                 tc_fence_after();
@@ -406,7 +405,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int quad = warp & 3;                   // TMEM lane quadrant this warp may read
         const int ew = warp - 2;                     // 0..3: staging slot
         uint8_t* wbuf = epi_base + ew * (2 * 32 * 128);
-        [[maybe_unused]] int box_it = 0;             // EPI == 2: boxes stored so far by this warp
+        int box_it = 0;                              // bf16 output: boxes stored so far by this warp
         int tile_it = 0;
         for (int item = first_item; item < items; item += item_stride, ++tile_it) {
             const WorkItem w = decode<CL>(p, item, cta_rank);
@@ -416,6 +415,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const bool direct = (p.splits == 1);
             mbar_wait(&tmem_full[as], (tile_it >> 1) & 1);
             tc_fence_after();
+            if (p.debug_skip & 2) { tc_fence_before(); mbar_arrive(&tmem_empty[as]); continue; }
             // fp32 bias slice of this tile, in the buffer of this tile's parity.  All four warps write the same
             // values; a warp two tiles ahead would reuse this buffer, but it cannot pass the tmem_full wait
             // above before every thread has finished the tile that last used it (tmem_empty arrives after the
@@ -434,70 +434,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
             const uint32_t t_row = tmem_base + as * C::ACC_STRIDE + (static_cast<uint32_t>(quad * 32) << 16);
             const int out_row0 = (direct ? 0 : w.split * p.partial_rows) + m0 + quad * 32;
-            if constexpr (EPI == 3) {
-                // ---- eight warps: warp (quad, half) owns the boxes half, half + 2, ... of its 32 rows and one private
-                // [32 rows x 128 B] staging box; both 32-column TMEM reads of a box are issued before either is used
-                constexpr int BOXES = BN / 64;
-                uint8_t* box_base = epi_base + ew * (32 * 128);
-                uint8_t* box = box_base + lane * 128;
-                // an odd number of boxes (192-wide tiles: three) alternates which warp of the pair takes two of them, so that
-                // over two tiles -- the slack the double-buffered accumulator gives -- both do three
-                const int first_box = (ew >> 2) ^ ((BOXES & 1) ? (tile_it & 1) : 0);
-#pragma unroll 1
-                for (int bx = first_box; bx < BOXES; bx += 2) {
-                    uint32_t r[2][32];
-                    tmem_ld_32x32(t_row + bx * 64, r[0]);
-                    tmem_ld_32x32(t_row + bx * 64 + 32, r[1]);
-                    if (lane == 0) tma_store_wait_read();                      // my previous store has read the box
-                    tmem_ld_wait_on(r[0]);
-                    tmem_ld_wait_on(r[1]);
-                    __syncwarp();
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int col_in_tile = bx * 64 + h * 32;
-                        float v[32];
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[h][i]);
-                        if (p.has_bias) {
-                            const float4* b4 = reinterpret_cast<const float4*>(wbias + col_in_tile);   // 128-byte aligned
-#pragma unroll
-                            for (int c = 0; c < 8; ++c) {
-                                const float4 t = b4[c];
-                                v[4 * c] += t.x; v[4 * c + 1] += t.y; v[4 * c + 2] += t.z; v[4 * c + 3] += t.w;
-                            }
-                        }
-                        if (p.aux != nullptr && n0 + col_in_tile == p.c_cols) {
-                            const int row = m0 + quad * 32 + lane;
-                            if (tile_valid && row < p.m) {
-                                float4* dst = reinterpret_cast<float4*>(p.aux + static_cast<long long>(row) * p.aux_ld);
-#pragma unroll
-                                for (int c = 0; c < 8; ++c)
-                                    if (4 * c < p.aux_cols) dst[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-                            }
-                        }
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const int chunk = h * 4 + c;
-                            *reinterpret_cast<uint4*>(box + ((chunk ^ (lane & 7)) << 4)) =
-                                make_uint4(Vec<__nv_bfloat16>::pack2(v[8 * c], v[8 * c + 1]),
-                                           Vec<__nv_bfloat16>::pack2(v[8 * c + 2], v[8 * c + 3]),
-                                           Vec<__nv_bfloat16>::pack2(v[8 * c + 4], v[8 * c + 5]),
-                                           Vec<__nv_bfloat16>::pack2(v[8 * c + 6], v[8 * c + 7]));
-                        }
-                    }
-                    fence_proxy_async();
-                    __syncwarp();
-                    const int col0 = n0 + bx * 64;
-                    if (lane == 0) {
-                        if (tile_valid && col0 < p.c_cols) tma_store_2d(&map_c, box_base, col0, out_row0);
-                        tma_store_commit();
-                    }
-                }
-                tc_fence_before();                                             // this warp's TMEM and bias reads are done
-                mbar_arrive(&tmem_empty[as]);
-                continue;
-            }
-            if constexpr (EPI == 2) {
+            {
                 if (!p.c_is_f32) {
                     // ---- pipelined bf16 epilogue: group g+1 is being read out of TMEM while group g is converted; box
                     // (g / 2) % 2 is refilled as soon as the store issued two boxes ago has read it (one may stay pending)
@@ -667,106 +604,7 @@ template <int BN> struct Cfg2 {
     static constexpr int SMEM_BYTES = STAGES_2SM * STAGE_BYTES + EPI_BYTES + 1024 + 256;
 };
 
-#define AECF_2SM_KERNEL gemm_tcgen05_2sm_kernel
-#define AECF_2SM_THREADS NUM_THREADS
-#define AECF_2SM_EW 4
-#define AECF_2SM_EPI_T EPI_THREADS
-#define AECF_2SM_AUX 0
-#define AECF_2SM_FIXED 0
 #include "gemm_tcgen05_2sm.inc"
-#undef AECF_2SM_KERNEL
-#undef AECF_2SM_THREADS
-#undef AECF_2SM_EW
-#undef AECF_2SM_EPI_T
-#undef AECF_2SM_AUX
-#undef AECF_2SM_FIXED
-#define AECF_2SM_KERNEL gemm_tcgen05_2sm_ew8_kernel
-#define AECF_2SM_THREADS (NUM_THREADS + 128)
-#define AECF_2SM_EW 8
-#define AECF_2SM_EPI_T 256
-#define AECF_2SM_AUX 0
-#define AECF_2SM_FIXED 0
-#include "gemm_tcgen05_2sm.inc"
-#undef AECF_2SM_KERNEL
-#undef AECF_2SM_THREADS
-#undef AECF_2SM_EW
-#undef AECF_2SM_EPI_T
-#undef AECF_2SM_AUX
-#undef AECF_2SM_FIXED
-// A-resident CTA-pair kernel (AECF_GEMM_APANEL=1), see gemm_tcgen05_apanel.inc
-template <int BN, int PKB> struct CfgAP {
-    static constexpr int PANEL_KB = PKB;                        // k-blocks of A kept resident: 8 (K <= 512) or 9 (K = 520, dX)
-    static constexpr int STAGES = PKB > 8 ? 3 : 4;              // B ring: one stage fewer pays for the ninth panel slot
-    static constexpr int A_BYTES = BM * BK * 2;                 // 16 KB per panel slot
-    static constexpr int B_BYTES = (BN / 2) * BK * 2;           // this CTA's half of the B tile
-    static constexpr int EPI_BUF = 2 * BM * 128;
-    static constexpr int EPI_BYTES = EPI_BUF;                   // ONE staging buffer
-    static constexpr int ACC_STRIDE = BN > 128 ? 256 : 128;
-    static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-    static constexpr int SMEM_BYTES = PANEL_KB * A_BYTES + STAGES * B_BYTES + EPI_BYTES + 1024 /*alignment*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
-};
-static_assert(CfgAP<256, 8>::SMEM_BYTES <= 232448 && CfgAP<256, 9>::SMEM_BYTES <= 232448,
-              "A panel + ring + staging must fit the 227 KB a CTA can opt into");
-#define AECF_AP_KERNEL gemm_tcgen05_apanel_kernel
-#define AECF_AP_THREADS NUM_THREADS
-#define AECF_AP_EW 4
-#define AECF_AP_EPI_T 128
-#include "gemm_tcgen05_apanel.inc"
-#undef AECF_AP_KERNEL
-#undef AECF_AP_THREADS
-#undef AECF_AP_EW
-#undef AECF_AP_EPI_T
-#define AECF_AP_KERNEL gemm_tcgen05_apanel_ew8_kernel
-#define AECF_AP_THREADS (NUM_THREADS + 128)
-#define AECF_AP_EW 8
-#define AECF_AP_EPI_T 256
-#include "gemm_tcgen05_apanel.inc"
-#undef AECF_AP_KERNEL
-#undef AECF_AP_THREADS
-#undef AECF_AP_EW
-#undef AECF_AP_EPI_T
-
-// the measured four-warp kernel with the bulk-group fix (AECF_GEMM_2SM_FIX=1), to become the default once re-measured
-#define AECF_2SM_KERNEL gemm_tcgen05_2sm_fixed_kernel
-#define AECF_2SM_THREADS NUM_THREADS
-#define AECF_2SM_EW 4
-#define AECF_2SM_EPI_T EPI_THREADS
-#define AECF_2SM_AUX 0
-#define AECF_2SM_FIXED 1
-#include "gemm_tcgen05_2sm.inc"
-#undef AECF_2SM_KERNEL
-#undef AECF_2SM_THREADS
-#undef AECF_2SM_EW
-#undef AECF_2SM_EPI_T
-#undef AECF_2SM_AUX
-#undef AECF_2SM_FIXED
-// the folded forward's 192-wide tiles with the fp32 score side output on CTA pairs (AECF_GEMM_2SM_AUX=1), both widths
-#define AECF_2SM_KERNEL gemm_tcgen05_2sm_aux_kernel
-#define AECF_2SM_THREADS NUM_THREADS
-#define AECF_2SM_EW 4
-#define AECF_2SM_EPI_T 128
-#define AECF_2SM_AUX 1
-#define AECF_2SM_FIXED 0
-#include "gemm_tcgen05_2sm.inc"
-#undef AECF_2SM_KERNEL
-#undef AECF_2SM_THREADS
-#undef AECF_2SM_EW
-#undef AECF_2SM_EPI_T
-#undef AECF_2SM_AUX
-#undef AECF_2SM_FIXED
-#define AECF_2SM_KERNEL gemm_tcgen05_2sm_aux_ew8_kernel
-#define AECF_2SM_THREADS (NUM_THREADS + 128)
-#define AECF_2SM_EW 8
-#define AECF_2SM_EPI_T 256
-#define AECF_2SM_AUX 1
-#define AECF_2SM_FIXED 0
-#include "gemm_tcgen05_2sm.inc"
-#undef AECF_2SM_KERNEL
-#undef AECF_2SM_THREADS
-#undef AECF_2SM_EW
-#undef AECF_2SM_EPI_T
-#undef AECF_2SM_AUX
-#undef AECF_2SM_FIXED
 
 // ---- host side -------------------------------------------------------------------------------
 using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -804,7 +642,7 @@ static bool make_map(CUtensorMap* map, const void* ptr, CUtensorMapDataType dt, 
            CUDA_SUCCESS;
 }
 
-struct Plan { bool ok, two_sm, apanel; int bn, cluster, tiles_m, tiles_n, groups_m, splits, kb_per_split, kb_total; };
+struct Plan { bool ok, two_sm; int bn, cluster, tiles_m, tiles_n, groups_m, splits, kb_per_split, kb_total; };
 
 // rows of B that carry the side output: aux_cols rounded up to 16 bytes of bf16
 static int aux_rows_of(int aux_cols) { return (aux_cols + 7) & ~7; }
@@ -855,16 +693,6 @@ static Plan make_plan(const aecf_gemm_desc* d, int aux_cols = 0) {
     static const int force_2sm = [] { const char* e = getenv("AECF_GEMM_2SM"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
     const bool long_k = pl.kb_per_split >= 9;
     pl.two_sm = pl.cluster == 2 && pl.bn == 256 && (force_2sm < 0 ? long_k : force_2sm == 1);
-    // EXPERIMENTAL (AECF_GEMM_2SM_AUX=1, functional emulation only so far): the side-output product (192-wide tiles) on
-    // CTA pairs too -- each CTA then stages 96 of the 192 B rows, 224 KB of operands per 128 x 192 x 512 tile instead of 320
-    static const bool two_sm_aux = [] { const char* e = getenv("AECF_GEMM_2SM_AUX"); return e && e[0] == '1'; }();
-    if (aux_cols > 0 && two_sm_aux && pl.cluster == 2 && pl.splits == 1) pl.two_sm = true;
-    // EXPERIMENTAL (AECF_GEMM_APANEL=1, functional emulation only so far): CTA pairs that keep their A panel resident over all
-    // column tiles of a row block (gemm_tcgen05_apanel.inc) for the K <= 512 products
-    static const bool apanel = [] { const char* e = getenv("AECF_GEMM_APANEL"); return e && e[0] == '1'; }();
-    pl.apanel = apanel && pl.cluster == 2 && pl.splits == 1 && (pl.bn == 256 ? pl.kb_total <= 9 : (pl.bn == 192 && pl.kb_total <= 8)) &&
-                (pl.bn == 256 || d->b_layout == AECF_K_MAJOR);
-    if (pl.apanel) pl.two_sm = true;                     // same tensor-map boxes (128-row stores) as the CTA-pair kernel
     if (aux_cols > 0 && pl.splits != 1) return pl;       // the side output is written by the direct epilogue only
     pl.ok = true;
     return pl;
@@ -879,7 +707,7 @@ size_t gemm_tcgen05_workspace_bytes(const aecf_gemm_desc* d) {
 }
 
 int gemm_tcgen05(const aecf_gemm_desc* d, const void* A, const void* B, const void* bias, void* C, void* workspace,
-                 size_t workspace_bytes, cudaStream_t s, float* aux, int aux_cols, long long aux_ld) {
+                 size_t workspace_bytes, cudaStream_t s, float* aux, int aux_cols, long long aux_ld, GemmPartials* defer) {
     using namespace tc;
     if (aux == nullptr) aux_cols = 0;
     const Plan pl = make_plan(d, aux_cols);
@@ -916,9 +744,10 @@ int gemm_tcgen05(const aecf_gemm_desc* d, const void* A, const void* B, const vo
     p.c_is_f32 = c_f32;
     p.has_bias = bias != nullptr; p.bias_is_bf16 = d->dtype_bias == AECF_BF16; p.bias = bias;
     p.partial_rows = pl.tiles_m * BM;              // padded: a ragged last row block must not spill into the next split
+    static const int debug_skip = [] { const char* e = getenv("AECF_GEMM_DEBUG_SKIP"); return e ? atoi(e) & 3 : 0; }();
+    p.debug_skip = debug_skip;
 
-    const long long items = pl.apanel ? pl.groups_m                                            // a CTA pair takes whole row blocks
-                                      : static_cast<long long>(pl.groups_m) * pl.tiles_n * pl.splits;     // one per cluster
+    const long long items = static_cast<long long>(pl.groups_m) * pl.tiles_n * pl.splits;     // one per cluster
     const int sms = sm_count(d->device);
     long long ctas = items * pl.cluster;
     const long long cap = sms / pl.cluster * pl.cluster;
@@ -933,46 +762,17 @@ int gemm_tcgen05(const aecf_gemm_desc* d, const void* A, const void* B, const vo
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    // AECF_GEMM_EPI=2 / 3 select the experimental epilogues (see gemm_tcgen05_kernel); 3 applies to direct bf16 output only
-    static const int epi_env = [] { const char* e = getenv("AECF_GEMM_EPI"); return (e && (e[0] == '2' || e[0] == '3')) ? e[0] - '0' : 1; }();
-    const int epi = (epi_env == 3 && (c_f32 || pl.two_sm)) ? 1 : epi_env;
-    if (epi == 3) cfg.blockDim = dim3(64 + 32 * epi_warps(3));
 #define AECF_TC_LAUNCH(BN_, CL_)                                                                                  \
     do {                                                                                                          \
-        auto kernel = epi == 3 ? gemm_tcgen05_kernel<BN_, CL_, 3>                                                 \
-                               : (epi == 2 ? gemm_tcgen05_kernel<BN_, CL_, 2> : gemm_tcgen05_kernel<BN_, CL_, 1>); \
+        auto kernel = gemm_tcgen05_kernel<BN_, CL_>;                                                              \
         cfg.dynamicSmemBytes = Cfg<BN_>::SMEM_BYTES;                                                              \
         AECF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN_>::SMEM_BYTES)); \
         AECF_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, map_a, map_b, map_c, p));                                   \
     } while (0)
-    static const bool two_sm_ew8 = [] { const char* e = getenv("AECF_GEMM_2SM_EW"); return e && e[0] == '8'; }();
-    if (pl.apanel) note_gemm_kernel("tcgen05 apanel bn%d ew%d kb%d", pl.bn, two_sm_ew8 ? 8 : 4, pl.kb_total > 8 ? 9 : 8);
-    else if (pl.two_sm) note_gemm_kernel("tcgen05 2sm bn%d ew%d%s splits%d", pl.bn, two_sm_ew8 ? 8 : 4, pl.bn == 192 ? " aux" : "", pl.splits);
-    else note_gemm_kernel("tcgen05 1sm bn%d cluster%d epi%d splits%d", pl.bn, pl.cluster, epi, pl.splits);
-#define AECF_AP_LAUNCH(BN_, PKB_)                                                                                    \
-    do {                                                                                                              \
-        auto kernel = two_sm_ew8 ? gemm_tcgen05_apanel_ew8_kernel<BN_, PKB_> : gemm_tcgen05_apanel_kernel<BN_, PKB_>; \
-        if (two_sm_ew8) cfg.blockDim = dim3(NUM_THREADS + 128);                                                       \
-        cfg.dynamicSmemBytes = CfgAP<BN_, PKB_>::SMEM_BYTES;                                                          \
-        AECF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgAP<BN_, PKB_>::SMEM_BYTES)); \
-        AECF_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, map_a, map_b, map_c, p));                                       \
-    } while (0)
-    if (pl.apanel) {
-        if (pl.bn == 192) AECF_AP_LAUNCH(192, 8);
-        else if (pl.kb_total > 8) AECF_AP_LAUNCH(256, 9);
-        else AECF_AP_LAUNCH(256, 8);
-    } else if (pl.two_sm && pl.bn == 192) {
-        auto kernel = two_sm_ew8 ? gemm_tcgen05_2sm_aux_ew8_kernel<192> : gemm_tcgen05_2sm_aux_kernel<192>;
-        if (two_sm_ew8) cfg.blockDim = dim3(NUM_THREADS + 128);
-        cfg.dynamicSmemBytes = Cfg2<192>::SMEM_BYTES;
-        AECF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<192>::SMEM_BYTES));
-        AECF_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, map_a, map_b, map_c, p));
-    } else if (pl.two_sm) {
-        // default: the kernel that commits one bulk group per epilogue round; AECF_GEMM_2SM_FIX=0 selects the round-1
-        // instantiation without it for ONE same-box A/B (r2 run 1), after which that instantiation is deleted
-        static const bool two_sm_fix = [] { const char* e = getenv("AECF_GEMM_2SM_FIX"); return !(e && e[0] == '0'); }();
-        auto kernel = two_sm_ew8 ? gemm_tcgen05_2sm_ew8_kernel<256> : (two_sm_fix ? gemm_tcgen05_2sm_fixed_kernel<256> : gemm_tcgen05_2sm_kernel<256>);
-        if (two_sm_ew8) cfg.blockDim = dim3(NUM_THREADS + 128);
+    if (pl.two_sm) note_gemm_kernel("tcgen05 2sm bn%d splits%d", pl.bn, pl.splits);
+    else note_gemm_kernel("tcgen05 1sm bn%d cluster%d splits%d", pl.bn, pl.cluster, pl.splits);
+    if (pl.two_sm) {
+        auto kernel = gemm_tcgen05_2sm_kernel<256>;
         cfg.dynamicSmemBytes = Cfg2<256>::SMEM_BYTES;
         AECF_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<256>::SMEM_BYTES));
         AECF_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, map_a, map_b, map_c, p));
@@ -980,9 +780,13 @@ int gemm_tcgen05(const aecf_gemm_desc* d, const void* A, const void* B, const vo
     else if (pl.bn == 192) { if (pl.cluster == 2) AECF_TC_LAUNCH(192, 2); else AECF_TC_LAUNCH(192, 1); }
     else { if (pl.cluster == 2) AECF_TC_LAUNCH(128, 2); else AECF_TC_LAUNCH(128, 1); }
 #undef AECF_TC_LAUNCH
-#undef AECF_AP_LAUNCH
     count_launch();
     AECF_CUDA_OK(cudaGetLastError());
+    if (defer != nullptr) {
+        if (partial) *defer = GemmPartials{static_cast<const float*>(workspace), pl.splits, static_cast<long long>(pl.tiles_m) * BM * d->n};
+        else *defer = GemmPartials{static_cast<const float*>(C), 1, 0};
+        return AECF_OK;
+    }
     if (!partial) return AECF_OK;
     GemmEpilogue ep = make_epilogue(d, bias, C);
     return launch_splitk_reduce(static_cast<const float*>(workspace), d->m, d->n, pl.splits,

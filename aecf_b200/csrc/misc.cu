@@ -3,6 +3,7 @@
 #include <cmath>
 
 #include "common.cuh"
+#include "pool_core.cuh"
 
 namespace aecf {
 
@@ -91,12 +92,6 @@ static int colsum_splits(long long rows) {
 }
 
 // ---- entropy loss -------------------------------------------------------------------------
-__device__ __forceinline__ float scrub_entropy(float e, bool* finite) {     // torch.nan_to_num(nan=0, posinf=1, neginf=0)
-    *finite = fabsf(e) <= 3.402823466e38f;
-    if (*finite) return e;
-    return (e == INFINITY) ? 1.0f : 0.0f;
-}
-
 __global__ void __launch_bounds__(1024) entropy_loss_fwd_kernel(const float* __restrict__ e, long long n, float target,
                                                                 float* __restrict__ loss) {
     __shared__ float warp_sum[32];

@@ -19,6 +19,7 @@
 // ever grow and are compared with >=, so a rank that is already in the next call cannot confuse a slower one.
 // Every spin has a clock-based bound and traps instead of hanging the GPU.
 #include "common.cuh"
+#include "grad_tail.cuh"
 
 namespace aecf {
 
@@ -27,6 +28,8 @@ constexpr int PEER_FLAG_WORDS = 64;                 // u32 per rank: [0, 8) data
 constexpr long long PEER_SPIN_LIMIT = 4000000000LL; // ~2 s of SM clocks
 
 struct PeerParams {
+    void* out[PEER_MAX_WORLD];                      // where the reduced slices go: == data for the in-place all-reduce, every
+                                                    // rank's `reduced` buffer for the backward's fused sum (grad_tail.cu)
     void* data[PEER_MAX_WORLD];                     // every rank's bucket as mapped in THIS process
     uint32_t* flags[PEER_MAX_WORLD];                // every rank's flag block
     long long count;                                // elements
@@ -109,7 +112,7 @@ peer_allreduce_kernel(const PeerParams p) {
         const uint4 out = Vec<T>::pack(acc);
 #pragma unroll
         for (int r = 0; r < PEER_MAX_WORLD; ++r)
-            if (r < W) st_peer(static_cast<char*>(p.data[r]) + c * 16, out);
+            if (r < W) st_peer(static_cast<char*>(p.out[r]) + c * 16, out);
     }
 
     // ---- 3. my slice has landed everywhere; leave when everybody's has -------------------------------------
@@ -130,6 +133,33 @@ peer_allreduce_kernel(const PeerParams p) {
         __threadfence();
         mine[16] = epoch;                                                 // next call's epoch base
     }
+}
+
+int launch_peer_sum(int device, const aecf_dp_desc* dp, long long count, cudaStream_t s) {
+    if (!dp || !dp->sums || !dp->reduced || !dp->flags) return AECF_ERR_INVALID;
+    if (dp->world < 2 || dp->world > PEER_MAX_WORLD || dp->rank < 0 || dp->rank >= dp->world || count <= 0 || count % 4 != 0)
+        return AECF_ERR_INVALID;
+    PeerParams p{};
+    for (int r = 0; r < dp->world; ++r) {
+        if (!dp->sums[r] || !dp->reduced[r] || !dp->flags[r]) return AECF_ERR_INVALID;
+        if (!aligned16(dp->sums[r]) || !aligned16(dp->reduced[r]) || !aligned16(dp->flags[r])) return AECF_ERR_ALIGNMENT;
+        p.data[r] = dp->sums[r];
+        p.out[r] = dp->reduced[r];
+        p.flags[r] = static_cast<uint32_t*>(dp->flags[r]);
+    }
+    p.count = count; p.world = dp->world; p.rank = dp->rank; p.average = dp->average;
+    int rc = use_device(device);
+    if (rc != AECF_OK) return rc;
+    // few CTAs: the kernel shares the SMs with the dX product's persistent CTAs (it needs no shared memory, so it fits
+    // next to them) and what it moves is small (world x 2 MB at D = 512) -- latency, not bandwidth
+    const long long per = (count / 4 + dp->world - 1) / dp->world;
+    long long blocks = (per + 511) / 512;
+    if (blocks > 32) blocks = 32;
+    if (blocks < 1) blocks = 1;
+    TimedLaunch timed(s, AECF_SITE_GRAD_PEER_SUM);
+    AECF_CUDA_OK(launch_pdl(peer_allreduce_kernel<float>, dim3(static_cast<unsigned>(blocks)), dim3(512), 0, s, p));
+    count_launch();
+    return AECF_OK;
 }
 
 }  // namespace aecf
@@ -164,6 +194,7 @@ int aecf_peer_allreduce(const aecf_peer_desc* d, void* const* peer_data, void* c
         if (!peer_data[r] || !peer_flags[r]) return AECF_ERR_INVALID;
         if (!aligned16(peer_data[r]) || !aligned16(peer_flags[r])) return AECF_ERR_ALIGNMENT;
         p.data[r] = peer_data[r];
+        p.out[r] = peer_data[r];
         p.flags[r] = static_cast<uint32_t*>(peer_flags[r]);
     }
     p.count = d->count; p.world = d->world; p.rank = d->rank; p.average = d->average;

@@ -286,190 +286,4 @@ pool_bwd_kernel(const PoolParams p) {
     }
 }
 
-// ---- streaming variant of the FOLDED backward (one warp owns a whole sample, WPS == 1) ------------------------------
-// EXPERIMENTAL, opt-in with AECF_POOL_BWD_STREAM=1: logic verified under the host emulation (tests/cuda_emu), not yet
-// run on hardware.  Same arithmetic and the same strips / partials / finalize as pool_bwd_kernel<FOLD>, other data
-// movement, the one pool_fwd_stream_kernel uses: persistent warps, each on a contiguous block of rows; the next row's
-// value chunks and its d_ctx chunk are copied global -> shared with cp.async (private per-warp 2-stage ring, no
-// register staging) while the current row is reduced, and the next row's scores are loaded one row ahead -- a warp
-// keeps a full row in flight at all times instead of issuing its loads at the top of every iteration.
-template <typename T, int M, int J, bool DROP>
-__global__ void __launch_bounds__((M * J <= 10 && J <= 2) ? 768 : 512, 1)
-pool_bwd_stream_kernel(const PoolParams p, const long long rows_per_warp) {
-    using Core = PoolCore<T, M, J, DROP>;
-    using Smem = BwdSmem<J, Core::V>;
-    constexpr int V = Core::V;
-    constexpr int Q4 = V / 4;
-    constexpr int CH = (M + 1) * J;                     // 16-byte chunks per lane per row: M value tokens + d_ctx
-
-    AECF_DYNAMIC_SMEM_ALIGNED16(float, smem);           // [warps][PER_WARP] strips | [warps][2 stages][CH][32 lanes] ring
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int warps = blockDim.x >> 5;
-    float* strip = smem + warp * Smem::PER_WARP;
-    float4* acc_bv = reinterpret_cast<float4*>(strip + Smem::ACC);    // [J][Q4][32]
-    float* acc_sds = strip + 2 * Smem::ACC;                           // [J][32]
-    uint4* my = reinterpret_cast<uint4*>(smem + warps * Smem::PER_WARP) + static_cast<size_t>(warp) * 2 * CH * 32;
-    for (int i = lane; i < Smem::PER_WARP; i += 32) strip[i] = 0.f;
-    __syncwarp();
-    const int c0 = lane;
-    const long long gw = static_cast<long long>(blockIdx.x) * warps + warp;
-    const long long row_begin = min(p.B, gw * rows_per_warp);
-    const long long row_end = min(p.B, row_begin + rows_per_warp);
-    auto valid = [&](int j) { return c0 + 32 * j < p.NC; };
-    pdl_wait();
-    const RngKey rng = effective_rng(p.rng, p.rng_state);
-
-    auto prefetch = [&](long long row, int stage) {
-        const char* v_src = static_cast<const char*>(p.kv) + Core::row_offset(p, row, c0);
-        const char* dc_src = static_cast<const char*>(p.d_ctx) + static_cast<size_t>(row) * p.D * sizeof(T) + static_cast<size_t>(c0) * 16;
-#pragma unroll
-        for (int j = 0; j < J; ++j)
-            if (valid(j)) {
-#pragma unroll
-                for (int m = 0; m < M; ++m) cp_async16(&my[(stage * CH + m * J + j) * 32 + lane], v_src + Core::kv_rel(p, m, 0, j));
-                cp_async16(&my[(stage * CH + M * J + j) * 32 + lane], dc_src + j * 512);
-            }
-        cp_async_commit();
-    };
-
-    float s_next[M][J];
-    if (row_begin < row_end) {
-        prefetch(row_begin, 0);
-        Core::load_scores(p, row_begin, c0, s_next);
-    }
-    int it = 0;
-    for (long long row = row_begin; row < row_end; ++row, ++it) {
-        const int stage = it & 1;
-        if (row + 1 < row_end) prefetch(row + 1, stage ^ 1);
-        else cp_async_commit();                         // empty group keeps the wait count uniform
-        float s[M][J];
-#pragma unroll
-        for (int m = 0; m < M; ++m)
-#pragma unroll
-            for (int j = 0; j < J; ++j) s[m][j] = s_next[m][j];
-        if (row + 1 < row_end) Core::load_scores(p, row + 1, c0, s_next);
-        float w[M][J], wd[M][J];
-        unsigned keep;
-        Core::softmax_dropout(p, rng, row, c0, s, w, wd, keep);
-        cp_async_wait<1>();                             // this row's chunks have landed (own copies only)
-        auto staged = [&](int slot, int j) -> uint4 {
-            return valid(j) ? my[(stage * CH + slot * J + j) * 32 + lane] : make_uint4(0, 0, 0, 0);
-        };
-        char* dkv_row = static_cast<char*>(p.d_kv) + Core::drow_offset(p, row, c0);
-
-        // ---- value pass: d wd = dctx . v ; dV = wd * dctx ; d_bias_v += (sum_m wd) * dctx --------
-        float dwd[M][J];
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-            float dc[V];
-            Vec<T>::unpack(staged(M, j), dc);
-            float sum_wd = 0.f;
-#pragma unroll
-            for (int m = 0; m < M; ++m) {
-                float f[V], dv[V];
-                Vec<T>::unpack(staged(m, j), f);
-                float a = 0.f;
-#pragma unroll
-                for (int v = 0; v < V; ++v) { a = fmaf(dc[v], f[v], a); dv[v] = wd[m][j] * dc[v]; }
-                dwd[m][j] = a;
-                sum_wd += wd[m][j];
-                if (valid(j)) stg_vec(dkv_row + Core::dkv_rel(p, m, 0, j), Vec<T>::pack(dv));
-            }
-#pragma unroll
-            for (int q4 = 0; q4 < Q4; ++q4) {
-                float4 a = acc_bv[(j * Q4 + q4) * 32 + lane];
-                a.x = fmaf(sum_wd, dc[4 * q4], a.x); a.y = fmaf(sum_wd, dc[4 * q4 + 1], a.y);
-                a.z = fmaf(sum_wd, dc[4 * q4 + 2], a.z); a.w = fmaf(sum_wd, dc[4 * q4 + 3], a.w);
-                acc_bv[(j * Q4 + q4) * 32 + lane] = a;
-            }
-        }
-        Core::head_reduce(p, dwd);
-
-        // gradient arriving through the head-averaged weights (see pool_bwd_kernel)
-        if (p.d_pooled != nullptr || p.d_entropy != nullptr) {
-            float dpw[M];
-#pragma unroll
-            for (int m = 0; m < M; ++m)
-                dpw[m] = p.d_pooled ? __ldg(p.d_pooled + static_cast<size_t>(row) * M + m) : 0.f;
-            if (p.d_entropy != nullptr) {
-                float pw[M];
-                Core::head_sum_partial(p, c0, wd, pw);  // WPS == 1: the warp holds every head
-                const float denom = static_cast<float>(p.H * p.R);
-#pragma unroll
-                for (int m = 0; m < M; ++m) pw[m] = pw[m] / denom;
-                float raw;
-                clamped_entropy<M>(pw, p.log_m, &raw);
-                const bool inside = (raw >= 0.f) && (raw <= p.log_m);
-                const float de = __ldg(p.d_entropy + row);
-#pragma unroll
-                for (int m = 0; m < M; ++m) dpw[m] += inside ? -(logf(pw[m]) + 1.0f) * de : 0.f;
-            }
-            const float h = static_cast<float>(p.H);
-#pragma unroll
-            for (int m = 0; m < M; ++m)
-#pragma unroll
-                for (int j = 0; j < J; ++j) dwd[m][j] += dpw[m] / h;
-        }
-
-        // ---- dropout and softmax backward ------------------------------------------------
-        float ds[M][J];
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-            float dot = 0.f;
-#pragma unroll
-            for (int m = 0; m < M; ++m) {
-                float dw = dwd[m][j];
-                if (DROP) dw = ((keep >> (m * J + j)) & 1u) ? dw / p.one_minus_p : 0.f;
-                ds[m][j] = dw;
-                dot = fmaf(w[m][j], dw, dot);
-            }
-            float sum_ds = 0.f;
-#pragma unroll
-            for (int m = 0; m < M; ++m) {
-                ds[m][j] = w[m][j] * (ds[m][j] - dot);
-                sum_ds += ds[m][j];
-            }
-            if (valid(j)) acc_sds[j * 32 + lane] += sum_ds;
-        }
-
-        // ---- score gradients next to dV (column D + head of every (row, m) line), padding columns zeroed ----
-        T* line = reinterpret_cast<T*>(static_cast<char*>(p.d_kv) + static_cast<size_t>(row) * p.dkv_sb * sizeof(T)) + p.D;
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-            const int c = c0 + 32 * j;
-            if (c < p.NC && (c & (p.G - 1)) == 0) {
-                const int head = c >> p.logG;
-#pragma unroll
-                for (int m = 0; m < M; ++m) line[m * p.dkv_sm + head] = from_float<T>(ds[m][j]);
-            }
-        }
-        if (lane < p.HSP - p.H) {
-#pragma unroll
-            for (int m = 0; m < M; ++m) line[m * p.dkv_sm + p.H + lane] = from_float<T>(0.f);
-        }
-        __syncwarp();                                   // every lane has read this stage before the next prefetch refills it
-    }
-
-    // ---- fold the warps' strips in a fixed order into this CTA's partial [3][D] (layout of pool_bwd_kernel) -------
-    __syncthreads();
-    const int D = p.D;
-    float* out = p.partials + static_cast<size_t>(blockIdx.x) * 3 * D;
-    for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) {
-        const int which = i / D, d = i - which * D;
-        const int c = d / V, v = d - c * V;
-        const int j = c >> 5, ln = c & 31;
-        const int idx = ((j * Q4 + (v >> 2)) * 32 + ln) * 4 + (v & 3);
-        float t = 0.f;
-        if (which != 0) {
-            for (int wi = 0; wi < warps; ++wi) {
-                const float* st = smem + wi * Smem::PER_WARP;
-                t += which == 1 ? st[Smem::ACC + idx] : st[2 * Smem::ACC + j * 32 + ln];
-            }
-        }
-        if (which == 2) t *= __ldg(static_cast<const float*>(p.q) + d) * p.scale;      // d_bias_k = scale q sum ds
-        out[i] = t;
-    }
-}
-
 }  // namespace aecf

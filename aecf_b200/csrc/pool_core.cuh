@@ -52,7 +52,20 @@ struct PoolParams {
     void* d_kv;
     void* d_q;
     float* partials;                        // [grid][3][D] fp32: dq | dbv | dbk
+    // fused CurriculumMasking.entropy_loss (streaming forward kernel only; include/aecf_b200.h aecf_pool_desc::loss_out)
+    float* loss_out;                        // [1], or null
+    float* loss_partials;                   // [gridDim.x] per-CTA sums of (scrubbed entropy - target)^2
+    unsigned* loss_ticket;                  // [2]: CTAs done; zero on entry and on exit
+    float loss_target;
 };
+
+constexpr int POOL_LOSS_MAX_CTAS = 4096;    // loss workspace: POOL_LOSS_MAX_CTAS floats + 64 bytes of counters
+
+__device__ __forceinline__ float scrub_entropy(float e, bool* finite) {     // torch.nan_to_num(nan=0, posinf=1, neginf=0)
+    *finite = fabsf(e) <= 3.402823466e38f;
+    if (*finite) return e;
+    return (e == INFINITY) ? 1.0f : 0.0f;
+}
 
 // Several fusion queries per sample (pool_multi.cuh): the S rows (b, 0 .. S-1) share the kv rows of sample b.
 // Info outputs, d_pooled, d_entropy and the Philox row are indexed b*S + s.  A second kernel argument, so that

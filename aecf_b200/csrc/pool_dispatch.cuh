@@ -33,8 +33,6 @@ namespace aecf {
 template <typename T, bool DROP> int launch_pool_fwd(int M, int J, const PoolParams& p, int grid, int sms, bool fold, void* stream);
 template <typename T, bool DROP> int launch_pool_bwd(int M, int J, const PoolParams& p, int grid, bool fold, void* stream);
 template <typename T, bool DROP> int pool_bwd_blocks_per_sm(int M, int J, bool fold);
-// EXPERIMENTAL streaming variant of the folded backward (pool_bwd_stream_kernel, WPS == 1 only); *ctas = CTAs launched
-template <typename T, bool DROP> int launch_pool_bwd_stream(int M, int J, const PoolParams& p, int sms, int* ctas, void* stream);
 // several fusion queries per sample (pool_multi.cuh); the backward runs one CTA per SM
 template <typename T, bool DROP> int launch_pool_fwd_multi(int M, int J, const PoolParams& p, const MultiQuery& mq, int grid, void* stream);
 template <typename T, bool DROP> int launch_pool_bwd_multi(int M, int J, const PoolParams& p, const MultiQuery& mq, int grid, void* stream);

@@ -218,9 +218,15 @@ pool_fwd_stream_kernel(const PoolParams p, const long long rows_per_warp) {
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const long long gw = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp;
-    const long long row_begin = gw * rows_per_warp;
+    const long long row_begin = min(p.B, gw * rows_per_warp);
     const long long row_end = min(p.B, row_begin + rows_per_warp);
-    if (row_begin >= row_end) return;                   // warp-uniform; no block-level barrier in this kernel
+    // fused entropy_loss: every warp, with or without rows, hands in a partial sum at the end (no block-level barrier:
+    // a shared-memory counter elects the CTA's last warp)
+    __shared__ float cta_loss[32];
+    __shared__ unsigned cta_done;
+    if (p.loss_out != nullptr && threadIdx.x == 0) cta_done = 0u;
+    if (p.loss_out != nullptr) __syncthreads();         // the only block-level barrier, before any warp can finish
+    float loss_acc = 0.f;                               // this lane's rows: sum of (scrubbed entropy - target)^2
     uint4* my = ring + static_cast<size_t>(warp) * 2 * CH * 32;
     const int c0 = lane;
     const char* kv = static_cast<const char*>(p.kv);
@@ -239,12 +245,14 @@ pool_fwd_stream_kernel(const PoolParams p, const long long rows_per_warp) {
                         cp_async16(&my[(stage * CH + (m * HALVES + half) * J + j) * 32 + lane], src + Core::kv_rel(p, m, half, j));
         cp_async_commit();
     };
-    prefetch(row_begin, 0);
+    if (row_begin < row_end) prefetch(row_begin, 0);
 
     float qs[J][V];
     if (!FOLD && p.q_shared) Core::load_query(p, 0, c0, qs);
     float s_next[M][J];                                 // folded: the next row's scores, loaded one row ahead
-    if constexpr (FOLD) Core::load_scores(p, row_begin, c0, s_next);
+    if constexpr (FOLD) {
+        if (row_begin < row_end) Core::load_scores(p, row_begin, c0, s_next);
+    }
     const float denom = static_cast<float>(p.H * p.R);
     float mine[M];                                      // head sums of the row this lane will finish
 #pragma unroll
@@ -316,9 +324,48 @@ pool_fwd_stream_kernel(const PoolParams p, const long long rows_per_warp) {
                 if (p.entropy) p.entropy[my_row] = entropy;
                 if (p.mask_rate) p.mask_rate[my_row] = mask_rate;
                 if (p.mask_bits) p.mask_bits[my_row] = static_cast<uint8_t>(bits);
+                if (p.loss_out != nullptr) {            // reference aecf/AECFLayer.py:299-311, the per-sample term
+                    bool fin;
+                    const float d = scrub_entropy(entropy, &fin) - p.loss_target;
+                    loss_acc = fmaf(d, d, loss_acc);
+                }
             }
             __syncwarp();
         }
+    }
+    if (p.loss_out == nullptr) return;
+    // ---- entropy_loss = max(0, mean_b (.)^2): lanes -> warp (xor shuffles), warps -> CTA and CTAs -> result in INDEX
+    // order by whoever finishes last: the value does not depend on the finishing order
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) loss_acc += __shfl_xor_sync(FULL_MASK, loss_acc, off);
+    const int warps = blockDim.x >> 5;
+    unsigned last_warp = 0u;
+    if (lane == 0) {
+        cta_loss[warp] = loss_acc;
+        __threadfence_block();
+        last_warp = (atomicAdd(&cta_done, 1u) == static_cast<unsigned>(warps - 1)) ? 1u : 0u;
+    }
+    last_warp = __shfl_sync(FULL_MASK, last_warp, 0);
+    if (!last_warp) return;
+    __threadfence_block();
+    unsigned last_cta = 0u;
+    if (lane == 0) {
+        float s = 0.f;
+        for (int w = 0; w < warps; ++w) s += cta_loss[w];
+        p.loss_partials[blockIdx.x] = s;
+        __threadfence();
+        last_cta = (atomicAdd(p.loss_ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    last_cta = __shfl_sync(FULL_MASK, last_cta, 0);
+    if (!last_cta) return;
+    __threadfence();
+    float s = 0.f;
+    for (unsigned b = lane; b < gridDim.x; b += 32) s += p.loss_partials[b];     // lane l: CTAs l, l + 32, ... in order
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(FULL_MASK, s, off);
+    if (lane == 0) {
+        p.loss_out[0] = fmaxf(s / static_cast<float>(p.B), 0.f);                 // .mean().clamp_(min=0)
+        *p.loss_ticket = 0u;                                                     // re-armed for the next launch
     }
 }
 

@@ -1,21 +1,23 @@
-"""Batch-sharded data parallelism for the fusion pool: one process per GPU, NCCL over NVLink.
+"""Batch-sharded data parallelism for the fusion pool: one process per GPU, NVLink between them.
 
 The reference has no distributed code; this layer is the north_star's item (3).
-Samples are independent in the forward and in every activation gradient, so ranks only meet in one
-sum-all-reduce of the fusion parameter gradients per step (1 051 136 elements at D = 512).
+Samples are independent in the forward and in every activation gradient, so ranks only meet in one sum of the
+fusion parameter gradients per step (1 051 136 parameters at D = 512).
 
   * rank r owns global rows [r*B/N, (r+1)*B/N); ``pool.row_offset`` keys the Philox counters on the
     GLOBAL row, so any N reproduces the 1-GPU masks and dropout bit for bit
-  * the backward writes its parameter gradients straight into one flat bucket (no copies), which is reduced
-    with ONE all-reduce after the backward, on the compute stream (the default): measured at 8 B200s with the
-    step replayed as a CUDA graph, 46 us on top of a 686 us step (profiles/r1_run17_dp8_study.json)
-  * ``overlap=True`` (or AECF_DP_OVERLAP=1) reduces in two groups in readiness order instead -- the
-    out-projection gradients on a side stream as soon as ``aecf_fusion_bwd(AECF_BWD_OUT_PROJ)`` has produced
-    them, the rest at the end.  It measured SLOWER (814 vs 732 us per step at N = 8): the persistent GEMM and
-    pool kernels size their grids to own every SM, and NCCL's CTAs landing on some SMs first delay the CTAs
-    that should have run there, which stretches the whole kernel
-
-Works with any ``torch.distributed`` backend: NCCL on the GPUs, gloo in the CPU tests of the host logic.
+  * ``collective="fused"`` (the default on CUDA with the folded key projection): the sum happens INSIDE the backward.
+    The backward's gradient tail (csrc/grad_tail.cu) leaves the raw fp32 sums -- [dWv ; R], dWo, colsum(d_out), the pool
+    kernel's bias sums, half as many numbers as there are parameters -- in a buffer every rank has mapped (CUDA IPC); one
+    kernel per rank then sums them over the ranks through NVLink peer loads (flag barrier, rank r sums slice r in rank
+    order and stores it to every rank, flag barrier) and only then are they converted to the parameter dtype.  The whole
+    tail runs on a side stream next to the dX product, so nothing of it is on the critical path, and the gradients are
+    summed in fp32 whatever the parameter dtype: an N-rank run rounds once, like a 1-rank run.  ``finish()`` is a no-op.
+  * ``collective="nccl"`` / ``"peer"``: the backward writes its parameter gradients into one flat bucket (no copies) and
+    ``finish()`` reduces it with ONE all-reduce after the backward -- ``torch.distributed`` (NCCL on the GPUs, gloo in the
+    CPU tests of the host logic) or ``PeerAllReduce`` (csrc/peer_allreduce.cu).  This is also what runs wherever the
+    fused tail does not apply (unfolded key projection, per-row queries).  ``overlap=True`` (AECF_DP_OVERLAP=1) reduces in
+    two groups in readiness order instead; it measured slower in round 1 (the NCCL kernel displaces persistent CTAs).
 """
 from __future__ import annotations
 
@@ -36,23 +38,85 @@ def shard_rows(global_batch: int, rank: int, world_size: int) -> Tuple[int, int]
     return start, base + (1 if rank < extra else 0)
 
 
+def _map_peer_tensors(tensors: List[torch.Tensor], group=None) -> List[List[torch.Tensor]]:
+    """Collective: every rank exports ``tensors`` (CUDA, kept alive by the caller) through CUDA IPC -- torch's tensor
+    sharing, handles travel through ``all_gather_object`` -- and maps every other rank's; returns, per tensor, the list of
+    its W instances as seen from THIS process (own rank: the tensor itself).  Peer access to the other devices is enabled."""
+    from torch.multiprocessing.reductions import reduce_tensor
+
+    from . import _lib
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = tensors[0].device
+    torch.cuda.synchronize(dev)
+    payload = ([reduce_tensor(t) for t in tensors], dev.index or 0)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, payload, group=group)
+    out: List[List[torch.Tensor]] = [[] for _ in tensors]
+    for r, (handles, peer_dev) in enumerate(gathered):
+        if r == rank:
+            for i, t in enumerate(tensors):
+                out[i].append(t)
+            continue
+        _lib.check(_lib.load().aecf_peer_enable_access(dev.index or 0, peer_dev), f"peer access {dev.index} -> {peer_dev}")
+        for i, (fn, args) in enumerate(handles):
+            out[i].append(fn(*args))                     # rebuild_cuda_tensor: rank r's memory mapped into this process
+    dist.barrier(group=group)                            # everybody has mapped everything before anybody signals
+    return out
+
+
+class FusedGradSum:
+    """The cross-rank gradient sum of the folded backward (``aecf_dp_desc``): raw-sum and reduced-sum buffers of every
+    rank mapped into this process, plus the flag blocks of the kernel's two barriers.  Construction is collective.
+    The pool's backward passes ``pointer()`` to ``aecf_fusion_bwd`` whenever ``usable(desc)``."""
+
+    def __init__(self, pool, group=None, average: bool = True):
+        import ctypes as C
+
+        from . import _lib, ops
+        att = pool.attention
+        dev, dtype = att.in_proj_weight.device, att.in_proj_weight.dtype
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise ValueError("the fused gradient sum covers the (at most 8) GPUs of one NVLink node")
+        probe = ops.make_pool_desc(dev, dtype, batch=1, num_tokens=2, embed_dim=pool.embed_dim, num_heads=pool.num_heads,
+                                   training=True, masking=0, min_active=1, q_is_shared=True, base_mask_prob=0.15,
+                                   entropy_target=0.7, dropout_p=0.0, seed=0, offset=0, row0=0, fold_key=True)
+        self.floats = ops.fusion_grad_sums_floats(probe)
+        if self.floats == 0:
+            raise ValueError("this pool has no fused gradient tail (the folded key projection does not apply)")
+        self.embed_dim, self.num_heads, self.dtype = pool.embed_dim, pool.num_heads, dtype
+        self.buffer = torch.zeros(2 * self.floats, dtype=torch.float32, device=dev)      # [raw sums | reduced sums]
+        self.flags = ops.peer_flag_block(dev)
+        buffers, flags = _map_peer_tensors([self.buffer, self.flags], group)
+        self._keep = (buffers, flags)
+        n = self.floats * 4
+        self._sums = (C.c_void_p * self.world)(*[b.data_ptr() for b in buffers])
+        self._reduced = (C.c_void_p * self.world)(*[b.data_ptr() + n for b in buffers])
+        self._flags = (C.c_void_p * self.world)(*[f.data_ptr() for f in flags])
+        self._desc = _lib.DpDesc(world=self.world, rank=self.rank, average=int(average), reserved0=0,
+                                 sums=self._sums, reduced=self._reduced, flags=self._flags)
+        self._ptr = C.pointer(self._desc)
+        self.ran = False                                 # set by the backward that used it (GradientSync.finish looks)
+
+    def usable(self, desc) -> bool:
+        return (self.world > 1 and desc.fold_key == 1 and desc.embed_dim == self.embed_dim and desc.num_heads == self.num_heads)
+
+    def pointer(self):
+        return self._ptr
+
+
 class PeerAllReduce:
     """In-place all-reduce of one CUDA tensor across the ranks of ONE node over NVLink peer memory, without NCCL:
     ``csrc/peer_allreduce.cu`` (barrier, every rank reduces its slice from all buckets in rank order and stores it
     into all buckets, barrier; bit-identical results on every rank, graph-capturable).
 
-    Construction is collective: every rank exports its bucket and a small flag block through CUDA IPC (torch's
-    tensor sharing), the handles travel through ``all_gather_object`` of ``group`` (any backend), and every rank
-    maps the other ranks' buffers and enables peer access to their devices.  The bucket must stay alive, and must
-    not be reallocated, for the lifetime of this object.  Opt-in (``GradientSync(collective="peer")`` or
-    ``AECF_DP_PEER=1``): single-device emulation is tested (``tests/test_gpu_peer_allreduce.py``), the
-    multi-process path is scheduled for its first hardware run in round 2.
+    Construction is collective (``_map_peer_tensors``).  The bucket must stay alive, and must not be reallocated, for the
+    lifetime of this object.  ``GradientSync(collective="peer")`` uses it for the gradient bucket where the backward's
+    own fused sum does not apply.
     """
 
     def __init__(self, bucket: torch.Tensor, group=None, average: bool = True):
-        from torch.multiprocessing.reductions import reduce_tensor
-
-        from . import _lib, ops
+        from . import ops
         if not bucket.is_cuda or not bucket.is_contiguous():
             raise ValueError("PeerAllReduce needs a contiguous CUDA tensor")
         self.bucket, self.group, self.average = bucket, group, average
@@ -60,24 +124,10 @@ class PeerAllReduce:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         if self.world > 8:
             raise ValueError("PeerAllReduce covers the (at most 8) GPUs of one NVLink node")
-        dev = bucket.device
-        self.flags = ops.peer_flag_block(dev)
+        self.flags = ops.peer_flag_block(bucket.device)
         self.buckets, self.flag_blocks = [bucket], [self.flags]
         if self.world > 1:
-            torch.cuda.synchronize(dev)
-            payload = (reduce_tensor(bucket), reduce_tensor(self.flags), dev.index or 0)
-            gathered = [None] * self.world
-            dist.all_gather_object(gathered, payload, group=group)
-            self.buckets, self.flag_blocks = [], []
-            for r, (b, f, peer_dev) in enumerate(gathered):
-                if r == self.rank:
-                    self.buckets.append(bucket)
-                    self.flag_blocks.append(self.flags)
-                    continue
-                _lib.check(_lib.load().aecf_peer_enable_access(dev.index or 0, peer_dev), f"peer access {dev.index} -> {peer_dev}")
-                self.buckets.append(b[0](*b[1]))             # rebuild_cuda_tensor: rank r's memory mapped into this process
-                self.flag_blocks.append(f[0](*f[1]))
-            dist.barrier(group=group)                        # everybody has mapped everything before anybody signals
+            self.buckets, self.flag_blocks = _map_peer_tensors([bucket, self.flags], group)
         self._ops = ops
 
     def __call__(self) -> None:
@@ -88,32 +138,71 @@ class PeerAllReduce:
             self._ops.peer_allreduce(self.buckets, self.flag_blocks, self.rank, average=self.average)
 
 
-class GradientSync:
-    """All-reduce (mean by default) of the fusion parameter gradients of one pool + its query.
+class _BucketViews:
+    """What the backward asks for a place to write a parameter gradient (``pool._grad_buffers``): the parameter's slice
+    of the all-reduce bucket -- unless ``param.grad`` already LIVES there (a second micro-batch before the optimizer step,
+    or ``zero_grad(set_to_none=False)``): writing the new gradient over the old one and letting autograd add the tensor
+    to itself would double it, so the backward then gets no buffer, allocates its own, and autograd accumulates into the
+    bucket slice in place."""
 
-    ``attach()`` hooks the pool: its backward then writes gradients into ``self.bucket`` and reports
-    each one the moment it is final.  ``finish()`` -- call it after ``loss.backward()`` -- waits for the
-    collectives and points every ``param.grad`` at its reduced slice of the bucket.
+    def __init__(self, sync: "GradientSync"):
+        self.sync = sync
+
+    def get(self, name: str):
+        view = self.sync.views.get(name)
+        if view is None:
+            return None
+        grad = self.sync.params[name].grad
+        if grad is None:
+            self.sync.bucket_is_reduced = False          # a fresh step overwrites the slice
+            return view
+        if grad.data_ptr() == view.data_ptr():
+            return None                                   # accumulate: see the class comment
+        raise RuntimeError(
+            f"GradientSync: {name}.grad is a tensor of its own; the synchronised gradients live in the sync's bucket. "
+            "Clear gradients with set_to_none=True (or keep the .grad tensors finish() assigned) when GradientSync is attached.")
+
+    def keys(self):
+        return self.sync.views.keys()
+
+    def __iter__(self):
+        return iter(self.sync.views)
+
+    def __getitem__(self, name):
+        return self.sync.views[name]
+
+
+class GradientSync:
+    """Sum (mean by default) of the fusion parameter gradients of one pool + its query over the ranks.
+
+    ``attach()`` hooks the pool.  With ``collective="fused"`` the pool's backward then sums across the ranks itself (see
+    the module docstring) and ``finish()`` has nothing left to do; otherwise the backward writes gradients into
+    ``self.bucket`` and ``finish()`` -- call it after ``loss.backward()`` either way -- reduces the bucket and points every
+    ``param.grad`` at its slice.  Gradient accumulation over micro-batches: set ``enabled = False`` for all but the last
+    micro-batch (like DDP's ``no_sync``) in bucket mode; in fused mode every backward is already summed over the ranks.
     """
 
     def __init__(self, pool, query: Optional[torch.nn.Parameter] = None, process_group=None,
                  average: bool = True, overlap: Optional[bool] = None, collective: Optional[str] = None):
         self.pool, self.query, self.group, self.average = pool, query, process_group, average
+        att = pool.attention
+        device, dtype = att.in_proj_weight.device, att.in_proj_weight.dtype
+        self.cuda = device.type == "cuda"
         if collective is None:
-            collective = "peer" if os.environ.get("AECF_DP_PEER", "0") == "1" else "nccl"
-        if collective not in ("nccl", "peer"):
-            raise ValueError(f"collective must be 'nccl' or 'peer', got {collective!r}")
-        self.collective = collective                     # 'nccl': torch.distributed all_reduce; 'peer': PeerAllReduce
+            collective = os.environ.get("AECF_DP_COLLECTIVE") or ("peer" if os.environ.get("AECF_DP_PEER", "0") == "1" else None)
+        if collective is None:
+            collective = "fused" if self.cuda else "nccl"
+        if collective not in ("fused", "nccl", "peer"):
+            raise ValueError(f"collective must be 'fused', 'nccl' or 'peer', got {collective!r}")
+        self.collective = collective
         if overlap is None:
             overlap = os.environ.get("AECF_DP_OVERLAP", "0") == "1"
         self.overlap = overlap
-        att = pool.attention
         self.params: Dict[str, torch.nn.Parameter] = {}
         for name, p in (("out_proj.bias", att.out_proj.bias), ("out_proj.weight", att.out_proj.weight),
                         ("in_proj_weight", att.in_proj_weight), ("in_proj_bias", att.in_proj_bias), ("query", query)):
             if p is not None:
                 self.params[name] = p
-        device, dtype = att.in_proj_weight.device, att.in_proj_weight.dtype
         if any(p.dtype != dtype for p in self.params.values()):
             raise ValueError("GradientSync needs the fusion query and the pool parameters in one dtype")
         self.slices: Dict[str, slice] = {}
@@ -127,30 +216,46 @@ class GradientSync:
                 self.early_end = n
         self.bucket = torch.zeros(n, dtype=dtype, device=device)
         self.views = {name: self.bucket[sl].view(self.params[name].shape) for name, sl in self.slices.items()}
-        self.cuda = device.type == "cuda"
         self.comm_stream = torch.cuda.Stream(device=device) if self.cuda else None
         self.pending: List[object] = []
         self.reported: set = set()
+        self.accumulated: set = set()                    # reported, but autograd adds them into the bucket after the backward
         self.reduced_upto = 0
-        self.enabled = True                              # False: gradients stay local (measurements, gradient accumulation)
+        self.bucket_is_reduced = False                   # the bucket holds a cross-rank result (a finished step)
+        self.enabled = True                              # False: gradients stay local (gradient accumulation, measurements)
         self.peer = None
-        if collective == "peer" and self.cuda and dist.is_initialized() and dist.get_world_size(process_group) > 1:
+        self.fused = None
+        multi = dist.is_initialized() and dist.get_world_size(process_group) > 1
+        if self.cuda and multi and collective == "fused":
+            try:
+                self.fused = FusedGradSum(pool, process_group, average)
+            except ValueError:
+                self.fused = None                        # no fused tail for this pool: bucket + NCCL
+        if self.cuda and multi and collective == "peer":
             self.peer = PeerAllReduce(self.bucket, process_group, average)     # one kernel for the whole bucket
             self.overlap = False
 
     # -- wiring -----------------------------------------------------------------------------
     def attach(self) -> "GradientSync":
         self.pool._grad_ready = self.on_ready
-        self.pool._grad_buffers = self.views            # the fused backward writes its gradients here
+        self.pool._grad_ready_early = bool(self.overlap)
+        self.pool._grad_buffers = _BucketViews(self)     # the fused backward writes its gradients here
+        self.pool._dp = self.fused
         if self.query is not None:
             self.query.register_hook(self._query_hook)
         return self
 
+    def _fused_ran(self) -> bool:
+        return self.fused is not None and self.fused.ran
+
     def _query_hook(self, grad: torch.Tensor) -> torch.Tensor:
+        if self._fused_ran() or not self.enabled or self.world_size == 1:
+            return grad                                  # already summed over the ranks inside the backward / nothing to do
         view = self.views["query"]
-        if grad.data_ptr() != view.data_ptr():          # the shared-query bypass did not apply: copy in
+        accumulating = self.query.grad is not None and self.query.grad.data_ptr() == view.data_ptr()
+        if grad.data_ptr() != view.data_ptr() and not accumulating:   # the shared-query bypass did not apply: copy in
             view.copy_(grad.reshape(view.shape))
-        self.on_ready("query", view)
+        self.on_ready("query", grad if accumulating else view)
         return grad
 
     @property
@@ -186,34 +291,47 @@ class GradientSync:
         if not self.enabled or name not in self.slices or name in self.reported or self.world_size == 1:
             return                                                     # single process: autograd's .grad is final
         view = self.views[name]
-        if grad.data_ptr() != view.data_ptr():                         # produced elsewhere: copy into the bucket
+        param_grad = self.params[name].grad
+        if param_grad is not None and param_grad.data_ptr() == view.data_ptr() and grad.data_ptr() != view.data_ptr():
+            # accumulation: param.grad lives in the bucket and autograd adds `grad` to it AFTER this backward returns, so
+            # the bucket is complete only in finish().  A bucket that already holds a cross-rank SUM must not be summed
+            # again (a mean may: every rank holds the same value).
+            if self.bucket_is_reduced and not self.average:
+                raise RuntimeError("GradientSync(average=False): accumulating onto gradients that were already summed over "
+                                   "the ranks; set enabled=False for all but the last micro-batch")
+            self.accumulated.add(name)
+        elif grad.data_ptr() != view.data_ptr():                       # produced elsewhere: copy into the bucket
             view.copy_(grad.reshape(view.shape))
         self.reported.add(name)
-        if self.overlap and self.reduced_upto == 0 and all(n in self.reported for n in EARLY if n in self.slices):
+        if (self.overlap and not self.accumulated and self.reduced_upto == 0
+                and all(n in self.reported for n in EARLY if n in self.slices)):
             self._reduce(0, self.early_end, side_stream=True)
             self.reduced_upto = self.early_end
 
     # -- called by the training loop after loss.backward() -----------------------------------
     def finish(self) -> None:
         """Reduce what is left, wait for the collectives and store the results in ``param.grad``."""
+        if self._fused_ran():
+            self.fused.ran = False                       # the backward summed over the ranks itself: .grad is final
+            self.reported.clear(); self.accumulated.clear()
+            return
         if not self.reported:
             return
         if self.peer is not None:
             self.peer()                                  # in place, on the compute stream, complete when it returns on-stream
-            for name in self.reported:
-                self.params[name].grad = self.views[name]
-            self.reported.clear()
-            return
-        self._reduce(self.reduced_upto, self.bucket.numel(), side_stream=False)
-        for work in self.pending:
-            work.wait()
-        if self.cuda and self.overlap:
-            torch.cuda.current_stream(self.bucket.device).wait_stream(self.comm_stream)
-        if getattr(self, "_scale_later", False):
-            self.bucket.mul_(1.0 / self.world_size)
-            self._scale_later = False
+        else:
+            self._reduce(self.reduced_upto, self.bucket.numel(), side_stream=False)
+            for work in self.pending:
+                work.wait()
+            if self.cuda and self.overlap:
+                torch.cuda.current_stream(self.bucket.device).wait_stream(self.comm_stream)
+            if getattr(self, "_scale_later", False):
+                self.bucket.mul_(1.0 / self.world_size)
+                self._scale_later = False
         for name in self.reported:
             self.params[name].grad = self.views[name]
+        self.bucket_is_reduced = True
         self.pending.clear()
         self.reported.clear()
+        self.accumulated.clear()
         self.reduced_upto = 0

@@ -42,9 +42,32 @@ class PoolConfig:
     # data-parallel hook: called in backward with (name, grad tensor) as soon as a parameter
     # gradient is final, so that its all-reduce overlaps the rest of the backward
     grad_ready: Optional[Callable[[str, torch.Tensor], None]] = None
+    grad_ready_early: bool = False      # True: two-phase backward, the out-projection gradients are reported before the rest
     # data-parallel: {parameter name: tensor} the backward writes that parameter's gradient into
     # (slices of the all-reduce bucket), instead of allocating it
     grad_buffers: Optional[dict] = None
+    # fused CurriculumMasking.entropy_loss: the target the module's entropy_loss() would use after this forward; the
+    # forward kernel then also produces the loss scalar (None: not wanted / not a training-mode masking forward)
+    loss_target: Optional[float] = None
+    # where the backward's gradient tail runs (side stream + fork / join events; None: on the compute stream)
+    side: Optional["SideStream"] = None
+    # data-parallel, folded path: sum the raw gradient sums over the ranks inside the backward (aecf_b200.dp.FusedGradSum)
+    dp: Optional[object] = None
+
+
+class SideStream:
+    """A second stream of the pool's device and the two events that fork the backward's gradient tail onto it and join
+    it back (``aecf_fusion_grads.side_stream / fork_event / join_event``).  The tail -- split-K folds, column sums, the
+    rank-H key/query terms, with data parallelism the cross-rank sum -- then runs NEXT TO the dX product.  Works eagerly
+    and under CUDA-graph capture (the event edges become graph edges)."""
+
+    def __init__(self, device: torch.device):
+        self.device = device
+        self.stream = torch.cuda.Stream(device=device)
+        self.fork, self.join = torch.cuda.Event(), torch.cuda.Event()
+        with torch.cuda.device(device):                 # the handles exist only after a first record
+            self.fork.record(self.stream)
+            self.join.record(self.stream)
 
 
 def _rows(x3d: torch.Tensor) -> torch.Tensor:
@@ -97,6 +120,11 @@ class FusedPoolFunction(torch.autograd.Function):
         mask_rate = torch.empty((R,), dtype=torch.float32, device=dev)
         masked = torch.empty((R, M), dtype=torch.float32, device=dev)
         bits = torch.empty((R if cfg.want_mask_bits else 0,), dtype=torch.uint8, device=dev)
+        loss = torch.empty((0,), dtype=torch.float32, device=dev)
+        if cfg.loss_target is not None and cfg.masking == 1 and ops.pool_fwd_has_loss(desc, fold):
+            loss = torch.empty((1,), dtype=torch.float32, device=dev)
+            ws = ops.loss_workspace(dev)
+            desc.loss_out, desc.loss_workspace, desc.loss_target = loss.data_ptr(), ws.data_ptr(), float(cfg.loss_target)
         p = _lib.ptr
         tensors = _lib.FusionTensors(
             query=p(q_in), key=p(key), value=p(value), in_proj_weight=p(in_w), in_proj_bias=p(in_b),
@@ -114,14 +142,15 @@ class FusedPoolFunction(torch.autograd.Function):
         ctx.query_rows = R
         ctx.q_shape = q_src.shape
         ctx.save_for_backward(q_in, key, value, in_w, in_b, out_w, out_b, qp, kv, attn, score_bias, scores, folded_w)
+        desc.loss_out = desc.loss_workspace = None      # the descriptor is kept for the backward: no dangling pointers
         if cfg.masking != 2:                            # entropy is detached in training mode (reference :278)
-            ctx.mark_non_differentiable(mask_rate, masked, bits, entropy)
+            ctx.mark_non_differentiable(mask_rate, masked, bits, entropy, loss)
         else:
-            ctx.mark_non_differentiable(mask_rate, masked, bits)
-        return out, pooled, entropy, mask_rate, masked, bits
+            ctx.mark_non_differentiable(mask_rate, masked, bits, loss)
+        return out, pooled, entropy, mask_rate, masked, bits, loss
 
     @staticmethod
-    def backward(ctx, g_out, g_pooled, g_entropy, _g_rate, _g_masked, _g_bits):
+    def backward(ctx, g_out, g_pooled, g_entropy, _g_rate, _g_masked, _g_bits, _g_loss):
         cfg: PoolConfig = ctx.cfg
         q_in, key, value, in_w, in_b, out_w, out_b, qp, kv, attn, score_bias, scores, folded_w = ctx.saved_tensors
         B, M, D = ctx.shape
@@ -150,7 +179,12 @@ class FusedPoolFunction(torch.autograd.Function):
         d_q_rows = None if cfg.q_shared else new((R, D))
         d_key = new(key.shape) if need_key else None
         d_value = new(value.shape) if (value is not None and need_value) else None
-        bufs = cfg.grad_buffers or {}
+        # fused tail: the folded backward as one call (phase ALL); with cfg.dp the cross-rank sum happens inside it and the
+        # gradients come back final, so they go to fresh tensors autograd owns, not into the all-reduce bucket
+        fused_dp = cfg.dp if (cfg.fold and cfg.dp is not None and cfg.dp.usable(ctx.desc)) else None
+        bufs = {} if fused_dp is not None else (cfg.grad_buffers or {})
+        if fused_dp is not None:
+            notify = None
 
         def grad_like(name, like):
             b = bufs.get(name)
@@ -173,12 +207,24 @@ class FusedPoolFunction(torch.autograd.Function):
             d_out=p(g), d_pooled=p(d_pooled), d_entropy=p(d_entropy), d_ctx=p(d_ctx), d_kv=p(d_kv), d_q_rows=p(d_q_rows),
             d_key=p(d_key), d_value=p(d_value), d_query=p(d_q), d_in_proj_weight=p(d_in_w), d_in_proj_bias=p(d_in_b),
             d_out_proj_weight=p(d_out_w), d_out_proj_bias=p(d_out_b))
+        side = cfg.side
+        if side is not None and cfg.fold and side.device == dev:
+            grads.side_stream, grads.fork_event, grads.join_event = (
+                side.stream.cuda_stream, side.fork.cuda_event, side.join.cuda_event)
+        if fused_dp is not None:
+            grads.dp = fused_dp.pointer()
+            fused_dp.ran = True
         ws = ops.fusion_workspace(ctx.desc, dev)
-        if notify is None:
+        if notify is None or not cfg.grad_ready_early:
             ops.fusion_bwd(ctx.desc, tensors, grads, _lib.BWD_ALL, ws, dev)
+            if notify is not None:                      # one bucket all-reduce after the backward (GradientSync.finish)
+                for name, t in (("out_proj.bias", d_out_b), ("out_proj.weight", d_out_w), ("in_proj_weight", d_in_w),
+                                ("in_proj_bias", d_in_b)):
+                    if t is not None:
+                        notify(name, t)
         else:
             # the out-projection gradients are final first: hand them to the all-reduce while the pool
-            # backward and the in-projection GEMMs run
+            # backward and the in-projection GEMMs run (two-phase call: the sequence without the fused tail)
             ops.fusion_bwd(ctx.desc, tensors, grads, _lib.BWD_OUT_PROJ, ws, dev)
             if d_out_b is not None:
                 notify("out_proj.bias", d_out_b)

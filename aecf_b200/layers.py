@@ -24,7 +24,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .fused_pool import EntropyFunction, EntropyLossFunction, FusedPoolFunction, PoolConfig
+from .fused_pool import EntropyFunction, EntropyLossFunction, FusedPoolFunction, PoolConfig, SideStream
 
 __all__ = ["CurriculumMasking", "MultimodalAttentionPool", "multimodal_attention_pool", "create_fusion_pool",
            "set_rng_state", "get_rng_state"]
@@ -173,12 +173,25 @@ class CurriculumMasking(nn.Module):
                 "target_entropy": torch.full_like(entropy, math.log(float(length)) * self.entropy_target)}
         return masked.reshape(weights.shape).to(weights.dtype), info
 
-    def entropy_loss(self, entropy: torch.Tensor) -> torch.Tensor:
-        """mean((entropy - entropy_target * log(L))^2), L = tokens of the last training forward (:285-314)."""
+    def _loss_target(self) -> float:
         seq_len = getattr(self, "_last_seq_len", 2)
-        max_entropy = math.log(float(seq_len)) if seq_len > 1 else 0.0
+        return (math.log(float(seq_len)) if seq_len > 1 else 0.0) * self.entropy_target
+
+    def entropy_loss(self, entropy: torch.Tensor) -> torch.Tensor:
+        """mean((entropy - entropy_target * log(L))^2), L = tokens of the last training forward (:285-314).
+
+        For the ``info['entropy']`` tensor of the pool's last training-mode forward the value was already produced by that
+        forward's kernel (the per-sample term is fused there, ``aecf_pool_desc::loss_out``) and is returned as is -- in
+        training mode the reference's entropy is detached (:278), so there is no gradient to carry.  Any other tensor
+        (eval mode, user-made, modified in place since) takes the stand-alone kernels."""
+        target = self._loss_target()
+        fused = getattr(entropy, "_aecf_fused_loss", None)      # attached to the very tensor object the forward returned
+        if fused is not None:
+            version, fused_target, loss = fused
+            if entropy._version == version and fused_target == target and not entropy.requires_grad:
+                return loss.reshape(()).to(entropy.dtype)
         ops.require_cuda(entropy)
-        return EntropyLossFunction.apply(entropy, max_entropy * self.entropy_target)
+        return EntropyLossFunction.apply(entropy, target)
 
     def extra_repr(self) -> str:
         return (f"base_mask_prob={self.base_mask_prob}, entropy_target={self.entropy_target}, "
@@ -247,6 +260,9 @@ class MultimodalAttentionPool(nn.Module):
         self.row_offset = 0
         self._grad_ready = None
         self._grad_buffers = None
+        self._grad_ready_early = False                # data parallelism: report the out-projection gradients early
+        self._dp = None                               # data parallelism: aecf_b200.dp.FusedGradSum
+        self._side = None                             # SideStream of the backward's gradient tail, made on first use
         self._want_mask_bits = False
         # Folded key projection (include/aecf_b200.h): None = automatic -- on for bf16 whenever one fusion query
         # is shared by all rows and key is value (AECF_FOLD=0 in the environment turns the automatic choice off);
@@ -329,6 +345,16 @@ class MultimodalAttentionPool(nn.Module):
         b, h, s, _ = bias.shape
         return bias, (h * s * tokens if b > 1 else 0, s * tokens if h > 1 else 0, tokens if s > 1 else 0)
 
+    def _side_stream(self, device: torch.device):
+        """The second stream the folded backward's gradient tail runs on (AECF_SIDE_STREAM=0: everything in order)."""
+        if os.environ.get("AECF_SIDE_STREAM", "1") == "0" or device.type != "cuda":
+            return None
+        if self._side is None or self._side.device != device:
+            if torch.cuda.is_current_stream_capturing():
+                return None                             # streams and events are made outside captures (the warm-up steps)
+            self._side = SideStream(device)
+        return self._side
+
     def forward(self, query: torch.Tensor, key: torch.Tensor, value: Optional[torch.Tensor] = None,
                 key_padding_mask: Optional[torch.Tensor] = None, attn_mask: Optional[torch.Tensor] = None,
                 return_info: bool = False, use_checkpoint: bool = False,
@@ -382,8 +408,11 @@ class MultimodalAttentionPool(nn.Module):
             min_active=cm.min_active if fused_cm else 1,
             seed=seed, offset=offset, rng_state=rng_state, row0=int(self.row_offset), q_shared=q_shared,
             seq_first=not self.batch_first, fold=fold, want_mask_bits=self._want_mask_bits, bias_strides=bias_strides,
-            tgt_len=tgt_len, grad_ready=self._grad_ready, grad_buffers=self._grad_buffers)
-        out, pooled, entropy, mask_rate, masked, bits = FusedPoolFunction.apply(
+            tgt_len=tgt_len, grad_ready=self._grad_ready, grad_buffers=self._grad_buffers,
+            grad_ready_early=bool(self._grad_ready_early),
+            loss_target=cm._loss_target() if (masking == 1 and return_info) else None,
+            side=self._side_stream(key.device) if fold else None, dp=self._dp)
+        out, pooled, entropy, mask_rate, masked, bits, fused_loss = FusedPoolFunction.apply(
             q_src, key_c, value_c, att.in_proj_weight, att.in_proj_bias, att.out_proj.weight, att.out_proj.bias,
             bias, cfg)
 
@@ -393,6 +422,8 @@ class MultimodalAttentionPool(nn.Module):
         if cm is not None:
             if fused_cm:
                 info["entropy"] = entropy.reshape(batch, tgt_len)
+                if fused_loss.numel() == 1:             # entropy_loss(info['entropy']) is already known: see there
+                    info["entropy"]._aecf_fused_loss = (info["entropy"]._version, cfg.loss_target, fused_loss)
                 info["mask_rate"] = mask_rate.reshape(batch, tgt_len)
                 if cm.training:                                         # eval mode has no target (:153-156)
                     target = math.log(float(tokens)) * cm.entropy_target if tokens > 1 else 0.0

@@ -117,7 +117,8 @@ def make_pool_desc(dev: torch.device, dtype: torch.dtype, *, batch: int, num_tok
                    row0: int, bias_strides: Tuple[int, ...] = (0, 0),
                    kv_strides: Tuple[int, int] = (0, 0), fold_key: bool = False,
                    rng_state: Optional[torch.Tensor] = None, tgt_len: int = 1,
-                   q_strides: Tuple[int, int] = (0, 0)) -> _lib.PoolDesc:
+                   q_strides: Tuple[int, int] = (0, 0), loss_out: Optional[torch.Tensor] = None,
+                   loss_workspace: Optional[torch.Tensor] = None, loss_target: float = 0.0) -> _lib.PoolDesc:
     """``bias_strides`` = (batch, head[, query]) element strides of the additive score bias; ``tgt_len`` > 1 and
     ``q_strides`` (rows of query (b, s): b*q_strides[0] + s*q_strides[1]) describe several queries per sample."""
     return _lib.PoolDesc(device=dev.index or 0, dtype=dtype_code(dtype), batch=batch, num_tokens=num_tokens,
@@ -129,7 +130,10 @@ def make_pool_desc(dev: torch.device, dtype: torch.dtype, *, batch: int, num_tok
                          kv_stride_b=kv_strides[0], kv_stride_m=kv_strides[1], fold_key=int(fold_key),
                          tgt_len=int(tgt_len), rng_state=None if rng_state is None else rng_state.data_ptr(),
                          q_stride_b=q_strides[0], q_stride_s=q_strides[1],
-                         bias_stride_s=bias_strides[2] if len(bias_strides) > 2 else 0)
+                         bias_stride_s=bias_strides[2] if len(bias_strides) > 2 else 0,
+                         loss_out=None if loss_out is None else loss_out.data_ptr(),
+                         loss_workspace=None if loss_workspace is None else loss_workspace.data_ptr(),
+                         loss_target=float(loss_target))
 
 
 def fold_score_cols(dtype: torch.dtype, num_heads: int) -> Tuple[int, int]:
@@ -273,6 +277,30 @@ def peer_allreduce(buckets, flags, rank: int, *, average: bool = False, stream: 
     flag_ptrs = (C.c_void_p * world)(*[f.data_ptr() for f in flags])
     rc = _lib.load().aecf_peer_allreduce(C.byref(d), data, flag_ptrs, _stream(dev) if stream is None else stream)
     _lib.check(rc, f"aecf_peer_allreduce world={world} rank={rank} count={mine.numel()}")
+
+
+_loss_workspaces: dict = {}
+
+
+def loss_workspace(dev: torch.device) -> torch.Tensor:
+    """The fused entropy_loss term's scratch (per-CTA partial sums and a "CTAs done" counter): zeroed once, re-armed by
+    the kernel.  One per device: forwards of one device are expected to be ordered (one stream, or one CUDA graph); it is
+    allocated outside any capture (the first eager or warm-up forward)."""
+    key = dev.index or 0
+    ws = _loss_workspaces.get(key)
+    if ws is None:
+        ws = torch.zeros(int(_lib.load().aecf_pool_loss_workspace_bytes()), dtype=torch.uint8, device=dev)
+        _loss_workspaces[key] = ws
+    return ws
+
+
+def pool_fwd_has_loss(desc: _lib.PoolDesc, folded: bool) -> bool:
+    return bool(_lib.load().aecf_pool_fwd_has_loss(C.byref(desc), int(folded)))
+
+
+def fusion_grad_sums_floats(desc: _lib.PoolDesc) -> int:
+    """fp32 elements of one raw-sum buffer of the backward's fused gradient tail (0: this descriptor has none)."""
+    return int(_lib.load().aecf_fusion_grad_sums_bytes(C.byref(desc))) // 4
 
 
 def fusion_workspace(desc: _lib.PoolDesc, dev: torch.device) -> torch.Tensor:

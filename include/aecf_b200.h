@@ -45,7 +45,7 @@ extern "C" {
 #define AECF_API
 #endif
 
-#define AECF_ABI_VERSION 3
+#define AECF_ABI_VERSION 4
 #define AECF_MAX_TOKENS 8
 
 typedef enum aecf_status {
@@ -98,6 +98,17 @@ typedef struct aecf_pool_desc {
     int64_t  q_stride_b;      /* ROW of query (b, s) in q / ctx / d_ctx / d_q and in the whole-step query / out / d_out: */
     int64_t  q_stride_s;      /*   b*q_stride_b + s*q_stride_s; (0, 0) = batch-first (S, 1); sequence-first is (1, B) */
     int64_t  bias_stride_s;   /* score_bias stride between the queries of a sample (0 broadcasts) */
+    /* Fused CurriculumMasking.entropy_loss (reference aecf/AECFLayer.py:285-314; north_star: "the per-sample entropy_loss
+     * term" in the fused kernel).  When loss_out is non-null, masking == 1 and one warp owns a sample (the streaming forward
+     * kernel: embed_dim <= 64 sixteen-byte chunks), the forward also writes
+     *     loss_out[0] = max(0, mean_b (nan_to_num(entropy[b], nan=0, posinf=1, neginf=0) - loss_target)^2)
+     * Per-warp partial sums are folded per CTA and then by the last CTA to finish, each in index order: the result does not
+     * depend on which CTA is last (no floating-point atomics).  Where the kernel in use does not carry the term, loss_out is
+     * left untouched and aecf_pool_fwd_has_loss(desc) says so beforehand: the caller then runs aecf_entropy_loss_fwd. */
+    float*   loss_out;        /* [1] fp32, nullable */
+    void*    loss_workspace;  /* aecf_pool_loss_workspace_bytes() bytes, zeroed ONCE by the caller (the kernel re-arms it) */
+    float    loss_target;     /* entropy_target * log(_last_seq_len), the value CurriculumMasking.entropy_loss would use */
+    int32_t  reserved0;
 } aecf_pool_desc;
 
 /* Several queries per sample (tgt_len = S > 1; reference aecf/AECFLayer.py:415 takes any [B, S, D] query).  Every
@@ -128,6 +139,9 @@ typedef struct aecf_pool_desc {
 AECF_API int aecf_pool_fwd(const aecf_pool_desc* desc, const void* q, const void* kv, const float* score_bias,
                   void* ctx, float* pooled, float* entropy, float* mask_rate, float* masked,
                   uint8_t* mask_bits, void* stream);
+AECF_API size_t aecf_pool_loss_workspace_bytes(void);
+/* 1 when aecf_pool_fwd / aecf_pool_fwd_folded (`folded` != 0) / aecf_fusion_fwd with this descriptor write desc->loss_out */
+AECF_API int aecf_pool_fwd_has_loss(const aecf_pool_desc* desc, int32_t folded);
 
 /* Backward: recomputes the attention weights from q/kv (nothing from forward is stored; this is what
  * use_checkpoint= asked for, reference aecf/AECFLayer.py:501-512) and produces every activation
@@ -175,6 +189,11 @@ AECF_API int aecf_pool_bwd_folded(const aecf_pool_desc* desc, const void* q_proj
  * q_proj [D] fp32 and in_proj_weight [3D, D]. */
 AECF_API int aecf_fold_prepare(int32_t device, int32_t dtype, int32_t embed_dim, int32_t num_heads, const float* q_proj,
                       const void* in_proj_weight, void* folded_w, void* stream);
+/* The same from the UNPROJECTED shared query [D] (dtype): also computes and writes q_proj [D] fp32 = Wq query + bq
+ * (torch/nn/functional.py:5854; in_proj_bias nullable) -- one launch in front of the forward GEMM instead of two. */
+AECF_API int aecf_fold_prepare_query(int32_t device, int32_t dtype, int32_t embed_dim, int32_t num_heads, const void* query,
+                            const void* in_proj_weight, const void* in_proj_bias, float* q_proj, void* folded_w,
+                            void* stream);
 /* Backward completion: from g = [dWv ; R] ([D + HSP, D] fp32, the output of the d_vs^T . X product) write
  * d_in_proj_weight rows [D, 2D) (dWk) and [2D, 3D) (dWv) in dtype (either may be skipped with a null
  * d_in_proj_weight) and d_q_proj [D] fp32 (+= nothing: overwritten). */
@@ -280,6 +299,22 @@ typedef struct aecf_fusion_tensors {
     void*    folded_w;             /* [D + HSP, D] */
 } aecf_fusion_tensors;
 
+/* Cross-rank sum of the parameter gradients INSIDE the backward (csrc/grad_tail.cu; north_star item 3).  Every rank maps
+ * every rank's buffers (CUDA IPC, aecf_b200.dp.GradientSync) and must have peer access enabled.  The raw gradient sums of
+ * the folded backward -- [dWv ; R], dWo, colsum(d_out), the pool kernel's bias sums: aecf_fusion_grad_sums_bytes(desc)
+ * bytes of fp32, about half the parameter count because dWk, dWq and d_query are linear images of R -- are summed over the
+ * ranks IN FP32 by one kernel (flag barrier; rank r sums slice r of all ranks' buffers in rank order and stores it into
+ * every rank's `reduced` buffer; flag barrier), and only then converted to the parameter dtype, so an N-rank run rounds once,
+ * like a 1-rank run.  The kernel runs on the side stream next to the dX product.  Host arrays of `world` DEVICE pointers. */
+typedef struct aecf_dp_desc {
+    int32_t world, rank;      /* world <= 8 (one NVLink node) */
+    int32_t average;          /* 1: divide the sums by world */
+    int32_t reserved0;
+    void* const* sums;        /* [world] every rank's raw-sum buffer as mapped in THIS process (this rank's is written here) */
+    void* const* reduced;     /* [world] every rank's reduced-sum buffer */
+    void* const* flags;       /* [world] every rank's flag block, aecf_peer_flag_bytes() bytes, zeroed once */
+} aecf_dp_desc;
+
 typedef struct aecf_fusion_grads {
     const void*  d_out;            /* [B, D] */
     const float* d_pooled;         /* [B, M] fp32, nullable */
@@ -296,6 +331,15 @@ typedef struct aecf_fusion_grads {
     void* d_in_proj_bias;          /* [3D] */
     void* d_out_proj_weight;       /* [D, D] */
     void* d_out_proj_bias;         /* [D] */
+    /* Folded backward, phase AECF_BWD_ALL: the small kernels that finish the parameter gradients (split-K folds, column
+     * sums, the rank-H key/query terms, conversion to dtype; csrc/grad_tail.cu) run on `side_stream` while the dX product
+     * runs on `stream`: fork_event is recorded on `stream` after the last product they need, join_event on `side_stream`
+     * after them, and `stream` waits for it before the call returns.  All three null: everything on `stream`, in order.
+     * The caller owns stream and events (cudaStream_t / cudaEvent_t handles); capture into a CUDA graph works as usual. */
+    void* side_stream;
+    void* fork_event;
+    void* join_event;
+    const aecf_dp_desc* dp;        /* nullable: sum the gradients over the ranks inside the backward (see aecf_dp_desc) */
 } aecf_fusion_grads;
 
 enum { AECF_BWD_ALL = 0, AECF_BWD_OUT_PROJ = 1, AECF_BWD_REST = 2 };
@@ -307,6 +351,9 @@ AECF_API int aecf_fusion_fwd(const aecf_pool_desc* desc, const aecf_fusion_tenso
 AECF_API int aecf_fusion_bwd(const aecf_pool_desc* desc, const aecf_fusion_tensors* t, const aecf_fusion_grads* g,
                              int32_t phase, void* workspace, size_t workspace_bytes, void* stream);
 AECF_API size_t aecf_fusion_workspace_bytes(const aecf_pool_desc* desc);
+/* bytes of ONE raw-sum (or reduced-sum) buffer of aecf_dp_desc for this descriptor; 0 where the backward has no fused tail
+ * (unfolded key projection, per-row queries) */
+AECF_API size_t aecf_fusion_grad_sums_bytes(const aecf_pool_desc* desc);
 
 /* ---- data-parallel all-reduce over NVLink peer memory ------------------------------------------------
  * In-place sum (or mean) of one gradient bucket across the W <= 8 ranks of a node, one kernel per rank over peer
@@ -334,7 +381,8 @@ typedef enum aecf_site {
     AECF_SITE_OTHER = 0, AECF_SITE_Q_PROJ, AECF_SITE_KV_PROJ, AECF_SITE_POOL_FWD, AECF_SITE_OUT_PROJ,
     AECF_SITE_D_OUT_BIAS, AECF_SITE_D_OUT_WEIGHT, AECF_SITE_D_CTX, AECF_SITE_POOL_BWD, AECF_SITE_POOL_BWD_FINALIZE,
     AECF_SITE_D_X, AECF_SITE_D_KV_WEIGHT, AECF_SITE_D_Q_WEIGHT, AECF_SITE_D_QUERY, AECF_SITE_D_IN_BIAS,
-    AECF_SITE_ENTROPY_LOSS, AECF_SITE_FOLD_PREPARE, AECF_SITE_FOLD_FINISH, AECF_SITE_COUNT
+    AECF_SITE_ENTROPY_LOSS, AECF_SITE_FOLD_PREPARE, AECF_SITE_FOLD_FINISH, AECF_SITE_GRAD_GATHER, AECF_SITE_GRAD_PEER_SUM,
+    AECF_SITE_GRAD_FINISH, AECF_SITE_COUNT
 } aecf_site;
 AECF_API int         aecf_timing_enable(int32_t enable);                    /* clears earlier records */
 AECF_API int         aecf_timing_collect(float* total_ms, int32_t* launches); /* arrays of AECF_SITE_COUNT; syncs */

@@ -237,10 +237,15 @@ cudaError_t cudaDeviceGetAttribute(int* value, enum cudaDeviceAttr, int) { *valu
 cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = nullptr; return cudaSuccess; }
 cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned int) { return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { std::memset(p, v, n); return cudaSuccess; }
 cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
 
 // entry points of the translation unit that is not emulated (NVLink peer memory)
 size_t aecf_peer_flag_bytes(void) { return 256; }
 int aecf_peer_enable_access(int32_t, int32_t) { return AECF_ERR_UNSUPPORTED; }
 int aecf_peer_allreduce(const aecf_peer_desc*, void* const*, void* const*, void*) { return AECF_ERR_UNSUPPORTED; }
+}
+namespace aecf {
+int launch_peer_sum(int, const aecf_dp_desc*, long long, cudaStream_t) { return AECF_ERR_UNSUPPORTED; }   // peer_allreduce.cu
 }

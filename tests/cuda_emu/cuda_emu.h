@@ -108,6 +108,7 @@ extern dim3 blockDim, gridDim;
 inline void __syncthreads() { cuda_emu::named_barrier(0, 0, true); }
 inline void __syncwarp(unsigned = 0xffffffffu) { cuda_emu::warp_barrier(); }
 inline void __threadfence() {}
+inline void __threadfence_block() {}
 inline void __threadfence_system() {}
 [[noreturn]] inline void __trap() { std::fprintf(stderr, "cuda_emu: __trap()\n"); std::abort(); }
 inline long long clock64() { return 0; }

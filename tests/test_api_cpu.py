@@ -21,7 +21,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.aecf_abi_version() == _lib.ABI_VERSION == 3
+    assert lib.aecf_abi_version() == _lib.ABI_VERSION == 4
     assert b"sm_100a" in lib.aecf_build_info()
     assert lib.aecf_strerror(-2).decode().startswith("shape or dtype outside")
 

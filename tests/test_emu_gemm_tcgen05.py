@@ -2,9 +2,10 @@
 functional model of tests/cuda_emu/tcgen05_emu.h behind its inline-PTX wrappers (mbarriers, tiled TMA with the 128-byte
 swizzle, cluster multicast, tensor memory, tcgen05.mma through the shared-memory / instruction descriptors,
 cta_group::2).  The model's layouts are validated by the kernels measured on hardware computing correct products under
-it; with that, the variants that have NOT run on hardware yet (AECF_GEMM_EPI=2 / 3, AECF_GEMM_2SM_EW=8, AECF_GEMM_2SM_AUX=1) are
-checked for what a functional model can see -- barrier counts and phases (a wrong count deadlocks the emulation), tile /
-box / column indexing, staging layout -- not for missing waits or fences, and not for speed.
+it.  It sees what a functional model can see -- barrier counts and phases (a wrong count deadlocks the emulation), tile /
+box / column indexing, staging layout, a staging box refilled before the wait that protects it -- not missing fences, and
+not speed.  (Round 1 used it to pre-check five kernel variants before their first hardware run; round 2 measured them,
+kept the pipelined epilogue and deleted the rest -- profiles/r2_gemm_where_the_time_goes.md.)
 """
 import os
 import subprocess
@@ -71,65 +72,19 @@ def test_whole_step_on_the_tensor_core_gemms():
     P.test_bf16_masks_exact_against_stage_rounded_oracle(case, False)
 
 
-def test_reported_kernel_follows_the_switches():
-    """aecf_gemm_last_kernel() names what ran, so an A/B run (and the variant runs below) can check that a switch took."""
+def test_reported_kernel():
+    """aecf_gemm_last_kernel() names what ran (bench.py records it per launch site)."""
     from aecf_b200 import ops
-    env = os.environ
-    ew = "8" if env.get("AECF_GEMM_2SM_EW") == "8" else "4"
-    epi = env.get("AECF_GEMM_EPI", "1")
-    cluster = "1" if env.get("AECF_GEMM_CLUSTER") == "1" else "2"
+    cluster = "1" if os.environ.get("AECF_GEMM_CLUSTER") == "1" else "2"
     bf = torch.bfloat16
     a, b = torch.randn(512, 128, dtype=bf), torch.randn(256, 128, dtype=bf)
-    apanel = env.get("AECF_GEMM_APANEL") == "1" and cluster == "2"
     ops.gemm(a, b, m=512, n=256, k=128, a_layout=_lib.K_MAJOR, b_layout=_lib.K_MAJOR, lda=128, ldb=128)           # 2 k-blocks
-    assert _lib.gemm_last_kernel() == (f"tcgen05 apanel bn256 ew{ew} kb8" if apanel else f"tcgen05 1sm bn256 cluster{cluster} epi{epi} splits1")
-    ops.gemm(a, b, m=512, n=256, k=128, a_layout=_lib.K_MAJOR, b_layout=_lib.K_MAJOR, lda=128, ldb=128, out_dtype=torch.float32)
-    assert _lib.gemm_last_kernel() == (f"tcgen05 apanel bn256 ew{ew} kb8" if apanel else
-                                       f"tcgen05 1sm bn256 cluster{cluster} epi{'1' if epi == '3' else epi} splits1")   # EPI 3: bf16 output only
+    assert _lib.gemm_last_kernel() == f"tcgen05 1sm bn256 cluster{cluster} splits1"
     a, b = torch.randn(512, 640, dtype=bf), torch.randn(256, 640, dtype=bf)
     ops.gemm(a, b, m=512, n=256, k=640, a_layout=_lib.K_MAJOR, b_layout=_lib.K_MAJOR, lda=640, ldb=640)           # 10 k-blocks
-    assert _lib.gemm_last_kernel() == (f"tcgen05 2sm bn256 ew{ew} splits1" if cluster == "2" else f"tcgen05 1sm bn256 cluster1 epi{epi} splits1")
+    assert _lib.gemm_last_kernel() == ("tcgen05 2sm bn256 splits1" if cluster == "2" else "tcgen05 1sm bn256 cluster1 splits1")
     a, b = torch.randn(640, 512, dtype=bf), torch.randn(520, 512, dtype=bf)
     ops.gemm_aux(a, b, m=640, n=512, k=512, aux_cols=8)
-    want = f"tcgen05 2sm bn192 ew{ew} aux splits1" if (env.get("AECF_GEMM_2SM_AUX") == "1" and cluster == "2") else f"tcgen05 1sm bn192 cluster{cluster} epi{epi} splits1"
-    if apanel:
-        want = f"tcgen05 apanel bn192 ew{ew} kb8"                              # K = 512: eight k-blocks, the panel fits
-    assert _lib.gemm_last_kernel() == want
+    assert _lib.gemm_last_kernel() == f"tcgen05 1sm bn192 cluster{cluster} splits1"
     ops.gemm(a[:64].float(), b[:64].float(), m=64, n=64, k=512, a_layout=_lib.K_MAJOR, b_layout=_lib.K_MAJOR, lda=512, ldb=512)
     assert _lib.gemm_last_kernel() == "simt"
-
-
-VARIANTS = {"pipelined_epilogue_and_fixed_cta_pairs": {"AECF_GEMM_EPI": "2", "AECF_GEMM_2SM_FIX": "1"},
-            "eight_warp_epilogues": {"AECF_GEMM_EPI": "3", "AECF_GEMM_2SM_EW": "8"},          # 1SM (cluster of two) and cta_group::2
-            "eight_warp_epilogue_no_cluster": {"AECF_GEMM_EPI": "3", "AECF_GEMM_CLUSTER": "1"},
-            "score_columns_on_cta_pairs": {"AECF_GEMM_2SM_AUX": "1", "AECF_GEMM_2SM_EW": "8"},
-            "resident_a_panel": {"AECF_GEMM_APANEL": "1", "AECF_GEMM_2SM_EW": "8"}}     # four epilogue warps: checked by hand runs
-
-
-@pytest.fixture(scope="module")
-def variant_runs():
-    """The library reads these switches once per process, hence one child pytest per variant, running the tests above with
-    the switches set; all children are started together and each test below waits for its own."""
-    if os.environ.get("AECF_EMU_GEMM_CHILD") == "1":
-        yield {}
-        return
-    from tests.emu_support import load_emulation
-    load_emulation()                                     # build once, before the children race for it
-    select = "(test_kernels and (384x256x128 or 392x520x200 or 512x256x640 or 1024x512x128 or 512x512x520)) or side_output or whole_step or reported_kernel or odd_number_of_row_blocks"
-    runs = {}
-    for name, switches in VARIANTS.items():
-        env = dict(os.environ, AECF_EMU_GEMM_CHILD="1", **switches)
-        runs[name] = subprocess.Popen([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", os.path.abspath(__file__),
-                                       "-k", select], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, cwd=ROOT)
-    yield runs
-    for proc in runs.values():
-        if proc.poll() is None:
-            proc.kill()
-
-
-@pytest.mark.parametrize("variant", sorted(VARIANTS))
-def test_epilogue_variant(variant_runs, variant):
-    if os.environ.get("AECF_EMU_GEMM_CHILD") == "1":
-        pytest.skip("already inside a variant run")
-    out, _ = variant_runs[variant].communicate(timeout=1500)
-    assert variant_runs[variant].returncode == 0, out[-4000:]

@@ -201,35 +201,6 @@ def test_random_multi_query_cases(multi_query, seed):
         MQ.test_bf16_masks_exact_against_stage_rounded_oracle(case)
 
 
-# ---- the streaming folded backward (AECF_POOL_BWD_STREAM=1, csrc/pool_bwd.cuh) ---------------------------------------
-@pytest.fixture
-def streaming_backward(monkeypatch):
-    monkeypatch.setenv("AECF_POOL_BWD_STREAM", "1")
-
-
-@pytest.mark.parametrize("case", P.FOLDABLE_FP32_CASES[1:8], ids=by_name)
-def test_streaming_backward_fp32_folded_matches_oracle(streaming_backward, case):
-    P.test_fp32_folded_key_projection_matches_oracle(case)
-
-
-@pytest.mark.parametrize("case", [c for c in P.BF16_CASES if not c.separate_value][1:], ids=by_name)
-def test_streaming_backward_bf16_matches_stage_rounded_oracle(streaming_backward, case):
-    P.test_bf16_masks_exact_against_stage_rounded_oracle(case, True)
-
-
-def test_streaming_backward_is_bit_identical_to_the_default(monkeypatch):
-    """Same arithmetic per row, same strips folded in the same order within a warp; only the row -> warp assignment differs,
-    so per-row outputs are identical bits and the batch-reduced bias gradients agree to rounding."""
-    from tests.golden.cases import CASES_BY_NAME, build_inputs
-    case = CASES_BY_NAME["d64_h8_m3_dropout"]
-    inp = build_inputs(case)
-    base = P.run_cuda(case, inp, torch.float32, fold=True)
-    monkeypatch.setenv("AECF_POOL_BWD_STREAM", "1")
-    new = P.run_cuda(case, inp, torch.float32, fold=True)
-    assert torch.equal(base[3]["key"], new[3]["key"])
-    assert_close("in_proj_bias", new[3]["in_proj_bias"], base[3]["in_proj_bias"], 1e-6)
-
-
 # ---- the device-side Philox pair a CUDA-graph capture reads (aecf_pool_desc::rng_state) ------------------------------
 @pytest.mark.parametrize("fold", [False, True], ids=["unfolded", "folded"])
 def test_device_side_philox_state_reproduces_the_by_value_pair(monkeypatch, fold):

@@ -626,8 +626,7 @@ def test_module_without_biases(dtype, fold):
 def test_unsupported_shapes_fail_loudly():
     pool = aecf_b200.MultimodalAttentionPool(64, num_heads=4, device=DEV)
     x = torch.randn(4, 3, 64, device=DEV)
-    with pytest.raises(_lib.UnsupportedShapeError):
-        pool(torch.randn(4, 2, 64, device=DEV), x)                  # two queries per sample
+    assert pool(torch.randn(4, 2, 64, device=DEV), x).shape == (4, 2, 64)            # two queries per sample: supported
     with pytest.raises(_lib.UnsupportedShapeError):
         pool(torch.randn(4, 1, 64, device=DEV), torch.randn(4, 9, 64, device=DEV))   # 9 tokens > 8
     odd = aecf_b200.MultimodalAttentionPool(60, num_heads=4, device=DEV)             # head_dim 15
