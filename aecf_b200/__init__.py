@@ -7,6 +7,7 @@ Same public names as the reference package ``aecf`` (reference ``aecf/__init__.p
 """
 from .layers import (CurriculumMasking, MultimodalAttentionPool, create_fusion_pool, get_rng_state,
                      multimodal_attention_pool, set_rng_state)
+from .projections import linear, project_tokens
 from . import graphs
 
 __version__ = "0.1.0"

@@ -85,7 +85,7 @@ class FusionGrads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "d_out", "d_pooled", "d_entropy", "d_ctx", "d_kv", "d_q_rows",
         "d_key", "d_value", "d_query", "d_in_proj_weight", "d_in_proj_bias", "d_out_proj_weight", "d_out_proj_bias",
-        "side_stream", "fork_event", "join_event")] + [("dp", C.POINTER(DpDesc))]
+        "side_stream", "fork_event", "fork_event2", "join_event")] + [("dp", C.POINTER(DpDesc))]
 
 
 BWD_ALL, BWD_OUT_PROJ, BWD_REST = 0, 1, 2

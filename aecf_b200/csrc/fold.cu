@@ -67,16 +67,59 @@ fold_prepare_query_kernel(const T* __restrict__ query, const T* __restrict__ in_
         const int strip = blockIdx.x - r * strips;
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         if (r < H) {
-            for (int j = warp; j < hd; j += 8) {
-                const T* wq = in_proj_weight + static_cast<size_t>(r * hd + j) * D;
-                float acc = 0.f;
-                for (int k = lane; k < D; k += 32) acc = fmaf(to_float<T>(query[k]), to_float<T>(wq[k]), acc);
+            // 16-byte loads, every load of a dot in flight before the first multiply; lanes cover the row chunk-wise and
+            // are folded by xor shuffles; chunks in order, so the value does not depend on the block that computes it
+            constexpr int V = Vec<T>::N;
+            const int NC = D / V;
+            // eight dots (rows j, j + 8, ... of the head) and their biases share one trip to memory
+            constexpr int Q = 8;
+            for (int j0 = warp; j0 < hd; j0 += 8 * Q) {
+                float acc[Q], bq[Q];
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(FULL_MASK, acc, off);
-                if (in_proj_bias != nullptr) acc += to_float<T>(in_proj_bias[r * hd + j]);
-                if (lane == 0) {
-                    qh[j] = acc;
-                    if (strip == 0) q_proj[r * hd + j] = acc;
+                for (int q = 0; q < Q; ++q) {
+                    acc[q] = 0.f;
+                    const int j = j0 + 8 * q;
+                    bq[q] = (in_proj_bias != nullptr && j < hd) ? to_float<T>(in_proj_bias[r * hd + j]) : 0.f;
+                }
+                for (int c0 = lane; c0 < NC; c0 += 64) {
+                    uint4 a[2], b[Q][2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int c = c0 + 32 * u;
+                        a[u] = c < NC ? ldg_cached(query + static_cast<size_t>(c) * V) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                        for (int q = 0; q < Q; ++q) {
+                            const int j = j0 + 8 * q;
+                            b[q][u] = (c < NC && j < hd) ? ldg_cached(in_proj_weight + static_cast<size_t>(r * hd + j) * D + static_cast<size_t>(c) * V)
+                                                         : make_uint4(0, 0, 0, 0);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        float fa[V];
+                        Vec<T>::unpack(a[u], fa);
+#pragma unroll
+                        for (int q = 0; q < Q; ++q) {
+                            float fb[V];
+                            Vec<T>::unpack(b[q][u], fb);
+#pragma unroll
+                            for (int v = 0; v < V; ++v) acc[q] = fmaf(fa[v], fb[v], acc[q]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const int j = j0 + 8 * q;
+                    float s = acc[q];
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(FULL_MASK, s, off);
+                    if (j < hd) {
+                        s += bq[q];
+                        if (lane == 0) {
+                            qh[j] = s;
+                            if (strip == 0) q_proj[r * hd + j] = s;
+                        }
+                    }
                 }
             }
         }
@@ -86,7 +129,7 @@ fold_prepare_query_kernel(const T* __restrict__ query, const T* __restrict__ in_
         float acc = 0.f;
         if (r < H && d < D) {
             const T* wk = in_proj_weight + (static_cast<size_t>(D) + static_cast<size_t>(r) * hd) * D + d;
-#pragma unroll 4
+#pragma unroll 8
             for (int j = y; j < hd; j += 8) acc = fmaf(qh[j], to_float<T>(wk[static_cast<size_t>(j) * D]), acc);
         }
         red[y][x] = acc;
@@ -237,7 +280,7 @@ int aecf_fold_prepare_query(int32_t device, int32_t dtype, int32_t embed_dim, in
     int rc = fold_check(dtype, embed_dim, num_heads);
     if (rc != AECF_OK) return rc;
     if (!query || !in_proj_weight || !q_proj || !folded_w) return AECF_ERR_INVALID;
-    if (!aligned16(in_proj_weight) || !aligned16(folded_w)) return AECF_ERR_ALIGNMENT;
+    if (!aligned16(in_proj_weight) || !aligned16(folded_w) || !aligned16(query)) return AECF_ERR_ALIGNMENT;
     if ((rc = use_device(device)) != AECF_OK) return rc;
     const int D = embed_dim, H = num_heads, hsp = aecf_fold_score_cols(dtype, H);
     const float scale = static_cast<float>(sqrt(1.0 / static_cast<double>(D / H)));

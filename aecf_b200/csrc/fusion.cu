@@ -138,9 +138,10 @@ static int carve(const aecf_pool_desc* d, const Geometry& g, void* base, Workspa
     return AECF_OK;
 }
 
-// ---- the folded backward, whole (phase AECF_BWD_ALL): five launches on `s`, the gradient tail next to the last one ----
-//   s    : dWo partials -> d_ctx -> pool backward -> [dWv ; R] partials -> (fork) -> dX -> (join)
-//   side :                                                              gather -> [peer sum] -> finish
+// ---- the folded backward, whole (phase AECF_BWD_ALL): five launches on `s`, the gradient tail next to them ----
+//   s    : dWo partials -> d_ctx -> pool backward -(fork)-> [dWv ; R] partials -(fork 2)-> dX -(join)->
+//   side :                                          colsum(d_out), dWo fold   [dWv ; R] fold, partial folds -> [peer sum] -> finish
+// Each half of the tail runs next to a tensor-core product that leaves half of the HBM bandwidth unused.
 static int folded_backward(const aecf_pool_desc* desc, const Geometry& g, const aecf_fusion_tensors* t,
                            const aecf_fusion_grads* gr, const Workspace& w, cudaStream_t s) {
     const int dt = g.dt, D = g.D, dev = desc->device, KF = g.D + g.HSP;
@@ -149,7 +150,8 @@ static int folded_backward(const aecf_pool_desc* desc, const Geometry& g, const 
     const aecf_dp_desc* dp = (gr->dp != nullptr && gr->dp->world > 1) ? gr->dp : nullptr;
     if (dp != nullptr && (dp->rank < 0 || dp->rank >= dp->world || dp->world > 8 || !dp->sums || !dp->reduced || !dp->flags))
         return AECF_ERR_INVALID;
-    const bool forked = gr->side_stream != nullptr && gr->fork_event != nullptr && gr->join_event != nullptr && want_tail;
+    const bool forked = gr->side_stream != nullptr && gr->fork_event != nullptr && gr->fork_event2 != nullptr &&
+                        gr->join_event != nullptr && want_tail;
     cudaStream_t side = forked ? static_cast<cudaStream_t>(gr->side_stream) : s;
     GradTailArgs a{};
     a.dtype = dt; a.D = D; a.H = g.H; a.HSP = g.HSP; a.sms = sm_count(dev);
@@ -158,6 +160,7 @@ static int folded_backward(const aecf_pool_desc* desc, const Geometry& g, const 
     a.q_proj = static_cast<const float*>(t->q_proj); a.in_proj_weight = t->in_proj_weight; a.query = t->query;
     a.d_in_w = gr->d_in_proj_weight; a.d_in_b = gr->d_in_proj_bias; a.d_out_w = gr->d_out_proj_weight;
     a.d_out_b = gr->d_out_proj_bias; a.d_query = gr->d_query;
+    a.d_out = gr->d_out_proj_bias ? gr->d_out : nullptr; a.rows = g.QR;
 
     if (gr->d_out_proj_weight) {                             // dWo = g^T ctx, left as split-K partials
         ScopedSite site(AECF_SITE_D_OUT_WEIGHT);
@@ -175,17 +178,24 @@ static int folded_backward(const aecf_pool_desc* desc, const Geometry& g, const 
                                           gr->d_entropy, gr->d_kv, w.pool, w.pool_bytes, s, &a.pool_blocks));
         a.pool_part = reinterpret_cast<const float*>(w.pool);
     }
+    if (want_tail) {
+        // first half of the tail (column sums of d_out, dWo fold: 86 MB of reads at config 2) next to the [dWv ; R] product.
+        // Not earlier: next to the pool backward it would only take HBM bandwidth from a kernel that is bound by it
+        // (r2 run 5: pool_bwd 88 -> 131 us), and the d_ctx product's CTAs leave no shared memory for a second CTA.
+        if (forked) {
+            AECF_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(gr->fork_event), s));
+            AECF_CUDA_OK(cudaStreamWaitEvent(side, static_cast<cudaEvent_t>(gr->fork_event), 0));
+        }
+        AECF_TRY(launch_grad_gather(a, GATHER_EARLY, side));
+    }
     if (want_in) {                                           // [dWv ; R] = [dV | ds]^T X, left as split-K partials
         ScopedSite site(AECF_SITE_D_KV_WEIGHT);
         const aecf_gemm_desc d = gemm_desc(dev, dt, dt, AECF_F32, dt, AECF_MN_MAJOR, AECF_MN_MAJOR, KF, D, g.rows, KF, D, D);
         AECF_TRY(gemm_partials(&d, gr->d_kv, t->key, w.gemm_g, w.gemm_g_bytes, s, &a.g));
     }
-    auto tail = [&]() -> int {
+    auto late = [&]() -> int {
         if (!want_tail) return AECF_OK;
-        a.d_out = gr->d_out_proj_bias ? gr->d_out : nullptr; a.rows = g.QR;
-        // the two "last block" counters at the end of the scratch: cleared here, so the caller's workspace needs no set-up
-        AECF_CUDA_OK(cudaMemsetAsync(w.tail + w.tail_bytes - 256, 0, 256, side));
-        AECF_TRY(launch_grad_gather(a, side));
+        AECF_TRY(launch_grad_gather(a, GATHER_LATE, side));
         const float* final_sums = a.sums;
         if (dp != nullptr) {
             AECF_TRY(launch_peer_sum(dev, dp, tail_layout(D, g.HSP).total, side));
@@ -194,9 +204,9 @@ static int folded_backward(const aecf_pool_desc* desc, const Geometry& g, const 
         return launch_grad_finish(a, final_sums, side);
     };
     if (forked) {
-        AECF_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(gr->fork_event), s));
-        AECF_CUDA_OK(cudaStreamWaitEvent(side, static_cast<cudaEvent_t>(gr->fork_event), 0));
-        AECF_TRY(tail());
+        AECF_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(gr->fork_event2), s));
+        AECF_CUDA_OK(cudaStreamWaitEvent(side, static_cast<cudaEvent_t>(gr->fork_event2), 0));
+        AECF_TRY(late());
         AECF_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(gr->join_event), side));
     }
     if (gr->d_key) {                                         // dX = [dV | ds] . [Wv ; Qk]
@@ -205,10 +215,9 @@ static int folded_backward(const aecf_pool_desc* desc, const Geometry& g, const 
         AECF_TRY(aecf_gemm(&d, gr->d_kv, t->folded_w, nullptr, gr->d_key, w.gemm, w.gemm_bytes, s));
     }
     if (forked) AECF_CUDA_OK(cudaStreamWaitEvent(s, static_cast<cudaEvent_t>(gr->join_event), 0));
-    else AECF_TRY(tail());
+    else AECF_TRY(late());
     return AECF_OK;
 }
-
 
 }  // namespace aecf
 

@@ -4,19 +4,24 @@
 // 604 us step, all on the critical path).
 //
 //   grad_gather   raw fp32 sums S = [ [dWv ; R] | dWo | colsum(d_out) | pool bias sums ]: folds the split-K partials of
-//                 the two weight-gradient products, the per-CTA partials of the pool backward and the column sums of
-//                 d_out (the gradient of out_proj.bias, torch/nn/functional.py:6653 backward) -- one pass, fixed orders
+//                 the two weight-gradient products and leaves per-block column sums of d_out (the gradient of
+//                 out_proj.bias, torch/nn/functional.py:6653 backward); grad_fold then folds those and the per-CTA
+//                 partials of the pool backward, one warp per column (every load in flight at once: these folds are
+//                 latency, not bandwidth)
 //   grad_peer_sum (world > 1) S summed over the ranks in fp32 through NVLink peer mappings: flag barrier, rank r sums
 //                 slice r of every rank's S in rank order and stores it into every rank's reduced buffer, flag barrier
 //                 (the scheme of peer_allreduce.cu, from one buffer into another)
 //   grad_finish   S -> parameter gradients in the parameter dtype: dWv, dWk = scale q (x) R, d_qp = scale Wk . R,
-//                 dWq = d_qp (x) q0, d_query = d_qp . Wq, the three in-projection bias thirds, dWo, d_out_proj_bias
-//                 (reference: what autograd derives from torch/nn/functional.py:5854-5855, 6653 for a shared query)
+//                 dWq = d_qp (x) q0, the three in-projection bias thirds, dWo, d_out_proj_bias; grad_dquery then forms
+//                 d_query = d_qp . Wq (reference: what autograd derives from torch/nn/functional.py:5854-5855, 6653 for a
+//                 shared query)
 //
 // Everything downstream of S is linear in S, so summing S over the ranks BEFORE grad_finish gives every rank the gradients
 // of the global batch with one rounding to the parameter dtype -- an N-rank run rounds like a 1-rank run (r1 reduced
 // bf16-rounded gradients).  S is half the size of the parameter set (dWk, dWq, d_query are images of the H rows of R).
-// All reductions are in fixed index order; the "last block" pattern only decides WHO does a final fold, never its order.
+// All reductions are in fixed index order (no atomics).  None of the kernels uses shared memory: they run NEXT TO the dX
+// product, whose persistent CTAs leave less than 2 KB of an SM's shared memory (cta_group::2 kernel: 225 KB + the per-CTA
+// reserve), and a CTA that needs more would wait for the product to end instead of sharing the SM with it.
 #include "common.cuh"
 #include "grad_tail.cuh"
 
@@ -24,15 +29,13 @@ namespace aecf {
 
 constexpr int TAIL_THREADS = 256;
 
-// ---- grad_gather ---------------------------------------------------------------------------------------------------
+// ---- grad_gather / grad_fold ------------------------------------------------------------------------------------------
 struct GatherParams {
     const float* g_part; int g_splits; long long g_stride;      // [dWv ; R] partials: g_splits slabs of (D + HSP) * D
     const float* o_part; int o_splits; long long o_stride;      // dWo partials: o_splits slabs of D * D
     const void* d_out; long long rows, ld;                      // [rows, D] in the parameter dtype: column sums -> bo
-    const float* pool_part; int pool_blocks;                    // [pool_blocks][3 D] per-CTA partials of the pool backward
     float* sums; TailLayout lay;
     float* colsum_part;                                         // [gridDim.x][D] scratch
-    unsigned* ticket;                                           // zero on entry, zero again on exit
     int D, HSP;
 };
 
@@ -40,23 +43,23 @@ template <typename T>
 __global__ void __launch_bounds__(TAIL_THREADS)
 grad_gather_kernel(const GatherParams p) {
     constexpr int V = Vec<T>::N;
-    __shared__ float red[TAIL_THREADS * 8];                     // [row lane][column] of one pass over the chunk columns
-    __shared__ int last;
     const int t = threadIdx.x;
     const int D = p.D;
     const int NC = D / V;                                       // 16-byte chunks per row of d_out
-    const int ncp = NC < TAIL_THREADS ? NC : TAIL_THREADS;      // chunk columns handled per pass
-    const int rl = TAIL_THREADS / ncp;                          // row lanes per pass
     pdl_wait();
 
-    // (1) column sums of this block's rows of d_out
+    // (1) column sums of this block's rows of d_out.  `rl` row lanes (a power of two, lanes of ONE warp, folded by xor
+    // shuffles in a fixed order) times 256 / rl chunk columns per pass.
     if (p.d_out != nullptr) {
+        int rl = 32;
+        while (rl > 1 && TAIL_THREADS / rl < NC) rl >>= 1;      // as many row lanes as still cover a row in one pass, if possible
+        const int ncp = TAIL_THREADS / rl;                      // chunk columns per pass
+        const int lane_r = t % rl, cc = t / rl;
         const long long per = (p.rows + gridDim.x - 1) / gridDim.x;
         const long long r0 = per * blockIdx.x, r1 = min(p.rows, r0 + per);
         const T* x = static_cast<const T*>(p.d_out);
         for (int cb = 0; cb < NC; cb += ncp) {
-            const int cc = t % ncp, lane_r = t / ncp;
-            const bool active = lane_r < rl && cb + cc < NC;
+            const bool active = cb + cc < NC;
             float acc[V];
 #pragma unroll
             for (int v = 0; v < V; ++v) acc[v] = 0.f;
@@ -83,44 +86,34 @@ grad_gather_kernel(const GatherParams p) {
                     for (int v = 0; v < V; ++v) acc[v] += f[v];
                 }
             }
-            __syncthreads();                                    // the previous pass has been read
-            if (active) {
+            for (int off = rl >> 1; off > 0; off >>= 1) {       // the rl row lanes are neighbouring lanes of one warp
 #pragma unroll
-                for (int v = 0; v < V; ++v) red[(lane_r * ncp + cc) * V + v] = acc[v];
+                for (int v = 0; v < V; ++v) acc[v] += __shfl_xor_sync(FULL_MASK, acc[v], off);
             }
-            __syncthreads();
-            for (int c = t; c < ncp * V && cb * V + c < D; c += TAIL_THREADS) {
-                float s = 0.f;
-                for (int y = 0; y < rl; ++y) s += red[y * ncp * V + c];
-                p.colsum_part[static_cast<long long>(blockIdx.x) * D + cb * V + c] = s;
+            if (active && lane_r == 0) {
+                float* out = p.colsum_part + static_cast<long long>(blockIdx.x) * D + static_cast<long long>(cb + cc) * V;
+#pragma unroll
+                for (int v = 0; v < V; ++v) out[v] = acc[v];
             }
         }
     }
 
-    // (2) the pool backward's per-CTA partials [d_q | d_bias_v | d_bias_k], one column per thread, blocks in order
+    // (2) split-K partials of the two weight-gradient products, splits in order, 16 bytes per thread, four splits in flight
     const long long gt = static_cast<long long>(blockIdx.x) * TAIL_THREADS + t;
-    if (p.pool_part != nullptr && gt < 3LL * D) {
-        float s = 0.f;
-        constexpr int U = 8;
-        int b = 0;
-        for (; b + U <= p.pool_blocks; b += U) {
-            float v[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) v[u] = p.pool_part[static_cast<long long>(b + u) * 3 * D + gt];
-#pragma unroll
-            for (int u = 0; u < U; ++u) s += v[u];
-        }
-        for (; b < p.pool_blocks; ++b) s += p.pool_part[static_cast<long long>(b) * 3 * D + gt];
-        p.sums[p.lay.pool + gt] = s;
-    }
-
-    // (3) split-K partials of the two weight-gradient products, splits in order, 16 bytes per thread
     const long long nthreads = static_cast<long long>(gridDim.x) * TAIL_THREADS;
     auto fold = [&](const float* part, int splits, long long stride, long long n, float* out) {
         if (part == nullptr) return;
         for (long long i = gt; i < n / 4; i += nthreads) {
             float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int z = 0; z < splits; ++z) {
+            int z = 0;
+            for (; z + 4 <= splits; z += 4) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(part + (z + u) * stride + 4 * i);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+            }
+            for (; z < splits; ++z) {
                 const float4 v = *reinterpret_cast<const float4*>(part + z * stride + 4 * i);
                 s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
             }
@@ -129,33 +122,48 @@ grad_gather_kernel(const GatherParams p) {
     };
     fold(p.g_part, p.g_splits, p.g_stride, static_cast<long long>(D + p.HSP) * D, p.sums + p.lay.g);
     fold(p.o_part, p.o_splits, p.o_stride, static_cast<long long>(D) * D, p.sums + p.lay.o);
-
-    // (4) the last block to get here folds the column-sum partials, blocks in order
-    if (p.d_out == nullptr) return;
-    __threadfence();
-    __syncthreads();
-    if (t == 0) last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
-    __syncthreads();
-    if (!last) return;
-    __threadfence();
-    for (int c = t; c < D; c += TAIL_THREADS) {
-        float s = 0.f;
-        constexpr int U = 8;
-        int b = 0;
-        for (; b + U <= static_cast<int>(gridDim.x); b += U) {
-            float v[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) v[u] = p.colsum_part[static_cast<long long>(b + u) * D + c];
-#pragma unroll
-            for (int u = 0; u < U; ++u) s += v[u];
-        }
-        for (; b < static_cast<int>(gridDim.x); ++b) s += p.colsum_part[static_cast<long long>(b) * D + c];
-        p.sums[p.lay.bo + c] = s;
-    }
-    if (t == 0) *p.ticket = 0u;                                 // re-armed for the next call (stream order makes it visible)
 }
 
-// ---- grad_finish ---------------------------------------------------------------------------------------------------
+// One warp per column: lane l sums rows l, l + 32, ... (every load issued before the first add), the 32 lane sums are
+// folded by xor shuffles.  Columns [0, D): the per-block column sums of d_out -> bo; columns [D, 4 D): the pool backward's
+// per-CTA partials [d_q | d_bias_v | d_bias_k] -> pool.
+struct FoldParams {
+    const float* colsum_part; int colsum_rows;                  // [colsum_rows][D], or null
+    const float* pool_part; int pool_rows;                      // [pool_rows][3 D], or null
+    float* sums; TailLayout lay;
+    int D;
+};
+
+__global__ void __launch_bounds__(TAIL_THREADS)
+grad_fold_kernel(const FoldParams p) {
+    const int lane = threadIdx.x & 31;
+    const int col = blockIdx.x * (TAIL_THREADS / 32) + (threadIdx.x >> 5);
+    pdl_wait();
+    if (col >= 4 * p.D) return;
+    const bool is_colsum = col < p.D;
+    const float* part = is_colsum ? p.colsum_part : p.pool_part;
+    if (part == nullptr) return;
+    const int rows = is_colsum ? p.colsum_rows : p.pool_rows;
+    const long long ld = is_colsum ? p.D : 3LL * p.D;
+    const int c = is_colsum ? col : col - p.D;
+    float s = 0.f;
+    constexpr int U = 16;
+    for (int r0 = lane; r0 < rows; r0 += 32 * U) {
+        float v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int r = r0 + 32 * u;
+            v[u] = r < rows ? part[static_cast<long long>(r) * ld + c] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) s += v[u];
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(FULL_MASK, s, off);
+    if (lane == 0) p.sums[(is_colsum ? p.lay.bo : p.lay.pool) + c] = s;
+}
+
+// ---- grad_finish / grad_dquery ----------------------------------------------------------------------------------------
 struct FinishParams {
     const float* sums; TailLayout lay;
     const float* q_proj;            // [D] fp32: projected query (unscaled)
@@ -166,163 +174,208 @@ struct FinishParams {
     void* d_out_w;                  // [D, D], nullable
     void* d_out_b;                  // [D], nullable
     void* d_query;                  // [D], nullable
-    float* dq_part;                 // [gridDim.x][D] scratch
-    unsigned* ticket;
+    float* d_qp;                    // [ceil(D / 8)][D] scratch: per-block partials of d_query
     int D, H, HSP;
     float scale;
 };
 
-// Block b owns the in-projection rows i = 8 b .. 8 b + 7, one warp per row (head h = i / head_dim):
+template <typename T> __device__ __forceinline__ void store4(T* p, float a, float b, float c, float d);
+template <> __device__ __forceinline__ void store4<float>(float* p, float a, float b, float c, float d) {
+    *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float a, float b, float c, float d) {
+    *reinterpret_cast<uint2*>(p) = make_uint2(Vec<__nv_bfloat16>::pack2(a, b), Vec<__nv_bfloat16>::pack2(c, d));
+}
+template <typename T> __device__ __forceinline__ float4 load4(const T* p);
+template <> __device__ __forceinline__ float4 load4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <> __device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
+    const uint2 r = *reinterpret_cast<const uint2*>(p);
+    return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16),
+                       __uint_as_float(r.y & 0xffff0000u));
+}
+
+// One warp per in-projection row i (head h = i / head_dim), 8 rows per block:
 //   dWv[i, :] = G[i, :]     dWk[i, :] = scale q[i] R[h, :]     d_qp[i] = scale Wk[i, :] . R[h, :]     dWo[i, :] = O[i, :]
-//   dWq[i, :] = d_qp[i] q0[:]     d_query[:] += d_qp[i] Wq[i, :]  (8 rows folded in shared memory, blocks by the last block)
-//   d_in_b = [ d_qp | d_bias_k | d_bias_v ]     d_out_b = colsum(d_out)
+//   dWq[i, :] = d_qp[i] q0[:]     d_in_b = [ d_qp | d_bias_k | d_bias_v ]     d_out_b = colsum(d_out)
 template <typename T>
 __global__ void __launch_bounds__(TAIL_THREADS)
 grad_finish_kernel(const FinishParams p) {
-    __shared__ float red[8][128 * 4 + 4];                       // one 512-column tile of the 8 rows' d_query terms
-    __shared__ int last;
+    __shared__ float qps[8];                                    // d_qp of the block's 8 rows
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int D = p.D;
     const int i = blockIdx.x * 8 + warp;
-    const bool row_ok = i < D;
     pdl_wait();
     const T* W = static_cast<const T*>(p.in_proj_weight);
     const T* q0 = static_cast<const T*>(p.query);
     T* d_in_w = static_cast<T*>(p.d_in_w);
     float d_qp = 0.f;
-    if (row_ok) {
-        const int h = i / (D / p.H);
-        const float* R = p.sums + p.lay.g + static_cast<long long>(D + h) * D;
-        const float* G = p.sums + p.lay.g + static_cast<long long>(i) * D;
-        const float* O = p.sums + p.lay.o + static_cast<long long>(i) * D;
-        const T* wk = W + (static_cast<long long>(D) + i) * D;
-        const float sq = p.scale * __ldg(p.q_proj + i);
-        float dot = 0.f;
-        for (int d = lane * 4; d < D; d += 128) {
-            const float4 r = *reinterpret_cast<const float4*>(R + d);
-            dot = fmaf(to_float<T>(wk[d]), r.x, dot); dot = fmaf(to_float<T>(wk[d + 1]), r.y, dot);
-            dot = fmaf(to_float<T>(wk[d + 2]), r.z, dot); dot = fmaf(to_float<T>(wk[d + 3]), r.w, dot);
+    if (i < D) {
+    const int h = i / (D / p.H);
+    const float* R = p.sums + p.lay.g + static_cast<long long>(D + h) * D;
+    const float* G = p.sums + p.lay.g + static_cast<long long>(i) * D;
+    const float* O = p.sums + p.lay.o + static_cast<long long>(i) * D;
+    const T* wk = W + (static_cast<long long>(D) + i) * D;
+    const float sq = p.scale * __ldg(p.q_proj + i);
+    float dot = 0.f;
+    // four 128-column steps (one 512-wide batch) at a time: every load of the batch is issued before anything is stored, so a
+    // row costs one trip to memory, not four (the kernel is nothing but latency)
+    for (int d0 = lane * 4; d0 < D; d0 += 512) {
+        float4 r[4], w[4], g[4], o[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int d = d0 + 128 * u;
+            const bool ok = d < D;
+            r[u] = ok ? *reinterpret_cast<const float4*>(R + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+            w[u] = ok ? load4<T>(wk + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+            g[u] = (ok && d_in_w != nullptr) ? *reinterpret_cast<const float4*>(G + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+            o[u] = (ok && p.d_out_w != nullptr) ? *reinterpret_cast<const float4*>(O + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int d = d0 + 128 * u;
+            if (d >= D) continue;
+            dot = fmaf(w[u].x, r[u].x, dot); dot = fmaf(w[u].y, r[u].y, dot);
+            dot = fmaf(w[u].z, r[u].z, dot); dot = fmaf(w[u].w, r[u].w, dot);
             if (d_in_w != nullptr) {
-                T* dwk = d_in_w + (static_cast<long long>(D) + i) * D + d;
-                T* dwv = d_in_w + (2LL * D + i) * D + d;
-                const float4 g = *reinterpret_cast<const float4*>(G + d);
-                dwk[0] = from_float<T>(sq * r.x); dwk[1] = from_float<T>(sq * r.y);
-                dwk[2] = from_float<T>(sq * r.z); dwk[3] = from_float<T>(sq * r.w);
-                dwv[0] = from_float<T>(g.x); dwv[1] = from_float<T>(g.y); dwv[2] = from_float<T>(g.z); dwv[3] = from_float<T>(g.w);
+                store4<T>(d_in_w + (static_cast<long long>(D) + i) * D + d, sq * r[u].x, sq * r[u].y, sq * r[u].z, sq * r[u].w);
+                store4<T>(d_in_w + (2LL * D + i) * D + d, g[u].x, g[u].y, g[u].z, g[u].w);
             }
-            if (p.d_out_w != nullptr) {
-                T* dwo = static_cast<T*>(p.d_out_w) + static_cast<long long>(i) * D + d;
-                const float4 o = *reinterpret_cast<const float4*>(O + d);
-                dwo[0] = from_float<T>(o.x); dwo[1] = from_float<T>(o.y); dwo[2] = from_float<T>(o.z); dwo[3] = from_float<T>(o.w);
-            }
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) dot += __shfl_xor_sync(FULL_MASK, dot, off);
-        d_qp = p.scale * dot;
-        if (lane == 0) {
-            if (p.d_in_b != nullptr) {
-                T* db = static_cast<T*>(p.d_in_b);
-                db[i] = from_float<T>(d_qp);
-                db[D + i] = from_float<T>(p.sums[p.lay.pool + 2LL * D + i]);       // d_bias_k
-                db[2 * D + i] = from_float<T>(p.sums[p.lay.pool + D + i]);         // d_bias_v
-            }
-            if (p.d_out_b != nullptr) static_cast<T*>(p.d_out_b)[i] = from_float<T>(p.sums[p.lay.bo + i]);
+            if (p.d_out_w != nullptr)
+                store4<T>(static_cast<T*>(p.d_out_w) + static_cast<long long>(i) * D + d, o[u].x, o[u].y, o[u].z, o[u].w);
         }
     }
-    // query side, 512 columns at a time
-    for (int c0 = 0; c0 < D; c0 += 512) {
-        float4 term = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int d = c0 + lane * 4;
-        // each lane covers columns c0 + 4 lane + {0..3} + 128 k, k = 0..3
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int dd = d + 128 * k;
-            term = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row_ok && dd < D) {
-                if (d_in_w != nullptr) {
-                    T* dwq = d_in_w + static_cast<long long>(i) * D + dd;
-                    dwq[0] = from_float<T>(d_qp * to_float<T>(q0[dd])); dwq[1] = from_float<T>(d_qp * to_float<T>(q0[dd + 1]));
-                    dwq[2] = from_float<T>(d_qp * to_float<T>(q0[dd + 2])); dwq[3] = from_float<T>(d_qp * to_float<T>(q0[dd + 3]));
-                }
-                const T* wq = W + static_cast<long long>(i) * D + dd;
-                term = make_float4(d_qp * to_float<T>(wq[0]), d_qp * to_float<T>(wq[1]), d_qp * to_float<T>(wq[2]),
-                                   d_qp * to_float<T>(wq[3]));
-            }
-            *reinterpret_cast<float4*>(&red[warp][(k * 32 + lane) * 4]) = term;
-        }
-        __syncthreads();
-        // column c0 + 128 k + 4 lane + e  <->  red[.][(k * 32 + lane) * 4 + e]: the layout is column-linear
-        for (int c = threadIdx.x; c < 512 && c0 + c < D; c += TAIL_THREADS) {
-            float s = 0.f;
+    for (int off = 16; off > 0; off >>= 1) dot += __shfl_xor_sync(FULL_MASK, dot, off);
+    d_qp = p.scale * dot;
+    if (d_in_w != nullptr) {
+        for (int d0 = lane * 4; d0 < D; d0 += 512) {
+            float4 q[4];
 #pragma unroll
-            for (int w = 0; w < 8; ++w) s += red[w][c];
-            p.dq_part[static_cast<long long>(blockIdx.x) * D + c0 + c] = s;
+            for (int u = 0; u < 4; ++u) q[u] = (d0 + 128 * u < D) ? load4<T>(q0 + d0 + 128 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (d0 + 128 * u < D)
+                    store4<T>(d_in_w + static_cast<long long>(i) * D + d0 + 128 * u, d_qp * q[u].x, d_qp * q[u].y, d_qp * q[u].z,
+                              d_qp * q[u].w);
         }
-        __syncthreads();
     }
+    if (lane == 0) {
+        if (p.d_in_b != nullptr) {
+            T* db = static_cast<T*>(p.d_in_b);
+            db[i] = from_float<T>(d_qp);
+            db[D + i] = from_float<T>(p.sums[p.lay.pool + 2LL * D + i]);       // d_bias_k
+            db[2 * D + i] = from_float<T>(p.sums[p.lay.pool + D + i]);         // d_bias_v
+        }
+        if (p.d_out_b != nullptr) static_cast<T*>(p.d_out_b)[i] = from_float<T>(p.sums[p.lay.bo + i]);
+    }
+    }   // i < D
+    // this block's share of d_query[c] = sum_i d_qp[i] Wq[i, c] (torch/nn/functional.py:5854 backward): a thread owns its
+    // columns and sums the block's 8 rows in order, all 8 loads in flight; grad_dquery_fold sums the blocks
     if (p.d_query == nullptr) return;
-    __threadfence();
+    if (lane == 0) qps[warp] = d_qp;                            // rows past D contribute 0
     __syncthreads();
-    if (threadIdx.x == 0) last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
-    __syncthreads();
-    if (!last) return;
-    __threadfence();
+    const int rows = min(8, D - static_cast<int>(blockIdx.x) * 8);
     for (int c = threadIdx.x; c < D; c += TAIL_THREADS) {
+        float w[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            w[k] = k < rows ? to_float<T>(W[(static_cast<long long>(blockIdx.x) * 8 + k) * D + c]) : 0.f;
         float s = 0.f;
-        for (int b = 0; b < static_cast<int>(gridDim.x); ++b) s += p.dq_part[static_cast<long long>(b) * D + c];
-        static_cast<T*>(p.d_query)[c] = from_float<T>(s);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s = fmaf(qps[k], w[k], s);
+        p.d_qp[static_cast<long long>(blockIdx.x) * D + c] = s;
     }
-    if (threadIdx.x == 0) *p.ticket = 0u;
+}
+
+// d_query[c] = sum over the blocks of grad_finish of their partials: one warp per column, every load in flight at once.
+template <typename T>
+__global__ void __launch_bounds__(TAIL_THREADS)
+grad_dquery_fold_kernel(const float* __restrict__ part, int rows, int D, T* __restrict__ d_query) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (TAIL_THREADS / 32) + (threadIdx.x >> 5);
+    pdl_wait();
+    if (c >= D) return;
+    float s = 0.f;
+    constexpr int U = 8;
+    for (int r0 = lane; r0 < rows; r0 += 32 * U) {
+        float v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = (r0 + 32 * u < rows) ? part[static_cast<long long>(r0 + 32 * u) * D + c] : 0.f;
+#pragma unroll
+        for (int u = 0; u < U; ++u) s += v[u];
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(FULL_MASK, s, off);
+    if (lane == 0) d_query[c] = from_float<T>(s);
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------------
+static size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+
 size_t grad_tail_scratch_bytes(int D, int sms) {
-    const size_t gather = static_cast<size_t>(2 * sms) * D * sizeof(float);              // colsum partials
-    const size_t finish = static_cast<size_t>((D + 7) / 8) * D * sizeof(float);           // d_query partials
-    return ((gather + 255) & ~static_cast<size_t>(255)) + ((finish + 255) & ~static_cast<size_t>(255)) + 256;   // + tickets
+    return align256(static_cast<size_t>(2 * sms) * D * sizeof(float))       // per-block column sums of d_out
+         + align256(static_cast<size_t>((D + 7) / 8) * D * sizeof(float));  // per-block partials of d_query
 }
 
-int launch_grad_gather(const GradTailArgs& a, cudaStream_t s) {
-    GatherParams p{};
-    p.g_part = a.g.partial; p.g_splits = a.g.splits; p.g_stride = a.g.stride;
-    p.o_part = a.o.partial; p.o_splits = a.o.splits; p.o_stride = a.o.stride;
-    p.d_out = a.d_out; p.rows = a.rows; p.ld = a.D;
-    p.pool_part = a.pool_part; p.pool_blocks = a.pool_blocks;
-    p.sums = a.sums; p.lay = tail_layout(a.D, a.HSP);
-    p.D = a.D; p.HSP = a.HSP;
-    char* scratch = static_cast<char*>(a.scratch);
-    const size_t gather = (static_cast<size_t>(2 * a.sms) * a.D * sizeof(float) + 255) & ~static_cast<size_t>(255);
-    const size_t finish = (static_cast<size_t>((a.D + 7) / 8) * a.D * sizeof(float) + 255) & ~static_cast<size_t>(255);
-    p.colsum_part = reinterpret_cast<float*>(scratch);
-    p.ticket = reinterpret_cast<unsigned*>(scratch + gather + finish);
+// which = GATHER_EARLY: column sums of d_out (per block) and the dWo fold -- everything the backward knows after its first
+// product; GATHER_LATE: the [dWv ; R] fold, then grad_fold (the column-sum and pool partials -> S).
+int launch_grad_gather(const GradTailArgs& a, int which, cudaStream_t s) {
     const int V = a.dtype == AECF_BF16 ? 8 : 4;
     if (a.D % V != 0) return AECF_ERR_UNSUPPORTED;
-    const dim3 grid(static_cast<unsigned>(2 * a.sms)), block(TAIL_THREADS);
+    const TailLayout lay = tail_layout(a.D, a.HSP);
+    const int blocks = 2 * a.sms;
+    GatherParams p{};
+    p.sums = a.sums; p.lay = lay; p.D = a.D; p.HSP = a.HSP;
+    p.colsum_part = static_cast<float*>(a.scratch);
+    const bool early = which == GATHER_EARLY;
+    if (early) {
+        p.o_part = a.o.partial; p.o_splits = a.o.splits; p.o_stride = a.o.stride;
+        p.d_out = a.d_out; p.rows = a.rows; p.ld = a.D;
+    } else {
+        p.g_part = a.g.partial; p.g_splits = a.g.splits; p.g_stride = a.g.stride;
+    }
     TimedLaunch timed(s, AECF_SITE_GRAD_GATHER);
-    if (a.dtype == AECF_BF16) AECF_CUDA_OK(launch_pdl(grad_gather_kernel<__nv_bfloat16>, grid, block, 0, s, p));
-    else AECF_CUDA_OK(launch_pdl(grad_gather_kernel<float>, grid, block, 0, s, p));
-    count_launch();
+    if (p.o_part != nullptr || p.d_out != nullptr || p.g_part != nullptr) {
+        if (a.dtype == AECF_BF16) AECF_CUDA_OK(launch_pdl(grad_gather_kernel<__nv_bfloat16>, dim3(blocks), dim3(TAIL_THREADS), 0, s, p));
+        else AECF_CUDA_OK(launch_pdl(grad_gather_kernel<float>, dim3(blocks), dim3(TAIL_THREADS), 0, s, p));
+        count_launch();
+    }
+    if (!early) {
+        FoldParams f{};
+        f.colsum_part = a.d_out ? p.colsum_part : nullptr; f.colsum_rows = blocks;
+        f.pool_part = a.pool_part; f.pool_rows = a.pool_blocks;
+        f.sums = a.sums; f.lay = lay; f.D = a.D;
+        AECF_CUDA_OK(launch_pdl(grad_fold_kernel, dim3((4 * a.D + 7) / 8), dim3(TAIL_THREADS), 0, s, f));
+        count_launch();
+    }
     return AECF_OK;
 }
 
 int launch_grad_finish(const GradTailArgs& a, const float* sums, cudaStream_t s) {
+    if (a.D % 4 != 0) return AECF_ERR_UNSUPPORTED;
     FinishParams p{};
     p.sums = sums; p.lay = tail_layout(a.D, a.HSP);
     p.q_proj = a.q_proj; p.in_proj_weight = a.in_proj_weight; p.query = a.query;
     p.d_in_w = a.d_in_w; p.d_in_b = a.d_in_b; p.d_out_w = a.d_out_w; p.d_out_b = a.d_out_b; p.d_query = a.d_query;
     p.D = a.D; p.H = a.H; p.HSP = a.HSP;
     p.scale = static_cast<float>(sqrt(1.0 / static_cast<double>(a.D / a.H)));
-    char* scratch = static_cast<char*>(a.scratch);
-    const size_t gather = (static_cast<size_t>(2 * a.sms) * a.D * sizeof(float) + 255) & ~static_cast<size_t>(255);
-    const size_t finish = (static_cast<size_t>((a.D + 7) / 8) * a.D * sizeof(float) + 255) & ~static_cast<size_t>(255);
-    p.dq_part = reinterpret_cast<float*>(scratch + gather);
-    p.ticket = reinterpret_cast<unsigned*>(scratch + gather + finish) + 1;
-    if (a.D % 4 != 0) return AECF_ERR_UNSUPPORTED;
+    p.d_qp = reinterpret_cast<float*>(static_cast<char*>(a.scratch) + align256(static_cast<size_t>(2 * a.sms) * a.D * sizeof(float)));
     const dim3 grid(static_cast<unsigned>((a.D + 7) / 8)), block(TAIL_THREADS);
     TimedLaunch timed(s, AECF_SITE_GRAD_FINISH);
     if (a.dtype == AECF_BF16) AECF_CUDA_OK(launch_pdl(grad_finish_kernel<__nv_bfloat16>, grid, block, 0, s, p));
     else AECF_CUDA_OK(launch_pdl(grad_finish_kernel<float>, grid, block, 0, s, p));
     count_launch();
+    if (a.d_query != nullptr) {
+        const dim3 g2(static_cast<unsigned>((a.D + 7) / 8));
+        const int rows = (a.D + 7) / 8;
+        if (a.dtype == AECF_BF16)
+            AECF_CUDA_OK(launch_pdl(grad_dquery_fold_kernel<__nv_bfloat16>, g2, block, 0, s, static_cast<const float*>(p.d_qp), rows, a.D,
+                                    static_cast<__nv_bfloat16*>(a.d_query)));
+        else
+            AECF_CUDA_OK(launch_pdl(grad_dquery_fold_kernel<float>, g2, block, 0, s, static_cast<const float*>(p.d_qp), rows, a.D,
+                                    static_cast<float*>(a.d_query)));
+        count_launch();
+    }
     return AECF_OK;
 }
 

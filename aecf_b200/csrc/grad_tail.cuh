@@ -24,13 +24,14 @@ struct GradTailArgs {
     const void* d_out; long long rows;  // column sums of d_out -> d_out_proj_bias (null: not wanted)
     const float* pool_part; int pool_blocks;
     float* sums;                        // S, tail_layout(D, HSP).total floats
-    void* scratch;                      // grad_tail_scratch_bytes(D, sms), its last 256 bytes zeroed once by the caller
+    void* scratch;                      // grad_tail_scratch_bytes(D, sms)
     const float* q_proj; const void* in_proj_weight; const void* query;
     void *d_in_w, *d_in_b, *d_out_w, *d_out_b, *d_query;
 };
 
 size_t grad_tail_scratch_bytes(int D, int sms);
-int launch_grad_gather(const GradTailArgs& a, cudaStream_t s);
+enum { GATHER_EARLY = 0, GATHER_LATE = 1 };
+int launch_grad_gather(const GradTailArgs& a, int which, cudaStream_t s);
 int launch_grad_finish(const GradTailArgs& a, const float* sums, cudaStream_t s);
 // peer_allreduce.cu: dst[r][i] = (1/world if average) * sum_r' src[r'][i] for every rank r, fp32, `count` floats
 int launch_peer_sum(int device, const aecf_dp_desc* dp, long long count, cudaStream_t s);

@@ -69,13 +69,18 @@ class FusedGradSum:
     rank mapped into this process, plus the flag blocks of the kernel's two barriers.  Construction is collective.
     The pool's backward passes ``pointer()`` to ``aecf_fusion_bwd`` whenever ``usable(desc)``."""
 
-    def __init__(self, pool, group=None, average: bool = True):
+    def __init__(self, pool, group=None, average: bool = True, *, local_ranks: Optional[Tuple[int, int, list, list]] = None):
+        """``local_ranks = (rank, world, buffers, flag blocks)``: W ranks EMULATED on one device (tests): the W buffers
+        (``None`` entries are allocated) and flag blocks are plain local tensors shared by the W instances, no IPC."""
         import ctypes as C
 
         from . import _lib, ops
         att = pool.attention
         dev, dtype = att.in_proj_weight.device, att.in_proj_weight.dtype
-        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if local_ranks is not None:
+            self.rank, self.world = local_ranks[0], local_ranks[1]
+        else:
+            self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         if self.world > 8:
             raise ValueError("the fused gradient sum covers the (at most 8) GPUs of one NVLink node")
         probe = ops.make_pool_desc(dev, dtype, batch=1, num_tokens=2, embed_dim=pool.embed_dim, num_heads=pool.num_heads,
@@ -85,9 +90,17 @@ class FusedGradSum:
         if self.floats == 0:
             raise ValueError("this pool has no fused gradient tail (the folded key projection does not apply)")
         self.embed_dim, self.num_heads, self.dtype = pool.embed_dim, pool.num_heads, dtype
-        self.buffer = torch.zeros(2 * self.floats, dtype=torch.float32, device=dev)      # [raw sums | reduced sums]
-        self.flags = ops.peer_flag_block(dev)
-        buffers, flags = _map_peer_tensors([self.buffer, self.flags], group)
+        if local_ranks is not None:
+            buffers, flags = local_ranks[2], local_ranks[3]
+            for r in range(self.world):
+                if buffers[r] is None:
+                    buffers[r] = torch.zeros(2 * self.floats, dtype=torch.float32, device=dev)
+                    flags[r] = ops.peer_flag_block(dev)
+            self.buffer, self.flags = buffers[self.rank], flags[self.rank]
+        else:
+            self.buffer = torch.zeros(2 * self.floats, dtype=torch.float32, device=dev)      # [raw sums | reduced sums]
+            self.flags = ops.peer_flag_block(dev)
+            buffers, flags = _map_peer_tensors([self.buffer, self.flags], group)
         self._keep = (buffers, flags)
         n = self.floats * 4
         self._sums = (C.c_void_p * self.world)(*[b.data_ptr() for b in buffers])
@@ -288,25 +301,40 @@ class GradientSync:
 
     # -- called from the backward (autograd worker thread) -----------------------------------
     def on_ready(self, name: str, grad: torch.Tensor) -> None:
-        if not self.enabled or name not in self.slices or name in self.reported or self.world_size == 1:
+        if name not in self.slices or self.world_size == 1:
             return                                                     # single process: autograd's .grad is final
         view = self.views[name]
         param_grad = self.params[name].grad
-        if param_grad is not None and param_grad.data_ptr() == view.data_ptr() and grad.data_ptr() != view.data_ptr():
-            # accumulation: param.grad lives in the bucket and autograd adds `grad` to it AFTER this backward returns, so
-            # the bucket is complete only in finish().  A bucket that already holds a cross-rank SUM must not be summed
-            # again (a mean may: every rank holds the same value).
-            if self.bucket_is_reduced and not self.average:
-                raise RuntimeError("GradientSync(average=False): accumulating onto gradients that were already summed over "
-                                   "the ranks; set enabled=False for all but the last micro-batch")
+        accumulating = (param_grad is not None and param_grad.data_ptr() == view.data_ptr()
+                        and grad.data_ptr() != view.data_ptr())
+        if not self.enabled:
+            if accumulating:
+                self.bucket_is_reduced = False           # local gradients are being added to the slice: reduce it whole later
+            return
+        if name in self.reported:
+            return
+        if accumulating:
+            # param.grad lives in the bucket and autograd adds `grad` to it AFTER this backward returns.
+            if self.bucket_is_reduced:
+                # ... onto numbers that are already a cross-rank result (or zeros): only the NEW gradient is reduced,
+                # here and now, before autograd adds it (rare path: one small collective per parameter)
+                self._reduce_now(grad)
+                return
+            # ... onto local, unreduced gradients (enabled=False micro-batches): the bucket is reduced whole in finish()
             self.accumulated.add(name)
         elif grad.data_ptr() != view.data_ptr():                       # produced elsewhere: copy into the bucket
             view.copy_(grad.reshape(view.shape))
         self.reported.add(name)
         if (self.overlap and not self.accumulated and self.reduced_upto == 0
                 and all(n in self.reported for n in EARLY if n in self.slices)):
-            self._reduce(0, self.early_end, side_stream=True)
+            self._reduce(0, self.early_end, side_stream=False if self.accumulated else True)
             self.reduced_upto = self.early_end
+
+    def _reduce_now(self, tensor: torch.Tensor) -> None:
+        avg = self.average and dist.get_backend(self.group) == "nccl"
+        dist.all_reduce(tensor, op=dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM, group=self.group)
+        if self.average and not avg:
+            tensor.mul_(1.0 / self.world_size)
 
     # -- called by the training loop after loss.backward() -----------------------------------
     def finish(self) -> None:

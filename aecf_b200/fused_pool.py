@@ -56,18 +56,24 @@ class PoolConfig:
 
 
 class SideStream:
-    """A second stream of the pool's device and the two events that fork the backward's gradient tail onto it and join
-    it back (``aecf_fusion_grads.side_stream / fork_event / join_event``).  The tail -- split-K folds, column sums, the
+    """A second stream of the pool's device and the events that fork the backward's gradient tail onto it (twice) and join
+    it back (``aecf_fusion_grads.side_stream / fork_event / fork_event2 / join_event``).  The tail -- split-K folds, column sums, the
     rank-H key/query terms, with data parallelism the cross-rank sum -- then runs NEXT TO the dX product.  Works eagerly
     and under CUDA-graph capture (the event edges become graph edges)."""
 
     def __init__(self, device: torch.device):
         self.device = device
         self.stream = torch.cuda.Stream(device=device)
-        self.fork, self.join = torch.cuda.Event(), torch.cuda.Event()
+        self.fork, self.fork2, self.join = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
         with torch.cuda.device(device):                 # the handles exist only after a first record
-            self.fork.record(self.stream)
-            self.join.record(self.stream)
+            for event in (self.fork, self.fork2, self.join):
+                event.record(self.stream)
+
+    def __deepcopy__(self, memo):                       # a copied module gets a stream and events of its own
+        return SideStream(self.device)
+
+    def __reduce__(self):
+        return (SideStream, (self.device,))
 
 
 def _rows(x3d: torch.Tensor) -> torch.Tensor:
@@ -209,8 +215,8 @@ class FusedPoolFunction(torch.autograd.Function):
             d_out_proj_weight=p(d_out_w), d_out_proj_bias=p(d_out_b))
         side = cfg.side
         if side is not None and cfg.fold and side.device == dev:
-            grads.side_stream, grads.fork_event, grads.join_event = (
-                side.stream.cuda_stream, side.fork.cuda_event, side.join.cuda_event)
+            grads.side_stream, grads.fork_event, grads.fork_event2, grads.join_event = (
+                side.stream.cuda_stream, side.fork.cuda_event, side.fork2.cuda_event, side.join.cuda_event)
         if fused_dp is not None:
             grads.dp = fused_dp.pointer()
             fused_dp.ran = True

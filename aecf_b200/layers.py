@@ -410,7 +410,7 @@ class MultimodalAttentionPool(nn.Module):
             seq_first=not self.batch_first, fold=fold, want_mask_bits=self._want_mask_bits, bias_strides=bias_strides,
             tgt_len=tgt_len, grad_ready=self._grad_ready, grad_buffers=self._grad_buffers,
             grad_ready_early=bool(self._grad_ready_early),
-            loss_target=cm._loss_target() if (masking == 1 and return_info) else None,
+            loss_target=cm._loss_target() if (masking == 1 and return_info and os.environ.get("AECF_FUSED_LOSS", "1") != "0") else None,
             side=self._side_stream(key.device) if fold else None, dp=self._dp)
         out, pooled, entropy, mask_rate, masked, bits, fused_loss = FusedPoolFunction.apply(
             q_src, key_c, value_c, att.in_proj_weight, att.in_proj_bias, att.out_proj.weight, att.out_proj.bias,

@@ -8,7 +8,10 @@
   curriculum stage that is switched on at run time.
 
 ``fusion`` selects the implementation of the four public names (default: this repo's ``aecf`` package);
-the parity tests pass an oracle-backed stand-in to check the callers end to end.
+the parity tests pass an oracle-backed stand-in to check the callers end to end.  Where the fusion package also
+offers ``project_tokens`` / ``linear`` (aecf_b200 does: the library's own GEMMs writing the encoder outputs straight into the
+``[B, M, D]`` token buffer), the models use them instead of ``torch.stack`` over ``nn.Linear`` outputs; the parameters are
+the same ``nn.Linear`` modules either way, so state_dicts match the reference model's.
 """
 from __future__ import annotations
 
@@ -31,14 +34,20 @@ class VisionLanguageModel(nn.Module):
         self.fusion_query, self.fusion_pool = fusion.create_fusion_pool(
             embed_dim=hidden_dim, num_modalities=2, mask_prob=mask_prob, **pool_kwargs)
         self.classifier = nn.Linear(hidden_dim, num_classes)
+        self._project_tokens = getattr(fusion, "project_tokens", None)
+        self._linear = getattr(fusion, "linear", None)
 
     def forward(self, image_feats: torch.Tensor, text_feats: torch.Tensor, return_info: bool = False):
-        tokens = torch.stack([self.img_proj(image_feats), self.txt_proj(text_feats)], dim=1)     # [B, 2, hidden]
+        if self._project_tokens is not None:
+            tokens = self._project_tokens([(image_feats, self.img_proj), (text_feats, self.txt_proj)])   # [B, 2, hidden], no stack
+        else:
+            tokens = torch.stack([self.img_proj(image_feats), self.txt_proj(text_feats)], dim=1)     # reference README.md:186
+        head = (lambda t: self._linear(t, self.classifier)) if self._linear is not None else self.classifier
         query = self.fusion_query.expand(tokens.size(0), -1, -1)
         if return_info:
             fused, info = self.fusion_pool(query, tokens, return_info=True)
-            return self.classifier(fused.squeeze(1)), info
-        return self.classifier(self.fusion_pool(query, tokens).squeeze(1))
+            return head(fused.squeeze(1)), info
+        return head(self.fusion_pool(query, tokens).squeeze(1))
 
 
 class XrayFusionModel(nn.Module):

@@ -332,12 +332,14 @@ typedef struct aecf_fusion_grads {
     void* d_out_proj_weight;       /* [D, D] */
     void* d_out_proj_bias;         /* [D] */
     /* Folded backward, phase AECF_BWD_ALL: the small kernels that finish the parameter gradients (split-K folds, column
-     * sums, the rank-H key/query terms, conversion to dtype; csrc/grad_tail.cu) run on `side_stream` while the dX product
-     * runs on `stream`: fork_event is recorded on `stream` after the last product they need, join_event on `side_stream`
-     * after them, and `stream` waits for it before the call returns.  All three null: everything on `stream`, in order.
+     * sums, the rank-H key/query terms, conversion to dtype; csrc/grad_tail.cu) run on `side_stream` NEXT TO the products on
+     * `stream`: fork_event is recorded on `stream` after the pool backward (the column sums of d_out and the dWo fold then run
+     * next to the [dWv ; R] product), fork_event2 after that product (the rest runs next to dX), join_event on `side_stream` after the last of them, and
+     * `stream` waits for it before the call returns.  Any of the four null: everything on `stream`, in order.
      * The caller owns stream and events (cudaStream_t / cudaEvent_t handles); capture into a CUDA graph works as usual. */
     void* side_stream;
     void* fork_event;
+    void* fork_event2;
     void* join_event;
     const aecf_dp_desc* dp;        /* nullable: sum the gradients over the ranks inside the backward (see aecf_dp_desc) */
 } aecf_fusion_grads;

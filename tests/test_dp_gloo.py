@@ -138,3 +138,79 @@ def test_single_process_sync_leaves_gradients_alone():
     pool._grad_ready("out_proj.weight", g * 3)          # ignored: there is nobody to reduce with
     sync.finish()
     assert torch.equal(pool.attention.out_proj.weight.grad, g) and not sync.pending
+
+
+# ---- gradient accumulation: param.grad lives in the bucket after finish() ------------------------------
+def _backward_like_the_fused_pool(pool, sync, grads):
+    """What FusedPoolFunction.backward + autograd's AccumulateGrad do with the sync's buffers: ask for a place to write
+    each gradient, report it, then either install it as .grad or add it to .grad in place."""
+    for name in ("out_proj.bias", "out_proj.weight", "in_proj_weight", "in_proj_bias"):
+        param = sync.params[name]
+        buf = pool._grad_buffers.get(name)
+        new = grads[name].clone() if buf is None else buf.copy_(grads[name])
+        pool._grad_ready(name, new)
+        if param.grad is None:
+            param.grad = new
+        else:
+            param.grad += new
+
+
+def _accumulate_worker(rank, port, out_dir, mode):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    try:
+        t = _inputs()
+        pool = _Params(t)
+        sync = GradientSync(pool, None, average=(mode == "mean_every_microbatch")).attach()
+        g1 = {n: torch.full_like(p, 1.0 + rank) for n, p in sync.params.items()}
+        g2 = {n: torch.full_like(p, 10.0 * (1 + rank)) for n, p in sync.params.items()}
+        if mode == "no_sync_then_sync":                      # DDP's no_sync pattern: reduce once, after the last micro-batch
+            sync.enabled = False
+            _backward_like_the_fused_pool(pool, sync, g1); sync.finish()
+            sync.enabled = True
+            _backward_like_the_fused_pool(pool, sync, g2); sync.finish()
+            want = (1.0 + 2.0) + (10.0 + 20.0)               # sum over ranks of g1 + g2
+        elif mode == "mean_every_microbatch":                # every micro-batch averaged over the ranks, then accumulated
+            _backward_like_the_fused_pool(pool, sync, g1); sync.finish()
+            _backward_like_the_fused_pool(pool, sync, g2); sync.finish()
+            want = 1.5 + 15.0
+        elif mode == "zero_grad_in_place":                   # zero_grad(set_to_none=False): .grad stays in the bucket, zeroed
+            _backward_like_the_fused_pool(pool, sync, g1); sync.finish()
+            for p in sync.params.values():
+                p.grad.zero_()
+            _backward_like_the_fused_pool(pool, sync, g2); sync.finish()
+            want = 10.0 + 20.0
+        elif mode == "sum_every_microbatch":                 # only the new gradient is summed, not the summed one again
+            _backward_like_the_fused_pool(pool, sync, g1); sync.finish()
+            _backward_like_the_fused_pool(pool, sync, g2); sync.finish()
+            want = (1.0 + 2.0) + (10.0 + 20.0)
+        else:                                                # zero in place, then the no_sync pattern
+            _backward_like_the_fused_pool(pool, sync, g1); sync.finish()
+            for p in sync.params.values():
+                p.grad.zero_()
+            sync.enabled = False
+            _backward_like_the_fused_pool(pool, sync, g1); sync.finish()
+            sync.enabled = True
+            _backward_like_the_fused_pool(pool, sync, g2); sync.finish()
+            want = (1.0 + 2.0) + (10.0 + 20.0)
+        ok = all(bool((p.grad == want).all()) for p in sync.params.values())
+        with open(os.path.join(out_dir, f"rank{rank}.txt"), "w") as f:
+            f.write("ok" if ok else f"got {float(sync.params['out_proj.bias'].grad[0])} want {want}")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["no_sync_then_sync", "mean_every_microbatch", "zero_grad_in_place", "sum_every_microbatch", "zero_in_place_then_no_sync"])
+def test_gradient_accumulation_with_the_bucket_attached(tmp_path, mode):
+    mp.spawn(_accumulate_worker, args=(_free_port(), str(tmp_path), mode), nprocs=WORLD, join=True)
+    for r in range(WORLD):
+        assert open(tmp_path / f"rank{r}.txt").read() == "ok"
+
+
+def test_a_grad_tensor_of_its_own_is_refused():
+    t = _inputs()
+    pool = _Params(t)
+    GradientSync(pool, None).attach()
+    pool.attention.out_proj.weight.grad = torch.zeros_like(pool.attention.out_proj.weight)
+    with pytest.raises(RuntimeError, match="set_to_none=True"):
+        pool._grad_buffers.get("out_proj.weight")

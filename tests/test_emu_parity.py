@@ -112,6 +112,10 @@ def test_functional_fast_path():
     assert_close("sdpa bf16", got, oracle.sdpa_single_head(q.bfloat16().float(), k.bfloat16().float(), k.bfloat16().float()), 2e-2)
 
 
+def test_entropy_loss_comes_out_of_the_forward_kernel():
+    P.test_entropy_loss_comes_out_of_the_forward_kernel()
+
+
 def test_full_size_test_body_on_a_small_batch():
     """The body of the B = 65 536 GPU test (tests/test_gpu_parity.py) on 192 rows, so that the test itself is tested."""
     P.test_full_size_bf16_folded_against_oracle(P.Case("small_d512_h8_m3", B=192, M=3, D=512, H=8, dropout=0.1, pooled_grad=True,

@@ -623,6 +623,42 @@ def test_module_without_biases(dtype, fold):
     assert_close("grad query0", query0.grad.float().cpu(), grads["query"].sum(0, keepdim=True), tol)
 
 
+def test_entropy_loss_comes_out_of_the_forward_kernel():
+    """The per-sample entropy_loss term is fused into the streaming forward kernel (aecf_pool_desc::loss_out): for the
+    info['entropy'] tensor of a training forward, CurriculumMasking.entropy_loss returns the kernel's scalar; a copy of the
+    tensor, a modified tensor or another target take the stand-alone kernels -- all equal the oracle's value."""
+    case = CASES_BY_NAME["d64_h8_m3_dropout"]
+    inp = build_inputs(case)
+    for dtype, fold in ((torch.float32, False), (torch.float32, True), (torch.bfloat16, True)):
+        pool, cm = make_pool(case, inp, dtype, fold)
+        launched = []
+        plain = ops.entropy_loss_fwd
+        try:
+            ops.entropy_loss_fwd = lambda e, t: (launched.append(1), plain(e, t))[1]
+            q = inp["query0"].to(DEV, dtype)
+            aecf_b200.set_rng_state(PHILOX_SEED, case.offset)
+            _, info = pool(q.expand(case.B, -1, -1), inp["x"].to(DEV, dtype), return_info=True)
+            aecf_b200.set_rng_state(None)
+            entropy = info["entropy"]
+            fused = cm.entropy_loss(entropy)
+            assert not launched and fused.shape == () and not fused.requires_grad
+            want = oracle.entropy_loss(entropy.detach().float().cpu(), case.M, case.entropy_target)
+            assert_close("fused entropy_loss", fused.float().cpu(), want, 1e-6, atol=1e-7)
+            separate = cm.entropy_loss(entropy.clone())                    # not the forward's tensor object
+            assert launched == [1]
+            assert_close("stand-alone entropy_loss", separate.float().cpu(), want, 1e-6, atol=1e-7)
+            cm.entropy_target = 0.5                                        # another target: the kernels again
+            assert_close("other target", cm.entropy_loss(entropy).float().cpu(),
+                         oracle.entropy_loss(entropy.detach().float().cpu(), case.M, 0.5), 1e-6, atol=1e-7)
+            cm.entropy_target = case.entropy_target
+            entropy.add_(1.0)                                              # modified in place since the forward
+            assert_close("modified entropy", cm.entropy_loss(entropy).float().cpu(),
+                         oracle.entropy_loss(entropy.detach().float().cpu(), case.M, case.entropy_target), 1e-6, atol=1e-7)
+            assert len(launched) == 3
+        finally:
+            ops.entropy_loss_fwd = plain
+
+
 def test_unsupported_shapes_fail_loudly():
     pool = aecf_b200.MultimodalAttentionPool(64, num_heads=4, device=DEV)
     x = torch.randn(4, 3, 64, device=DEV)
