@@ -29,7 +29,7 @@ EXPORTS = (
     "aecf_colsum", "aecf_colsum_workspace_bytes",
     "aecf_entropy_loss_fwd", "aecf_entropy_loss_bwd", "aecf_curriculum_mask", "aecf_entropy_bwd", "aecf_sdpa_fwd",
     "aecf_fusion_fwd", "aecf_fusion_bwd", "aecf_fusion_workspace_bytes", "aecf_fusion_grad_sums_bytes",
-    "aecf_peer_flag_bytes", "aecf_peer_enable_access", "aecf_peer_allreduce",
+    "aecf_peer_flag_bytes", "aecf_peer_enable_access", "aecf_peer_allreduce", "aecf_peer_export", "aecf_peer_import",
     "aecf_timing_enable", "aecf_timing_collect", "aecf_timing_site_name", "aecf_timing_site_gemm_kernel",
     "aecf_abi_version", "aecf_strerror", "aecf_last_cuda_error", "aecf_launch_count", "aecf_build_info",
     "aecf_gemm_last_kernel",
@@ -169,6 +169,10 @@ def _declare(lib):
     lib.aecf_peer_enable_access.argtypes = [C.c_int32, C.c_int32]
     lib.aecf_peer_allreduce.restype = C.c_int
     lib.aecf_peer_allreduce.argtypes = [C.POINTER(PeerDesc), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), vp]
+    lib.aecf_peer_export.restype = C.c_int
+    lib.aecf_peer_export.argtypes = [C.c_int32, vp, vp, C.POINTER(C.c_int64)]
+    lib.aecf_peer_import.restype = C.c_int
+    lib.aecf_peer_import.argtypes = [C.c_int32, vp, C.POINTER(C.c_void_p)]
     lib.aecf_timing_enable.restype = C.c_int
     lib.aecf_timing_enable.argtypes = [C.c_int32]
     lib.aecf_timing_collect.restype = C.c_int

@@ -53,7 +53,7 @@ fold_prepare_kernel(const float* __restrict__ q_proj, const T* __restrict__ in_p
 // xor-shuffle order; 16 blocks repeat the same 64 dots of a 512-vector -- cheaper than a launch boundary); the block of
 // strip 0 also writes them out, the backward needs q_proj.
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 1)
 fold_prepare_query_kernel(const T* __restrict__ query, const T* __restrict__ in_proj_weight, const T* __restrict__ in_proj_bias,
                           int D, int H, int HSP, float scale, int fold_blocks, float* __restrict__ q_proj,
                           T* __restrict__ folded_w) {

@@ -178,20 +178,21 @@ static int folded_backward(const aecf_pool_desc* desc, const Geometry& g, const 
                                           gr->d_entropy, gr->d_kv, w.pool, w.pool_bytes, s, &a.pool_blocks));
         a.pool_part = reinterpret_cast<const float*>(w.pool);
     }
-    if (want_tail) {
-        // first half of the tail (column sums of d_out, dWo fold: 86 MB of reads at config 2) next to the [dWv ; R] product.
-        // Not earlier: next to the pool backward it would only take HBM bandwidth from a kernel that is bound by it
-        // (r2 run 5: pool_bwd 88 -> 131 us), and the d_ctx product's CTAs leave no shared memory for a second CTA.
-        if (forked) {
-            AECF_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(gr->fork_event), s));
-            AECF_CUDA_OK(cudaStreamWaitEvent(side, static_cast<cudaEvent_t>(gr->fork_event), 0));
-        }
-        AECF_TRY(launch_grad_gather(a, GATHER_EARLY, side));
-    }
+    // Each half of the tail is enqueued AFTER the product it runs next to: the product's persistent CTAs (one per SM, all
+    // but 2 KB of its shared memory) are placed first and the tail's blocks fill in beside them -- the other way round a
+    // product CTA finds its SM taken and the whole product ends late by as long as it waited.
+    if (forked) AECF_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(gr->fork_event), s));          // after the pool backward
     if (want_in) {                                           // [dWv ; R] = [dV | ds]^T X, left as split-K partials
         ScopedSite site(AECF_SITE_D_KV_WEIGHT);
         const aecf_gemm_desc d = gemm_desc(dev, dt, dt, AECF_F32, dt, AECF_MN_MAJOR, AECF_MN_MAJOR, KF, D, g.rows, KF, D, D);
         AECF_TRY(gemm_partials(&d, gr->d_kv, t->key, w.gemm_g, w.gemm_g_bytes, s, &a.g));
+    }
+    if (want_tail) {
+        // first half of the tail (column sums of d_out, dWo fold: 86 MB of reads at config 2) next to the [dWv ; R] product.
+        // Not earlier: next to the pool backward it would only take HBM bandwidth from a kernel that is bound by it
+        // (r2 run 5: pool_bwd 88 -> 131 us), and the d_ctx product's CTAs leave no shared memory for a second CTA.
+        if (forked) AECF_CUDA_OK(cudaStreamWaitEvent(side, static_cast<cudaEvent_t>(gr->fork_event), 0));
+        AECF_TRY(launch_grad_gather(a, GATHER_EARLY, side));
     }
     auto late = [&]() -> int {
         if (!want_tail) return AECF_OK;
@@ -203,16 +204,16 @@ static int folded_backward(const aecf_pool_desc* desc, const Geometry& g, const 
         }
         return launch_grad_finish(a, final_sums, side);
     };
-    if (forked) {
-        AECF_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(gr->fork_event2), s));
-        AECF_CUDA_OK(cudaStreamWaitEvent(side, static_cast<cudaEvent_t>(gr->fork_event2), 0));
-        AECF_TRY(late());
-        AECF_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(gr->join_event), side));
-    }
+    if (forked) AECF_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(gr->fork_event2), s));         // after the [dWv ; R] product
     if (gr->d_key) {                                         // dX = [dV | ds] . [Wv ; Qk]
         ScopedSite site(AECF_SITE_D_X);
         const aecf_gemm_desc d = gemm_desc(dev, dt, dt, dt, dt, AECF_K_MAJOR, AECF_MN_MAJOR, g.rows, D, KF, KF, D, D);
         AECF_TRY(aecf_gemm(&d, gr->d_kv, t->folded_w, nullptr, gr->d_key, w.gemm, w.gemm_bytes, s));
+    }
+    if (forked) {
+        AECF_CUDA_OK(cudaStreamWaitEvent(side, static_cast<cudaEvent_t>(gr->fork_event2), 0));
+        AECF_TRY(late());
+        AECF_CUDA_OK(cudaEventRecord(static_cast<cudaEvent_t>(gr->join_event), side));
     }
     if (forked) AECF_CUDA_OK(cudaStreamWaitEvent(s, static_cast<cudaEvent_t>(gr->join_event), 0));
     else AECF_TRY(late());

@@ -28,6 +28,23 @@
 namespace aecf {
 
 constexpr int TAIL_THREADS = 256;
+template <int N> struct IntTag { static constexpr int value = N; };
+
+// ptxas sinks independent loads next to their uses to save registers (r2 run 6: a batch of 32 loads compiled to four in
+// flight); these kernels want the opposite -- every load of a batch issued before the first use -- so the loads are
+// volatile and a compiler-level memory barrier separates the issue loop from the consume loop.
+#ifdef AECF_CUDA_EMU
+__device__ __forceinline__ uint4 ldg_batch(const void* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void issue_barrier() {}
+#else
+__device__ __forceinline__ uint4 ldg_batch(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void issue_barrier() { asm volatile("" ::: "memory"); }
+#endif
 
 // ---- grad_gather / grad_fold ------------------------------------------------------------------------------------------
 struct GatherParams {
@@ -40,7 +57,7 @@ struct GatherParams {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(TAIL_THREADS)
+__global__ void __launch_bounds__(TAIL_THREADS, 1)
 grad_gather_kernel(const GatherParams p) {
     constexpr int V = Vec<T>::N;
     const int t = threadIdx.x;
@@ -65,26 +82,28 @@ grad_gather_kernel(const GatherParams p) {
             for (int v = 0; v < V; ++v) acc[v] = 0.f;
             if (active) {
                 const T* col = x + static_cast<long long>(cb + cc) * V;
-                constexpr int U = 8;
+                // 16 rows in flight per thread: next to a tensor-core product a trip to memory takes several microseconds,
+                // and what this kernel costs is the number of trips (r2 run 6: 26 us alone, 4x that next to a product at U = 8)
                 long long r = r0 + lane_r;
-                for (; r + static_cast<long long>(U - 1) * rl < r1; r += static_cast<long long>(U) * rl) {
-                    uint4 raw[U];
+                auto batch = [&](auto tag) {                    // tag.value rows in flight at once
+                    constexpr int U = decltype(tag)::value;
+                    for (; r + static_cast<long long>(U - 1) * rl < r1; r += static_cast<long long>(U) * rl) {
+                        uint4 raw[U];
 #pragma unroll
-                    for (int u = 0; u < U; ++u) raw[u] = ldg_stream(col + (r + static_cast<long long>(u) * rl) * p.ld);
+                        for (int u = 0; u < U; ++u) raw[u] = ldg_batch(col + (r + static_cast<long long>(u) * rl) * p.ld);
+                        issue_barrier();
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        float f[V];
-                        Vec<T>::unpack(raw[u], f);
+                        for (int u = 0; u < U; ++u) {
+                            float f[V];
+                            Vec<T>::unpack(raw[u], f);
 #pragma unroll
-                        for (int v = 0; v < V; ++v) acc[v] += f[v];
+                            for (int v = 0; v < V; ++v) acc[v] += f[v];
+                        }
                     }
-                }
-                for (; r < r1; r += rl) {
-                    float f[V];
-                    Vec<T>::unpack(ldg_stream(col + r * p.ld), f);
-#pragma unroll
-                    for (int v = 0; v < V; ++v) acc[v] += f[v];
-                }
+                };
+                batch(IntTag<16>{});
+                batch(IntTag<4>{});
+                batch(IntTag<1>{});
             }
             for (int off = rl >> 1; off > 0; off >>= 1) {       // the rl row lanes are neighbouring lanes of one warp
 #pragma unroll
@@ -106,12 +125,28 @@ grad_gather_kernel(const GatherParams p) {
         for (long long i = gt; i < n / 4; i += nthreads) {
             float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
             int z = 0;
-            for (; z + 4 <= splits; z += 4) {
-                float4 v[4];
+            for (; z + 8 <= splits; z += 8) {
+                uint4 v[8];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(part + (z + u) * stride + 4 * i);
+                for (int u = 0; u < 8; ++u) v[u] = ldg_batch(part + (z + u) * stride + 4 * i);
+                issue_barrier();
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+                for (int u = 0; u < 8; ++u) {
+                    s.x += __uint_as_float(v[u].x); s.y += __uint_as_float(v[u].y);
+                    s.z += __uint_as_float(v[u].z); s.w += __uint_as_float(v[u].w);
+                }
+            }
+            if (z < splits) {                                   // the rest, also in one trip
+                uint4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = (z + u < splits) ? ldg_batch(part + (z + u) * stride + 4 * i) : make_uint4(0, 0, 0, 0);
+                issue_barrier();
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    s.x += __uint_as_float(v[u].x); s.y += __uint_as_float(v[u].y);
+                    s.z += __uint_as_float(v[u].z); s.w += __uint_as_float(v[u].w);
+                }
+                z = splits;
             }
             for (; z < splits; ++z) {
                 const float4 v = *reinterpret_cast<const float4*>(part + z * stride + 4 * i);
@@ -134,10 +169,10 @@ struct FoldParams {
     int D;
 };
 
-__global__ void __launch_bounds__(TAIL_THREADS)
+__global__ void __launch_bounds__(512, 1)
 grad_fold_kernel(const FoldParams p) {
     const int lane = threadIdx.x & 31;
-    const int col = blockIdx.x * (TAIL_THREADS / 32) + (threadIdx.x >> 5);
+    const int col = blockIdx.x * 16 + (threadIdx.x >> 5);
     pdl_wait();
     if (col >= 4 * p.D) return;
     const bool is_colsum = col < p.D;
@@ -198,7 +233,7 @@ template <> __device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bf
 //   dWv[i, :] = G[i, :]     dWk[i, :] = scale q[i] R[h, :]     d_qp[i] = scale Wk[i, :] . R[h, :]     dWo[i, :] = O[i, :]
 //   dWq[i, :] = d_qp[i] q0[:]     d_in_b = [ d_qp | d_bias_k | d_bias_v ]     d_out_b = colsum(d_out)
 template <typename T>
-__global__ void __launch_bounds__(TAIL_THREADS)
+__global__ void __launch_bounds__(TAIL_THREADS, 1)
 grad_finish_kernel(const FinishParams p) {
     __shared__ float qps[8];                                    // d_qp of the block's 8 rows
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -289,7 +324,7 @@ grad_finish_kernel(const FinishParams p) {
 
 // d_query[c] = sum over the blocks of grad_finish of their partials: one warp per column, every load in flight at once.
 template <typename T>
-__global__ void __launch_bounds__(TAIL_THREADS)
+__global__ void __launch_bounds__(TAIL_THREADS, 1)
 grad_dquery_fold_kernel(const float* __restrict__ part, int rows, int D, T* __restrict__ d_query) {
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * (TAIL_THREADS / 32) + (threadIdx.x >> 5);
@@ -313,7 +348,7 @@ grad_dquery_fold_kernel(const float* __restrict__ part, int rows, int D, T* __re
 static size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
 size_t grad_tail_scratch_bytes(int D, int sms) {
-    return align256(static_cast<size_t>(2 * sms) * D * sizeof(float))       // per-block column sums of d_out
+    return align256(static_cast<size_t>(sms) * D * sizeof(float))           // per-block column sums of d_out
          + align256(static_cast<size_t>((D + 7) / 8) * D * sizeof(float));  // per-block partials of d_query
 }
 
@@ -323,7 +358,9 @@ int launch_grad_gather(const GradTailArgs& a, int which, cudaStream_t s) {
     const int V = a.dtype == AECF_BF16 ? 8 : 4;
     if (a.D % V != 0) return AECF_ERR_UNSUPPORTED;
     const TailLayout lay = tail_layout(a.D, a.HSP);
-    const int blocks = 2 * a.sms;
+    // at most one block per SM: two of them take the 2 KB of shared memory a product's CTA leaves, and a persistent CTA
+    // that cannot start on its SM delays the whole product by as long as it waits (r2 run 6: dX 116 -> 134 us)
+    const int blocks = a.sms;
     GatherParams p{};
     p.sums = a.sums; p.lay = lay; p.D = a.D; p.HSP = a.HSP;
     p.colsum_part = static_cast<float*>(a.scratch);
@@ -345,7 +382,7 @@ int launch_grad_gather(const GradTailArgs& a, int which, cudaStream_t s) {
         f.colsum_part = a.d_out ? p.colsum_part : nullptr; f.colsum_rows = blocks;
         f.pool_part = a.pool_part; f.pool_rows = a.pool_blocks;
         f.sums = a.sums; f.lay = lay; f.D = a.D;
-        AECF_CUDA_OK(launch_pdl(grad_fold_kernel, dim3((4 * a.D + 7) / 8), dim3(TAIL_THREADS), 0, s, f));
+        AECF_CUDA_OK(launch_pdl(grad_fold_kernel, dim3((4 * a.D + 15) / 16), dim3(512), 0, s, f));
         count_launch();
     }
     return AECF_OK;
@@ -359,7 +396,7 @@ int launch_grad_finish(const GradTailArgs& a, const float* sums, cudaStream_t s)
     p.d_in_w = a.d_in_w; p.d_in_b = a.d_in_b; p.d_out_w = a.d_out_w; p.d_out_b = a.d_out_b; p.d_query = a.d_query;
     p.D = a.D; p.H = a.H; p.HSP = a.HSP;
     p.scale = static_cast<float>(sqrt(1.0 / static_cast<double>(a.D / a.H)));
-    p.d_qp = reinterpret_cast<float*>(static_cast<char*>(a.scratch) + align256(static_cast<size_t>(2 * a.sms) * a.D * sizeof(float)));
+    p.d_qp = reinterpret_cast<float*>(static_cast<char*>(a.scratch) + align256(static_cast<size_t>(a.sms) * a.D * sizeof(float)));
     const dim3 grid(static_cast<unsigned>((a.D + 7) / 8)), block(TAIL_THREADS);
     TimedLaunch timed(s, AECF_SITE_GRAD_FINISH);
     if (a.dtype == AECF_BF16) AECF_CUDA_OK(launch_pdl(grad_finish_kernel<__nv_bfloat16>, grid, block, 0, s, p));

@@ -18,6 +18,10 @@
 // lives in device memory and is advanced by the kernel, so the call can be captured into a CUDA graph.  Flags only
 // ever grow and are compared with >=, so a rank that is already in the next call cannot confuse a slower one.
 // Every spin has a clock-based bound and traps instead of hanging the GPU.
+#include <cuda.h>
+
+#include <cstring>
+
 #include "common.cuh"
 #include "grad_tail.cuh"
 
@@ -180,6 +184,40 @@ int aecf_peer_enable_access(int32_t device, int32_t peer_device) {
     const cudaError_t err = cudaDeviceEnablePeerAccess(peer_device, 0);
     if (err == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return AECF_OK; }
     AECF_CUDA_OK(err);
+    return AECF_OK;
+}
+
+// CUDA IPC, mapped into the context of THIS rank's device.  (torch's tensor sharing re-opens a handle under the EXPORTING
+// device's ordinal, which is right for torch ops on that tensor but leaves a kernel running on this rank's GPU without a
+// mapping: r2 run 8/9, illegal address in the first peer access.)  The handle names the whole allocation a pointer lies
+// in, so the offset inside it travels with it.
+int aecf_peer_export(int32_t device, const void* ptr, void* handle64, int64_t* offset) {
+    if (!ptr || !handle64 || !offset) return AECF_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the ABI carries IPC handles as 64 bytes");
+    int rc = use_device(device);
+    if (rc != AECF_OK) return rc;
+    using RangeFn = CUresult (*)(CUdeviceptr*, size_t*, CUdeviceptr);
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    AECF_CUDA_OK(cudaGetDriverEntryPoint("cuMemGetAddressRange", &sym, cudaEnableDefault, &q));
+    if (q != cudaDriverEntryPointSuccess || sym == nullptr) return AECF_ERR_UNSUPPORTED;
+    CUdeviceptr base = 0;
+    size_t size = 0;
+    if (reinterpret_cast<RangeFn>(sym)(&base, &size, reinterpret_cast<CUdeviceptr>(ptr)) != CUDA_SUCCESS) return AECF_ERR_INVALID;
+    cudaIpcMemHandle_t h;
+    AECF_CUDA_OK(cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(base)));
+    std::memcpy(handle64, &h, sizeof(h));
+    *offset = static_cast<int64_t>(reinterpret_cast<CUdeviceptr>(ptr) - base);
+    return AECF_OK;
+}
+
+int aecf_peer_import(int32_t device, const void* handle64, void** base_out) {
+    if (!handle64 || !base_out) return AECF_ERR_INVALID;
+    int rc = use_device(device);
+    if (rc != AECF_OK) return rc;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle64, sizeof(h));
+    AECF_CUDA_OK(cudaIpcOpenMemHandle(base_out, h, cudaIpcMemLazyEnablePeerAccess));
     return AECF_OK;
 }
 

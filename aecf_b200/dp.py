@@ -38,28 +38,42 @@ def shard_rows(global_batch: int, rank: int, world_size: int) -> Tuple[int, int]
     return start, base + (1 if rank < extra else 0)
 
 
-def _map_peer_tensors(tensors: List[torch.Tensor], group=None) -> List[List[torch.Tensor]]:
-    """Collective: every rank exports ``tensors`` (CUDA, kept alive by the caller) through CUDA IPC -- torch's tensor
-    sharing, handles travel through ``all_gather_object`` -- and maps every other rank's; returns, per tensor, the list of
-    its W instances as seen from THIS process (own rank: the tensor itself).  Peer access to the other devices is enabled."""
-    from torch.multiprocessing.reductions import reduce_tensor
+_imported: Dict[bytes, int] = {}          # IPC handle bytes -> base address in this process (a handle is opened once)
+
+
+def _map_peer_tensors(tensors: List[torch.Tensor], group=None) -> List[List[int]]:
+    """Collective: every rank exports ``tensors`` (CUDA, kept alive by the caller) through CUDA IPC -- 64-byte handle of the
+    allocation each one lies in plus its offset, gathered with ``all_gather_object`` -- and opens every other rank's in the
+    context of ITS OWN device (``aecf_peer_import``), so that kernels of this rank can address them.  Returns, per tensor,
+    the W device ADDRESSES of its instances as seen from this process (own rank: ``tensor.data_ptr()``)."""
+    import ctypes as C
 
     from . import _lib
+    lib = _lib.load()
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     dev = tensors[0].device
     torch.cuda.synchronize(dev)
-    payload = ([reduce_tensor(t) for t in tensors], dev.index or 0)
+    exported = []
+    for t in tensors:
+        handle, offset = (C.c_char * 64)(), C.c_int64(0)
+        _lib.check(lib.aecf_peer_export(dev.index or 0, t.data_ptr(), handle, C.byref(offset)), "aecf_peer_export")
+        exported.append((bytes(handle), int(offset.value)))
     gathered = [None] * world
-    dist.all_gather_object(gathered, payload, group=group)
-    out: List[List[torch.Tensor]] = [[] for _ in tensors]
+    dist.all_gather_object(gathered, (exported, dev.index or 0), group=group)
+    out: List[List[int]] = [[] for _ in tensors]
     for r, (handles, peer_dev) in enumerate(gathered):
         if r == rank:
             for i, t in enumerate(tensors):
-                out[i].append(t)
+                out[i].append(t.data_ptr())
             continue
-        _lib.check(_lib.load().aecf_peer_enable_access(dev.index or 0, peer_dev), f"peer access {dev.index} -> {peer_dev}")
-        for i, (fn, args) in enumerate(handles):
-            out[i].append(fn(*args))                     # rebuild_cuda_tensor: rank r's memory mapped into this process
+        _lib.check(lib.aecf_peer_enable_access(dev.index or 0, peer_dev), f"peer access {dev.index} -> {peer_dev}")
+        for i, (handle, offset) in enumerate(handles):
+            base = _imported.get(handle)
+            if base is None:
+                ptr = C.c_void_p()
+                _lib.check(lib.aecf_peer_import(dev.index or 0, handle, C.byref(ptr)), f"aecf_peer_import (rank {r})")
+                base = _imported[handle] = int(ptr.value)
+            out[i].append(base + offset)
     dist.barrier(group=group)                            # everybody has mapped everything before anybody signals
     return out
 
@@ -97,15 +111,16 @@ class FusedGradSum:
                     buffers[r] = torch.zeros(2 * self.floats, dtype=torch.float32, device=dev)
                     flags[r] = ops.peer_flag_block(dev)
             self.buffer, self.flags = buffers[self.rank], flags[self.rank]
+            self._keep = (buffers, flags)
+            buffer_ptrs, flag_ptrs = [b.data_ptr() for b in buffers], [f.data_ptr() for f in flags]
         else:
             self.buffer = torch.zeros(2 * self.floats, dtype=torch.float32, device=dev)      # [raw sums | reduced sums]
             self.flags = ops.peer_flag_block(dev)
-            buffers, flags = _map_peer_tensors([self.buffer, self.flags], group)
-        self._keep = (buffers, flags)
+            buffer_ptrs, flag_ptrs = _map_peer_tensors([self.buffer, self.flags], group)
         n = self.floats * 4
-        self._sums = (C.c_void_p * self.world)(*[b.data_ptr() for b in buffers])
-        self._reduced = (C.c_void_p * self.world)(*[b.data_ptr() + n for b in buffers])
-        self._flags = (C.c_void_p * self.world)(*[f.data_ptr() for f in flags])
+        self._sums = (C.c_void_p * self.world)(*buffer_ptrs)
+        self._reduced = (C.c_void_p * self.world)(*[b + n for b in buffer_ptrs])
+        self._flags = (C.c_void_p * self.world)(*flag_ptrs)
         self._desc = _lib.DpDesc(world=self.world, rank=self.rank, average=int(average), reserved0=0,
                                  sums=self._sums, reduced=self._reduced, flags=self._flags)
         self._ptr = C.pointer(self._desc)
@@ -138,7 +153,7 @@ class PeerAllReduce:
         if self.world > 8:
             raise ValueError("PeerAllReduce covers the (at most 8) GPUs of one NVLink node")
         self.flags = ops.peer_flag_block(bucket.device)
-        self.buckets, self.flag_blocks = [bucket], [self.flags]
+        self.buckets, self.flag_blocks = [bucket.data_ptr()], [self.flags.data_ptr()]     # device addresses, rank order
         if self.world > 1:
             self.buckets, self.flag_blocks = _map_peer_tensors([bucket, self.flags], group)
         self._ops = ops
@@ -148,7 +163,7 @@ class PeerAllReduce:
         if self.world == 1:
             return
         with torch.cuda.device(self.bucket.device):
-            self._ops.peer_allreduce(self.buckets, self.flag_blocks, self.rank, average=self.average)
+            self._ops.peer_allreduce(self.buckets, self.flag_blocks, self.rank, average=self.average, mine=self.bucket)
 
 
 class _BucketViews:
@@ -257,6 +272,16 @@ class GradientSync:
         if self.query is not None:
             self.query.register_hook(self._query_hook)
         return self
+
+    def select(self, mode: str) -> None:
+        """Switch what the next backward does with the gradients (measurements): 'fused' (the in-backward sum, where it was
+        set up), 'bucket' (one all-reduce of the bucket in finish()), 'local' (no cross-rank sum at all)."""
+        if mode not in ("fused", "bucket", "local"):
+            raise ValueError(mode)
+        if mode == "fused" and self.fused is None:
+            raise ValueError("the fused gradient sum was not set up for this pool")
+        self.pool._dp = self.fused if mode == "fused" else None
+        self.enabled = mode != "local"
 
     def _fused_ran(self) -> bool:
         return self.fused is not None and self.fused.ran

@@ -264,17 +264,20 @@ def peer_flag_block(dev: torch.device) -> torch.Tensor:
 
 
 def peer_allreduce(buckets, flags, rank: int, *, average: bool = False, stream: Optional[int] = None,
-                   grid_limit: int = 0) -> None:
+                   grid_limit: int = 0, mine: Optional[torch.Tensor] = None) -> None:
     """In-place sum (mean) of ``buckets[rank]`` with every other entry of ``buckets`` -- this process's mappings of
     all ranks' buckets -- over peer memory (``aecf_peer_allreduce``).  Every rank makes the same call with its own
-    ``rank``; the call returns at once and completes on the stream when the whole bucket is reduced."""
-    mine = buckets[rank]
-    dev = require_cuda(mine, flags[rank])
+    ``rank``; the call returns at once and completes on the stream when the whole bucket is reduced.  ``buckets`` /
+    ``flags`` hold tensors or plain device addresses (IPC mappings); ``mine`` is this rank's bucket tensor when they are
+    addresses."""
+    mine = buckets[rank] if mine is None else mine
+    dev = require_cuda(mine)
     world = len(buckets)
+    addr = lambda x: x if isinstance(x, int) else x.data_ptr()
     d = _lib.PeerDesc(device=dev.index or 0, dtype=dtype_code(mine.dtype), world=world, rank=rank,
                       count=mine.numel(), average=int(average), grid_limit=int(grid_limit))
-    data = (C.c_void_p * world)(*[b.data_ptr() for b in buckets])
-    flag_ptrs = (C.c_void_p * world)(*[f.data_ptr() for f in flags])
+    data = (C.c_void_p * world)(*[addr(b) for b in buckets])
+    flag_ptrs = (C.c_void_p * world)(*[addr(f) for f in flags])
     rc = _lib.load().aecf_peer_allreduce(C.byref(d), data, flag_ptrs, _stream(dev) if stream is None else stream)
     _lib.check(rc, f"aecf_peer_allreduce world={world} rank={rank} count={mine.numel()}")
 

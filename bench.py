@@ -349,14 +349,18 @@ def kernel_averages(sites, steps):
     return {name: {"ms": total / count, "calls_per_step": count / steps} for name, (total, count) in sites.items()}
 
 
-def finish_process(world):
-    """Leave without tearing NCCL down.  With the step captured into CUDA graphs that hold NCCL kernels,
-    destroy_process_group() blocked for minutes on the 8-GPU box (r1 run 16); every rank has passed the last
-    barrier and rank 0 has printed its line, so exit directly."""
+def finish_process(world, nccl_in_graphs=True):
+    """With the step captured into CUDA graphs that hold NCCL kernels, destroy_process_group() blocked for minutes on the
+    8-GPU box (r1 run 16: the communicator waits for work it believes outstanding); in that case every rank has passed
+    the last barrier and rank 0 has printed its line, so leave directly.  With the gradient sum inside the backward
+    (the default) no NCCL kernel is ever captured and the group is torn down normally."""
     sys.stdout.flush()
     sys.stderr.flush()
     if world > 1:
-        os._exit(0)
+        if nccl_in_graphs:
+            os._exit(0)
+        import torch.distributed as dist
+        dist.destroy_process_group()
 
 
 def run_b200(args):
@@ -459,6 +463,10 @@ def run_b200(args):
     launches0 = _lib.launch_count()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
+        if world > 1:
+            # device-side rendezvous right before the clock starts: the host barrier above lets the ranks go tens of
+            # microseconds apart, which a 12 ms timed region would count as step time (scaling item iii)
+            dist.all_reduce(torch.zeros(1, device=dev))
         start.record()
         t_issue = time.perf_counter()
         for _ in range(args.steps):
@@ -503,29 +511,27 @@ def run_b200(args):
     if world > 1:
         per_rank = gather_ms(ms)
         ms = max(per_rank)
-        dp_info = {"all_reduce": "overlapped on a side stream (two groups)" if sync.overlap else "one call after the backward",
-                   "per_rank_ms": per_rank, "in_graph": use_graph}
+        dp_info = {"gradient_sum": ("inside the backward: fp32 raw sums over NVLink peer memory, one kernel per rank on the side stream "
+                                    "(csrc/grad_tail.cu, peer_allreduce.cu)") if sync.fused is not None else
+                                   ("bucket, overlapped NCCL all-reduce in two groups" if sync.overlap else "bucket, one NCCL all-reduce after the backward"),
+                   "collective": sync.collective, "per_rank_ms": per_rank, "rank_spread": (max(per_rank) - min(per_rank)) / max(per_rank),
+                   "in_graph": use_graph}
         if args.dp_study:
-            def variant(configure, restore):
-                configure(); clear()
+            def variant(mode):
+                sync.select(mode); clear()
                 if use_graph:
                     g = aecf_b200.graphs.GraphedStep(lambda: step(x), reset=clear, warmup=1, device=dev)
                     t_ms = time_region(g)
                     del g
                 else:
                     t_ms = time_region(lambda: (step(x), clear()))
-                restore(); clear()
+                clear()
                 return gather_ms(t_ms)
 
-            was = sync.overlap
-            other = variant(lambda: setattr(sync, "overlap", not was), lambda: setattr(sync, "overlap", was))
-            dp_info["other_mode"] = {"all_reduce": "one call after the backward" if was else "overlapped on a side stream",
-                                     "per_rank_ms": other, "ms_per_step": max(other),
-                                     "value": total_rows / (max(other) * 1e-3)}
-            # no collective at all: what rank-to-rank variance alone costs
-            alone = variant(lambda: setattr(sync, "enabled", False), lambda: setattr(sync, "enabled", True))
-            dp_info["no_all_reduce"] = {"per_rank_ms": alone, "ms_per_step": max(alone),
-                                        "value": total_rows / (max(alone) * 1e-3)}
+            for mode in ("bucket", "local"):               # one NCCL all-reduce after the backward / no cross-rank sum at all
+                t = variant(mode)
+                dp_info[mode] = {"per_rank_ms": t, "ms_per_step": max(t), "value": total_rows / (max(t) * 1e-3)}
+            sync.select("fused" if sync.fused is not None else "bucket")
     value = total_rows / (ms * 1e-3)
 
     # ---- end to end: batch starts in pinned host memory every step -----------------------------
@@ -593,9 +599,10 @@ def run_b200(args):
                "h2d_bytes_per_step": total_rows * M * D * es, "d2h_bytes_per_step": 4 * world,
                "note": "host batch -> double-buffered H2D on a copy stream -> step -> loss scalar D2H"}
 
+    nccl_captured = use_graph and world > 1 and (sync.fused is None or args.dp_study)
     if rank != 0:
         barrier()                                        # rank 0 is past its last collective too
-        finish_process(world)
+        finish_process(world, nccl_captured)
         return
 
     # ---- roofline of the fused pool kernels and tensor-pipe use of the GEMMs ----------------------
@@ -670,7 +677,7 @@ def run_b200(args):
                                           + f" ({cpu_model()})", "ms_per_step": cpu_ms}
     print(json.dumps(line))
     barrier()
-    finish_process(world)
+    finish_process(world, nccl_captured)
 
 
 def main():

@@ -377,6 +377,12 @@ typedef struct aecf_peer_desc {
 AECF_API size_t aecf_peer_flag_bytes(void);
 AECF_API int    aecf_peer_enable_access(int32_t device, int32_t peer_device);
 AECF_API int    aecf_peer_allreduce(const aecf_peer_desc* desc, void* const* peer_data, void* const* peer_flags, void* stream);
+/* CUDA IPC for those buffers.  export: the 64-byte IPC handle of the allocation `ptr` lies in and ptr's offset inside it
+ * (the bytes travel to the other ranks by any means).  import: opens a handle in the context of `device` -- THIS rank's GPU,
+ * so that its kernels can address the memory -- and returns the allocation's base; the buffer is at base + offset.  A
+ * handle must be imported once per process (keep a cache keyed by its bytes); mappings live until the process exits. */
+AECF_API int    aecf_peer_export(int32_t device, const void* ptr, void* handle64, int64_t* offset);
+AECF_API int    aecf_peer_import(int32_t device, const void* handle64, void** base_out);
 
 /* ---- per-kernel timing (CUDA events recorded next to each launch, on the launching stream) ------------- */
 typedef enum aecf_site {

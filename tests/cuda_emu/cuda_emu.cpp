@@ -245,6 +245,8 @@ cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.
 size_t aecf_peer_flag_bytes(void) { return 256; }
 int aecf_peer_enable_access(int32_t, int32_t) { return AECF_ERR_UNSUPPORTED; }
 int aecf_peer_allreduce(const aecf_peer_desc*, void* const*, void* const*, void*) { return AECF_ERR_UNSUPPORTED; }
+int aecf_peer_export(int32_t, const void*, void*, int64_t*) { return AECF_ERR_UNSUPPORTED; }
+int aecf_peer_import(int32_t, const void*, void**) { return AECF_ERR_UNSUPPORTED; }
 }
 namespace aecf {
 int launch_peer_sum(int, const aecf_dp_desc*, long long, cudaStream_t) { return AECF_ERR_UNSUPPORTED; }   // peer_allreduce.cu
