@@ -5,10 +5,11 @@
     python examples/train_vlm.py --steps 30
     python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 examples/train_vlm.py --steps 30
 
-The fusion parameters go through aecf_b200.dp.GradientSync (written in place into one bucket by the fused backward,
-one all-reduce per step);
-the encoders and the head are ordinary torch modules whose gradients are all-reduced in one flat call.
-Prints one JSON line with samples/s (synthetic features, random-init weights).
+The fusion parameters go through aecf_b200.dp.GradientSync (summed over the ranks inside the pool's backward); the two
+encoder projections and the classifier are the model's nn.Linear PARAMETERS driven by the library's GEMMs
+(aecf_b200.project_tokens / linear: the encoders write straight into the [B, 2, 512] token buffer, no torch.stack, no
+cuBLAS), and their gradients are all-reduced in one flat NCCL call.  Prints one JSON line with samples/s (synthetic
+features, random-init weights).  --launch-list prints the kernels of one step by name (torch profiler) to show that.
 """
 from __future__ import annotations
 
@@ -34,6 +35,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16384, help="rows per GPU")
     ap.add_argument("--heads", type=int, default=1, help="the README model uses the default single head")
     ap.add_argument("--dtype", choices=["bf16", "fp32"], default="bf16")
+    ap.add_argument("--launch-list", action="store_true", help="rank 0: kernel names of one step (torch profiler)")
     args = ap.parse_args()
 
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
@@ -90,7 +92,21 @@ def main():
     ms = torch.tensor([t0.elapsed_time(t1) / args.steps], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    kernels = None
+    if args.launch_list and rank == 0 and world == 1:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step()
+            torch.cuda.synchronize()
+        names = {}
+        for e in prof.events():
+            if e.device_type is not None and "cuda" in str(e.device_type).lower():
+                names[e.name] = names.get(e.name, 0) + 1
+        kernels = {"kernels_of_one_step": names,
+                   "cublas_or_cutlass_kernels": sorted(n for n in names if any(t in n.lower() for t in ("cublas", "cutlass", "gemm_", "sm90", "sm100", "xmma", "nvjet")) and "aecf" not in n and "tc::" not in n)}
     if rank == 0:
+        if kernels is not None:
+            print(json.dumps(kernels))
         print(json.dumps({"workload": "VisionLanguageModel training step (README.md:162-208 of the reference)",
                           "value": args.batch * world / (float(ms) * 1e-3), "unit": "samples/s", "n_gpus": world,
                           "ms_per_step": float(ms), "batch_per_gpu": args.batch, "dtype": args.dtype,
