@@ -27,7 +27,7 @@ EXPORTS = (
     "aecf_fold_finish",
     "aecf_gemm", "aecf_gemm_aux", "aecf_gemm_workspace_bytes",
     "aecf_colsum", "aecf_colsum_workspace_bytes",
-    "aecf_entropy_loss_fwd", "aecf_entropy_loss_bwd", "aecf_curriculum_mask", "aecf_entropy_bwd", "aecf_sdpa_fwd",
+    "aecf_entropy_loss_fwd", "aecf_entropy_loss_bwd", "aecf_curriculum_mask", "aecf_curriculum_mask_bwd", "aecf_entropy_bwd", "aecf_sdpa_fwd", "aecf_sdpa_bwd",
     "aecf_fusion_fwd", "aecf_fusion_bwd", "aecf_fusion_workspace_bytes", "aecf_fusion_grad_sums_bytes",
     "aecf_peer_flag_bytes", "aecf_peer_enable_access", "aecf_peer_allreduce", "aecf_peer_export", "aecf_peer_import",
     "aecf_timing_enable", "aecf_timing_collect", "aecf_timing_site_name", "aecf_timing_site_gemm_kernel",
@@ -50,6 +50,7 @@ class PoolDesc(C.Structure):
         ("rng_state", C.c_void_p),
         ("q_stride_b", C.c_int64), ("q_stride_s", C.c_int64), ("bias_stride_s", C.c_int64),
         ("loss_out", C.c_void_p), ("loss_workspace", C.c_void_p), ("loss_target", C.c_float), ("reserved0", C.c_int32),
+        ("row_index", C.c_void_p), ("src_rows", C.c_int64),
     ]
 
 
@@ -152,10 +153,16 @@ def _declare(lib):
     lib.aecf_curriculum_mask.restype = C.c_int
     lib.aecf_curriculum_mask.argtypes = [C.c_int32, f32p, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_int32,
                                          C.c_uint64, C.c_uint64, C.c_uint64, f32p, f32p, f32p, vp]
+    lib.aecf_curriculum_mask_bwd.restype = C.c_int
+    lib.aecf_curriculum_mask_bwd.argtypes = [C.c_int32, f32p, C.c_int64, C.c_int32, C.c_float, C.c_int32, C.c_uint64, C.c_uint64,
+                                             C.c_uint64, f32p, f32p, vp]
     lib.aecf_entropy_bwd.restype = C.c_int
     lib.aecf_entropy_bwd.argtypes = [C.c_int32, f32p, C.c_int64, C.c_int32, f32p, f32p, vp]
     lib.aecf_sdpa_fwd.restype = C.c_int
     lib.aecf_sdpa_fwd.argtypes = [C.c_int32, C.c_int32, vp, vp, vp, vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, vp]
+    lib.aecf_sdpa_bwd.restype = C.c_int
+    lib.aecf_sdpa_bwd.argtypes = [C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp, C.c_size_t, C.c_int64, C.c_int32, C.c_int32,
+                                  C.c_int32, vp]
     lib.aecf_fusion_fwd.restype = C.c_int
     lib.aecf_fusion_fwd.argtypes = [C.POINTER(PoolDesc), C.POINTER(FusionTensors), vp, C.c_size_t, vp]
     lib.aecf_fusion_bwd.restype = C.c_int

@@ -156,6 +156,12 @@ static int make_plan(const aecf_pool_desc* d, PoolPlan* plan, bool fold = false)
         plan->mq.bias_sb = d->bias_stride_b; plan->mq.bias_sh = d->bias_stride_h; plan->mq.bias_ss = d->bias_stride_s;
         p.rng.row0 = d->row0 * static_cast<unsigned long long>(S);  // Philox row of (b, s): (row0 + b) * S + s
     }
+    if (d->row_index != nullptr) {
+        if (!d->q_is_shared || plan->multi) return AECF_ERR_UNSUPPORTED;
+        if (d->src_rows < d->batch) return AECF_ERR_INVALID;
+        if (p.bias_sb != 0 || p.bias_sh != 0) return AECF_ERR_UNSUPPORTED;      // a per-row score bias would need the indirection too
+        p.row_index = reinterpret_cast<const long long*>(d->row_index);
+    }
     plan->fold = fold;
     plan->M = d->num_tokens; plan->J = J;
     plan->drop = d->training && d->dropout_p > 0.f;
@@ -193,7 +199,7 @@ const char* aecf_build_info(void) {
 
 // the streaming forward kernel (one warp per sample, at most one CTA per SM) carries the fused entropy_loss term
 static bool pool_fwd_carries_loss(const PoolPlan& plan, const aecf_pool_desc& d) {
-    return !plan.multi && plan.p.WPS == 1 && d.masking == 1 && sm_count(d.device) <= POOL_LOSS_MAX_CTAS;
+    return !plan.multi && plan.p.WPS == 1 && d.masking == 1 && d.row_index == nullptr && sm_count(d.device) <= POOL_LOSS_MAX_CTAS;
 }
 
 static int pool_fwd_impl(const aecf_pool_desc* desc, bool fold, const void* q, const float* scores, const void* kv,
@@ -205,7 +211,9 @@ static int pool_fwd_impl(const aecf_pool_desc* desc, bool fold, const void* q, c
     if (desc->batch == 0) return AECF_OK;
     if ((!fold && !q) || (fold && !scores) || !kv || !ctx || !pooled) return AECF_ERR_INVALID;
     if ((q && !aligned16(q)) || !aligned16(kv) || !aligned16(ctx)) return AECF_ERR_ALIGNMENT;
-    if ((rc = use_device(desc->device)) != AECF_OK) return rc;
+    if (desc->row_index != nullptr && score_bias != nullptr) return AECF_ERR_UNSUPPORTED;
+    DeviceScope device_scope__(desc->device);
+    if ((rc = device_scope__.rc) != AECF_OK) return rc;
     PoolParams& p = plan.p;
     p.q = q; p.kv = kv; p.bias = score_bias; p.scores = scores;
     p.ctx = ctx; p.pooled = pooled; p.entropy = entropy; p.mask_rate = mask_rate; p.masked = masked;
@@ -283,8 +291,10 @@ static int pool_bwd_impl(const aecf_pool_desc* desc, bool fold, const void* q, c
         !aligned16(workspace))
         return AECF_ERR_ALIGNMENT;
     if (workspace_bytes < aecf_pool_bwd_workspace_bytes(desc)) return AECF_ERR_WORKSPACE;
+    if (desc->row_index != nullptr && score_bias != nullptr) return AECF_ERR_UNSUPPORTED;
     if (desc->batch == 0) return AECF_OK;
-    if ((rc = use_device(desc->device)) != AECF_OK) return rc;
+    DeviceScope device_scope__(desc->device);
+    if ((rc = device_scope__.rc) != AECF_OK) return rc;
     PoolParams& p = plan.p;
     p.q = q; p.kv = kv; p.bias = score_bias; p.scores = scores;
     p.d_ctx = d_ctx; p.d_pooled = d_pooled; p.d_entropy = d_entropy; p.d_kv = d_kv; p.d_q = d_q;

@@ -30,6 +30,22 @@ constexpr unsigned FULL_MASK = 0xffffffffu;
 void count_launch(unsigned n = 1);
 int set_cuda_error(cudaError_t err, const char* what);   // records and returns AECF_ERR_CUDA
 int use_device(int device);                               // cudaSetDevice; 0 or AECF_ERR_CUDA
+// Every entry point runs on the device of its descriptor and leaves the calling thread's current device as it found it
+// (a caller holding tensors on several GPUs must not find torch's current device changed under it).
+struct DeviceScope {
+    int previous = -1, rc = AECF_OK;
+    bool changed = false;
+    explicit DeviceScope(int device) {
+        if (cudaGetDevice(&previous) != cudaSuccess) previous = -1;
+        if (previous != device) {
+            rc = use_device(device);
+            changed = rc == AECF_OK && previous >= 0;
+        }
+    }
+    ~DeviceScope() { if (changed) cudaSetDevice(previous); }
+    DeviceScope(const DeviceScope&) = delete;
+    DeviceScope& operator=(const DeviceScope&) = delete;
+};
 int sm_count(int device);
 
 // per-kernel timing (timing.cu): the current site is thread-local, set by the whole-step entry points

@@ -256,7 +256,8 @@ int aecf_fold_prepare(int32_t device, int32_t dtype, int32_t embed_dim, int32_t 
     if (rc != AECF_OK) return rc;
     if (!q_proj || !in_proj_weight || !folded_w) return AECF_ERR_INVALID;
     if (!aligned16(in_proj_weight) || !aligned16(folded_w)) return AECF_ERR_ALIGNMENT;
-    if ((rc = use_device(device)) != AECF_OK) return rc;
+    DeviceScope device_scope__(device);
+    if ((rc = device_scope__.rc) != AECF_OK) return rc;
     const int D = embed_dim, H = num_heads, hsp = aecf_fold_score_cols(dtype, H);
     const float scale = static_cast<float>(sqrt(1.0 / static_cast<double>(D / H)));
     const int fold_blocks = hsp * ((D + 31) / 32);
@@ -281,7 +282,8 @@ int aecf_fold_prepare_query(int32_t device, int32_t dtype, int32_t embed_dim, in
     if (rc != AECF_OK) return rc;
     if (!query || !in_proj_weight || !q_proj || !folded_w) return AECF_ERR_INVALID;
     if (!aligned16(in_proj_weight) || !aligned16(folded_w) || !aligned16(query)) return AECF_ERR_ALIGNMENT;
-    if ((rc = use_device(device)) != AECF_OK) return rc;
+    DeviceScope device_scope__(device);
+    if ((rc = device_scope__.rc) != AECF_OK) return rc;
     const int D = embed_dim, H = num_heads, hsp = aecf_fold_score_cols(dtype, H);
     const float scale = static_cast<float>(sqrt(1.0 / static_cast<double>(D / H)));
     const int fold_blocks = hsp * ((D + 31) / 32);
@@ -310,7 +312,8 @@ int aecf_fold_finish(int32_t device, int32_t dtype, int32_t embed_dim, int32_t n
     int rc = fold_check(dtype, embed_dim, num_heads);
     if (rc != AECF_OK) return rc;
     if (!g || !q_proj || !in_proj_weight) return AECF_ERR_INVALID;
-    if ((rc = use_device(device)) != AECF_OK) return rc;
+    DeviceScope device_scope__(device);
+    if ((rc = device_scope__.rc) != AECF_OK) return rc;
     const int D = embed_dim, H = num_heads;
     const float scale = static_cast<float>(sqrt(1.0 / static_cast<double>(D / H)));
     cudaStream_t s = static_cast<cudaStream_t>(stream);

@@ -27,8 +27,12 @@ struct Geometry {
 static int geometry(const aecf_pool_desc* d, Geometry* g) {
     if (!d || d->batch < 0 || d->embed_dim <= 0 || d->num_tokens <= 0) return AECF_ERR_INVALID;
     if (d->dtype != AECF_F32 && d->dtype != AECF_BF16) return AECF_ERR_INVALID;
-    g->B = d->batch; g->M = d->num_tokens; g->D = d->embed_dim; g->rows = g->B * g->M;
-    g->QR = g->B * (d->tgt_len > 1 ? d->tgt_len : 1);
+    g->B = d->batch; g->M = d->num_tokens; g->D = d->embed_dim;
+    // row indirection: the pool kernels take the `batch` listed rows, the products around them all `src_rows` samples
+    const long long samples = d->row_index != nullptr ? d->src_rows : d->batch;
+    if (d->row_index != nullptr && (d->src_rows < d->batch || d->tgt_len > 1 || !d->q_is_shared)) return AECF_ERR_UNSUPPORTED;
+    g->rows = samples * g->M;
+    g->QR = samples * (d->tgt_len > 1 ? d->tgt_len : 1);
     g->dt = d->dtype; g->es = d->dtype == AECF_BF16 ? 2 : 4; g->shared = d->q_is_shared != 0;
     g->H = d->num_heads; g->fold = d->fold_key != 0;
     g->HS = (g->H + 3) & ~3; g->HSP = aecf_fold_score_cols(d->dtype, g->H);
@@ -172,6 +176,8 @@ static int folded_backward(const aecf_pool_desc* desc, const Geometry& g, const 
         const aecf_gemm_desc d = gemm_desc(dev, dt, dt, dt, dt, AECF_K_MAJOR, AECF_MN_MAJOR, g.QR, D, D, D, D, D);
         AECF_TRY(aecf_gemm(&d, gr->d_out, t->out_proj_weight, nullptr, gr->d_ctx, w.gemm, w.gemm_bytes, s));
     }
+    if (desc->row_index != nullptr)                              // unlisted samples: zero rows of [dV | ds]
+        AECF_CUDA_OK(cudaMemsetAsync(gr->d_kv, 0, static_cast<size_t>(g.rows) * KF * g.es, s));
     {
         ScopedSite site(AECF_SITE_POOL_BWD);
         AECF_TRY(pool_bwd_folded_partials(desc, t->q_proj, t->scores, t->kv, t->score_bias, gr->d_ctx, gr->d_pooled,
@@ -276,6 +282,8 @@ int aecf_fusion_fwd(const aecf_pool_desc* desc, const aecf_fusion_tensors* t, vo
             AECF_TRY(aecf_gemm_aux(&v, t->key, t->folded_w, bias ? at(t->in_proj_bias, 2 * D, es) : nullptr, t->kv, t->scores,
                                    g.H, g.HS, w.gemm, w.gemm_bytes, stream));
         }
+        if (desc->row_index != nullptr)                          // unlisted samples: a zero context
+            AECF_CUDA_OK(cudaMemsetAsync(t->ctx, 0, static_cast<size_t>(g.QR) * D * es, static_cast<cudaStream_t>(stream)));
         {
             ScopedSite site(AECF_SITE_POOL_FWD);
             AECF_TRY(aecf_pool_fwd_folded(desc, t->scores, t->kv, t->score_bias, t->ctx, t->pooled, t->entropy, t->mask_rate,
@@ -296,6 +304,8 @@ int aecf_fusion_fwd(const aecf_pool_desc* desc, const aecf_fusion_tensors* t, vo
                                bias ? at(t->in_proj_bias, 2 * D, es) : nullptr, at(t->kv, D, es), w.gemm, w.gemm_bytes, stream));
         }
     }
+    if (desc->row_index != nullptr)
+        AECF_CUDA_OK(cudaMemsetAsync(t->ctx, 0, static_cast<size_t>(g.QR) * D * es, static_cast<cudaStream_t>(stream)));
     {
         ScopedSite site(AECF_SITE_POOL_FWD);
         AECF_TRY(aecf_pool_fwd(desc, t->q_proj, t->kv, t->score_bias, t->ctx, t->pooled, t->entropy, t->mask_rate,
@@ -353,6 +363,8 @@ int aecf_fusion_bwd(const aecf_pool_desc* desc, const aecf_fusion_tensors* t, co
     if (g.fold) {
         if (t->value || !t->scores || !t->folded_w) return AECF_ERR_INVALID;
         const int KF = D + g.HSP;                            // contraction / row width of d_vs = [dV | ds]
+        if (desc->row_index != nullptr)
+            AECF_CUDA_OK(cudaMemsetAsync(gr->d_kv, 0, static_cast<size_t>(g.rows) * KF * es, s));
         {
             ScopedSite site(AECF_SITE_POOL_BWD);
             AECF_TRY(aecf_pool_bwd_folded(desc, t->q_proj, t->scores, t->kv, t->score_bias, gr->d_ctx, gr->d_pooled,
@@ -374,6 +386,8 @@ int aecf_fusion_bwd(const aecf_pool_desc* desc, const aecf_fusion_tensors* t, co
                                       gr->d_in_proj_weight, w.d_qp, stream));
         }
     } else {
+    if (desc->row_index != nullptr)
+        AECF_CUDA_OK(cudaMemsetAsync(gr->d_kv, 0, static_cast<size_t>(g.rows) * 2 * D * es, s));
     {   // ---- fused recompute backward of the pool ---------------------------------------------------
         ScopedSite site(AECF_SITE_POOL_BWD);
         void* dq = g.shared ? static_cast<void*>(w.d_qp) : gr->d_q_rows;

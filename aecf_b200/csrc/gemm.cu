@@ -255,7 +255,8 @@ int gemm_partials(const aecf_gemm_desc* d, const void* A, const void* B, void* w
     if (rc != AECF_OK) return rc;
     if (!A || !B || !workspace || !out) return AECF_ERR_INVALID;
     if (workspace_bytes < gemm_partials_workspace_bytes(d)) return AECF_ERR_WORKSPACE;
-    if ((rc = use_device(d->device)) != AECF_OK) return rc;
+    DeviceScope device_scope__(d->device);
+    if ((rc = device_scope__.rc) != AECF_OK) return rc;
     char* head = static_cast<char*>(workspace);
     char* tail = head + partials_head_bytes(d);
     const size_t tail_bytes = workspace_bytes - partials_head_bytes(d);
@@ -291,7 +292,8 @@ int aecf_gemm(const aecf_gemm_desc* d, const void* A, const void* B, const void*
     if (rc != AECF_OK) return rc;
     if (d->m == 0 || d->n == 0) return AECF_OK;
     if (!A || !B || !C) return AECF_ERR_INVALID;
-    if ((rc = use_device(d->device)) != AECF_OK) return rc;
+    DeviceScope device_scope__(d->device);
+    if ((rc = device_scope__.rc) != AECF_OK) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     TimedLaunch timed(s);
     if (d->impl != AECF_GEMM_SIMT) {
@@ -308,7 +310,8 @@ int aecf_gemm_aux(const aecf_gemm_desc* d, const void* A, const void* B, const v
     if (aux_cols <= 0 || aux_cols > 32 || aux_ld < ((aux_cols + 3) & ~3) || d->accumulate) return AECF_ERR_INVALID;
     if (d->m == 0 || d->n == 0) return AECF_OK;
     if (!A || !B || !C || !aux) return AECF_ERR_INVALID;
-    if ((rc = use_device(d->device)) != AECF_OK) return rc;
+    DeviceScope device_scope__(d->device);
+    if ((rc = device_scope__.rc) != AECF_OK) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     TimedLaunch timed(s);
     if (d->impl != AECF_GEMM_SIMT) {

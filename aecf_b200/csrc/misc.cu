@@ -149,11 +149,19 @@ __device__ __forceinline__ float entropy_of(const float* w, int len, float log_l
 __global__ void curriculum_mask_kernel(const float* __restrict__ weights, long long rows, int len, int mode,
                                        float base_mask_prob, int min_active, float log_len, RngKey rng,
                                        float* __restrict__ masked, float* __restrict__ entropy,
-                                       float* __restrict__ mask_rate) {
+                                       float* __restrict__ mask_rate, const float* __restrict__ d_masked = nullptr,
+                                       float* __restrict__ d_weights = nullptr) {
+    // d_weights != nullptr: the BACKWARD of the training-mode call (mode 1) -- the mask is redrawn from the same Philox
+    // row, then d_weights = d(final_weights)/d(weights)^T d_masked; mask, top-k set and entropy carry no gradient
+    // (torch.bernoulli / topk indices in the reference, aecf/AECFLayer.py:204-260)
     const long long row = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (row >= rows) return;
     float w[MASK_MAX_LEN];
     for (int i = 0; i < len; ++i) w[i] = weights[row * len + i];
+    if (d_weights != nullptr && len <= 1) {                 // a single token passes through unchanged (:159-167)
+        for (int i = 0; i < len; ++i) d_weights[row * len + i] = d_masked[row * len + i];
+        return;
+    }
     if (mode != 1 || len <= 1) {                    // eval mode / entropy only / single token (:150-167)
         const float e = (mode == 1) ? 0.f : entropy_of(w, len, log_len, nullptr);
         if (entropy) entropy[row] = e;
@@ -162,8 +170,10 @@ __global__ void curriculum_mask_kernel(const float* __restrict__ weights, long l
         return;
     }
     float total = 0.f;
+    unsigned long long finite = 0ull;
     for (int i = 0; i < len; ++i) {
-        w[i] = (fabsf(w[i]) <= 3.402823466e38f) ? w[i] : 0.f;
+        if (fabsf(w[i]) <= 3.402823466e38f) finite |= 1ull << i;
+        else w[i] = 0.f;
         total = __fadd_rn(total, w[i]);
     }
     const bool degenerate = total < 1e-8f;
@@ -195,6 +205,24 @@ __global__ void curriculum_mask_kernel(const float* __restrict__ weights, long l
     float kept_sum = 0.f;
     for (int i = 0; i < len; ++i) kept_sum = __fadd_rn(kept_sum, ((bits >> i) & 1ull) ? w[i] : 0.f);
     const bool valid = kept_sum > 1e-8f;
+    if (d_weights != nullptr) {
+        // valid: final = wn m / kept_sum (degree 0 in wn, so the 1/total of wn = w / total is all that is left of it);
+        // fallback: final = wn.  A degenerate row (wn = uniform) and non-finite entries get no gradient.
+        float dot = 0.f;
+        for (int i = 0; i < len; ++i) {
+            const float fin = valid ? ((((bits >> i) & 1ull) ? w[i] : 0.f) / kept_sum) : w[i];
+            dot = fmaf(d_masked[row * len + i], fin, dot);
+        }
+        for (int i = 0; i < len; ++i) {
+            float d = 0.f;
+            if (!degenerate && ((finite >> i) & 1ull)) {
+                const float g = d_masked[row * len + i];
+                d = valid ? (((bits >> i) & 1ull) ? (g - dot) / kept_sum / total : 0.f) : (g - dot) / total;
+            }
+            d_weights[row * len + i] = d;
+        }
+        return;
+    }
     if (masked)
         for (int i = 0; i < len; ++i)
             masked[row * len + i] = valid ? (((bits >> i) & 1ull) ? w[i] : 0.f) / kept_sum : w[i];
@@ -299,6 +327,173 @@ static int launch_sdpa(const void* q, const void* k, const void* v, void* out, l
     return AECF_OK;
 }
 
+
+// ---- backward of the projection-free attention (reference aecf/AECFLayer.py:573-581 is differentiable) -----------------
+// out[s] = sum_t p[s,t] v[t],  p = softmax_t(scale q[s] . k[t]):
+//   dP[s,t] = g[s] . v[t]      delta[s] = sum_t p dP      dS = p (dP - delta)
+//   dq[s] = scale sum_t dS k[t]        dk[t] = scale sum_s dS q[s]        dv[t] = sum_s p g[s]
+// Two kernels, nothing stored by the forward: one warp per QUERY row recomputes its scores (log-sum-exp, then delta, then
+// dq: three passes over the sample's keys, which sit in L1/L2) and leaves lse / delta; one warp per KEY row then walks the
+// sample's queries.  A warp covers the row chunk-wise (16 bytes per lane) and dots are xor-shuffle reductions.
+template <typename T, int JMAX>
+__device__ __forceinline__ float sdpa_dot(const float (&a)[JMAX][Vec<T>::N], const T* row, int lane, int NC) {
+    constexpr int V = Vec<T>::N;
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < JMAX; ++j) {
+        const int c = lane + 32 * j;
+        if (c < NC) {
+            float f[V];
+            Vec<T>::unpack(ldg_cached(row + static_cast<long long>(c) * V), f);
+#pragma unroll
+            for (int x = 0; x < V; ++x) dot = fmaf(a[j][x], f[x], dot);
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) dot += __shfl_xor_sync(FULL_MASK, dot, off);
+    return dot;
+}
+
+template <typename T, int JMAX>
+__device__ __forceinline__ void sdpa_load(float (&a)[JMAX][Vec<T>::N], const T* row, int lane, int NC) {
+    constexpr int V = Vec<T>::N;
+#pragma unroll
+    for (int j = 0; j < JMAX; ++j) {
+        const int c = lane + 32 * j;
+#pragma unroll
+        for (int x = 0; x < V; ++x) a[j][x] = 0.f;
+        if (c < NC) Vec<T>::unpack(ldg_cached(row + static_cast<long long>(c) * V), a[j]);
+    }
+}
+
+template <typename T, int JMAX>
+__global__ void __launch_bounds__(256) sdpa_bwd_q_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v,
+                                                         const T* __restrict__ g, T* __restrict__ d_q, float* __restrict__ lse,
+                                                         float* __restrict__ delta, long long rows, int tgt_len, int src_len,
+                                                         int D, float scale) {
+    constexpr int V = Vec<T>::N;
+    const int lane = threadIdx.x & 31;
+    const long long qrow = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (qrow >= rows) return;
+    const long long b = qrow / tgt_len;
+    const int NC = D / V;
+    float qf[JMAX][V], gf[JMAX][V], acc[JMAX][V];
+    sdpa_load<T, JMAX>(qf, q + qrow * D, lane, NC);
+    sdpa_load<T, JMAX>(gf, g + qrow * D, lane, NC);
+    float mx = -INFINITY, sum = 0.f;
+    for (int t = 0; t < src_len; ++t) {
+        const float s = sdpa_dot<T, JMAX>(qf, k + (b * src_len + t) * D, lane, NC) * scale;
+        const float nm = fmaxf(mx, s);
+        sum = sum * expf(mx - nm) + expf(s - nm);
+        mx = nm;
+    }
+    const float l = mx + logf(sum);
+    float dl = 0.f;
+    for (int t = 0; t < src_len; ++t) {
+        const long long krow = (b * src_len + t) * D;
+        const float p = expf(sdpa_dot<T, JMAX>(qf, k + krow, lane, NC) * scale - l);
+        dl = fmaf(p, sdpa_dot<T, JMAX>(gf, v + krow, lane, NC), dl);
+    }
+#pragma unroll
+    for (int j = 0; j < JMAX; ++j)
+#pragma unroll
+        for (int x = 0; x < V; ++x) acc[j][x] = 0.f;
+    for (int t = 0; t < src_len; ++t) {
+        const long long krow = (b * src_len + t) * D;
+        const float p = expf(sdpa_dot<T, JMAX>(qf, k + krow, lane, NC) * scale - l);
+        const float ds = p * (sdpa_dot<T, JMAX>(gf, v + krow, lane, NC) - dl) * scale;
+#pragma unroll
+        for (int j = 0; j < JMAX; ++j) {
+            const int c = lane + 32 * j;
+            if (c < NC) {
+                float f[V];
+                Vec<T>::unpack(ldg_cached(k + krow + static_cast<long long>(c) * V), f);
+#pragma unroll
+                for (int x = 0; x < V; ++x) acc[j][x] = fmaf(ds, f[x], acc[j][x]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < JMAX; ++j) {
+        const int c = lane + 32 * j;
+        if (c < NC) stg_vec(d_q + qrow * D + static_cast<long long>(c) * V, Vec<T>::pack(acc[j]));
+    }
+    if (lane == 0) { lse[qrow] = l; delta[qrow] = dl; }
+}
+
+template <typename T, int JMAX>
+__global__ void __launch_bounds__(256) sdpa_bwd_kv_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v,
+                                                          const T* __restrict__ g, const float* __restrict__ lse,
+                                                          const float* __restrict__ delta, T* __restrict__ d_k, T* __restrict__ d_v,
+                                                          long long key_rows, int tgt_len, int src_len, int D, float scale) {
+    constexpr int V = Vec<T>::N;
+    const int lane = threadIdx.x & 31;
+    const long long krow = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (krow >= key_rows) return;
+    const long long b = krow / src_len;
+    const int NC = D / V;
+    float kf[JMAX][V], vf[JMAX][V], dk[JMAX][V], dv[JMAX][V];
+    sdpa_load<T, JMAX>(kf, k + krow * D, lane, NC);
+    sdpa_load<T, JMAX>(vf, v + krow * D, lane, NC);
+#pragma unroll
+    for (int j = 0; j < JMAX; ++j)
+#pragma unroll
+        for (int x = 0; x < V; ++x) { dk[j][x] = 0.f; dv[j][x] = 0.f; }
+    for (int s = 0; s < tgt_len; ++s) {
+        const long long qrow = b * tgt_len + s;
+        const float p = expf(sdpa_dot<T, JMAX>(kf, q + qrow * D, lane, NC) * scale - lse[qrow]);
+        const float ds = p * (sdpa_dot<T, JMAX>(vf, g + qrow * D, lane, NC) - delta[qrow]) * scale;
+#pragma unroll
+        for (int j = 0; j < JMAX; ++j) {
+            const int c = lane + 32 * j;
+            if (c < NC) {
+                float fq[V], fg[V];
+                Vec<T>::unpack(ldg_cached(q + qrow * D + static_cast<long long>(c) * V), fq);
+                Vec<T>::unpack(ldg_cached(g + qrow * D + static_cast<long long>(c) * V), fg);
+#pragma unroll
+                for (int x = 0; x < V; ++x) { dk[j][x] = fmaf(ds, fq[x], dk[j][x]); dv[j][x] = fmaf(p, fg[x], dv[j][x]); }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < JMAX; ++j) {
+        const int c = lane + 32 * j;
+        if (c < NC) {
+            stg_vec(d_k + krow * D + static_cast<long long>(c) * V, Vec<T>::pack(dk[j]));
+            stg_vec(d_v + krow * D + static_cast<long long>(c) * V, Vec<T>::pack(dv[j]));
+        }
+    }
+}
+
+template <typename T>
+static int launch_sdpa_bwd(const void* q, const void* k, const void* v, const void* g, void* d_q, void* d_k, void* d_v,
+                           float* ws, long long batch, int tgt, int src, int D, cudaStream_t s) {
+    constexpr int V = Vec<T>::N;
+    const int NC = D / V;
+    const float scale = static_cast<float>(1.0 / std::sqrt(static_cast<double>(D)));
+    const long long qrows = batch * tgt, krows = batch * src;
+    float* lse = ws;
+    float* delta = ws + qrows;
+#define AECF_SDPA_BWD(JM)                                                                                              \
+    do {                                                                                                               \
+        AECF_CUDA_OK(launch_plain(sdpa_bwd_q_kernel<T, JM>, dim3(static_cast<unsigned>((qrows + 7) / 8)), dim3(256), 0, s,         \
+                                  static_cast<const T*>(q), static_cast<const T*>(k), static_cast<const T*>(v),        \
+                                  static_cast<const T*>(g), static_cast<T*>(d_q), lse, delta, qrows, tgt, src, D, scale));          \
+        AECF_CUDA_OK(launch_plain(sdpa_bwd_kv_kernel<T, JM>, dim3(static_cast<unsigned>((krows + 7) / 8)), dim3(256), 0, s,        \
+                                  static_cast<const T*>(q), static_cast<const T*>(k), static_cast<const T*>(v),        \
+                                  static_cast<const T*>(g), static_cast<const float*>(lse), static_cast<const float*>(delta),      \
+                                  static_cast<T*>(d_k), static_cast<T*>(d_v), krows, tgt, src, D, scale));                         \
+    } while (0)
+    if (NC <= 32) AECF_SDPA_BWD(1);
+    else if (NC <= 64) AECF_SDPA_BWD(2);
+    else if (NC <= 128) AECF_SDPA_BWD(4);
+    else if (NC <= 256) AECF_SDPA_BWD(8);
+    else return AECF_ERR_UNSUPPORTED;
+#undef AECF_SDPA_BWD
+    count_launch(2);
+    return AECF_OK;
+}
+
 }  // namespace aecf
 
 using namespace aecf;
@@ -320,7 +515,8 @@ int aecf_colsum(int32_t device, int32_t dtype_x, int32_t dtype_out, const void* 
     if (cols % V != 0) return AECF_ERR_UNSUPPORTED;
     if (!aligned16(x) || (static_cast<size_t>(ld) * es) % 16 != 0) return AECF_ERR_ALIGNMENT;
     if (workspace_bytes < aecf_colsum_workspace_bytes(rows, cols)) return AECF_ERR_WORKSPACE;
-    int rc = use_device(device);
+    DeviceScope device_scope__(device);
+    int rc = device_scope__.rc;
     if (rc != AECF_OK) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     TimedLaunch timed(s);
@@ -345,7 +541,8 @@ int aecf_colsum(int32_t device, int32_t dtype_x, int32_t dtype_out, const void* 
 
 int aecf_entropy_loss_fwd(int32_t device, const float* entropy, int64_t n, float target, float* loss, void* stream) {
     if (!entropy || !loss || n <= 0) return AECF_ERR_INVALID;
-    int rc = use_device(device);
+    DeviceScope device_scope__(device);
+    int rc = device_scope__.rc;
     if (rc != AECF_OK) return rc;
     TimedLaunch timed(static_cast<cudaStream_t>(stream), AECF_SITE_ENTROPY_LOSS);
     AECF_CUDA_OK(launch_pdl(entropy_loss_fwd_kernel, dim3(1), dim3(1024), 0, static_cast<cudaStream_t>(stream), entropy,
@@ -357,7 +554,8 @@ int aecf_entropy_loss_fwd(int32_t device, const float* entropy, int64_t n, float
 int aecf_entropy_loss_bwd(int32_t device, const float* entropy, int64_t n, float target, const float* d_loss,
                           float* d_entropy, void* stream) {
     if (!entropy || !d_loss || !d_entropy || n <= 0) return AECF_ERR_INVALID;
-    int rc = use_device(device);
+    DeviceScope device_scope__(device);
+    int rc = device_scope__.rc;
     if (rc != AECF_OK) return rc;
     AECF_CUDA_OK(launch_plain(entropy_loss_bwd_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0,
                               static_cast<cudaStream_t>(stream), entropy, static_cast<long long>(n), target, d_loss, d_entropy));
@@ -371,7 +569,8 @@ int aecf_curriculum_mask(int32_t device, const float* weights, int64_t rows, int
     if (!weights || rows < 0 || len <= 0 || mode < 1 || mode > 3 || (offset >> 32)) return AECF_ERR_INVALID;
     if (len > MASK_MAX_LEN) return AECF_ERR_UNSUPPORTED;
     if (rows == 0) return AECF_OK;
-    int rc = use_device(device);
+    DeviceScope device_scope__(device);
+    int rc = device_scope__.rc;
     if (rc != AECF_OK) return rc;
     RngKey rng;
     rng.k0 = static_cast<uint32_t>(seed); rng.k1 = static_cast<uint32_t>(seed >> 32);
@@ -379,7 +578,29 @@ int aecf_curriculum_mask(int32_t device, const float* weights, int64_t rows, int
     const float log_len = static_cast<float>(std::log(static_cast<double>(len)));
     AECF_CUDA_OK(launch_plain(curriculum_mask_kernel, dim3(static_cast<unsigned>((rows + 127) / 128)), dim3(128), 0,
                               static_cast<cudaStream_t>(stream), weights, static_cast<long long>(rows), len, mode, base_mask_prob,
-                              min_active, log_len, rng, masked, entropy, mask_rate));
+                              min_active, log_len, rng, masked, entropy, mask_rate, static_cast<const float*>(nullptr),
+                              static_cast<float*>(nullptr)));
+    count_launch();
+    return AECF_OK;
+}
+
+int aecf_curriculum_mask_bwd(int32_t device, const float* weights, int64_t rows, int32_t len, float base_mask_prob,
+                             int32_t min_active, uint64_t seed, uint64_t offset, uint64_t row0, const float* d_masked,
+                             float* d_weights, void* stream) {
+    if (!weights || !d_masked || !d_weights || rows < 0 || len <= 0 || (offset >> 32)) return AECF_ERR_INVALID;
+    if (len > MASK_MAX_LEN) return AECF_ERR_UNSUPPORTED;
+    if (rows == 0) return AECF_OK;
+    DeviceScope device_scope__(device);
+    int rc = device_scope__.rc;
+    if (rc != AECF_OK) return rc;
+    RngKey rng;
+    rng.k0 = static_cast<uint32_t>(seed); rng.k1 = static_cast<uint32_t>(seed >> 32);
+    rng.offset = static_cast<uint32_t>(offset); rng.row0 = row0;
+    const float log_len = static_cast<float>(std::log(static_cast<double>(len)));
+    AECF_CUDA_OK(launch_plain(curriculum_mask_kernel, dim3(static_cast<unsigned>((rows + 127) / 128)), dim3(128), 0,
+                              static_cast<cudaStream_t>(stream), weights, static_cast<long long>(rows), len, 1, base_mask_prob,
+                              min_active, log_len, rng, static_cast<float*>(nullptr), static_cast<float*>(nullptr),
+                              static_cast<float*>(nullptr), d_masked, d_weights));
     count_launch();
     return AECF_OK;
 }
@@ -389,7 +610,8 @@ int aecf_entropy_bwd(int32_t device, const float* weights, int64_t rows, int32_t
     if (!weights || !d_entropy || !d_weights || rows < 0 || len <= 0) return AECF_ERR_INVALID;
     if (len > MASK_MAX_LEN) return AECF_ERR_UNSUPPORTED;
     if (rows == 0) return AECF_OK;
-    int rc = use_device(device);
+    DeviceScope device_scope__(device);
+    int rc = device_scope__.rc;
     if (rc != AECF_OK) return rc;
     const float log_len = static_cast<float>(std::log(static_cast<double>(len)));
     AECF_CUDA_OK(launch_plain(entropy_bwd_kernel, dim3(static_cast<unsigned>((rows + 127) / 128)), dim3(128), 0,
@@ -407,12 +629,35 @@ int aecf_sdpa_fwd(int32_t device, int32_t dtype, const void* q, const void* k, c
     const int V = dtype == AECF_BF16 ? 8 : 4;
     if (embed_dim % V != 0) return AECF_ERR_UNSUPPORTED;
     if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(out)) return AECF_ERR_ALIGNMENT;
-    int rc = use_device(device);
+    DeviceScope device_scope__(device);
+    int rc = device_scope__.rc;
     if (rc != AECF_OK) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const long long rows = static_cast<long long>(batch) * tgt_len;
     return dtype == AECF_BF16 ? launch_sdpa<__nv_bfloat16>(q, k, v, out, rows, tgt_len, src_len, embed_dim, s)
                               : launch_sdpa<float>(q, k, v, out, rows, tgt_len, src_len, embed_dim, s);
+}
+
+/* d_q / d_k / d_v of aecf_sdpa_fwd for an upstream gradient d_out [B, tgt, D]; workspace >= 2 * B * tgt_len floats */
+int aecf_sdpa_bwd(int32_t device, int32_t dtype, const void* q, const void* k, const void* v, const void* d_out, void* d_q,
+                  void* d_k, void* d_v, void* workspace, size_t workspace_bytes, int64_t batch, int32_t tgt_len,
+                  int32_t src_len, int32_t embed_dim, void* stream) {
+    if (!q || !k || !v || !d_out || !d_q || !d_k || !d_v || !workspace || batch < 0 || tgt_len <= 0 || src_len <= 0 || embed_dim <= 0)
+        return AECF_ERR_INVALID;
+    if (dtype != AECF_F32 && dtype != AECF_BF16) return AECF_ERR_INVALID;
+    if (batch == 0) return AECF_OK;
+    const int V = dtype == AECF_BF16 ? 8 : 4;
+    if (embed_dim % V != 0) return AECF_ERR_UNSUPPORTED;
+    if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(d_out) || !aligned16(d_q) || !aligned16(d_k) || !aligned16(d_v))
+        return AECF_ERR_ALIGNMENT;
+    if (workspace_bytes < static_cast<size_t>(2) * batch * tgt_len * sizeof(float)) return AECF_ERR_WORKSPACE;
+    DeviceScope device_scope__(device);
+    int rc = device_scope__.rc;
+    if (rc != AECF_OK) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    return dtype == AECF_BF16
+        ? launch_sdpa_bwd<__nv_bfloat16>(q, k, v, d_out, d_q, d_k, d_v, static_cast<float*>(workspace), batch, tgt_len, src_len, embed_dim, s)
+        : launch_sdpa_bwd<float>(q, k, v, d_out, d_q, d_k, d_v, static_cast<float*>(workspace), batch, tgt_len, src_len, embed_dim, s);
 }
 
 }  // extern "C"

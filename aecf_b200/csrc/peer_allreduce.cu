@@ -152,7 +152,8 @@ int launch_peer_sum(int device, const aecf_dp_desc* dp, long long count, cudaStr
         p.flags[r] = static_cast<uint32_t*>(dp->flags[r]);
     }
     p.count = count; p.world = dp->world; p.rank = dp->rank; p.average = dp->average;
-    int rc = use_device(device);
+    DeviceScope device_scope__(device);
+    int rc = device_scope__.rc;
     if (rc != AECF_OK) return rc;
     // few CTAs: the kernel shares the SMs with the dX product's persistent CTAs (it needs no shared memory, so it fits
     // next to them) and what it moves is small (world x 2 MB at D = 512) -- latency, not bandwidth
@@ -176,7 +177,8 @@ size_t aecf_peer_flag_bytes(void) { return PEER_FLAG_WORDS * sizeof(uint32_t); }
 
 int aecf_peer_enable_access(int32_t device, int32_t peer_device) {
     if (device == peer_device) return AECF_OK;
-    int rc = use_device(device);
+    DeviceScope device_scope__(device);
+    int rc = device_scope__.rc;
     if (rc != AECF_OK) return rc;
     int can = 0;
     AECF_CUDA_OK(cudaDeviceCanAccessPeer(&can, device, peer_device));
@@ -194,7 +196,8 @@ int aecf_peer_enable_access(int32_t device, int32_t peer_device) {
 int aecf_peer_export(int32_t device, const void* ptr, void* handle64, int64_t* offset) {
     if (!ptr || !handle64 || !offset) return AECF_ERR_INVALID;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the ABI carries IPC handles as 64 bytes");
-    int rc = use_device(device);
+    DeviceScope device_scope__(device);
+    int rc = device_scope__.rc;
     if (rc != AECF_OK) return rc;
     using RangeFn = CUresult (*)(CUdeviceptr*, size_t*, CUdeviceptr);
     void* sym = nullptr;
@@ -213,7 +216,8 @@ int aecf_peer_export(int32_t device, const void* ptr, void* handle64, int64_t* o
 
 int aecf_peer_import(int32_t device, const void* handle64, void** base_out) {
     if (!handle64 || !base_out) return AECF_ERR_INVALID;
-    int rc = use_device(device);
+    DeviceScope device_scope__(device);
+    int rc = device_scope__.rc;
     if (rc != AECF_OK) return rc;
     cudaIpcMemHandle_t h;
     std::memcpy(&h, handle64, sizeof(h));
@@ -236,7 +240,8 @@ int aecf_peer_allreduce(const aecf_peer_desc* d, void* const* peer_data, void* c
         p.flags[r] = static_cast<uint32_t*>(peer_flags[r]);
     }
     p.count = d->count; p.world = d->world; p.rank = d->rank; p.average = d->average;
-    int rc = use_device(d->device);
+    DeviceScope device_scope__(d->device);
+    int rc = device_scope__.rc;
     if (rc != AECF_OK) return rc;
     // enough CTAs to keep a bucket's worth of 16-byte peer loads in flight, few enough that W ranks emulated on ONE
     // device (the single-GPU test) are all resident at once

@@ -70,15 +70,16 @@ pool_bwd_kernel(const PoolParams p) {
         const bool row_ok = row_raw < p.B;
         const long long row = row_ok ? row_raw : p.B - 1;
         if (!FOLD && !p.q_shared) Core::load_query(p, row, c0, qs);
+        const long long src = source_row(p, row);          // where the row's sample lives in kv / scores / d_ctx / d_kv
 
-        const char* kv_row = static_cast<const char*>(p.kv) + Core::row_offset(p, row, c0);
-        char* dkv_row = static_cast<char*>(p.d_kv) + Core::drow_offset(p, row, c0);
+        const char* kv_row = static_cast<const char*>(p.kv) + Core::row_offset(p, src, c0);
+        char* dkv_row = static_cast<char*>(p.d_kv) + Core::drow_offset(p, src, c0);
         auto valid = [&](int j) { return c0 + 32 * j < p.NC; };
 
         // upstream gradient of the context and the values, issued first
         uint4 dcraw[J];
         {
-            const char* dc = static_cast<const char*>(p.d_ctx) + static_cast<size_t>(row) * p.D * sizeof(T)
+            const char* dc = static_cast<const char*>(p.d_ctx) + static_cast<size_t>(src) * p.D * sizeof(T)
                              + static_cast<size_t>(c0) * 16;
 #pragma unroll
             for (int j = 0; j < J; ++j) dcraw[j] = valid(j) ? ldg_stream(dc + j * 512) : make_uint4(0, 0, 0, 0);
@@ -97,7 +98,7 @@ pool_bwd_kernel(const PoolParams p) {
         unsigned keep;
         if constexpr (FOLD) {
             float s[M][J];
-            Core::load_scores(p, row, c0, s);
+            Core::load_scores(p, src, c0, s);
             Core::softmax_dropout(p, rng, row, c0, s, w, wd, keep);
         } else {
             Core::attention_weights(
@@ -194,7 +195,7 @@ pool_bwd_kernel(const PoolParams p) {
             // ---- score gradients next to dV: column D + head of the (row, m) line of d_kv; the first lane of
             // each head writes it, lanes 0 .. HSP-H-1 of the sample's first warp zero the padding columns
             if (row_ok) {
-                T* line = reinterpret_cast<T*>(static_cast<char*>(p.d_kv) + static_cast<size_t>(row) * p.dkv_sb * sizeof(T)) + p.D;
+                T* line = reinterpret_cast<T*>(static_cast<char*>(p.d_kv) + static_cast<size_t>(src) * p.dkv_sb * sizeof(T)) + p.D;
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
                     const int c = c0 + 32 * j;

@@ -52,6 +52,10 @@ struct PoolParams {
     void* d_kv;
     void* d_q;
     float* partials;                        // [grid][3][D] fp32: dq | dbv | dbk
+    // Row indirection (aecf_pool_desc::row_index): row i of this call -- its Philox row, its info outputs, d_pooled /
+    // d_entropy -- is SAMPLE row_index[i] of the kv / scores / ctx / d_ctx / d_kv buffers (the reference's x-ray model pools
+    // only the rows where both modalities are present, xrays/train_xrays_example.py:202-222).  Null: the identity.
+    const long long* row_index;
     // fused CurriculumMasking.entropy_loss (streaming forward kernel only; include/aecf_b200.h aecf_pool_desc::loss_out)
     float* loss_out;                        // [1], or null
     float* loss_partials;                   // [gridDim.x] per-CTA sums of (scrubbed entropy - target)^2
@@ -76,6 +80,10 @@ struct MultiQuery {
     const float* bias;                      // additive score bias (PoolParams::bias stays null in this mode) ...
     long long bias_sb, bias_sh, bias_ss;    // ... element (b, h, s, m) at b*bias_sb + h*bias_sh + s*bias_ss + m
 };
+
+__device__ __forceinline__ long long source_row(const PoolParams& p, long long row) {
+    return p.row_index != nullptr ? __ldg(p.row_index + row) : row;
+}
 
 template <typename T, int M, int J, bool DROP>
 struct PoolCore {

@@ -106,8 +106,9 @@ pool_fwd_kernel(const PoolParams p) {
     const int c0 = slice * Core::CPW + lane;
     pdl_wait();
     const RngKey rng = effective_rng(p.rng, p.rng_state);
+    const long long src = source_row(p, row);              // where the row's sample lives in kv / scores / ctx
 
-    const char* kv_row = static_cast<const char*>(p.kv) + Core::row_offset(p, row, c0);
+    const char* kv_row = static_cast<const char*>(p.kv) + Core::row_offset(p, src, c0);
     auto load_kv = [&](int m, int half, int j) -> uint4 {
         return (c0 + 32 * j < p.NC) ? ldg_stream(kv_row + Core::kv_rel(p, m, half, j)) : make_uint4(0, 0, 0, 0);
     };
@@ -127,7 +128,7 @@ pool_fwd_kernel(const PoolParams p) {
     unsigned keep;
     if constexpr (FOLD) {
         float s[M][J];
-        Core::load_scores(p, row, c0, s);
+        Core::load_scores(p, src, c0, s);
         Core::softmax_dropout(p, rng, row, c0, s, w, wd, keep);
     } else {
         float qs[J][V];
@@ -156,7 +157,7 @@ pool_fwd_kernel(const PoolParams p) {
         }
     }
     if (row_ok) {
-        char* ctx = static_cast<char*>(p.ctx) + static_cast<size_t>(row) * p.D * sizeof(T) + static_cast<size_t>(c0) * 16;
+        char* ctx = static_cast<char*>(p.ctx) + static_cast<size_t>(src) * p.D * sizeof(T) + static_cast<size_t>(c0) * 16;
 #pragma unroll
         for (int j = 0; j < J; ++j)
             if (c0 + 32 * j < p.NC) stg_vec(ctx + j * 512, Vec<T>::pack(acc[j]));

@@ -53,6 +53,8 @@ class PoolConfig:
     side: Optional["SideStream"] = None
     # data-parallel, folded path: sum the raw gradient sums over the ranks inside the backward (aecf_b200.dp.FusedGradSum)
     dp: Optional[object] = None
+    # int64 [nb] device tensor: pool only these samples of the batch, in place (aecf_pool_desc::row_index)
+    sample_index: Optional[torch.Tensor] = None
 
 
 class SideStream:
@@ -104,13 +106,16 @@ class FusedPoolFunction(torch.autograd.Function):
         hs, hsp = ops.fold_score_cols(dt, H)
         S = int(cfg.tgt_len)
         R = B * S                       # query rows (b, s): b-major for batch-first input, s-major for sequence-first
+        index = cfg.sample_index
+        NB = B if index is None else int(index.numel())        # rows the pool kernels and the info outputs see
         desc = ops.make_pool_desc(
-            dev, dt, batch=B, num_tokens=M, embed_dim=D, num_heads=cfg.num_heads, training=cfg.training,
+            dev, dt, batch=NB, num_tokens=M, embed_dim=D, num_heads=cfg.num_heads, training=cfg.training,
             masking=cfg.masking, min_active=cfg.min_active, q_is_shared=cfg.q_shared,
             base_mask_prob=cfg.base_mask_prob, entropy_target=cfg.entropy_target, dropout_p=cfg.dropout_p,
             seed=cfg.seed, offset=cfg.offset, row0=cfg.row0, bias_strides=cfg.bias_strides, kv_strides=kv_strides,
             fold_key=fold, rng_state=cfg.rng_state, tgt_len=S,
-            q_strides=(1, B) if (S > 1 and cfg.seq_first) else (0, 0))
+            q_strides=(1, B) if (S > 1 and cfg.seq_first) else (0, 0), row_index=index, src_rows=B if index is not None else 0)
+        IR = NB * S                                            # rows of the info tensors
 
         q_in = q_src.reshape(D) if cfg.q_shared else q_src.reshape(R, D)
         if not q_in.is_contiguous():
@@ -121,11 +126,11 @@ class FusedPoolFunction(torch.autograd.Function):
         folded_w = torch.empty((D + hsp, D), dtype=dt, device=dev) if fold else None
         attn = torch.empty((R, D), dtype=dt, device=dev)
         out = torch.empty((R, D), dtype=dt, device=dev)
-        pooled = torch.empty((R, M), dtype=torch.float32, device=dev)        # info tensors: rows b*S + s always
-        entropy = torch.empty((R,), dtype=torch.float32, device=dev)
-        mask_rate = torch.empty((R,), dtype=torch.float32, device=dev)
-        masked = torch.empty((R, M), dtype=torch.float32, device=dev)
-        bits = torch.empty((R if cfg.want_mask_bits else 0,), dtype=torch.uint8, device=dev)
+        pooled = torch.empty((IR, M), dtype=torch.float32, device=dev)       # info tensors: rows b*S + s always
+        entropy = torch.empty((IR,), dtype=torch.float32, device=dev)
+        mask_rate = torch.empty((IR,), dtype=torch.float32, device=dev)
+        masked = torch.empty((IR, M), dtype=torch.float32, device=dev)
+        bits = torch.empty((IR if cfg.want_mask_bits else 0,), dtype=torch.uint8, device=dev)
         loss = torch.empty((0,), dtype=torch.float32, device=dev)
         if cfg.loss_target is not None and cfg.masking == 1 and ops.pool_fwd_has_loss(desc, fold):
             loss = torch.empty((1,), dtype=torch.float32, device=dev)
@@ -146,6 +151,8 @@ class FusedPoolFunction(torch.autograd.Function):
         ctx.set_materialize_grads(False)
         ctx.shape = (B, M, D)
         ctx.query_rows = R
+        ctx.info_rows = IR
+        ctx.index = index
         ctx.q_shape = q_src.shape
         ctx.save_for_backward(q_in, key, value, in_w, in_b, out_w, out_b, qp, kv, attn, score_bias, scores, folded_w)
         desc.loss_out = desc.loss_workspace = None      # the descriptor is kept for the backward: no dangling pointers
@@ -173,10 +180,11 @@ class FusedPoolFunction(torch.autograd.Function):
                 g = g.to(dt).contiguous()
         d_pooled = None
         if g_pooled is not None:
-            d_pooled = g_pooled.reshape(R, M).to(torch.float32).contiguous()
+            d_pooled = g_pooled.reshape(ctx.info_rows, M).to(torch.float32).contiguous()
         d_entropy = None
         if g_entropy is not None and cfg.masking == 2:
-            d_entropy = g_entropy.reshape(R).to(torch.float32).contiguous()
+            d_entropy = g_entropy.reshape(ctx.info_rows).to(torch.float32).contiguous()
+        ctx.desc.row_index = None if ctx.index is None else ctx.index.data_ptr()     # (kept alive by ctx.index)
 
         new = lambda shape, dtype=dt: torch.empty(shape, dtype=dtype, device=dev)
         # folded: rows of d_kv are [dV (D) | ds (HSP)]
@@ -280,3 +288,44 @@ class EntropyFunction(torch.autograd.Function):
         (w2,) = ctx.saved_tensors
         d = ops.entropy_bwd(w2, g.reshape(-1).to(torch.float32).contiguous())
         return d.reshape(ctx.shape).to(ctx.dtype)
+
+
+class SdpaFunction(torch.autograd.Function):
+    """The projection-free single-head attention of the functional fast path (reference aecf/AECFLayer.py:556-581),
+    differentiable like the reference's: the backward recomputes the weights (two kernels, nothing stored)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v):
+        ctx.save_for_backward(q, k, v)
+        return ops.sdpa_fwd(q, k, v)
+
+    @staticmethod
+    def backward(ctx, g):
+        q, k, v = ctx.saved_tensors
+        d_q, d_k, d_v = ops.sdpa_bwd(q, k, v, g.to(q.dtype).contiguous())
+        return (d_q if ctx.needs_input_grad[0] else None, d_k if ctx.needs_input_grad[1] else None,
+                d_v if ctx.needs_input_grad[2] else None)
+
+
+class CurriculumMaskFunction(torch.autograd.Function):
+    """Stand-alone training-mode CurriculumMasking.forward on user weights (reference aecf/AECFLayer.py:168-283): the
+    masked, renormalised weights keep their graph like the reference's ``final_weights``; entropy and mask_rate do not."""
+
+    @staticmethod
+    def forward(ctx, weights, base_mask_prob: float, min_active: int, seed: int, offset: int):
+        w2 = weights.detach().reshape(-1, weights.shape[-1]).to(torch.float32).contiguous()
+        masked, entropy, mask_rate = ops.curriculum_mask(w2, 1, base_mask_prob=base_mask_prob, min_active=min_active,
+                                                         seed=seed, offset=offset)
+        ctx.save_for_backward(w2)
+        ctx.args = (base_mask_prob, min_active, seed, offset)
+        ctx.shape, ctx.dtype = weights.shape, weights.dtype
+        ctx.mark_non_differentiable(entropy, mask_rate)
+        return masked.reshape(weights.shape).to(weights.dtype), entropy, mask_rate
+
+    @staticmethod
+    def backward(ctx, g_masked, _g_entropy, _g_rate):
+        (w2,) = ctx.saved_tensors
+        base_mask_prob, min_active, seed, offset = ctx.args
+        g = g_masked.reshape(w2.shape).to(torch.float32).contiguous()
+        d = ops.curriculum_mask_bwd(w2, g, base_mask_prob=base_mask_prob, min_active=min_active, seed=seed, offset=offset)
+        return d.reshape(ctx.shape).to(ctx.dtype), None, None, None, None

@@ -24,7 +24,8 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .fused_pool import EntropyFunction, EntropyLossFunction, FusedPoolFunction, PoolConfig, SideStream
+from .fused_pool import (CurriculumMaskFunction, EntropyFunction, EntropyLossFunction, FusedPoolFunction, PoolConfig,
+                         SdpaFunction, SideStream)
 
 __all__ = ["CurriculumMasking", "MultimodalAttentionPool", "multimodal_attention_pool", "create_fusion_pool",
            "set_rng_state", "get_rng_state"]
@@ -152,8 +153,9 @@ class CurriculumMasking(nn.Module):
     def forward(self, weights: torch.Tensor) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
         """Standalone masking of caller-supplied weights (..., L), L <= 64 (reference :130-283).
 
-        Inside MultimodalAttentionPool this stage runs fused in the pool kernel instead.  The masked
-        weights returned here in training mode are detached.
+        Inside MultimodalAttentionPool this stage runs fused in the pool kernel instead.  The masked weights
+        returned here in training mode keep their graph, like the reference's ``final_weights`` (the mask itself and
+        the entropy carry no gradient).
         """
         ops.require_cuda(weights)
         lead, length = weights.shape[:-1], weights.shape[-1]
@@ -165,13 +167,11 @@ class CurriculumMasking(nn.Module):
             return weights, {"entropy": zeros, "mask_rate": zeros.clone(), "target_entropy": zeros.clone()}
         self._last_seq_len = length                                       # :187
         seed, offset = _rng.next(weights.device)
-        w2 = weights.detach().reshape(-1, length).to(torch.float32).contiguous()
-        masked, entropy, mask_rate = ops.curriculum_mask(
-            w2, 1, base_mask_prob=self.base_mask_prob, min_active=self.min_active, seed=seed, offset=offset)
+        masked, entropy, mask_rate = CurriculumMaskFunction.apply(weights, self.base_mask_prob, self.min_active, seed, offset)
         entropy = entropy.reshape(lead).to(weights.dtype)
         info = {"entropy": entropy, "mask_rate": mask_rate.reshape(lead).to(weights.dtype),
                 "target_entropy": torch.full_like(entropy, math.log(float(length)) * self.entropy_target)}
-        return masked.reshape(weights.shape).to(weights.dtype), info
+        return masked, info
 
     def _loss_target(self) -> float:
         seq_len = getattr(self, "_last_seq_len", 2)
@@ -357,8 +357,14 @@ class MultimodalAttentionPool(nn.Module):
 
     def forward(self, query: torch.Tensor, key: torch.Tensor, value: Optional[torch.Tensor] = None,
                 key_padding_mask: Optional[torch.Tensor] = None, attn_mask: Optional[torch.Tensor] = None,
-                return_info: bool = False, use_checkpoint: bool = False,
+                return_info: bool = False, use_checkpoint: bool = False, sample_index: Optional[torch.Tensor] = None,
                 ) -> Union[torch.Tensor, Tuple[torch.Tensor, Dict[str, Any]]]:
+        """Same arguments as the reference (``aecf/AECFLayer.py:409-418``) plus one extension, ``sample_index``: a 1-D integer
+        tensor of DISTINCT batch indices.  Only those samples are pooled -- exactly as if the reference had been called on
+        ``query[idx], key[idx]`` (same Philox rows, info tensors of ``len(idx)`` rows) -- but in place: the output keeps the
+        full batch layout ``[B, 1, D]``, rows of unlisted samples hold ``out_proj.bias`` (the projection of a zero context; mask
+        them, e.g. with ``torch.where``) and get no gradient.  This is the reference x-ray model's gather -> pool -> scatter
+        (``xrays/train_xrays_example.py:202-222``) without the two indexing copies.  Needs the shared fusion query and no masks."""
         batch, tgt_len, tokens, embed = self._validate(query, key, value)
         if value is key:
             value = None
@@ -382,6 +388,15 @@ class MultimodalAttentionPool(nn.Module):
         key_c = key.contiguous()
         value_c = None if value is None else value.contiguous()
         bias, bias_strides = self._score_bias(key_padding_mask, attn_mask, batch, tokens, key.device, tgt_len)
+        index = None
+        if sample_index is not None:
+            if not q_shared or multi or bias is not None or not self.batch_first:
+                raise ops._lib.UnsupportedShapeError(
+                    ops._lib.ERR_UNSUPPORTED, "MultimodalAttentionPool",
+                    "sample_index needs the shared fusion query (an expand of one [1, 1, D] tensor), batch_first and no masks")
+            if sample_index.dim() != 1 or sample_index.dtype not in (torch.int64, torch.int32) or sample_index.device != key.device:
+                raise ValueError("sample_index must be a 1-D int64 / int32 tensor on the inputs' device")
+            index = sample_index.to(torch.int64).contiguous()
 
         cm = self.curriculum_masking
         fused_cm = cm is not None and type(cm).forward is CurriculumMasking.forward
@@ -411,24 +426,25 @@ class MultimodalAttentionPool(nn.Module):
             tgt_len=tgt_len, grad_ready=self._grad_ready, grad_buffers=self._grad_buffers,
             grad_ready_early=bool(self._grad_ready_early),
             loss_target=cm._loss_target() if (masking == 1 and return_info and os.environ.get("AECF_FUSED_LOSS", "1") != "0") else None,
-            side=self._side_stream(key.device) if fold else None, dp=self._dp)
+            side=self._side_stream(key.device) if fold else None, dp=self._dp, sample_index=index)
+        info_rows = batch if index is None else int(index.numel())
         out, pooled, entropy, mask_rate, masked, bits, fused_loss = FusedPoolFunction.apply(
             q_src, key_c, value_c, att.in_proj_weight, att.in_proj_bias, att.out_proj.weight, att.out_proj.bias,
             bias, cfg)
 
         attn_output = out.reshape(batch, tgt_len, embed) if self.batch_first else out.reshape(tgt_len, batch, embed)
-        pooled_weights = pooled.reshape(batch, tgt_len, tokens)         # [B, S, M] whatever batch_first (functional.py:6657)
+        pooled_weights = pooled.reshape(info_rows, tgt_len, tokens)     # [B, S, M] whatever batch_first (functional.py:6657)
         info: Dict[str, Any] = {}
         if cm is not None:
             if fused_cm:
-                info["entropy"] = entropy.reshape(batch, tgt_len)
+                info["entropy"] = entropy.reshape(info_rows, tgt_len)
                 if fused_loss.numel() == 1:             # entropy_loss(info['entropy']) is already known: see there
                     info["entropy"]._aecf_fused_loss = (info["entropy"]._version, cfg.loss_target, fused_loss)
-                info["mask_rate"] = mask_rate.reshape(batch, tgt_len)
+                info["mask_rate"] = mask_rate.reshape(info_rows, tgt_len)
                 if cm.training:                                         # eval mode has no target (:153-156)
                     target = math.log(float(tokens)) * cm.entropy_target if tokens > 1 else 0.0
                     info["target_entropy"] = torch.full_like(info["entropy"], target)
-                masked_weights = masked.reshape(batch, tgt_len, tokens)
+                masked_weights = masked.reshape(info_rows, tgt_len, tokens)
             else:
                 masked_weights, mask_info = cm(pooled_weights)          # user-overridden forward (README.md:341-350)
                 info.update(mask_info)
@@ -436,7 +452,7 @@ class MultimodalAttentionPool(nn.Module):
             if return_info:
                 info["masked_attention_weights"] = masked_weights.detach()
                 if self._want_mask_bits:
-                    info["mask_bits"] = bits.reshape(batch, tgt_len) if multi else bits
+                    info["mask_bits"] = bits.reshape(info_rows, tgt_len) if multi else bits
         elif return_info:
             info["attention_weights"] = pooled_weights
         if return_info:
@@ -455,7 +471,7 @@ def multimodal_attention_pool(query: torch.Tensor, key: torch.Tensor, value: Opt
     """Functional interface (reference ``aecf/AECFLayer.py:584-652``).
 
     Fast path (eval, single head, no masking, no dropout): projection-free scaled dot-product
-    attention, one kernel, any source/target length, forward only.  Otherwise a freshly initialised
+    attention, one kernel, any source/target length; differentiable (a two-kernel recompute backward).  Otherwise a freshly initialised
     :class:`MultimodalAttentionPool` is built per call, as in the reference -- but on the inputs'
     device and dtype (the reference builds it on CPU/fp32 and cannot take CUDA inputs; quirk D6).
     """
@@ -467,7 +483,9 @@ def multimodal_attention_pool(query: torch.Tensor, key: torch.Tensor, value: Opt
         ops.require_cuda(query, key, value)
         if query.dim() != 3 or key.dim() != 3 or value.dim() != 3:
             raise ValueError("expected 3D query, key and value tensors")
-        return ops.sdpa_fwd(query.contiguous(), key.contiguous(), value.contiguous())
+        if query.dtype != key.dtype or query.dtype != value.dtype:
+            raise RuntimeError(f"expected query/key/value of one dtype, got {query.dtype}/{key.dtype}/{value.dtype}")
+        return SdpaFunction.apply(query.contiguous(), key.contiguous(), value.contiguous())
     pool = MultimodalAttentionPool(embed_dim=embed_dim, num_heads=num_heads, dropout=dropout,
                                    curriculum_masking=curriculum_masking, batch_first=True,
                                    device=query.device, dtype=query.dtype)

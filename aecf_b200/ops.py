@@ -118,7 +118,8 @@ def make_pool_desc(dev: torch.device, dtype: torch.dtype, *, batch: int, num_tok
                    kv_strides: Tuple[int, int] = (0, 0), fold_key: bool = False,
                    rng_state: Optional[torch.Tensor] = None, tgt_len: int = 1,
                    q_strides: Tuple[int, int] = (0, 0), loss_out: Optional[torch.Tensor] = None,
-                   loss_workspace: Optional[torch.Tensor] = None, loss_target: float = 0.0) -> _lib.PoolDesc:
+                   loss_workspace: Optional[torch.Tensor] = None, loss_target: float = 0.0,
+                   row_index: Optional[torch.Tensor] = None, src_rows: int = 0) -> _lib.PoolDesc:
     """``bias_strides`` = (batch, head[, query]) element strides of the additive score bias; ``tgt_len`` > 1 and
     ``q_strides`` (rows of query (b, s): b*q_strides[0] + s*q_strides[1]) describe several queries per sample."""
     return _lib.PoolDesc(device=dev.index or 0, dtype=dtype_code(dtype), batch=batch, num_tokens=num_tokens,
@@ -133,7 +134,8 @@ def make_pool_desc(dev: torch.device, dtype: torch.dtype, *, batch: int, num_tok
                          bias_stride_s=bias_strides[2] if len(bias_strides) > 2 else 0,
                          loss_out=None if loss_out is None else loss_out.data_ptr(),
                          loss_workspace=None if loss_workspace is None else loss_workspace.data_ptr(),
-                         loss_target=float(loss_target))
+                         loss_target=float(loss_target),
+                         row_index=None if row_index is None else row_index.data_ptr(), src_rows=int(src_rows))
 
 
 def fold_score_cols(dtype: torch.dtype, num_heads: int) -> Tuple[int, int]:
@@ -232,6 +234,19 @@ def sdpa_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def sdpa_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, d_out: torch.Tensor):
+    dev = require_cuda(q, k, v, d_out)
+    B, S, D = q.shape
+    T = k.shape[1]
+    d_q, d_k, d_v = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    ws = torch.empty(2 * B * S, dtype=torch.float32, device=dev)
+    rc = _lib.load().aecf_sdpa_bwd(dev.index or 0, dtype_code(q.dtype), q.data_ptr(), k.data_ptr(), v.data_ptr(), d_out.data_ptr(),
+                                   d_q.data_ptr(), d_k.data_ptr(), d_v.data_ptr(), ws.data_ptr(), ws.numel() * 4, B, S, T, D,
+                                   _stream(dev))
+    _lib.check(rc, f"aecf_sdpa_bwd B={B} S={S} T={T} D={D}")
+    return d_q, d_k, d_v
+
+
 def curriculum_mask(weights2d: torch.Tensor, mode: int, *, base_mask_prob: float = 0.15, min_active: int = 1,
                     seed: int = 0, offset: int = 0, row0: int = 0, want_masked: bool = True):
     """Standalone masking stage on fp32 [rows, len] weights.  Returns (masked or None, entropy, mask_rate)."""
@@ -246,6 +261,18 @@ def curriculum_mask(weights2d: torch.Tensor, mode: int, *, base_mask_prob: float
                                           mask_rate.data_ptr(), _stream(dev))
     _lib.check(rc, f"aecf_curriculum_mask rows={rows} len={length}")
     return masked, entropy, mask_rate
+
+
+def curriculum_mask_bwd(weights2d: torch.Tensor, d_masked: torch.Tensor, *, base_mask_prob: float, min_active: int, seed: int,
+                        offset: int, row0: int = 0) -> torch.Tensor:
+    dev = require_cuda(weights2d, d_masked)
+    rows, length = weights2d.shape
+    d_w = torch.empty_like(weights2d)
+    rc = _lib.load().aecf_curriculum_mask_bwd(dev.index or 0, weights2d.data_ptr(), rows, length, float(base_mask_prob),
+                                              int(min_active), seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFF, row0,
+                                              d_masked.data_ptr(), d_w.data_ptr(), _stream(dev))
+    _lib.check(rc, "aecf_curriculum_mask_bwd")
+    return d_w
 
 
 def entropy_bwd(weights2d: torch.Tensor, d_entropy: torch.Tensor) -> torch.Tensor:

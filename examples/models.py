@@ -67,6 +67,10 @@ class XrayFusionModel(nn.Module):
         self.fusion_proj = nn.Linear(hidden_dim, hidden_dim * 2)
         self.classifier = nn.Sequential(nn.Linear(hidden_dim * 2, hidden_dim), nn.ReLU(), nn.Dropout(encoder_dropout),
                                         nn.Linear(hidden_dim, num_classes))
+        import inspect
+        # aecf_b200's pool can take the both-present rows as an index list and pool them IN PLACE (no gather before, no
+        # scatter after); the reference's API (and the oracle stand-in of the parity tests) cannot
+        self._in_place = "sample_index" in inspect.signature(self.attention_pool.forward).parameters
 
     def toggle_curriculum(self, enabled: bool) -> None:
         """The reference swaps the pool's masking module at epoch 40 (xrays/train_xrays_example.py:179-187)."""
@@ -80,8 +84,18 @@ class XrayFusionModel(nn.Module):
         txt_present = text_features.norm(dim=1) > 1e-6
         fused = torch.zeros(image_features.size(0), self.hidden_dim * 2, device=image_features.device, dtype=img.dtype)
 
-        both = torch.where(img_present & txt_present)[0]
-        if both.numel():
+        both_mask = img_present & txt_present
+        both = torch.where(both_mask)[0]
+        if both.numel() and self._in_place:
+            # the pool reads the listed rows of the full token buffer and writes their outputs to the same rows of a full-size
+            # output: what reference xrays/train_xrays_example.py:212-222 does with img[both] / txt[both] / fused[both] = ...
+            tokens = torch.stack([img, txt], dim=1)
+            query = self.fusion_query.expand(tokens.size(0), -1, -1)
+            pooled, pool_info = self.attention_pool(query=query, key=tokens, value=tokens, return_info=True, sample_index=both)
+            fused = torch.where(both_mask.unsqueeze(1), self.fusion_proj(pooled.squeeze(1)), fused)
+            if return_info:
+                info.update(pool_info)
+        elif both.numel():
             tokens = torch.stack([img[both], txt[both]], dim=1)                  # the variable-size both-present subset
             query = self.fusion_query.expand(both.numel(), -1, -1)
             pooled, pool_info = self.attention_pool(query=query, key=tokens, value=tokens, return_info=True)

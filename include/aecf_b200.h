@@ -109,6 +109,15 @@ typedef struct aecf_pool_desc {
     void*    loss_workspace;  /* aecf_pool_loss_workspace_bytes() bytes, zeroed ONCE by the caller (the kernel re-arms it) */
     float    loss_target;     /* entropy_target * log(_last_seq_len), the value CurriculumMasking.entropy_loss would use */
     int32_t  reserved0;
+    /* Row indirection (reference xrays/train_xrays_example.py:202-222 gathers the rows where both modalities are present,
+     * pools them and scatters the result back; here the pool kernels do both ends themselves).  With row_index non-null,
+     * `batch` counts the LISTED rows: row i of this call -- its Philox row (row0 + i), its pooled / entropy / mask_rate /
+     * masked / mask_bits outputs, its d_pooled / d_entropy -- is sample row_index[i] of kv / scores / ctx / d_ctx / d_kv, which
+     * keep their full-batch layout of `src_rows` samples.  ctx rows of unlisted samples are zeroed by the whole-step forward,
+     * their d_kv rows by the whole-step backward, so the products around the pool simply run over all src_rows samples.
+     * Needs a shared query (q_is_shared), one query per sample, no score_bias. */
+    const int64_t* row_index; /* [batch] DEVICE, distinct values in [0, src_rows); null: the identity */
+    int64_t  src_rows;        /* samples in the buffers when row_index is set */
 } aecf_pool_desc;
 
 /* Several queries per sample (tgt_len = S > 1; reference aecf/AECFLayer.py:415 takes any [B, S, D] query).  Every
@@ -257,6 +266,12 @@ AECF_API int aecf_entropy_loss_bwd(int32_t device, const float* entropy, int64_t
 AECF_API int aecf_curriculum_mask(int32_t device, const float* weights, int64_t rows, int32_t len, int32_t mode,
                                   float base_mask_prob, int32_t min_active, uint64_t seed, uint64_t offset,
                                   uint64_t row0, float* masked, float* entropy, float* mask_rate, void* stream);
+/* Backward of the mode-1 call: d_weights [rows, len] for d_masked [rows, len].  The mask is REDRAWN from the same
+ * (seed, offset, row0); mask, top-k repair set and entropy carry no gradient, the renormalisations do (the reference's
+ * final_weights = weights * mask / sum keeps its graph, aecf/AECFLayer.py:262-272). */
+AECF_API int aecf_curriculum_mask_bwd(int32_t device, const float* weights, int64_t rows, int32_t len, float base_mask_prob,
+                                      int32_t min_active, uint64_t seed, uint64_t offset, uint64_t row0,
+                                      const float* d_masked, float* d_weights, void* stream);
 /* d_weights = d_entropy * d clamp(-sum xlogy(w, w), 0, log len) / d w */
 AECF_API int aecf_entropy_bwd(int32_t device, const float* weights, int64_t rows, int32_t len,
                               const float* d_entropy, float* d_weights, void* stream);
@@ -265,6 +280,11 @@ AECF_API int aecf_entropy_bwd(int32_t device, const float* weights, int64_t rows
  * (reference aecf/AECFLayer.py:556-581): out[b, s, :] = softmax_t(q[b,s]·k[b,t] / sqrt(D)) · v[b,t]. */
 AECF_API int aecf_sdpa_fwd(int32_t device, int32_t dtype, const void* q, const void* k, const void* v, void* out,
                   int64_t batch, int32_t tgt_len, int32_t src_len, int32_t embed_dim, void* stream);
+/* Its backward (the reference's function is plain differentiable torch): d_q [B, tgt, D], d_k / d_v [B, src, D] for
+ * d_out [B, tgt, D]; nothing is stored by the forward, the weights are recomputed.  workspace >= 2 * B * tgt_len floats. */
+AECF_API int aecf_sdpa_bwd(int32_t device, int32_t dtype, const void* q, const void* k, const void* v, const void* d_out,
+                  void* d_q, void* d_k, void* d_v, void* workspace, size_t workspace_bytes, int64_t batch,
+                  int32_t tgt_len, int32_t src_len, int32_t embed_dim, void* stream);
 
 /* ---- whole-step entry points -------------------------------------------------------------
  * The complete forward and backward of MultimodalAttentionPool (reference aecf/AECFLayer.py:515-541 and

@@ -230,6 +230,7 @@ void run_grid(const std::function<void()>& body, dim3 grid, dim3 block_dim, size
 // ---- the CUDA runtime entry points the host code of the library calls ------------------------------------------
 extern "C" {
 cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 cudaError_t cudaGetLastError(void) { return cudaSuccess; }
 const char* cudaGetErrorName(cudaError_t) { return "cudaEmu"; }
 const char* cudaGetErrorString(cudaError_t) { return "host emulation"; }

@@ -116,6 +116,17 @@ def test_entropy_loss_comes_out_of_the_forward_kernel():
     P.test_entropy_loss_comes_out_of_the_forward_kernel()
 
 
+@pytest.mark.parametrize("shape", [(6, 2, 5, 64), (3, 1, 3, 512), (4, 7, 9, 136)], ids=lambda s: "x".join(map(str, s)))
+def test_functional_fast_path_is_differentiable(shape):
+    P.test_functional_fast_path_is_differentiable(shape)
+
+
+@pytest.mark.parametrize("dtype,fold", [(torch.float32, False), (torch.float32, True), (torch.bfloat16, True), (torch.bfloat16, False)],
+                         ids=["fp32_unfolded", "fp32_folded", "bf16_folded", "bf16_unfolded"])
+def test_sample_index_pools_the_listed_rows_in_place(dtype, fold):
+    P.test_sample_index_pools_the_listed_rows_in_place(dtype, fold)
+
+
 def test_full_size_test_body_on_a_small_batch():
     """The body of the B = 65 536 GPU test (tests/test_gpu_parity.py) on 192 rows, so that the test itself is tested."""
     P.test_full_size_bf16_folded_against_oracle(P.Case("small_d512_h8_m3", B=192, M=3, D=512, H=8, dropout=0.1, pooled_grad=True,

@@ -659,6 +659,51 @@ def test_entropy_loss_comes_out_of_the_forward_kernel():
             ops.entropy_loss_fwd = plain
 
 
+@pytest.mark.parametrize("dtype,fold", [(torch.float32, False), (torch.float32, True), (torch.bfloat16, True), (torch.bfloat16, False)],
+                         ids=["fp32_unfolded", "fp32_folded", "bf16_folded", "bf16_unfolded"])
+def test_sample_index_pools_the_listed_rows_in_place(dtype, fold):
+    """pool(query, x, sample_index=idx) against pool(query[idx], x[idx]) -- the reference x-ray model's gather -> pool ->
+    scatter (xrays/train_xrays_example.py:202-222): same Philox rows, same info tensors, the same output rows at their places
+    in the full batch, the same input gradients there and none anywhere else, the same parameter gradients."""
+    case = CASES_BY_NAME["d64_h8_m3_dropout"]
+    inp = build_inputs(case)
+    B = case.B
+    idx = torch.tensor([b for b in range(B) if (b * 7 + 3) % 5 not in (0, 1)], device=DEV)       # an irregular 3/5 of the rows
+    g = inp["grad_out"].to(DEV, dtype)
+    runs = {}
+    for mode in ("gathered", "in_place"):
+        pool, cm = make_pool(case, inp, dtype, fold)
+        q = torch.nn.Parameter(inp["query0"].to(DEV, dtype))
+        x = inp["x"].to(DEV, dtype).requires_grad_(True)
+        aecf_b200.set_rng_state(PHILOX_SEED, case.offset)
+        if mode == "gathered":
+            out, info = pool(q.expand(idx.numel(), -1, -1), x[idx], return_info=True)
+            loss = (out.float() * g[idx].float()).sum()
+        else:
+            out, info = pool(q.expand(B, -1, -1), x, return_info=True, sample_index=idx)
+            assert out.shape == (B, 1, case.D)
+            out = out[idx]                                       # (the test looks at the listed rows; a model would mask)
+            loss = (out.float() * g[idx].float()).sum()
+        (loss + (info["attention_weights"] * 0.3).sum()).backward()
+        aecf_b200.set_rng_state(None)
+        torch.cuda.synchronize()
+        runs[mode] = dict(out=out.detach(), info={k: v.detach() for k, v in info.items()}, gx=x.grad,
+                          gw=pool.attention.in_proj_weight.grad, gb=pool.attention.in_proj_bias.grad,
+                          gwo=pool.attention.out_proj.weight.grad, gbo=pool.attention.out_proj.bias.grad, gq=q.grad)
+    a, b = runs["gathered"], runs["in_place"]
+    assert torch.equal(a["out"], b["out"])
+    for k in a["info"]:
+        assert a["info"][k].shape == b["info"][k].shape and torch.equal(a["info"][k], b["info"][k]), k
+    assert torch.equal(a["gx"][idx], b["gx"][idx])
+    others = torch.ones(B, dtype=torch.bool, device=DEV)
+    others[idx] = False
+    assert float(b["gx"][others].abs().max()) == 0.0
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    for k in ("gw", "gb", "gwo", "gbo", "gq"):
+        scale = float(a[k].float().abs().max())
+        assert_close(k, b[k].float().cpu(), a[k].float().cpu(), tol, atol=tol * scale)
+
+
 def test_unsupported_shapes_fail_loudly():
     pool = aecf_b200.MultimodalAttentionPool(64, num_heads=4, device=DEV)
     x = torch.randn(4, 3, 64, device=DEV)
@@ -686,6 +731,34 @@ def test_functional_fast_path_and_module_path():
     assert y.shape == (8, 1, 64) and y.is_cuda and torch.isfinite(y).all()
 
 
+@pytest.mark.parametrize("shape", [(6, 2, 5, 64), (3, 1, 3, 512), (4, 7, 9, 136)], ids=lambda s: "x".join(map(str, s)))
+def test_functional_fast_path_is_differentiable(shape):
+    """reference aecf/AECFLayer.py:573-581 is plain torch, so gradients flow to query, key and value; here a recompute
+    backward (aecf_sdpa_bwd) against autograd through the oracle's restatement -- also with key is value."""
+    B, S, T, D = shape
+    qc = torch.from_numpy(philox.normal(11, (B, S, D))).float()
+    kc = torch.from_numpy(philox.normal(12, (B, T, D))).float()
+    vc = torch.from_numpy(philox.normal(13, (B, T, D))).float()
+    gc = torch.from_numpy(philox.normal(14, (B, S, D))).float()
+    for dtype, tol in ((torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)):
+        if dtype == torch.bfloat16 and D % 8:
+            continue
+        ref_in = [t.to(dtype).float().requires_grad_(True) for t in (qc, kc, vc)]
+        (oracle.sdpa_single_head(*ref_in) * gc.to(dtype).float()).sum().backward()
+        ours = [t.to(DEV, dtype).requires_grad_(True) for t in (qc, kc, vc)]
+        out = aecf_b200.multimodal_attention_pool(ours[0], ours[1], ours[2])
+        assert out.requires_grad
+        (out.float() * gc.to(DEV, dtype).float()).sum().backward()
+        for name, a, b in zip(("d_query", "d_key", "d_value"), ours, ref_in):
+            assert_close(name, a.grad.float().cpu(), b.grad, tol)
+        kv = kc.to(DEV, dtype).requires_grad_(True)                   # value=None: key is value, the two gradients add up
+        q2 = qc.to(DEV, dtype).requires_grad_(True)
+        (aecf_b200.multimodal_attention_pool(q2, kv).float() * gc.to(DEV, dtype).float()).sum().backward()
+        rk = kc.to(dtype).float().requires_grad_(True)
+        (oracle.sdpa_single_head(qc.to(dtype).float(), rk, rk) * gc.to(dtype).float()).sum().backward()
+        assert_close("d_key (key is value)", kv.grad.float().cpu(), rk.grad, tol)
+
+
 def test_standalone_masking_and_entropy():
     cm = aecf_b200.CurriculumMasking(base_mask_prob=0.9, min_active=2).to(DEV)
     w = torch.softmax(2 * torch.from_numpy(philox.normal(5, (257, 10))).float(), -1)
@@ -700,6 +773,19 @@ def test_standalone_masking_and_entropy():
     assert_close("masked", masked.cpu(), ref["masked"], FP32_TOL, atol=1e-6)
     assert_close("entropy", info["entropy"].cpu(), ref["entropy"], FP32_TOL, atol=1e-6)
     assert cm._last_seq_len == 10
+    # the masked weights keep their graph (reference :262-272: final_weights = weights * mask / sum); mask and entropy do not
+    g = torch.from_numpy(philox.normal(6, (257, 10))).float()
+    wg = (w * 3.0).to(DEV).requires_grad_(True)                  # unnormalised rows: the first renormalisation matters too
+    aecf_b200.set_rng_state(77, 5)
+    mg, ig = cm(wg)
+    aecf_b200.set_rng_state(None)
+    assert mg.requires_grad and not ig["entropy"].requires_grad and not ig["mask_rate"].requires_grad
+    (mg * g.to(DEV)).sum().backward()
+    wr = (w * 3.0).clone().requires_grad_(True)
+    keep = (ref["masked"] > 0).float()
+    wn = wr / wr.sum(-1, keepdim=True)
+    ((wn * keep / (wn * keep).sum(-1, keepdim=True)) * g).sum().backward()
+    assert_close("d masked / d weights", wg.grad.cpu(), wr.grad, FP32_TOL, atol=1e-6)
     # eval mode: weights pass through, entropy stays differentiable (reference :150-156)
     cm.eval()
     wd = w.to(DEV).requires_grad_(True)
