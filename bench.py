@@ -276,6 +276,50 @@ def time_reference_gpu_eager(args, dev, steps=10, warmup=3):
         return {"error": f"{type(e).__name__}: {e}"[:300]}
 
 
+def cublas_yardstick(args, dev, folded):
+    """torch.matmul (cuBLAS) on the six projection shapes of this workload, CUDA events, us per call, operand sets rotated
+    so that no call finds its operands in L2 -- a yardstick for `gemm_tensor_pipe`, not a path of this library: at K = 512
+    with 400 MB of traffic per product nobody reaches the 8192^3 rate the `peak` of that object quotes (profiles/
+    r2_gemm_where_the_time_goes.md)."""
+    import torch
+    if args.dtype != "bf16":
+        return None
+    try:
+        B, M, D = args.batch, args.tokens, args.dim
+        rows, kf = B * M, (D + 8 if folded else 2 * D)
+        bf = torch.bfloat16
+        rnd = lambda *shape: (torch.randn(*shape, device=dev) * 0.1).to(bf)
+
+        def timed(make, sets):
+            ops_ = [make() for _ in range(sets)]
+            for i in range(3):
+                ops_[i % sets]()
+            torch.cuda.synchronize(dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(10):
+                ops_[i % sets]()
+            b.record()
+            torch.cuda.synchronize(dev)
+            return a.elapsed_time(b) * 100.0          # ms / 10 calls -> us per call
+
+        def prod(a_shape, b_shape, ta=False, tb=False):
+            def make():
+                a, b = rnd(*a_shape), rnd(*b_shape)
+                return lambda: torch.matmul(a.t() if ta else a, b.t() if tb else b)
+            return make
+        out = {"kv_proj": timed(prod((rows, D), (kf if folded else 2 * D, D), tb=True), 2),
+               "out_proj": timed(prod((B, D), (D, D), tb=True), 4), "d_ctx": timed(prod((B, D), (D, D)), 4),
+               "d_out_weight": timed(prod((B, D), (B, D), ta=True), 4),
+               "d_x": timed(prod((rows, kf), (kf, D)), 2), "d_kv_weight": timed(prod((rows, kf), (rows, D), ta=True), 2)}
+        torch.cuda.empty_cache()
+        out["note"] = ("torch.matmul, bf16, same shapes" + (" (kv_proj with the 8 score rows as ordinary output columns)" if folded else "")
+                       + "; not a path of this library")
+        return out
+    except Exception as e:
+        return {"error": f"{type(e).__name__}: {e}"[:200]}
+
+
 def cpu_model():
     try:
         with open("/proc/cpuinfo") as f:
@@ -477,6 +521,11 @@ def run_b200(args):
         ms = start.elapsed_time(end) / args.steps
         launches = launches_per_step * args.steps if use_graph else (_lib.launch_count() - launches0)
         clear()
+        # region B measures each kernel ON ITS OWN: the gradient tail, which the timed step runs on a side stream next to the
+        # [dWv;R] and dX products, is serialised onto the compute stream here (next to a product its kernels take several
+        # times longer and the product a little longer -- durations that describe the overlap, not the kernels)
+        side_was = os.environ.get("AECF_SIDE_STREAM")
+        os.environ["AECF_SIDE_STREAM"] = "0"
         _lib.timing_enable(True)
         start_b, end_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         start_b.record()
@@ -484,6 +533,10 @@ def run_b200(args):
             step(xs[i % rot]); clear()
         end_b.record()
         barrier()
+        if side_was is None:
+            os.environ.pop("AECF_SIDE_STREAM", None)
+        else:
+            os.environ["AECF_SIDE_STREAM"] = side_was
     ms_with_events = start_b.elapsed_time(end_b) / args.steps
     kernels = kernel_averages(_lib.timing_collect(), args.steps)
     _lib.timing_enable(False)
@@ -651,7 +704,12 @@ def run_b200(args):
             "dtype": "bf16" if dtype == torch.bfloat16 else "f32", "data": "synthetic",
             "config": workload_config(args, world), "impl": "b200",
             "implementation": {"fold_key_projection": bool(args.folded),
-                               "cuda_graph": "step captured once with aecf_b200.graphs.GraphedStep and replayed" if use_graph else "eager"},
+                               "cuda_graph": "step captured once with aecf_b200.graphs.GraphedStep and replayed" if use_graph else "eager",
+                               "gradient_tail": ("on a side stream next to the [dWv;R] and dX products" if os.environ.get("AECF_SIDE_STREAM", "1") != "0"
+                                                 else "on the compute stream"),
+                               "entropy_loss": "fused into the pool forward kernel" if os.environ.get("AECF_FUSED_LOSS", "1") != "0" else "stand-alone kernel",
+                               "kernels_note": "`kernels`, `roofline*` and `gemm_tensor_pipe` are per-kernel durations with the gradient tail "
+                                               "serialised (each kernel on its own); `ms_per_step` / `value` is the overlapped, graph-replayed step"},
             "roofline": roof, "roofline_pool_fwd": hbm("pool_fwd", fwd_bytes),
             "pool_kernels_only": {"value": B / (pool_ms * 1e-3) if pool_ms else None, "unit": UNIT, "ms": pool_ms,
                                   "bytes_per_sample": (fwd_bytes + bwd_bytes) // B,
@@ -668,6 +726,7 @@ def run_b200(args):
         line["data_parallel"] = dp_info
 
     if world == 1 and not args.no_cpu_baseline:
+        line["gemm_yardstick_cublas_us"] = cublas_yardstick(args, dev, bool(args.folded))
         line["reference_gpu_eager"] = time_reference_gpu_eager(args, dev)
         cpu_value, cpu_ms, cores, kind, rows = time_cpu(args, args.cpu_sample or B, 3, 1, budget_s=40.0)
         line["cpu_baseline"] = {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": kind,

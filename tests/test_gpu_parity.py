@@ -743,18 +743,18 @@ def test_functional_fast_path_is_differentiable(shape):
     for dtype, tol in ((torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)):
         if dtype == torch.bfloat16 and D % 8:
             continue
-        ref_in = [t.to(dtype).float().requires_grad_(True) for t in (qc, kc, vc)]
+        ref_in = [t.to(dtype).float().clone().requires_grad_(True) for t in (qc, kc, vc)]     # clones: fresh leaves
         (oracle.sdpa_single_head(*ref_in) * gc.to(dtype).float()).sum().backward()
-        ours = [t.to(DEV, dtype).requires_grad_(True) for t in (qc, kc, vc)]
+        ours = [t.detach().to(DEV, dtype).clone().requires_grad_(True) for t in (qc, kc, vc)]
         out = aecf_b200.multimodal_attention_pool(ours[0], ours[1], ours[2])
         assert out.requires_grad
         (out.float() * gc.to(DEV, dtype).float()).sum().backward()
         for name, a, b in zip(("d_query", "d_key", "d_value"), ours, ref_in):
             assert_close(name, a.grad.float().cpu(), b.grad, tol)
-        kv = kc.to(DEV, dtype).requires_grad_(True)                   # value=None: key is value, the two gradients add up
-        q2 = qc.to(DEV, dtype).requires_grad_(True)
+        kv = kc.detach().to(DEV, dtype).clone().requires_grad_(True)  # value=None: key is value, the two gradients add up
+        q2 = qc.detach().to(DEV, dtype).clone().requires_grad_(True)
         (aecf_b200.multimodal_attention_pool(q2, kv).float() * gc.to(DEV, dtype).float()).sum().backward()
-        rk = kc.to(dtype).float().requires_grad_(True)
+        rk = kc.to(dtype).float().clone().requires_grad_(True)
         (oracle.sdpa_single_head(qc.to(dtype).float(), rk, rk) * gc.to(dtype).float()).sum().backward()
         assert_close("d_key (key is value)", kv.grad.float().cpu(), rk.grad, tol)
 
