@@ -385,7 +385,7 @@ AECF_API size_t aecf_fusion_grad_sums_bytes(const aecf_pool_desc* desc);
  *   peer_data[r]  : HOST array of W DEVICE pointers -- rank r's bucket as mapped in this process (CUDA IPC); all
  *                   buckets hold `count` elements padded to a multiple of 16 bytes
  *   peer_flags[r] : HOST array of W DEVICE pointers -- rank r's flag block, aecf_peer_flag_bytes() bytes, zeroed once
- * The caller maps the buffers (aecf_b200.dp.PeerAllReduce does it with torch's CUDA IPC) and must have enabled peer
+ * The caller maps the buffers (aecf_peer_export / aecf_peer_import below; aecf_b200.dp does it that way) and must have enabled peer
  * access (aecf_peer_enable_access).  Every rank must make the same sequence of calls.  Graph-capturable: the call
  * epoch lives in the flag block and is advanced by the kernel. */
 typedef struct aecf_peer_desc {
