@@ -42,6 +42,7 @@ int sm_count(int device) {
 }
 
 constexpr int POOL_BWD_MAX_BLOCKS = 2048;
+constexpr long long POOL_BWD_CHUNK = 16;     // samples per CTA of the pool backward (0: persistent grid-stride schedule)
 
 // Sum the per-block partials: d_q[D] (scaled) and d_bias_kv[2D] = [dbk | dbv].  Block (32 columns x 32
 // lanes): lane y sums partials y, y+32, ... in order (all loads issued together), the 32 lane sums are
@@ -54,7 +55,7 @@ pool_bwd_finalize_kernel(const float* __restrict__ partials, int blocks, int D, 
     const int i = blockIdx.x * 32 + x;
     float s = 0.f;
     pdl_wait();
-    if (i < 3 * D) {
+    if (i < 3 * D && (i >= D || (q_shared && d_q))) {       // (the d_q third is not written when nobody wants it: folded)
 #pragma unroll 16
         for (int b = y; b < blocks; b += 32) s += partials[static_cast<size_t>(b) * 3 * D + i];
     }
@@ -282,15 +283,16 @@ size_t aecf_pool_bwd_workspace_bytes(const aecf_pool_desc* desc) {
 static int pool_bwd_impl(const aecf_pool_desc* desc, bool fold, const void* q, const float* scores, const void* kv,
                          const float* score_bias, const void* d_ctx, const float* d_pooled, const float* d_entropy,
                          void* d_kv, void* d_q, float* d_bias_kv, void* workspace, size_t workspace_bytes, void* stream,
-                         int* blocks_out = nullptr) {
+                         bool no_sums = false, float* rowsum = nullptr) {
     PoolPlan plan;
     int rc = make_plan(desc, &plan, fold);
     if (rc != AECF_OK) return rc;
-    if (!q || !kv || !d_ctx || !d_kv || (!fold && !d_q) || (fold && !scores) || !workspace) return AECF_ERR_INVALID;
+    if (!q || !kv || !d_ctx || !d_kv || (!fold && !d_q) || (fold && !scores) || (!workspace && !no_sums)) return AECF_ERR_INVALID;
     if (!aligned16(q) || !aligned16(kv) || !aligned16(d_ctx) || !aligned16(d_kv) || (d_q && !aligned16(d_q)) ||
         !aligned16(workspace))
         return AECF_ERR_ALIGNMENT;
-    if (workspace_bytes < aecf_pool_bwd_workspace_bytes(desc)) return AECF_ERR_WORKSPACE;
+    if (!no_sums && workspace_bytes < aecf_pool_bwd_workspace_bytes(desc)) return AECF_ERR_WORKSPACE;
+    if (no_sums && (!fold || plan.multi)) return AECF_ERR_INVALID;
     if (desc->row_index != nullptr && score_bias != nullptr) return AECF_ERR_UNSUPPORTED;
     if (desc->batch == 0) return AECF_OK;
     DeviceScope device_scope__(desc->device);
@@ -298,7 +300,8 @@ static int pool_bwd_impl(const aecf_pool_desc* desc, bool fold, const void* q, c
     PoolParams& p = plan.p;
     p.q = q; p.kv = kv; p.bias = score_bias; p.scores = scores;
     p.d_ctx = d_ctx; p.d_pooled = d_pooled; p.d_entropy = d_entropy; p.d_kv = d_kv; p.d_q = d_q;
-    p.partials = static_cast<float*>(workspace);
+    p.partials = no_sums ? nullptr : static_cast<float*>(workspace);
+    p.rowsum = no_sums ? rowsum : nullptr;
 
     int per_sm;
     if (plan.multi) per_sm = 1;                         // pool_bwd_multi_kernel: __launch_bounds__(256, 1)
@@ -312,6 +315,19 @@ static int pool_bwd_impl(const aecf_pool_desc* desc, bool fold, const void* q, c
     if (cap > POOL_BWD_MAX_BLOCKS) cap = POOL_BWD_MAX_BLOCKS;
     int grid = static_cast<int>(want < cap ? want : cap);
     if (grid < 1) grid = 1;
+    // Chunked schedule (pool_bwd.cuh), for the kernel without batch sums: CTA b owns `chunk` consecutive samples, several
+    // CTAs per resident slot, handed out by the block scheduler as CTAs retire.  AECF_POOL_BWD_CHUNK: samples per CTA
+    // (0: the persistent schedule) -- a measurement switch.
+    if (no_sums) {
+        static const long long env_chunk = [] { const char* e = getenv("AECF_POOL_BWD_CHUNK"); return e ? atoll(e) : -1LL; }();
+        long long chunk = env_chunk >= 0 ? env_chunk : POOL_BWD_CHUNK;
+        if (chunk > 0) {
+            chunk = (chunk + p.SPC - 1) / p.SPC * p.SPC;
+            while ((p.B + chunk - 1) / chunk > 0x7fffffffLL) chunk *= 2;
+            p.chunk = chunk;
+            grid = static_cast<int>((p.B + chunk - 1) / chunk);
+        }
+    }
 
     {
         TimedLaunch timed(static_cast<cudaStream_t>(stream));
@@ -332,10 +348,7 @@ static int pool_bwd_impl(const aecf_pool_desc* desc, bool fold, const void* q, c
                            : launch_pool_bwd<float, false>(plan.M, plan.J, p, grid, fold, stream);
     }
     if (rc != AECF_OK) return rc;
-    if (blocks_out != nullptr) {                        // the caller folds the per-CTA partials itself (grad_tail.cu)
-        *blocks_out = grid;
-        return AECF_OK;
-    }
+    if (no_sums) return AECF_OK;                        // the caller forms the batch sums itself (grad_tail.cu)
     const int n = 3 * p.D;
     TimedLaunch timed_finalize(static_cast<cudaStream_t>(stream), AECF_SITE_POOL_BWD_FINALIZE);
     AECF_CUDA_OK(launch_pdl(pool_bwd_finalize_kernel, dim3((n + 31) / 32), dim3(1024), 0, static_cast<cudaStream_t>(stream),
@@ -346,12 +359,13 @@ static int pool_bwd_impl(const aecf_pool_desc* desc, bool fold, const void* q, c
 }
 
 namespace aecf {
-// fusion.cu: the folded backward without the finalize launch; *blocks = CTAs that wrote [3 D] partials into `workspace`
-int pool_bwd_folded_partials(const aecf_pool_desc* desc, const void* q_proj, const float* scores, const void* v,
-                             const float* score_bias, const void* d_ctx, const float* d_pooled, const float* d_entropy,
-                             void* d_vs, void* workspace, size_t workspace_bytes, void* stream, int* blocks) {
+// fusion.cu: the folded backward without its batch sums (pool_bwd.cuh).  rowsum null: nothing is left for the tail to sum
+// (no dropout, every sample pooled); else the kernel leaves [s | sum_m ds] per sample and head there ([src_rows][2 HSP] fp32).
+int pool_bwd_folded_nosums(const aecf_pool_desc* desc, const void* q_proj, const float* scores, const void* v,
+                           const float* score_bias, const void* d_ctx, const float* d_pooled, const float* d_entropy,
+                           void* d_vs, float* rowsum, void* stream) {
     return pool_bwd_impl(desc, true, q_proj, scores, v, score_bias, d_ctx, d_pooled, d_entropy, d_vs, nullptr, nullptr,
-                         workspace, workspace_bytes, stream, blocks);
+                         nullptr, 0, stream, true, rowsum);
 }
 }  // namespace aecf
 

@@ -47,9 +47,9 @@ static const void* at(const void* p, long long elems, int es) {
 static void* at(void* p, long long elems, int es) { return p ? static_cast<char*>(p) + elems * es : nullptr; }
 
 // api.cu
-int pool_bwd_folded_partials(const aecf_pool_desc* desc, const void* q_proj, const float* scores, const void* v,
-                             const float* score_bias, const void* d_ctx, const float* d_pooled, const float* d_entropy,
-                             void* d_vs, void* workspace, size_t workspace_bytes, void* stream, int* blocks);
+int pool_bwd_folded_nosums(const aecf_pool_desc* desc, const void* q_proj, const float* scores, const void* v,
+                           const float* score_bias, const void* d_ctx, const float* d_pooled, const float* d_entropy,
+                           void* d_vs, float* rowsum, void* stream);
 
 struct Workspace {
     char* gemm; size_t gemm_bytes;
@@ -65,6 +65,7 @@ struct Workspace {
     char* gemm_g; size_t gemm_g_bytes;
     float* sums;
     char* tail; size_t tail_bytes;
+    float* rowsum; size_t rowsum_bytes;   // [samples][2 HSP] fp32: what the pool backward leaves for the tail's bias sums
     size_t total;
 };
 
@@ -124,8 +125,8 @@ static int carve(const aecf_pool_desc* d, const Geometry& g, void* base, Workspa
     w->d_bq = reinterpret_cast<float*>(b + off); off += align256(sizeof(float) * g.D);
     w->fold_g = reinterpret_cast<float*>(b + off);
     if (g.fold) off += align256(sizeof(float) * (g.D + g.HSP) * g.D);
-    w->gemm_o = w->gemm_g = w->tail = nullptr; w->sums = nullptr;
-    w->gemm_o_bytes = w->gemm_g_bytes = w->tail_bytes = 0;
+    w->gemm_o = w->gemm_g = w->tail = nullptr; w->sums = nullptr; w->rowsum = nullptr;
+    w->gemm_o_bytes = w->gemm_g_bytes = w->tail_bytes = w->rowsum_bytes = 0;
     if (g.fold) {
         const int dt = g.dt, D = g.D, KF = g.D + g.HSP;
         const aecf_gemm_desc o = gemm_desc(d->device, dt, dt, AECF_F32, dt, AECF_MN_MAJOR, AECF_MN_MAJOR, D, D, g.QR, D, D, D);
@@ -137,6 +138,8 @@ static int carve(const aecf_pool_desc* d, const Geometry& g, void* base, Workspa
         w->gemm_g = b + off; off += w->gemm_g_bytes;
         w->sums = reinterpret_cast<float*>(b + off); off += align256(sizeof(float) * tail_layout(D, g.HSP).total);
         w->tail = b + off; off += w->tail_bytes;
+        w->rowsum_bytes = align256(sizeof(float) * 2 * g.HSP * static_cast<size_t>(g.QR));
+        w->rowsum = reinterpret_cast<float*>(b + off); off += w->rowsum_bytes;
     }
     w->total = off;
     return AECF_OK;
@@ -144,7 +147,8 @@ static int carve(const aecf_pool_desc* d, const Geometry& g, void* base, Workspa
 
 // ---- the folded backward, whole (phase AECF_BWD_ALL): five launches on `s`, the gradient tail next to them ----
 //   s    : dWo partials -> d_ctx -> pool backward -(fork)-> [dWv ; R] partials -(fork 2)-> dX -(join)->
-//   side :                                          colsum(d_out), dWo fold   [dWv ; R] fold, partial folds -> [peer sum] -> finish
+//   side :                                          colsum(d_out), dWo fold,  [dWv ; R] fold, partial folds -> [peer sum] -> finish
+//                                                   bias sums over d_ctx
 // Each half of the tail runs next to a tensor-core product that leaves half of the HBM bandwidth unused.
 static int folded_backward(const aecf_pool_desc* desc, const Geometry& g, const aecf_fusion_tensors* t,
                            const aecf_fusion_grads* gr, const Workspace& w, cudaStream_t s) {
@@ -164,7 +168,7 @@ static int folded_backward(const aecf_pool_desc* desc, const Geometry& g, const 
     a.q_proj = static_cast<const float*>(t->q_proj); a.in_proj_weight = t->in_proj_weight; a.query = t->query;
     a.d_in_w = gr->d_in_proj_weight; a.d_in_b = gr->d_in_proj_bias; a.d_out_w = gr->d_out_proj_weight;
     a.d_out_b = gr->d_out_proj_bias; a.d_query = gr->d_query;
-    a.d_out = gr->d_out_proj_bias ? gr->d_out : nullptr; a.rows = g.QR;
+    a.d_out = (gr->d_out_proj_bias || gr->d_in_proj_bias) ? gr->d_out : nullptr; a.rows = g.QR;   // (the in-projection bias may need the sums too)
 
     if (gr->d_out_proj_weight) {                             // dWo = g^T ctx, left as split-K partials
         ScopedSite site(AECF_SITE_D_OUT_WEIGHT);
@@ -176,13 +180,22 @@ static int folded_backward(const aecf_pool_desc* desc, const Geometry& g, const 
         const aecf_gemm_desc d = gemm_desc(dev, dt, dt, dt, dt, AECF_K_MAJOR, AECF_MN_MAJOR, g.QR, D, D, D, D, D);
         AECF_TRY(aecf_gemm(&d, gr->d_out, t->out_proj_weight, nullptr, gr->d_ctx, w.gemm, w.gemm_bytes, s));
     }
-    if (desc->row_index != nullptr)                              // unlisted samples: zero rows of [dV | ds]
+    // The value and key thirds of the in-projection bias gradient (pool_bwd.cuh).  No dropout, every sample pooled: the
+    // softmax weights of a sample sum to one, so d_bias_v = sum_b d_ctx[b, :] = Wo^T colsum(d_out) and d_bias_k = 0 -- the tail
+    // forms them from the column sums of d_out and the pool backward carries no batch sums at all.  Otherwise the kernel
+    // leaves [s | sum_m ds] per sample and head and the tail walks d_ctx once more.
+    const bool bias_from_bo = desc->row_index == nullptr && !(desc->training && desc->dropout_p > 0.f);
+    float* rowsum = (gr->d_in_proj_bias && !bias_from_bo) ? w.rowsum : nullptr;
+    if (desc->row_index != nullptr) {                            // unlisted samples: zero rows of [dV | ds], no share in the bias sums
         AECF_CUDA_OK(cudaMemsetAsync(gr->d_kv, 0, static_cast<size_t>(g.rows) * KF * g.es, s));
+        if (rowsum) AECF_CUDA_OK(cudaMemsetAsync(rowsum, 0, w.rowsum_bytes, s));
+    }
     {
         ScopedSite site(AECF_SITE_POOL_BWD);
-        AECF_TRY(pool_bwd_folded_partials(desc, t->q_proj, t->scores, t->kv, t->score_bias, gr->d_ctx, gr->d_pooled,
-                                          gr->d_entropy, gr->d_kv, w.pool, w.pool_bytes, s, &a.pool_blocks));
-        a.pool_part = reinterpret_cast<const float*>(w.pool);
+        AECF_TRY(pool_bwd_folded_nosums(desc, t->q_proj, t->scores, t->kv, t->score_bias, gr->d_ctx, gr->d_pooled,
+                                        gr->d_entropy, gr->d_kv, rowsum, s));
+        if (rowsum) { a.rowsum = rowsum; a.d_ctx = gr->d_ctx; a.samples = g.QR; }
+        else if (gr->d_in_proj_bias) a.out_proj_weight = t->out_proj_weight;      // d_bias_v = Wo^T colsum(d_out)
     }
     // Each half of the tail is enqueued AFTER the product it runs next to: the product's persistent CTAs (one per SM, all
     // but 2 KB of its shared memory) are placed first and the tail's blocks fill in beside them -- the other way round a

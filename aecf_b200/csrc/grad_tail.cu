@@ -51,10 +51,26 @@ struct GatherParams {
     const float* g_part; int g_splits; long long g_stride;      // [dWv ; R] partials: g_splits slabs of (D + HSP) * D
     const float* o_part; int o_splits; long long o_stride;      // dWo partials: o_splits slabs of D * D
     const void* d_out; long long rows, ld;                      // [rows, D] in the parameter dtype: column sums -> bo
+    // the in-projection bias sums the pool backward no longer forms (pool_bwd.cuh): per sample and head it leaves
+    // [s = sum_m wd | sum_m ds] in rowsum [samples][2 HSP]; d_bias_v[d] = sum_b s[b, h(d)] d_ctx[b, d] and
+    // d_bias_k[d] = scale q[d] sum_b sum_m ds[b, m, h(d)] (analytically zero; kept as the arithmetic leaves it)
+    const float* rowsum; const void* d_ctx; long long samples;
+    const float* q_proj; float scale; int head_dim;
+    float* pool_part;                                           // [gridDim.x][3 D] scratch: per-block [ - | d_bias_v | d_bias_k ]
     float* sums; TailLayout lay;
     float* colsum_part;                                         // [gridDim.x][D] scratch
     int D, HSP;
 };
+
+#ifdef AECF_CUDA_EMU
+__device__ __forceinline__ float ldg_batch_f32(const float* p) { return *p; }
+#else
+__device__ __forceinline__ float ldg_batch_f32(const float* p) {
+    float r;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+#endif
 
 template <typename T>
 __global__ void __launch_bounds__(TAIL_THREADS, 1)
@@ -117,6 +133,68 @@ grad_gather_kernel(const GatherParams p) {
         }
     }
 
+    // (1b) the same walk over d_ctx, every row weighted per head: this block's share of d_bias_v and d_bias_k
+    if (p.rowsum != nullptr) {
+        int rl = 32;
+        while (rl > 1 && TAIL_THREADS / rl < NC) rl >>= 1;
+        const int ncp = TAIL_THREADS / rl;
+        const int lane_r = t % rl, cc = t / rl;
+        const long long per = (p.samples + gridDim.x - 1) / gridDim.x;
+        const long long r0 = per * blockIdx.x, r1 = min(p.samples, r0 + per);
+        const T* x = static_cast<const T*>(p.d_ctx);
+        const long long wld = 2LL * p.HSP;
+        for (int cb = 0; cb < NC; cb += ncp) {
+            const bool active = cb + cc < NC;
+            float acc[V], acc_k = 0.f;
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc[v] = 0.f;
+            if (active) {
+                const T* col = x + static_cast<long long>(cb + cc) * V;
+                const float* wcol = p.rowsum + ((cb + cc) * V) / p.head_dim;     // this chunk's head
+                long long r = r0 + lane_r;
+                auto batch = [&](auto tag) {
+                    constexpr int U = decltype(tag)::value;
+                    for (; r + static_cast<long long>(U - 1) * rl < r1; r += static_cast<long long>(U) * rl) {
+                        uint4 raw[U];
+                        float ws[U], wk[U];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            const long long rr = r + static_cast<long long>(u) * rl;
+                            raw[u] = ldg_batch(col + rr * D);
+                            ws[u] = ldg_batch_f32(wcol + rr * wld);
+                            wk[u] = ldg_batch_f32(wcol + rr * wld + p.HSP);
+                        }
+                        issue_barrier();
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            float f[V];
+                            Vec<T>::unpack(raw[u], f);
+#pragma unroll
+                            for (int v = 0; v < V; ++v) acc[v] = fmaf(ws[u], f[v], acc[v]);
+                            acc_k += wk[u];
+                        }
+                    }
+                };
+                batch(IntTag<8>{});
+                batch(IntTag<1>{});
+            }
+            for (int off = rl >> 1; off > 0; off >>= 1) {
+#pragma unroll
+                for (int v = 0; v < V; ++v) acc[v] += __shfl_xor_sync(FULL_MASK, acc[v], off);
+                acc_k += __shfl_xor_sync(FULL_MASK, acc_k, off);
+            }
+            if (active && lane_r == 0) {
+                const int c = (cb + cc) * V;
+                float* out = p.pool_part + static_cast<long long>(blockIdx.x) * 3 * D;
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    out[D + c + v] = acc[v];
+                    out[2 * D + c + v] = p.scale * __ldg(p.q_proj + c + v) * acc_k;
+                }
+            }
+        }
+    }
+
     // (2) split-K partials of the two weight-gradient products, splits in order, 16 bytes per thread, four splits in flight
     const long long gt = static_cast<long long>(blockIdx.x) * TAIL_THREADS + t;
     const long long nthreads = static_cast<long long>(gridDim.x) * TAIL_THREADS;
@@ -161,10 +239,10 @@ grad_gather_kernel(const GatherParams p) {
 
 // One warp per column: lane l sums rows l, l + 32, ... (every load issued before the first add), the 32 lane sums are
 // folded by xor shuffles.  Columns [0, D): the per-block column sums of d_out -> bo; columns [D, 4 D): the pool backward's
-// per-CTA partials [d_q | d_bias_v | d_bias_k] -> pool.
+// per-block in-projection bias sums [ - | d_bias_v | d_bias_k] of grad_gather -> pool.
 struct FoldParams {
     const float* colsum_part; int colsum_rows;                  // [colsum_rows][D], or null
-    const float* pool_part; int pool_rows;                      // [pool_rows][3 D], or null
+    const float* pool_part; int pool_rows;                      // [pool_rows][3 D], or null; the first third is not written (folded)
     float* sums; TailLayout lay;
     int D;
 };
@@ -175,6 +253,10 @@ grad_fold_kernel(const FoldParams p) {
     const int col = blockIdx.x * 16 + (threadIdx.x >> 5);
     pdl_wait();
     if (col >= 4 * p.D) return;
+    if (col >= p.D && col < 2 * p.D) {                          // (the d_q third of the unfolded layout: unused here)
+        if (lane == 0) p.sums[p.lay.pool + col - p.D] = 0.f;
+        return;
+    }
     const bool is_colsum = col < p.D;
     const float* part = is_colsum ? p.colsum_part : p.pool_part;
     if (part == nullptr) return;
@@ -204,6 +286,7 @@ struct FinishParams {
     const float* q_proj;            // [D] fp32: projected query (unscaled)
     const void* in_proj_weight;     // [3D, D]
     const void* query;              // [D]
+    const void* out_proj_weight;    // [D, D] or null; non-null: d_bias_v = Wo^T colsum(d_out), d_bias_k = 0 (pool_bwd.cuh)
     void* d_in_w;                   // [3D, D], nullable
     void* d_in_b;                   // [3D], nullable
     void* d_out_w;                  // [D, D], nullable
@@ -294,12 +377,36 @@ grad_finish_kernel(const FinishParams p) {
                               d_qp * q[u].w);
         }
     }
+    float bias_v = 0.f;
+    if (p.d_in_b != nullptr && p.out_proj_weight != nullptr) {  // column i of Wo against the column sums of d_out
+        const T* wo = static_cast<const T*>(p.out_proj_weight) + i;
+        const float* bo = p.sums + p.lay.bo;
+        constexpr int U = 16;
+        for (int j0 = lane; j0 < D; j0 += 32 * U) {
+            float w[U], b[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int j = j0 + 32 * u;
+                w[u] = j < D ? to_float<T>(wo[static_cast<long long>(j) * D]) : 0.f;
+                b[u] = j < D ? bo[j] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) bias_v = fmaf(w[u], b[u], bias_v);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) bias_v += __shfl_xor_sync(FULL_MASK, bias_v, off);
+    }
     if (lane == 0) {
         if (p.d_in_b != nullptr) {
             T* db = static_cast<T*>(p.d_in_b);
             db[i] = from_float<T>(d_qp);
-            db[D + i] = from_float<T>(p.sums[p.lay.pool + 2LL * D + i]);       // d_bias_k
-            db[2 * D + i] = from_float<T>(p.sums[p.lay.pool + D + i]);         // d_bias_v
+            if (p.out_proj_weight != nullptr) {
+                db[D + i] = from_float<T>(0.f);                                    // d_bias_k
+                db[2 * D + i] = from_float<T>(bias_v);                             // d_bias_v
+            } else {
+                db[D + i] = from_float<T>(p.sums[p.lay.pool + 2LL * D + i]);       // d_bias_k
+                db[2 * D + i] = from_float<T>(p.sums[p.lay.pool + D + i]);         // d_bias_v
+            }
         }
         if (p.d_out_b != nullptr) static_cast<T*>(p.d_out_b)[i] = from_float<T>(p.sums[p.lay.bo + i]);
     }
@@ -349,7 +456,8 @@ static size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255);
 
 size_t grad_tail_scratch_bytes(int D, int sms) {
     return align256(static_cast<size_t>(sms) * D * sizeof(float))           // per-block column sums of d_out
-         + align256(static_cast<size_t>((D + 7) / 8) * D * sizeof(float));  // per-block partials of d_query
+         + align256(static_cast<size_t>((D + 7) / 8) * D * sizeof(float))   // per-block partials of d_query
+         + align256(static_cast<size_t>(sms) * 3 * D * sizeof(float));      // per-block in-projection bias sums
 }
 
 // which = GATHER_EARLY: column sums of d_out (per block) and the dWo fold -- everything the backward knows after its first
@@ -365,14 +473,22 @@ int launch_grad_gather(const GradTailArgs& a, int which, cudaStream_t s) {
     p.sums = a.sums; p.lay = lay; p.D = a.D; p.HSP = a.HSP;
     p.colsum_part = static_cast<float*>(a.scratch);
     const bool early = which == GATHER_EARLY;
+    float* pool_part = reinterpret_cast<float*>(static_cast<char*>(a.scratch) + align256(static_cast<size_t>(a.sms) * a.D * sizeof(float))
+                                                + align256(static_cast<size_t>((a.D + 7) / 8) * a.D * sizeof(float)));
     if (early) {
         p.o_part = a.o.partial; p.o_splits = a.o.splits; p.o_stride = a.o.stride;
         p.d_out = a.d_out; p.rows = a.rows; p.ld = a.D;
+        if (a.rowsum != nullptr && a.d_ctx != nullptr) {
+            p.rowsum = a.rowsum; p.d_ctx = a.d_ctx; p.samples = a.samples; p.q_proj = a.q_proj;
+            p.head_dim = a.D / a.H;
+            p.scale = static_cast<float>(sqrt(1.0 / static_cast<double>(a.D / a.H)));
+            p.pool_part = pool_part;
+        }
     } else {
         p.g_part = a.g.partial; p.g_splits = a.g.splits; p.g_stride = a.g.stride;
     }
     TimedLaunch timed(s, AECF_SITE_GRAD_GATHER);
-    if (p.o_part != nullptr || p.d_out != nullptr || p.g_part != nullptr) {
+    if (p.o_part != nullptr || p.d_out != nullptr || p.g_part != nullptr || p.rowsum != nullptr) {
         if (a.dtype == AECF_BF16) AECF_CUDA_OK(launch_pdl(grad_gather_kernel<__nv_bfloat16>, dim3(blocks), dim3(TAIL_THREADS), 0, s, p));
         else AECF_CUDA_OK(launch_pdl(grad_gather_kernel<float>, dim3(blocks), dim3(TAIL_THREADS), 0, s, p));
         count_launch();
@@ -380,7 +496,7 @@ int launch_grad_gather(const GradTailArgs& a, int which, cudaStream_t s) {
     if (!early) {
         FoldParams f{};
         f.colsum_part = a.d_out ? p.colsum_part : nullptr; f.colsum_rows = blocks;
-        f.pool_part = a.pool_part; f.pool_rows = a.pool_blocks;
+        f.pool_part = (a.rowsum != nullptr && a.d_ctx != nullptr) ? pool_part : nullptr; f.pool_rows = blocks;
         f.sums = a.sums; f.lay = lay; f.D = a.D;
         AECF_CUDA_OK(launch_pdl(grad_fold_kernel, dim3((4 * a.D + 15) / 16), dim3(512), 0, s, f));
         count_launch();
@@ -392,7 +508,7 @@ int launch_grad_finish(const GradTailArgs& a, const float* sums, cudaStream_t s)
     if (a.D % 4 != 0) return AECF_ERR_UNSUPPORTED;
     FinishParams p{};
     p.sums = sums; p.lay = tail_layout(a.D, a.HSP);
-    p.q_proj = a.q_proj; p.in_proj_weight = a.in_proj_weight; p.query = a.query;
+    p.q_proj = a.q_proj; p.in_proj_weight = a.in_proj_weight; p.query = a.query; p.out_proj_weight = a.out_proj_weight;
     p.d_in_w = a.d_in_w; p.d_in_b = a.d_in_b; p.d_out_w = a.d_out_w; p.d_out_b = a.d_out_b; p.d_query = a.d_query;
     p.D = a.D; p.H = a.H; p.HSP = a.HSP;
     p.scale = static_cast<float>(sqrt(1.0 / static_cast<double>(a.D / a.H)));

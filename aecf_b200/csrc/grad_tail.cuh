@@ -22,7 +22,11 @@ struct GradTailArgs {
     int dtype, D, H, HSP, sms;
     GemmPartials g, o;                  // [dWv ; R] and dWo as left by gemm_partials (o.partial null: no dWo wanted)
     const void* d_out; long long rows;  // column sums of d_out -> d_out_proj_bias (null: not wanted)
-    const float* pool_part; int pool_blocks;
+    // the pool backward's per-sample [s | sum_m ds] ([samples][2 HSP] fp32) and d_ctx: d_bias_v = sum_b s[b, h] d_ctx[b, :],
+    // d_bias_k = scale q sum_b sum_m ds (null: in_proj_bias gradient not wanted)
+    const float* rowsum; const void* d_ctx; long long samples;
+    // ... or, when the weights of every sample sum to one: d_bias_v = Wo^T colsum(d_out), d_bias_k = 0 (null: not this way)
+    const void* out_proj_weight;
     float* sums;                        // S, tail_layout(D, HSP).total floats
     void* scratch;                      // grad_tail_scratch_bytes(D, sms)
     const float* q_proj; const void* in_proj_weight; const void* query;

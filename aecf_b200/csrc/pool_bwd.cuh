@@ -53,7 +53,17 @@ pool_bwd_kernel(const PoolParams p) {
     float4* acc_q = reinterpret_cast<float4*>(strip);                 // [J][Q4][32]
     float4* acc_bv = reinterpret_cast<float4*>(strip + Smem::ACC);    // [J][Q4][32]
     float* acc_sds = strip + 2 * Smem::ACC;                           // [J][32]
-    for (int i = lane; i < Smem::PER_WARP; i += 32) strip[i] = 0.f;
+    // Folded backward inside aecf_fusion_bwd (p.partials == null): no batch sums here at all.  Without cross-sample state a
+    // CTA costs nothing to start or to retire, which is what makes the chunked schedule below pay (r2 run 20: 86.3 us
+    // persistent, 80.3 us in chunks of 32; with a per-CTA fold of the strips the chunks LOSE 8 us).  The sums in question
+    // are the value and key thirds of the in-projection bias gradient:
+    //   d_bias_v[d] = sum_b s[b, h(d)] d_ctx[b, d],  s = sum_m wd       d_bias_k[d] = scale q[d] sum_b sum_m ds[b, m, h(d)]
+    // Without dropout s = sum_m softmax = 1 and sum_m ds = 0 identically, so d_bias_v = sum_b d_ctx[b, :] = Wo^T d_bias_o and
+    // d_bias_k = 0: the gradient tail forms them from the column sums of d_out it already has (grad_tail.cu), and nothing is
+    // left to do here (p.rowsum == null).  With dropout, or when only listed samples are pooled, the kernel leaves
+    // [s | sum_m ds] per sample and head in p.rowsum and the tail walks d_ctx once more.
+    const bool sums = p.partials != nullptr;
+    if (sums) for (int i = lane; i < Smem::PER_WARP; i += 32) strip[i] = 0.f;
     __syncwarp();
     pdl_wait();
     const RngKey rng = effective_rng(p.rng, p.rng_state);
@@ -64,10 +74,17 @@ pool_bwd_kernel(const PoolParams p) {
     float qs[J][V];
     if (!FOLD && p.q_shared) Core::load_query(p, 0, c0, qs);
 
-    const long long stride = static_cast<long long>(gridDim.x) * p.SPC;
-    for (long long base = static_cast<long long>(blockIdx.x) * p.SPC; base < p.B; base += stride) {
+    // Two schedules.  chunk == 0: persistent, CTAs stride over the batch.  chunk > 0: CTA b owns the `chunk` consecutive
+    // samples from b * chunk and the grid is as long as the batch needs -- the hardware's block scheduler hands the chunks
+    // out as CTAs retire, which evens out the SMs' unequal shares of the memory system (r2 runs 15-17: the bare memory
+    // skeleton of this kernel runs 81.7 us persistent and 77.5 / 75.9 / 74.3 us with 32 / 16 / 8 samples per CTA).
+    // Either way a CTA's partial sums cover a set of samples that depends on the launch geometry only: bit-reproducible.
+    const long long stride = p.chunk ? p.SPC : static_cast<long long>(gridDim.x) * p.SPC;
+    const long long first = p.chunk ? static_cast<long long>(blockIdx.x) * p.chunk : static_cast<long long>(blockIdx.x) * p.SPC;
+    const long long last = p.chunk ? min(p.B, first + p.chunk) : p.B;
+    for (long long base = first; base < last; base += stride) {
         const long long row_raw = base + warp / p.WPS;
-        const bool row_ok = row_raw < p.B;
+        const bool row_ok = row_raw < last;
         const long long row = row_ok ? row_raw : p.B - 1;
         if (!FOLD && !p.q_shared) Core::load_query(p, row, c0, qs);
         const long long src = source_row(p, row);          // where the row's sample lives in kv / scores / d_ctx / d_kv
@@ -131,7 +148,7 @@ pool_bwd_kernel(const PoolParams p) {
                 sum_wd += wd[m][j];
                 if (row_ok && valid(j)) stg_vec(dkv_row + Core::dkv_rel(p, m, VHALF, j), Vec<T>::pack(dv));
             }
-            if (row_ok) {
+            if (row_ok && sums) {
 #pragma unroll
                 for (int q4 = 0; q4 < Q4; ++q4) {
                     float4 a = acc_bv[(j * Q4 + q4) * 32 + lane];
@@ -188,7 +205,18 @@ pool_bwd_kernel(const PoolParams p) {
                 ds[m][j] = w[m][j] * (ds[m][j] - dot);
                 sum_ds += ds[m][j];
             }
-            if (row_ok && valid(j)) acc_sds[j * 32 + lane] += sum_ds;
+            if (row_ok && valid(j) && sums) acc_sds[j * 32 + lane] += sum_ds;
+            if (FOLD && p.rowsum != nullptr && row_ok) {     // the first lane of each head: [s | sum_m ds] of this sample
+                const int c = c0 + 32 * j;
+                if (c < p.NC && (c & (p.G - 1)) == 0) {
+                    float s_wd = 0.f;
+#pragma unroll
+                    for (int m = 0; m < M; ++m) s_wd += wd[m][j];
+                    float* rs = p.rowsum + static_cast<size_t>(src) * (2 * p.HSP) + (c >> p.logG);
+                    rs[0] = s_wd;
+                    rs[p.HSP] = sum_ds;
+                }
+            }
         }
 
         if constexpr (FOLD) {
@@ -265,11 +293,12 @@ pool_bwd_kernel(const PoolParams p) {
 
     // ---- fold the warps' strips in a fixed order into this CTA's partial [3][D] -----------------
     // partial[0] = d_q (shared query, unscaled)   partial[1] = d_bias_v   partial[2] = d_bias_k
+    if (!sums) return;
     __syncthreads();
     const int D = p.D;
     float* out = p.partials + static_cast<size_t>(blockIdx.x) * 3 * D;
     const float* strips = smem + POOL_WARPS * M;
-    for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) {
+    for (int i = threadIdx.x + (FOLD ? D : 0); i < 3 * D; i += blockDim.x) {     // folded: there is no d_q third
         const int which = i / D, d = i - which * D;
         const int c = d / V, v = d - c * V;
         const int sl = c / Core::CPW, cl = c - sl * Core::CPW;

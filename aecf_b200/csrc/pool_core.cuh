@@ -51,7 +51,9 @@ struct PoolParams {
     const float* d_entropy;
     void* d_kv;
     void* d_q;
-    float* partials;                        // [grid][3][D] fp32: dq | dbv | dbk
+    float* partials;                        // [grid][3][D] fp32: dq | dbv | dbk (folded key projection: the first third is not written)
+    float* rowsum;                          // backward, folded: [src_rows][2 HSP] fp32 per-sample sums [s | sum_m ds] (see pool_bwd.cuh), or null
+    long long chunk;                        // backward: samples per CTA (CTA b owns [b * chunk, (b + 1) * chunk)); 0: grid-stride
     // Row indirection (aecf_pool_desc::row_index): row i of this call -- its Philox row, its info outputs, d_pooled /
     // d_entropy -- is SAMPLE row_index[i] of the kv / scores / ctx / d_ctx / d_kv buffers (the reference's x-ray model pools
     // only the rows where both modalities are present, xrays/train_xrays_example.py:202-222).  Null: the identity.
