@@ -127,6 +127,11 @@ def test_sample_index_pools_the_listed_rows_in_place(dtype, fold):
     P.test_sample_index_pools_the_listed_rows_in_place(dtype, fold)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_in_projection_bias_gradient_both_ways(dtype):
+    P.test_in_projection_bias_gradient_both_ways(dtype)
+
+
 def test_full_size_test_body_on_a_small_batch():
     """The body of the B = 65 536 GPU test (tests/test_gpu_parity.py) on 192 rows, so that the test itself is tested."""
     P.test_full_size_bf16_folded_against_oracle(P.Case("small_d512_h8_m3", B=192, M=3, D=512, H=8, dropout=0.1, pooled_grad=True,

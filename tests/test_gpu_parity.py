@@ -704,6 +704,36 @@ def test_sample_index_pools_the_listed_rows_in_place(dtype, fold):
         assert_close(k, b[k].float().cpu(), a[k].float().cpu(), tol, atol=tol * scale)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_in_projection_bias_gradient_both_ways(dtype):
+    """The folded backward forms the value / key thirds of in_proj_bias.grad in one of two ways (csrc/pool_bwd.cuh): without
+    dropout from the column sums of d_out (the softmax weights of a sample sum to one: d_bias_v = Wo^T colsum(d_out),
+    d_bias_k = 0), otherwise from per-sample head sums and a walk over d_ctx.  sample_index=arange(B) forces the second way on
+    a case without dropout: both must agree with each other, and the plain run with the oracle (the parity tests above)."""
+    case = Case("bias_both_ways", B=200, M=3, D=128, H=8, pooled_grad=True, data_seed=77, offset=2)
+    inp = build_inputs(case)
+    g = inp["grad_out"].to(DEV, dtype)
+    grads = {}
+    for mode in ("column_sums", "per_sample_sums"):
+        pool, cm = make_pool(case, inp, dtype, True)
+        q = torch.nn.Parameter(inp["query0"].to(DEV, dtype))
+        x = inp["x"].to(DEV, dtype).requires_grad_(True)
+        aecf_b200.set_rng_state(PHILOX_SEED, case.offset)
+        kw = {} if mode == "column_sums" else {"sample_index": torch.arange(case.B, device=DEV)}
+        out, info = pool(q.expand(case.B, -1, -1), x, return_info=True, **kw)
+        ((out.float() * g.float()).sum() + (info["attention_weights"] * 0.3).sum()).backward()
+        aecf_b200.set_rng_state(None)
+        grads[mode] = pool.attention.in_proj_bias.grad.float().cpu()
+    a, b = grads["column_sums"], grads["per_sample_sums"]
+    D = case.D
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    scale = float(b.abs().max())
+    assert_close("query third", a[:D], b[:D], tol, atol=tol * scale)
+    assert_close("value third", a[2 * D:], b[2 * D:], tol, atol=tol * scale)
+    assert float(a[D:2 * D].abs().max()) == 0.0                    # analytically zero, and written as such
+    assert float(b[D:2 * D].abs().max()) <= tol * scale            # ... where the other way leaves rounding noise
+
+
 def test_unsupported_shapes_fail_loudly():
     pool = aecf_b200.MultimodalAttentionPool(64, num_heads=4, device=DEV)
     x = torch.randn(4, 3, 64, device=DEV)
