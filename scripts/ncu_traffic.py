@@ -1,6 +1,6 @@
 """profiles/ncu_traffic.json from an `ncu --page raw --csv` export of one step of the default workload:
 
-    python scripts/ncu_traffic.py gpurun_out/r2_14_prof_raw.csv "profiles/r2_14_ncu_all_kernels.txt" [key]
+    python scripts/ncu_traffic.py gpurun_out/r2_26_prof_raw.csv "profiles/r2_26_ncu_all_kernels.txt" [key]
 
 DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch of the two pool kernels; bench.py quotes them as
 `roofline.traffic` for the workload whose key matches (B, M, D, H, dtype, dropout[, fold])."""
