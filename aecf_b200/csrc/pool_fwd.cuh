@@ -207,7 +207,10 @@ pool_fwd_kernel(const PoolParams p) {
 // reduced, so every warp keeps one full sample (6 KB at M=3, D=512 bf16) in flight at all times and the
 // arithmetic never waits on HBM.  Head sums of up to 32 consecutive rows stay in lane registers (lane i
 // keeps row i); the masking stage then runs once per 32 rows with one row per lane.
-template <typename T, int M, int J, bool DROP, bool FOLD>
+// DENSE (folded only): every lane owns J valid chunks (D = 32 J chunks exactly) and a sample's M value rows are contiguous,
+// so chunk (m, j) sits at the compile-time offset (m J + j) * 512 and no access needs a validity test -- 50 of the generic
+// kernel's 493 instructions per sample were address arithmetic and tests of exactly that (ncu source page, r2 run 26).
+template <typename T, int M, int J, bool DROP, bool FOLD, bool DENSE = false>
 __global__ void __launch_bounds__((FOLD && J <= 2) ? 768 : 512, 1)
 pool_fwd_stream_kernel(const PoolParams p, const long long rows_per_warp) {
     using Core = PoolCore<T, M, J, DROP>;
@@ -245,8 +248,9 @@ pool_fwd_stream_kernel(const PoolParams p, const long long rows_per_warp) {
             for (int half = 0; half < HALVES; ++half)
 #pragma unroll
                 for (int j = 0; j < J; ++j)
-                    if (c0 + 32 * j < p.NC)
-                        cp_async16(&my[(stage * CH + (m * HALVES + half) * J + j) * 32 + lane], src + Core::kv_rel(p, m, half, j));
+                    if (DENSE || c0 + 32 * j < p.NC)
+                        cp_async16(&my[(stage * CH + (m * HALVES + half) * J + j) * 32 + lane],
+                                   src + (DENSE ? (m * J + j) * 512 : Core::kv_rel(p, m, half, j)));
         cp_async_commit();
     };
     if (row_begin < row_end) prefetch(row_begin, 0);
@@ -278,7 +282,7 @@ pool_fwd_stream_kernel(const PoolParams p, const long long rows_per_warp) {
         }
         cp_async_wait<1>();                             // this row's chunks have landed (own copies only)
         auto staged = [&](int m, int half, int j) -> uint4 {
-            return (c0 + 32 * j < p.NC) ? my[(stage * CH + (m * HALVES + half) * J + j) * 32 + lane] : make_uint4(0, 0, 0, 0);
+            return (DENSE || c0 + 32 * j < p.NC) ? my[(stage * CH + (m * HALVES + half) * J + j) * 32 + lane] : make_uint4(0, 0, 0, 0);
         };
 
         float w[M][J], wd[M][J];
@@ -303,7 +307,7 @@ pool_fwd_stream_kernel(const PoolParams p, const long long rows_per_warp) {
         char* ctx = static_cast<char*>(p.ctx) + static_cast<size_t>(row) * p.D * sizeof(T) + static_cast<size_t>(c0) * 16;
 #pragma unroll
         for (int j = 0; j < J; ++j)
-            if (c0 + 32 * j < p.NC) stg_vec(ctx + j * 512, Vec<T>::pack(acc[j]));
+            if (DENSE || c0 + 32 * j < p.NC) stg_vec(ctx + j * 512, Vec<T>::pack(acc[j]));
 
         float total[M];
         Core::head_sum_partial(p, c0, wd, total);       // WPS == 1: the warp holds every head
