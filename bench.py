@@ -708,6 +708,10 @@ def run_b200(args):
                                "gradient_tail": ("on a side stream next to the [dWv;R] and dX products" if os.environ.get("AECF_SIDE_STREAM", "1") != "0"
                                                  else "on the compute stream"),
                                "entropy_loss": "fused into the pool forward kernel" if os.environ.get("AECF_FUSED_LOSS", "1") != "0" else "stand-alone kernel",
+                               "pool_backward": ("no batch sums in the kernel (the tail forms the in-projection bias gradient from colsum(d_out)); "
+                                                 + ("persistent grid" if os.environ.get("AECF_POOL_BWD_CHUNK") == "0" else
+                                                    f"{os.environ.get('AECF_POOL_BWD_CHUNK', '16')} consecutive samples per CTA, handed out by the block scheduler"))
+                                                if args.folded and args.dropout == 0.0 else "see DESIGN.md section 4.1",
                                "kernels_note": "`kernels`, `roofline*` and `gemm_tensor_pipe` are per-kernel durations with the gradient tail "
                                                "serialised (each kernel on its own); `ms_per_step` / `value` is the overlapped, graph-replayed step"},
             "roofline": roof, "roofline_pool_fwd": hbm("pool_fwd", fwd_bytes),
